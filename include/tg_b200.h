@@ -1,0 +1,148 @@
+/*
+ * tg_b200.h -- C ABI of libtg_b200.so, the B200-native (sm_100a) batched polynomial trajectory optimiser.
+ *
+ * Drop-in boundary for the hot path of ctu-mrs/mrs_uav_trajectory_generation.  The
+ * reference has no FFI around this path: it is in-process C++ (static library + header templates, namespace
+ * eth_trajectory_generation) called from exactly one place, MrsTrajectoryGeneration::findTrajectory /
+ * optimize().  Each entry point below names the reference interface it replaces (file:line under the reference
+ * root).  INTEGRATION.md shows the C++ shim (include/eth_trajectory_generation_b200.hpp) with the reference's
+ * class names that forwards to these functions, and the ctypes binding used by the tests.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; caller owns every host buffer; the library owns device workspaces in tg_ctx;
+ *     no pointer is retained after a call returns.
+ *   - every function returns TG_OK (0) or a negative TG_ERR_* code; tg_last_error() gives the text.  Nothing throws
+ *     or aborts across the ABI (the reference's CHECK macros print and continue, eth/misc.h:6-38); per-problem
+ *     outcomes are reported in tg_result.
+ *   - a tg_ctx is bound to one CUDA device and one stream; calls on one ctx are serialised by the caller, several
+ *     ctxs (one per GPU / host thread) may run concurrently.  There is NO CPU fallback: creating a ctx fails
+ *     loudly without a CUDA device.
+ *   - arithmetic: IEEE binary64 everywhere (the reference is fp64 Eigen), compiled without FMA contraction.
+ *
+ * Ragged batch layout: problem p owns waypoints wp_off[p] .. wp_off[p+1]-1 (V_p = count, S_p = V_p - 1 segments).
+ *   waypoint: 4 doubles x, y, z, heading.   coefficients: per segment [4 dims][10], increasing powers
+ *   (eth/polynomial.h:35-37).   samples: 4 doubles x, y, z, heading as getTrajectoryReference emits them
+ *   (src/mrs_trajectory_generation.cpp:1578-1602).
+ */
+#ifndef TG_B200_H_
+#define TG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_OK 0
+#define TG_ERR_NO_DEVICE (-1)
+#define TG_ERR_CUDA (-2)
+#define TG_ERR_INVALID (-3)
+#define TG_ERR_NO_RESULT (-4)
+
+typedef struct tg_ctx tg_ctx;
+
+/* Parameters of one batch call.  Defaults (tg_default_params) are the reference's production constants
+ * (SURVEY.md section 5): config/private/trajectory_generation.yaml:4-11, config/public/trajectory_generation.yaml:11-36,
+ * src/mrs_trajectory_generation.cpp:884-896. */
+typedef struct tg_params {
+  int derivative_to_optimize;   /* 2 acceleration (default), 3 jerk, 4 snap  (node.cpp:904-919) */
+  int max_evals;                /* NLopt maxeval = max_iterations (10) */
+  double f_rel, x_rel;          /* 0.05, 0.1 (node.cpp:884-885) */
+  double limits[9];             /* v_h, v_v, a_h, a_v, j_h, j_v, v_heading, a_heading, j_heading (node.cpp:981-1038) */
+  double dt;                    /* sampling_dt 0.2 s */
+  int check_deviation;          /* check_trajectory_deviation/enabled */
+  double max_deviation;         /* 0.05 m */
+  int max_deviation_iters;      /* 6 */
+  int first_segment_checked;    /* max_deviation_first_segment_ (node.cpp:874-878) */
+  double max_len_factor, min_len_factor; /* 3.0, 0.33 (node.cpp:1178-1199) */
+  int run_time_alloc;           /* 1: full findTrajectory; 0: linear solve at the Euclidean times + sampling */
+} tg_params;
+
+/* Per-problem outcome of tg_optimize_batch. */
+typedef struct tg_result {
+  int status;          /* 0 ok, 1 optimiser code rejected (node.cpp:1138-1149), 2 too long, 3 too short (node.cpp:1178-1199), 4 sampling failed */
+  int success;         /* optimize() produced a trajectory */
+  int nlopt_code;      /* NLopt-style result code of the last findTrajectory (1,3,4,5 success codes, -1 generic failure) */
+  int n_evals;         /* objective evaluations of the last findTrajectory (OptimizationInfo::n_iterations) */
+  int rounds;          /* subdivision rounds executed (re-solves) */
+  int safe;            /* last validation verdict (validateTrajectorySpatial) */
+  int n_waypoints;     /* final vertex count */
+  int n_samples;       /* final sample count */
+  int n_scale_passes;  /* passes of scaleSegmentTimesToMeetConstraints in the last findTrajectory */
+  int overflow;        /* reserved (always 0: outputs are sized by the library) */
+  double max_dev;      /* last measured path deviation [m] */
+  double final_cost;   /* objective at the optimiser's last accepted point */
+  double baca_total;   /* sum of estimateSegmentTimesBaca (node.cpp:1048-1056) */
+  long long total_solves, total_root_calls, total_evals; /* reference-equivalent work over all rounds */
+} tg_result;
+
+/* Library / context ------------------------------------------------------------------------------------------------ */
+const char* tg_version(void);
+void tg_default_params(tg_params* p);
+/* Creates a context on CUDA device `device` (its own stream).  Fails with TG_ERR_NO_DEVICE when no GPU is usable. */
+int tg_ctx_create(int device, tg_ctx** out);
+void tg_ctx_destroy(tg_ctx* ctx);
+const char* tg_last_error(const tg_ctx* ctx);
+/* counters[8]: kernel launches, linear solves, objective evaluations, root finds, segment setups, samples, 0, 0
+ * (cumulative since the context was created). */
+int tg_get_counters(const tg_ctx* ctx, long long* counters);
+/* Milliseconds of device time (CUDA events on the context's stream) spent inside the last batch call. */
+double tg_last_device_ms(const tg_ctx* ctx);
+
+/* The hot path --------------------------------------------------------------------------------------------------------
+ * tg_optimize_batch = for every problem: MrsTrajectoryGeneration::optimize()'s numeric core
+ *   (src/mrs_trajectory_generation.cpp:620-851): findTrajectory (857-1209: vertex recipe 923-977, estimateSegmentTimes
+ *   + Baca 1045-1056, PolynomialOptimizationNonLinear<10>::setupFromVertices / addMaximumMagnitudeConstraint x12 /
+ *   optimize 1063-1083, acceptance 1138-1149, sampleWholeTrajectory 1169, length check 1178-1199), then
+ *   validateTrajectorySpatial (1401-1455) and midpoint subdivision + re-solve (729-785) up to max_deviation_iters.
+ * init14 (optional, [B][14]): {present, heading, vel[4], acc[4], jerk[4]} = the TrackerCommand fields read at
+ *   node.cpp:925-957; NULL means "no initial state" for every problem (dont_prepend_current_state).
+ * inputs_on_device != 0: wp, stop_at, init14 are device pointers on the context's device (wp_off stays on the host).
+ * results: [B] host.  totals[2]: total segments and total samples of the final trajectories (sizes for tg_fetch_outputs). */
+int tg_optimize_batch(tg_ctx* ctx, int B, const int* wp_off, const double* wp, const uint8_t* stop_at, const double* init14,
+                      const tg_params* params, int inputs_on_device, tg_result* results, long long* totals);
+/* Copies the outputs of the last tg_optimize_batch to host buffers (any pointer may be NULL):
+ *   seg_off[B+1] (segment offsets; vertex offset of problem p = seg_off[p] + p), wp[(totS+B)*4] final waypoint lists,
+ *   times[totS], coef[totS*40], smp_off[B+1], samples[totM*4].
+ * Replaces PolynomialOptimization::getSegments (lin.h:177), getTrajectory (nl.h:181) and getTrajectoryReference
+ * (node.cpp:1560-1606) for the whole batch. */
+int tg_fetch_outputs(tg_ctx* ctx, int* seg_off, double* wp, double* times, double* coef, int* smp_off, double* samples);
+
+/* Pieces of the path with the reference's class-level meaning --------------------------------------------------------
+ * tg_solve_linear_batch = PolynomialOptimization<10>::setupFromVertices + solveLinear + getSegments + computeCost
+ *   (lin_impl.h:61-106, 340-373, 263-282, 127-141) for B independent problems.
+ *   vtx_off[B+1] vertex offsets; vmask[totV] bit k set = derivative k fixed (Vertex::addConstraint, eth/vertex.cpp:134-137);
+ *   vval[totV][5][4] fixed values; times[totS]; r = derivative_to_optimize.  Outputs: coef[totS*40], cost[B]. */
+int tg_solve_linear_batch(tg_ctx* ctx, int B, const int* vtx_off, const uint8_t* vmask, const double* vval, const double* times, int r,
+                          double* coef, double* cost);
+/* tg_sample_batch = sampleWholeTrajectory (eth/trajectory_sampling.cpp:119-124, 49-104) for B trajectories given as
+ *   seg_off[B+1], coef, times.  Two-call convention: with samples == NULL only counts[B] is filled.
+ *   samples: [sum counts][4] (x y z heading); full (optional): [sum counts][19] = p4 v4 a4 j3 s3 yaw. */
+int tg_sample_batch(tg_ctx* ctx, int B, const int* seg_off, const double* coef, const double* times, double dt, int* counts,
+                    double* samples, double* full);
+/* tg_evaluate_batch = Trajectory::evaluate(t, derivative) (eth/trajectory.cpp:55-87) at n query times of ONE trajectory.
+ *   out: [n][4]; ok[n] = 0 where t is past the end (the reference logs and returns zeros). */
+int tg_evaluate_batch(tg_ctx* ctx, int S, const double* coef, const double* times, int n, const double* t, int derivative, double* out,
+                      uint8_t* ok);
+/* tg_extrema_batch = Trajectory::computeMaxDerivatives{Horizontal,Vertical,Heading}(.., seg) (eth/trajectory.cpp:422-565)
+ *   for totS segments: maxima[totS][9] = hor v,a,j ; ver v,a,j ; heading v,a,j. */
+int tg_extrema_batch(tg_ctx* ctx, int totS, const double* coef, const double* times, double* maxima);
+/* tg_scale_times_batch = Trajectory::scaleSegmentTimesToMeetConstraints (eth/trajectory.cpp:598-692), in place on
+ *   coef/times; passes[B], within[B]. */
+int tg_scale_times_batch(tg_ctx* ctx, int B, const int* seg_off, double* coef, double* times, const double* limits9, int* passes,
+                         uint8_t* within);
+/* tg_sweep_costs (BASELINE config 5) = updateSegmentTimes + solveLinear + computeCost for K candidate time vectors
+ *   of ONE problem (lin_impl.h:288-304, 340-373, 127-141).  cand[K][S] host (or device when cand_on_device).
+ *   costs (optional) [K] host; best_index / best_cost = argmin (first minimum). */
+int tg_sweep_costs(tg_ctx* ctx, int V, const uint8_t* vmask, const double* vval, int r, long long K, const double* cand,
+                   int cand_on_device, double* costs, long long* best_index, double* best_cost);
+
+/* Host-side evaluation of the deterministic math layer (include/tg_detmath.h), for tests:
+ *   fn 0 log, 1 exp, 2 sin, 3 cos, 4 atan2(x, y), 5 cbrt, 6 pow(x, (int)y). */
+double tg_detmath_eval(int fn, double x, double y);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* TG_B200_H_ */

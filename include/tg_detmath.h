@@ -1,0 +1,318 @@
+/*
+ * tg_detmath.h -- deterministic libm subset (host + device).
+ *
+ * Why this exists: the reference (ctu-mrs/mrs_uav_trajectory_generation) calls
+ * glibc's atan2/sin/cos (eth/vertex.cpp:512-520), exp/log
+ * (eth/rpoly/rpoly_ak1.cpp:156,227,246), cbrt (eth/trajectory.cpp:642) and
+ * pow(t, integer) (lin_impl.h:615).  The CUDA math library and glibc differ in
+ * the last ulp, and one ulp in a segment time decorrelates the rounding noise
+ * of the ill-conditioned reduced system (cond(Rpp) ~ 1e8), which
+ * would break the 1e-9 coefficient parity between the GPU path and the CPU
+ * oracle.  These routines use only IEEE-754 +,-,*,/ and explicit fma, so they
+ * return bit-identical results under `gcc -ffp-contract=off` and
+ * `nvcc -fmad=false`.  Accuracy (measured in tests/test_detmath.py against
+ * glibc): <= 2 ulp on the ranges the path uses.
+ *
+ * Coefficient tables come from tools/gen_detmath_coeffs.py (mpmath, 60 digits).
+ */
+#ifndef TG_DETMATH_H_
+#define TG_DETMATH_H_
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TG_HD __host__ __device__ __forceinline__
+#define TG_HD_NOINLINE __host__ __device__
+#else
+#define TG_HD inline
+#define TG_HD_NOINLINE
+#include <cmath>
+#include <cstring>
+#endif
+
+namespace tgdm {
+
+TG_HD int64_t dbits(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double_as_longlong(x);
+#else
+  int64_t b;
+  memcpy(&b, &x, 8);
+  return b;
+#endif
+}
+TG_HD double bitsd(int64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(b);
+#else
+  double x;
+  memcpy(&x, &b, 8);
+  return x;
+#endif
+}
+TG_HD double dabs(double x) { return bitsd(dbits(x) & 0x7fffffffffffffffLL); }
+TG_HD double dsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return __dsqrt_rn(x);
+#else
+  return std::sqrt(x);
+#endif
+}
+/* exact fused multiply-add (IEEE), identical on both sides */
+TG_HD double dfma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return std::fma(a, b, c);
+#endif
+}
+/* 2^e for -1022 <= e <= 1023 (exact) */
+TG_HD double pow2i(int e) { return bitsd((int64_t)(e + 1023) << 52); }
+/* x * 2^e with e split so that intermediate scale factors stay normal */
+TG_HD double scalb(double x, int e) {
+  if (e > 1000) { x = x * pow2i(1000); e -= 1000; if (e > 1000) { x = x * pow2i(1000); e -= 1000; } }
+  if (e < -1000) { x = x * pow2i(-1000); e += 1000; if (e < -1000) { x = x * pow2i(-1000); e += 1000; } }
+  return x * pow2i(e);
+}
+TG_HD bool disnan(double x) { return (dbits(x) & 0x7fffffffffffffffLL) > 0x7ff0000000000000LL; }
+TG_HD bool disinf(double x) { return (dbits(x) & 0x7fffffffffffffffLL) == 0x7ff0000000000000LL; }
+
+/* ---- log --------------------------------------------------------------- */
+TG_HD double dlog(double x) {
+  const double ln2_hi = 0x1.62e42fee00000p-1, ln2_lo = 0x1.a39ef35793c76p-33;
+  int64_t b = dbits(x);
+  int k = 0;
+  if (b < 0x0010000000000000LL) { /* zero, subnormal or negative */
+    if ((b & 0x7fffffffffffffffLL) == 0) return -bitsd(0x7ff0000000000000LL);
+    if (b < 0) return bitsd(0x7ff8000000000000LL);
+    x = x * 0x1p54;
+    b = dbits(x);
+    k = -54;
+  }
+  if (b >= 0x7ff0000000000000LL) return x; /* inf or nan */
+  k += (int)(b >> 52) - 1023;
+  int64_t m = b & 0x000fffffffffffffLL;
+  /* mantissa in [sqrt(1/2), sqrt(2)) */
+  if (m >= 0x6a09e667f3bcdLL) { k += 1; b = m | 0x3fe0000000000000LL; } else { b = m | 0x3ff0000000000000LL; }
+  const double f = bitsd(b) - 1.0;
+  const double s = f / (2.0 + f);
+  const double z = s * s;
+  double R = 0x1.0c135adcf3011p-3;
+  R = R * z + 0x1.0fbd140544b63p-3;
+  R = R * z + 0x1.3b1c43c68eb6dp-3;
+  R = R * z + 0x1.745cf8c09a9d4p-3;
+  R = R * z + 0x1.c71c7201fc0e6p-3;
+  R = R * z + 0x1.249249247670ap-2;
+  R = R * z + 0x1.9999999999a3ap-2;
+  R = R * z + 0x1.5555555555555p-1;
+  R = R * z;
+  const double hfsq = 0.5 * f * f;
+  const double dk = (double)k;
+  return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+}
+
+/* ---- exp --------------------------------------------------------------- */
+TG_HD double dexp(double x) {
+  const double ln2_hi = 0x1.62e42fee00000p-1, ln2_lo = 0x1.a39ef35793c76p-33, inv_ln2 = 0x1.71547652b82fep+0;
+  if (disnan(x)) return x;
+  if (x > 709.782712893384) return bitsd(0x7ff0000000000000LL);
+  if (x < -745.2) return 0.0;
+  const double t = x * inv_ln2;
+  const int k = (int)(t < 0 ? t - 0.5 : t + 0.5);
+  const double dk = (double)k;
+  const double hi = x - dk * ln2_hi;
+  const double lo = dk * ln2_lo;
+  const double r = hi - lo;
+  const double z = r * r;
+  double P = -0x1.1fdd0fa97e0efp-30;
+  P = P * z + 0x1.66a6198d419e5p-25;
+  P = P * z + -0x1.bbd777c80a4a2p-20;
+  P = P * z + 0x1.1566abbfe86bap-14;
+  P = P * z + -0x1.6c16c16c16be1p-9;
+  P = P * z + 0x1.5555555555555p-3;
+  const double c = r - z * P;
+  const double y = 1.0 - ((lo - (r * c) / (2.0 - c)) - hi);
+  return scalb(y, k);
+}
+
+/* ---- sin / cos ---------------------------------------------------------- */
+TG_HD double ksin(double r) {
+  const double z = r * r;
+  double S = -0x1.ab16f5caa198ap-41;
+  S = S * z + 0x1.61217d9252c03p-33;
+  S = S * z + -0x1.ae645410e937bp-26;
+  S = S * z + 0x1.71de3a545f836p-19;
+  S = S * z + -0x1.a01a01a01992fp-13;
+  S = S * z + 0x1.1111111111110p-7;
+  S = S * z + -0x1.5555555555555p-3;
+  return r + (r * z) * S;
+}
+TG_HD double kcos(double r) {
+  const double z = r * r;
+  double C = 0x1.ab779550c8d9bp-45;
+  C = C * z + -0x1.9394b8bd50ae1p-37;
+  C = C * z + 0x1.1eed8deac3dfep-29;
+  C = C * z + -0x1.27e4fb77125c5p-22;
+  C = C * z + 0x1.a01a01a019d06p-16;
+  C = C * z + -0x1.6c16c16c16c16p-10;
+  C = C * z + 0x1.5555555555555p-5;
+  const double hz = 0.5 * z;
+  const double w = 1.0 - hz;
+  return w + (((1.0 - w) - hz) + (z * z) * C);
+}
+/* Cody-Waite reduction; adequate for |x| < 2^20 * pi/2 (headings, inclinations) */
+TG_HD int rem_pio2(double x, double* r) {
+  const double two_over_pi = 0x1.45f306dc9c883p-1;
+  const double p1 = 0x1.921fb54400000p+0, p2 = 0x1.0b4611a600000p-34, p3 = 0x1.3198a2e037073p-69;
+  const double t = x * two_over_pi;
+  const int n = (int)(t < 0 ? t - 0.5 : t + 0.5);
+  const double dn = (double)n;
+  *r = ((x - dn * p1) - dn * p2) - dn * p3;
+  return n;
+}
+TG_HD double dsin(double x) {
+  if (disnan(x) || disinf(x)) return bitsd(0x7ff8000000000000LL);
+  if (dabs(x) <= 0x1.921fb54442d18p-1) return ksin(x);
+  double r;
+  const int n = rem_pio2(x, &r) & 3;
+  if (n == 0) return ksin(r);
+  if (n == 1) return kcos(r);
+  if (n == 2) return -ksin(r);
+  return -kcos(r);
+}
+TG_HD double dcos(double x) {
+  if (disnan(x) || disinf(x)) return bitsd(0x7ff8000000000000LL);
+  if (dabs(x) <= 0x1.921fb54442d18p-1) return kcos(x);
+  double r;
+  const int n = rem_pio2(x, &r) & 3;
+  if (n == 0) return kcos(r);
+  if (n == 1) return -ksin(r);
+  if (n == 2) return -kcos(r);
+  return ksin(r);
+}
+
+/* ---- atan / atan2 ------------------------------------------------------- */
+TG_HD double katan(double t) { /* |t| <= 7/16 */
+  const double z = t * t;
+  double T = 0x1.99b8c7f011ec9p-7;
+  T = T * z + -0x1.ddb926fc36723p-6;
+  T = T * z + 0x1.4ab4bf74b2a16p-5;
+  T = T * z + -0x1.8129cf6a2388dp-5;
+  T = T * z + 0x1.ae7f800dc449fp-5;
+  T = T * z + -0x1.e1d2299aa18b2p-5;
+  T = T * z + 0x1.11108fdc27707p-4;
+  T = T * z + -0x1.3b13aba41be33p-4;
+  T = T * z + 0x1.745d171ded7a6p-4;
+  T = T * z + -0x1.c71c71c672863p-4;
+  T = T * z + 0x1.24924924918cap-3;
+  T = T * z + -0x1.999999999998fp-3;
+  T = T * z + 0x1.5555555555555p-2;
+  return t - (t * z) * T;
+}
+TG_HD double datan(double x) {
+  if (disnan(x)) return x;
+  const bool neg = dbits(x) < 0;
+  const double a = dabs(x);
+  double res;
+  if (a < 0.4375) {
+    res = katan(a);
+  } else if (a < 0.6875) { /* atan(0.5) + atan((2a-1)/(2+a)) */
+    const double t = (2.0 * a - 1.0) / (2.0 + a);
+    res = 0x1.dac670561bb4fp-2 + (katan(t) + 0x1.a2b7f222f65e2p-56);
+  } else if (a < 1.1875) { /* atan(1) + atan((a-1)/(a+1)) */
+    const double t = (a - 1.0) / (a + 1.0);
+    res = 0x1.921fb54442d18p-1 + (katan(t) + 0x1.1a62633145c07p-55);
+  } else if (a < 2.4375) { /* atan(1.5) + atan((a-1.5)/(1+1.5a)) */
+    const double t = (a - 1.5) / (1.0 + 1.5 * a);
+    res = 0x1.f730bd281f69bp-1 + (katan(t) + 0x1.007887af0cbbdp-56);
+  } else if (a < 0x1p66) { /* pi/2 - atan(1/a) */
+    const double t = -1.0 / a;
+    res = 0x1.921fb54442d18p+0 + (katan(t) + 0x1.1a62633145c07p-54);
+  } else {
+    res = 0x1.921fb54442d18p+0;
+  }
+  return neg ? -res : res;
+}
+TG_HD double datan2(double y, double x) {
+  const double pi = 0x1.921fb54442d18p+1, pi_lo = 0x1.1a62633145c07p-53, pio2 = 0x1.921fb54442d18p+0;
+  if (disnan(x) || disnan(y)) return x + y;
+  const bool yneg = dbits(y) < 0, xneg = dbits(x) < 0;
+  if (y == 0.0) return xneg ? (yneg ? -pi : pi) : y;
+  if (x == 0.0) return yneg ? -pio2 : pio2;
+  if (disinf(x)) {
+    if (disinf(y)) {
+      const double q = xneg ? 3.0 * 0x1.921fb54442d18p-1 : 0x1.921fb54442d18p-1;
+      return yneg ? -q : q;
+    }
+    return xneg ? (yneg ? -pi : pi) : (yneg ? -0.0 : 0.0);
+  }
+  if (disinf(y)) return yneg ? -pio2 : pio2;
+  const double z = datan(dabs(y / x));
+  double r;
+  if (!xneg) r = z; else r = pi - (z - pi_lo);
+  return yneg ? -r : r;
+}
+
+/* ---- cbrt --------------------------------------------------------------- */
+TG_HD double dcbrt(double x) {
+  if (disnan(x) || disinf(x) || x == 0.0) return x;
+  const bool neg = dbits(x) < 0;
+  double a = dabs(x);
+  int e3 = 0;
+  int64_t b = dbits(a);
+  if (b < 0x0010000000000000LL) { a = a * 0x1p54; b = dbits(a); e3 = -18; }
+  int e = (int)(b >> 52) - 1023;
+  /* e = 3q + rem, rem in {0,1,2}; m in [1,8) */
+  int q = e / 3;
+  int rem = e - 3 * q;
+  if (rem < 0) { rem += 3; q -= 1; }
+  const double m = bitsd((b & 0x000fffffffffffffLL) | ((int64_t)(1023 + rem) << 52));
+  /* cubic seed on [1,8): ~7 bits */
+  double t = 0x1.aaa35d014643bp-10;
+  t = t * m + -0x1.16bdce74d65dbp-5;
+  t = t * m + 0x1.50ba80e69b747p-2;
+  t = t * m + 0x1.6ef7d7cd66d8cp-1;
+  /* Halley iterations: t <- t*(t^3 + 2m)/(2t^3 + m): 7 -> 21 -> 63 bits */
+  for (int i = 0; i < 3; ++i) {
+    const double t3 = t * t * t;
+    t = t * ((t3 + 2.0 * m) / (2.0 * t3 + m));
+  }
+  /* one Newton correction with the residual computed by exact fma products */
+  {
+    const double t2 = t * t;
+    const double t2e = dfma(t, t, -t2);        /* t*t = t2 + t2e */
+    const double t3 = t2 * t;
+    const double t3e = dfma(t2, t, -t3) + t2e * t; /* t^3 ~= t3 + t3e */
+    const double resid = (m - t3) - t3e;
+    t = t + resid / (3.0 * t2);
+  }
+  const double r = t * pow2i(q + e3);
+  return neg ? -r : r;
+}
+
+/* ---- integer power, correctly rounded in all but pathological cases ------ */
+/* pow(t, n) for n >= 1 via double-double products (error-free fma splitting):
+   restates glibc pow(t, exponent) of lin_impl.h:615 (glibc pow is < 1 ulp and
+   agrees with the correctly rounded value except in rare half-way cases). */
+struct dd { double hi, lo; };
+TG_HD dd dd_mul_d(dd a, double b) {
+  const double p = a.hi * b;
+  const double e = dfma(a.hi, b, -p) + a.lo * b;
+  dd r;
+  r.hi = p + e;
+  r.lo = e - (r.hi - p);
+  return r;
+}
+/* fills out[k] = t^(k+1), k = 0..nmax-1, each rounded from a double-double */
+TG_HD void powers(double t, int nmax, double* out) {
+  dd acc; acc.hi = t; acc.lo = 0.0;
+  out[0] = t;
+  for (int k = 1; k < nmax; ++k) {
+    acc = dd_mul_d(acc, t);
+    out[k] = acc.hi;
+  }
+}
+
+}  // namespace tgdm
+
+#endif  // TG_DETMATH_H_

@@ -1,0 +1,207 @@
+// tg_capi_impl.hpp -- the extern "C" functions of include/tg_b200.h, written once over a Backend type.
+// cuda_backend.cu defines TG_BACKEND = CudaBackend and includes this file (the product, libtg_b200.so);
+// tests/host_emu/emu.cpp defines TG_BACKEND = EmuBackend (test-only CPU emulation of the same code).
+#ifndef TG_CAPI_IMPL_HPP_
+#define TG_CAPI_IMPL_HPP_
+
+#include <exception>
+#include <string>
+
+#include "../../include/tg_b200.h"
+#include "tg_pipeline.hpp"
+
+struct tg_ctx {
+  TG_BACKEND be;
+  tg::Pipeline<TG_BACKEND> pipe;
+  std::string err;
+  std::vector<tg::Result> last;
+  int last_B = 0;
+  double last_ms = 0.0;
+  explicit tg_ctx(int device) : be(device), pipe(be) {}
+};
+
+static_assert(sizeof(tg_params) == sizeof(tg::Params), "tg_params / tg::Params layout mismatch");
+static_assert(sizeof(tg_result) == sizeof(tg::Result), "tg_result / tg::Result layout mismatch");
+
+namespace {
+template <class F>
+int tg_guard(tg_ctx* ctx, F&& f) {
+  if (!ctx) return TG_ERR_INVALID;
+  try {
+    ctx->err.clear();
+    return f();
+  } catch (const std::exception& e) {
+    ctx->err = e.what();
+    return TG_ERR_CUDA;
+  } catch (...) {
+    ctx->err = "unknown error";
+    return TG_ERR_CUDA;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+const char* tg_version(void) { return TG_VERSION_STRING; }
+
+void tg_default_params(tg_params* p) {
+  if (!p) return;
+  p->derivative_to_optimize = 2;
+  p->max_evals = 10;
+  p->f_rel = 0.05;
+  p->x_rel = 0.1;
+  const double lim[9] = {4.0, 2.0, 2.0, 1.0, 20.0, 20.0, 1.0, 2.0, 10.0};  // SURVEY.md 8(d) synthetic dynamics limits
+  for (int i = 0; i < 9; ++i) p->limits[i] = lim[i];
+  p->dt = 0.2;
+  p->check_deviation = 1;
+  p->max_deviation = 0.05;
+  p->max_deviation_iters = 6;
+  p->first_segment_checked = 1;
+  p->max_len_factor = 3.0;
+  p->min_len_factor = 0.33;
+  p->run_time_alloc = 1;
+}
+
+int tg_ctx_create(int device, tg_ctx** out) {
+  if (!out) return TG_ERR_INVALID;
+  *out = nullptr;
+  try {
+    *out = new tg_ctx(device);
+    return TG_OK;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "tg_ctx_create: %s\n", e.what());
+    return TG_ERR_NO_DEVICE;
+  }
+}
+
+void tg_ctx_destroy(tg_ctx* ctx) { delete ctx; }
+
+const char* tg_last_error(const tg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int tg_get_counters(const tg_ctx* ctx, long long* c) {
+  if (!ctx || !c) return TG_ERR_INVALID;
+  const tg::Counters& k = ctx->pipe.counters;
+  c[0] = k.launches; c[1] = k.solves; c[2] = k.evals; c[3] = k.root_finds; c[4] = k.segment_setups; c[5] = k.samples; c[6] = 0; c[7] = 0;
+  return TG_OK;
+}
+
+double tg_last_device_ms(const tg_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
+
+static bool tg_params_valid(const tg_params* P) {
+  if (!P) return false;
+  if (P->derivative_to_optimize < 2 || P->derivative_to_optimize > 4) return false;
+  if (P->max_evals < 1 || !(P->dt > 0.0) || P->max_deviation_iters < 0) return false;
+  for (int i = 0; i < 9; ++i)
+    if (!(P->limits[i] > 0.0)) return false;
+  return true;
+}
+
+int tg_optimize_batch(tg_ctx* ctx, int B, const int* wp_off, const double* wp, const uint8_t* stop_at, const double* init14,
+                      const tg_params* params, int inputs_on_device, tg_result* results, long long* totals) {
+  return tg_guard(ctx, [&]() -> int {
+    if (B < 0 || !wp_off || !wp || !results || !tg_params_valid(params)) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    tg::Params P;
+    std::memcpy(&P, params, sizeof(P));
+    ctx->last.assign(B, tg::Result());
+    ctx->last_B = B;
+    ctx->be.timer_start();
+    if (B > 0) ctx->pipe.optimize_batch(B, wp_off, wp, stop_at, init14, P, inputs_on_device != 0, ctx->last.data());
+    ctx->last_ms = ctx->be.timer_stop();
+    std::memcpy(results, ctx->last.data(), sizeof(tg_result) * (size_t)B);
+    if (totals) ctx->pipe.output_sizes(totals, ctx->last.data());
+    return TG_OK;
+  });
+}
+
+int tg_fetch_outputs(tg_ctx* ctx, int* seg_off, double* wp, double* times, double* coef, int* smp_off, double* samples) {
+  return tg_guard(ctx, [&]() -> int {
+    if (ctx->last_B <= 0) { ctx->err = "no batch result to fetch"; return TG_ERR_NO_RESULT; }
+    ctx->pipe.fetch_outputs(ctx->last.data(), seg_off, wp, times, coef, smp_off, samples);
+    return TG_OK;
+  });
+}
+
+int tg_solve_linear_batch(tg_ctx* ctx, int B, const int* vtx_off, const uint8_t* vmask, const double* vval, const double* times, int r,
+                          double* coef, double* cost) {
+  return tg_guard(ctx, [&]() -> int {
+    if (B < 1 || !vtx_off || !vmask || !vval || !times || r < 2 || r > 4) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    ctx->be.timer_start();
+    const bool ok = ctx->pipe.linear_batch(B, vtx_off, vmask, vval, times, r, coef, cost);
+    ctx->last_ms = ctx->be.timer_stop();
+    if (!ok) { ctx->err = "every problem needs at least two vertices"; return TG_ERR_INVALID; }
+    return TG_OK;
+  });
+}
+
+int tg_sample_batch(tg_ctx* ctx, int B, const int* seg_off, const double* coef, const double* times, double dt, int* counts,
+                    double* samples, double* full) {
+  return tg_guard(ctx, [&]() -> int {
+    if (B < 1 || !seg_off || !coef || !times || !counts || !(dt > 0.0)) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    ctx->be.timer_start();
+    ctx->pipe.sample_batch(B, seg_off, coef, times, dt, counts, samples, full);
+    ctx->last_ms = ctx->be.timer_stop();
+    return TG_OK;
+  });
+}
+
+int tg_evaluate_batch(tg_ctx* ctx, int S, const double* coef, const double* times, int n, const double* t, int derivative, double* out,
+                      uint8_t* ok) {
+  return tg_guard(ctx, [&]() -> int {
+    if (S < 1 || n < 0 || !coef || !times || !t || !out || derivative < 0) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    if (n > 0) ctx->pipe.evaluate_batch(S, coef, times, n, t, derivative, out, ok);
+    return TG_OK;
+  });
+}
+
+int tg_extrema_batch(tg_ctx* ctx, int totS, const double* coef, const double* times, double* maxima) {
+  return tg_guard(ctx, [&]() -> int {
+    if (totS < 1 || !coef || !times || !maxima) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    ctx->be.timer_start();
+    ctx->pipe.extrema_batch(totS, coef, times, maxima);
+    ctx->last_ms = ctx->be.timer_stop();
+    return TG_OK;
+  });
+}
+
+int tg_scale_times_batch(tg_ctx* ctx, int B, const int* seg_off, double* coef, double* times, const double* limits9, int* passes,
+                         uint8_t* within) {
+  return tg_guard(ctx, [&]() -> int {
+    if (B < 1 || !seg_off || !coef || !times || !limits9) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    ctx->pipe.scale_times_batch(B, seg_off, coef, times, limits9, passes, within);
+    return TG_OK;
+  });
+}
+
+int tg_sweep_costs(tg_ctx* ctx, int V, const uint8_t* vmask, const double* vval, int r, long long K, const double* cand, int cand_on_device,
+                   double* costs, long long* best_index, double* best_cost) {
+  return tg_guard(ctx, [&]() -> int {
+    if (V < 2 || !vmask || !vval || !cand || K < 1 || r < 2 || r > 4) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    ctx->be.timer_start();
+    const bool ok = ctx->pipe.sweep_costs(V, vmask, vval, r, K, cand, cand_on_device != 0, costs, best_index, best_cost);
+    ctx->last_ms = ctx->be.timer_stop();
+    return ok ? TG_OK : TG_ERR_INVALID;
+  });
+}
+
+double tg_detmath_eval(int fn, double x, double y) {
+  switch (fn) {
+    case 0: return tgdm::dlog(x);
+    case 1: return tgdm::dexp(x);
+    case 2: return tgdm::dsin(x);
+    case 3: return tgdm::dcos(x);
+    case 4: return tgdm::datan2(x, y);
+    case 5: return tgdm::dcbrt(x);
+    case 6: {
+      double pw[64];
+      const int e = (int)y;
+      if (e < 1 || e > 64) return 0.0;
+      tgdm::powers(x, e, pw);
+      return pw[e - 1];
+    }
+  }
+  return 0.0;
+}
+
+}  // extern "C"
+
+#endif  // TG_CAPI_IMPL_HPP_

@@ -1,0 +1,578 @@
+// tg_kernels.cuh -- the per-thread / per-warp work items of every kernel, as TG_HD functors over raw device
+// pointers.  cuda_backend.cu wraps them in __global__ kernels; tests/host_emu runs the same functors in loops.
+//
+// Ragged batch layout (all arrays in HBM, struct-of-arrays, problem p owns contiguous slices):
+//   seg_off[B+1]             first segment of problem p; vertices start at seg_off[p] + p (V = S + 1)
+//   wp[totV][4], stop[totV]  waypoints x y z heading, stop_at flags
+//   vmask[totV], vval[totV][5][4], vfree[totV + B]   vertex constraints and free-unknown index (V+1 per problem)
+//   times/xeval/x/g/d[totS], hist_s/hist_y[11][totS], coef[totS][4][10], recs[totS*{1,3}][216], maxima[totS][9]
+//   costs[totV]              cost of solve instance (p, n): n = 0 base, n >= 1 perturbed segment n-1
+#ifndef TG_KERNELS_CUH_
+#define TG_KERNELS_CUH_
+
+#include "tg_common.cuh"
+#include "tg_lbfgs.cuh"
+#include "tg_node.cuh"
+#include "tg_poly.cuh"
+#include "tg_segment.cuh"
+#include "tg_solve.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define TG_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#define TG_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#elif defined(__CUDACC__)
+// host pass of nvcc over TG_HD code: never executed (the library has no CPU path)
+#define TG_ATOMIC_MAX(p, v) ((void)0)
+#define TG_ATOMIC_ADD(p, v) ((void)0)
+#else
+// tests/host_emu only (g++): the emulator runs work items on several host threads
+static inline void tg_host_atomic_max(int* p, int v) {
+  int cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (cur < v && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+  }
+}
+#define TG_ATOMIC_MAX(p, v) tg_host_atomic_max((p), (v))
+#define TG_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
+#endif
+
+namespace tg {
+
+enum FindStatus { kFindOk = 0, kFindNloptRejected = 1, kFindTooLong = 2, kFindTooShort = 3, kFindSampleFail = 4 };
+
+// per-problem record of one findTrajectory pass (device side)
+struct ProbState {
+  int status;          // FindStatus
+  int nlopt_code;
+  int n_evals;
+  int n_scale_passes;
+  int scale_done;
+  int n_samples;
+  int sample_cap;
+  int safe;
+  int next_V;          // vertex count after subdivision (0: no re-solve needed)
+  int pad;
+  double final_cost;   // cost reported by the optimiser (f at the last accepted point)
+  double cost;         // cost of the final linear solve
+  double baca_total;
+  double max_dev;
+};
+
+struct BatchPtrs {
+  int B, totS, totV, r;
+  const int* seg_off;
+  const int* prob_of_vtx;
+  const int* prob_of_seg;
+  const double* wp;
+  const uint8_t* stop;
+  const double* init14;  // [B][14] or null
+  uint8_t* vmask;
+  double* vval;
+  int* vfree;
+  int* np;
+  int* hbw;
+  int* stats;            // [0] = max solve workspace doubles, [1] = problems still to scale, [2] = scratch
+  double *times, *baca, *xeval, *x, *g, *d, *hist_s, *hist_y;
+  LbfgsScalars* lb;
+  double* recs;
+  double* costs;
+  double* coef;
+  double* maxima;
+  ProbState* ps;
+};
+
+TG_HD int vtx_off(const BatchPtrs& b, int p) { return b.seg_off[p] + p; }
+
+// ---- 1. vertex recipe + unknown indexing: one thread per problem ----------------------------------------------
+struct PrepareFn {
+  BatchPtrs b;
+  int from_waypoints;  // 1: node recipe from wp/stop/init ; 0: masks/values supplied by the caller
+  TG_HD void operator()(size_t pi) const {
+    const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0, V = S + 1, v0 = s0 + p;
+    int hbw = 0, np;
+    if (from_waypoints)
+      np = build_vertices(V, b.wp + 4 * (size_t)v0, b.stop ? b.stop + v0 : nullptr, b.init14 ? b.init14 + 14 * (size_t)p : nullptr, b.r,
+                          b.vmask + v0, b.vval + (size_t)v0 * TG_HALF * TG_D, b.vfree + v0 + p, &hbw);
+    else
+      np = index_vertices(V, b.vmask + v0, b.vfree + v0 + p, &hbw);
+    b.np[p] = np;
+    b.hbw[p] = hbw;
+    TG_ATOMIC_MAX(&b.stats[0], solve_ws_doubles(S, np, hbw));
+    ProbState& ps = b.ps[p];
+    ps.status = kFindOk;
+    ps.nlopt_code = 1;
+    ps.n_evals = 0;
+    ps.n_scale_passes = 0;
+    ps.scale_done = 0;
+    ps.n_samples = 0;
+    ps.sample_cap = 0;
+    ps.safe = 0;
+    ps.next_V = 0;
+    ps.final_cost = 0.0;
+    ps.cost = 0.0;
+    ps.baca_total = 0.0;
+    ps.max_dev = 0.0;
+  }
+};
+
+// ---- 2. initial segment times: one thread per segment, then one per problem for the Baca total ------------------
+struct TimesFn {
+  BatchPtrs b;
+  double L[9];
+  TG_HD void operator()(size_t gs) const {
+    const int p = b.prob_of_seg[gs];
+    const int s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0, i = (int)gs - s0, v0 = s0 + p;
+    const double* vpos = b.vval + (size_t)v0 * TG_HALF * TG_D;
+    const int stride = TG_HALF * TG_D;
+    b.times[gs] = segment_time_euclidean(vpos + (size_t)i * stride, vpos + (size_t)(i + 1) * stride, L);
+    b.baca[gs] = segment_time_baca(vpos, stride, i, S + 1, L);
+  }
+};
+struct BacaTotalFn {
+  BatchPtrs b;
+  TG_HD void operator()(size_t pi) const {
+    const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
+    double tot = 0.0;
+    for (int i = 0; i < S; ++i) tot = tot + b.baca[s0 + i];  // node.cpp:1053-1056
+    b.ps[p].baca_total = tot;
+  }
+};
+
+// ---- 3. per-segment records ------------------------------------------------------------------------------------------
+// base: one record per segment at times[]; Mellinger: three per segment at xeval, xeval+0.1, max(lb, xeval-corr)
+struct SetupBaseFn {
+  BatchPtrs b;
+  const double* T;
+  TG_HD void operator()(size_t gs) const { setup_segment_record(T[gs], b.r, b.recs + gs * TG_REC_SIZE); }
+};
+struct SetupMellingerFn {
+  BatchPtrs b;
+  TG_HD void operator()(size_t item) const {
+    const size_t gs = item / 3;
+    const int which = (int)(item - gs * 3);
+    const int p = b.prob_of_seg[gs];
+    if (b.lb[p].done) return;
+    const int S = b.seg_off[p + 1] - b.seg_off[p];
+    if (S == 1 && which != 0) return;
+    double T = b.xeval[gs];
+    if (which == 1) {
+      T = T + 0.1;
+      T = dmax(kTimeLowerBound, T);
+    } else if (which == 2) {
+      const double corr = 0.1 / ((double)S - 1.0);  // nl_impl.h:288
+      T = T - corr;
+      T = dmax(kTimeLowerBound, T);
+    }
+    setup_segment_record(T, b.r, b.recs + item * TG_REC_SIZE);
+  }
+};
+
+// ---- 4. warp solves ----------------------------------------------------------------------------------------------------
+struct SolveProblemDesc {
+  BatchPtrs b;
+  int mellinger;  // 1: instance = vertex index (problem, variant); 0: instance = problem, base times, rec_stride 1
+  double* dp_out; // optional [sum np][4]-> per problem offset by 4*vfree base (only base mode), may be null
+  const int* dp_off;
+  TG_HD bool instance(size_t inst, SolveInst& I) const {
+    int p, n;
+    if (mellinger) {
+      p = b.prob_of_vtx[inst];
+      n = (int)inst - vtx_off(b, p);
+      if (b.lb[p].done) return false;
+    } else {
+      p = (int)inst;
+      n = 0;
+    }
+    const int s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0, v0 = s0 + p;
+    if (mellinger && S == 1 && n > 0) return false;
+    I.S = S;
+    I.np = b.np[p];
+    I.hbw = b.hbw[p];
+    I.variant = n;
+    I.rec_stride = mellinger ? 3 : 1;
+    I.r = b.r;
+    I.vmask = b.vmask + v0;
+    I.vfree = b.vfree + v0 + p;
+    I.vval = b.vval + (size_t)v0 * TG_HALF * TG_D;
+    I.recs = b.recs + (size_t)s0 * I.rec_stride * TG_REC_SIZE;
+    I.coef_out = (n == 0) ? b.coef + (size_t)s0 * TG_D * TG_N : nullptr;
+    I.cost_out = mellinger ? b.costs + v0 + n : &b.ps[p].cost;
+    I.dp_out = (dp_out && !mellinger) ? dp_out + (size_t)TG_D * dp_off[p] : nullptr;
+    return true;
+  }
+};
+// time-vector sweep (BASELINE config 5): K candidates for ONE problem, records laid out [candidate][segment]
+struct SolveSweepDesc {
+  BatchPtrs b;  // a batch holding the single problem
+  const double* recs;
+  double* costs;
+  TG_HD bool instance(size_t k, SolveInst& I) const {
+    const int S = b.seg_off[1] - b.seg_off[0];
+    I.S = S;
+    I.np = b.np[0];
+    I.hbw = b.hbw[0];
+    I.variant = 0;
+    I.rec_stride = 1;
+    I.r = b.r;
+    I.vmask = b.vmask;
+    I.vfree = b.vfree;
+    I.vval = b.vval;
+    I.recs = recs + k * (size_t)S * TG_REC_SIZE;
+    I.coef_out = nullptr;
+    I.cost_out = costs + k;
+    I.dp_out = nullptr;
+    return true;
+  }
+};
+struct SetupSweepFn {
+  int S, r;
+  const double* cand;  // [K][S]
+  double* recs;
+  TG_HD void operator()(size_t item) const { setup_segment_record(cand[item], r, recs + item * TG_REC_SIZE); }
+};
+
+// ---- 5. L-BFGS state machine: one thread per problem -----------------------------------------------------------------------
+TG_HD LbfgsVectors lbfgs_vectors(const BatchPtrs& b, int p) {
+  LbfgsVectors v;
+  const int s0 = b.seg_off[p];
+  v.x = b.x + s0;
+  v.g = b.g + s0;
+  v.d = b.d + s0;
+  v.xeval = b.xeval + s0;
+  v.hist_s = b.hist_s + s0;
+  v.hist_y = b.hist_y + s0;
+  v.hstride = (size_t)b.totS;
+  return v;
+}
+struct LbfgsBeginFn {
+  BatchPtrs b;
+  TG_HD void operator()(size_t pi) const {
+    const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
+    lbfgs_begin(S, b.lb[p], lbfgs_vectors(b, p), b.times + s0);
+  }
+};
+struct LbfgsAdvanceFn {
+  BatchPtrs b;
+  int max_evals;
+  double f_rel, x_rel;
+  TG_HD void operator()(size_t pi) const {
+    const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
+    LbfgsScalars& st = b.lb[p];
+    if (st.done) return;
+    lbfgs_advance(S, st, lbfgs_vectors(b, p), b.costs + vtx_off(b, p), max_evals, f_rel, x_rel, -1.0, -1.0);
+  }
+};
+// after the loop: times <- last evaluated point (what poly_opt_ holds when nlopt returns, nl_impl.h:210-215)
+struct LbfgsFinishFn {
+  BatchPtrs b;
+  TG_HD void operator()(size_t pi) const {
+    const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
+    for (int i = 0; i < S; ++i) b.times[s0 + i] = b.xeval[s0 + i];
+    ProbState& ps = b.ps[p];
+    ps.nlopt_code = b.lb[p].code;
+    ps.n_evals = b.lb[p].n_evals;
+    ps.final_cost = b.lb[p].f;
+    const int code = ps.nlopt_code;
+    if (!((code >= 1 && code != 6) || code == -1)) ps.status = kFindNloptRejected;  // node.cpp:1138-1149
+  }
+};
+
+// ---- 6. extrema + time scaling ------------------------------------------------------------------------------------------------
+struct ExtremaFn {  // one thread per (segment, quantity); quantity-major so that a warp shares one polynomial degree
+  BatchPtrs b;
+  int* shift_count;  // optional counter of fixed-shift stages (flop accounting)
+  TG_HD void operator()(size_t item) const {
+    const size_t q = item / (size_t)b.totS, gs = item - q * (size_t)b.totS;
+    const int p = b.prob_of_seg[gs];
+    if (b.ps[p].scale_done) return;
+    int shifts = 0;
+    b.maxima[gs * 9 + q] = segment_max_magnitude(b.coef + gs * TG_D * TG_N, b.times[gs], (int)q, &shifts);
+    if (shift_count) TG_ATOMIC_ADD(shift_count, shifts);
+  }
+};
+struct ScaleFn {  // one thread per segment (eth/trajectory.cpp:610-658)
+  BatchPtrs b;
+  double L[9];
+  TG_HD void operator()(size_t gs) const {
+    const int p = b.prob_of_seg[gs];
+    if (b.ps[p].scale_done) return;
+    const double s = violation_scaling(b.maxima + gs * 9, L);
+    scale_segment(b.coef + gs * TG_D * TG_N, b.times + gs, s);
+  }
+};
+struct ScaleCheckFn {  // one thread per problem: the global re-check (eth/trajectory.cpp:660-689)
+  BatchPtrs b;
+  double L[9];
+  TG_HD void operator()(size_t pi) const {
+    const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
+    ProbState& ps = b.ps[p];
+    if (ps.scale_done) return;
+    ps.n_scale_passes += 1;
+    double g[9];
+    for (int q = 0; q < 9; ++q) g[q] = TG_DBL_LOWEST;
+    for (int i = 0; i < S; ++i)
+      for (int q = 0; q < 9; ++q) {
+        const double m = b.maxima[(size_t)(s0 + i) * 9 + q];
+        if (m > g[q]) g[q] = m;
+      }
+    if (violation_within(g, L) || ps.n_scale_passes >= 20) ps.scale_done = 1;
+    else TG_ATOMIC_ADD(&b.stats[1], 1);
+  }
+};
+
+// ---- 7. sampling ----------------------------------------------------------------------------------------------------------------
+struct SampleCapFn {
+  BatchPtrs b;
+  double dt;
+  int* cap;  // [B]
+  TG_HD void operator()(size_t pi) const {
+    const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
+    cap[p] = (b.ps[p].status == kFindOk) ? sample_cap(S, b.times + s0, dt) : 0;
+  }
+};
+struct SampleWalkFn {
+  BatchPtrs b;
+  double dt;
+  const int* smp_off;  // [B+1] exclusive scan of cap
+  int* seg_idx;
+  double* t_in;
+  TG_HD void operator()(size_t pi) const {
+    const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
+    ProbState& ps = b.ps[p];
+    const int cap = smp_off[p + 1] - smp_off[p];
+    ps.sample_cap = cap;
+    if (ps.status != kFindOk) { ps.n_samples = 0; return; }
+    const int m = sample_walk(S, b.times + s0, dt, cap, seg_idx + smp_off[p], t_in + smp_off[p]);
+    ps.n_samples = m;
+    if (m > cap) { ps.n_samples = cap; ps.status = kFindSampleFail; }
+  }
+};
+struct SampleEvalFn {  // one thread per sample slot
+  BatchPtrs b;
+  const int* smp_off;
+  const int* smp_prob;  // slot -> problem
+  const int* seg_idx;
+  const double* t_in;
+  double* xyzh;  // [slots][4]
+  double* full;  // [slots][19] or null
+  TG_HD void operator()(size_t slot) const {
+    const int p = smp_prob[slot];
+    if ((int)slot - smp_off[p] >= b.ps[p].n_samples) return;
+    const int gs = b.seg_off[p] + seg_idx[slot];
+    sample_eval(b.coef + (size_t)gs * TG_D * TG_N, t_in[slot], xyzh + 4 * slot, full ? full + 19 * slot : nullptr);
+  }
+};
+struct SlotProblemFn {  // fills slot -> problem map: one thread per problem
+  int B;
+  const int* smp_off;
+  int* smp_prob;
+  TG_HD void operator()(size_t pi) const {
+    for (int s = smp_off[pi]; s < smp_off[pi + 1]; ++s) smp_prob[s] = (int)pi;
+  }
+};
+struct LengthCheckFn {  // node.cpp:1178-1199
+  BatchPtrs b;
+  double dt, max_factor, min_factor;
+  TG_HD void operator()(size_t pi) const {
+    ProbState& ps = b.ps[pi];
+    if (ps.status != kFindOk) return;
+    const double len = (double)ps.n_samples * dt;
+    if (len > 1.0 && len > (max_factor * ps.baca_total)) ps.status = kFindTooLong;
+    else if (len > 1.0 && len < (min_factor * ps.baca_total)) ps.status = kFindTooShort;
+  }
+};
+
+// ---- 8. validation + subdivision: one thread per problem -------------------------------------------------------------------
+struct ValidateFn {
+  BatchPtrs b;
+  const int* smp_off;
+  const double* xyzh;
+  uint8_t* seg_ok;  // [totS]
+  double max_deviation;
+  int first_segment_checked, check_deviation;
+  TG_HD void operator()(size_t pi) const {
+    const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0, V = S + 1, v0 = s0 + p;
+    ProbState& ps = b.ps[p];
+    ps.next_V = 0;
+    if (ps.status != kFindOk) return;
+    double md = 0.0;
+    const int safe = validate_spatial(ps.n_samples, xyzh + 4 * (size_t)smp_off[p], V, b.wp + 4 * (size_t)v0, max_deviation,
+                                      first_segment_checked, seg_ok + s0, &md);
+    ps.max_dev = md;
+    ps.safe = safe;
+    if (check_deviation && !safe)
+      ps.next_V = subdivide(V, b.wp + 4 * (size_t)v0, nullptr, seg_ok + s0, first_segment_checked, nullptr, nullptr);
+  }
+};
+struct SubdivideFillFn {  // one thread per problem of the NEXT batch
+  BatchPtrs old_b;
+  const uint8_t* seg_ok;
+  const int* src;          // next-batch problem -> old-batch problem
+  const int* new_seg_off;  // next batch
+  double* new_wp;
+  uint8_t* new_stop;
+  double* new_init14;      // or null
+  int first_segment_checked;
+  TG_HD void operator()(size_t qi) const {
+    const int q = (int)qi, p = src[q];
+    const int s0 = old_b.seg_off[p], V = old_b.seg_off[p + 1] - s0 + 1, v0 = s0 + p;
+    const int nv0 = new_seg_off[q] + q;
+    subdivide(V, old_b.wp + 4 * (size_t)v0, old_b.stop ? old_b.stop + v0 : nullptr, seg_ok + s0, first_segment_checked,
+              new_wp + 4 * (size_t)nv0, new_stop + nv0);
+    if (new_init14)
+      for (int e = 0; e < 14; ++e) new_init14[14 * (size_t)q + e] = old_b.init14[14 * (size_t)p + e];
+  }
+};
+
+// ---- 9. stand-alone pieces behind the class-level entry points ---------------------------------------------------------------
+struct InitStateFn {  // ProbState reset for bare batches (no vertex recipe)
+  ProbState* ps;
+  TG_HD void operator()(size_t p) const {
+    ProbState z;
+    z.status = kFindOk; z.nlopt_code = 1; z.n_evals = 0; z.n_scale_passes = 0; z.scale_done = 0; z.n_samples = 0;
+    z.sample_cap = 0; z.safe = 0; z.next_V = 0; z.pad = 0; z.final_cost = 0.0; z.cost = 0.0; z.baca_total = 0.0; z.max_dev = 0.0;
+    ps[p] = z;
+  }
+};
+struct CostOutFn {
+  const ProbState* ps;
+  double* cost;
+  TG_HD void operator()(size_t p) const { cost[p] = ps[p].cost; }
+};
+struct CountOutFn {
+  const ProbState* ps;
+  int* counts;
+  TG_HD void operator()(size_t p) const { counts[p] = ps[p].n_samples; }
+};
+struct ScaleOutFn {
+  const ProbState* ps;
+  const double* maxima;
+  const int* seg_off;
+  double L[9];
+  int* passes;
+  uint8_t* within;
+  TG_HD void operator()(size_t p) const {
+    passes[p] = ps[p].n_scale_passes;
+    double g[9];
+    for (int q = 0; q < 9; ++q) g[q] = TG_DBL_LOWEST;
+    for (int i = seg_off[p]; i < seg_off[p + 1]; ++i)
+      for (int q = 0; q < 9; ++q)
+        if (maxima[(size_t)i * 9 + q] > g[q]) g[q] = maxima[(size_t)i * 9 + q];
+    within[p] = violation_within(g, L) ? 1 : 0;
+  }
+};
+// Trajectory::evaluate(t, derivative) (eth/trajectory.cpp:55-87): one thread per query time
+struct EvaluateFn {
+  int S, deriv;
+  const double* coef;
+  const double* T;
+  const double* tq;
+  double* out;
+  uint8_t* ok;
+  TG_HD void operator()(size_t qi) const {
+    const double t = tq[qi];
+    double acc = 0.0;
+    int i = 0;
+    for (i = 0; i < S; ++i) {
+      acc = acc + T[i];
+      if (acc > t) break;
+    }
+    if (t > acc) {
+      for (int d = 0; d < TG_D; ++d) out[4 * qi + d] = 0.0;
+      if (ok) ok[qi] = 0;
+      return;
+    }
+    if (i >= S) i = S - 1;
+    acc = acc - T[i];
+    for (int d = 0; d < TG_D; ++d) out[4 * qi + d] = (deriv >= TG_N) ? 0.0 : poly_eval(coef + ((size_t)i * TG_D + d) * TG_N, t - acc, deriv);
+    if (ok) ok[qi] = 1;
+  }
+};
+struct ExtremaRawFn {  // one thread per (segment, quantity), quantity-major
+  size_t totS;
+  const double* coef;
+  const double* times;
+  double* maxima;
+  TG_HD void operator()(size_t item) const {
+    const size_t q = item / totS, gs = item - q * totS;
+    maxima[gs * 9 + q] = segment_max_magnitude(coef + gs * TG_D * TG_N, times[gs], (int)q, nullptr);
+  }
+};
+struct CompactSamplesFn {  // one thread per sample slot: slot arrays (with per-problem slack) -> contiguous outputs
+  const int* smp_off;
+  const int* smp_prob;
+  const int* dst_off;  // [B] exclusive scan of the true counts
+  const ProbState* ps;
+  const double* xyzh;
+  const double* full;
+  double* o_xyzh;
+  double* o_full;
+  TG_HD void operator()(size_t slot) const {
+    const int p = smp_prob[slot], k = (int)slot - smp_off[p];
+    if (k >= ps[p].n_samples) return;
+    const size_t dst = (size_t)dst_off[p] + k;
+    if (o_xyzh)
+      for (int e = 0; e < 4; ++e) o_xyzh[4 * dst + e] = xyzh[4 * slot + e];
+    if (o_full)
+      for (int e = 0; e < 19; ++e) o_full[19 * dst + e] = full[19 * slot + e];
+  }
+};
+// first-minimum argmin over chunks of 1024 candidates (the host finishes over the chunk results)
+struct ArgminChunkFn {
+  long long K;
+  const double* costs;
+  double* cmin;
+  long long* cidx;
+  TG_HD void operator()(size_t c) const {
+    const long long k0 = (long long)c * 1024, k1 = (k0 + 1024 < K) ? k0 + 1024 : K;
+    double best = costs[k0];
+    long long bi = k0;
+    for (long long k = k0 + 1; k < k1; ++k)
+      if (costs[k] < best) { best = costs[k]; bi = k; }
+    cmin[c] = best;
+    cidx[c] = bi;
+  }
+};
+
+// final gather: 32 consecutive items (one warp) copy the outputs of one group member into the contiguous result arrays
+struct GatherFn {
+  const int* seg_off;
+  const int* smp_off;
+  const ProbState* ps;
+  const int* dst_seg;  // [B] destination segment offset, or -1 when this group does not hold the member's final result
+  const int* dst_vtx;
+  const int* dst_smp;
+  const double *wp, *times, *coef, *xyzh;
+  double *o_wp, *o_times, *o_coef, *o_xyzh;
+  TG_HD void operator()(size_t item) const {
+    const int m = (int)(item >> 5), lane = (int)(item & 31);
+    const int ds = dst_seg[m];
+    if (ds < 0) return;
+    const int s0 = seg_off[m], S = seg_off[m + 1] - s0, v0 = s0 + m;
+    if (o_times)
+      for (int i = lane; i < S; i += 32) o_times[ds + i] = times[s0 + i];
+    if (o_coef)
+      for (int i = lane; i < S * TG_D * TG_N; i += 32) o_coef[(size_t)ds * TG_D * TG_N + i] = coef[(size_t)s0 * TG_D * TG_N + i];
+    if (o_wp)
+      for (int i = lane; i < (S + 1) * 4; i += 32) o_wp[4 * (size_t)dst_vtx[m] + i] = wp[4 * (size_t)v0 + i];
+    if (o_xyzh) {
+      const int n = ps[m].n_samples * 4;
+      for (int i = lane; i < n; i += 32) o_xyzh[4 * (size_t)dst_smp[m] + i] = xyzh[4 * (size_t)smp_off[m] + i];
+    }
+  }
+};
+
+// vertex -> problem map: one thread per problem
+struct VtxProblemFn {
+  const int* seg_off;
+  int* prob_of_vtx;
+  int* prob_of_seg;
+  TG_HD void operator()(size_t pi) const {
+    const int p = (int)pi, s0 = seg_off[p], v0 = s0 + p, S = seg_off[p + 1] - s0;
+    for (int v = 0; v < S + 1; ++v) prob_of_vtx[v0 + v] = p;
+    for (int i = 0; i < S; ++i) prob_of_seg[s0 + i] = p;
+  }
+};
+
+}  // namespace tg
+
+#endif  // TG_KERNELS_CUH_

@@ -1,0 +1,674 @@
+// tg_pipeline.hpp -- host-side orchestration of the batched trajectory pipeline, templated on a Backend that knows
+// how to allocate device memory, copy, and launch the functors of tg_kernels.cuh (CudaBackend in cuda_backend.cu;
+// tests/host_emu/EmuBackend runs the same code on the CPU for GPU-less bit-parity tests).
+//
+// find_batch()     = MrsTrajectoryGeneration::findTrajectory for every problem of a ragged batch (node.cpp:857-1209)
+// optimize_batch() = the validation / midpoint-subdivision loop of optimize() around it (node.cpp:729-785)
+#ifndef TG_PIPELINE_HPP_
+#define TG_PIPELINE_HPP_
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "tg_kernels.cuh"
+
+namespace tg {
+
+// bump allocator over backend device memory; chunks are kept and reused across calls
+template <class BE>
+class Arena {
+ public:
+  explicit Arena(BE& be, size_t chunk = (size_t)256 << 20) : be_(be), chunk_(chunk) {}
+  ~Arena() {
+    for (auto& c : chunks_) be_.dev_free(c.ptr);
+  }
+  void* alloc_bytes(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    while (cur_ < chunks_.size()) {
+      Chunk& c = chunks_[cur_];
+      if (c.used + bytes <= c.size) {
+        void* p = (char*)c.ptr + c.used;
+        c.used += bytes;
+        return p;
+      }
+      ++cur_;
+    }
+    Chunk c;
+    c.size = std::max(chunk_, bytes);
+    c.ptr = be_.dev_alloc(c.size);
+    c.used = bytes;
+    chunks_.push_back(c);
+    cur_ = chunks_.size() - 1;
+    return c.ptr;
+  }
+  template <class T>
+  T* alloc(size_t n) { return (T*)alloc_bytes(n * sizeof(T)); }
+  void reset() {
+    for (auto& c : chunks_) c.used = 0;
+    cur_ = 0;
+  }
+  size_t bytes_reserved() const {
+    size_t t = 0;
+    for (auto& c : chunks_) t += c.size;
+    return t;
+  }
+
+ private:
+  struct Chunk { void* ptr; size_t size, used; };
+  BE& be_;
+  size_t chunk_;
+  std::vector<Chunk> chunks_;
+  size_t cur_ = 0;
+};
+
+// host-visible per-problem result (mirrors tg_result in include/tg_b200.h)
+struct Result {
+  int status, success, nlopt_code, n_evals, rounds, safe, n_waypoints, n_samples, n_scale_passes, overflow;
+  double max_dev, final_cost, baca_total;
+  long long total_solves, total_root_calls, total_evals;
+};
+
+// One processed group of problems whose outputs stay on the device until gathered.
+struct Group {
+  int B = 0, totS = 0, totV = 0, totSlots = 0;
+  std::vector<int> seg_off, smp_off;       // host copies
+  std::vector<ProbState> ps;               // host copy after find
+  std::vector<int> orig;                   // original problem index of each member
+  // device (persistent arena)
+  int* d_seg_off = nullptr;
+  double* d_wp = nullptr;
+  uint8_t* d_stop = nullptr;
+  double* d_init14 = nullptr;
+  double* d_times = nullptr;
+  double* d_coef = nullptr;
+  double* d_xyzh = nullptr;
+  int* d_smp_off = nullptr;
+  uint8_t* d_seg_ok = nullptr;
+  ProbState* d_ps = nullptr;
+  BatchPtrs bp;
+};
+
+struct Counters {
+  long long launches = 0, solves = 0, evals = 0, root_finds = 0, segment_setups = 0, samples = 0;
+};
+
+template <class BE>
+class Pipeline {
+ public:
+  explicit Pipeline(BE& be) : be_(be), persist_(be), scratch_(be) {}
+
+  BE& backend() { return be_; }
+  Counters counters;
+  size_t seg_budget = (size_t)1 << 21;  // max segments per group (bounds scratch memory: ~5.6 kB per segment)
+
+  // ---------------------------------------------------------------------------------------------------------------
+  // findTrajectory over one group.  Inputs (wp/stop/init14) already in device memory inside `g`.
+  void find_group(Group& g, const Params& P) {
+    const int B = g.B, totS = g.totS, totV = g.totV;
+    BatchPtrs& b = g.bp;
+    std::memset(&b, 0, sizeof(b));
+    b.B = B; b.totS = totS; b.totV = totV; b.r = P.derivative_to_optimize;
+    b.seg_off = g.d_seg_off;
+    b.wp = g.d_wp; b.stop = g.d_stop; b.init14 = g.d_init14;
+    int* pov = scratch_.template alloc<int>(totV);
+    int* pos = scratch_.template alloc<int>(totS);
+    b.prob_of_vtx = pov; b.prob_of_seg = pos;
+    b.vmask = scratch_.template alloc<uint8_t>(totV);
+    b.vval = scratch_.template alloc<double>((size_t)totV * TG_HALF * TG_D);
+    b.vfree = scratch_.template alloc<int>((size_t)totV + B);
+    b.np = scratch_.template alloc<int>(B);
+    b.hbw = scratch_.template alloc<int>(B);
+    b.stats = scratch_.template alloc<int>(4);
+    b.times = g.d_times;
+    b.baca = scratch_.template alloc<double>(totS);
+    b.coef = g.d_coef;
+    b.ps = g.d_ps;
+    be_.dev_memset(b.stats, 0, 4 * sizeof(int));
+    be_.for_each(B, VtxProblemFn{g.d_seg_off, pov, pos}); launches(1);
+    be_.for_each(B, PrepareFn{b, 1}); launches(1);
+    TimesFn tf{b, {}};
+    for (int i = 0; i < 9; ++i) tf.L[i] = P.limits[i];
+    be_.for_each(totS, tf); launches(1);
+    be_.for_each(B, BacaTotalFn{b}); launches(1);
+    int stats[4];
+    be_.d2h(stats, b.stats, sizeof(stats));
+    const int ws = stats[0];
+    if (P.run_time_alloc) {
+      b.xeval = scratch_.template alloc<double>(totS);
+      b.x = scratch_.template alloc<double>(totS);
+      b.g = scratch_.template alloc<double>(totS);
+      b.d = scratch_.template alloc<double>(totS);
+      b.hist_s = scratch_.template alloc<double>((size_t)(kLbfgsMem + 1) * totS);
+      b.hist_y = scratch_.template alloc<double>((size_t)(kLbfgsMem + 1) * totS);
+      b.lb = scratch_.template alloc<LbfgsScalars>(B);
+      b.recs = scratch_.template alloc<double>((size_t)totS * 3 * TG_REC_SIZE);
+      b.costs = scratch_.template alloc<double>(totV);
+      b.maxima = scratch_.template alloc<double>((size_t)totS * 9);
+      be_.for_each(B, LbfgsBeginFn{b}); launches(1);
+      for (int e = 0; e < P.max_evals; ++e) {
+        be_.for_each((size_t)totS * 3, SetupMellingerFn{b});
+        be_.solve((size_t)totV, ws, SolveProblemDesc{b, 1, nullptr, nullptr});
+        be_.for_each(B, LbfgsAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel});
+        launches(3);
+      }
+      be_.for_each(B, LbfgsFinishFn{b}); launches(1);
+      // time scaling (nl_impl.h:335-427 -> eth/trajectory.cpp:598-692)
+      ScaleFn sf{b, {}};
+      ScaleCheckFn cf{b, {}};
+      for (int i = 0; i < 9; ++i) { sf.L[i] = P.limits[i]; cf.L[i] = P.limits[i]; }
+      be_.for_each((size_t)totS * 9, ExtremaFn{b, nullptr}); launches(1);
+      for (int pass = 0; pass < 20; ++pass) {
+        be_.dev_memset(b.stats + 1, 0, sizeof(int));
+        be_.for_each(totS, sf);
+        be_.for_each((size_t)totS * 9, ExtremaFn{b, nullptr});
+        be_.for_each(B, cf);
+        launches(3);
+        int pending = 0;
+        be_.d2h(&pending, b.stats + 1, sizeof(int));
+        if (pending == 0) break;
+      }
+    } else {
+      b.recs = scratch_.template alloc<double>((size_t)totS * TG_REC_SIZE);
+    }
+    // final linear solve at the (scaled) times (nl_impl.h:405-408 / lin_impl.h:340-373)
+    be_.for_each(totS, SetupBaseFn{b, b.times});
+    be_.solve((size_t)B, ws, SolveProblemDesc{b, 0, nullptr, nullptr});
+    launches(2);
+    // sampling (eth/trajectory_sampling.cpp:49-104)
+    int* cap = scratch_.template alloc<int>((size_t)B + 1);
+    g.d_smp_off = persist_.template alloc<int>((size_t)B + 1);
+    be_.for_each(B, SampleCapFn{b, P.dt, cap}); launches(1);
+    be_.exclusive_scan(cap, g.d_smp_off, B); launches(1);
+    g.smp_off.resize(B + 1);
+    be_.d2h(g.smp_off.data(), g.d_smp_off, sizeof(int) * (B + 1));
+    g.totSlots = g.smp_off[B];
+    const size_t slots = (size_t)std::max(g.totSlots, 1);
+    int* seg_idx = scratch_.template alloc<int>(slots);
+    int* smp_prob = scratch_.template alloc<int>(slots);
+    double* t_in = scratch_.template alloc<double>(slots);
+    g.d_xyzh = persist_.template alloc<double>(slots * 4);
+    be_.for_each(B, SampleWalkFn{b, P.dt, g.d_smp_off, seg_idx, t_in});
+    be_.for_each(B, SlotProblemFn{B, g.d_smp_off, smp_prob});
+    be_.for_each((size_t)g.totSlots, SampleEvalFn{b, g.d_smp_off, smp_prob, seg_idx, t_in, g.d_xyzh, nullptr});
+    be_.for_each(B, LengthCheckFn{b, P.dt, P.max_len_factor, P.min_len_factor});
+    launches(4);
+    g.ps.resize(B);
+    be_.d2h(g.ps.data(), g.d_ps, sizeof(ProbState) * B);
+    for (int p = 0; p < B; ++p) {
+      const int S = g.seg_off[p + 1] - g.seg_off[p];
+      const int ev = g.ps[p].n_evals;
+      counters.evals += ev;
+      counters.solves += (long long)ev * (S == 1 ? 1 : S + 1) + 1;
+      counters.segment_setups += (long long)ev * S * (S == 1 ? 1 : 3) + S;
+      counters.root_finds += (long long)(P.run_time_alloc ? (g.ps[p].n_scale_passes + 1) * 9 * S : 0);
+      counters.samples += g.ps[p].n_samples;
+    }
+  }
+
+  // ---------------------------------------------------------------------------------------------------------------
+  // Builds a group on the device from host inputs (problem subset [p0, p1) of a host batch).
+  Group* make_group_from_host(const std::vector<int>& members, const int* wp_off, const double* wp, const uint8_t* stop,
+                              const double* init14, bool on_device_inputs) {
+    groups_.emplace_back(new Group());
+    Group& g = *groups_.back();
+    const int B = (int)members.size();
+    g.B = B;
+    g.orig = members;
+    g.seg_off.resize(B + 1);
+    g.seg_off[0] = 0;
+    for (int i = 0; i < B; ++i) g.seg_off[i + 1] = g.seg_off[i] + (wp_off[members[i] + 1] - wp_off[members[i]] - 1);
+    g.totS = g.seg_off[B];
+    g.totV = g.totS + B;
+    alloc_group_outputs(g, init14 != nullptr);
+    // members are a contiguous range of the host batch: copy straight through
+    const int first = members.front();
+    const size_t v0 = (size_t)wp_off[first];
+    if (on_device_inputs) {
+      be_.d2d(g.d_wp, wp + 4 * v0, sizeof(double) * 4 * g.totV);
+      if (stop) be_.d2d(g.d_stop, stop + v0, g.totV);
+      if (init14) be_.d2d(g.d_init14, init14 + 14 * (size_t)first, sizeof(double) * 14 * B);
+    } else {
+      be_.h2d(g.d_wp, wp + 4 * v0, sizeof(double) * 4 * g.totV);
+      if (stop) be_.h2d(g.d_stop, stop + v0, g.totV);
+      if (init14) be_.h2d(g.d_init14, init14 + 14 * (size_t)first, sizeof(double) * 14 * B);
+    }
+    if (!stop) be_.dev_memset(g.d_stop, 0, g.totV);
+    return &g;
+  }
+
+  void alloc_group_outputs(Group& g, bool with_init) {
+    const int B = g.B;
+    g.d_seg_off = persist_.template alloc<int>((size_t)B + 1);
+    be_.h2d(g.d_seg_off, g.seg_off.data(), sizeof(int) * (B + 1));
+    g.d_wp = persist_.template alloc<double>((size_t)g.totV * 4);
+    g.d_stop = persist_.template alloc<uint8_t>(g.totV);
+    g.d_init14 = with_init ? persist_.template alloc<double>((size_t)B * 14) : nullptr;
+    g.d_times = persist_.template alloc<double>(g.totS);
+    g.d_coef = persist_.template alloc<double>((size_t)g.totS * TG_D * TG_N);
+    g.d_seg_ok = persist_.template alloc<uint8_t>(g.totS);
+    g.d_ps = persist_.template alloc<ProbState>(B);
+  }
+
+  // ---------------------------------------------------------------------------------------------------------------
+  // optimize(): findTrajectory + validation + subdivision rounds for a whole host batch.
+  // wp_off: [B+1] vertex offsets (host).  wp/stop/init14: host pointers, or device pointers when on_device_inputs.
+  void optimize_batch(int B, const int* wp_off, const double* wp, const uint8_t* stop, const double* init14, const Params& P,
+                      bool on_device_inputs, Result* results) {
+    persist_.reset();
+    scratch_.reset();
+    groups_.clear();
+    final_group_.assign(B, -1);
+    final_index_.assign(B, -1);
+    B_ = B;
+    for (int p = 0; p < B; ++p) {
+      std::memset(&results[p], 0, sizeof(Result));
+      results[p].nlopt_code = -1;
+    }
+    // round 0: consecutive groups within the segment budget
+    std::vector<Group*> current;
+    {
+      std::vector<int> members;
+      size_t segs = 0;
+      for (int p = 0; p < B; ++p) {
+        const int S = wp_off[p + 1] - wp_off[p] - 1;
+        if (S < 1) {  // "the path is empty (after postprocessing)" (node.cpp:676-681)
+          if (!members.empty()) { current.push_back(make_group_from_host(members, wp_off, wp, stop, init14, on_device_inputs)); members.clear(); segs = 0; }
+          results[p].status = kFindSampleFail;
+          continue;
+        }
+        if (!members.empty() && segs + S > seg_budget) {
+          current.push_back(make_group_from_host(members, wp_off, wp, stop, init14, on_device_inputs));
+          members.clear();
+          segs = 0;
+        }
+        members.push_back(p);
+        segs += S;
+      }
+      if (!members.empty()) current.push_back(make_group_from_host(members, wp_off, wp, stop, init14, on_device_inputs));
+    }
+    for (int round = 0;; ++round) {
+      // run findTrajectory on every group of this round, then validate
+      std::vector<std::pair<Group*, int>> pending;  // (group, member) that need another round
+      for (Group* g : current) {
+        scratch_.reset();
+        find_group(*g, P);
+        const bool last_round = (round >= P.max_deviation_iters);
+        if (!last_round) {
+          be_.for_each(g->B, ValidateFn{g->bp, g->d_smp_off, g->d_xyzh, g->d_seg_ok, P.max_deviation, P.first_segment_checked, P.check_deviation});
+          launches(1);
+          be_.d2h(g->ps.data(), g->d_ps, sizeof(ProbState) * g->B);
+        }
+        const int gi = group_index(g);
+        for (int m = 0; m < g->B; ++m) {
+          const int p = g->orig[m];
+          const ProbState& ps = g->ps[m];
+          Result& R = results[p];
+          final_group_[p] = gi;
+          final_index_[p] = m;
+          const int S = g->seg_off[m + 1] - g->seg_off[m];
+          R.status = ps.status;
+          R.nlopt_code = ps.nlopt_code;
+          R.n_evals = ps.n_evals;
+          R.rounds = round;
+          R.n_waypoints = S + 1;
+          R.n_samples = ps.n_samples;
+          R.n_scale_passes = ps.n_scale_passes;
+          R.final_cost = P.run_time_alloc ? ps.final_cost : ps.cost;
+          R.baca_total = ps.baca_total;
+          R.total_evals += ps.n_evals;
+          R.total_solves += (long long)ps.n_evals * (S == 1 ? 1 : S + 2) + 1;  // reference count: S+2 solves per evaluation
+          R.total_root_calls += P.run_time_alloc ? (long long)ps.n_scale_passes * 18 * S : 0;
+          if (ps.status != kFindOk) { R.success = 0; continue; }
+          R.success = 1;
+          if (last_round) { R.safe = 0; continue; }  // returned without re-validation (node.cpp:729-785)
+          R.max_dev = ps.max_dev;
+          if (ps.next_V > 0) pending.emplace_back(g, m);
+          else R.safe = 1;
+        }
+      }
+      if (pending.empty()) break;
+      // build the next round's groups by midpoint insertion on the device
+      std::vector<Group*> next;
+      size_t i = 0;
+      while (i < pending.size()) {
+        Group* src = pending[i].first;
+        groups_.emplace_back(new Group());
+        Group& ng = *groups_.back();
+        std::vector<int> srcm;
+        size_t segs = 0;
+        ng.seg_off.push_back(0);
+        while (i < pending.size() && pending[i].first == src) {
+          const int m = pending[i].second;
+          const int newS = src->ps[m].next_V - 1;
+          if (!srcm.empty() && segs + newS > seg_budget) break;
+          srcm.push_back(m);
+          ng.orig.push_back(src->orig[m]);
+          ng.seg_off.push_back(ng.seg_off.back() + newS);
+          segs += newS;
+          ++i;
+        }
+        ng.B = (int)srcm.size();
+        ng.totS = ng.seg_off.back();
+        ng.totV = ng.totS + ng.B;
+        alloc_group_outputs(ng, src->d_init14 != nullptr);
+        int* d_src = scratch_.template alloc<int>(ng.B);
+        be_.h2d(d_src, srcm.data(), sizeof(int) * ng.B);
+        be_.for_each(ng.B, SubdivideFillFn{src->bp, src->d_seg_ok, d_src, ng.d_seg_off, ng.d_wp, ng.d_stop, ng.d_init14, P.first_segment_checked});
+        launches(1);
+        be_.sync();  // d_src lives in scratch, which the next find_group resets
+        next.push_back(&ng);
+      }
+      current.swap(next);
+    }
+  }
+
+  // sizes of the ragged outputs of the last optimize_batch: totals[0] = segments, totals[1] = samples
+  void output_sizes(long long* totals, const Result* results) const {
+    long long s = 0, m = 0;
+    for (int p = 0; p < B_; ++p) {
+      if (final_group_[p] < 0) continue;
+      s += results[p].n_waypoints - 1;
+      m += results[p].n_samples;
+    }
+    totals[0] = s;
+    totals[1] = m;
+  }
+
+  // Gathers the final outputs into contiguous ragged arrays and copies them to host buffers (any may be null).
+  void fetch_outputs(const Result* results, int* seg_off_out, double* wp_out, double* times_out, double* coef_out, int* smp_off_out,
+                     double* samples_out) {
+    const int B = B_;
+    std::vector<int> so(B + 1, 0), mo(B + 1, 0);
+    for (int p = 0; p < B; ++p) {
+      const bool have = final_group_[p] >= 0;
+      so[p + 1] = so[p] + (have ? results[p].n_waypoints - 1 : 0);
+      mo[p + 1] = mo[p] + (have ? results[p].n_samples : 0);
+    }
+    if (seg_off_out) std::memcpy(seg_off_out, so.data(), sizeof(int) * (B + 1));
+    if (smp_off_out) std::memcpy(smp_off_out, mo.data(), sizeof(int) * (B + 1));
+    const long long totS = so[B], totM = mo[B];
+    scratch_.reset();
+    double* o_wp = wp_out ? scratch_.template alloc<double>((size_t)(totS + B) * 4) : nullptr;
+    double* o_times = times_out ? scratch_.template alloc<double>((size_t)std::max<long long>(totS, 1)) : nullptr;
+    double* o_coef = coef_out ? scratch_.template alloc<double>((size_t)std::max<long long>(totS, 1) * TG_D * TG_N) : nullptr;
+    double* o_xyzh = samples_out ? scratch_.template alloc<double>((size_t)std::max<long long>(totM, 1) * 4) : nullptr;
+    // problems without any result (S < 1) still own one vertex slot in the output numbering: vertex offset = so[p] + p
+    for (size_t gi = 0; gi < groups_.size(); ++gi) {
+      Group& g = *groups_[gi];
+      std::vector<int> dst(3 * (size_t)g.B);
+      bool any = false;
+      for (int m = 0; m < g.B; ++m) {
+        const int p = g.orig[m];
+        const bool fin = final_group_[p] == (int)gi;
+        dst[m] = fin ? so[p] : -1;
+        dst[g.B + m] = fin ? so[p] + p : -1;
+        dst[2 * g.B + m] = fin ? mo[p] : -1;
+        any = any || fin;
+      }
+      if (!any) continue;
+      int* d_dst = scratch_.template alloc<int>(dst.size());
+      be_.h2d(d_dst, dst.data(), sizeof(int) * dst.size());
+      be_.for_each((size_t)g.B * 32, GatherFn{g.d_seg_off, g.d_smp_off, g.d_ps, d_dst, d_dst + g.B, d_dst + 2 * g.B, g.d_wp, g.d_times, g.d_coef,
+                                               g.d_xyzh, o_wp, o_times, o_coef, o_xyzh});
+      launches(1);
+    }
+    if (wp_out) be_.d2h(wp_out, o_wp, sizeof(double) * 4 * (size_t)(totS + B));
+    if (times_out && totS) be_.d2h(times_out, o_times, sizeof(double) * (size_t)totS);
+    if (coef_out && totS) be_.d2h(coef_out, o_coef, sizeof(double) * (size_t)totS * TG_D * TG_N);
+    if (samples_out && totM) be_.d2h(samples_out, o_xyzh, sizeof(double) * 4 * (size_t)totM);
+  }
+
+
+  // ===============================================================================================================
+  // Class-level pieces (PolynomialOptimization / Trajectory / sampling) on caller-supplied data
+  // ===============================================================================================================
+  struct Bare {
+    BatchPtrs b;
+    int* d_seg_off;
+  };
+  // device batch skeleton from host segment offsets (scratch arena)
+  Bare bare_batch(int B, const int* seg_off, int r) {
+    Bare o;
+    BatchPtrs& b = o.b;
+    std::memset(&b, 0, sizeof(b));
+    b.B = B; b.totS = seg_off[B]; b.totV = b.totS + B; b.r = r;
+    o.d_seg_off = scratch_.template alloc<int>((size_t)B + 1);
+    be_.h2d(o.d_seg_off, seg_off, sizeof(int) * (B + 1));
+    b.seg_off = o.d_seg_off;
+    int* pov = scratch_.template alloc<int>(b.totV);
+    int* pos = scratch_.template alloc<int>(std::max(b.totS, 1));
+    b.prob_of_vtx = pov; b.prob_of_seg = pos;
+    b.ps = scratch_.template alloc<ProbState>(B);
+    b.stats = scratch_.template alloc<int>(4);
+    be_.dev_memset(b.stats, 0, 4 * sizeof(int));
+    be_.for_each(B, VtxProblemFn{o.d_seg_off, pov, pos});
+    be_.for_each(B, InitStateFn{b.ps});
+    launches(2);
+    return o;
+  }
+
+  // PolynomialOptimization<10>::setupFromVertices + solveLinear + getSegments + computeCost for B problems
+  bool linear_batch(int B, const int* vtx_off, const uint8_t* vmask, const double* vval, const double* times, int r, double* coef, double* cost) {
+    scratch_.reset();
+    std::vector<int> so(B + 1);
+    for (int p = 0; p <= B; ++p) so[p] = vtx_off[p] - p;
+    for (int p = 0; p < B; ++p)
+      if (so[p + 1] - so[p] < 1) return false;
+    Bare bb = bare_batch(B, so.data(), r);
+    BatchPtrs& b = bb.b;
+    b.vmask = scratch_.template alloc<uint8_t>(b.totV);
+    b.vval = scratch_.template alloc<double>((size_t)b.totV * TG_HALF * TG_D);
+    b.vfree = scratch_.template alloc<int>((size_t)b.totV + B);
+    b.np = scratch_.template alloc<int>(B);
+    b.hbw = scratch_.template alloc<int>(B);
+    b.times = scratch_.template alloc<double>(b.totS);
+    b.coef = scratch_.template alloc<double>((size_t)b.totS * TG_D * TG_N);
+    b.recs = scratch_.template alloc<double>((size_t)b.totS * TG_REC_SIZE);
+    double* d_cost = scratch_.template alloc<double>(B);
+    be_.h2d(b.vmask, vmask, b.totV);
+    be_.h2d(b.vval, vval, sizeof(double) * (size_t)b.totV * TG_HALF * TG_D);
+    be_.h2d(b.times, times, sizeof(double) * b.totS);
+    be_.for_each(B, PrepareFn{b, 0});
+    int stats[4];
+    be_.d2h(stats, b.stats, sizeof(stats));
+    be_.for_each(b.totS, SetupBaseFn{b, b.times});
+    be_.solve((size_t)B, stats[0], SolveProblemDesc{b, 0, nullptr, nullptr});
+    be_.for_each(B, CostOutFn{b.ps, d_cost});
+    launches(4);
+    counters.solves += B;
+    counters.segment_setups += b.totS;
+    if (coef) be_.d2h(coef, b.coef, sizeof(double) * (size_t)b.totS * TG_D * TG_N);
+    if (cost) be_.d2h(cost, d_cost, sizeof(double) * B);
+    return true;
+  }
+
+  // sampleWholeTrajectory for B trajectories
+  void sample_batch(int B, const int* seg_off, const double* coef, const double* times, double dt, int* counts, double* samples, double* full) {
+    scratch_.reset();
+    Bare bb = bare_batch(B, seg_off, 2);
+    BatchPtrs& b = bb.b;
+    b.times = scratch_.template alloc<double>(std::max(b.totS, 1));
+    b.coef = scratch_.template alloc<double>((size_t)std::max(b.totS, 1) * TG_D * TG_N);
+    be_.h2d(b.times, times, sizeof(double) * b.totS);
+    be_.h2d(b.coef, coef, sizeof(double) * (size_t)b.totS * TG_D * TG_N);
+    int* cap = scratch_.template alloc<int>((size_t)B + 1);
+    int* d_smp_off = scratch_.template alloc<int>((size_t)B + 1);
+    be_.for_each(B, SampleCapFn{b, dt, cap});
+    be_.exclusive_scan(cap, d_smp_off, B);
+    std::vector<int> smp_off(B + 1);
+    be_.d2h(smp_off.data(), d_smp_off, sizeof(int) * (B + 1));
+    const size_t slots = (size_t)std::max(smp_off[B], 1);
+    int* seg_idx = scratch_.template alloc<int>(slots);
+    int* smp_prob = scratch_.template alloc<int>(slots);
+    double* t_in = scratch_.template alloc<double>(slots);
+    be_.for_each(B, SampleWalkFn{b, dt, d_smp_off, seg_idx, t_in});
+    launches(3);
+    std::vector<ProbState> ps(B);
+    be_.d2h(ps.data(), b.ps, sizeof(ProbState) * B);
+    std::vector<int> dst(B + 1, 0);
+    for (int p = 0; p < B; ++p) {
+      counts[p] = ps[p].n_samples;
+      dst[p + 1] = dst[p] + ps[p].n_samples;
+    }
+    counters.samples += dst[B];
+    if (!samples && !full) return;
+    double* d_xyzh = scratch_.template alloc<double>(slots * 4);
+    double* d_full = full ? scratch_.template alloc<double>(slots * 19) : nullptr;
+    const size_t tot = (size_t)std::max(dst[B], 1);
+    double* o_xyzh = samples ? scratch_.template alloc<double>(tot * 4) : nullptr;
+    double* o_full = full ? scratch_.template alloc<double>(tot * 19) : nullptr;
+    int* d_dst = scratch_.template alloc<int>((size_t)B + 1);
+    be_.h2d(d_dst, dst.data(), sizeof(int) * (B + 1));
+    be_.for_each(B, SlotProblemFn{B, d_smp_off, smp_prob});
+    be_.for_each((size_t)smp_off[B], SampleEvalFn{b, d_smp_off, smp_prob, seg_idx, t_in, d_xyzh, d_full});
+    be_.for_each((size_t)smp_off[B], CompactSamplesFn{d_smp_off, smp_prob, d_dst, b.ps, d_xyzh, d_full, o_xyzh, o_full});
+    launches(3);
+    if (samples && dst[B]) be_.d2h(samples, o_xyzh, sizeof(double) * 4 * (size_t)dst[B]);
+    if (full && dst[B]) be_.d2h(full, o_full, sizeof(double) * 19 * (size_t)dst[B]);
+  }
+
+  // Trajectory::evaluate at n times of one trajectory
+  void evaluate_batch(int S, const double* coef, const double* times, int n, const double* t, int deriv, double* out, uint8_t* ok) {
+    scratch_.reset();
+    double* d_coef = scratch_.template alloc<double>((size_t)S * TG_D * TG_N);
+    double* d_T = scratch_.template alloc<double>(S);
+    double* d_t = scratch_.template alloc<double>(std::max(n, 1));
+    double* d_out = scratch_.template alloc<double>((size_t)std::max(n, 1) * 4);
+    uint8_t* d_ok = scratch_.template alloc<uint8_t>(std::max(n, 1));
+    be_.h2d(d_coef, coef, sizeof(double) * (size_t)S * TG_D * TG_N);
+    be_.h2d(d_T, times, sizeof(double) * S);
+    be_.h2d(d_t, t, sizeof(double) * n);
+    be_.for_each(n, EvaluateFn{S, deriv, d_coef, d_T, d_t, d_out, d_ok});
+    launches(1);
+    be_.d2h(out, d_out, sizeof(double) * 4 * (size_t)n);
+    if (ok) be_.d2h(ok, d_ok, n);
+  }
+
+  // per-segment maxima of |v|,|a|,|j| for the three dimension groups
+  void extrema_batch(int totS, const double* coef, const double* times, double* maxima) {
+    scratch_.reset();
+    double* d_coef = scratch_.template alloc<double>((size_t)totS * TG_D * TG_N);
+    double* d_T = scratch_.template alloc<double>(totS);
+    double* d_m = scratch_.template alloc<double>((size_t)totS * 9);
+    be_.h2d(d_coef, coef, sizeof(double) * (size_t)totS * TG_D * TG_N);
+    be_.h2d(d_T, times, sizeof(double) * totS);
+    be_.for_each((size_t)totS * 9, ExtremaRawFn{(size_t)totS, d_coef, d_T, d_m});
+    launches(1);
+    counters.root_finds += (long long)totS * 9;
+    be_.d2h(maxima, d_m, sizeof(double) * (size_t)totS * 9);
+  }
+
+  // Trajectory::scaleSegmentTimesToMeetConstraints in place
+  void scale_times_batch(int B, const int* seg_off, double* coef, double* times, const double* L9, int* passes, uint8_t* within) {
+    scratch_.reset();
+    Bare bb = bare_batch(B, seg_off, 2);
+    BatchPtrs& b = bb.b;
+    b.times = scratch_.template alloc<double>(b.totS);
+    b.coef = scratch_.template alloc<double>((size_t)b.totS * TG_D * TG_N);
+    b.maxima = scratch_.template alloc<double>((size_t)b.totS * 9);
+    be_.h2d(b.times, times, sizeof(double) * b.totS);
+    be_.h2d(b.coef, coef, sizeof(double) * (size_t)b.totS * TG_D * TG_N);
+    ScaleFn sf{b, {}};
+    ScaleCheckFn cf{b, {}};
+    ScaleOutFn of{b.ps, b.maxima, bb.d_seg_off, {}, nullptr, nullptr};
+    for (int i = 0; i < 9; ++i) { sf.L[i] = L9[i]; cf.L[i] = L9[i]; of.L[i] = L9[i]; }
+    be_.for_each((size_t)b.totS * 9, ExtremaFn{b, nullptr}); launches(1);
+    for (int pass = 0; pass < 20; ++pass) {
+      be_.dev_memset(b.stats + 1, 0, sizeof(int));
+      be_.for_each(b.totS, sf);
+      be_.for_each((size_t)b.totS * 9, ExtremaFn{b, nullptr});
+      be_.for_each(B, cf);
+      launches(3);
+      int pending = 0;
+      be_.d2h(&pending, b.stats + 1, sizeof(int));
+      if (pending == 0) break;
+    }
+    int* d_passes = scratch_.template alloc<int>(B);
+    uint8_t* d_within = scratch_.template alloc<uint8_t>(B);
+    of.passes = d_passes;
+    of.within = d_within;
+    be_.for_each(B, of); launches(1);
+    be_.d2h(coef, b.coef, sizeof(double) * (size_t)b.totS * TG_D * TG_N);
+    be_.d2h(times, b.times, sizeof(double) * b.totS);
+    if (passes) be_.d2h(passes, d_passes, sizeof(int) * B);
+    if (within) be_.d2h(within, d_within, B);
+  }
+
+  // cost of ONE problem at K candidate segment-time vectors + first-minimum argmin
+  bool sweep_costs(int V, const uint8_t* vmask, const double* vval, int r, long long K, const double* cand, bool cand_on_device, double* costs,
+                   long long* best_index, double* best_cost) {
+    scratch_.reset();
+    const int S = V - 1;
+    if (S < 1 || K < 1) return false;
+    const int so[2] = {0, S};
+    Bare bb = bare_batch(1, so, r);
+    BatchPtrs& b = bb.b;
+    b.vmask = scratch_.template alloc<uint8_t>(V);
+    b.vval = scratch_.template alloc<double>((size_t)V * TG_HALF * TG_D);
+    b.vfree = scratch_.template alloc<int>((size_t)V + 1);
+    b.np = scratch_.template alloc<int>(1);
+    b.hbw = scratch_.template alloc<int>(1);
+    be_.h2d(b.vmask, vmask, V);
+    be_.h2d(b.vval, vval, sizeof(double) * (size_t)V * TG_HALF * TG_D);
+    be_.for_each(1, PrepareFn{b, 0}); launches(1);
+    int stats[4];
+    be_.d2h(stats, b.stats, sizeof(stats));
+    const long long chunk = std::min<long long>(K, (long long)sweep_chunk);
+    double* d_recs = scratch_.template alloc<double>((size_t)chunk * S * TG_REC_SIZE);
+    double* d_costs = scratch_.template alloc<double>((size_t)K);
+    const double* d_cand = cand;
+    if (!cand_on_device) {
+      double* dc = scratch_.template alloc<double>((size_t)K * S);
+      be_.h2d(dc, cand, sizeof(double) * (size_t)K * S);
+      d_cand = dc;
+    }
+    for (long long k0 = 0; k0 < K; k0 += chunk) {
+      const long long kc = std::min(chunk, K - k0);
+      be_.for_each((size_t)kc * S, SetupSweepFn{S, r, d_cand + (size_t)k0 * S, d_recs});
+      be_.solve((size_t)kc, stats[0], SolveSweepDesc{b, d_recs, d_costs + k0});
+      launches(2);
+    }
+    counters.solves += K;
+    counters.segment_setups += K * S;
+    const long long nchunks = (K + 1023) / 1024;
+    double* d_cmin = scratch_.template alloc<double>((size_t)nchunks);
+    long long* d_cidx = scratch_.template alloc<long long>((size_t)nchunks);
+    be_.for_each((size_t)nchunks, ArgminChunkFn{K, d_costs, d_cmin, d_cidx}); launches(1);
+    std::vector<double> cmin(nchunks);
+    std::vector<long long> cidx(nchunks);
+    be_.d2h(cmin.data(), d_cmin, sizeof(double) * nchunks);
+    be_.d2h(cidx.data(), d_cidx, sizeof(long long) * nchunks);
+    long long bi = cidx[0];
+    double bc = cmin[0];
+    for (long long c = 1; c < nchunks; ++c)
+      if (cmin[c] < bc) { bc = cmin[c]; bi = cidx[c]; }
+    if (best_index) *best_index = bi;
+    if (best_cost) *best_cost = bc;
+    if (costs) be_.d2h(costs, d_costs, sizeof(double) * (size_t)K);
+    return true;
+  }
+  size_t sweep_chunk = (size_t)1 << 17;
+
+ private:
+  int group_index(const Group* g) const {
+    for (size_t i = 0; i < groups_.size(); ++i)
+      if (groups_[i].get() == g) return (int)i;
+    return -1;
+  }
+  void launches(int n) { counters.launches += n; }
+
+  BE& be_;
+  Arena<BE> persist_, scratch_;
+  std::vector<std::unique_ptr<Group>> groups_;
+  std::vector<int> final_group_, final_index_;
+  int B_ = 0;
+};
+
+}  // namespace tg
+
+#endif  // TG_PIPELINE_HPP_

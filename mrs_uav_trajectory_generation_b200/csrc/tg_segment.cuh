@@ -1,0 +1,190 @@
+// tg_segment.cuh -- per-segment matrices for one segment time T: Q, A^-1 (Schur form) and H = (A^-T Q) A^-1.
+// Replaces PolynomialOptimization<10>::updateSegmentTimes + the per-segment part of constructR
+// (reference: lin_impl.h:288-304, 605-618, 112-121, 147-177, 317-320).  One thread computes one record;
+// all arrays are statically indexed so they live in registers.  Structural zeros of A^-1 and Q are skipped:
+// adding an exact zero does not change an IEEE sum, so the result equals the dense evaluation.
+#ifndef TG_SEGMENT_CUH_
+#define TG_SEGMENT_CUH_
+
+#include "tg_common.cuh"
+
+namespace tg {
+
+// 5x5 inverse: LU with first-maximum row pivoting, multipliers by division, then identity columns solved by
+// forward (ascending j) and back substitution (ascending j).  DESIGN.md "numeric contract" item C.
+TG_HD void inverse5(const double (&Din)[5][5], double (&out)[5][5]) {
+  double lu[5][5];
+  int perm[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    perm[i] = i;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) lu[i][j] = Din[i][j];
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    int piv = k;
+    double best = dabs(lu[k][k]);
+#pragma unroll
+    for (int i = k + 1; i < 5; ++i) {
+      const double a = dabs(lu[i][k]);
+      if (a > best) { best = a; piv = i; }
+    }
+    // swap rows k and piv with static indices (select instead of dynamic addressing)
+#pragma unroll
+    for (int i = k + 1; i < 5; ++i) {
+      const bool sw = (piv == i);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const double a = lu[k][j], b = lu[i][j];
+        lu[k][j] = sw ? b : a;
+        lu[i][j] = sw ? a : b;
+      }
+      const int pa = perm[k], pb = perm[i];
+      perm[k] = sw ? pb : pa;
+      perm[i] = sw ? pa : pb;
+    }
+#pragma unroll
+    for (int i = k + 1; i < 5; ++i) lu[i][k] = lu[i][k] / lu[k][k];
+#pragma unroll
+    for (int i = k + 1; i < 5; ++i)
+#pragma unroll
+      for (int j = k + 1; j < 5; ++j) lu[i][j] = lu[i][j] - lu[i][k] * lu[k][j];
+  }
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    double y[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      double s = (perm[i] == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int j = 0; j < i; ++j) s = s - lu[i][j] * y[j];
+      y[i] = s;
+    }
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+      double s = y[i];
+#pragma unroll
+      for (int j = i + 1; j < 5; ++j) s = s - lu[i][j] * y[j];
+      y[i] = s / lu[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) out[i][c] = y[i];
+  }
+}
+
+// Computes the record for one (segment, time).  r = derivative whose squared integral is minimised (2..4).
+template <int R>
+TG_HD void setup_segment_record_r(double T, double* __restrict__ rec) {
+  constexpr int NQ = TG_N - R;           // non-zero rows/cols of Q start at index R
+  constexpr int EMAX = (TG_N - 1 - R) * 2 + 1;
+  // --- Q (lin_impl.h:605-618): Q[i][j] = B[r][i]*B[r][j]*pow(T, e)*2/e, e = i+j-2r+1, left to right
+  double pw[EMAX];
+  tgdm::powers(T, EMAX, pw);
+  double Q[NQ][NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i)
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      const int e = i + j + 1;  // (i+R) + (j+R) - 2R + 1
+      Q[i][j] = bcoef(R, i + R) * bcoef(R, j + R) * pw[e - 1] * 2.0 / (double)e;
+    }
+  // --- A rows at t = T (eth/polynomial.h:208-226): entry[j] = B[k][j]*tp, tp = tp*T (plain chain)
+  double tp[TG_N];  // tp[m] = T^m by repeated multiplication, m >= 1
+  tp[0] = 1.0;
+  tp[1] = T;
+#pragma unroll
+  for (int m = 2; m < TG_N; ++m) tp[m] = tp[m - 1] * T;
+  const bool tzero = dabs(T) < TG_DBL_EPSILON;
+  double Dm[5][5], Cm[5][5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      Dm[k][j] = tzero ? 0.0 : bcoef(k, 5 + j) * tp[5 + j - k];
+      Cm[k][j] = (j < k) ? 0.0 : ((j == k) ? bcoef(k, k) : (tzero ? 0.0 : bcoef(k, j) * tp[j - k]));
+    }
+  // --- A^-1 (lin_impl.h:147-177)
+  double Dinv[5][5];
+  inverse5(Dm, Dinv);
+  const double a_inv[5] = {1.0 / 1.0, 1.0 / 1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0};
+  double X[5][5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      double m = (-Dinv[i][0]) * Cm[0][j];
+#pragma unroll
+      for (int k = 1; k <= j; ++k) m = m + (-Dinv[i][k]) * Cm[k][j];  // C[k][j] == 0 for k > j
+      X[i][j] = m * a_inv[j];
+    }
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      rec[TG_REC_DINV + i * 5 + j] = Dinv[i][j];
+      rec[TG_REC_X + i * 5 + j] = X[i][j];
+    }
+#pragma unroll
+  for (int i = 0; i < NQ; ++i)
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) rec[TG_REC_Q + i * 8 + j] = Q[i][j];
+  // --- H = (A^-T Q) A^-1 (lin_impl.h:320), inner sums over ascending k, zero terms skipped
+  // A^-1 = [ diag(a_inv) 0 ; X Dinv ].  Row a of W = A^-T Q :  W[a][b] = sum_k Ainv[k][a] Q[k][b]
+#pragma unroll
+  for (int a = 0; a < TG_N; ++a) {
+    double W[NQ];  // W[a][R + b]
+#pragma unroll
+    for (int b = 0; b < NQ; ++b) {
+      double s;
+      if (a < 5) {
+        // k = a contributes only when a >= R (Q rows below R are zero); then k = 5..9 through X
+        bool have = false;
+        s = 0.0;
+        if (a >= R) { s = a_inv[a] * Q[(a >= R) ? a - R : 0][b]; have = true; }
+#pragma unroll
+        for (int k = 5; k < TG_N; ++k) {
+          const double t = X[k - 5][a] * Q[k - R][b];
+          s = have ? s + t : t;
+          have = true;
+        }
+      } else {
+        s = Dinv[0][a - 5] * Q[5 - R][b];
+#pragma unroll
+        for (int k = 6; k < TG_N; ++k) s = s + Dinv[k - 5][a - 5] * Q[k - R][b];
+      }
+      W[b] = s;
+    }
+    // H[a][b] = sum_k W[a][k] Ainv[k][b], k ascending from R
+#pragma unroll
+    for (int b = 0; b < TG_N; ++b) {
+      double s;
+      if (b < 5) {
+        bool have = false;
+        s = 0.0;
+        if (b >= R) { s = W[(b >= R) ? b - R : 0] * a_inv[b]; have = true; }
+#pragma unroll
+        for (int k = 5; k < TG_N; ++k) {
+          const double t = W[k - R] * X[k - 5][b];
+          s = have ? s + t : t;
+          have = true;
+        }
+      } else {
+        s = W[5 - R] * Dinv[0][b - 5];
+#pragma unroll
+        for (int k = 6; k < TG_N; ++k) s = s + W[k - R] * Dinv[k - 5][b - 5];
+      }
+      rec[TG_REC_H + a * TG_N + b] = s;
+    }
+  }
+}
+
+TG_HD_NOINLINE void setup_segment_record(double T, int r, double* __restrict__ rec) {
+  if (r == 2) setup_segment_record_r<2>(T, rec);
+  else if (r == 3) setup_segment_record_r<3>(T, rec);
+  else setup_segment_record_r<4>(T, rec);
+}
+
+}  // namespace tg
+
+#endif  // TG_SEGMENT_CUH_

@@ -1,0 +1,86 @@
+// tests/host_emu/emu.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the product's TG_HD device functions, functors and host pipeline (mrs_uav_trajectory_generation_b200/csrc)
+// with g++ and runs them on CPU threads, so that bit-parity with the oracle can be checked on machines without a GPU
+// (`pytest -m "not gpu"`).  The resulting libtg_emu.so exports the same C ABI as libtg_b200.so but is never loaded by
+// the package: the product has no CPU path and fails loudly without CUDA.
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <thread>
+#include <vector>
+
+#define TG_VERSION_STRING "tg_emu (host emulation, tests only)"
+
+#include "../../mrs_uav_trajectory_generation_b200/csrc/tg_kernels.cuh"
+
+struct EmuBackend {
+  int nthreads;
+  explicit EmuBackend(int) {
+    const char* e = std::getenv("TG_EMU_THREADS");
+    nthreads = e ? std::atoi(e) : (int)std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+  }
+  void* dev_alloc(size_t n) {
+    void* p = std::malloc(n);
+    if (!p) throw std::runtime_error("emu: out of memory");
+    return p;
+  }
+  void dev_free(void* p) { std::free(p); }
+  void h2d(void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
+  void d2h(void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
+  void d2d(void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
+  void dev_memset(void* d, int v, size_t n) { std::memset(d, v, n); }
+  void sync() {}
+  void timer_start() {}
+  double timer_stop() { return 0.0; }
+
+  template <class W>
+  void parallel(size_t n, const W& work) {
+    if (n == 0) return;
+    const int nt = (int)std::min<size_t>((size_t)nthreads, (n + 63) / 64);
+    if (nt <= 1) {
+      for (size_t i = 0; i < n; ++i) work(i);
+      return;
+    }
+    std::atomic<size_t> next(0);
+    auto run = [&]() {
+      for (;;) {
+        const size_t i0 = next.fetch_add(64);
+        if (i0 >= n) break;
+        const size_t i1 = std::min(n, i0 + 64);
+        for (size_t i = i0; i < i1; ++i) work(i);
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(run);
+    run();
+    for (auto& t : th) t.join();
+  }
+  template <class F>
+  void for_each(size_t n, const F& f) { parallel(n, [&](size_t i) { f(i); }); }
+  // one "warp" per instance: phases run lane by lane (lanes own disjoint outputs within a phase)
+  template <class D>
+  void solve(size_t n_inst, int ws_doubles, const D& desc) {
+    parallel(n_inst, [&](size_t inst) {
+      tg::SolveInst I;
+      if (!desc.instance(inst, I)) return;
+      std::vector<double> ws((size_t)ws_doubles);
+      tg::solve_ws_bind(I, ws.data());
+      const int nph = tg::solve_num_phases(I);
+      for (int ph = 0; ph < nph; ++ph)
+        for (int lane = 0; lane < 32; ++lane) tg::solve_phase(I, ph, lane);
+    });
+  }
+  void exclusive_scan(const int* in, int* out, int n) {
+    int acc = 0;
+    for (int i = 0; i < n; ++i) {
+      out[i] = acc;
+      acc += in[i];
+    }
+    out[n] = acc;
+  }
+};
+
+#define TG_BACKEND EmuBackend
+#include "../../mrs_uav_trajectory_generation_b200/csrc/tg_capi_impl.hpp"
