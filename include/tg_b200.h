@@ -83,9 +83,12 @@ void tg_default_params(tg_params* p);
 int tg_ctx_create(int device, tg_ctx** out);
 void tg_ctx_destroy(tg_ctx* ctx);
 const char* tg_last_error(const tg_ctx* ctx);
-/* counters[8]: kernel launches, linear solves, objective evaluations, root finds, segment setups, samples, 0, 0
- * (cumulative since the context was created). */
+/* counters[8]: kernel launches, linear solves, objective evaluations, root finds, segment setups, samples,
+ * solves inside the time-allocation loop, launches of that solve kernel (cumulative since the context was created). */
 int tg_get_counters(const tg_ctx* ctx, long long* counters);
+/* flops[4]: ALGORITHMIC flops (SURVEY.md 8(d) formula) of the launched work: solve kernels, segment-setup
+ * kernels, sampling, 0 -- the numerators of the roofline report. */
+int tg_get_flop_counters(const tg_ctx* ctx, double* flops);
 /* Milliseconds of device time (CUDA events on the context's stream) spent inside the last batch call. */
 double tg_last_device_ms(const tg_ctx* ctx);
 
@@ -136,6 +139,15 @@ int tg_scale_times_batch(tg_ctx* ctx, int B, const int* seg_off, double* coef, d
  *   costs (optional) [K] host; best_index / best_cost = argmin (first minimum). */
 int tg_sweep_costs(tg_ctx* ctx, int V, const uint8_t* vmask, const double* vval, int r, long long K, const double* cand,
                    int cand_on_device, double* costs, long long* best_index, double* best_cost);
+
+/* Measurement hooks (bench.py) ------------------------------------------------------------------------------------------
+ * tg_set_profiling: when on, every kernel launch is bracketed by CUDA events on the context's stream and accumulated
+ *   per kernel (serialises the host; never enabled inside a timed region).  tg_get_profile returns the table.
+ * tg_measure_fp64_peak: TFLOP/s of the FP64 pipe; mode 0 = DFMA chains, mode 1 = DMUL+DADD (the -fmad=false mix the
+ *   product kernels issue).  This is the roofline denominator for this path. */
+int tg_set_profiling(tg_ctx* ctx, int on);
+int tg_get_profile(tg_ctx* ctx, int cap, char* names, int names_cap, double* ms, long long* launches, long long* items);
+double tg_measure_fp64_peak(tg_ctx* ctx, int mode);
 
 /* Host-side evaluation of the deterministic math layer (include/tg_detmath.h), for tests:
  *   fn 0 log, 1 exp, 2 sin, 3 cos, 4 atan2(x, y), 5 cbrt, 6 pow(x, (int)y). */

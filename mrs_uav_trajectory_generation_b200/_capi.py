@@ -108,6 +108,7 @@ class Library:
         L.tg_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.tg_ctx_destroy.argtypes = [C.c_void_p]
         L.tg_get_counters.argtypes = [C.c_void_p, _llp]
+        L.tg_get_flop_counters.argtypes = [C.c_void_p, _dp]
         L.tg_optimize_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _u8p, _dp, C.POINTER(Params), C.c_int, C.c_void_p, _llp]
         L.tg_fetch_outputs.argtypes = [C.c_void_p, _ip, _dp, _dp, _dp, _ip, _dp]
         L.tg_solve_linear_batch.argtypes = [C.c_void_p, C.c_int, _ip, _u8p, _dp, _dp, C.c_int, _dp, _dp]
@@ -117,6 +118,10 @@ class Library:
         L.tg_scale_times_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp, _ip, _u8p]
         L.tg_sweep_costs.argtypes = [C.c_void_p, C.c_int, _u8p, _dp, C.c_int, C.c_longlong, _dp, C.c_int, _dp, _llp, _dp]
         L.tg_default_params.argtypes = [C.POINTER(Params)]
+        L.tg_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.tg_get_profile.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, _dp, _llp, _llp]
+        L.tg_measure_fp64_peak.restype = C.c_double
+        L.tg_measure_fp64_peak.argtypes = [C.c_void_p, C.c_int]
 
     def version(self):
         return self.lib.tg_version().decode()
@@ -166,7 +171,36 @@ class Context:
     def counters(self):
         c = (C.c_longlong * 8)()
         self.L.lib.tg_get_counters(self.h, c)
-        return dict(launches=c[0], solves=c[1], evals=c[2], root_finds=c[3], segment_setups=c[4], samples=c[5])
+        f = (C.c_double * 4)()
+        self.L.lib.tg_get_flop_counters(self.h, f)
+        return dict(launches=c[0], solves=c[1], evals=c[2], root_finds=c[3], segment_setups=c[4], samples=c[5],
+                    mellinger_solves=c[6], mellinger_launches=c[7], flops_solve=f[0], flops_setup=f[1], flops_sample=f[2])
+
+    def set_profiling(self, on):
+        self.L.lib.tg_set_profiling(self.h, 1 if on else 0)
+
+    def profile(self):
+        """Per-kernel device time since profiling was switched on: {kernel: (ms, launches, items)}."""
+        import subprocess
+
+        cap = 64
+        names = C.create_string_buffer(1 << 16)
+        ms = (C.c_double * cap)()
+        ln = (C.c_longlong * cap)()
+        it = (C.c_longlong * cap)()
+        n = self.L.lib.tg_get_profile(self.h, cap, names, len(names), ms, ln, it)
+        out = {}
+        mangled = names.value.decode().split("\n")[:max(n, 0)]
+        for i, m in enumerate(mangled):
+            try:
+                nm = subprocess.run(["c++filt", "-t", m], capture_output=True, text=True).stdout.strip() or m
+            except Exception:
+                nm = m
+            out[nm.replace("tg::", "")] = (ms[i], ln[i], it[i])
+        return out
+
+    def fp64_peak_tflops(self, mode=1):
+        return self.L.lib.tg_measure_fp64_peak(self.h, int(mode))
 
     def last_device_ms(self):
         return self.L.lib.tg_last_device_ms(self.h)

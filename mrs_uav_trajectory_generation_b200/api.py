@@ -1,0 +1,273 @@
+"""Host-side mirror of the reference's interface for the hot path (names, argument meaning and error behaviour follow
+the C++ classes of include/eth_trajectory_generation/*.h), implemented on the C ABI of libtg_b200.so.
+
+The reference API is one-object-per-problem; every class here also accepts batches because the GPU path is batched
+(SURVEY.md H7).  The C++ shim with the same class names is include/eth_trajectory_generation_b200.hpp.
+"""
+import numpy as np
+
+from ._capi import Context, Library, N, D, HALF
+
+
+class derivative_order:  # eth/motion_defines.h
+    POSITION, VELOCITY, ACCELERATION, JERK, SNAP = 0, 1, 2, 3, 4
+    INVALID = -1
+
+
+_default_ctx = None
+
+
+def default_context():
+    """Lazily created process-wide context on device 0 (fails loudly without a GPU)."""
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(Library(), 0)
+    return _default_ctx
+
+
+class Vertex:
+    """eth_trajectory_generation::Vertex (eth/vertex.h:42-116): derivative -> D-vector constraints."""
+
+    def __init__(self, dimension=D):
+        if dimension != D:
+            raise ValueError("the B200 path is built for D = 4 (x, y, z, heading) like the node (node.cpp:902)")
+        self.D = dimension
+        self.constraints = {}
+
+    def addConstraint(self, derivative, value):  # eth/vertex.cpp:134-137
+        v = np.asarray(value, dtype=np.float64).reshape(-1)
+        if v.shape[0] != self.D:
+            raise ValueError("constraint dimension mismatch")
+        self.constraints[int(derivative)] = v.copy()
+
+    def makeStartOrEnd(self, value, up_to_derivative):  # eth/vertex.cpp:158-163
+        self.addConstraint(derivative_order.POSITION, value)
+        for i in range(1, up_to_derivative + 1):
+            self.constraints[i] = np.zeros(self.D)
+
+    def removeConstraint(self, derivative):
+        return self.constraints.pop(int(derivative), None) is not None
+
+    def hasConstraint(self, derivative):
+        return int(derivative) in self.constraints
+
+    def getConstraint(self, derivative):
+        return self.constraints.get(int(derivative))
+
+    def mask_and_values(self):
+        """Constraints with derivative > 4 are dropped, as setupFromVertices does (lin_impl.h:84-102)."""
+        m = 0
+        vals = np.zeros((HALF, D))
+        for k, v in self.constraints.items():
+            if 0 <= k < HALF:
+                m |= 1 << k
+                vals[k] = v
+        return m, vals
+
+
+def pack_vertices(vertex_lists):
+    vtx_off = [0]
+    masks, vals = [], []
+    for vl in vertex_lists:
+        for v in vl:
+            m, x = v.mask_and_values()
+            masks.append(m)
+            vals.append(x)
+        vtx_off.append(len(masks))
+    return np.array(vtx_off, dtype=np.int32), np.array(masks, dtype=np.uint8), np.array(vals, dtype=np.float64)
+
+
+class Trajectory:
+    """eth_trajectory_generation::Trajectory (eth/trajectory.h): segments = (coefficients [S,4,10], times [S])."""
+
+    def __init__(self, coef=None, times=None, ctx=None):
+        self.coef = None if coef is None else np.ascontiguousarray(coef, dtype=np.float64)
+        self.times = None if times is None else np.ascontiguousarray(times, dtype=np.float64)
+        self._ctx = ctx
+
+    def _c(self):
+        return self._ctx or default_context()
+
+    def K(self):
+        return 0 if self.times is None else len(self.times)
+
+    def getMinTime(self):
+        return 0.0
+
+    def getMaxTime(self):  # eth/trajectory.h:76-83: accumulated in segment order
+        t = 0.0
+        for x in self.times:
+            t += float(x)
+        return t
+
+    def getSegmentTimes(self):
+        return self.times.copy()
+
+    def evaluate(self, t, derivative=derivative_order.POSITION):
+        """Trajectory::evaluate (eth/trajectory.cpp:55-87); t may be an array.  Past-the-end queries return zeros."""
+        out, ok = self._c().evaluate(self.coef, self.times, t, derivative)
+        return out[0] if np.isscalar(t) else out
+
+    def computeMaxDerivatives(self):
+        """Per-segment maxima [S, 9] = hor v,a,j ; ver v,a,j ; heading v,a,j (eth/trajectory.cpp:422-565)."""
+        return self._c().extrema(self.coef, self.times)
+
+    def scaleSegmentTimesToMeetConstraints(self, limits9):
+        """eth/trajectory.cpp:598-692, in place; returns within_range."""
+        seg_off = np.array([0, len(self.times)], dtype=np.int32)
+        self.coef, self.times, _, within = self._c().scale_times(seg_off, self.coef, self.times, limits9)
+        return bool(within[0])
+
+
+def sample_whole_trajectory(trajectory, dt, full=False, ctx=None):
+    """eth_trajectory_generation::sampleWholeTrajectory (eth/trajectory_sampling.cpp:119-124).
+    Returns samples [M, 4] (x, y, z, heading) or, with full=True, [M, 19] = p4 v4 a4 j3 s3 yaw."""
+    c = ctx or trajectory._c()
+    seg_off = np.array([0, trajectory.K()], dtype=np.int32)
+    counts, samples, fullv = c.sample_batch(seg_off, trajectory.coef, trajectory.times, dt, full=full)
+    return fullv if full else samples
+
+
+class PolynomialOptimization:
+    """eth_trajectory_generation::PolynomialOptimization<10> (lin.h:60-233) for one problem or a batch."""
+
+    N = N
+
+    def __init__(self, dimension=D, ctx=None):
+        if dimension != D:
+            raise ValueError("D = 4 only")
+        self._ctx = ctx
+        self._lists = None
+        self.derivative_to_optimize = derivative_order.INVALID
+        self.coef = self.cost = None
+
+    def _c(self):
+        return self._ctx or default_context()
+
+    def setupFromVertices(self, vertices, times, derivative_to_optimize):  # lin_impl.h:61-106
+        if not (0 <= derivative_to_optimize <= 4):
+            print("You tried to optimize a derivative that is not possible")  # CHECK prints and continues (eth/misc.h)
+            return False
+        single = len(vertices) > 0 and isinstance(vertices[0], Vertex)
+        self._lists = [vertices] if single else list(vertices)
+        self._times = [np.asarray(times, dtype=np.float64)] if single else [np.asarray(t, dtype=np.float64) for t in times]
+        for vl, t in zip(self._lists, self._times):
+            if len(vl) != len(t) + 1:
+                print("Size of times must be one less than positions.")
+                return False
+        self.derivative_to_optimize = derivative_to_optimize
+        self._single = single
+        return True
+
+    def updateSegmentTimes(self, times):  # lin_impl.h:288-304
+        self._times = [np.asarray(times, dtype=np.float64)] if self._single else [np.asarray(t, dtype=np.float64) for t in times]
+
+    def solveLinear(self):  # lin_impl.h:340-373
+        vtx_off, masks, vals = pack_vertices(self._lists)
+        self._seg_off = vtx_off - np.arange(len(vtx_off), dtype=np.int32)
+        self.coef, self.cost = self._c().solve_linear_batch(vtx_off, masks, vals, np.concatenate(self._times),
+                                                            max(2, self.derivative_to_optimize))
+        return True
+
+    def computeCost(self):  # lin_impl.h:127-141
+        return float(self.cost[0]) if self._single else self.cost.copy()
+
+    def getSegmentTimes(self):
+        return self._times[0].copy() if self._single else [t.copy() for t in self._times]
+
+    def getTrajectory(self, index=0):  # lin.h:153-160
+        s0, s1 = self._seg_off[index], self._seg_off[index + 1]
+        return Trajectory(self.coef[s0:s1], self._times[index], self._ctx)
+
+    def getSegments(self, index=0):  # lin.h:177
+        t = self.getTrajectory(index)
+        return t.coef, t.times
+
+
+class NonlinearOptimizationParameters:
+    """nl.h:35-110 (the fields the Mellinger path reads)."""
+
+    def __init__(self):
+        self.f_rel = 0.05
+        self.x_rel = 0.1
+        self.max_iterations = 10
+        self.time_alloc_method = 2  # kMellingerOuterLoop
+
+
+class PolynomialOptimizationNonLinear:
+    """eth_trajectory_generation::PolynomialOptimizationNonLinear<10> (nl.h:147-197), Mellinger outer loop."""
+
+    def __init__(self, dimension=D, parameters=None, ctx=None):
+        self.params = parameters or NonlinearOptimizationParameters()
+        self._gen = TrajectoryGenerator(ctx=ctx)
+        self._limits = [None] * 9
+
+    def setupFromWaypoints(self, waypoints, initial_state=None, derivative_to_optimize=2):
+        """The node builds the vertices from waypoints (node.cpp:923-977); the batched kernel does the same on device."""
+        self._wp = np.asarray(waypoints, dtype=np.float64)
+        self._init = initial_state
+        self._r = derivative_to_optimize
+        return True
+
+    def addMaximumMagnitudeConstraint(self, dimension, derivative, maximum_value):  # nl_impl.h:538-565, mapping 355-381
+        if derivative not in (1, 2, 3) or dimension not in (0, 1, 2, 3):
+            return False
+        group = 0 if dimension <= 1 else (1 if dimension == 2 else 2)
+        idx = {(0, 1): 0, (1, 1): 1, (0, 2): 2, (1, 2): 3, (0, 3): 4, (1, 3): 5, (2, 1): 6, (2, 2): 7, (2, 3): 8}[(group, derivative)]
+        self._limits[idx] = float(maximum_value)
+        return True
+
+    def optimize(self):  # nl_impl.h:89-118 -> returns the nlopt-style code
+        p = self._gen.params(derivative_to_optimize=self._r, max_evals=self.params.max_iterations, f_rel=self.params.f_rel,
+                             x_rel=self.params.x_rel, check_deviation=0,
+                             limits=[l if l is not None else 3.4028234663852886e38 for l in self._limits])
+        self.result = self._gen.optimize([self._wp], initial_states=None if self._init is None else [self._init], params=p)
+        return int(self.result.results["nlopt_code"][0])
+
+    def getTrajectory(self):
+        return self.result.trajectory(0)
+
+
+class BatchResult:
+    def __init__(self, results, out):
+        self.results = results
+        self.out = out
+
+    def trajectory(self, p):
+        s0, s1 = self.out["seg_off"][p], self.out["seg_off"][p + 1]
+        return Trajectory(self.out["coef"][s0:s1], self.out["times"][s0:s1])
+
+    def samples(self, p):
+        m0, m1 = self.out["smp_off"][p], self.out["smp_off"][p + 1]
+        return self.out["samples"][m0:m1]
+
+    def waypoints(self, p):
+        s0, s1 = self.out["seg_off"][p], self.out["seg_off"][p + 1]
+        return self.out["wp"][s0 + p: s1 + p + 1]
+
+
+class TrajectoryGenerator:
+    """The numeric core of MrsTrajectoryGeneration::optimize() / findTrajectory() (node.cpp:620-851, 857-1209) for batches."""
+
+    def __init__(self, ctx=None, device=0):
+        self.ctx = ctx or (default_context() if device == 0 else Context(Library(), device))
+
+    def params(self, **kw):
+        return self.ctx.L.default_params(**kw)
+
+    def optimize(self, paths, stop_at=None, initial_states=None, params=None):
+        """paths: list of [V_p, 4] arrays.  initial_states: optional list of 14-vectors (workloads.init14)."""
+        wp_off = np.zeros(len(paths) + 1, dtype=np.int32)
+        wp_off[1:] = np.cumsum([len(p) for p in paths])
+        wp = np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 4) for p in paths])
+        stop = None if stop_at is None else np.concatenate([np.asarray(s, dtype=np.uint8) for s in stop_at])
+        init = None if initial_states is None else np.stack([np.asarray(i, dtype=np.float64) for i in initial_states])
+        res, _ = self.ctx.optimize_batch(wp_off, wp, stop, init, params)
+        return BatchResult(res, self.ctx.fetch_outputs())
+
+    def findTrajectory(self, waypoints, initial_state=None, params=None):
+        """One findTrajectory pass without the deviation loop (node.cpp:857-1209)."""
+        p = params or self.params()
+        p.check_deviation = 0
+        r = self.optimize([waypoints], initial_states=None if initial_state is None else [initial_state], params=p)
+        return r.samples(0) if r.results["success"][0] else None

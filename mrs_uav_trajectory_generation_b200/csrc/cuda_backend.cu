@@ -1,0 +1,295 @@
+// cuda_backend.cu -- the CUDA side of libtg_b200.so: kernels wrapping the functors of tg_kernels.cuh, the CudaBackend
+// used by tg_pipeline.hpp, and (through tg_capi_impl.hpp) the C ABI of include/tg_b200.h.
+// Build: nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false (see build.py).
+// -fmad=false is part of the numeric contract: the reference is built for baseline x86-64 (no FMA contraction,
+// CMakeLists.txt:4-12) and 1e-9 coefficient parity needs the same roundings.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_scan.cuh>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <typeinfo>
+
+#define TG_VERSION_STRING "tg_b200 0.1.0 (sm_100a, fp64, -fmad=false)"
+
+#include "tg_kernels.cuh"
+
+namespace {
+
+#define TG_CUDA_CHECK(expr)                                                                              \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e__));                     \
+  } while (0)
+
+// one thread per work item
+template <class F>
+__global__ void __launch_bounds__(128) k_for_each(const F f, const size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f(i);
+}
+
+// one warp per solve instance, grid-stride over instances; the per-warp workspace lives in dynamic shared memory
+// (or in a global slab when it does not fit).  Phases are separated by __syncwarp() (see tg_solve.cuh).
+constexpr int kSolveWarps = 4;
+template <class D>
+__global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const size_t n_inst, const int ws_doubles, double* __restrict__ gws) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t gw = (size_t)blockIdx.x * kSolveWarps + warp, nw = (size_t)gridDim.x * kSolveWarps;
+  double* ws = gws ? gws + gw * (size_t)ws_doubles : smem + (size_t)warp * ws_doubles;
+  for (size_t inst = gw; inst < n_inst; inst += nw) {
+    tg::SolveInst I;
+    if (!desc.instance(inst, I)) continue;  // warp-uniform
+    tg::solve_ws_bind(I, ws);
+    const int nph = tg::solve_num_phases(I);
+    for (int ph = 0; ph < nph; ++ph) {
+      tg::solve_phase(I, ph, lane);
+      __syncwarp();
+    }
+  }
+}
+
+
+// FP64 pipe peak probes (the roofline denominator for this path; MEASURED_PEAKS.json has HBM and bf16 only).
+// mode 0: DFMA chains; mode 1: DMUL+DADD pairs as generated under -fmad=false (what the product kernels issue).
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, int mode) {
+  double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3, a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3,
+         a7 = a0 + 7e-3;
+  const double m = 1.0 - 1e-12, c = 1e-13;
+  if (mode == 0) {
+    for (int i = 0; i < iters; ++i) {
+      a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+      a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+    }
+  } else {
+    for (int i = 0; i < iters; ++i) {
+      a0 = __dadd_rn(__dmul_rn(a0, m), c); a1 = __dadd_rn(__dmul_rn(a1, m), c); a2 = __dadd_rn(__dmul_rn(a2, m), c);
+      a3 = __dadd_rn(__dmul_rn(a3, m), c); a4 = __dadd_rn(__dmul_rn(a4, m), c); a5 = __dadd_rn(__dmul_rn(a5, m), c);
+      a6 = __dadd_rn(__dmul_rn(a6, m), c); a7 = __dadd_rn(__dmul_rn(a7, m), c);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace
+
+struct CudaBackend {
+  int device = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  void* scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
+  double* solve_slab = nullptr;
+  size_t solve_slab_doubles = 0;
+  // optional per-kernel timing (bench.py roofline leg): events around every launch, accumulated per functor type
+  bool profiling = false;
+  cudaEvent_t pev0 = nullptr, pev1 = nullptr;
+  struct ProfEntry { double ms = 0; long long launches = 0; long long items = 0; };
+  std::map<std::string, ProfEntry> prof;
+
+  explicit CudaBackend(int dev) : device(dev) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) throw std::runtime_error("no CUDA device available (libtg_b200 has no CPU fallback)");
+    if (dev < 0 || dev >= n) throw std::runtime_error("CUDA device index out of range");
+    TG_CUDA_CHECK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    TG_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    sm_count = prop.multiProcessorCount;
+    smem_optin = prop.sharedMemPerBlockOptin;
+    TG_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    TG_CUDA_CHECK(cudaEventCreate(&ev0));
+    TG_CUDA_CHECK(cudaEventCreate(&ev1));
+    TG_CUDA_CHECK(cudaEventCreate(&pev0));
+    TG_CUDA_CHECK(cudaEventCreate(&pev1));
+  }
+  ~CudaBackend() {
+    cudaSetDevice(device);
+    if (scan_tmp) cudaFree(scan_tmp);
+    if (solve_slab) cudaFree(solve_slab);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (pev0) cudaEventDestroy(pev0);
+    if (pev1) cudaEventDestroy(pev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+  CudaBackend(const CudaBackend&) = delete;
+  CudaBackend& operator=(const CudaBackend&) = delete;
+
+  void bind() { TG_CUDA_CHECK(cudaSetDevice(device)); }
+  void* dev_alloc(size_t n) {
+    bind();
+    void* p = nullptr;
+    TG_CUDA_CHECK(cudaMalloc(&p, n));
+    return p;
+  }
+  void dev_free(void* p) {
+    cudaSetDevice(device);
+    cudaFree(p);
+  }
+  void h2d(void* d, const void* s, size_t n) {
+    if (n) TG_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream));
+  }
+  void d2h(void* d, const void* s, size_t n) {
+    if (n) TG_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream));
+    TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+  }
+  void d2d(void* d, const void* s, size_t n) {
+    if (n) TG_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream));
+  }
+  void dev_memset(void* d, int v, size_t n) {
+    if (n) TG_CUDA_CHECK(cudaMemsetAsync(d, v, n, stream));
+  }
+  void sync() { TG_CUDA_CHECK(cudaStreamSynchronize(stream)); }
+  void timer_start() {
+    bind();
+    TG_CUDA_CHECK(cudaEventRecord(ev0, stream));
+  }
+  double timer_stop() {
+    TG_CUDA_CHECK(cudaEventRecord(ev1, stream));
+    TG_CUDA_CHECK(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    TG_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+    return (double)ms;
+  }
+
+  template <class F>
+  void for_each(size_t n, const F& f) {
+    if (n == 0) return;
+    const unsigned block = 128;
+    const size_t grid = (n + block - 1) / block;
+    prof_begin();
+    k_for_each<F><<<(unsigned)grid, block, 0, stream>>>(f, n);
+    TG_CUDA_CHECK(cudaGetLastError());
+    prof_end(typeid(F).name(), n);
+  }
+  void prof_begin() {
+    if (profiling) TG_CUDA_CHECK(cudaEventRecord(pev0, stream));
+  }
+  void prof_end(const char* name, size_t items) {
+    if (!profiling) return;
+    TG_CUDA_CHECK(cudaEventRecord(pev1, stream));
+    TG_CUDA_CHECK(cudaEventSynchronize(pev1));
+    float ms = 0.f;
+    TG_CUDA_CHECK(cudaEventElapsedTime(&ms, pev0, pev1));
+    ProfEntry& e = prof[name];
+    e.ms += ms;
+    e.launches += 1;
+    e.items += (long long)items;
+  }
+  // TFLOP/s of the FP64 pipe: mode 0 DFMA (2 flop), mode 1 DMUL+DADD (2 flop in two instructions)
+  double fp64_peak_tflops(int mode) {
+    bind();
+    const int blocks = sm_count * 16, threads = 256, iters = 1 << 14;
+    double* out = nullptr;
+    TG_CUDA_CHECK(cudaMalloc(&out, sizeof(double) * (size_t)blocks * threads));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+      TG_CUDA_CHECK(cudaEventRecord(pev0, stream));
+      k_fp64_peak<<<blocks, threads, 0, stream>>>(out, iters, mode);
+      TG_CUDA_CHECK(cudaEventRecord(pev1, stream));
+      TG_CUDA_CHECK(cudaEventSynchronize(pev1));
+      float ms = 0.f;
+      TG_CUDA_CHECK(cudaEventElapsedTime(&ms, pev0, pev1));
+      const double flop = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+      if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaFree(out);
+    return best;
+  }
+
+  template <class D>
+  void solve(size_t n_inst, int ws_doubles, const D& desc) {
+    if (n_inst == 0) return;
+    const size_t ws_bytes = (size_t)ws_doubles * sizeof(double);
+    const size_t smem = ws_bytes * kSolveWarps;
+    const size_t blocks_needed = (n_inst + kSolveWarps - 1) / kSolveWarps;
+    prof_begin();
+    if (smem <= smem_optin) {
+      TG_CUDA_CHECK(cudaFuncSetAttribute(k_solve<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve<D>, kSolveWarps * 32, smem));
+      if (per_sm < 1) per_sm = 1;
+      const size_t grid = std::min(blocks_needed, (size_t)sm_count * per_sm);
+      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, smem, stream>>>(desc, n_inst, ws_doubles, nullptr);
+    } else {
+      // long paths: per-warp workspace in a global slab (L2 resident), persistent grid
+      const size_t grid = std::min(blocks_needed, (size_t)sm_count * 8);
+      const size_t need = grid * kSolveWarps * (size_t)ws_doubles;
+      if (need > solve_slab_doubles) {
+        if (solve_slab) {
+          TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+          TG_CUDA_CHECK(cudaFree(solve_slab));
+        }
+        TG_CUDA_CHECK(cudaMalloc(&solve_slab, need * sizeof(double)));
+        solve_slab_doubles = need;
+      }
+      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, 0, stream>>>(desc, n_inst, ws_doubles, solve_slab);
+    }
+    TG_CUDA_CHECK(cudaGetLastError());
+    prof_end(typeid(D).name(), n_inst);
+  }
+
+  // out[0..n] = exclusive prefix sums of in[0..n-1], out[n] = total.  `in` must have n+1 elements.
+  void exclusive_scan(int* in, int* out, int n) {
+    TG_CUDA_CHECK(cudaMemsetAsync(in + n, 0, sizeof(int), stream));
+    size_t bytes = 0;
+    TG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n + 1, stream));
+    if (bytes > scan_tmp_bytes) {
+      if (scan_tmp) {
+        TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        TG_CUDA_CHECK(cudaFree(scan_tmp));
+      }
+      TG_CUDA_CHECK(cudaMalloc(&scan_tmp, bytes));
+      scan_tmp_bytes = bytes;
+    }
+    TG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(scan_tmp, bytes, in, out, n + 1, stream));
+  }
+};
+
+#define TG_BACKEND CudaBackend
+#include "tg_capi_impl.hpp"
+
+// ---- CUDA-only entry points (declared in include/tg_b200.h) ------------------------------------------------------------
+extern "C" {
+
+int tg_set_profiling(tg_ctx* ctx, int on) {
+  if (!ctx) return TG_ERR_INVALID;
+  ctx->be.profiling = on != 0;
+  ctx->be.prof.clear();
+  return TG_OK;
+}
+
+// Writes up to `cap` entries: names as a '\n'-separated list into `names` (size names_cap), ms / launches / items arrays.
+int tg_get_profile(tg_ctx* ctx, int cap, char* names, int names_cap, double* ms, long long* launches, long long* items) {
+  if (!ctx || !names || !ms || !launches || !items) return TG_ERR_INVALID;
+  int n = 0;
+  std::string all;
+  for (const auto& kv : ctx->be.prof) {
+    if (n >= cap) break;
+    all += kv.first;
+    all += "\n";
+    ms[n] = kv.second.ms;
+    launches[n] = kv.second.launches;
+    items[n] = kv.second.items;
+    ++n;
+  }
+  if ((int)all.size() + 1 > names_cap) return TG_ERR_INVALID;
+  std::memcpy(names, all.c_str(), all.size() + 1);
+  return n;
+}
+
+double tg_measure_fp64_peak(tg_ctx* ctx, int mode) {
+  if (!ctx) return 0.0;
+  try {
+    return ctx->be.fp64_peak_tflops(mode);
+  } catch (...) {
+    return 0.0;
+  }
+}
+
+}  // extern "C"

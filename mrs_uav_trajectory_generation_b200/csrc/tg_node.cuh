@@ -14,7 +14,7 @@ namespace tg {
 TG_HD double dfmod(double x, double y) {
   // exact IEEE remainder with the sign of x, by long division on the exponent difference (|x/y| small here)
   const double ax = dabs(x), ay = dabs(y);
-  if (!(ay > 0.0) || !dfinite(x)) return x * 0.0 / 0.0;
+  if (!(ay > 0.0) || !dfinite(x)) return tgdm::bitsd(0x7ff8000000000000LL);
   if (ax < ay) return x;
   double r = ax;
   // subtract y * 2^k from the top; each subtraction is exact because r and y*2^k share an exponent window

@@ -95,6 +95,9 @@ struct Group {
 
 struct Counters {
   long long launches = 0, solves = 0, evals = 0, root_finds = 0, segment_setups = 0, samples = 0;
+  // algorithmic flops (SURVEY.md 8(d) formula) of the work actually launched, per kernel family
+  double flops_solve = 0, flops_setup = 0, flops_sample = 0;
+  long long mellinger_solves = 0, mellinger_launches = 0;
 };
 
 template <class BE>
@@ -199,12 +202,26 @@ class Pipeline {
     launches(4);
     g.ps.resize(B);
     be_.d2h(g.ps.data(), g.d_ps, sizeof(ProbState) * B);
+    std::vector<int> h_np(B), h_hbw(B);
+    be_.d2h(h_np.data(), b.np, sizeof(int) * B);
+    be_.d2h(h_hbw.data(), b.hbw, sizeof(int) * B);
+    if (P.run_time_alloc) counters.mellinger_launches += P.max_evals;
     for (int p = 0; p < B; ++p) {
       const int S = g.seg_off[p + 1] - g.seg_off[p];
       const int ev = g.ps[p].n_evals;
+      const long long nsolve = (long long)ev * (S == 1 ? 1 : S + 1) + 1;
+      const long long nsetup = (long long)ev * S * (S == 1 ? 1 : 3) + S;
+      const double np_ = h_np[p], bw = h_hbw[p];
+      const double f_solve = np_ * (bw * bw + 3.0 * bw) + 4.0 * (2.0 * np_ * 15.0 + 4.0 * np_ * bw + S * 200.0 + S * 220.0);
+      const double nq = TG_N - P.derivative_to_optimize;
+      const double f_setup = 3.0 * nq * nq + 525.0 + 4.0 * TG_N * TG_N * TG_N;
+      counters.flops_solve += f_solve * (double)nsolve;
+      counters.flops_setup += f_setup * (double)nsetup;
+      counters.flops_sample += 340.0 * g.ps[p].n_samples;
+      counters.mellinger_solves += nsolve - 1;
       counters.evals += ev;
-      counters.solves += (long long)ev * (S == 1 ? 1 : S + 1) + 1;
-      counters.segment_setups += (long long)ev * S * (S == 1 ? 1 : 3) + S;
+      counters.solves += nsolve;
+      counters.segment_setups += nsetup;
       counters.root_finds += (long long)(P.run_time_alloc ? (g.ps[p].n_scale_passes + 1) * 9 * S : 0);
       counters.samples += g.ps[p].n_samples;
     }

@@ -32,6 +32,7 @@ struct EmuBackend {
   void d2d(void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
   void dev_memset(void* d, int v, size_t n) { std::memset(d, v, n); }
   void sync() {}
+  void bind() {}
   void timer_start() {}
   double timer_stop() { return 0.0; }
 
@@ -84,3 +85,13 @@ struct EmuBackend {
 
 #define TG_BACKEND EmuBackend
 #include "../../mrs_uav_trajectory_generation_b200/csrc/tg_capi_impl.hpp"
+
+// measurement hooks exist only in the CUDA build; stubs keep the exported symbol set identical
+extern "C" {
+int tg_set_profiling(tg_ctx*, int) { return TG_OK; }
+int tg_get_profile(tg_ctx*, int, char* names, int names_cap, double*, long long*, long long*) {
+  if (names && names_cap > 0) names[0] = 0;
+  return 0;
+}
+double tg_measure_fp64_peak(tg_ctx*, int) { return 0.0; }
+}

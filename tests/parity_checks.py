@@ -1,0 +1,272 @@
+"""Parity checks shared by the CPU-emulation tests (tests/test_emu_parity.py, `-m "not gpu"`) and the GPU tests
+(tests/test_gpu_parity.py, `-m gpu`).  Each check runs the SAME inputs through the product's C ABI (`ctx`) and through
+the oracle (CPU restatement of the reference, deterministic-math mode) and compares.
+
+Tolerances (BASELINE.json north_star): coefficients 1e-9 relative, sampled positions 1e-6 m, feasibility verdicts,
+subdivision counts, segment counts and sample indices exact.  Because both sides follow one numeric contract
+ the observed differences are 0; the asserts use the stated tolerances and the tests also report
+whether the match was bit-exact.
+"""
+import numpy as np
+
+import oracle_lib as O
+from mrs_uav_trajectory_generation_b200 import workloads as W
+
+COEF_RTOL = 1e-9     # north_star: coefficients within 1e-9 relative
+SAMPLE_ATOL = 1e-6   # north_star: sampled positions within 1e-6 m
+
+
+def coef_rel_err(c, ref, times):
+    """max_k |dc_k| T^k / max_k |c_k| T^k per (segment, dimension) -- SURVEY.md H1's definition of 'relative'."""
+    c = np.asarray(c)
+    ref = np.asarray(ref)
+    T = np.asarray(times)[:, None, None]
+    w = T ** np.arange(c.shape[-1])[None, None, :]
+    num = (np.abs(c - ref) * w).max(axis=-1)
+    den = (np.abs(ref) * w).max(axis=-1)
+    den = np.where(den > 0, den, 1.0)
+    return float((num / den).max()) if c.size else 0.0
+
+
+def random_linear_problem(rng, V, kind=0):
+    wp = np.cumsum(rng.uniform(-2, 2, (V, 4)), axis=0)
+    m = np.ones(V, np.uint8)
+    m[0] = 7
+    m[-1] = 7
+    v = np.zeros((V, 5, 4))
+    v[:, 0, :] = wp
+    if kind == 1:  # initial state present: start fixes p, v, a, j with non-zero values
+        m[0] = 15
+        v[0, 1:4, :] = rng.uniform(-1, 1, (3, 4))
+    if kind == 2 and V > 3:  # a stop_at waypoint in the middle
+        m[V // 2] = 15
+    if kind == 3:  # min-snap recipe: ends fix 0..4
+        m[0] = 31
+        m[-1] = 31
+    if kind == 4:  # generic: a vertex with velocity fixed, one with nothing but position
+        m[1] = 3
+        v[1, 1, :] = rng.uniform(-1, 1, 4)
+    if kind == 5:  # everything fixed: n_free == 0 (lin_impl.h:344-349)
+        m[:] = 31
+        v[:, 1:, :] = rng.uniform(-0.2, 0.2, (V, 4, 4))
+    t = rng.uniform(0.3, 3.0, V - 1)
+    return m, v, t
+
+
+def check_linear_batch(ctx, seed=0, B=24, r=2):
+    rng = np.random.default_rng(seed)
+    masks, vals, times, Vs = [], [], [], []
+    for p in range(B):
+        V = int(rng.integers(2, 24))
+        m, v, t = random_linear_problem(rng, V, kind=p % 6)
+        masks.append(m)
+        vals.append(v)
+        times.append(t)
+        Vs.append(V)
+    vtx_off = np.concatenate([[0], np.cumsum(Vs)]).astype(np.int32)
+    coef, cost = ctx.solve_linear_batch(vtx_off, np.concatenate(masks), np.concatenate(vals), np.concatenate(times), r)
+    worst, exact = 0.0, True
+    s0 = 0
+    for p in range(B):
+        c, co, _, _ = O.solve_linear(masks[p], vals[p], times[p], r)
+        S = Vs[p] - 1
+        mine = coef[s0:s0 + S]
+        worst = max(worst, coef_rel_err(mine, c, times[p]))
+        assert abs(cost[p] - co) <= 1e-9 * max(1.0, abs(co)), (p, cost[p], co)
+        exact = exact and np.array_equal(mine, c) and cost[p] == co
+        s0 += S
+    assert worst <= COEF_RTOL, worst
+    return worst, exact
+
+
+def check_sampling(ctx, seed=1, B=12):
+    rng = np.random.default_rng(seed)
+    coefs, times, seg_off = [], [], [0]
+    for p in range(B):
+        V = int(rng.integers(2, 16))
+        m, v, t = random_linear_problem(rng, V, kind=p % 3)
+        c, _, _, _ = O.solve_linear(m, v, t, 2)
+        coefs.append(c)
+        times.append(t)
+        seg_off.append(seg_off[-1] + V - 1)
+    dt = 0.2
+    counts, samples, full = ctx.sample_batch(np.array(seg_off, np.int32), np.concatenate(coefs), np.concatenate(times), dt, full=True)
+    m0 = 0
+    exact = True
+    for p in range(B):
+        ref, tns = O.sample(coefs[p], times[p], dt)
+        assert counts[p] == len(ref), (p, counts[p], len(ref))  # sample indices bit-exact
+        mine = full[m0:m0 + counts[p]]
+        assert np.abs(mine[:, :3] - ref[:, :3]).max() <= SAMPLE_ATOL
+        assert np.abs(mine - ref).max() <= 1e-6
+        assert np.abs(samples[m0:m0 + counts[p], 3] - ref[:, 18]).max() <= 1e-9
+        exact = exact and np.array_equal(mine, ref)
+        m0 += counts[p]
+    return exact
+
+
+def check_evaluate(ctx, seed=2):
+    rng = np.random.default_rng(seed)
+    m, v, t = random_linear_problem(rng, 9, kind=1)
+    c, _, _, _ = O.solve_linear(m, v, t, 2)
+    tq = np.concatenate([[0.0, t[0], t.sum(), t.sum() + 1.0], rng.uniform(0, t.sum(), 50)])
+    exact = True
+    for k in range(5):
+        out, ok = ctx.evaluate(c, t, tq, k)
+        for i, tt in enumerate(tq):
+            ref, rok = O.trajectory_evaluate(c, t, tt, k)
+            assert ok[i] == rok
+            assert np.abs(out[i] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
+            exact = exact and np.array_equal(out[i], ref)
+    return exact
+
+
+def check_extrema_and_scaling(ctx, seed=3, B=6):
+    rng = np.random.default_rng(seed)
+    exact = True
+    coefs, times, seg_off = [], [], [0]
+    for p in range(B):
+        V = int(rng.integers(3, 14))
+        m, v, t = random_linear_problem(rng, V, kind=p % 3)
+        t = t * 0.4  # short times -> limits are violated and scaling has work to do
+        c, _, _, _ = O.solve_linear(m, v, t, 2)
+        coefs.append(c)
+        times.append(t)
+        seg_off.append(seg_off[-1] + V - 1)
+    allc, allt = np.concatenate(coefs), np.concatenate(times)
+    mx = ctx.extrema(allc, allt)
+    ref = np.concatenate([O.segment_maxima(coefs[p], times[p]) for p in range(B)])
+    assert np.abs(mx - ref).max() <= 1e-9 * np.abs(ref).max()
+    exact = exact and np.array_equal(mx, ref)
+    c2, t2, passes, within = ctx.scale_times(np.array(seg_off, np.int32), allc, allt, O.DEFAULT_LIMITS)
+    for p in range(B):
+        rc, rt, rp, rw = O.scale_times(coefs[p], times[p])
+        s0, s1 = seg_off[p], seg_off[p + 1]
+        assert passes[p] == rp and bool(within[p]) == rw
+        assert np.allclose(t2[s0:s1], rt, rtol=1e-12, atol=0)
+        exact = exact and np.array_equal(t2[s0:s1], rt) and np.array_equal(c2[s0:s1], rc)
+        # the stretched trajectory satisfies the limits (eth/trajectory.cpp:640: within 1 + 1e-3)
+        post = ctx.extrema(c2[s0:s1], t2[s0:s1]).max(axis=0)
+        lim = np.array(O.DEFAULT_LIMITS)[[0, 2, 4, 1, 3, 5, 6, 7, 8]]
+        assert np.all(post <= lim * (1 + 1e-3) + 1e-12)
+    return exact
+
+
+def compare_optimize(ctx, wp_off, wp, stop_at=None, init=None, params_kw=None, cap_wp=1400, cap_samples=6000):
+    """Runs the full optimize() pipeline on both sides; asserts parity; returns (results, bit_exact, worst_coef_err)."""
+    params_kw = params_kw or {}
+    ref = O.optimize_batch(wp_off, wp, stop_at=stop_at, init=init, params=O.default_params(**params_kw), cap_wp=cap_wp,
+                           cap_samples=cap_samples)
+    res, totals = ctx.optimize_batch(wp_off, wp, stop_at, init, ctx.L.default_params(**params_kw))
+    out = ctx.fetch_outputs()
+    B = len(wp_off) - 1
+    exact = True
+    worst = 0.0
+    ints = ("status", "success", "nlopt_code", "n_evals", "rounds", "safe", "n_waypoints", "n_samples", "n_scale_passes",
+            "total_solves", "total_root_calls", "total_evals")
+    for p in range(B):
+        r, g = ref["res"][p], res[p]
+        assert not r.overflow
+        for k in ints:  # verdicts, subdivision counts, segment counts, sample counts: exact
+            assert getattr(r, k) == g[k], (p, k, getattr(r, k), g[k])
+        s0, s1 = out["seg_off"][p], out["seg_off"][p + 1]
+        m0, m1 = out["smp_off"][p], out["smp_off"][p + 1]
+        S = s1 - s0
+        assert S == g["n_waypoints"] - 1 and m1 - m0 == g["n_samples"]
+        if not g["success"]:
+            continue
+        rt, rc = ref["times"][p, :S], ref["coeffs"][p, :S]
+        rs, rw = ref["samples"][p, :m1 - m0], ref["wp"][p, :S + 1]
+        assert np.allclose(out["times"][s0:s1], rt, rtol=1e-12, atol=0)
+        worst = max(worst, coef_rel_err(out["coef"][s0:s1], rc, rt))
+        assert np.abs(out["samples"][m0:m1, :3] - rs[:, :3]).max() <= SAMPLE_ATOL
+        assert np.abs(out["wp"][s0 + p:s1 + p + 1] - rw).max() <= 1e-12
+        assert abs(g["max_dev"] - r.max_dev) <= 1e-9 and abs(g["final_cost"] - r.final_cost) <= 1e-9 * max(1.0, abs(r.final_cost))
+        exact = (exact and np.array_equal(out["times"][s0:s1], rt) and np.array_equal(out["coef"][s0:s1], rc)
+                 and np.array_equal(out["samples"][m0:m1], rs) and np.array_equal(out["wp"][s0 + p:s1 + p + 1], rw)
+                 and g["max_dev"] == r.max_dev and g["final_cost"] == r.final_cost and g["baca_total"] == r.baca_total)
+    assert worst <= COEF_RTOL, worst
+    return res, out, exact, worst
+
+
+def check_random_flier(ctx, B, first_index=0, **params_kw):
+    wp_off, wp = W.random_flier_paths(B, first_index=first_index)
+    return compare_optimize(ctx, wp_off, wp, params_kw=params_kw)
+
+
+def check_fixtures(ctx):
+    """F1a (the reference tests' 4-waypoint path + prepended start) and F1b (10-waypoint zig-zag)."""
+    paths = [W.F1A_WAYPOINTS, W.F1B_WAYPOINTS]
+    wp_off = np.array([0, len(paths[0]), len(paths[0]) + len(paths[1])], np.int32)
+    wp = np.concatenate(paths)
+    init = np.stack([W.init14(W.F1A_INIT_HEADING), W.init14(W.F1B_INIT_HEADING)])
+    res, out, exact, worst = compare_optimize(ctx, wp_off, wp, init=init)
+    assert res["success"].all()
+    return res, out, exact
+
+
+def check_mixed_batch(ctx, seed=5):
+    """Ragged batch: different waypoint counts, stop_at flags, initial states with non-zero derivatives, heading wraps,
+    a two-waypoint path (S = 1: Mellinger gradient is defined as zero, nl_impl.h:264-271)."""
+    rng = np.random.default_rng(seed)
+    paths, stops, inits = [], [], []
+    for p in range(14):
+        nwp = [2, 3, 5, 8, 11, 14, 20][p % 7]
+        path = W.random_flier_path(1000 + p, nwp)
+        if p % 3 == 0:
+            path[:, 3] += 5.5  # headings beyond pi: exercises sradians::unwrap / radians::interp
+        st = np.zeros(nwp, np.uint8)
+        if p % 4 == 1 and nwp > 3:
+            st[nwp // 2] = 1
+        paths.append(path)
+        stops.append(st)
+        if p % 2 == 0:
+            inits.append(W.init14(path[0, 3] + 0.3, vel=rng.uniform(-0.5, 0.5, 4), acc=rng.uniform(-0.2, 0.2, 4), jerk=rng.uniform(-0.1, 0.1, 4)))
+        else:
+            z = np.zeros(14)
+            inits.append(z)
+    wp_off = np.concatenate([[0], np.cumsum([len(p) for p in paths])]).astype(np.int32)
+    return compare_optimize(ctx, wp_off, np.concatenate(paths), stop_at=np.concatenate(stops), init=np.stack(inits))
+
+
+def check_config2(ctx, B=64, r=2):
+    """BASELINE config 2: linear solve at the Euclidean times + sampling, no time allocation, no deviation loop."""
+    wp_off, wp = W.random_flier_paths(B, first_index=5000)
+    return compare_optimize(ctx, wp_off, wp, params_kw=dict(run_time_alloc=0, check_deviation=0, derivative_to_optimize=r))
+
+
+def check_sweep(ctx, K=300, seed=7):
+    """BASELINE config 5: K candidate time vectors of one problem; best index and cost must match the oracle."""
+    rng = np.random.default_rng(seed)
+    path = W.random_flier_path(0)
+    V = len(path)
+    m = np.ones(V, np.uint8)
+    m[0] = 7
+    m[-1] = 7
+    v = np.zeros((V, 5, 4))
+    v[:, 0, :] = path
+    T0, _ = O.estimate_times(path)
+    cand = np.maximum(0.01, T0[None, :] * np.exp(rng.uniform(-0.5, 0.5, (K, V - 1))))
+    costs, bi, bc = ctx.sweep_costs(m, v, cand, r=2)
+    ref = O.sweep_costs(m, v, 2, cand)
+    assert np.allclose(costs, ref, rtol=1e-9, atol=0)
+    assert bi == int(np.argmin(ref)) and bc == ref.min()
+    return np.array_equal(costs, ref)
+
+
+def geometric_predicate(samples, waypoints, pos_tol=0.5, hdg_tol=0.2):
+    """The reference tests' acceptance check (test/include/get_path_test.h:45-68): every input waypoint is approached
+    within 0.5 m / 0.2 rad by some sample, in order."""
+    idx = 0
+    for w in waypoints:
+        found = False
+        while idx < len(samples):
+            s = samples[idx]
+            dh = abs((s[3] - w[3] + np.pi) % (2 * np.pi) - np.pi)
+            if np.linalg.norm(s[:3] - w[:3]) < pos_tol and dh < hdg_tol:
+                found = True
+                break
+            idx += 1
+        if not found:
+            return False
+    return True

@@ -1,0 +1,62 @@
+"""CPU-side parity: the product's device code + host pipeline, compiled for the host by tests/host_emu (same C ABI),
+against the oracle.  These run without a GPU; tests/test_gpu_parity.py repeats them through libtg_b200.so on the B200."""
+import numpy as np
+import pytest
+
+import parity_checks as PC
+
+
+@pytest.mark.parametrize("r", [2, 3, 4])
+def test_linear_batch(emu_ctx, oracle, r):
+    worst, exact = PC.check_linear_batch(emu_ctx, seed=10 + r, B=24, r=r)
+    assert exact, worst
+
+
+def test_sampling(emu_ctx, oracle):
+    assert PC.check_sampling(emu_ctx)
+
+
+def test_evaluate(emu_ctx, oracle):
+    assert PC.check_evaluate(emu_ctx)
+
+
+def test_extrema_and_scaling(emu_ctx, oracle):
+    assert PC.check_extrema_and_scaling(emu_ctx)
+
+
+def test_random_flier_full_pipeline(emu_ctx, oracle):
+    res, out, exact, worst = PC.check_random_flier(emu_ctx, 48)
+    assert exact
+    assert res["success"].all()
+
+
+def test_fixtures(emu_ctx, oracle):
+    res, out, exact = PC.check_fixtures(emu_ctx)
+    assert exact
+    # the reference tests' geometric acceptance predicate on the original waypoints (get_path_test.h:45-68)
+    from mrs_uav_trajectory_generation_b200 import workloads as W
+
+    for p, wps in enumerate([W.F1A_WAYPOINTS, W.F1B_WAYPOINTS]):
+        smp = out["samples"][out["smp_off"][p]:out["smp_off"][p + 1]]
+        assert PC.geometric_predicate(smp, wps[1:])
+
+
+def test_mixed_ragged_batch(emu_ctx, oracle):
+    res, out, exact, worst = PC.check_mixed_batch(emu_ctx)
+    assert exact
+
+
+@pytest.mark.parametrize("r", [2, 4])
+def test_config2_linear_plus_sampling(emu_ctx, oracle, r):
+    res, out, exact, worst = PC.check_config2(emu_ctx, B=32, r=r)
+    assert exact
+
+
+def test_sweep(emu_ctx, oracle):
+    assert PC.check_sweep(emu_ctx, K=200)
+
+
+def test_jerk_and_snap_full_pipeline(emu_ctx, oracle):
+    for r in (3, 4):
+        res, out, exact, worst = PC.check_random_flier(emu_ctx, 6, first_index=300, derivative_to_optimize=r)
+        assert exact

