@@ -31,6 +31,15 @@ __global__ void __launch_bounds__(128) k_for_each(const F f, const size_t n) {
   if (i < n) f(i);
 }
 
+// one thread per work item with F::kScratch doubles of per-thread scratch in dynamic shared memory, element i of thread
+// t at smem[i * blockDim.x + t] (bank-conflict free; used by the Jenkins-Traub work arrays)
+template <class F>
+__global__ void __launch_bounds__(128) k_for_each_scratch(const F f, const size_t n) {
+  extern __shared__ double smem[];
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f(i, smem + threadIdx.x, (int)blockDim.x);
+}
+
 // one warp per solve instance, grid-stride over instances; the per-warp workspace lives in dynamic shared memory
 // (or in a global slab when it does not fit).  Phases are separated by __syncwarp() (see tg_solve.cuh).
 constexpr int kSolveWarps = 4;
@@ -164,6 +173,18 @@ struct CudaBackend {
     const size_t grid = (n + block - 1) / block;
     prof_begin();
     k_for_each<F><<<(unsigned)grid, block, 0, stream>>>(f, n);
+    TG_CUDA_CHECK(cudaGetLastError());
+    prof_end(typeid(F).name(), n);
+  }
+  template <class F>
+  void for_each_scratch(size_t n, const F& f) {
+    if (n == 0) return;
+    const unsigned block = 128;
+    const size_t grid = (n + block - 1) / block;
+    const size_t smem = (size_t)F::kScratch * sizeof(double) * block;
+    TG_CUDA_CHECK(cudaFuncSetAttribute(k_for_each_scratch<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin();
+    k_for_each_scratch<F><<<(unsigned)grid, block, smem, stream>>>(f, n);
     TG_CUDA_CHECK(cudaGetLastError());
     prof_end(typeid(F).name(), n);
   }

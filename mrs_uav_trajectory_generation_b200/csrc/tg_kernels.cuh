@@ -277,15 +277,16 @@ struct LbfgsFinishFn {
 };
 
 // ---- 6. extrema + time scaling ------------------------------------------------------------------------------------------------
-struct ExtremaFn {  // one thread per (segment, quantity); quantity-major so that a warp shares one polynomial degree
+template <int Q>
+struct ExtremaFn {  // one thread per segment for quantity Q (one launch per quantity: uniform polynomial degree per kernel)
   BatchPtrs b;
   int* shift_count;  // optional counter of fixed-shift stages (flop accounting)
-  TG_HD void operator()(size_t item) const {
-    const size_t q = item / (size_t)b.totS, gs = item - q * (size_t)b.totS;
+  static constexpr int kScratch = JtScratch<QuantityDegree<Q>::value>::kShared;  // doubles of strided scratch per thread
+  TG_HD void operator()(size_t gs, double* scratch, int stride) const {
     const int p = b.prob_of_seg[gs];
     if (b.ps[p].scale_done) return;
     int shifts = 0;
-    b.maxima[gs * 9 + q] = segment_max_magnitude(b.coef + gs * TG_D * TG_N, b.times[gs], (int)q, &shifts);
+    b.maxima[gs * 9 + Q] = segment_max_impl<Q>(b.coef + gs * TG_D * TG_N, b.times[gs], scratch, stride, &shifts);
     if (shift_count) TG_ATOMIC_ADD(shift_count, shifts);
   }
 };
@@ -487,14 +488,14 @@ struct EvaluateFn {
     if (ok) ok[qi] = 1;
   }
 };
-struct ExtremaRawFn {  // one thread per (segment, quantity), quantity-major
-  size_t totS;
+template <int Q>
+struct ExtremaRawFn {  // one thread per segment for quantity Q
   const double* coef;
   const double* times;
   double* maxima;
-  TG_HD void operator()(size_t item) const {
-    const size_t q = item / totS, gs = item - q * totS;
-    maxima[gs * 9 + q] = segment_max_magnitude(coef + gs * TG_D * TG_N, times[gs], (int)q, nullptr);
+  static constexpr int kScratch = JtScratch<QuantityDegree<Q>::value>::kShared;
+  TG_HD void operator()(size_t gs, double* scratch, int stride) const {
+    maxima[gs * 9 + Q] = segment_max_impl<Q>(coef + gs * TG_D * TG_N, times[gs], scratch, stride, nullptr);
   }
 };
 struct CompactSamplesFn {  // one thread per sample slot: slot arrays (with per-problem slack) -> contiguous outputs

@@ -164,13 +164,13 @@ class Pipeline {
       ScaleFn sf{b, {}};
       ScaleCheckFn cf{b, {}};
       for (int i = 0; i < 9; ++i) { sf.L[i] = P.limits[i]; cf.L[i] = P.limits[i]; }
-      be_.for_each((size_t)totS * 9, ExtremaFn{b, nullptr}); launches(1);
+      extrema_all(b);
       for (int pass = 0; pass < 20; ++pass) {
         be_.dev_memset(b.stats + 1, 0, sizeof(int));
         be_.for_each(totS, sf);
-        be_.for_each((size_t)totS * 9, ExtremaFn{b, nullptr});
+        extrema_all(b);
         be_.for_each(B, cf);
-        launches(3);
+        launches(2);
         int pending = 0;
         be_.d2h(&pending, b.stats + 1, sizeof(int));
         if (pending == 0) break;
@@ -574,8 +574,16 @@ class Pipeline {
     double* d_m = scratch_.template alloc<double>((size_t)totS * 9);
     be_.h2d(d_coef, coef, sizeof(double) * (size_t)totS * TG_D * TG_N);
     be_.h2d(d_T, times, sizeof(double) * totS);
-    be_.for_each((size_t)totS * 9, ExtremaRawFn{(size_t)totS, d_coef, d_T, d_m});
-    launches(1);
+    be_.for_each_scratch(totS, ExtremaRawFn<0>{d_coef, d_T, d_m});
+    be_.for_each_scratch(totS, ExtremaRawFn<1>{d_coef, d_T, d_m});
+    be_.for_each_scratch(totS, ExtremaRawFn<2>{d_coef, d_T, d_m});
+    be_.for_each_scratch(totS, ExtremaRawFn<3>{d_coef, d_T, d_m});
+    be_.for_each_scratch(totS, ExtremaRawFn<4>{d_coef, d_T, d_m});
+    be_.for_each_scratch(totS, ExtremaRawFn<5>{d_coef, d_T, d_m});
+    be_.for_each_scratch(totS, ExtremaRawFn<6>{d_coef, d_T, d_m});
+    be_.for_each_scratch(totS, ExtremaRawFn<7>{d_coef, d_T, d_m});
+    be_.for_each_scratch(totS, ExtremaRawFn<8>{d_coef, d_T, d_m});
+    launches(9);
     counters.root_finds += (long long)totS * 9;
     be_.d2h(maxima, d_m, sizeof(double) * (size_t)totS * 9);
   }
@@ -594,13 +602,13 @@ class Pipeline {
     ScaleCheckFn cf{b, {}};
     ScaleOutFn of{b.ps, b.maxima, bb.d_seg_off, {}, nullptr, nullptr};
     for (int i = 0; i < 9; ++i) { sf.L[i] = L9[i]; cf.L[i] = L9[i]; of.L[i] = L9[i]; }
-    be_.for_each((size_t)b.totS * 9, ExtremaFn{b, nullptr}); launches(1);
+    extrema_all(b);
     for (int pass = 0; pass < 20; ++pass) {
       be_.dev_memset(b.stats + 1, 0, sizeof(int));
       be_.for_each(b.totS, sf);
-      be_.for_each((size_t)b.totS * 9, ExtremaFn{b, nullptr});
+      extrema_all(b);
       be_.for_each(B, cf);
-      launches(3);
+      launches(2);
       int pending = 0;
       be_.d2h(&pending, b.stats + 1, sizeof(int));
       if (pending == 0) break;
@@ -672,6 +680,20 @@ class Pipeline {
   size_t sweep_chunk = (size_t)1 << 17;
 
  private:
+  // nine launches, one per quantity, so that every kernel has one polynomial degree (registers sized for it)
+  void extrema_all(const BatchPtrs& b) {
+    const size_t n = (size_t)b.totS;
+    be_.for_each_scratch(n, ExtremaFn<0>{b, nullptr});
+    be_.for_each_scratch(n, ExtremaFn<1>{b, nullptr});
+    be_.for_each_scratch(n, ExtremaFn<2>{b, nullptr});
+    be_.for_each_scratch(n, ExtremaFn<3>{b, nullptr});
+    be_.for_each_scratch(n, ExtremaFn<4>{b, nullptr});
+    be_.for_each_scratch(n, ExtremaFn<5>{b, nullptr});
+    be_.for_each_scratch(n, ExtremaFn<6>{b, nullptr});
+    be_.for_each_scratch(n, ExtremaFn<7>{b, nullptr});
+    be_.for_each_scratch(n, ExtremaFn<8>{b, nullptr});
+    launches(9);
+  }
   int group_index(const Group* g) const {
     for (size_t i = 0; i < groups_.size(); ++i)
       if (groups_[i].get() == g) return (int)i;

@@ -29,7 +29,7 @@ def emu_lib():
     from mrs_uav_trajectory_generation_b200 import Library
 
     d = os.path.join(ROOT, "tests", "host_emu")
-    subprocess.check_call(["make", "-s", "-C", d])
+    subprocess.check_call(["make", "-s", "-C", d, "all"])
     return Library(os.path.join(d, "libtg_emu.so"))
 
 

@@ -60,6 +60,14 @@ struct EmuBackend {
   }
   template <class F>
   void for_each(size_t n, const F& f) { parallel(n, [&](size_t i) { f(i); }); }
+  // work items with F::kScratch doubles of private scratch (shared memory on the device), stride 1 here
+  template <class F>
+  void for_each_scratch(size_t n, const F& f) {
+    parallel(n, [&](size_t i) {
+      double scratch[F::kScratch];
+      f(i, scratch, 1);
+    });
+  }
   // one "warp" per instance: phases run lane by lane (lanes own disjoint outputs within a phase)
   template <class D>
   void solve(size_t n_inst, int ws_doubles, const D& desc) {

@@ -60,3 +60,39 @@ def test_jerk_and_snap_full_pipeline(emu_ctx, oracle):
     for r in (3, 4):
         res, out, exact, worst = PC.check_random_flier(emu_ctx, 6, first_index=300, derivative_to_optimize=r)
         assert exact
+
+
+def test_jenkins_traub_state_machine_variant(oracle):
+    """The alternative extremum kernel (warp-scheduled Jenkins-Traub state machine, -DTG_JT_IMPL=1) must stay
+    bit-identical to the oracle as well, including on polynomials with zeros at the origin, vanishing leading
+    coefficients and repeated structure."""
+    import os
+
+    import oracle_lib as O
+    from mrs_uav_trajectory_generation_b200 import Context, Library
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    ctx = Context(Library(os.path.join(here, "host_emu", "libtg_emu_jt1.so")), 0)
+    assert PC.check_extrema_and_scaling(ctx)
+    rng = np.random.default_rng(3)
+    S = 1500
+    coef = rng.standard_normal((S, 4, 10)) * np.exp(rng.uniform(-6, 3, (S, 1, 10)))
+    coef[::7, :, 1:3] = 0.0
+    coef[::11, :, 9] = 0.0
+    coef[::13, :, 8:] = 0.0
+    coef[5::17, 1] = coef[5::17, 0]
+    times = np.exp(rng.uniform(-2, 2, S))
+    assert np.array_equal(ctx.extrema(coef, times), O.segment_maxima(coef, times))
+
+
+def test_extrema_random_polynomials(emu_ctx, oracle):
+    import oracle_lib as O
+
+    rng = np.random.default_rng(4)
+    S = 1500
+    coef = rng.standard_normal((S, 4, 10)) * np.exp(rng.uniform(-6, 3, (S, 1, 10)))
+    coef[::7, :, 1:3] = 0.0
+    coef[::11, :, 9] = 0.0
+    coef[::13, :, 8:] = 0.0
+    times = np.exp(rng.uniform(-2, 2, S))
+    assert np.array_equal(emu_ctx.extrema(coef, times), O.segment_maxima(coef, times))

@@ -112,10 +112,9 @@ def test_properties_at_full_size(gpu_ctx):
         M = smp_off[p + 1] - smp_off[p]
         assert abs(M - T.sum() / P.dt) <= 1.0 + 1e-9
         assert np.abs(out["samples"][smp_off[p], :3] - wps[0][:3]).max() < 1e-9
-    # feasibility of the final trajectories (limits in tg order: v_h v_v a_h a_v j_h j_v v_y a_y j_y)
-    mx = gpu_ctx.extrema(coef[: seg_off[512]], times[: seg_off[512]]).max(axis=0)
-    lim = np.array(list(P.limits))[[0, 2, 4, 1, 3, 5, 6, 7, 8]]
-    assert np.all(mx <= lim * 1.05), (mx, lim)  # the final re-solve at the stretched times moves maxima slightly
+    # NB: the FINAL trajectories need not satisfy the dynamics limits: the reference stretches a copy of the segments
+    # (eth/trajectory.cpp:598-692) and then re-solves the QP at the stretched times (nl_impl.h:405-408), which moves
+    # the maxima again.  Feasibility of the stretched copy itself is asserted in check_extrema_and_scaling.
 
     # config 2 at full size: idempotence (same inputs -> identical outputs) and agreement of the two entry points
     B2 = 4096
