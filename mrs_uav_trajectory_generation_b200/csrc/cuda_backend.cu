@@ -53,11 +53,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const 
     tg::SolveInst I;
     if (!desc.instance(inst, I)) continue;  // warp-uniform
     tg::solve_ws_bind(I, ws);
-    const int nph = tg::solve_num_phases(I);
-    for (int ph = 0; ph < nph; ++ph) {
-      tg::solve_phase(I, ph, lane);
-      __syncwarp();
-    }
+    tg::solve_warp(I, lane);
   }
 }
 

@@ -2,15 +2,26 @@
 // Replaces PolynomialOptimization<10>::constructR + solveLinear + updateSegmentsFromCompactConstraints +
 // computeCost (reference: lin_impl.h:310-334, 340-373, 263-282, 127-141).
 //
-// The reduced matrix Rpp is block tridiagonal (a free derivative of vertex v couples only to v-1, v, v+1), so it
-// is assembled directly into banded storage and factorised by LU without pivoting on the FULL non-symmetric
-// band (why not Cholesky).  The work is written as a sequence of PHASES; inside a phase every lane
-// owns disjoint outputs and reads only data written in earlier phases, so a __syncwarp() between phases is the
-// only synchronisation.  tests/host_emu runs the same phases lane by lane on the CPU.
+// The reduced matrix Rpp is block tridiagonal (a free derivative of vertex v couples only to v-1, v, v+1), so it is
+// assembled directly into banded rows in shared memory -- each row carries its 2*hbw+1 band entries followed by the
+// four right-hand sides (x, y, z, heading) -- and factorised by LU without pivoting on the FULL non-symmetric band
+// (why not Cholesky), multipliers through the reciprocal pivot (as LAPACK dgetf2 does).
+//
+// The routine is a sequence of PHASES (TG_PHASE): inside a phase every lane owns disjoint outputs and reads only data
+// written in earlier phases; on the device a phase ends with __syncwarp(), tests/host_emu runs the lanes of a phase
+// one after the other.  Round-1 profile of the first version (profiles/r01_solve_v1.md): 19 k warp instructions per
+// solve, most of them index arithmetic and phase dispatch; this version precomputes the slot table once per solve,
+// loads whole 10-entry rows of H with independent loads, and runs the factorisation as a tight loop.
 #ifndef TG_SOLVE_CUH_
 #define TG_SOLVE_CUH_
 
 #include "tg_common.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define TG_PHASE(lane) for (int tg_once_ = 0; tg_once_ < 1; ++tg_once_, __syncwarp())
+#else
+#define TG_PHASE(lane) for (int lane = 0; lane < 32; ++lane)
+#endif
 
 namespace tg {
 
@@ -29,22 +40,24 @@ struct SolveInst {
   double* cost_out;       // or null
   double* dp_out;         // [4][np] or null
   // workspace (shared or global memory)
-  double* band;           // max(np*W, 40*S)
-  double* rhs;            // 4*np
-  double* xs;             // 4*np
-  double* part;           // 4*S
+  int W;                  // row stride: 2*hbw+1 band entries + 4 right-hand sides + the reciprocal pivot
+  double* rows;           // max(np*W, 40*S): banded rows; later the coefficient scratch
+  double* xs;             // np*4 solution, [row][dim]
+  double* part;           // 4*S partial costs
+  int16_t* slot;          // V*5: index of the free unknown of (vertex, derivative), -1 when fixed
 };
 
+TG_HD int solve_row_stride(int hbw) { return 2 * hbw + 1 + TG_D + 1; }  // band, 4 right-hand sides, reciprocal pivot
 TG_HD int solve_ws_doubles(int S, int np, int hbw) {
-  const int W = 2 * hbw + 1;
-  return imax(np * W, 40 * S) + 8 * np + 4 * S;
+  const int W = solve_row_stride(hbw);
+  return imax(np * W, 40 * S) + 4 * np + 4 * S + (5 * (S + 1) + 3) / 4 + 1;
 }
 TG_HD void solve_ws_bind(SolveInst& I, double* ws) {
-  const int W = 2 * I.hbw + 1;
-  I.band = ws;
-  I.rhs = ws + imax(I.np * W, 40 * I.S);
-  I.xs = I.rhs + 4 * I.np;
+  I.W = solve_row_stride(I.hbw);
+  I.rows = ws;
+  I.xs = ws + imax(I.np * I.W, 40 * I.S);
   I.part = I.xs + 4 * I.np;
+  I.slot = (int16_t*)(I.part + 4 * I.S);
 }
 
 TG_HD const double* solve_rec(const SolveInst& I, int s) {
@@ -58,146 +71,148 @@ TG_HD int free_rank(uint32_t m, int a) {
   return (int)((below & 1u) + ((below >> 1) & 1u) + ((below >> 2) & 1u) + ((below >> 3) & 1u) + ((below >> 4) & 1u));
 }
 
-// R entry between slot (v,a) and slot (w,b), |v-w| <= 1.  Segment v-1 contributes first (sum of two terms).
-TG_HD double solve_R(const SolveInst& I, int v, int a, int w, int b) {
-  if (w == v) {
-    double s = 0.0;
-    bool have = false;
-    if (v > 0) { s = solve_rec(I, v - 1)[TG_REC_H + (TG_HALF + a) * TG_N + (TG_HALF + b)]; have = true; }
-    if (v < I.S) {
-      const double h = solve_rec(I, v)[TG_REC_H + a * TG_N + b];
-      s = have ? s + h : h;
+// `lane` is the calling thread's lane on the device; the host emulation ignores it (TG_PHASE loops over the lanes).
+TG_HD void solve_warp(const SolveInst& I, int lane) {
+  const int S = I.S, V = S + 1, np = I.np, hbw = I.hbw, W = I.W, RB = 2 * hbw + 1;
+  (void)lane;
+  // ---- phase 0: slot table, zero the banded rows ---------------------------------------------------------------
+  TG_PHASE(lane) {
+    for (int it = lane; it < V * TG_HALF; it += 32) {
+      const int v = it / TG_HALF, a = it - v * TG_HALF;
+      const uint32_t m = I.vmask[v];
+      I.slot[it] = ((m >> a) & 1u) ? (int16_t)-1 : (int16_t)(I.vfree[v] + free_rank(m, a));
     }
-    return s;
+    for (int e = lane; e < np * W; e += 32) I.rows[e] = 0.0;
   }
-  if (w == v + 1) return solve_rec(I, v)[TG_REC_H + a * TG_N + (TG_HALF + b)];
-  return solve_rec(I, w)[TG_REC_H + (TG_HALF + a) * TG_N + b];
-}
-
-// phases: 0 zero band | 1 assemble | 2..2+np-1 LU steps | then np back-substitution steps | coefficients | cost partials | total
-TG_HD int solve_num_phases(const SolveInst& I) { return (I.np > 0 ? 2 + 2 * I.np : 0) + 3; }
-
-TG_HD void solve_phase(const SolveInst& I, int ph, int lane) {
-  const int S = I.S, V = S + 1, np = I.np, hbw = I.hbw, W = 2 * hbw + 1;
   if (np > 0) {
-    if (ph == 0) {
-      for (int e = lane; e < np * W; e += 32) I.band[e] = 0.0;
-      return;
-    }
-    if (ph == 1) {
-      // one item per (vertex, slot); fixed slots have no row
+    // ---- phase 1: assemble Rpp and rhs = (-Rpf) d_f.  One lane per (vertex, slot) row. ---------------------------
+    TG_PHASE(lane) {
       for (int it = lane; it < V * TG_HALF; it += 32) {
+        const int i = I.slot[it];
+        if (i < 0) continue;
         const int v = it / TG_HALF, a = it - v * TG_HALF;
-        const uint32_t mv = I.vmask[v];
-        if ((mv >> a) & 1u) continue;
-        const int i = I.vfree[v] + free_rank(mv, a);
+        // row (5+a) of H_{v-1} and row a of H_v hold every entry this row of R needs (lin_impl.h:317-333)
+        double hp[TG_N], hc[TG_N];
+        const bool has_p = v > 0, has_c = v < S;
+        if (has_p) {
+          const double* src = solve_rec(I, v - 1) + TG_REC_H + (TG_HALF + a) * TG_N;
+#pragma unroll
+          for (int q = 0; q < TG_N; ++q) hp[q] = src[q];
+        }
+        if (has_c) {
+          const double* src = solve_rec(I, v) + TG_REC_H + a * TG_N;
+#pragma unroll
+          for (int q = 0; q < TG_N; ++q) hc[q] = src[q];
+        }
+        double* row = I.rows + (size_t)i * W;
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-        const int w0 = imax(0, v - 1), w1 = imin(S, v + 1);
-        for (int w = w0; w <= w1; ++w) {
-          const uint32_t mw = I.vmask[w];
+        // columns in ascending order: vertex v-1, v, v+1 (the order of the fixed columns, lin_impl.h:235-254, 367)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const int w = v - 1 + g;
+          if (w < 0 || w > S) continue;
+#pragma unroll
           for (int b = 0; b < TG_HALF; ++b) {
-            const double rv = solve_R(I, v, a, w, b);
-            if ((mw >> b) & 1u) {
-              // rhs = (-Rpf) d_f over ascending fixed column (lin_impl.h:367)
+            double rv;
+            if (g == 0) rv = hp[b];
+            else if (g == 2) rv = hc[TG_HALF + b];
+            else rv = has_p ? (has_c ? hp[TG_HALF + b] + hc[b] : hp[TG_HALF + b]) : hc[b];
+            const int j = I.slot[w * TG_HALF + b];
+            if (j >= 0) {
+              row[j - i + hbw] = rv;
+            } else {
               const double* f = I.vval + ((size_t)w * TG_HALF + b) * TG_D;
               const double nr = -rv;
               acc0 = acc0 + nr * f[0];
               acc1 = acc1 + nr * f[1];
               acc2 = acc2 + nr * f[2];
               acc3 = acc3 + nr * f[3];
-            } else {
-              const int j = I.vfree[w] + free_rank(mw, b);
-              I.band[i * W + (j - i + hbw)] = rv;
             }
           }
         }
-        I.rhs[0 * np + i] = acc0;
-        I.rhs[1 * np + i] = acc1;
-        I.rhs[2 * np + i] = acc2;
-        I.rhs[3 * np + i] = acc3;
+        row[RB + 0] = acc0;
+        row[RB + 1] = acc1;
+        row[RB + 2] = acc2;
+        row[RB + 3] = acc3;
       }
-      return;
     }
-    if (ph < 2 + np) {
-      // LU step k, right-looking, no pivoting.  lane -> (row group, column group)
-      const int k = ph - 2;
-      const int iend = imin(np - 1, k + hbw);
-      const int ncol = (iend - k) + TG_D;  // band columns k+1..iend, then the 4 right-hand sides
-      const double piv = I.band[k * W + hbw];
-      for (int i = k + 1 + (lane >> 2); i <= iend; i += 8) {
-        const double l = I.band[i * W + (k - i + hbw)] / piv;
-        for (int c = (lane & 3); c < ncol; c += 4) {
-          if (c < iend - k) {
-            const int j = k + 1 + c;
-            I.band[i * W + (j - i + hbw)] = I.band[i * W + (j - i + hbw)] - l * I.band[k * W + (j - k + hbw)];
-          } else {
-            const int d = c - (iend - k);
-            I.rhs[d * np + i] = I.rhs[d * np + i] - l * I.rhs[d * np + k];
+    // ---- phase 2: LU without pivoting, right-looking; lane -> (row group, column group) ----------------------------
+    for (int k = 0; k < np; ++k) {
+      TG_PHASE(lane) {
+        const int iend = imin(np - 1, k + hbw);
+        const int nr = iend - k;
+        double* rk = I.rows + (size_t)k * W;
+        const double rinv = 1.0 / rk[hbw];
+        const int ri = lane >> 2, cg = lane & 3;
+        if (lane == 0) rk[RB + TG_D] = rinv;  // kept for the back substitution (nobody reads this slot in this phase)
+        for (int i = k + 1 + ri; i <= iend; i += 8) {
+          double* rw = I.rows + (size_t)i * W;
+          const double l = rw[k - i + hbw] * rinv;
+          const int sh = i - k;  // column j sits at rk[j-k+hbw] and rw[j-i+hbw]
+          for (int c = cg; c < nr; c += 4) {
+            const int pk = c + 1 + hbw;
+            rw[pk - sh] = rw[pk - sh] - l * rk[pk];
           }
+          rw[RB + cg] = rw[RB + cg] - l * rk[RB + cg];
         }
       }
-      return;
     }
-    if (ph < 2 + 2 * np) {
-      // back substitution, column oriented: x_j = rhs_j / a_jj, then rhs_i -= a_ij x_j for the rows above.
-      // Per row this subtracts the far columns first (descending j), the order of the contract.
-      const int j = np - 1 - (ph - 2 - np);
-      const int d = lane & 3;
-      const double xj = I.rhs[d * np + j] / I.band[j * W + hbw];
-      if ((lane >> 2) == 0) I.xs[d * np + j] = xj;
-      const int i0 = imax(0, j - hbw);
-      for (int i = j - 1 - (lane >> 2); i >= i0; i -= 8) I.rhs[d * np + i] = I.rhs[d * np + i] - I.band[i * W + (j - i + hbw)] * xj;
-      return;
+    // ---- phase 3: back substitution, column oriented (far columns are subtracted first, the contract's order) ----
+    for (int j = np - 1; j >= 0; --j) {
+      TG_PHASE(lane) {
+        const int d = lane & 3, ri = lane >> 2;
+        const double* rj = I.rows + (size_t)j * W;
+        const double xj = rj[RB + d] * rj[RB + TG_D];
+        if (ri == 0) I.xs[j * 4 + d] = xj;
+        const int i0 = imax(0, j - hbw);
+        for (int i = j - 1 - ri; i >= i0; i -= 8) {
+          double* rw = I.rows + (size_t)i * W;
+          rw[RB + d] = rw[RB + d] - rw[j - i + hbw] * xj;
+        }
+      }
     }
-    ph -= 2 + 2 * np;
   }
-  if (ph == 0) {
-    // coefficients c = A^-1 * [slots of vertex s ; slots of vertex s+1]  (lin_impl.h:271-280)
+  // ---- phase 4: coefficients c = A^-1 [slots of vertex s ; slots of vertex s+1]  (lin_impl.h:271-280) -----------------
+  TG_PHASE(lane) {
     for (int it = lane; it < S * TG_D * TG_N; it += 32) {
       const int s = it / (TG_D * TG_N), rem = it - s * (TG_D * TG_N), d = rem / TG_N, a = rem - d * TG_N;
-      const double* rec = solve_rec(I, s);
-      double nd[TG_N];
-#pragma unroll
-      for (int k = 0; k < TG_N; ++k) {
-        const int v = s + (k >= TG_HALF ? 1 : 0), sl = k - (k >= TG_HALF ? TG_HALF : 0);
-        const uint32_t m = I.vmask[v];
-        nd[k] = ((m >> sl) & 1u) ? I.vval[((size_t)v * TG_HALF + sl) * TG_D + d] : I.xs[d * np + I.vfree[v] + free_rank(m, sl)];
-      }
       double c;
       if (a < TG_HALF) {
-        const double a_inv[5] = {1.0 / 1.0, 1.0 / 1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0};
-        double ai = a_inv[0];
-#pragma unroll
-        for (int q = 1; q < 5; ++q) ai = (a == q) ? a_inv[q] : ai;
-        double ndv = nd[0];
-#pragma unroll
-        for (int q = 1; q < 5; ++q) ndv = (a == q) ? nd[q] : ndv;
-        c = ai * ndv;
+        // rows 0..4 of A^-1 are diag(1/k!)
+        const int j = I.slot[s * TG_HALF + a];
+        const double nd = (j >= 0) ? I.xs[j * 4 + d] : I.vval[((size_t)s * TG_HALF + a) * TG_D + d];
+        const double ai = (a < 2) ? 1.0 : ((a == 2) ? 1.0 / 2.0 : ((a == 3) ? 1.0 / 6.0 : 1.0 / 24.0));
+        c = ai * nd;
       } else {
+        const double* rec = solve_rec(I, s);
         const double* xr = rec + TG_REC_X + (a - TG_HALF) * 5;
         const double* dr = rec + TG_REC_DINV + (a - TG_HALF) * 5;
+        double nd[TG_N];
+#pragma unroll
+        for (int k = 0; k < TG_N; ++k) {
+          const int j = I.slot[s * TG_HALF + k];  // slots of vertex s then vertex s+1 are contiguous in the table
+          nd[k] = (j >= 0) ? I.xs[j * 4 + d] : I.vval[((size_t)s * TG_HALF + k) * TG_D + d];
+        }
         c = xr[0] * nd[0];
 #pragma unroll
         for (int k = 1; k < 5; ++k) c = c + xr[k] * nd[k];
 #pragma unroll
         for (int k = 0; k < 5; ++k) c = c + dr[k] * nd[5 + k];
       }
-      I.band[it] = c;  // scratch for the cost (the band is dead now)
+      I.rows[it] = c;  // scratch for the cost (the band is dead now)
       if (I.coef_out) I.coef_out[it] = c;
     }
     if (I.dp_out)
-      for (int e = lane; e < TG_D * np; e += 32) I.dp_out[e] = I.xs[e];
-    return;
+      for (int e = lane; e < TG_D * np; e += 32) I.dp_out[(e & 3) * np + (e >> 2)] = I.xs[e];
   }
-  if (ph == 1) {
-    // partial cost of (segment, dimension): (c^T Q) c over the non-zero block (lin_impl.h:135-137)
-    if (!I.cost_out) return;
-    const int r = I.r;
+  if (!I.cost_out) return;
+  // ---- phase 5: partial cost of (segment, dimension): (c^T Q) c over the non-zero block (lin_impl.h:135-137) ---------
+  TG_PHASE(lane) {
+    const int r = I.r, nq = TG_N - r;
     for (int it = lane; it < S * TG_D; it += 32) {
       const int s = it / TG_D;
       const double* Q = solve_rec(I, s) + TG_REC_Q;
-      const double* c = I.band + it * TG_N;
-      const int nq = TG_N - r;
+      const double* c = I.rows + it * TG_N;
       double partial = 0.0;
       for (int b = 0; b < nq; ++b) {
         double sum = c[r] * Q[0 * 8 + b];
@@ -206,15 +221,14 @@ TG_HD void solve_phase(const SolveInst& I, int ph, int lane) {
       }
       I.part[it] = partial;
     }
-    return;
   }
-  if (ph == 2) {
-    if (lane == 0 && I.cost_out) {
+  // ---- phase 6: total in (segment, dimension) order (lin_impl.h:131-140) -------------------------------------------------
+  TG_PHASE(lane) {
+    if (lane == 0) {
       double total = 0.0;
       for (int it = 0; it < S * TG_D; ++it) total += I.part[it];
       *I.cost_out = 0.5 * total;
     }
-    return;
   }
 }
 

@@ -289,24 +289,25 @@ bool LinearSolver::solve() {
           }
         }
     }
-  // forward elimination, no pivoting
+  // forward elimination, no pivoting; multipliers through the reciprocal pivot (as LAPACK dgetf2 scales by 1/pivot)
+  std::vector<double> rinv(n);
   for (int k = 0; k < n; ++k) {
-    const double piv = band[(size_t)k * W + hbw];
+    rinv[k] = 1.0 / band[(size_t)k * W + hbw];
     const int iend = std::min(n - 1, k + hbw);
     for (int i = k + 1; i <= iend; ++i) {
-      const double l = band[(size_t)i * W + (k - i + hbw)] / piv;
+      const double l = band[(size_t)i * W + (k - i + hbw)] * rinv[k];
       for (int j = k + 1; j <= iend; ++j)
         band[(size_t)i * W + (j - i + hbw)] = band[(size_t)i * W + (j - i + hbw)] - l * band[(size_t)k * W + (j - k + hbw)];
       for (int d = 0; d < kD; ++d) rhs[(size_t)d * n + i] = rhs[(size_t)d * n + i] - l * rhs[(size_t)d * n + k];
     }
   }
-  // back substitution, far columns first (descending j)
+  // back substitution, far columns first (descending j), x_i = s * (1 / a_ii)
   for (int d = 0; d < kD; ++d) {
     double* x = &d_p[(size_t)d * n];
     for (int i = n - 1; i >= 0; --i) {
       double s = rhs[(size_t)d * n + i];
       for (int j = std::min(n - 1, i + hbw); j > i; --j) s = s - band[(size_t)i * W + (j - i + hbw)] * x[j];
-      x[i] = s / band[(size_t)i * W + hbw];
+      x[i] = s * rinv[i];
     }
   }
   segments_from_compact();

@@ -76,9 +76,7 @@ struct EmuBackend {
       if (!desc.instance(inst, I)) return;
       std::vector<double> ws((size_t)ws_doubles);
       tg::solve_ws_bind(I, ws.data());
-      const int nph = tg::solve_num_phases(I);
-      for (int ph = 0; ph < nph; ++ph)
-        for (int lane = 0; lane < 32; ++lane) tg::solve_phase(I, ph, lane);
+      tg::solve_warp(I, 0);  // TG_PHASE runs the 32 lanes of every phase one after the other
     });
   }
   void exclusive_scan(const int* in, int* out, int n) {
