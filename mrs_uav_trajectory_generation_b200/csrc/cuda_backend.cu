@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cub/device/device_scan.cuh>
+#include <cstdlib>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -58,6 +59,40 @@ __global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const 
 }
 
 
+// Four solve instances per warp, eight lanes each (tg_solve_octet.cuh).  A warp whose four instances are not all eligible
+// for the octet routine runs them one after the other through the general warp routine in the same shared memory.
+constexpr int kOctWarps = 2;
+template <class D>
+__global__ void __launch_bounds__(kOctWarps * 32) k_solve_oct(const D desc, const size_t n_inst, const int oct_ws_doubles, const int warp_ws_doubles) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, oct = lane >> 3;
+  const size_t gw = (size_t)blockIdx.x * kOctWarps + warp, nw = (size_t)gridDim.x * kOctWarps;
+  double* wws = smem + (size_t)warp * warp_ws_doubles;
+  for (size_t base = gw * 4; base < n_inst; base += nw * 4) {
+    tg::SolveInst I;
+    const size_t inst = base + oct;
+    bool ok = inst < n_inst && desc.instance(inst, I);
+    if (!ok) {
+      I.S = 0; I.np = 0; I.hbw = tg::kOctHbw; I.dp_out = nullptr; I.coef_out = nullptr; I.cost_out = nullptr;
+    }
+    const bool fits = !ok || (tg::octet_eligible(I) && tg::octet_ws_doubles(I.S, I.np) <= oct_ws_doubles);
+    if (__all_sync(0xffffffffu, fits)) {
+      tg::octet_ws_bind(I, wws + (size_t)oct * oct_ws_doubles);
+      const int nmax = __reduce_max_sync(0xffffffffu, I.np);
+      tg::solve_octets(&I, lane, nmax);
+    } else {
+      for (int o = 0; o < 4; ++o) {
+        tg::SolveInst J;
+        if (base + o >= n_inst || !desc.instance(base + o, J)) continue;  // warp-uniform
+        tg::solve_ws_bind(J, wws);
+        tg::solve_warp(J, lane);
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // FP64 pipe peak probes (the roofline denominator for this path; MEASURED_PEAKS.json has HBM and bf16 only).
 // mode 0: DFMA chains; mode 1: DMUL+DADD pairs as generated under -fmad=false (what the product kernels issue).
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, int mode) {
@@ -84,7 +119,8 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, int m
 struct CudaBackend {
   int device = 0;
   int sm_count = 148;
-  size_t smem_optin = 0;
+  size_t smem_optin = 0, smem_per_sm = 0;
+  bool force_general_solve = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   void* scan_tmp = nullptr;
@@ -106,6 +142,8 @@ struct CudaBackend {
     TG_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     sm_count = prop.multiProcessorCount;
     smem_optin = prop.sharedMemPerBlockOptin;
+    smem_per_sm = prop.sharedMemPerMultiprocessor;
+    force_general_solve = std::getenv("TG_NO_OCTET") != nullptr;
     TG_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     TG_CUDA_CHECK(cudaEventCreate(&ev0));
     TG_CUDA_CHECK(cudaEventCreate(&ev1));
@@ -220,8 +258,24 @@ struct CudaBackend {
   }
 
   template <class D>
-  void solve(size_t n_inst, int ws_doubles, const D& desc) {
+  void solve(size_t n_inst, int ws_doubles, int oct_ws_doubles, const D& desc) {
     if (n_inst == 0) return;
+    // octet kernel: four instances per warp in shared memory (the common case); otherwise one warp per instance
+    const size_t warp_ws = (size_t)std::max(4 * oct_ws_doubles, ws_doubles);
+    const size_t oct_smem = warp_ws * sizeof(double) * kOctWarps;
+    if (oct_ws_doubles > 0 && !force_general_solve && oct_smem * 2 + 2048 <= smem_per_sm) {
+      prof_begin();
+      TG_CUDA_CHECK(cudaFuncSetAttribute(k_solve_oct<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oct_smem));
+      int per_sm = 0;
+      TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_oct<D>, kOctWarps * 32, oct_smem));
+      if (per_sm < 1) per_sm = 1;
+      const size_t blocks_needed = (n_inst + 4 * kOctWarps - 1) / (4 * kOctWarps);
+      const size_t grid = std::min(blocks_needed, (size_t)sm_count * per_sm);
+      k_solve_oct<D><<<(unsigned)grid, kOctWarps * 32, oct_smem, stream>>>(desc, n_inst, oct_ws_doubles, (int)warp_ws);
+      TG_CUDA_CHECK(cudaGetLastError());
+      prof_end(typeid(D).name(), n_inst);
+      return;
+    }
     const size_t ws_bytes = (size_t)ws_doubles * sizeof(double);
     const size_t smem = ws_bytes * kSolveWarps;
     const size_t blocks_needed = (n_inst + kSolveWarps - 1) / kSolveWarps;

@@ -16,6 +16,7 @@
 #include "tg_poly.cuh"
 #include "tg_segment.cuh"
 #include "tg_solve.cuh"
+#include "tg_solve_octet.cuh"
 
 #if defined(__CUDA_ARCH__)
 #define TG_ATOMIC_MAX(p, v) atomicMax((p), (v))
@@ -70,7 +71,7 @@ struct BatchPtrs {
   int* vfree;
   int* np;
   int* hbw;
-  int* stats;            // [0] = max solve workspace doubles, [1] = problems still to scale, [2] = scratch
+  int* stats;            // [0] = max solve workspace doubles, [1] = problems still to scale, [2] = max octet-solve workspace doubles
   double *times, *baca, *xeval, *x, *g, *d, *hist_s, *hist_y;
   LbfgsScalars* lb;
   double* recs;
@@ -97,6 +98,7 @@ struct PrepareFn {
     b.np[p] = np;
     b.hbw[p] = hbw;
     TG_ATOMIC_MAX(&b.stats[0], solve_ws_doubles(S, np, hbw));
+    if (hbw == kOctHbw && np > 0) TG_ATOMIC_MAX(&b.stats[2], octet_ws_doubles(S, np));
     ProbState& ps = b.ps[p];
     ps.status = kFindOk;
     ps.nlopt_code = 1;

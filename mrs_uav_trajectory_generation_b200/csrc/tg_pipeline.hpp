@@ -140,7 +140,7 @@ class Pipeline {
     be_.for_each(B, BacaTotalFn{b}); launches(1);
     int stats[4];
     be_.d2h(stats, b.stats, sizeof(stats));
-    const int ws = stats[0];
+    const int ws = stats[0], ows = stats[2];
     if (P.run_time_alloc) {
       b.xeval = scratch_.template alloc<double>(totS);
       b.x = scratch_.template alloc<double>(totS);
@@ -155,7 +155,7 @@ class Pipeline {
       be_.for_each(B, LbfgsBeginFn{b}); launches(1);
       for (int e = 0; e < P.max_evals; ++e) {
         be_.for_each((size_t)totS * 3, SetupMellingerFn{b});
-        be_.solve((size_t)totV, ws, SolveProblemDesc{b, 1, nullptr, nullptr});
+        be_.solve((size_t)totV, ws, ows, SolveProblemDesc{b, 1, nullptr, nullptr});
         be_.for_each(B, LbfgsAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel});
         launches(3);
       }
@@ -180,7 +180,7 @@ class Pipeline {
     }
     // final linear solve at the (scaled) times (nl_impl.h:405-408 / lin_impl.h:340-373)
     be_.for_each(totS, SetupBaseFn{b, b.times});
-    be_.solve((size_t)B, ws, SolveProblemDesc{b, 0, nullptr, nullptr});
+    be_.solve((size_t)B, ws, ows, SolveProblemDesc{b, 0, nullptr, nullptr});
     launches(2);
     // sampling (eth/trajectory_sampling.cpp:49-104)
     int* cap = scratch_.template alloc<int>((size_t)B + 1);
@@ -494,7 +494,7 @@ class Pipeline {
     int stats[4];
     be_.d2h(stats, b.stats, sizeof(stats));
     be_.for_each(b.totS, SetupBaseFn{b, b.times});
-    be_.solve((size_t)B, stats[0], SolveProblemDesc{b, 0, nullptr, nullptr});
+    be_.solve((size_t)B, stats[0], stats[2], SolveProblemDesc{b, 0, nullptr, nullptr});
     be_.for_each(B, CostOutFn{b.ps, d_cost});
     launches(4);
     counters.solves += B;
@@ -655,7 +655,7 @@ class Pipeline {
     for (long long k0 = 0; k0 < K; k0 += chunk) {
       const long long kc = std::min(chunk, K - k0);
       be_.for_each((size_t)kc * S, SetupSweepFn{S, r, d_cand + (size_t)k0 * S, d_recs});
-      be_.solve((size_t)kc, stats[0], SolveSweepDesc{b, d_recs, d_costs + k0});
+      be_.solve((size_t)kc, stats[0], stats[2], SolveSweepDesc{b, d_recs, d_costs + k0});
       launches(2);
     }
     counters.solves += K;

@@ -45,6 +45,7 @@ struct SolveInst {
   double* xs;             // np*4 solution, [row][dim]
   double* part;           // 4*S partial costs
   int16_t* slot;          // V*5: index of the free unknown of (vertex, derivative), -1 when fixed
+  int16_t* rowva;         // np: (vertex, derivative) of each free unknown (octet kernel only)
 };
 
 TG_HD int solve_row_stride(int hbw) { return 2 * hbw + 1 + TG_D + 1; }  // band, 4 right-hand sides, reciprocal pivot

@@ -4,6 +4,7 @@
 // (`pytest -m "not gpu"`).  The resulting libtg_emu.so exports the same C ABI as libtg_b200.so but is never loaded by
 // the package: the product has no CPU path and fails loudly without CUDA.
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -68,15 +69,49 @@ struct EmuBackend {
       f(i, scratch, 1);
     });
   }
-  // one "warp" per instance: phases run lane by lane (lanes own disjoint outputs within a phase)
+  // one "warp" per group of four instances (octet kernel) or per instance (general kernel): phases run lane by lane
+  // (lanes own disjoint outputs within a phase).  Mirrors k_solve_oct / k_solve of cuda_backend.cu.
   template <class D>
-  void solve(size_t n_inst, int ws_doubles, const D& desc) {
-    parallel(n_inst, [&](size_t inst) {
-      tg::SolveInst I;
-      if (!desc.instance(inst, I)) return;
-      std::vector<double> ws((size_t)ws_doubles);
-      tg::solve_ws_bind(I, ws.data());
-      tg::solve_warp(I, 0);  // TG_PHASE runs the 32 lanes of every phase one after the other
+  void solve(size_t n_inst, int ws_doubles, int oct_ws_doubles, const D& desc) {
+    if (oct_ws_doubles <= 0 || std::getenv("TG_EMU_NO_OCTET")) {
+      parallel(n_inst, [&](size_t inst) {
+        tg::SolveInst I;
+        if (!desc.instance(inst, I)) return;
+        std::vector<double> ws((size_t)ws_doubles);
+        tg::solve_ws_bind(I, ws.data());
+        tg::solve_warp(I, 0);  // TG_PHASE runs the 32 lanes of every phase one after the other
+      });
+      return;
+    }
+    const size_t warp_ws = (size_t)std::max(4 * oct_ws_doubles, ws_doubles);
+    if (std::getenv("TG_EMU_TRACE")) std::fprintf(stderr, "[emu] octet solve path: %zu instances\n", n_inst);
+    parallel((n_inst + 3) / 4, [&](size_t grp) {
+      tg::SolveInst I[4];
+      bool ok[4], all_oct = true;
+      int nmax = 0;
+      std::vector<double> ws(warp_ws);
+      for (int o = 0; o < 4; ++o) {
+        const size_t inst = grp * 4 + o;
+        ok[o] = inst < n_inst && desc.instance(inst, I[o]);
+        if (!ok[o]) {
+          I[o] = tg::SolveInst{};
+          continue;
+        }
+        if (!tg::octet_eligible(I[o]) || tg::octet_ws_doubles(I[o].S, I[o].np) > oct_ws_doubles) all_oct = false;
+      }
+      if (all_oct) {
+        for (int o = 0; o < 4; ++o) {
+          tg::octet_ws_bind(I[o], ws.data() + (size_t)o * oct_ws_doubles);
+          if (ok[o]) nmax = std::max(nmax, I[o].np);
+        }
+        tg::solve_octets(I, 0, nmax);
+      } else {
+        for (int o = 0; o < 4; ++o) {
+          if (!ok[o]) continue;
+          tg::solve_ws_bind(I[o], ws.data());
+          tg::solve_warp(I[o], 0);
+        }
+      }
     });
   }
   void exclusive_scan(const int* in, int* out, int n) {

@@ -1,0 +1,48 @@
+#!/usr/bin/env python3
+"""Prints the metrics that matter from an .ncu-rep (per kernel launch): duration, occupancy, pipe use, stall mix, traffic.
+usage: ncu_summary.py report.ncu-rep [kernel-substring]"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.per_cycle_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fma.sum",
+    "sm__inst_executed_pipe_lsu.sum", "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_cbu.sum",
+    "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum", "smsp__inst_executed_op_global_ld.sum",
+    "smsp__inst_executed_op_global_st.sum", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "l1tex__t_bytes.sum", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
+    "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum",
+]
+
+
+def main():
+    rep = sys.argv[1]
+    sub = sys.argv[2] if len(sys.argv) > 2 else ""
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    for r in rows[2:]:
+        if sub and sub not in r[ki]:
+            continue
+        print("==", r[ki][:110])
+        d = {h: (u, v) for h, u, v in zip(hdr, units, r)}
+        for k in KEYS:
+            if k in d:
+                print(f"  {k:72s} {d[k][1]} {d[k][0]}")
+        stalls = [(float(v[1].replace(',', '')), h) for h, v in d.items() if "issue_stalled" in h and h.endswith("_per_warp_active.pct") and v[1]]
+        for val, h in sorted(stalls, reverse=True)[:8]:
+            print(f"  stall {h.split('issue_stalled_')[1].replace('_per_warp_active.pct', ''):40s} {val:.1f} %")
+
+
+if __name__ == "__main__":
+    main()
