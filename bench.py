@@ -160,7 +160,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    ctx = tg.Context(tg.Library(), local_rank)
+    ctx = tg.Context(tg.Library(os.environ.get("TG_LIB") or None), local_rank)
     P = ctx.L.default_params()
     B = args.batch
     wp_off, wp = W.random_flier_paths_fast(B, first_index=rank)

@@ -93,6 +93,82 @@ __global__ void __launch_bounds__(kOctWarps * 32) k_solve_oct(const D desc, cons
   }
 }
 
+// The micro-op Jenkins-Traub machine (tg_poly_vm.cuh), warp-scheduled with lane refill.  Every lane works on one prepared
+// polynomial; each pass of the loop runs ONE micro-op, the one most lanes are waiting for; a lane whose polynomial is
+// finished stores its maximum and takes the next work item of the warp's chunk (chunks of kVmChunk items come from a
+// global counter).  Work arrays: shared memory, element i of thread t at smem[i * blockDim.x + t].
+constexpr int kVmChunk = 64;
+constexpr int kVmThreads = 128;
+template <class F>
+__global__ void __launch_bounds__(kVmThreads) k_vm(const F f, const int n_max, const int* __restrict__ n_dev, int* __restrict__ counter) {
+  extern __shared__ double smem[];
+  constexpr int Q = F::kQuantity;
+  constexpr int M = tg::VmQuantity<Q>::kMaxDegree;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int n = n_dev ? min(n_max, *n_dev) : n_max;
+  double* scratch = smem + threadIdx.x;
+  const int stride = blockDim.x;
+  double svk[M + 1], tmp[M + 1];
+  tg::JtVm m;
+  m.p = tg::WArr{scratch, stride};
+  m.qp = tg::WArr{scratch + (size_t)(M + 1) * stride, stride};
+  m.K = tg::WArr{scratch + (size_t)2 * (M + 1) * stride, stride};
+  m.qk = tg::WArr{scratch + (size_t)3 * (M + 1) * stride, stride};
+  m.svk = svk;
+  m.tmp = tmp;
+  m.state = tg::JtVm::kDone;
+  tg::VmEmit<Q> emit{nullptr, 0.0, 0.0};
+  int item = -1;          // work item the lane is iterating on
+  size_t seg = 0;
+  int next = 0, end = 0;  // the warp's chunk of work items
+  bool exhausted = false;
+  for (;;) {
+    const bool idle = (m.state == tg::JtVm::kDone);
+    const unsigned idle_mask = __ballot_sync(full, idle);
+    if (idle_mask) {
+      if (idle && item >= 0) {
+        f.maxima[seg * 9 + Q] = emit.best;
+        item = -1;
+      }
+      if (!exhausted && next >= end) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counter, kVmChunk);
+        base = __shfl_sync(full, base, 0);
+        next = base;
+        end = min(base + kVmChunk, n);
+        if (next >= n) exhausted = true;
+      }
+      if (!exhausted) {
+        const int rank = __popc(idle_mask & ((1u << lane) - 1u));
+        const int avail = end - next;
+        if (idle && rank < avail) {
+          item = next + rank;
+          const int degree = f.vb.degree[item];
+          seg = f.segment((size_t)item);
+          emit.coef = f.coef + seg * TG_D * TG_N;
+          emit.T = f.times[seg];
+          emit.best = f.maxima[seg * 9 + Q];
+          const double* poly = f.vb.polys + (size_t)item * tg::kVmPolyStride;
+          for (int i = 0; i <= degree; ++i) m.p[i] = poly[i];
+          m.begin(degree);
+        }
+        next += min(__popc(idle_mask), avail);
+      }
+    }
+    const int st = m.state;
+    const unsigned same = __match_any_sync(full, st);
+    const unsigned key = (st == tg::JtVm::kDone) ? 0u : (((unsigned)__popc(same) << 8) | (unsigned)(st + 1));
+    const unsigned win = __reduce_max_sync(full, key);
+    if (win == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+    const int cur = (int)(win & 0xffu) - 1;
+    if (st == cur) m.step(cur, emit);
+  }
+}
+
 // FP64 pipe peak probes (the roofline denominator for this path; MEASURED_PEAKS.json has HBM and bf16 only).
 // mode 0: DFMA chains; mode 1: DMUL+DADD pairs as generated under -fmad=false (what the product kernels issue).
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, int mode) {
@@ -221,6 +297,23 @@ struct CudaBackend {
     k_for_each_scratch<F><<<(unsigned)grid, block, smem, stream>>>(f, n);
     TG_CUDA_CHECK(cudaGetLastError());
     prof_end(typeid(F).name(), n);
+  }
+  // micro-op Jenkins-Traub machine over n_max work items (or *n_dev of them); `counter` must be zero at launch
+  template <class F>
+  void vm_run(size_t n_max, const int* n_dev, int* counter, const F& f) {
+    if (n_max == 0) return;
+    const size_t smem = (size_t)F::kScratch * sizeof(double) * kVmThreads;
+    TG_CUDA_CHECK(cudaFuncSetAttribute(k_vm<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vm<F>, kVmThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const size_t warps_needed = (n_max + kVmChunk - 1) / kVmChunk;
+    const size_t blocks_needed = (warps_needed + kVmThreads / 32 - 1) / (kVmThreads / 32);
+    const size_t grid = std::min(blocks_needed, (size_t)sm_count * per_sm);
+    prof_begin();
+    k_vm<F><<<(unsigned)grid, kVmThreads, smem, stream>>>(f, (int)n_max, n_dev, counter);
+    TG_CUDA_CHECK(cudaGetLastError());
+    prof_end(typeid(F).name(), n_max);
   }
   void prof_begin() {
     if (profiling) TG_CUDA_CHECK(cudaEventRecord(pev0, stream));

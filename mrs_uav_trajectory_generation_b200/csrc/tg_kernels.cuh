@@ -14,6 +14,7 @@
 #include "tg_lbfgs.cuh"
 #include "tg_node.cuh"
 #include "tg_poly.cuh"
+#include "tg_poly_vm.cuh"
 #include "tg_segment.cuh"
 #include "tg_solve.cuh"
 #include "tg_solve_octet.cuh"
@@ -21,10 +22,12 @@
 #if defined(__CUDA_ARCH__)
 #define TG_ATOMIC_MAX(p, v) atomicMax((p), (v))
 #define TG_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define TG_ATOMIC_ADD_RET(p, v) atomicAdd((p), (v))
 #elif defined(__CUDACC__)
 // host pass of nvcc over TG_HD code: never executed (the library has no CPU path)
 #define TG_ATOMIC_MAX(p, v) ((void)0)
 #define TG_ATOMIC_ADD(p, v) ((void)0)
+#define TG_ATOMIC_ADD_RET(p, v) (0)
 #else
 // tests/host_emu only (g++): the emulator runs work items on several host threads
 static inline void tg_host_atomic_max(int* p, int v) {
@@ -34,6 +37,7 @@ static inline void tg_host_atomic_max(int* p, int v) {
 }
 #define TG_ATOMIC_MAX(p, v) tg_host_atomic_max((p), (v))
 #define TG_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
+#define TG_ATOMIC_ADD_RET(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
 #endif
 
 namespace tg {
@@ -292,14 +296,70 @@ struct ExtremaFn {  // one thread per segment for quantity Q (one launch per qua
     if (shift_count) TG_ATOMIC_ADD(shift_count, shifts);
   }
 };
+// ---- 6b. extrema through the micro-op machine (tg_poly_vm.cuh): a prepare kernel and a machine kernel per quantity ----
+// Work items are entries of an optional work list (segments whose polynomial changed since their maxima were computed).
+struct VmBuffers {
+  const int* work;   // [n] segment indices, or null for the identity
+  const int* n_dev;  // number of work items when it lives in device memory (work-list length), or null
+  double* polys;     // [n][kVmPolyStride]
+  int* degree;       // [n]
+};
+template <int Q>
+struct ExtremaPrepFn {  // one thread per work item
+  const double* coef;
+  const double* times;
+  double* maxima;
+  VmBuffers vb;
+  TG_HD void operator()(size_t item) const {
+    if (vb.n_dev && item >= (size_t)*vb.n_dev) return;
+    const size_t gs = vb.work ? (size_t)vb.work[item] : item;
+    double best;
+    vb.degree[item] = extrema_prepare<Q>(coef + gs * TG_D * TG_N, times[gs], vb.polys + item * kVmPolyStride, &best);
+    maxima[gs * 9 + Q] = best;
+  }
+};
+template <int Q>
+struct ExtremaVmFn {  // the machine: cuda_backend.cu runs it warp-scheduled with lane refill, the emulator item by item
+  const double* coef;
+  const double* times;
+  double* maxima;
+  VmBuffers vb;
+  static constexpr int kQuantity = Q;
+  static constexpr int kScratch = VmScratch<Q>::kShared;
+  TG_HD size_t segment(size_t item) const { return vb.work ? (size_t)vb.work[item] : item; }
+  TG_HD void single(size_t item, double* scratch, int stride) const {
+    const int degree = vb.degree[item];
+    if (degree < 1) return;
+    const size_t gs = segment(item);
+    maxima[gs * 9 + Q] = vm_run_single<Q>(coef + gs * TG_D * TG_N, times[gs], vb.polys + item * kVmPolyStride, degree, maxima[gs * 9 + Q], scratch, stride);
+  }
+};
+// work list of the segments whose maxima must be recomputed after a scaling pass: the problem is still being scaled
+// and the segment was stretched by a factor other than exactly 1 (a factor of 1 leaves every coefficient bit-identical,
+// eth/polynomial.cpp:218-224, so its zeros and maxima are unchanged)
+struct ExtremaWorkFn {
+  const int* prob_of_seg;
+  const ProbState* ps;
+  const uint8_t* changed;  // [totS] written by ScaleFn
+  int* work;
+  int* count;
+  TG_HD void operator()(size_t gs) const {
+    if (ps[prob_of_seg[gs]].scale_done || !changed[gs]) return;
+    const int at = TG_ATOMIC_ADD_RET(count, 1);
+    work[at] = (int)gs;
+  }
+};
+
 struct ScaleFn {  // one thread per segment (eth/trajectory.cpp:610-658)
   BatchPtrs b;
   double L[9];
+  uint8_t* changed;  // optional [totS]: 1 when the segment was stretched by a factor other than exactly 1
   TG_HD void operator()(size_t gs) const {
     const int p = b.prob_of_seg[gs];
     if (b.ps[p].scale_done) return;
     const double s = violation_scaling(b.maxima + gs * 9, L);
     scale_segment(b.coef + gs * TG_D * TG_N, b.times + gs, s);
+    if (changed) changed[gs] = (s != 1.0) ? 1 : 0;
   }
 };
 struct ScaleCheckFn {  // one thread per problem: the global re-check (eth/trajectory.cpp:660-689)
@@ -491,12 +551,16 @@ struct EvaluateFn {
   }
 };
 template <int Q>
-struct ExtremaRawFn {  // one thread per segment for quantity Q
+struct ExtremaRawFn {  // one thread per work item (segment, or entry of a device work list) for quantity Q
   const double* coef;
   const double* times;
   double* maxima;
+  const int* work;   // optional work list
+  const int* n_dev;  // optional length of the work list (device memory)
   static constexpr int kScratch = JtScratch<QuantityDegree<Q>::value>::kShared;
-  TG_HD void operator()(size_t gs, double* scratch, int stride) const {
+  TG_HD void operator()(size_t item, double* scratch, int stride) const {
+    if (n_dev && item >= (size_t)*n_dev) return;
+    const size_t gs = work ? (size_t)work[item] : item;
     maxima[gs * 9 + Q] = segment_max_impl<Q>(coef + gs * TG_D * TG_N, times[gs], scratch, stride, nullptr);
   }
 };

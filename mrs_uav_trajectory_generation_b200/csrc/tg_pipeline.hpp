@@ -161,20 +161,7 @@ class Pipeline {
       }
       be_.for_each(B, LbfgsFinishFn{b}); launches(1);
       // time scaling (nl_impl.h:335-427 -> eth/trajectory.cpp:598-692)
-      ScaleFn sf{b, {}};
-      ScaleCheckFn cf{b, {}};
-      for (int i = 0; i < 9; ++i) { sf.L[i] = P.limits[i]; cf.L[i] = P.limits[i]; }
-      extrema_all(b);
-      for (int pass = 0; pass < 20; ++pass) {
-        be_.dev_memset(b.stats + 1, 0, sizeof(int));
-        be_.for_each(totS, sf);
-        extrema_all(b);
-        be_.for_each(B, cf);
-        launches(2);
-        int pending = 0;
-        be_.d2h(&pending, b.stats + 1, sizeof(int));
-        if (pending == 0) break;
-      }
+      scale_loop(b, P.limits);
     } else {
       b.recs = scratch_.template alloc<double>((size_t)totS * TG_REC_SIZE);
     }
@@ -574,16 +561,8 @@ class Pipeline {
     double* d_m = scratch_.template alloc<double>((size_t)totS * 9);
     be_.h2d(d_coef, coef, sizeof(double) * (size_t)totS * TG_D * TG_N);
     be_.h2d(d_T, times, sizeof(double) * totS);
-    be_.for_each_scratch(totS, ExtremaRawFn<0>{d_coef, d_T, d_m});
-    be_.for_each_scratch(totS, ExtremaRawFn<1>{d_coef, d_T, d_m});
-    be_.for_each_scratch(totS, ExtremaRawFn<2>{d_coef, d_T, d_m});
-    be_.for_each_scratch(totS, ExtremaRawFn<3>{d_coef, d_T, d_m});
-    be_.for_each_scratch(totS, ExtremaRawFn<4>{d_coef, d_T, d_m});
-    be_.for_each_scratch(totS, ExtremaRawFn<5>{d_coef, d_T, d_m});
-    be_.for_each_scratch(totS, ExtremaRawFn<6>{d_coef, d_T, d_m});
-    be_.for_each_scratch(totS, ExtremaRawFn<7>{d_coef, d_T, d_m});
-    be_.for_each_scratch(totS, ExtremaRawFn<8>{d_coef, d_T, d_m});
-    launches(9);
+    ExtremaScratch es = extrema_scratch((size_t)totS);
+    extrema_segments(d_coef, d_T, d_m, (size_t)totS, nullptr, nullptr, es);
     counters.root_finds += (long long)totS * 9;
     be_.d2h(maxima, d_m, sizeof(double) * (size_t)totS * 9);
   }
@@ -598,21 +577,9 @@ class Pipeline {
     b.maxima = scratch_.template alloc<double>((size_t)b.totS * 9);
     be_.h2d(b.times, times, sizeof(double) * b.totS);
     be_.h2d(b.coef, coef, sizeof(double) * (size_t)b.totS * TG_D * TG_N);
-    ScaleFn sf{b, {}};
-    ScaleCheckFn cf{b, {}};
     ScaleOutFn of{b.ps, b.maxima, bb.d_seg_off, {}, nullptr, nullptr};
-    for (int i = 0; i < 9; ++i) { sf.L[i] = L9[i]; cf.L[i] = L9[i]; of.L[i] = L9[i]; }
-    extrema_all(b);
-    for (int pass = 0; pass < 20; ++pass) {
-      be_.dev_memset(b.stats + 1, 0, sizeof(int));
-      be_.for_each(b.totS, sf);
-      extrema_all(b);
-      be_.for_each(B, cf);
-      launches(2);
-      int pending = 0;
-      be_.d2h(&pending, b.stats + 1, sizeof(int));
-      if (pending == 0) break;
-    }
+    for (int i = 0; i < 9; ++i) of.L[i] = L9[i];
+    scale_loop(b, L9);
     int* d_passes = scratch_.template alloc<int>(B);
     uint8_t* d_within = scratch_.template alloc<uint8_t>(B);
     of.passes = d_passes;
@@ -680,20 +647,93 @@ class Pipeline {
   size_t sweep_chunk = (size_t)1 << 17;
 
  private:
-  // nine launches, one per quantity, so that every kernel has one polynomial degree (registers sized for it)
-  void extrema_all(const BatchPtrs& b) {
-    const size_t n = (size_t)b.totS;
-    be_.for_each_scratch(n, ExtremaFn<0>{b, nullptr});
-    be_.for_each_scratch(n, ExtremaFn<1>{b, nullptr});
-    be_.for_each_scratch(n, ExtremaFn<2>{b, nullptr});
-    be_.for_each_scratch(n, ExtremaFn<3>{b, nullptr});
-    be_.for_each_scratch(n, ExtremaFn<4>{b, nullptr});
-    be_.for_each_scratch(n, ExtremaFn<5>{b, nullptr});
-    be_.for_each_scratch(n, ExtremaFn<6>{b, nullptr});
-    be_.for_each_scratch(n, ExtremaFn<7>{b, nullptr});
-    be_.for_each_scratch(n, ExtremaFn<8>{b, nullptr});
-    launches(9);
+  // Trajectory::scaleSegmentTimesToMeetConstraints over a batch (eth/trajectory.cpp:598-692): maxima of every segment,
+  // then up to 20 passes of { stretch every segment, recompute the maxima of the segments that changed, global check }.
+  void scale_loop(BatchPtrs& b, const double* L9) {
+    const size_t totS = (size_t)b.totS;
+    ScaleFn sf{b, {}, nullptr};
+    ScaleCheckFn cf{b, {}};
+    for (int i = 0; i < 9; ++i) { sf.L[i] = L9[i]; cf.L[i] = L9[i]; }
+    uint8_t* changed = scratch_.template alloc<uint8_t>(totS);
+    int* work = scratch_.template alloc<int>(totS);
+    int* count = scratch_.template alloc<int>(1);
+    sf.changed = changed;
+    ExtremaScratch es = extrema_scratch(totS);
+    extrema_segments(b.coef, b.times, b.maxima, totS, nullptr, nullptr, es);
+    for (int pass = 0; pass < 20; ++pass) {
+      be_.dev_memset(b.stats + 1, 0, sizeof(int));
+      be_.dev_memset(count, 0, sizeof(int));
+      be_.for_each(totS, sf);
+      be_.for_each(totS, ExtremaWorkFn{b.prob_of_seg, b.ps, changed, work, count});
+      extrema_segments(b.coef, b.times, b.maxima, totS, work, count, es);
+      be_.for_each((size_t)b.B, cf);
+      launches(3);
+      int pending = 0;
+      be_.d2h(&pending, b.stats + 1, sizeof(int));
+      if (pending == 0) break;
+    }
   }
+
+  // per-segment maxima of the nine quantities for n_max work items (all segments, or the entries of a device work
+  // list whose length lives in device memory); one launch pair per quantity so that every kernel has one degree
+  struct ExtremaScratch {
+    double* polys = nullptr;
+    int* degree = nullptr;
+    int* counters = nullptr;
+  };
+  ExtremaScratch extrema_scratch(size_t n_max) {
+    ExtremaScratch es;
+#if TG_JT_IMPL == 2
+    es.polys = scratch_.template alloc<double>(std::max<size_t>(n_max, 1) * kVmPolyStride);
+    es.degree = scratch_.template alloc<int>(std::max<size_t>(n_max, 1));
+    es.counters = scratch_.template alloc<int>(16);
+#else
+    (void)n_max;
+#endif
+    return es;
+  }
+  void extrema_segments(const double* coef, const double* times, double* maxima, size_t n_max, const int* work, const int* n_dev,
+                        const ExtremaScratch& es) {
+    if (n_max == 0) return;
+#if TG_JT_IMPL == 2
+    VmBuffers vb;
+    vb.work = work;
+    vb.n_dev = n_dev;
+    vb.polys = es.polys;
+    vb.degree = es.degree;
+    int* counters = es.counters;
+    be_.dev_memset(counters, 0, 16 * sizeof(int));
+    extrema_quantity<0>(coef, times, maxima, n_max, vb, counters);
+    extrema_quantity<1>(coef, times, maxima, n_max, vb, counters);
+    extrema_quantity<2>(coef, times, maxima, n_max, vb, counters);
+    extrema_quantity<3>(coef, times, maxima, n_max, vb, counters);
+    extrema_quantity<4>(coef, times, maxima, n_max, vb, counters);
+    extrema_quantity<5>(coef, times, maxima, n_max, vb, counters);
+    extrema_quantity<6>(coef, times, maxima, n_max, vb, counters);
+    extrema_quantity<7>(coef, times, maxima, n_max, vb, counters);
+    extrema_quantity<8>(coef, times, maxima, n_max, vb, counters);
+    launches(18);
+#else
+    (void)es;
+    be_.for_each_scratch(n_max, ExtremaRawFn<0>{coef, times, maxima, work, n_dev});
+    be_.for_each_scratch(n_max, ExtremaRawFn<1>{coef, times, maxima, work, n_dev});
+    be_.for_each_scratch(n_max, ExtremaRawFn<2>{coef, times, maxima, work, n_dev});
+    be_.for_each_scratch(n_max, ExtremaRawFn<3>{coef, times, maxima, work, n_dev});
+    be_.for_each_scratch(n_max, ExtremaRawFn<4>{coef, times, maxima, work, n_dev});
+    be_.for_each_scratch(n_max, ExtremaRawFn<5>{coef, times, maxima, work, n_dev});
+    be_.for_each_scratch(n_max, ExtremaRawFn<6>{coef, times, maxima, work, n_dev});
+    be_.for_each_scratch(n_max, ExtremaRawFn<7>{coef, times, maxima, work, n_dev});
+    be_.for_each_scratch(n_max, ExtremaRawFn<8>{coef, times, maxima, work, n_dev});
+    launches(9);
+#endif
+  }
+#if TG_JT_IMPL == 2
+  template <int Q>
+  void extrema_quantity(const double* coef, const double* times, double* maxima, size_t n_max, const VmBuffers& vb, int* counters) {
+    be_.for_each(n_max, ExtremaPrepFn<Q>{coef, times, maxima, vb});
+    be_.vm_run(n_max, vb.n_dev, counters + Q, ExtremaVmFn<Q>{coef, times, maxima, vb});
+  }
+#endif
   int group_index(const Group* g) const {
     for (size_t i = 0; i < groups_.size(); ++i)
       if (groups_[i].get() == g) return (int)i;

@@ -62,12 +62,26 @@ struct WArr {
 #ifndef TG_JT_REP
 #define TG_JT_REP 1
 #endif
+#ifndef TG_JT_SCHED
+#define TG_JT_SCHED 1  // 0: majority state first, 1: oldest first
+#endif
+// FP64 division, square root and the sign-preserving helpers are the bulk of the machine's code when inlined at ~40
+// sites (an IEEE division is ~25 SASS instructions); one out-of-line copy keeps the kernel inside the instruction cache.
+#if defined(__CUDA_ARCH__) && !defined(TG_JT_INLINE_DIV)
+__device__ __noinline__ double tg_jt_div(double a, double b) { return a / b; }
+__device__ __noinline__ double tg_jt_sqrt(double a) { return tgdm::dsqrt(a); }
+#define TG_DIV(a, b) tg_jt_div((a), (b))
+#define TG_SQRT(a) tg_jt_sqrt(a)
+#else
+#define TG_DIV(a, b) ((a) / (b))
+#define TG_SQRT(a) tgdm::dsqrt(a)
+#endif
 struct JtMachine {
   enum State { kRootBegin, kChop, kNewton, kKInit, kShiftBegin, kFsPrep, kFixedStep, kQuadStep, kRealStep, kDone };
   WArr p, qp, K, qk;  // shared-memory work arrays (degree + 1 entries each)
   double* svk;        // per-thread save areas (rarely touched): svk[0..M], tmp[0..M]
   double* tmp;
-  int N, NN, state;
+  int N, NN, state, nfound;
   // calcSC scalars
   double a, b, c, d, e, f, g, h, a1, a3, a7;
   double szr, szi, lzr, lzi;
@@ -91,6 +105,7 @@ struct JtMachine {
     double bb, aa;
     q[0] = bb = pp[0];
     q[1] = aa = -(bb * uu) + pp[1];
+#pragma unroll 1
     for (int i = 2; i < nn; i++) {
       const double t = -(aa * uu + bb * vv_) + pp[i];
       q[i] = t;
@@ -107,38 +122,41 @@ struct JtMachine {
     }
     h = vv_ * b;
     if (dabs(d) >= dabs(c)) {
-      e = a / d;
-      f = c / d;
+      e = TG_DIV(a, d);
+      f = TG_DIV(c, d);
       g = uu * b;
-      a3 = e * (g + a) + h * (b / d);
+      a3 = e * (g + a) + h * TG_DIV(b, d);
       a1 = -a + f * b;
       a7 = h + (f + uu) * a;
       return 2;
     }
-    e = a / c;
-    f = d / c;
+    e = TG_DIV(a, c);
+    f = TG_DIV(d, c);
     g = e * uu;
-    a3 = e * a + (g + h / c) * b;
-    a1 = -(a * (d / c)) + b;
+    a3 = e * a + (g + TG_DIV(h, c)) * b;
+    a1 = -(a * TG_DIV(d, c)) + b;
     a7 = g * d + h * f + a;
     return 1;
   }
   TG_HD void next_k(int tf) {  // rpoly_ak1.cpp:604-645
     if (tf == 3) {
       K[1] = K[0] = 0.0;
+#pragma unroll 1
       for (int i = 2; i < N; i++) K[i] = qk[i - 2];
       return;
     }
     const double temp = ((tf == 1) ? b : a);
     if (dabs(a1) > (10.0 * TG_DBL_EPSILON * dabs(temp))) {
-      a7 = a7 / a1;
-      a3 = a3 / a1;
+      a7 = TG_DIV(a7, a1);
+      a3 = TG_DIV(a3, a1);
       K[0] = qp[0];
       K[1] = -(a7 * qp[0]) + qp[1];
+#pragma unroll 1
       for (int i = 2; i < N; i++) K[i] = -(a7 * qp[i - 1]) + a3 * qk[i - 2] + qp[i];
     } else {
       K[0] = 0.0;
       K[1] = -a7 * qp[0];
+#pragma unroll 1
       for (int i = 2; i < N; i++) K[i] = -(a7 * qp[i - 1]) + a3 * qk[i - 2];
     }
   }
@@ -154,51 +172,52 @@ struct JtMachine {
       a5 = (f + uu) * c + vv_ * d;
     }
     const double pN = p[N], pN1 = p[N - 1], kN1 = K[N - 1], kN2 = K[N - 2];
-    const double b1 = -kN1 / pN;
-    const double b2 = -(kN2 + b1 * pN1) / pN;
+    const double b1 = TG_DIV(-kN1, pN);
+    const double b2 = TG_DIV(-(kN2 + b1 * pN1), pN);
     const double c1 = vv_ * b2 * a1;
     const double c2 = b1 * a7;
     const double c3 = b1 * b1 * a3;
     const double c4 = -(c2 + c3) + c1;
     const double temp = -c4 + a5 + b1 * a4;
     if (temp != 0.0) {
-      *ou = -((uu * (c3 + c2) + vv_ * (b1 * a1 + b2 * a7)) / temp) + uu;
-      *ov = vv_ * (1.0 + c4 / temp);
+      *ou = -TG_DIV(uu * (c3 + c2) + vv_ * (b1 * a1 + b2 * a7), temp) + uu;
+      *ov = vv_ * (1.0 + TG_DIV(c4, temp));
     }
   }
   TG_HD static void quad(double qa, double b1, double qc, double* sr, double* si, double* lr, double* li) {  // rpoly_ak1.cpp:881-932
     *sr = *si = *lr = *li = 0.0;
     if (qa == 0) {
-      *sr = ((b1 != 0) ? -(qc / b1) : *sr);
+      *sr = ((b1 != 0) ? -TG_DIV(qc, b1) : *sr);
       return;
     }
     if (qc == 0) {
-      *lr = -(b1 / qa);
+      *lr = -TG_DIV(b1, qa);
       return;
     }
     const double bb = b1 / 2.0;
     double dd, ee;
     if (dabs(bb) < dabs(qc)) {
       ee = ((qc >= 0) ? qa : -qa);
-      ee = -ee + bb * (bb / dabs(qc));
-      dd = dsqrt(dabs(ee)) * dsqrt(dabs(qc));
+      ee = -ee + bb * TG_DIV(bb, dabs(qc));
+      dd = TG_SQRT(dabs(ee)) * TG_SQRT(dabs(qc));
     } else {
-      ee = -((qa / bb) * (qc / bb)) + 1.0;
-      dd = dsqrt(dabs(ee)) * (dabs(bb));
+      ee = -(TG_DIV(qa, bb) * TG_DIV(qc, bb)) + 1.0;
+      dd = TG_SQRT(dabs(ee)) * (dabs(bb));
     }
     if (ee >= 0) {
       dd = ((bb >= 0) ? -dd : dd);
-      *lr = (-bb + dd) / qa;
-      *sr = ((*lr != 0) ? (qc / (*lr)) / qa : *sr);
+      *lr = TG_DIV(-bb + dd, qa);
+      *sr = ((*lr != 0) ? TG_DIV(TG_DIV(qc, *lr), qa) : *sr);
     } else {
-      *lr = *sr = -(bb / qa);
-      *si = dabs(dd / qa);
+      *lr = *sr = -TG_DIV(bb, qa);
+      *si = dabs(TG_DIV(dd, qa));
       *li = -(*si);
     }
   }
 
   // ---- control-flow glue of Fxshfr_ak1's third-stage do-while (rpoly_ak1.cpp:459-523) --------------------------
   TG_HD void restore_k() {
+#pragma unroll 1
     for (int i = 0; i < N; i++) K[i] = svk[i];
   }
   TG_HD void begin_quad() {
@@ -258,8 +277,10 @@ struct JtMachine {
   TG_HD void root_found(int nz, Sink& sink) {  // rpoly_ak1.cpp:338-356
     sink(szr, szi);
     if (nz != 1) sink(lzr, lzi);
+    nfound += nz;
     NN = NN - nz;
     N = NN - 1;
+#pragma unroll 1
     for (int i = 0; i < NN; i++) p[i] = qp[i];
     state = kRootBegin;
   }
@@ -277,6 +298,7 @@ struct JtMachine {
     xx = 0x1.6a09e667f3bcdp-1;  // sqrt(0.5)
     yy = -xx;
     state = kRootBegin;
+    nfound = 0;
 #if defined(__CUDA_ARCH__)
     const unsigned lanes = __activemask();  // the lanes that run this machine together
 #endif
@@ -287,11 +309,22 @@ struct JtMachine {
       // lanes per instruction).  Lanes are independent, so the schedule cannot change any result.
       int cur = state;
 #if defined(__CUDA_ARCH__)
+#if TG_JT_SCHED == 0
       const unsigned same = __match_any_sync(lanes, state);
       const unsigned key = (state == kDone) ? 0u : (((unsigned)__popc(same) << 8) | (unsigned)(state + 1));
       const unsigned win = __reduce_max_sync(lanes, key);
       if (win == 0u) break;
       cur = (int)(win & 0xffu) - 1;
+#else
+      // oldest first: the lanes that are furthest behind (fewest zeros found, then earliest stage of the round) run;
+      // lanes that are ahead wait for them, which keeps the warp in step round after round instead of letting it
+      // split into groups that time-share the SM
+      const unsigned key = (state == kDone) ? 0xffffffffu : (((unsigned)nfound << 8) | (unsigned)state);
+      const unsigned win = __reduce_min_sync(lanes, key);
+      if (win == 0xffffffffu) break;
+      cur = (int)(win & 0xffu);
+      if (key != win) continue;
+#endif
 #else
       if (cur == kDone) break;
 #endif
@@ -303,12 +336,15 @@ struct JtMachine {
 #if defined(TG_JT_STATS)
       npass[cur]++;
 #endif
+#if defined(TG_JT_TRACE)
+      tg_jt_trace(cur, N);
+#endif
       if (cur == kRootBegin) {
         if (N < 1) {
           state = kDone;
         } else if (N <= 2) {
           if (N < 2) {
-            sink(-(p[1] / p[0]), 0.0);
+            sink(-TG_DIV(p[1], p[0]), 0.0);
           } else {
             double sr_, si_, lr_, li_;
             quad(p[0], p[1], p[2], &sr_, &si_, &lr_, &li_);
@@ -318,24 +354,26 @@ struct JtMachine {
           state = kDone;
         } else {
           double moduli_max = 0.0, moduli_min = TG_FLT_MAX;
+#pragma unroll 1
           for (int i = 0; i < NN; i++) {
             const double xa = dabs(p[i]);
             if (xa > moduli_max) moduli_max = xa;
             if ((xa != 0) && (xa < moduli_min)) moduli_min = xa;
           }
-          double sc = lo / moduli_min;
-          if (((sc <= 1.0) && (moduli_max >= 10)) || ((sc > 1.0) && (TG_FLT_MAX / sc >= moduli_max))) {
+          double sc = TG_DIV(lo, moduli_min);
+          if (((sc <= 1.0) && (moduli_max >= 10)) || ((sc > 1.0) && (TG_DIV(TG_FLT_MAX, sc) >= moduli_max))) {
             sc = ((sc == 0) ? TG_FLT_MIN : sc);
-            const int l = (int)(tgdm::dlog(sc) / lb2 + 0.5);
+            const int l = (int)(TG_DIV(tgdm::dlog(sc), lb2) + 0.5);
             const double factor = tgdm::scalb(1.0, l);
             if (factor != 1.0)
+#pragma unroll 1
               for (int i = 0; i < NN; i++) p[i] = p[i] * factor;
           }
           // upper estimate of the lower bound on the zero moduli; pt[i] = |p[i]|, pt[N] = -|p[N]|
           const double ptN = -dabs(p[N]), pt0 = dabs(p[0]), ptNM1 = dabs(p[N - 1]);
-          x = tgdm::dexp((tgdm::dlog(-ptN) - tgdm::dlog(pt0)) / (double)N);
+          x = tgdm::dexp(TG_DIV(tgdm::dlog(-ptN) - tgdm::dlog(pt0), (double)N));
           if (ptNM1 != 0) {
-            const double xm_ = -ptN / ptNM1;
+            const double xm_ = TG_DIV(-ptN, ptNM1);
             x = ((xm_ < x) ? xm_ : x);
           }
           xm = x;
@@ -346,6 +384,7 @@ struct JtMachine {
         x = xm;
         xm = 0.1 * x;
         ff = dabs(p[0]);
+#pragma unroll 1
         for (int i = 1; i < N; i++) ff = ff * xm + dabs(p[i]);
         ff = ff * xm + (-dabs(p[N]));
         if (!(ff > 0)) {
@@ -354,15 +393,16 @@ struct JtMachine {
         }
       }
       else if (cur == kNewton) {  // one pass of: while (|dx/x| > 0.005) { Newton step }
-        if (dabs(dx / x) > 0.005) {
+        if (dabs(TG_DIV(dx, x)) > 0.005) {
           double df;
           df = ff = dabs(p[0]);
+#pragma unroll 1
           for (int i = 1; i < N; i++) {
             ff = x * ff + dabs(p[i]);
             df = x * df + ff;
           }
           ff = x * ff + (-dabs(p[N]));
-          dx = ff / df;
+          dx = TG_DIV(ff, df);
           x = x - dx;
         } else {
           bnd = x;
@@ -371,13 +411,16 @@ struct JtMachine {
       }
       else if (cur == kKInit) {  // K = p'/N and five no-shift steps (rpoly_ak1.cpp:285-320)
         const int NM1 = N - 1;
-        for (int i = 1; i < N; i++) K[i] = (double)(N - i) * p[i] / ((double)N);
+#pragma unroll 1
+        for (int i = 1; i < N; i++) K[i] = TG_DIV((double)(N - i) * p[i], (double)N);
         K[0] = p[0];
         const double aa = p[N], bb = p[NM1];
         int zerok = ((K[NM1] == 0) ? 1 : 0);
+#pragma unroll 1
         for (int q = 0; q < 5; q++) {
           const double cc = K[NM1];
           if (zerok) {
+#pragma unroll 1
             for (int i = 0; i < NM1; i++) {
               const int jx = NM1 - i;
               K[jx] = K[jx - 1];
@@ -385,7 +428,8 @@ struct JtMachine {
             K[0] = 0;
             zerok = ((K[NM1] == 0) ? 1 : 0);
           } else {
-            const double t = -aa / cc;
+            const double t = TG_DIV(-aa, cc);
+#pragma unroll 1
             for (int i = 0; i < NM1; i++) {
               const int jx = NM1 - i;
               K[jx] = t * K[jx - 1] + p[jx];
@@ -394,6 +438,7 @@ struct JtMachine {
             zerok = ((dabs(K[NM1]) <= dabs(bb) * TG_DBL_EPSILON * 10.0) ? 1 : 0);
           }
         }
+#pragma unroll 1
         for (int i = 0; i < N; i++) tmp[i] = K[i];
         jj = 1;
         state = kShiftBegin;
@@ -432,6 +477,7 @@ struct JtMachine {
       }
       else if (cur == kFixedStep) {  // one pass of the fixed-shift loop (rpoly_ak1.cpp:415-538)
         if (j >= L2) {
+#pragma unroll 1
           for (int i = 0; i < N; i++) K[i] = tmp[i];  // unsuccessful shift: restore K, next jj
           jj++;
           state = kShiftBegin;
@@ -441,17 +487,18 @@ struct JtMachine {
           newest(tFlag, u, v, &ui, &vi);
           vv = vi;
           const double kN1 = K[N - 1];
-          ss = ((kN1 != 0.0) ? -(p[N] / kN1) : 0.0);
+          ss = ((kN1 != 0.0) ? -TG_DIV(p[N], kN1) : 0.0);
           ts = tv = 1.0;
           bool stage3 = false;
           if ((j != 0) && (tFlag != 3)) {
-            tv = ((vv != 0.0) ? dabs((vv - ovv) / vv) : tv);
-            ts = ((ss != 0.0) ? dabs((ss - oss) / ss) : ts);
+            tv = ((vv != 0.0) ? dabs(TG_DIV(vv - ovv, vv)) : tv);
+            ts = ((ss != 0.0) ? dabs(TG_DIV(ss - oss, ss)) : ts);
             tvv = ((tv < otv) ? tv * otv : 1.0);
             tss = ((ts < ots) ? ts * ots : 1.0);
             vpass = ((tvv < betav) ? 1 : 0);
             spass = ((tss < betas) ? 1 : 0);
             if ((spass) || (vpass)) {
+#pragma unroll 1
               for (int i = 0; i < N; i++) svk[i] = K[i];
               s = ss;
               stry = vtry = 0;
@@ -477,9 +524,10 @@ struct JtMachine {
         } else {
           quad_sd(NN, qu, qv, p, qp, &a, &b);
           const double mp = dabs(-(szr * b) + a) + dabs(szi * b);
-          const double zm = dsqrt(dabs(qv));
+          const double zm = TG_SQRT(dabs(qv));
           double ee = 2.0 * dabs(qp[0]);
           const double t = -(szr * b);
+#pragma unroll 1
           for (int i = 1; i < N; i++) ee = ee * zm + dabs(qp[i]);
           ee = ee * zm + dabs(a + t);
           ee = (9.0 * ee + 2.0 * dabs(t) - 7.0 * (dabs(a + t) + zm * dabs(b))) * TG_DBL_EPSILON;
@@ -493,10 +541,11 @@ struct JtMachine {
               if (qj >= 2) {
                 if ((qrelstp <= 0.01) && (mp >= qomp) && (!qtried)) {
                   // a cluster stalls the convergence: five fixed-shift steps close to it
-                  qrelstp = ((qrelstp < TG_DBL_EPSILON) ? dsqrt(TG_DBL_EPSILON) : dsqrt(qrelstp));
+                  qrelstp = ((qrelstp < TG_DBL_EPSILON) ? TG_SQRT(TG_DBL_EPSILON) : TG_SQRT(qrelstp));
                   qu = qu - qu * qrelstp;
                   qv = qv + qv * qrelstp;
                   quad_sd(NN, qu, qv, p, qp, &a, &b);
+#pragma unroll 1
                   for (int i = 0; i < 5; i++) {
                     const int tf = calc_sc(qu, qv);
                     next_k(tf);
@@ -512,7 +561,7 @@ struct JtMachine {
               double qui, qvi;
               newest(tf, qu, qv, &qui, &qvi);
               if (qvi != 0) {
-                qrelstp = dabs((-qv + qvi) / qvi);
+                qrelstp = dabs(TG_DIV(-qv + qvi, qvi));
                 qu = qui;
                 qv = qvi;
               } else {
@@ -528,10 +577,12 @@ struct JtMachine {
         const int nm1 = N - 1;
         double pv;
         qp[0] = pv = p[0];
+#pragma unroll 1
         for (int i = 1; i < NN; i++) qp[i] = pv = pv * rs + p[i];
         const double mp = dabs(pv);
         const double ms = dabs(rs);
         double ee = 0.5 * dabs(qp[0]);
+#pragma unroll 1
         for (int i = 1; i < NN; i++) ee = ee * ms + dabs(qp[i]);
         if (mp <= 20.0 * TG_DBL_EPSILON * (2.0 * ee - mp)) {
           szr = rs;
@@ -548,18 +599,22 @@ struct JtMachine {
             romp = mp;
             double kv;
             qk[0] = kv = K[0];
+#pragma unroll 1
             for (int i = 1; i < N; i++) qk[i] = kv = kv * rs + K[i];
             if (dabs(kv) > dabs(K[nm1]) * 10.0 * TG_DBL_EPSILON) {
-              rt = -(pv / kv);
+              rt = -TG_DIV(pv, kv);
               K[0] = qp[0];
+#pragma unroll 1
               for (int i = 1; i < N; i++) K[i] = rt * qk[i - 1] + qp[i];
             } else {
               K[0] = 0.0;
+#pragma unroll 1
               for (int i = 1; i < N; i++) K[i] = qk[i - 1];
             }
             kv = K[0];
+#pragma unroll 1
             for (int i = 1; i < N; i++) kv = kv * rs + K[i];
-            rt = ((dabs(kv) > (dabs(K[nm1]) * 10.0 * TG_DBL_EPSILON)) ? -(pv / kv) : 0.0);
+            rt = ((dabs(kv) > (dabs(K[nm1]) * 10.0 * TG_DBL_EPSILON)) ? -TG_DIV(pv, kv) : 0.0);
             rs = rs + rt;
           }
         }
@@ -572,7 +627,7 @@ struct JtMachine {
 // doubles of strided scratch a thread needs for polynomials of degree <= M
 template <int M>
 struct JtScratch {
-#if !defined(TG_JT_IMPL) || TG_JT_IMPL == 0
+#if defined(TG_JT_IMPL) && TG_JT_IMPL == 0
   static constexpr int kShared = 1;
 #else
   static constexpr int kShared = 4 * (M + 1);  // p, qp, K, qk
@@ -707,7 +762,7 @@ TG_HD double segment_max_q(const double* __restrict__ coef, double T, double* sc
 #include "tg_poly_naive.cuh"
 namespace tg {
 #ifndef TG_JT_IMPL
-#define TG_JT_IMPL 0  // 0: direct transcription, work arrays in local memory (fastest measured, profiles/r01_jt_variants.md); 1: warp-scheduled state machine, shared-memory work arrays
+#define TG_JT_IMPL 1  // 0: direct transcription, work arrays in local memory; 1: warp-scheduled stage machine, shared-memory work arrays (fastest measured, profiles/r01_extrema.md); 2: micro-op machine with lane refill (tg_poly_vm.cuh)
 #endif
 template <int Q>
 TG_HD double segment_max_impl(const double* __restrict__ coef, double T, double* scratch, int stride, int* shifts) {

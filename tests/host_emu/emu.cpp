@@ -114,6 +114,15 @@ struct EmuBackend {
       }
     });
   }
+  // the micro-op Jenkins-Traub machine, item by item (the CUDA build schedules it warp-wide with lane refill)
+  template <class F>
+  void vm_run(size_t n_max, const int* n_dev, int*, const F& f) {
+    const size_t n = n_dev ? std::min<size_t>(n_max, (size_t)*n_dev) : n_max;
+    parallel(n, [&](size_t i) {
+      double scratch[F::kScratch];
+      f.single(i, scratch, 1);
+    });
+  }
   void exclusive_scan(const int* in, int* out, int n) {
     int acc = 0;
     for (int i = 0; i < n; ++i) {

@@ -8,7 +8,7 @@ import os
 libpath = sys.argv[1] if len(sys.argv) > 1 else None
 ctx = tg.Context(tg.Library(libpath), 0)
 print('library', libpath or 'default')
-B = 4096
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 wp_off, wp = W.random_flier_paths_fast(B, first_index=0)
 P = ctx.L.default_params(check_deviation=0)
 res, tot = ctx.optimize_batch(wp_off, wp, None, None, P)
