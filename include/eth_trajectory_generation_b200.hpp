@@ -1,0 +1,592 @@
+// eth_trajectory_generation_b200.hpp -- header-only C++ host side of the B200 path, with the reference's class names.
+//
+// Drop-in for the classes MrsTrajectoryGeneration::findTrajectory uses (src/mrs_trajectory_generation.cpp:857-1209):
+//   eth_trajectory_generation::Vertex                          eth/vertex.h:42-116
+//   eth_trajectory_generation::Segment / Trajectory            eth/segment.h, eth/trajectory.h:51-190
+//   eth_trajectory_generation::PolynomialOptimization<N>       lin.h:60-233
+//   eth_trajectory_generation::NonlinearOptimizationParameters nl.h:35-110
+//   eth_trajectory_generation::PolynomialOptimizationNonLinear<N>  nl.h:147-197
+//   eth_trajectory_generation::sampleWholeTrajectory           eth/trajectory_sampling.h:44
+// Same method names, argument meaning and error behaviour (bool returns, print-and-continue -- eth/misc.h:6-38 -- and the
+// NLopt-style int of optimize()).  Every method marshals into the C ABI of include/tg_b200.h, i.e. into the sm_100a
+// kernels of libtg_b200.so; one object = a batch of one.  There is no CPU arithmetic here and no fallback: constructing
+// the first object fails (std::runtime_error) when no CUDA device is usable.
+//
+// Types: the reference passes Eigen::VectorXd; Eigen is not a dependency of this header.  `Vector` below is
+// std::vector<double>; when <Eigen/Core> was included first, overloads taking / returning Eigen::VectorXd are enabled.
+//
+// Additions that the one-problem-per-object reference API cannot express: TrajectoryGeneratorBatch (the numeric core of
+// optimize()/findTrajectory for many paths in one call).
+#ifndef ETH_TRAJECTORY_GENERATION_B200_HPP_
+#define ETH_TRAJECTORY_GENERATION_B200_HPP_
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "tg_b200.h"
+
+namespace eth_trajectory_generation {
+
+namespace derivative_order {  // eth/motion_defines.h:33-44
+static constexpr int POSITION = 0;
+static constexpr int VELOCITY = 1;
+static constexpr int ACCELERATION = 2;
+static constexpr int JERK = 3;
+static constexpr int SNAP = 4;
+static constexpr int INVALID = -1;
+}  // namespace derivative_order
+
+typedef std::vector<double> Vector;
+
+namespace b200 {
+constexpr int kN = 10;    // coefficients per segment and dimension (node.cpp:1063)
+constexpr int kD = 4;     // x, y, z, heading (node.cpp:902)
+constexpr int kHalf = 5;  // derivative slots per vertex (lin_impl.h:206)
+
+// One tg_ctx per device for the process, created on first use.
+class Context {
+ public:
+  static Context& instance(int device = 0) {
+    static std::map<int, std::unique_ptr<Context>> all;
+    std::unique_ptr<Context>& c = all[device];
+    if (!c) c.reset(new Context(device));
+    return *c;
+  }
+  tg_ctx* get() const { return ctx_; }
+  void check(int rc, const char* what) const {
+    if (rc != TG_OK) throw std::runtime_error(std::string(what) + ": " + tg_last_error(ctx_));
+  }
+  ~Context() {
+    if (ctx_) tg_ctx_destroy(ctx_);
+  }
+
+ private:
+  explicit Context(int device) {
+    const int rc = tg_ctx_create(device, &ctx_);
+    if (rc != TG_OK || !ctx_) throw std::runtime_error("tg_ctx_create failed: libtg_b200 needs a CUDA device (no CPU fallback)");
+  }
+  tg_ctx* ctx_ = nullptr;
+};
+}  // namespace b200
+
+// ---- Vertex (eth/vertex.h:42-116, eth/vertex.cpp:134-177) ----------------------------------------------------------
+class Vertex {
+ public:
+  typedef std::vector<Vertex> Vector;
+  typedef eth_trajectory_generation::Vector ConstraintValue;
+  typedef std::map<int, ConstraintValue> Constraints;
+
+  explicit Vertex(size_t dimension) : D_(dimension) {}
+  size_t D() const { return D_; }
+
+  void addConstraint(int derivative_order, double value) { constraints_[derivative_order] = ConstraintValue(D_, value); }
+  void addConstraint(int type, const ConstraintValue& constraint) {
+    if (constraint.size() != D_) {
+      std::printf("[Vertex]: dimension of the constraint does not match the vertex\n");  // CHECK prints and continues
+      return;
+    }
+    constraints_[type] = constraint;
+  }
+  // start or end vertex: position fixed, derivatives 1 .. up_to_derivative fixed at zero (eth/vertex.cpp:158-163)
+  void makeStartOrEnd(const ConstraintValue& constraint, int up_to_derivative) {
+    addConstraint(derivative_order::POSITION, constraint);
+    for (int i = 1; i <= up_to_derivative; ++i) constraints_[i] = ConstraintValue(D_, 0.0);
+  }
+  void makeStartOrEnd(double value, int up_to_derivative) { makeStartOrEnd(ConstraintValue(D_, value), up_to_derivative); }
+  bool hasConstraint(int derivative_order) const { return constraints_.find(derivative_order) != constraints_.end(); }
+  bool getConstraint(int derivative_order, ConstraintValue* constraint) const {
+    const auto it = constraints_.find(derivative_order);
+    if (it == constraints_.end()) return false;
+    if (constraint) *constraint = it->second;
+    return true;
+  }
+  bool removeConstraint(int type) { return constraints_.erase(type) > 0; }
+  size_t getNumberOfConstraints() const { return constraints_.size(); }
+  const Constraints& constraints() const { return constraints_; }
+
+ private:
+  size_t D_;
+  Constraints constraints_;
+};
+
+// ---- Segment / Trajectory (eth/segment.h, eth/trajectory.h) -------------------------------------------------------------
+class Segment {
+ public:
+  typedef std::vector<Segment> Vector;
+  Segment() : time_(0.0), coef_(b200::kD * b200::kN, 0.0) {}
+  int N() const { return b200::kN; }
+  int D() const { return b200::kD; }
+  double getTime() const { return time_; }
+  void setTime(double t) { time_ = t; }
+  // coefficients of dimension `dim`, increasing powers (eth/polynomial.h:35-37)
+  const double* coefficients(int dim) const { return coef_.data() + dim * b200::kN; }
+  double* coefficients(int dim) { return coef_.data() + dim * b200::kN; }
+  const double* data() const { return coef_.data(); }
+
+ private:
+  double time_;
+  std::vector<double> coef_;
+};
+
+class Trajectory {
+ public:
+  Trajectory() {}
+  int D() const { return b200::kD; }
+  int N() const { return b200::kN; }
+  int K() const { return (int)segments_.size(); }
+  bool empty() const { return segments_.empty(); }
+  void clear() { segments_.clear(); }
+  void setSegments(const Segment::Vector& segments) { segments_ = segments; }
+  void getSegments(Segment::Vector* segments) const {
+    if (segments) *segments = segments_;
+  }
+  const Segment::Vector& segments() const { return segments_; }
+  double getMinTime() const { return 0.0; }
+  double getMaxTime() const {  // accumulated in segment order (eth/trajectory.h:76-83)
+    double t = 0.0;
+    for (const Segment& s : segments_) t += s.getTime();
+    return t;
+  }
+  std::vector<double> getSegmentTimes() const {
+    std::vector<double> t;
+    for (const Segment& s : segments_) t.push_back(s.getTime());
+    return t;
+  }
+  // Trajectory::evaluate(t, derivative) (eth/trajectory.cpp:55-87); past the end: prints, returns zeros.
+  Vector evaluate(double t, int derivative = derivative_order::POSITION) const {
+    Vector out(b200::kD, 0.0);
+    if (segments_.empty()) return out;
+    std::vector<double> coef, times;
+    pack(&coef, &times);
+    uint8_t ok = 0;
+    b200::Context& c = b200::Context::instance();
+    c.check(tg_evaluate_batch(c.get(), K(), coef.data(), times.data(), 1, &t, derivative, out.data(), &ok), "tg_evaluate_batch");
+    if (!ok) std::printf("[Trajectory]: time out of range, returning zeros\n");
+    return out;
+  }
+  // evaluateRange (eth/trajectory.cpp:93-151): the dt walk of the sampler, derivative `derivative` only
+  void evaluateRange(double t_start, double t_end, double dt, int derivative, std::vector<Vector>* result) const;
+  // maxima of |v|, |a|, |j| over the whole trajectory for the three dimension groups (eth/trajectory.cpp:422-565)
+  void computeMaxDerivativesHorizontal(double* v_max, double* a_max, double* j_max) const { max_of_group(0, v_max, a_max, j_max); }
+  void computeMaxDerivativesVertical(double* v_max, double* a_max, double* j_max) const { max_of_group(1, v_max, a_max, j_max); }
+  void computeMaxDerivativesHeading(double* v_max, double* a_max, double* j_max) const { max_of_group(2, v_max, a_max, j_max); }
+  // eth/trajectory.cpp:598-692, argument order of the reference
+  bool scaleSegmentTimesToMeetConstraints(double v_max_horizontal, double v_max_vertical, double a_max_horizontal, double a_max_vertical,
+                                          double j_max_horizontal, double j_max_vertical, double v_max_heading, double a_max_heading,
+                                          double j_max_heading) {
+    if (segments_.empty()) return true;
+    std::vector<double> coef, times;
+    pack(&coef, &times);
+    const double L[9] = {v_max_horizontal, v_max_vertical, a_max_horizontal, a_max_vertical, j_max_horizontal,
+                         j_max_vertical,   v_max_heading,  a_max_heading,    j_max_heading};
+    const int seg_off[2] = {0, K()};
+    int passes = 0;
+    uint8_t within = 0;
+    b200::Context& c = b200::Context::instance();
+    c.check(tg_scale_times_batch(c.get(), 1, seg_off, coef.data(), times.data(), L, &passes, &within), "tg_scale_times_batch");
+    unpack(coef, times);
+    return within != 0;
+  }
+
+  // marshalling helpers (also used by the optimisers)
+  void pack(std::vector<double>* coef, std::vector<double>* times) const {
+    coef->resize((size_t)K() * b200::kD * b200::kN);
+    times->resize(K());
+    for (int i = 0; i < K(); ++i) {
+      (*times)[i] = segments_[i].getTime();
+      for (int e = 0; e < b200::kD * b200::kN; ++e) (*coef)[(size_t)i * b200::kD * b200::kN + e] = segments_[i].data()[e];
+    }
+  }
+  void unpack(const std::vector<double>& coef, const std::vector<double>& times) {
+    segments_.assign(times.size(), Segment());
+    for (size_t i = 0; i < times.size(); ++i) {
+      segments_[i].setTime(times[i]);
+      for (int d = 0; d < b200::kD; ++d)
+        for (int k = 0; k < b200::kN; ++k) segments_[i].coefficients(d)[k] = coef[(i * b200::kD + d) * b200::kN + k];
+    }
+  }
+
+ private:
+  void max_of_group(int group, double* v_max, double* a_max, double* j_max) const {
+    double m[3] = {-1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
+    if (!segments_.empty()) {
+      std::vector<double> coef, times, maxima((size_t)K() * 9);
+      pack(&coef, &times);
+      b200::Context& c = b200::Context::instance();
+      c.check(tg_extrema_batch(c.get(), K(), coef.data(), times.data(), maxima.data()), "tg_extrema_batch");
+      for (int i = 0; i < K(); ++i)
+        for (int q = 0; q < 3; ++q)
+          if (m[q] < maxima[(size_t)i * 9 + group * 3 + q]) m[q] = maxima[(size_t)i * 9 + group * 3 + q];
+    }
+    if (v_max) *v_max = m[0];
+    if (a_max) *a_max = m[1];
+    if (j_max) *j_max = m[2];
+  }
+  Segment::Vector segments_;
+};
+
+// ---- sampling (eth/trajectory_sampling.h:44, eth_mav_msgs/eigen_mav_msgs.h:188-240) -------------------------------------
+// The fields of EigenTrajectoryPoint the sampler fills (eth/trajectory_sampling.cpp:73-88).
+struct TrajectoryPoint {
+  typedef std::vector<TrajectoryPoint> Vector;
+  int64_t time_from_start_ns;
+  double position_W[3], velocity_W[3], acceleration_W[3], jerk_W[3], snap_W[3];
+  double yaw;                 // getYaw(): yawFromQuaternion(quaternionFromYaw(heading)) (eth_mav_msgs/common.h:130-140)
+  double yaw_rate, yaw_acc;   // v[3], a[3]
+  double heading_raw;         // p[3] before the quaternion round trip
+};
+
+inline bool sampleWholeTrajectory(const Trajectory& trajectory, double sampling_interval, TrajectoryPoint::Vector* states) {
+  if (!states) return false;
+  states->clear();
+  if (trajectory.empty() || !(sampling_interval > 0.0)) {
+    std::printf("[sampleWholeTrajectory]: empty trajectory or non-positive sampling interval\n");
+    return false;
+  }
+  std::vector<double> coef, times;
+  trajectory.pack(&coef, &times);
+  const int seg_off[2] = {0, trajectory.K()};
+  int count = 0;
+  b200::Context& c = b200::Context::instance();
+  c.check(tg_sample_batch(c.get(), 1, seg_off, coef.data(), times.data(), sampling_interval, &count, nullptr, nullptr), "tg_sample_batch");
+  if (count <= 0) return false;
+  std::vector<double> xyzh((size_t)count * 4), full((size_t)count * 19);
+  c.check(tg_sample_batch(c.get(), 1, seg_off, coef.data(), times.data(), sampling_interval, &count, xyzh.data(), full.data()), "tg_sample_batch");
+  states->resize(count);
+  for (int i = 0; i < count; ++i) {
+    TrajectoryPoint& s = (*states)[i];
+    const double* f = &full[(size_t)i * 19];  // p4 v4 a4 j3 s3 yaw
+    s.time_from_start_ns = (int64_t)((0.0 + sampling_interval * (double)i) * 1.e9);  // eth/trajectory_sampling.cpp:98
+    for (int k = 0; k < 3; ++k) {
+      s.position_W[k] = f[k];
+      s.velocity_W[k] = f[4 + k];
+      s.acceleration_W[k] = f[8 + k];
+      s.jerk_W[k] = f[12 + k];
+      s.snap_W[k] = f[15 + k];
+    }
+    s.heading_raw = f[3];
+    s.yaw_rate = f[7];
+    s.yaw_acc = f[11];
+    s.yaw = f[18];
+  }
+  return true;
+}
+
+inline void Trajectory::evaluateRange(double t_start, double t_end, double dt, int derivative, std::vector<Vector>* result) const {
+  // the node only ever samples the whole trajectory from 0 (eth/trajectory_sampling.cpp:119-124)
+  if (!result) return;
+  result->clear();
+  if (t_start != 0.0 || derivative < 0 || derivative > 4) {
+    std::printf("[Trajectory]: evaluateRange is supported from t_start = 0 for derivatives 0..4\n");
+    return;
+  }
+  TrajectoryPoint::Vector pts;
+  if (!sampleWholeTrajectory(*this, dt, &pts)) return;
+  for (const TrajectoryPoint& p : pts) {
+    if ((double)p.time_from_start_ns * 1e-9 > t_end) break;
+    const double* src = derivative == 0 ? p.position_W : derivative == 1 ? p.velocity_W : derivative == 2 ? p.acceleration_W : derivative == 3 ? p.jerk_W : p.snap_W;
+    Vector v(b200::kD, 0.0);
+    for (int k = 0; k < 3; ++k) v[k] = src[k];
+    v[3] = derivative == 0 ? p.heading_raw : derivative == 1 ? p.yaw_rate : derivative == 2 ? p.yaw_acc : 0.0;
+    result->push_back(v);
+  }
+}
+
+// ---- vertex marshalling ------------------------------------------------------------------------------------------------
+namespace b200 {
+// masks / fixed values of a vertex list; constraints above derivative 4 are dropped with a warning (lin_impl.h:84-102)
+inline bool pack_vertices(const Vertex::Vector& vertices, std::vector<uint8_t>* mask, std::vector<double>* vals) {
+  mask->assign(vertices.size(), 0);
+  vals->assign(vertices.size() * kHalf * kD, 0.0);
+  for (size_t v = 0; v < vertices.size(); ++v) {
+    if (vertices[v].D() != (size_t)kD) {
+      std::printf("[PolynomialOptimization]: the B200 path is built for 4 dimensions (x, y, z, heading)\n");
+      return false;
+    }
+    for (const auto& kv : vertices[v].constraints()) {
+      if (kv.first < 0 || kv.first >= kHalf) {
+        std::printf("[PolynomialOptimization]: constraint of derivative %d ignored (highest possible: %d)\n", kv.first, kHalf - 1);
+        continue;
+      }
+      (*mask)[v] |= (uint8_t)(1u << kv.first);
+      for (int d = 0; d < kD; ++d) (*vals)[(v * kHalf + kv.first) * kD + d] = kv.second[d];
+    }
+  }
+  return true;
+}
+}  // namespace b200
+
+// ---- PolynomialOptimization<N> (lin.h:60-233) -----------------------------------------------------------------------------
+template <int _N = 10>
+class PolynomialOptimization {
+  static_assert(_N == 10, "the B200 kernels are built for N = 10 coefficients (the node's only instantiation, node.cpp:1063)");
+
+ public:
+  enum { N = _N };
+  explicit PolynomialOptimization(size_t dimension) : dimension_(dimension), derivative_to_optimize_(derivative_order::INVALID), cost_(0.0), solved_(false) {}
+
+  // lin_impl.h:61-106
+  bool setupFromVertices(const Vertex::Vector& vertices, const std::vector<double>& segment_times, int derivative_to_optimize) {
+    if (!(derivative_to_optimize >= 0 && derivative_to_optimize <= b200::kHalf - 1)) {
+      std::printf("[PolynomialOptimization]: you tried to optimize a derivative that is not possible\n");
+      return false;
+    }
+    if (dimension_ != (size_t)b200::kD) {
+      std::printf("[PolynomialOptimization]: the B200 path is built for 4 dimensions (x, y, z, heading)\n");
+      return false;
+    }
+    if (vertices.size() < 2 || segment_times.size() != vertices.size() - 1) {
+      std::printf("[PolynomialOptimization]: size of times must be one less than positions\n");
+      return false;
+    }
+    derivative_to_optimize_ = derivative_to_optimize;
+    vertices_ = vertices;
+    segment_times_ = segment_times;
+    solved_ = false;
+    return b200::pack_vertices(vertices_, &mask_, &vals_);
+  }
+  // lin_impl.h:288-304
+  void updateSegmentTimes(const std::vector<double>& segment_times) {
+    if (segment_times.size() != segment_times_.size()) {
+      std::printf("[PolynomialOptimization]: number of segment times does not match\n");
+      return;
+    }
+    segment_times_ = segment_times;
+    solved_ = false;
+  }
+  // lin_impl.h:340-373 (+ updateSegmentsFromCompactConstraints 263-282)
+  bool solveLinear() {
+    if (vertices_.empty()) return false;
+    const int V = (int)vertices_.size();
+    const int vtx_off[2] = {0, V};
+    coef_.resize((size_t)(V - 1) * b200::kD * b200::kN);
+    b200::Context& c = b200::Context::instance();
+    const int r = derivative_to_optimize_ < 2 ? 2 : derivative_to_optimize_;  // the kernels integrate r in {2, 3, 4}
+    const int rc = tg_solve_linear_batch(c.get(), 1, vtx_off, mask_.data(), vals_.data(), segment_times_.data(), r, coef_.data(), &cost_);
+    if (rc != TG_OK) {
+      std::printf("[PolynomialOptimization]: solveLinear failed: %s\n", tg_last_error(c.get()));
+      return false;
+    }
+    solved_ = true;
+    return true;
+  }
+  double computeCost() const { return cost_; }  // lin_impl.h:127-141
+  void getSegmentTimes(std::vector<double>* segment_times) const {
+    if (segment_times) *segment_times = segment_times_;
+  }
+  void getVertices(Vertex::Vector* vertices) const {
+    if (vertices) *vertices = vertices_;
+  }
+  void getSegments(Segment::Vector* segments) const {  // lin.h:177
+    Trajectory t;
+    getTrajectory(&t);
+    t.getSegments(segments);
+  }
+  void getTrajectory(Trajectory* trajectory) const {  // lin.h:153-160
+    if (!trajectory) return;
+    trajectory->clear();
+    if (solved_) trajectory->unpack(coef_, segment_times_);
+  }
+  size_t getDimension() const { return dimension_; }
+  size_t getNumberSegments() const { return segment_times_.size(); }
+  int getDerivativeToOptimize() const { return derivative_to_optimize_; }
+
+  // used by PolynomialOptimizationNonLinear
+  const std::vector<uint8_t>& vertexMasks() const { return mask_; }
+  const std::vector<double>& vertexValues() const { return vals_; }
+  void adopt(const std::vector<double>& times, const std::vector<double>& coef, double cost) {
+    segment_times_ = times;
+    coef_ = coef;
+    cost_ = cost;
+    solved_ = true;
+  }
+
+ private:
+  size_t dimension_;
+  int derivative_to_optimize_;
+  Vertex::Vector vertices_;
+  std::vector<double> segment_times_;
+  std::vector<uint8_t> mask_;
+  std::vector<double> vals_;
+  std::vector<double> coef_;
+  double cost_;
+  bool solved_;
+};
+
+// ---- NonlinearOptimizationParameters (nl.h:35-110): the fields the production path reads ---------------------------------
+struct NonlinearOptimizationParameters {
+  enum TimeAllocMethod { kSquaredTime, kRichterTime, kMellingerOuterLoop, kSquaredTimeAndConstraints, kRichterTimeAndConstraints, kUnknown };
+  double f_abs = -1, f_rel = 0.05, x_rel = 0.1, x_abs = -1;  // node.cpp:884-887
+  int max_iterations = 10;                                   // NLopt maxeval (config/private/trajectory_generation.yaml:10)
+  TimeAllocMethod time_alloc_method = kMellingerOuterLoop;   // config/private/trajectory_generation.yaml:7
+  bool print_debug_info = false, print_debug_info_time_allocation = false;
+};
+
+struct OptimizationInfo {  // nl.h:112-130
+  int n_iterations = 0;
+  int stopping_reason = -1;  // NLopt-style code
+  double cost_trajectory = 0.0;
+  int n_scale_passes = 0;
+};
+
+// ---- PolynomialOptimizationNonLinear<N> (nl.h:147-197) -------------------------------------------------------------------
+template <int _N = 10>
+class PolynomialOptimizationNonLinear {
+ public:
+  enum { N = _N };
+  PolynomialOptimizationNonLinear(size_t dimension, const NonlinearOptimizationParameters& parameters)
+      : poly_opt_(dimension), optimization_parameters_(parameters) {
+    for (double& l : limits_) l = 3.40282346638528859812e+38;  // "no constraint"
+  }
+  // nl_impl.h:51-82
+  bool setupFromVertices(const Vertex::Vector& vertices, const std::vector<double>& segment_times, int derivative_to_optimize) {
+    return poly_opt_.setupFromVertices(vertices, segment_times, derivative_to_optimize);
+  }
+  // nl_impl.h:538-565; the (dimension, derivative) -> limit mapping of scaleSegmentTimesWithViolation (355-381):
+  // dimensions 0,1 -> horizontal, 2 -> vertical, 3 -> heading; a later call overwrites an earlier one
+  bool addMaximumMagnitudeConstraint(int dimension, int derivative, double maximum_value) {
+    if (derivative < derivative_order::VELOCITY || derivative > derivative_order::JERK || dimension < 0 || dimension > 3) {
+      std::printf("[PolynomialOptimizationNonLinear]: constraint (dimension %d, derivative %d) has no effect on this path\n", dimension, derivative);
+      return false;
+    }
+    const int d = derivative - 1;  // 0 v, 1 a, 2 j
+    int idx;                       // tg_params::limits order: v_h v_v a_h a_v j_h j_v v_hdg a_hdg j_hdg
+    if (dimension <= 1) idx = 2 * d;
+    else if (dimension == 2) idx = 2 * d + 1;
+    else idx = 6 + d;
+    limits_[idx] = maximum_value;
+    return true;
+  }
+  // nl_impl.h:89-118: returns the NLopt-style result code (the node accepts >= 1 except 6, and -1; node.cpp:1138-1149)
+  int optimize() {
+    if (optimization_parameters_.time_alloc_method != NonlinearOptimizationParameters::kMellingerOuterLoop) {
+      std::printf("[PolynomialOptimizationNonLinear]: only kMellingerOuterLoop (the production default) runs on the B200 path\n");
+      return -1;
+    }
+    std::vector<double> times;
+    poly_opt_.getSegmentTimes(&times);
+    const int S = (int)times.size(), V = S + 1;
+    if (S < 1) return -1;
+    tg_params P;
+    tg_default_params(&P);
+    P.derivative_to_optimize = poly_opt_.getDerivativeToOptimize() < 2 ? 2 : poly_opt_.getDerivativeToOptimize();
+    P.max_evals = optimization_parameters_.max_iterations;
+    P.f_rel = optimization_parameters_.f_rel;
+    P.x_rel = optimization_parameters_.x_rel;
+    for (int i = 0; i < 9; ++i) P.limits[i] = limits_[i];
+    const int vtx_off[2] = {0, V};
+    std::vector<double> coef((size_t)S * b200::kD * b200::kN);
+    int code = -1, evals = 0, passes = 0;
+    double cost = 0.0;
+    b200::Context& c = b200::Context::instance();
+    const int rc = tg_time_alloc_batch(c.get(), 1, vtx_off, poly_opt_.vertexMasks().data(), poly_opt_.vertexValues().data(), times.data(), &P,
+                                       coef.data(), &code, &evals, &passes, &cost);
+    if (rc != TG_OK) {
+      std::printf("[PolynomialOptimizationNonLinear]: optimize failed: %s\n", tg_last_error(c.get()));
+      return -1;  // nlopt::FAILURE
+    }
+    poly_opt_.adopt(times, coef, cost);
+    optimization_info_.n_iterations = evals;
+    optimization_info_.stopping_reason = code;
+    optimization_info_.cost_trajectory = cost;
+    optimization_info_.n_scale_passes = passes;
+    return code;
+  }
+  void getTrajectory(Trajectory* trajectory) const { poly_opt_.getTrajectory(trajectory); }
+  const PolynomialOptimization<_N>& getPolynomialOptimizationRef() const { return poly_opt_; }
+  PolynomialOptimization<_N>& getPolynomialOptimizationRef() { return poly_opt_; }
+  OptimizationInfo getOptimizationInfo() const { return optimization_info_; }
+
+ private:
+  PolynomialOptimization<_N> poly_opt_;
+  NonlinearOptimizationParameters optimization_parameters_;
+  OptimizationInfo optimization_info_;
+  double limits_[9];
+};
+
+// ---- batch entry: the numeric core of optimize() / findTrajectory for many paths (node.cpp:620-851, 857-1209) -------------
+struct Waypoint {
+  double x, y, z, heading;
+  bool stop_at;
+};
+struct InitialState {  // the TrackerCommand fields findTrajectory reads (node.cpp:925-957)
+  double heading;
+  double velocity[4], acceleration[4], jerk[4];  // x y z heading-rate
+};
+struct PathResult {
+  tg_result info;
+  std::vector<Waypoint> waypoints;    // after subdivision
+  Trajectory trajectory;              // final segments
+  std::vector<double> samples_xyzh;   // [M][4] as getTrajectoryReference emits them (node.cpp:1578-1602)
+};
+
+class TrajectoryGeneratorBatch {
+ public:
+  explicit TrajectoryGeneratorBatch(int device = 0) : device_(device) { tg_default_params(&params); }
+  tg_params params;  // production defaults; edit before optimize()
+
+  // initial_states: empty (no prepended state, node.cpp:508-510) or one per path
+  bool optimize(const std::vector<std::vector<Waypoint>>& paths, const std::vector<InitialState>& initial_states, std::vector<PathResult>* out) {
+    if (!out) return false;
+    const int B = (int)paths.size();
+    if (B < 1 || (!initial_states.empty() && (int)initial_states.size() != B)) return false;
+    std::vector<int> wp_off(B + 1, 0);
+    for (int p = 0; p < B; ++p) wp_off[p + 1] = wp_off[p] + (int)paths[p].size();
+    std::vector<double> wp((size_t)wp_off[B] * 4);
+    std::vector<uint8_t> stop(wp_off[B]);
+    for (int p = 0; p < B; ++p)
+      for (size_t i = 0; i < paths[p].size(); ++i) {
+        const Waypoint& w = paths[p][i];
+        double* dst = &wp[((size_t)wp_off[p] + i) * 4];
+        dst[0] = w.x; dst[1] = w.y; dst[2] = w.z; dst[3] = w.heading;
+        stop[wp_off[p] + i] = w.stop_at ? 1 : 0;
+      }
+    std::vector<double> init14;
+    if (!initial_states.empty()) {
+      init14.resize((size_t)B * 14);
+      for (int p = 0; p < B; ++p) {
+        double* d = &init14[(size_t)p * 14];
+        d[0] = 1.0;
+        d[1] = initial_states[p].heading;
+        for (int k = 0; k < 4; ++k) { d[2 + k] = initial_states[p].velocity[k]; d[6 + k] = initial_states[p].acceleration[k]; d[10 + k] = initial_states[p].jerk[k]; }
+      }
+    }
+    b200::Context& c = b200::Context::instance(device_);
+    std::vector<tg_result> res(B);
+    long long totals[2] = {0, 0};
+    int rc = tg_optimize_batch(c.get(), B, wp_off.data(), wp.data(), stop.data(), init14.empty() ? nullptr : init14.data(), &params, 0, res.data(), totals);
+    if (rc != TG_OK) {
+      std::printf("[TrajectoryGeneratorBatch]: %s\n", tg_last_error(c.get()));
+      return false;
+    }
+    std::vector<int> seg_off(B + 1), smp_off(B + 1);
+    std::vector<double> o_wp((size_t)(totals[0] + B) * 4), times((size_t)totals[0]), coef((size_t)totals[0] * 40), samples((size_t)totals[1] * 4);
+    rc = tg_fetch_outputs(c.get(), seg_off.data(), o_wp.data(), times.data(), coef.data(), smp_off.data(), samples.data());
+    if (rc != TG_OK) return false;
+    out->assign(B, PathResult());
+    for (int p = 0; p < B; ++p) {
+      PathResult& r = (*out)[p];
+      r.info = res[p];
+      const int s0 = seg_off[p], s1 = seg_off[p + 1];
+      if (s1 > s0) {
+        for (int v = s0 + p; v <= s1 + p; ++v) r.waypoints.push_back(Waypoint{o_wp[(size_t)v * 4], o_wp[(size_t)v * 4 + 1], o_wp[(size_t)v * 4 + 2], o_wp[(size_t)v * 4 + 3], false});
+        r.trajectory.unpack(std::vector<double>(coef.begin() + (size_t)s0 * 40, coef.begin() + (size_t)s1 * 40),
+                            std::vector<double>(times.begin() + s0, times.begin() + s1));
+      }
+      r.samples_xyzh.assign(samples.begin() + (size_t)smp_off[p] * 4, samples.begin() + (size_t)smp_off[p + 1] * 4);
+    }
+    return true;
+  }
+
+ private:
+  int device_;
+};
+
+}  // namespace eth_trajectory_generation
+
+#endif  // ETH_TRAJECTORY_GENERATION_B200_HPP_

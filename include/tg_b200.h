@@ -118,6 +118,14 @@ int tg_fetch_outputs(tg_ctx* ctx, int* seg_off, double* wp, double* times, doubl
  *   vval[totV][5][4] fixed values; times[totS]; r = derivative_to_optimize.  Outputs: coef[totS*40], cost[B]. */
 int tg_solve_linear_batch(tg_ctx* ctx, int B, const int* vtx_off, const uint8_t* vmask, const double* vval, const double* times, int r,
                           double* coef, double* cost);
+/* tg_time_alloc_batch = PolynomialOptimizationNonLinear<10>::setupFromVertices + addMaximumMagnitudeConstraint x12 +
+ *   optimize() + getTrajectory (nl.h:147-197; nl_impl.h:51-82, 538-565, 89-118 -> optimizeTimeMellingerOuterLoop 159-234 with
+ *   the objective / forward-difference gradient of 256-333 -> scaleSegmentTimesWithViolation 335-427) for B problems given
+ *   as vertices.  times[totS]: initial segment times in, allocated + stretched times out.  params: derivative_to_optimize,
+ *   max_evals, f_rel, x_rel and limits are read.  Outputs (any may be NULL): coef[totS*40] of the final solve,
+ *   nlopt_code[B] (NLopt-style result code), n_evals[B] (OptimizationInfo::n_iterations), n_scale_passes[B], final_cost[B]. */
+int tg_time_alloc_batch(tg_ctx* ctx, int B, const int* vtx_off, const uint8_t* vmask, const double* vval, double* times,
+                        const tg_params* params, double* coef, int* nlopt_code, int* n_evals, int* n_scale_passes, double* final_cost);
 /* tg_sample_batch = sampleWholeTrajectory (eth/trajectory_sampling.cpp:119-124, 49-104) for B trajectories given as
  *   seg_off[B+1], coef, times.  Two-call convention: with samples == NULL only counts[B] is filled.
  *   samples: [sum counts][4] (x y z heading); full (optional): [sum counts][19] = p4 v4 a4 j3 s3 yaw. */

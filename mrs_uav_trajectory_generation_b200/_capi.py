@@ -112,6 +112,7 @@ class Library:
         L.tg_optimize_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _u8p, _dp, C.POINTER(Params), C.c_int, C.c_void_p, _llp]
         L.tg_fetch_outputs.argtypes = [C.c_void_p, _ip, _dp, _dp, _dp, _ip, _dp]
         L.tg_solve_linear_batch.argtypes = [C.c_void_p, C.c_int, _ip, _u8p, _dp, _dp, C.c_int, _dp, _dp]
+        L.tg_time_alloc_batch.argtypes = [C.c_void_p, C.c_int, _ip, _u8p, _dp, _dp, C.POINTER(Params), _dp, _ip, _ip, _ip, _dp]
         L.tg_sample_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_double, _ip, _dp, _dp]
         L.tg_evaluate_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, _dp, _u8p]
         L.tg_extrema_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
@@ -257,6 +258,25 @@ class Context:
         cost = np.empty(B)
         self._check(self.L.lib.tg_solve_linear_batch(self.h, B, _p(vtx_off, _ip), _p(vmask, _u8p), _p(vval), _p(times), int(r), _p(coef), _p(cost)))
         return coef, cost
+
+    def time_alloc_batch(self, vtx_off, vmask, vval, times, params=None):
+        """PolynomialOptimizationNonLinear::optimize() for B problems given as vertices.  Returns a dict with the allocated
+        times, the coefficients of the final solve, nlopt_code / n_evals / n_scale_passes / final_cost per problem."""
+        vtx_off = np.ascontiguousarray(vtx_off, dtype=np.int32)
+        vmask = np.ascontiguousarray(vmask, dtype=np.uint8)
+        vval = np.ascontiguousarray(vval, dtype=np.float64)
+        times = np.array(times, dtype=np.float64, copy=True)
+        B = len(vtx_off) - 1
+        totS = int(vtx_off[-1]) - B
+        P = params or self.L.default_params()
+        coef = np.empty((totS, D, N))
+        code = np.zeros(B, dtype=np.int32)
+        evals = np.zeros(B, dtype=np.int32)
+        passes = np.zeros(B, dtype=np.int32)
+        cost = np.zeros(B)
+        self._check(self.L.lib.tg_time_alloc_batch(self.h, B, _p(vtx_off, _ip), _p(vmask, _u8p), _p(vval), _p(times), C.byref(P), _p(coef),
+                                                   _p(code, _ip), _p(evals, _ip), _p(passes, _ip), _p(cost)))
+        return {"times": times, "coef": coef, "nlopt_code": code, "n_evals": evals, "n_scale_passes": passes, "final_cost": cost}
 
     def sample_batch(self, seg_off, coef, times, dt, full=False):
         seg_off = np.ascontiguousarray(seg_off, dtype=np.int32)

@@ -141,6 +141,24 @@ int tg_solve_linear_batch(tg_ctx* ctx, int B, const int* vtx_off, const uint8_t*
   });
 }
 
+int tg_time_alloc_batch(tg_ctx* ctx, int B, const int* vtx_off, const uint8_t* vmask, const double* vval, double* times,
+                        const tg_params* params, double* coef, int* nlopt_code, int* n_evals, int* n_scale_passes, double* final_cost) {
+  return tg_guard(ctx, [&]() -> int {
+    if (B < 1 || !vtx_off || !vmask || !vval || !times || !params || params->derivative_to_optimize < 2 || params->derivative_to_optimize > 4 ||
+        params->max_evals < 1) {
+      ctx->err = "invalid argument";
+      return TG_ERR_INVALID;
+    }
+    tg::Params P;
+    std::memcpy(&P, params, sizeof(P));
+    ctx->be.timer_start();
+    const bool ok = ctx->pipe.time_alloc_batch(B, vtx_off, vmask, vval, times, P, coef, nlopt_code, n_evals, n_scale_passes, final_cost);
+    ctx->last_ms = ctx->be.timer_stop();
+    if (!ok) { ctx->err = "every problem needs at least two vertices"; return TG_ERR_INVALID; }
+    return TG_OK;
+  });
+}
+
 int tg_sample_batch(tg_ctx* ctx, int B, const int* seg_off, const double* coef, const double* times, double dt, int* counts,
                     double* samples, double* full) {
   return tg_guard(ctx, [&]() -> int {

@@ -142,26 +142,7 @@ class Pipeline {
     be_.d2h(stats, b.stats, sizeof(stats));
     const int ws = stats[0], ows = stats[2];
     if (P.run_time_alloc) {
-      b.xeval = scratch_.template alloc<double>(totS);
-      b.x = scratch_.template alloc<double>(totS);
-      b.g = scratch_.template alloc<double>(totS);
-      b.d = scratch_.template alloc<double>(totS);
-      b.hist_s = scratch_.template alloc<double>((size_t)(kLbfgsMem + 1) * totS);
-      b.hist_y = scratch_.template alloc<double>((size_t)(kLbfgsMem + 1) * totS);
-      b.lb = scratch_.template alloc<LbfgsScalars>(B);
-      b.recs = scratch_.template alloc<double>((size_t)totS * 3 * TG_REC_SIZE);
-      b.costs = scratch_.template alloc<double>(totV);
-      b.maxima = scratch_.template alloc<double>((size_t)totS * 9);
-      be_.for_each(B, LbfgsBeginFn{b}); launches(1);
-      for (int e = 0; e < P.max_evals; ++e) {
-        be_.for_each((size_t)totS * 3, SetupMellingerFn{b});
-        be_.solve((size_t)totV, ws, ows, SolveProblemDesc{b, 1, nullptr, nullptr});
-        be_.for_each(B, LbfgsAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel});
-        launches(3);
-      }
-      be_.for_each(B, LbfgsFinishFn{b}); launches(1);
-      // time scaling (nl_impl.h:335-427 -> eth/trajectory.cpp:598-692)
-      scale_loop(b, P.limits);
+      time_alloc_core(b, P, ws, ows);
     } else {
       b.recs = scratch_.template alloc<double>((size_t)totS * TG_REC_SIZE);
     }
@@ -488,6 +469,78 @@ class Pipeline {
     counters.segment_setups += b.totS;
     if (coef) be_.d2h(coef, b.coef, sizeof(double) * (size_t)b.totS * TG_D * TG_N);
     if (cost) be_.d2h(cost, d_cost, sizeof(double) * B);
+    return true;
+  }
+
+  // PolynomialOptimizationNonLinear<10>::optimize() for every problem of the batch: Mellinger outer loop (nl_impl.h:159-234,
+  // objective + forward-difference gradient 256-333 as S+1 batched solves per evaluation) then the time scaling of
+  // scaleSegmentTimesWithViolation (335-427).  Needs b.times (initial), vmask/vval/vfree/np/hbw, coef, ps; leaves the
+  // stretched times in b.times (the caller runs the final solve).
+  void time_alloc_core(BatchPtrs& b, const Params& P, int ws, int ows) {
+    const int B = b.B, totS = b.totS, totV = b.totV;
+    b.xeval = scratch_.template alloc<double>(totS);
+    b.x = scratch_.template alloc<double>(totS);
+    b.g = scratch_.template alloc<double>(totS);
+    b.d = scratch_.template alloc<double>(totS);
+    b.hist_s = scratch_.template alloc<double>((size_t)(kLbfgsMem + 1) * totS);
+    b.hist_y = scratch_.template alloc<double>((size_t)(kLbfgsMem + 1) * totS);
+    b.lb = scratch_.template alloc<LbfgsScalars>(B);
+    b.recs = scratch_.template alloc<double>((size_t)totS * 3 * TG_REC_SIZE);
+    b.costs = scratch_.template alloc<double>(totV);
+    b.maxima = scratch_.template alloc<double>((size_t)totS * 9);
+    be_.for_each(B, LbfgsBeginFn{b}); launches(1);
+    for (int e = 0; e < P.max_evals; ++e) {
+      be_.for_each((size_t)totS * 3, SetupMellingerFn{b});
+      be_.solve((size_t)totV, ws, ows, SolveProblemDesc{b, 1, nullptr, nullptr});
+      be_.for_each(B, LbfgsAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel});
+      launches(3);
+    }
+    be_.for_each(B, LbfgsFinishFn{b}); launches(1);
+    // time scaling (nl_impl.h:335-427 -> eth/trajectory.cpp:598-692)
+    scale_loop(b, P.limits);
+  }
+
+  // PolynomialOptimizationNonLinear<10>::setupFromVertices + addMaximumMagnitudeConstraint + optimize() + getTrajectory
+  // for B problems given as vertices (masks / fixed values) and initial segment times.
+  bool time_alloc_batch(int B, const int* vtx_off, const uint8_t* vmask, const double* vval, double* times, const Params& P, double* coef,
+                        int* nlopt_code, int* n_evals, int* n_scale_passes, double* final_cost) {
+    scratch_.reset();
+    std::vector<int> so(B + 1);
+    for (int p = 0; p <= B; ++p) so[p] = vtx_off[p] - p;
+    for (int p = 0; p < B; ++p)
+      if (so[p + 1] - so[p] < 1) return false;
+    Bare bb = bare_batch(B, so.data(), P.derivative_to_optimize);
+    BatchPtrs& b = bb.b;
+    b.vmask = scratch_.template alloc<uint8_t>(b.totV);
+    b.vval = scratch_.template alloc<double>((size_t)b.totV * TG_HALF * TG_D);
+    b.vfree = scratch_.template alloc<int>((size_t)b.totV + B);
+    b.np = scratch_.template alloc<int>(B);
+    b.hbw = scratch_.template alloc<int>(B);
+    b.times = scratch_.template alloc<double>(b.totS);
+    b.coef = scratch_.template alloc<double>((size_t)b.totS * TG_D * TG_N);
+    be_.h2d(b.vmask, vmask, b.totV);
+    be_.h2d(b.vval, vval, sizeof(double) * (size_t)b.totV * TG_HALF * TG_D);
+    be_.h2d(b.times, times, sizeof(double) * b.totS);
+    be_.for_each(B, PrepareFn{b, 0}); launches(1);
+    int stats[4];
+    be_.d2h(stats, b.stats, sizeof(stats));
+    time_alloc_core(b, P, stats[0], stats[2]);
+    be_.for_each(b.totS, SetupBaseFn{b, b.times});
+    be_.solve((size_t)B, stats[0], stats[2], SolveProblemDesc{b, 0, nullptr, nullptr});
+    launches(2);
+    std::vector<ProbState> ps(B);
+    be_.d2h(ps.data(), b.ps, sizeof(ProbState) * B);
+    for (int p = 0; p < B; ++p) {
+      if (nlopt_code) nlopt_code[p] = ps[p].nlopt_code;
+      if (n_evals) n_evals[p] = ps[p].n_evals;
+      if (n_scale_passes) n_scale_passes[p] = ps[p].n_scale_passes;
+      if (final_cost) final_cost[p] = ps[p].final_cost;
+      const int S = so[p + 1] - so[p];
+      counters.evals += ps[p].n_evals;
+      counters.solves += (long long)ps[p].n_evals * (S == 1 ? 1 : S + 1) + 1;
+    }
+    be_.d2h(times, b.times, sizeof(double) * b.totS);
+    if (coef) be_.d2h(coef, b.coef, sizeof(double) * (size_t)b.totS * TG_D * TG_N);
     return true;
   }
 

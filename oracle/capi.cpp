@@ -93,6 +93,26 @@ int orc_solve_linear(int V, const uint8_t* mask, const double* vals, const doubl
   return 0;
 }
 
+// PolynomialOptimizationNonLinear::optimize() from vertices: Mellinger loop + time scaling + final solve
+int orc_time_alloc(int V, const uint8_t* mask, const double* vals, double* times, int r, const orc_params* prm, double* coeffs, int* code,
+                   int* n_evals, int* n_scale_passes, double* final_cost) {
+  LinearSolver ls;
+  std::vector<double> t(times, times + (V - 1));
+  if (!ls.setup(make_vertices(V, mask, vals), t, r)) return 1;
+  const NodeParams np = to_node(prm);
+  NlInfo info;
+  optimize_time_mellinger(ls, np.nl, np.lim, &info);
+  for (int i = 0; i < ls.S; ++i) {
+    times[i] = ls.seg[i].T;
+    for (int d = 0; d < kD; ++d) std::memcpy(coeffs + ((size_t)i * kD + d) * kN, ls.seg[i].c[d], sizeof(double) * kN);
+  }
+  *code = info.code;
+  *n_evals = info.n_evals;
+  *n_scale_passes = info.n_scale_passes;
+  *final_cost = info.final_cost;
+  return 0;
+}
+
 // dense R for structure tests: R is (n_fixed+n_free)^2 row-major
 int orc_dense_R(int V, const uint8_t* mask, const double* vals, const double* times, int r, double* R) {
   LinearSolver ls;

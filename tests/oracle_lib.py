@@ -160,6 +160,22 @@ def solve_linear(mask, vals, times, r):
     return coeffs, cost.value, dpv[: D * nfree].reshape(D, nfree), (dims[0], dims[1])
 
 
+def time_alloc(mask, vals, times, r=2, params=None):
+    """PolynomialOptimizationNonLinear::optimize() from vertices (Mellinger loop + time scaling + final solve)."""
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    t = np.array(times, dtype=np.float64, copy=True)
+    V = len(mask)
+    coeffs = np.empty((V - 1, D, N))
+    code, ev, passes = C.c_int(0), C.c_int(0), C.c_int(0)
+    cost = C.c_double(0)
+    P = params or default_params()
+    rc = lib().orc_time_alloc(V, _ptr(mask, u8p), _ptr(vals), _ptr(t), int(r), C.byref(P), _ptr(coeffs), C.byref(code),
+                              C.byref(ev), C.byref(passes), C.byref(cost))
+    assert rc == 0
+    return {"times": t, "coef": coeffs, "nlopt_code": code.value, "n_evals": ev.value, "n_scale_passes": passes.value, "final_cost": cost.value}
+
+
 def dense_R(mask, vals, times, r):
     mask = np.ascontiguousarray(mask, dtype=np.uint8)
     vals = np.ascontiguousarray(vals, dtype=np.float64)

@@ -79,6 +79,41 @@ def check_linear_batch(ctx, seed=0, B=24, r=2):
     return worst, exact
 
 
+def check_time_alloc(ctx, seed=21, B=10, r=2):
+    """tg_time_alloc_batch (PolynomialOptimizationNonLinear::optimize from vertices) against the oracle: nlopt code, evaluation
+    and scaling-pass counts exactly; allocated times and coefficients bit for bit."""
+    rng = np.random.default_rng(seed)
+    probs = []
+    for p in range(B):
+        V = int(rng.integers(3, 14))
+        wp = W.random_flier_path(1000 + seed * 100 + p, V)
+        mask = np.zeros(V, np.uint8)
+        vals = np.zeros((V, O.HALF, O.D))
+        for v in range(V):
+            vals[v, 0] = wp[v]
+            if v == 0 or v == V - 1:
+                mask[v] = (1 << (r + 1)) - 1  # makeStartOrEnd(position, r)
+            else:
+                mask[v] = 1
+        times = O.estimate_times(wp)[0]
+        probs.append((mask, vals, times))
+    vtx_off = np.cumsum([0] + [len(m) for m, _, _ in probs]).astype(np.int32)
+    P = ctx.L.default_params(derivative_to_optimize=r)
+    got = ctx.time_alloc_batch(vtx_off, np.concatenate([m for m, _, _ in probs]), np.concatenate([v for _, v, _ in probs]),
+                               np.concatenate([t for _, _, t in probs]), P)
+    exact = True
+    s0 = 0
+    for p, (mask, vals, times) in enumerate(probs):
+        ref = O.time_alloc(mask, vals, times, r, O.default_params(derivative_to_optimize=r))
+        S = len(times)
+        ok = (ref["nlopt_code"] == got["nlopt_code"][p] and ref["n_evals"] == got["n_evals"][p] and ref["n_scale_passes"] == got["n_scale_passes"][p]
+              and np.array_equal(ref["times"], got["times"][s0:s0 + S]) and np.array_equal(ref["coef"], got["coef"][s0:s0 + S])
+              and ref["final_cost"] == got["final_cost"][p])
+        exact = exact and ok
+        s0 += S
+    return exact
+
+
 def check_sampling(ctx, seed=1, B=12):
     rng = np.random.default_rng(seed)
     coefs, times, seg_off = [], [], [0]

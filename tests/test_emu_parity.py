@@ -12,6 +12,11 @@ def test_linear_batch(emu_ctx, oracle, r):
     assert exact, worst
 
 
+@pytest.mark.parametrize("r", [2, 3])
+def test_time_alloc_from_vertices(emu_ctx, oracle, r):
+    assert PC.check_time_alloc(emu_ctx, r=r)
+
+
 def test_sampling(emu_ctx, oracle):
     assert PC.check_sampling(emu_ctx)
 

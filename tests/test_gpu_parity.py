@@ -19,6 +19,11 @@ def test_linear_batch(gpu_ctx, oracle, r):
     assert exact, worst
 
 
+@pytest.mark.parametrize("r", [2, 3])
+def test_time_alloc_from_vertices(gpu_ctx, oracle, r):
+    assert PC.check_time_alloc(gpu_ctx, r=r)
+
+
 def test_sampling(gpu_ctx, oracle):
     assert PC.check_sampling(gpu_ctx, B=32)
 
