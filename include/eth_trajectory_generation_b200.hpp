@@ -583,6 +583,66 @@ class TrajectoryGeneratorBatch {
     return true;
   }
 
+  // MrsTrajectoryGeneration::preprocessPath (node.cpp:431-500) for one path
+  std::vector<Waypoint> preprocessPath(const std::vector<Waypoint>& in, double min_waypoint_distance = 0.05, bool straightener = false,
+                                       double max_deviation = 0.05, double max_hdg_deviation = 0.1) const {
+    std::vector<Waypoint> out;
+    const int V = (int)in.size();
+    if (V < 1) return out;
+    const int wp_off[2] = {0, V};
+    std::vector<double> wp((size_t)V * 4), owp((size_t)V * 4);
+    std::vector<uint8_t> stop(V), ostop(V);
+    for (int i = 0; i < V; ++i) {
+      wp[4 * i] = in[i].x; wp[4 * i + 1] = in[i].y; wp[4 * i + 2] = in[i].z; wp[4 * i + 3] = in[i].heading;
+      stop[i] = in[i].stop_at ? 1 : 0;
+    }
+    int count = 0;
+    b200::Context& c = b200::Context::instance(device_);
+    c.check(tg_preprocess_paths(c.get(), 1, wp_off, wp.data(), stop.data(), min_waypoint_distance, straightener ? 1 : 0, max_deviation, max_hdg_deviation,
+                                &count, owp.data(), ostop.data()), "tg_preprocess_paths");
+    for (int i = 0; i < count; ++i) out.push_back(Waypoint{owp[4 * i], owp[4 * i + 1], owp[4 * i + 2], owp[4 * i + 3], ostop[i] != 0});
+    return out;
+  }
+  // MrsTrajectoryGeneration::findTrajectoryFallback (node.cpp:1215-1395) for one path: samples x y z heading, [M][4].
+  // speed_factor / accel_factor / stopping_time: config/public/trajectory_generation.yaml:47-54
+  std::vector<double> findTrajectoryFallback(const std::vector<Waypoint>& in, double speed_factor = 1.0, double accel_factor = 1.0,
+                                             double stopping_time = 2.0) const {
+    const int V = (int)in.size();
+    std::vector<double> samples;
+    if (V < 2) return samples;
+    const int wp_off[2] = {0, V};
+    std::vector<double> wp((size_t)V * 4);
+    std::vector<uint8_t> stop(V);
+    for (int i = 0; i < V; ++i) {
+      wp[4 * i] = in[i].x; wp[4 * i + 1] = in[i].y; wp[4 * i + 2] = in[i].z; wp[4 * i + 3] = in[i].heading;
+      stop[i] = in[i].stop_at ? 1 : 0;
+    }
+    double L[9];
+    for (int i = 0; i < 9; ++i) L[i] = params.limits[i];
+    L[0] *= speed_factor; L[1] *= speed_factor; L[2] *= accel_factor; L[3] *= accel_factor;  // node.cpp:1296-1300
+    int count = 0;
+    b200::Context& c = b200::Context::instance(device_);
+    c.check(tg_fallback_sample_batch(c.get(), 1, wp_off, wp.data(), stop.data(), L, params.dt, stopping_time, &count, nullptr), "tg_fallback_sample_batch");
+    samples.resize((size_t)count * 4);
+    if (count > 0)
+      c.check(tg_fallback_sample_batch(c.get(), 1, wp_off, wp.data(), stop.data(), L, params.dt, stopping_time, &count, samples.data()), "tg_fallback_sample_batch");
+    return samples;
+  }
+  // MrsTrajectoryGeneration::getWaypointInTrajectoryIdxs (node.cpp:1461-1499) for one path
+  std::vector<int> getWaypointInTrajectoryIdxs(const std::vector<double>& samples_xyzh, const std::vector<Waypoint>& waypoints) const {
+    const int V = (int)waypoints.size(), M = (int)(samples_xyzh.size() / 4);
+    std::vector<int> idxs(V > 0 ? V : 1);
+    if (V < 1 || M < 1) return std::vector<int>();
+    const int wp_off[2] = {0, V}, smp_off[2] = {0, M};
+    std::vector<double> wp((size_t)V * 4);
+    for (int i = 0; i < V; ++i) { wp[4 * i] = waypoints[i].x; wp[4 * i + 1] = waypoints[i].y; wp[4 * i + 2] = waypoints[i].z; wp[4 * i + 3] = waypoints[i].heading; }
+    int count = 0;
+    b200::Context& c = b200::Context::instance(device_);
+    c.check(tg_waypoint_idxs_batch(c.get(), 1, smp_off, samples_xyzh.data(), wp_off, wp.data(), &count, idxs.data()), "tg_waypoint_idxs_batch");
+    idxs.resize(count);
+    return idxs;
+  }
+
  private:
   int device_;
 };

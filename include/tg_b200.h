@@ -148,6 +148,24 @@ int tg_scale_times_batch(tg_ctx* ctx, int B, const int* seg_off, double* coef, d
 int tg_sweep_costs(tg_ctx* ctx, int V, const uint8_t* vmask, const double* vval, int r, long long K, const double* cand,
                    int cand_on_device, double* costs, long long* best_index, double* best_cost);
 
+/* The steps either side of the path, batched, one path per thread --------------------------------
+ * tg_preprocess_paths = MrsTrajectoryGeneration::preprocessPath (src/mrs_trajectory_generation.cpp:431-500): optional path
+ *   straightener (config/public/trajectory_generation.yaml:20-23) then the min_waypoint_distance filter (:27).
+ *   Outputs: out_count[B]; out_wp / out_stop_at have the INPUT layout (problem p writes out_count[p] waypoints from wp_off[p]).
+ * tg_fallback_sample_batch = findTrajectoryFallback (node.cpp:1215-1395): constant-velocity samples along the polyline with
+ *   estimateSegmentTimesBaca times; limits9 already carry fallback_sampling/speed_factor and accel_factor (yaml:47-54);
+ *   stopping_time = fallback_sampling/stopping_time.  Two-call convention: samples == NULL fills counts[B] only.
+ *   samples: [sum counts][4] = x y z heading as getTrajectoryReference emits them.
+ * tg_waypoint_idxs_batch = getWaypointInTrajectoryIdxs (node.cpp:1461-1499): for every path the sample indices at which the
+ *   trajectory passes its waypoints (chord within 0.1 m).  idxs has the waypoint layout (problem p writes counts[p] entries
+ *   from wp_off[p]). */
+int tg_preprocess_paths(tg_ctx* ctx, int B, const int* wp_off, const double* wp, const uint8_t* stop_at, double min_waypoint_distance,
+                        int straightener_enabled, double straightener_max_deviation, double straightener_max_hdg_deviation, int* out_count,
+                        double* out_wp, uint8_t* out_stop_at);
+int tg_fallback_sample_batch(tg_ctx* ctx, int B, const int* wp_off, const double* wp, const uint8_t* stop_at, const double* limits9, double dt,
+                             double stopping_time, int* counts, double* samples);
+int tg_waypoint_idxs_batch(tg_ctx* ctx, int B, const int* smp_off, const double* samples, const int* wp_off, const double* wp, int* counts, int* idxs);
+
 /* Measurement hooks (bench.py) ------------------------------------------------------------------------------------------
  * tg_set_profiling: when on, every kernel launch is bracketed by CUDA events on the context's stream and accumulated
  *   per kernel (serialises the host; never enabled inside a timed region).  tg_get_profile returns the table.

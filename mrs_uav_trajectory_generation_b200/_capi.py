@@ -113,6 +113,9 @@ class Library:
         L.tg_fetch_outputs.argtypes = [C.c_void_p, _ip, _dp, _dp, _dp, _ip, _dp]
         L.tg_solve_linear_batch.argtypes = [C.c_void_p, C.c_int, _ip, _u8p, _dp, _dp, C.c_int, _dp, _dp]
         L.tg_time_alloc_batch.argtypes = [C.c_void_p, C.c_int, _ip, _u8p, _dp, _dp, C.POINTER(Params), _dp, _ip, _ip, _ip, _dp]
+        L.tg_preprocess_paths.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _u8p, C.c_double, C.c_int, C.c_double, C.c_double, _ip, _dp, _u8p]
+        L.tg_fallback_sample_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _u8p, _dp, C.c_double, C.c_double, _ip, _dp]
+        L.tg_waypoint_idxs_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _ip, _dp, _ip, _ip]
         L.tg_sample_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_double, _ip, _dp, _dp]
         L.tg_evaluate_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, _dp, _u8p]
         L.tg_extrema_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
@@ -277,6 +280,53 @@ class Context:
         self._check(self.L.lib.tg_time_alloc_batch(self.h, B, _p(vtx_off, _ip), _p(vmask, _u8p), _p(vval), _p(times), C.byref(P), _p(coef),
                                                    _p(code, _ip), _p(evals, _ip), _p(passes, _ip), _p(cost)))
         return {"times": times, "coef": coef, "nlopt_code": code, "n_evals": evals, "n_scale_passes": passes, "final_cost": cost}
+
+    # ---- the steps either side of the path ---------------------------------------------------------------
+    def preprocess_paths(self, wp_off, wp, stop_at=None, min_waypoint_distance=0.05, straightener=False, max_deviation=0.05, max_hdg_deviation=0.1):
+        """preprocessPath (node.cpp:431-500).  Returns (wp_off_out, wp_out, stop_out) as a compact ragged batch."""
+        wp_off = np.ascontiguousarray(wp_off, dtype=np.int32)
+        wp = np.ascontiguousarray(wp, dtype=np.float64)
+        stop = None if stop_at is None else np.ascontiguousarray(stop_at, dtype=np.uint8)
+        B = len(wp_off) - 1
+        cnt = np.zeros(B, dtype=np.int32)
+        owp = np.zeros_like(wp)
+        ostop = np.zeros(len(wp), dtype=np.uint8)
+        self._check(self.L.lib.tg_preprocess_paths(self.h, B, _p(wp_off, _ip), _p(wp), _p(stop, _u8p), float(min_waypoint_distance), int(bool(straightener)),
+                                                   float(max_deviation), float(max_hdg_deviation), _p(cnt, _ip), _p(owp), _p(ostop, _u8p)))
+        keep = np.concatenate([np.arange(wp_off[p], wp_off[p] + cnt[p]) for p in range(B)]) if B else np.zeros(0, int)
+        off = np.zeros(B + 1, dtype=np.int32)
+        off[1:] = np.cumsum(cnt)
+        return off, owp[keep], ostop[keep]
+
+    def fallback_sample_batch(self, wp_off, wp, stop_at=None, limits=None, dt=0.2, stopping_time=2.0):
+        """findTrajectoryFallback (node.cpp:1215-1395).  Returns (smp_off, samples [M, 4])."""
+        wp_off = np.ascontiguousarray(wp_off, dtype=np.int32)
+        wp = np.ascontiguousarray(wp, dtype=np.float64)
+        stop = None if stop_at is None else np.ascontiguousarray(stop_at, dtype=np.uint8)
+        lim = np.array(list(self.L.default_params().limits) if limits is None else limits, dtype=np.float64)
+        B = len(wp_off) - 1
+        cnt = np.zeros(B, dtype=np.int32)
+        self._check(self.L.lib.tg_fallback_sample_batch(self.h, B, _p(wp_off, _ip), _p(wp), _p(stop, _u8p), _p(lim), float(dt), float(stopping_time),
+                                                        _p(cnt, _ip), None))
+        smp = np.zeros((int(cnt.sum()), 4))
+        if len(smp):
+            self._check(self.L.lib.tg_fallback_sample_batch(self.h, B, _p(wp_off, _ip), _p(wp), _p(stop, _u8p), _p(lim), float(dt), float(stopping_time),
+                                                            _p(cnt, _ip), _p(smp)))
+        off = np.zeros(B + 1, dtype=np.int32)
+        off[1:] = np.cumsum(cnt)
+        return off, smp
+
+    def waypoint_idxs_batch(self, smp_off, samples, wp_off, wp):
+        """getWaypointInTrajectoryIdxs (node.cpp:1461-1499).  Returns a list of index arrays, one per path."""
+        smp_off = np.ascontiguousarray(smp_off, dtype=np.int32)
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        wp_off = np.ascontiguousarray(wp_off, dtype=np.int32)
+        wp = np.ascontiguousarray(wp, dtype=np.float64)
+        B = len(wp_off) - 1
+        cnt = np.zeros(B, dtype=np.int32)
+        idx = np.zeros(max(len(wp), 1), dtype=np.int32)
+        self._check(self.L.lib.tg_waypoint_idxs_batch(self.h, B, _p(smp_off, _ip), _p(samples), _p(wp_off, _ip), _p(wp), _p(cnt, _ip), _p(idx, _ip)))
+        return [idx[wp_off[p]: wp_off[p] + cnt[p]].copy() for p in range(B)]
 
     def sample_batch(self, seg_off, coef, times, dt, full=False):
         seg_off = np.ascontiguousarray(seg_off, dtype=np.int32)

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(128) k_for_each(const F f, const size_t n) {
 
 // one thread per work item with F::kScratch doubles of per-thread scratch in dynamic shared memory, element i of thread
 // t at smem[i * blockDim.x + t] (bank-conflict free; used by the Jenkins-Traub work arrays)
+static_assert(TG_WARR_DEVICE_STRIDE == 128, "strided scratch kernels run 128 threads per block");
 template <class F>
 __global__ void __launch_bounds__(128) k_for_each_scratch(const F f, const size_t n) {
   extern __shared__ double smem[];
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(kOctWarps * 32) k_solve_oct(const D desc, cons
 // finished stores its maximum and takes the next work item of the warp's chunk (chunks of kVmChunk items come from a
 // global counter).  Work arrays: shared memory, element i of thread t at smem[i * blockDim.x + t].
 constexpr int kVmChunk = 64;
-constexpr int kVmThreads = 128;
+constexpr int kVmThreads = TG_WARR_DEVICE_STRIDE;
 template <class F>
 __global__ void __launch_bounds__(kVmThreads) k_vm(const F f, const int n_max, const int* __restrict__ n_dev, int* __restrict__ counter) {
   extern __shared__ double smem[];

@@ -159,6 +159,39 @@ int tg_time_alloc_batch(tg_ctx* ctx, int B, const int* vtx_off, const uint8_t* v
   });
 }
 
+int tg_preprocess_paths(tg_ctx* ctx, int B, const int* wp_off, const double* wp, const uint8_t* stop_at, double min_waypoint_distance, int straightener_enabled,
+                        double straightener_max_deviation, double straightener_max_hdg_deviation, int* out_count, double* out_wp, uint8_t* out_stop_at) {
+  return tg_guard(ctx, [&]() -> int {
+    if (B < 1 || !wp_off || !wp || !out_count) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    ctx->be.timer_start();
+    ctx->pipe.preprocess_batch(B, wp_off, wp, stop_at, min_waypoint_distance, straightener_enabled, straightener_max_deviation,
+                               straightener_max_hdg_deviation, out_count, out_wp, out_stop_at);
+    ctx->last_ms = ctx->be.timer_stop();
+    return TG_OK;
+  });
+}
+
+int tg_fallback_sample_batch(tg_ctx* ctx, int B, const int* wp_off, const double* wp, const uint8_t* stop_at, const double* limits9, double dt,
+                             double stopping_time, int* counts, double* samples) {
+  return tg_guard(ctx, [&]() -> int {
+    if (B < 1 || !wp_off || !wp || !limits9 || !counts || !(dt > 0.0)) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    ctx->be.timer_start();
+    ctx->pipe.fallback_batch(B, wp_off, wp, stop_at, limits9, dt, stopping_time, counts, samples);
+    ctx->last_ms = ctx->be.timer_stop();
+    return TG_OK;
+  });
+}
+
+int tg_waypoint_idxs_batch(tg_ctx* ctx, int B, const int* smp_off, const double* samples, const int* wp_off, const double* wp, int* counts, int* idxs) {
+  return tg_guard(ctx, [&]() -> int {
+    if (B < 1 || !smp_off || !samples || !wp_off || !wp || !counts || !idxs) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    ctx->be.timer_start();
+    ctx->pipe.waypoint_idxs_batch(B, smp_off, samples, wp_off, wp, counts, idxs);
+    ctx->last_ms = ctx->be.timer_stop();
+    return TG_OK;
+  });
+}
+
 int tg_sample_batch(tg_ctx* ctx, int B, const int* seg_off, const double* coef, const double* times, double dt, int* counts,
                     double* samples, double* full) {
   return tg_guard(ctx, [&]() -> int {

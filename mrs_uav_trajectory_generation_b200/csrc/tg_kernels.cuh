@@ -640,6 +640,52 @@ struct VtxProblemFn {
   }
 };
 
+// ---- 10. the steps either side of the path: one thread per path ----------------------------------------------------------
+struct PreprocessFn {
+  const int* wp_off;
+  const double* wp;
+  const uint8_t* stop;  // or null
+  double min_dist, max_dev, max_hdg_dev;
+  int straighten;
+  double* out_wp;       // [totV][4], problem p writes from wp_off[p]
+  uint8_t* out_stop;
+  int* out_count;
+  TG_HD void operator()(size_t p) const {
+    const int v0 = wp_off[p], V = wp_off[p + 1] - v0;
+    out_count[p] = preprocess_path(V, wp + 4 * (size_t)v0, stop ? stop + v0 : nullptr, min_dist, straighten, max_dev, max_hdg_dev, out_wp + 4 * (size_t)v0,
+                                   out_stop + v0);
+  }
+};
+struct FallbackFn {
+  const int* wp_off;
+  const double* wp;
+  const uint8_t* stop;
+  double L[9];
+  double dt, stopping_time;
+  double* vpos;          // scratch [totV][4]
+  int* count;            // [B]
+  const int* smp_off;    // null in the counting pass
+  double* samples;       // null in the counting pass
+  TG_HD void operator()(size_t p) const {
+    const int v0 = wp_off[p], V = wp_off[p + 1] - v0;
+    const int n = fallback_samples(V, wp + 4 * (size_t)v0, stop ? stop + v0 : nullptr, L, dt, stopping_time, vpos + 4 * (size_t)v0,
+                                   samples ? samples + 4 * (size_t)smp_off[p] : nullptr);
+    if (!samples) count[p] = n;
+  }
+};
+struct WaypointIdxFn {
+  const int* smp_off;
+  const double* samples;
+  const int* wp_off;
+  const double* wp;
+  int* idxs;    // [totV], problem p writes from wp_off[p]
+  int* count;   // [B]
+  TG_HD void operator()(size_t p) const {
+    const int m0 = smp_off[p], M = smp_off[p + 1] - m0, v0 = wp_off[p], V = wp_off[p + 1] - v0;
+    count[p] = waypoint_idxs(M, samples + 4 * (size_t)m0, V, wp + 4 * (size_t)v0, idxs + v0);
+  }
+};
+
 }  // namespace tg
 
 #endif  // TG_KERNELS_CUH_

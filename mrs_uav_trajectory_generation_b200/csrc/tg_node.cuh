@@ -371,6 +371,109 @@ TG_HD_NOINLINE int subdivide(int V, const double* __restrict__ wp, const uint8_t
   return n;
 }
 
+// ---- the steps either side of the path; one thread per path ----------------------------------
+// preprocessPath (node.cpp:431-500): optional straightener, then the min-distance filter.  The reference's expression
+// `fabs(radians::diff(a, b) > limit)` (fabs of a bool) is kept as written: it is true iff the SIGNED difference exceeds the limit.
+TG_HD_NOINLINE int preprocess_path(int V, const double* __restrict__ wp, const uint8_t* __restrict__ stop, double min_dist, int straighten,
+                                   double max_dev, double max_hdg_dev, double* __restrict__ out_wp, uint8_t* __restrict__ out_stop) {
+  int n = 0, last_added = 0;
+  for (int i = 0; i < V; ++i) {
+    if (straighten && V >= 3 && i > 0 && i < V - 1) {
+      const double* first = wp + 4 * (size_t)last_added;
+      const double* last = wp + 4 * (size_t)(i + 1);
+      bool segment_is_ok = true;
+      for (int j = last_added + 1; j < i + 1; ++j) {
+        const double* mid = wp + 4 * (size_t)j;
+        const double d = dist_from_segment(mid, first, last);
+        if (d > max_dev || (rad_diff(first[3], mid[3]) > max_hdg_dev) || (rad_diff(last[3], mid[3]) > max_hdg_dev)) {
+          segment_is_ok = false;
+          break;
+        }
+      }
+      if (segment_is_ok) continue;
+    }
+    if (i > 0 && i < V - 1) {
+      const double* first = wp + 4 * (size_t)last_added;
+      const double* last = wp + 4 * (size_t)i;
+      const double dx = first[0] - last[0], dy = first[1] - last[1], dz = first[2] - last[2];
+      if (dsqrt(dx * dx + dy * dy + dz * dz) < min_dist) continue;
+    }
+    for (int d = 0; d < 4; ++d) out_wp[4 * (size_t)n + d] = wp[4 * (size_t)i + d];
+    out_stop[n] = stop ? stop[i] : 0;
+    ++n;
+    last_added = i;
+  }
+  return n;
+}
+
+// findTrajectoryFallback (node.cpp:1215-1395): constant-velocity samples along the polyline with Baca segment times.
+// vpos: scratch [V][4] for the vertex positions with the heading unwrapped (node.cpp:1236-1248).  out == null: count only.
+TG_HD_NOINLINE int fallback_samples(int V, const double* __restrict__ wp, const uint8_t* __restrict__ stop, const double* __restrict__ L, double dt,
+                                    double stopping_time, double* __restrict__ vpos, double* __restrict__ out) {
+  if (V < 2) return 0;
+  double last_heading = wp[3];
+  for (int i = 0; i < V; ++i) {
+    const double heading = srad_unwrap(wp[4 * (size_t)i + 3], last_heading);
+    last_heading = heading;
+    vpos[4 * (size_t)i + 0] = wp[4 * (size_t)i + 0];
+    vpos[4 * (size_t)i + 1] = wp[4 * (size_t)i + 1];
+    vpos[4 * (size_t)i + 2] = wp[4 * (size_t)i + 2];
+    vpos[4 * (size_t)i + 3] = heading;
+  }
+  int n = 0;
+  for (int i = 0; i + 1 < V; ++i) {
+    const double segment_time = segment_time_baca(vpos, 4, i, V, L);
+    int n_samples;
+    double interp_step;
+    if (segment_time > 1e-1) {
+      n_samples = (int)::ceil(segment_time / dt);
+      interp_step = (n_samples > 0) ? 1.0 / (double)n_samples : 0.5;
+    } else {
+      n_samples = 0;
+      interp_step = 0;
+    }
+    if (n_samples > 0 && i == V - 2) n_samples++;
+    const double* a = wp + 4 * (size_t)i;
+    const double* b = wp + 4 * (size_t)(i + 1);
+    for (int j = 0; j < n_samples; ++j) {
+      int reps = 1;
+      if (j == 0 && i > 0 && stop && stop[i]) reps += (int)::round(stopping_time / dt);
+      if (out) {
+        const double c = (double)j * interp_step;
+        const double x = a[0] + c * (b[0] - a[0]), y = a[1] + c * (b[1] - a[1]), z = a[2] + c * (b[2] - a[2]);
+        const double h = rad_interp(a[3], b[3], c);
+        const double ha = 0.5 * h;
+        const double qw = tgdm::dcos(ha), qz = tgdm::dsin(ha);
+        const double yaw = tgdm::datan2(2.0 * (qw * qz + 0.0 * 0.0), 1.0 - 2.0 * (0.0 * 0.0 + qz * qz));
+        for (int k = 0; k < reps; ++k) {
+          double* o = out + 4 * (size_t)(n + k);
+          o[0] = x;
+          o[1] = y;
+          o[2] = z;
+          o[3] = yaw;
+        }
+      }
+      n += reps;
+    }
+  }
+  return n;
+}
+
+// getWaypointInTrajectoryIdxs (node.cpp:1461-1499)
+TG_HD_NOINLINE int waypoint_idxs(int M, const double* __restrict__ samples, int V, const double* __restrict__ wp, int* __restrict__ idxs) {
+  int n = 0, waypoint_idx = 0;
+  if (M < 1 || V < 1) return 0;
+  for (int i = 0; i + 1 < M; ++i) {
+    const double d = dist_from_segment(wp + 4 * (size_t)waypoint_idx, samples + 4 * (size_t)i, samples + 4 * (size_t)(i + 1));
+    if (d < 0.1) {
+      idxs[n++] = i;
+      waypoint_idx++;
+    }
+    if (waypoint_idx == V) break;
+  }
+  return n;
+}
+
 }  // namespace tg
 
 #endif  // TG_NODE_CUH_

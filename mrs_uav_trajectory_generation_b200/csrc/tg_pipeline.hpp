@@ -544,6 +544,76 @@ class Pipeline {
     return true;
   }
 
+  // ---------------------------------------------------------------------------------------------------------------
+  // The steps either side of the path: preprocessPath, findTrajectoryFallback, getWaypointInTrajectoryIdxs
+  void preprocess_batch(int B, const int* wp_off, const double* wp, const uint8_t* stop, double min_dist, int straighten, double max_dev,
+                        double max_hdg_dev, int* out_count, double* out_wp, uint8_t* out_stop) {
+    scratch_.reset();
+    const int totV = wp_off[B];
+    int* d_off = scratch_.template alloc<int>((size_t)B + 1);
+    double* d_wp = scratch_.template alloc<double>((size_t)std::max(totV, 1) * 4);
+    uint8_t* d_stop = stop ? scratch_.template alloc<uint8_t>(std::max(totV, 1)) : nullptr;
+    double* d_owp = scratch_.template alloc<double>((size_t)std::max(totV, 1) * 4);
+    uint8_t* d_ostop = scratch_.template alloc<uint8_t>(std::max(totV, 1));
+    int* d_cnt = scratch_.template alloc<int>(B);
+    be_.h2d(d_off, wp_off, sizeof(int) * (B + 1));
+    be_.h2d(d_wp, wp, sizeof(double) * 4 * (size_t)totV);
+    if (stop) be_.h2d(d_stop, stop, totV);
+    be_.for_each(B, PreprocessFn{d_off, d_wp, d_stop, min_dist, max_dev, max_hdg_dev, straighten, d_owp, d_ostop, d_cnt});
+    launches(1);
+    be_.d2h(out_count, d_cnt, sizeof(int) * B);
+    if (out_wp) be_.d2h(out_wp, d_owp, sizeof(double) * 4 * (size_t)totV);
+    if (out_stop) be_.d2h(out_stop, d_ostop, totV);
+  }
+  void fallback_batch(int B, const int* wp_off, const double* wp, const uint8_t* stop, const double* L9, double dt, double stopping_time, int* counts,
+                      double* samples) {
+    scratch_.reset();
+    const int totV = wp_off[B];
+    int* d_off = scratch_.template alloc<int>((size_t)B + 1);
+    double* d_wp = scratch_.template alloc<double>((size_t)std::max(totV, 1) * 4);
+    uint8_t* d_stop = stop ? scratch_.template alloc<uint8_t>(std::max(totV, 1)) : nullptr;
+    double* d_vpos = scratch_.template alloc<double>((size_t)std::max(totV, 1) * 4);
+    int* d_cnt = scratch_.template alloc<int>((size_t)B + 1);
+    int* d_smp_off = scratch_.template alloc<int>((size_t)B + 1);
+    be_.h2d(d_off, wp_off, sizeof(int) * (B + 1));
+    be_.h2d(d_wp, wp, sizeof(double) * 4 * (size_t)totV);
+    if (stop) be_.h2d(d_stop, stop, totV);
+    FallbackFn f{d_off, d_wp, d_stop, {}, dt, stopping_time, d_vpos, d_cnt, nullptr, nullptr};
+    for (int i = 0; i < 9; ++i) f.L[i] = L9[i];
+    be_.for_each(B, f);
+    be_.exclusive_scan(d_cnt, d_smp_off, B);
+    launches(2);
+    std::vector<int> off(B + 1);
+    be_.d2h(off.data(), d_smp_off, sizeof(int) * (B + 1));
+    for (int p = 0; p < B; ++p) counts[p] = off[p + 1] - off[p];
+    if (!samples || off[B] == 0) return;
+    double* d_smp = scratch_.template alloc<double>((size_t)off[B] * 4);
+    f.smp_off = d_smp_off;
+    f.samples = d_smp;
+    be_.for_each(B, f);
+    launches(1);
+    be_.d2h(samples, d_smp, sizeof(double) * 4 * (size_t)off[B]);
+    counters.samples += off[B];
+  }
+  void waypoint_idxs_batch(int B, const int* smp_off, const double* samples, const int* wp_off, const double* wp, int* counts, int* idxs) {
+    scratch_.reset();
+    const int totV = wp_off[B], totM = smp_off[B];
+    int* d_soff = scratch_.template alloc<int>((size_t)B + 1);
+    int* d_woff = scratch_.template alloc<int>((size_t)B + 1);
+    double* d_smp = scratch_.template alloc<double>((size_t)std::max(totM, 1) * 4);
+    double* d_wp = scratch_.template alloc<double>((size_t)std::max(totV, 1) * 4);
+    int* d_idx = scratch_.template alloc<int>(std::max(totV, 1));
+    int* d_cnt = scratch_.template alloc<int>(B);
+    be_.h2d(d_soff, smp_off, sizeof(int) * (B + 1));
+    be_.h2d(d_woff, wp_off, sizeof(int) * (B + 1));
+    be_.h2d(d_smp, samples, sizeof(double) * 4 * (size_t)totM);
+    be_.h2d(d_wp, wp, sizeof(double) * 4 * (size_t)totV);
+    be_.for_each(B, WaypointIdxFn{d_soff, d_smp, d_woff, d_wp, d_idx, d_cnt});
+    launches(1);
+    be_.d2h(counts, d_cnt, sizeof(int) * B);
+    be_.d2h(idxs, d_idx, sizeof(int) * totV);
+  }
+
   // sampleWholeTrajectory for B trajectories
   void sample_batch(int B, const int* seg_off, const double* coef, const double* times, double dt, int* counts, double* samples, double* full) {
     scratch_.reset();

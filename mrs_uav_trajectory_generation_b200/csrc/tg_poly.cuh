@@ -44,10 +44,17 @@ TG_HD double poly_eval_s(const double* __restrict__ c, double t) {
 #if defined(TG_JT_STATS)
 static thread_local long long tg_jt_stats[16];
 #endif
+// The device kernels that use it run 128 threads per block (cuda_backend.cu asserts it), so the stride is a
+// compile-time constant there and an element address is one shift-add.
+#define TG_WARR_DEVICE_STRIDE 128
 struct WArr {
   double* b;
   int st;
+#if defined(__CUDA_ARCH__)
+  TG_HD double& operator[](int i) const { return b[i * TG_WARR_DEVICE_STRIDE]; }
+#else
   TG_HD double& operator[](int i) const { return b[(size_t)i * st]; }
+#endif
 };
 
 // Jenkins-Traub three-stage iteration (TOMS 493) as an explicit per-thread STATE MACHINE.

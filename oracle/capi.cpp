@@ -113,6 +113,42 @@ int orc_time_alloc(int V, const uint8_t* mask, const double* vals, double* times
   return 0;
 }
 
+// the steps either side of the path
+static std::vector<Waypoint> make_waypoints(int V, const double* wp, const uint8_t* stop) {
+  std::vector<Waypoint> w(V);
+  for (int i = 0; i < V; ++i) {
+    for (int d = 0; d < 4; ++d) w[i].c[d] = wp[4 * i + d];
+    w[i].stop_at = stop ? stop[i] != 0 : false;
+  }
+  return w;
+}
+int orc_preprocess_path(int V, const double* wp, const uint8_t* stop, double min_dist, int straighten, double max_dev, double max_hdg_dev, double* out_wp,
+                        uint8_t* out_stop) {
+  const std::vector<Waypoint> o = preprocess_path(make_waypoints(V, wp, stop), min_dist, straighten != 0, max_dev, max_hdg_dev);
+  for (size_t i = 0; i < o.size(); ++i) {
+    for (int d = 0; d < 4; ++d) out_wp[4 * i + d] = o[i].c[d];
+    out_stop[i] = o[i].stop_at ? 1 : 0;
+  }
+  return (int)o.size();
+}
+int orc_fallback_sample(int V, const double* wp, const uint8_t* stop, const double* limits9, double dt, double stopping_time, int cap, double* out) {
+  Limits L{limits9[0], limits9[1], limits9[2], limits9[3], limits9[4], limits9[5], limits9[6], limits9[7], limits9[8]};
+  std::vector<std::array<double, 4>> s;
+  fallback_sample(make_waypoints(V, wp, stop), L, dt, stopping_time, &s);
+  if ((int)s.size() > cap) return -(int)s.size();
+  for (size_t i = 0; i < s.size(); ++i)
+    for (int d = 0; d < 4; ++d) out[4 * i + d] = s[i][d];
+  return (int)s.size();
+}
+int orc_waypoint_idxs(int M, const double* samples, int V, const double* wp, int* idxs) {
+  std::vector<std::array<double, 4>> s(M);
+  for (int i = 0; i < M; ++i)
+    for (int d = 0; d < 4; ++d) s[i][d] = samples[4 * i + d];
+  const std::vector<int> o = waypoint_trajectory_idxs(s, make_waypoints(V, wp, nullptr));
+  for (size_t i = 0; i < o.size(); ++i) idxs[i] = o[i];
+  return (int)o.size();
+}
+
 // dense R for structure tests: R is (n_fixed+n_free)^2 row-major
 int orc_dense_R(int V, const uint8_t* mask, const double* vals, const double* times, int r, double* R) {
   LinearSolver ls;

@@ -149,6 +149,102 @@ Waypoint interpolate_point(const Waypoint& a, const Waypoint& b, double coeff) {
   return o;
 }
 
+// node.cpp:431-500
+std::vector<Waypoint> preprocess_path(const std::vector<Waypoint>& in, double min_waypoint_distance, bool straightener_enabled,
+                                      double straightener_max_deviation, double straightener_max_hdg_deviation) {
+  std::vector<Waypoint> out;
+  size_t last_added_idx = 0;
+  for (size_t i = 0; i < in.size(); ++i) {
+    if (straightener_enabled && in.size() >= 3 && i > 0 && i < (in.size() - 1)) {
+      const double* first = in[last_added_idx].c;
+      const double* last = in[i + 1].c;
+      const double first_hdg = first[3], last_hdg = last[3];
+      bool segment_is_ok = true;
+      for (size_t j = last_added_idx + 1; j < i + 1; ++j) {
+        const double* mid = in[j].c;
+        const double mid_hdg = mid[3];
+        const double d = dist_from_segment(mid, first, last);
+        // as written in the reference: fabs() of the comparison's bool
+        if (d > straightener_max_deviation || std::fabs((double)(rad_diff(first_hdg, mid_hdg) > straightener_max_hdg_deviation)) != 0.0 ||
+            std::fabs((double)(rad_diff(last_hdg, mid_hdg) > straightener_max_hdg_deviation)) != 0.0) {
+          segment_is_ok = false;
+          break;
+        }
+      }
+      if (segment_is_ok) continue;
+    }
+    if (i > 0 && i < (in.size() - 1)) {
+      const double* first = in[last_added_idx].c;
+      const double* last = in[i].c;
+      const double dx = first[0] - last[0], dy = first[1] - last[1], dz = first[2] - last[2];
+      if (std::sqrt(dx * dx + dy * dy + dz * dz) < min_waypoint_distance) continue;  // mrs_lib::geometry::dist
+    }
+    out.push_back(in[i]);
+    last_added_idx = i;
+  }
+  return out;
+}
+
+// node.cpp:1215-1395
+void fallback_sample(const std::vector<Waypoint>& wp, const Limits& L, double dt, double stopping_time, std::vector<std::array<double, 4>>* out) {
+  out->clear();
+  if (wp.size() < 2) return;
+  std::vector<Vertex> vertices(wp.size());
+  double last_heading = wp[0].c[3];
+  for (size_t i = 0; i < wp.size(); ++i) {
+    const double heading = srad_unwrap(wp[i].c[3], last_heading);
+    last_heading = heading;
+    vertices[i].mask = 1;
+    vertices[i].val[0][0] = wp[i].c[0];
+    vertices[i].val[0][1] = wp[i].c[1];
+    vertices[i].val[0][2] = wp[i].c[2];
+    vertices[i].val[0][3] = heading;
+  }
+  const std::vector<double> baca = estimate_times_baca(vertices, L);
+  for (size_t i = 0; i + 1 < wp.size(); ++i) {
+    const double segment_time = baca[i];
+    int n_samples;
+    double interp_step;
+    if (segment_time > 1e-1) {
+      n_samples = (int)std::ceil(segment_time / dt);
+      interp_step = (n_samples > 0) ? 1.0 / (double)n_samples : 0.5;
+    } else {
+      n_samples = 0;
+      interp_step = 0;
+    }
+    if (n_samples > 0 && i == wp.size() - 2) n_samples++;  // the last segment hits the last waypoint
+    for (int j = 0; j < n_samples; ++j) {
+      const Waypoint pt = interpolate_point(wp[i], wp[i + 1], (double)j * interp_step);
+      // setFromYaw -> quaternion -> the heading getTrajectoryReference reads back (eth_mav_msgs/common.h:130-140)
+      const double ha = 0.5 * pt.c[3];
+      const double qw = m_cos(ha), qz = m_sin(ha);
+      const double yaw = m_atan2(2.0 * (qw * qz + 0.0 * 0.0), 1.0 - 2.0 * (0.0 * 0.0 + qz * qz));
+      const std::array<double, 4> smp = {pt.c[0], pt.c[1], pt.c[2], yaw};
+      out->push_back(smp);
+      if (j == 0 && i > 0 && wp[i].stop_at) {
+        const int insert_samples = (int)std::round(stopping_time / dt);
+        for (int k = 0; k < insert_samples; ++k) out->push_back(smp);
+      }
+    }
+  }
+}
+
+// node.cpp:1461-1499
+std::vector<int> waypoint_trajectory_idxs(const std::vector<std::array<double, 4>>& samples, const std::vector<Waypoint>& wp) {
+  std::vector<int> idxs;
+  int waypoint_idx = 0;
+  if (samples.empty() || wp.empty()) return idxs;
+  for (size_t i = 0; i + 1 < samples.size(); ++i) {
+    const double d = dist_from_segment(wp[waypoint_idx].c, samples[i].data(), samples[i + 1].data());
+    if (d < 0.1) {
+      idxs.push_back((int)i);
+      waypoint_idx++;
+    }
+    if (waypoint_idx == (int)wp.size()) break;
+  }
+  return idxs;
+}
+
 // node.cpp:620-851, numeric part
 OptimizeResult optimize_path(const std::vector<Waypoint>& wp_in, const InitialState& init, const NodeParams& P) {
   OptimizeResult O;

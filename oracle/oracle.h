@@ -30,6 +30,7 @@
 #define ORACLE_ORACLE_H_
 
 #include <cstdint>
+#include <array>
 #include <vector>
 
 namespace orc {
@@ -203,6 +204,17 @@ struct Validation {
 Validation validate_spatial(const std::vector<Sample>& traj, const std::vector<Waypoint>& wp, const NodeParams& P);
 double dist_from_segment(const double* p, const double* a, const double* b);  // node.cpp:1533-1554
 Waypoint interpolate_point(const Waypoint& a, const Waypoint& b, double coeff);  // node.cpp:1612-1625
+
+// ---- the steps either side of the path ---------------------------------------------------
+// preprocessPath (node.cpp:431-500): optional straightener, then the min-distance filter.  Keeps the reference's
+// `fabs(radians::diff(a, b) > limit)` expression as written (fabs of a bool).
+std::vector<Waypoint> preprocess_path(const std::vector<Waypoint>& in, double min_waypoint_distance, bool straightener_enabled,
+                                      double straightener_max_deviation, double straightener_max_hdg_deviation);
+// findTrajectoryFallback (node.cpp:1215-1395): constant-velocity samples along the polyline, Baca segment times.
+// `L` already carries the fallback speed / acceleration factors; out: x, y, z, heading (after the quaternion round trip).
+void fallback_sample(const std::vector<Waypoint>& wp, const Limits& L, double dt, double stopping_time, std::vector<std::array<double, 4>>* out);
+// getWaypointInTrajectoryIdxs (node.cpp:1461-1499): index of the first sample whose chord passes within 0.1 m of each waypoint
+std::vector<int> waypoint_trajectory_idxs(const std::vector<std::array<double, 4>>& samples, const std::vector<Waypoint>& wp);
 // node.cpp:620-851 restricted to the numeric part: findTrajectory + validation + subdivision rounds
 struct OptimizeResult {
   bool success = false;

@@ -116,6 +116,19 @@ int main(int argc, char** argv) {
     dump_traj(f, "batch", res[p].trajectory);
     dump(f, "batch_samples", res[p].samples_xyzh.data(), res[p].samples_xyzh.size());
   }
+  // --- the steps either side of the path: preprocessPath / findTrajectoryFallback / getWaypointInTrajectoryIdxs
+  std::vector<Waypoint> raw = paths[0];
+  raw.insert(raw.begin() + 3, Waypoint{raw[2].x + 0.01, raw[2].y, raw[2].z, raw[2].heading, false});  // closer than min_waypoint_distance
+  raw[6].stop_at = true;
+  const std::vector<Waypoint> pre = gen.preprocessPath(raw);
+  std::vector<double> flat_pre;
+  for (const Waypoint& w : pre) { flat_pre.push_back(w.x); flat_pre.push_back(w.y); flat_pre.push_back(w.z); flat_pre.push_back(w.heading); flat_pre.push_back(w.stop_at ? 1.0 : 0.0); }
+  dump(f, "pre", flat_pre.data(), flat_pre.size());
+  const std::vector<double> fb = gen.findTrajectoryFallback(pre, 0.75, 0.75, 2.0);
+  dump(f, "fallback", fb.data(), fb.size());
+  const std::vector<int> ix = gen.getWaypointInTrajectoryIdxs(fb, pre);
+  std::vector<double> ixd(ix.begin(), ix.end());
+  dump(f, "idxs", ixd.data(), ixd.size());
   std::fclose(f);
   std::printf("shim test wrote %s (%s)\n", argv[1], tg_version());
   return 0;

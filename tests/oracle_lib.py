@@ -245,6 +245,36 @@ def trajectory_evaluate(coeffs, times, t, deriv):
     return out, bool(ok)
 
 
+def preprocess_path(wp, stop_at=None, min_dist=0.05, straightener=False, max_dev=0.05, max_hdg_dev=0.1):
+    wp = np.ascontiguousarray(wp, dtype=np.float64)
+    V = len(wp)
+    stop = np.zeros(V, np.uint8) if stop_at is None else np.ascontiguousarray(stop_at, dtype=np.uint8)
+    owp = np.zeros((V, 4))
+    ostop = np.zeros(V, np.uint8)
+    n = lib().orc_preprocess_path(V, _ptr(wp), _ptr(stop, u8p), C.c_double(min_dist), int(bool(straightener)), C.c_double(max_dev), C.c_double(max_hdg_dev),
+                                  _ptr(owp), _ptr(ostop, u8p))
+    return owp[:n].copy(), ostop[:n].copy()
+
+
+def fallback_sample(wp, stop_at=None, limits=DEFAULT_LIMITS, dt=0.2, stopping_time=2.0, cap=200000):
+    wp = np.ascontiguousarray(wp, dtype=np.float64)
+    V = len(wp)
+    stop = np.zeros(V, np.uint8) if stop_at is None else np.ascontiguousarray(stop_at, dtype=np.uint8)
+    lim = np.array(limits, dtype=np.float64)
+    out = np.zeros((cap, 4))
+    n = lib().orc_fallback_sample(V, _ptr(wp), _ptr(stop, u8p), _ptr(lim), C.c_double(dt), C.c_double(stopping_time), cap, _ptr(out))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def waypoint_idxs(samples, wp):
+    samples = np.ascontiguousarray(samples, dtype=np.float64)
+    wp = np.ascontiguousarray(wp, dtype=np.float64)
+    idx = np.zeros(len(wp) + 1, dtype=np.int32)
+    n = lib().orc_waypoint_idxs(len(samples), _ptr(samples), len(wp), _ptr(wp), idx.ctypes.data_as(C.POINTER(C.c_int)))
+    return idx[:n].copy()
+
+
 def dist_from_segment(p, a, b):
     p, a, b = (np.ascontiguousarray(x, dtype=np.float64) for x in (p, a, b))
     return lib().orc_dist_from_segment(_ptr(p), _ptr(a), _ptr(b))

@@ -289,6 +289,43 @@ def check_sweep(ctx, K=300, seed=7):
     return np.array_equal(costs, ref)
 
 
+def check_path_side_steps(ctx, seed=31, B=40):
+    """preprocessPath, findTrajectoryFallback and getWaypointInTrajectoryIdxs against the oracle, bit for bit."""
+    rng = np.random.default_rng(seed)
+    paths, stops = [], []
+    for p in range(B):
+        V = int(rng.integers(2, 24))
+        wp = W.random_flier_path(3000 + seed * 100 + p, V)
+        if p % 3 == 0:  # near-duplicate and collinear waypoints: work for the min-distance filter and the straightener
+            k = int(rng.integers(1, V)) if V > 2 else 1
+            wp[k] = wp[k - 1] + np.array([0.01, 0.0, 0.0, 0.0]) * (p % 2)
+            if V > 4:
+                wp[2] = 0.5 * (wp[1] + wp[3])
+        if p % 5 == 0:
+            wp[:, 3] = rng.uniform(-7, 7, V)  # headings that need wrapping / unwrapping
+        st = (rng.uniform(size=V) < 0.15).astype(np.uint8)
+        paths.append(wp)
+        stops.append(st)
+    wp_off = np.cumsum([0] + [len(w) for w in paths]).astype(np.int32)
+    wp = np.concatenate(paths)
+    stop = np.concatenate(stops)
+    ok = True
+    for straight in (False, True):
+        off, owp, ostop = ctx.preprocess_paths(wp_off, wp, stop, 0.05, straight, 0.05, 0.1)
+        for p in range(B):
+            rw, rs = O.preprocess_path(paths[p], stops[p], 0.05, straight, 0.05, 0.1)
+            ok = ok and np.array_equal(owp[off[p]:off[p + 1]], rw) and np.array_equal(ostop[off[p]:off[p + 1]], rs)
+    lim = np.array(O.DEFAULT_LIMITS) * np.array([0.75, 0.75, 0.75, 0.75, 1, 1, 1, 1, 1])  # speed / acceleration factors applied by the caller
+    soff, smp = ctx.fallback_sample_batch(wp_off, wp, stop, lim, 0.2, 2.0)
+    for p in range(B):
+        ref = O.fallback_sample(paths[p], stops[p], lim, 0.2, 2.0)
+        ok = ok and np.array_equal(smp[soff[p]:soff[p + 1]], ref)
+    idx = ctx.waypoint_idxs_batch(soff, smp, wp_off, wp)
+    for p in range(B):
+        ok = ok and np.array_equal(idx[p], O.waypoint_idxs(smp[soff[p]:soff[p + 1]], paths[p]))
+    return ok
+
+
 def geometric_predicate(samples, waypoints, pos_tol=0.5, hdg_tol=0.2):
     """The reference tests' acceptance check (test/include/get_path_test.h:45-68): every input waypoint is approached
     within 0.5 m / 0.2 rad by some sample, in order."""

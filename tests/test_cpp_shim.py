@@ -70,10 +70,28 @@ def _check(res):
         assert np.array_equal(res["batch_samples"][p].reshape(-1, 4), o["samples"])
 
 
+def _check_side_steps(res):
+    raw = W.F1B_WAYPOINTS.copy()
+    raw = np.insert(raw, 3, raw[2] + np.array([0.01, 0, 0, 0]), axis=0)
+    stop = np.zeros(len(raw), np.uint8)
+    stop[6] = 1
+    pw, ps = O.preprocess_path(raw, stop)
+    got = res["pre"][0].reshape(-1, 5)
+    assert np.array_equal(got[:, :4], pw) and np.array_equal(got[:, 4].astype(np.uint8), ps) and len(pw) == len(raw) - 1
+    lim = np.array(O.DEFAULT_LIMITS) * np.array([0.75, 0.75, 0.75, 0.75, 1, 1, 1, 1, 1])
+    fb = O.fallback_sample(pw, ps, lim, 0.2, 2.0)
+    assert np.array_equal(res["fallback"][0].reshape(-1, 4), fb)
+    assert np.array_equal(res["idxs"][0].astype(np.int32), O.waypoint_idxs(fb, pw))
+
+
 def test_cpp_shim_on_host_emulation(oracle, emu_lib, tmp_path):
-    _check(_run_shim(os.path.join(ROOT, "tests", "host_emu"), "tg_emu", tmp_path))
+    res = _run_shim(os.path.join(ROOT, "tests", "host_emu"), "tg_emu", tmp_path)
+    _check(res)
+    _check_side_steps(res)
 
 
 @pytest.mark.gpu
 def test_cpp_shim_on_gpu(oracle, gpu_ctx, tmp_path):
-    _check(_run_shim(os.path.join(ROOT, "mrs_uav_trajectory_generation_b200"), "tg_b200", tmp_path))
+    res = _run_shim(os.path.join(ROOT, "mrs_uav_trajectory_generation_b200"), "tg_b200", tmp_path)
+    _check(res)
+    _check_side_steps(res)

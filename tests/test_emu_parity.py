@@ -17,6 +17,10 @@ def test_time_alloc_from_vertices(emu_ctx, oracle, r):
     assert PC.check_time_alloc(emu_ctx, r=r)
 
 
+def test_preprocess_fallback_and_waypoint_indices(emu_ctx, oracle):
+    assert PC.check_path_side_steps(emu_ctx)
+
+
 def test_sampling(emu_ctx, oracle):
     assert PC.check_sampling(emu_ctx)
 

@@ -24,6 +24,10 @@ def test_time_alloc_from_vertices(gpu_ctx, oracle, r):
     assert PC.check_time_alloc(gpu_ctx, r=r)
 
 
+def test_preprocess_fallback_and_waypoint_indices(gpu_ctx, oracle):
+    assert PC.check_path_side_steps(gpu_ctx)
+
+
 def test_sampling(gpu_ctx, oracle):
     assert PC.check_sampling(gpu_ctx, B=32)
 

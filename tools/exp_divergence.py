@@ -5,7 +5,7 @@ import numpy as np
 import mrs_uav_trajectory_generation_b200 as tg
 from mrs_uav_trajectory_generation_b200 import workloads as W
 import os
-libpath = sys.argv[1] if len(sys.argv) > 1 else None
+libpath = (sys.argv[1] or None) if len(sys.argv) > 1 else None
 ctx = tg.Context(tg.Library(libpath), 0)
 print('library', libpath or 'default')
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
