@@ -175,6 +175,10 @@ int tg_set_profiling(tg_ctx* ctx, int on);
 int tg_get_profile(tg_ctx* ctx, int cap, char* names, int names_cap, double* ms, long long* launches, long long* items);
 double tg_measure_fp64_peak(tg_ctx* ctx, int mode);
 
+/* Test hook: the tolerance of scaleSegmentTimesToMeetConstraints' global check (1e-3, eth/trajectory.cpp:604).  With the
+ * reference's value a second pass practically never happens; tests lower it to drive the multi-pass path. */
+int tg_test_set_scale_tolerance(tg_ctx* ctx, double tolerance);
+
 /* Host-side evaluation of the deterministic math layer (include/tg_detmath.h), for tests:
  *   fn 0 log, 1 exp, 2 sin, 3 cos, 4 atan2(x, y), 5 cbrt, 6 pow(x, (int)y). */
 double tg_detmath_eval(int fn, double x, double y);

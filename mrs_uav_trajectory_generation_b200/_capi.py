@@ -203,6 +203,10 @@ class Context:
             out[nm.replace("tg::", "")] = (ms[i], ln[i], it[i])
         return out
 
+    def test_set_scale_tolerance(self, tol):
+        self.L.lib.tg_test_set_scale_tolerance.argtypes = [C.c_void_p, C.c_double]
+        self._check(self.L.lib.tg_test_set_scale_tolerance(self.h, float(tol)))
+
     def fp64_peak_tflops(self, mode=1):
         return self.L.lib.tg_measure_fp64_peak(self.h, int(mode))
 

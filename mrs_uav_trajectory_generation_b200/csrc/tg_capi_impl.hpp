@@ -4,6 +4,7 @@
 #ifndef TG_CAPI_IMPL_HPP_
 #define TG_CAPI_IMPL_HPP_
 
+#include <cstdlib>
 #include <exception>
 #include <string>
 
@@ -17,7 +18,9 @@ struct tg_ctx {
   std::vector<tg::Result> last;
   int last_B = 0;
   double last_ms = 0.0;
-  explicit tg_ctx(int device) : be(device), pipe(be) {}
+  explicit tg_ctx(int device) : be(device), pipe(be) {
+    if (std::getenv("TG_NO_PRUNE")) pipe.prune_extrema = false;
+  }
 };
 
 static_assert(sizeof(tg_params) == sizeof(tg::Params), "tg_params / tg::Params layout mismatch");
@@ -157,6 +160,12 @@ int tg_time_alloc_batch(tg_ctx* ctx, int B, const int* vtx_off, const uint8_t* v
     if (!ok) { ctx->err = "every problem needs at least two vertices"; return TG_ERR_INVALID; }
     return TG_OK;
   });
+}
+
+int tg_test_set_scale_tolerance(tg_ctx* ctx, double tolerance) {
+  if (!ctx) return TG_ERR_INVALID;
+  ctx->pipe.scale_tolerance = tolerance;
+  return TG_OK;
 }
 
 int tg_preprocess_paths(tg_ctx* ctx, int B, const int* wp_off, const double* wp, const uint8_t* stop_at, double min_waypoint_distance, int straightener_enabled,

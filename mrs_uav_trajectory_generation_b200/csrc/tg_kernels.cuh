@@ -11,6 +11,7 @@
 #define TG_KERNELS_CUH_
 
 #include "tg_common.cuh"
+#include "tg_bound.cuh"
 #include "tg_lbfgs.cuh"
 #include "tg_node.cuh"
 #include "tg_poly.cuh"
@@ -350,6 +351,171 @@ struct ExtremaWorkFn {
   }
 };
 
+// Certificates for the global check (tg_bound.cuh): one thread per entry of the changed-segment work list.  A quantity
+// whose Bernstein bound already passes the 1.001 x limit test gets the bound stored and flagged; the others are appended
+// to the per-quantity work lists for exact root finding.
+struct ExtremaBoundFn {
+  const double* coef;
+  const double* times;
+  double* maxima;
+  uint8_t* is_bound;   // [totS * 9]
+  const int* work;     // changed segments
+  const int* n_work;   // device count
+  int* lists;          // [9][list_stride]
+  int* counts;         // [9]
+  int list_stride;
+  double L[9];
+  double tol;
+  TG_HD void operator()(size_t item) const {
+    if (item >= (size_t)*n_work) return;
+    const size_t gs = (size_t)work[item];
+    for (int q = 0; q < 9; ++q) {
+      // a value v with v / L <= 1 + tol passes the check (eth/trajectory.cpp:676-681); thr is such a value with a margin
+      const double thr = L[limit_index(q)] * (1.0 + tol) * (1.0 - 1e-12);
+      const bool passes = (thr / L[limit_index(q)] <= 1.0 + tol) && certify_quantity_le(coef + gs * TG_D * TG_N, times[gs], q, thr);
+      if (passes) {
+        maxima[gs * 9 + q] = thr;
+        is_bound[gs * 9 + q] = 1;
+      } else {
+        is_bound[gs * 9 + q] = 0;
+        const int at = TG_ATOMIC_ADD_RET(&counts[q], 1);
+        lists[(size_t)q * list_stride + at] = (int)gs;
+      }
+    }
+  }
+};
+// ---- pruned maxima for the per-segment stretch factor ----------------------------------------------------------------
+// The stretch factor of a segment (eth/trajectory.cpp:640-655) is s = max(1, V, sqrt(A), cbrt(J)) over the nine maxima:
+// only the largest transformed ratio matters.  With rigorous upper bounds u_q (tg_bound.cuh) and r_q = g_q(u_q / L_q)
+// (g = identity / sqrt / cbrt, inflated by 1e-9 so that cbrt needs no monotonicity at the ulp level):
+//   A. r_max <= 1  => no quantity can exceed its limit, s = 1 exactly, nothing to compute;
+//      otherwise the quantity q* with the largest r is computed exactly (Jenkins-Traub);
+//   C. M = max(1, g(exact ratio of q*)); every q with r_q <= M cannot raise the maximum and is dropped (its slot gets 0,
+//      which never binds); the others are computed exactly.
+// s is then evaluated by the reference's expression over the exact values -- bit-identical to evaluating it over all
+// nine (the dropped transformed values are <= M <= s).
+TG_HD double prune_transform(int q, double ratio) {
+  const int d = q % 3;  // 0 velocity, 1 acceleration, 2 jerk
+  return d == 0 ? ratio : (d == 1 ? dsqrt(ratio) : tgdm::dcbrt(ratio));
+}
+struct ExtremaPruneAFn {
+  BatchPtrs b;
+  double L[9];
+  double* rq;          // [totS][9] transformed bounds
+  uint8_t* qstar;      // [totS] quantity computed first, 0xff: none needed, 0xfe: all nine (bounds unusable)
+  int* lists;          // [9][list_stride]
+  int* counts;         // [9]
+  int list_stride;
+  TG_HD void operator()(size_t gs) const {
+    const double* coef = b.coef + gs * TG_D * TG_N;
+    const double T = b.times[gs];
+    double bnd[9];
+    segment_bounds(coef, T, bnd);
+    double rmax = -1.0;
+    int qs = -1;
+    bool usable = true;
+    for (int q = 0; q < 9; ++q) {
+      const double lim = L[limit_index(q)];
+      const double ratio = bnd[q] / lim;
+      double r = prune_transform(q, ratio) * (1.0 + 1e-9);
+      if (!(r >= 0.0) || tgdm::disinf(r) || !(lim > 0.0)) usable = false;  // NaN, non-positive limits, overflow: no pruning here
+      // a quantity that provably stays within its limit can never raise s above 1 (s = max(1, ...)): drop it
+      if (usable && (r <= 1.0 || certify_quantity_le(coef, T, q, lim * (1.0 - 1e-9)))) r = 0.0;
+      rq[gs * 9 + q] = r;
+      if (r > rmax) rmax = r;
+    }
+    if (usable && rmax > 1.0) {
+      // which of the remaining quantities to compute first: the one that most likely binds, judged by curve values at five
+      // points (a LOWER estimate of each maximum); the choice affects only how much is pruned afterwards, never the result
+      double best = -1.0;
+      for (int q = 0; q < 9; ++q) {
+        if (!(rq[gs * 9 + q] > 1.0)) continue;
+        const int group = q / 3, deriv = q % 3 + 1;
+        const int d0 = (group == 0) ? 0 : (group == 1 ? 2 : 3), nd = (group == 0) ? 2 : 1;
+        double lo = 0.0;
+        for (int k = 0; k <= 4; ++k) {
+          const double t = 0.25 * (double)k * T;
+          double mag = 0.0;
+          for (int dim = d0; dim < d0 + nd; ++dim) {
+            const double v = poly_eval(coef + dim * TG_N, t, deriv);
+            mag = mag + v * v;
+          }
+          if (mag > lo) lo = mag;
+        }
+        const double est = prune_transform(q, dsqrt(lo) / L[limit_index(q)]);
+        if (est > best) { best = est; qs = q; }
+      }
+    }
+    if (!usable) {
+      qstar[gs] = 0xfe;
+      for (int q = 0; q < 9; ++q) {
+        const int at = TG_ATOMIC_ADD_RET(&counts[q], 1);
+        lists[(size_t)q * list_stride + at] = (int)gs;
+      }
+      return;
+    }
+    if (rmax <= 1.0) {
+      qstar[gs] = 0xff;
+      for (int q = 0; q < 9; ++q) b.maxima[gs * 9 + q] = 0.0;
+      return;
+    }
+    qstar[gs] = (uint8_t)qs;
+    const int at = TG_ATOMIC_ADD_RET(&counts[qs], 1);
+    lists[(size_t)qs * list_stride + at] = (int)gs;
+  }
+};
+struct ExtremaPruneCFn {
+  BatchPtrs b;
+  double L[9];
+  const double* rq;
+  const uint8_t* qstar;
+  int* lists;
+  int* counts;
+  int list_stride;
+  TG_HD void operator()(size_t gs) const {
+    const int qs = qstar[gs];
+    if (qs >= 9) return;
+    const double m = prune_transform(qs, b.maxima[gs * 9 + qs] / L[limit_index(qs)]);
+    const double M = (1.0 < m) ? m : 1.0;
+    for (int q = 0; q < 9; ++q) {
+      if (q == qs) continue;
+      bool drop = rq[gs * 9 + q] <= M;
+      if (!drop) {
+        // largest maximum of q whose transformed ratio stays below M: L*M, L*M^2, L*M^3 (with a margin)
+        const int d = q % 3;
+        const double lim = L[limit_index(q)];
+        const double thr = (d == 0 ? lim * M : (d == 1 ? lim * M * M : lim * M * M * M)) * (1.0 - 1e-9);
+        drop = certify_quantity_le(b.coef + gs * TG_D * TG_N, b.times[gs], q, thr);
+      }
+      if (drop) {
+        b.maxima[gs * 9 + q] = 0.0;
+      } else {
+        const int at = TG_ATOMIC_ADD_RET(&counts[q], 1);
+        lists[(size_t)q * list_stride + at] = (int)gs;
+      }
+    }
+  }
+};
+
+// Before another scaling pass reads the maxima of a problem that failed the check: its flagged entries become exact.
+struct ExtremaCompleteFn {
+  const int* prob_of_seg;
+  const ProbState* ps;
+  uint8_t* is_bound;
+  int* lists;
+  int* counts;
+  int list_stride;
+  TG_HD void operator()(size_t gs) const {
+    if (ps[prob_of_seg[gs]].scale_done) return;
+    for (int q = 0; q < 9; ++q)
+      if (is_bound[gs * 9 + q]) {
+        is_bound[gs * 9 + q] = 0;
+        const int at = TG_ATOMIC_ADD_RET(&counts[q], 1);
+        lists[(size_t)q * list_stride + at] = (int)gs;
+      }
+  }
+};
+
 struct ScaleFn {  // one thread per segment (eth/trajectory.cpp:610-658)
   BatchPtrs b;
   double L[9];
@@ -365,6 +531,7 @@ struct ScaleFn {  // one thread per segment (eth/trajectory.cpp:610-658)
 struct ScaleCheckFn {  // one thread per problem: the global re-check (eth/trajectory.cpp:660-689)
   BatchPtrs b;
   double L[9];
+  double tol;  // 1e-3 (eth/trajectory.cpp:604)
   TG_HD void operator()(size_t pi) const {
     const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
     ProbState& ps = b.ps[p];
@@ -377,7 +544,7 @@ struct ScaleCheckFn {  // one thread per problem: the global re-check (eth/traje
         const double m = b.maxima[(size_t)(s0 + i) * 9 + q];
         if (m > g[q]) g[q] = m;
       }
-    if (violation_within(g, L) || ps.n_scale_passes >= 20) ps.scale_done = 1;
+    if (violation_within(g, L, tol) || ps.n_scale_passes >= 20) ps.scale_done = 1;
     else TG_ATOMIC_ADD(&b.stats[1], 1);
   }
 };
@@ -513,6 +680,7 @@ struct ScaleOutFn {
   double L[9];
   int* passes;
   uint8_t* within;
+  double tol;
   TG_HD void operator()(size_t p) const {
     passes[p] = ps[p].n_scale_passes;
     double g[9];
@@ -520,7 +688,7 @@ struct ScaleOutFn {
     for (int i = seg_off[p]; i < seg_off[p + 1]; ++i)
       for (int q = 0; q < 9; ++q)
         if (maxima[(size_t)i * 9 + q] > g[q]) g[q] = maxima[(size_t)i * 9 + q];
-    within[p] = violation_within(g, L) ? 1 : 0;
+    within[p] = violation_within(g, L, tol) ? 1 : 0;
   }
 };
 // Trajectory::evaluate(t, derivative) (eth/trajectory.cpp:55-87): one thread per query time

@@ -201,11 +201,11 @@ TG_HD double violation_scaling(const double* __restrict__ m, const double* __res
   const double jv = dmax(dmax(m[2] / L[4], m[5] / L[5]), m[8] / L[8]);
   return dmax(1.0, dmax(dmax(vv, dsqrt(av)), tgdm::dcbrt(jv)));
 }
-TG_HD bool violation_within(const double* __restrict__ g, const double* __restrict__ L) {
+TG_HD bool violation_within(const double* __restrict__ g, const double* __restrict__ L, double tol = 1e-3) {
   const double vv = dmax(dmax(g[0] / L[0], g[3] / L[1]), g[6] / L[6]);
   const double av = dmax(dmax(g[1] / L[2], g[4] / L[3]), g[7] / L[7]);
   const double jv = dmax(dmax(g[2] / L[4], g[5] / L[5]), g[8] / L[8]);
-  return vv <= 1.0 + 1e-3 && av <= 1.0 + 1e-3 && jv <= 1.0 + 1e-3;
+  return vv <= 1.0 + tol && av <= 1.0 + tol && jv <= 1.0 + tol;  // tol = 1e-3 (eth/trajectory.cpp:604)
 }
 // scalePolynomialInTime(1/s) on the 4 polynomials of a segment + T *= s (polynomial.cpp:218-224)
 TG_HD void scale_segment(double* __restrict__ coef, double* __restrict__ T, double scaling) {

@@ -107,6 +107,8 @@ class Pipeline {
 
   BE& backend() { return be_; }
   Counters counters;
+  bool prune_extrema = true;            // tg_bound.cuh certificates (exact); off only for A/B measurements (TG_NO_PRUNE)
+  double scale_tolerance = 1e-3;        // eth/trajectory.cpp:604; tg_test_set_scale_tolerance changes it (tests only)
   size_t seg_budget = (size_t)1 << 21;  // max segments per group (bounds scratch memory: ~5.6 kB per segment)
 
   // ---------------------------------------------------------------------------------------------------------------
@@ -700,7 +702,7 @@ class Pipeline {
     b.maxima = scratch_.template alloc<double>((size_t)b.totS * 9);
     be_.h2d(b.times, times, sizeof(double) * b.totS);
     be_.h2d(b.coef, coef, sizeof(double) * (size_t)b.totS * TG_D * TG_N);
-    ScaleOutFn of{b.ps, b.maxima, bb.d_seg_off, {}, nullptr, nullptr};
+    ScaleOutFn of{b.ps, b.maxima, bb.d_seg_off, {}, nullptr, nullptr, scale_tolerance};
     for (int i = 0; i < 9; ++i) of.L[i] = L9[i];
     scale_loop(b, L9);
     int* d_passes = scratch_.template alloc<int>(B);
@@ -770,35 +772,6 @@ class Pipeline {
   size_t sweep_chunk = (size_t)1 << 17;
 
  private:
-  // Trajectory::scaleSegmentTimesToMeetConstraints over a batch (eth/trajectory.cpp:598-692): maxima of every segment,
-  // then up to 20 passes of { stretch every segment, recompute the maxima of the segments that changed, global check }.
-  void scale_loop(BatchPtrs& b, const double* L9) {
-    const size_t totS = (size_t)b.totS;
-    ScaleFn sf{b, {}, nullptr};
-    ScaleCheckFn cf{b, {}};
-    for (int i = 0; i < 9; ++i) { sf.L[i] = L9[i]; cf.L[i] = L9[i]; }
-    uint8_t* changed = scratch_.template alloc<uint8_t>(totS);
-    int* work = scratch_.template alloc<int>(totS);
-    int* count = scratch_.template alloc<int>(1);
-    sf.changed = changed;
-    ExtremaScratch es = extrema_scratch(totS);
-    extrema_segments(b.coef, b.times, b.maxima, totS, nullptr, nullptr, es);
-    for (int pass = 0; pass < 20; ++pass) {
-      be_.dev_memset(b.stats + 1, 0, sizeof(int));
-      be_.dev_memset(count, 0, sizeof(int));
-      be_.for_each(totS, sf);
-      be_.for_each(totS, ExtremaWorkFn{b.prob_of_seg, b.ps, changed, work, count});
-      extrema_segments(b.coef, b.times, b.maxima, totS, work, count, es);
-      be_.for_each((size_t)b.B, cf);
-      launches(3);
-      int pending = 0;
-      be_.d2h(&pending, b.stats + 1, sizeof(int));
-      if (pending == 0) break;
-    }
-  }
-
-  // per-segment maxima of the nine quantities for n_max work items (all segments, or the entries of a device work
-  // list whose length lives in device memory); one launch pair per quantity so that every kernel has one degree
   struct ExtremaScratch {
     double* polys = nullptr;
     int* degree = nullptr;
@@ -815,6 +788,94 @@ class Pipeline {
 #endif
     return es;
   }
+  // Trajectory::scaleSegmentTimesToMeetConstraints over a batch (eth/trajectory.cpp:598-692): maxima of every segment,
+  // then up to 20 passes of { stretch every segment, recompute the maxima of the segments that changed, global check }.
+  void scale_loop(BatchPtrs& b, const double* L9) {
+    const size_t totS = (size_t)b.totS;
+    ScaleFn sf{b, {}, nullptr};
+    ScaleCheckFn cf{b, {}, scale_tolerance};
+    for (int i = 0; i < 9; ++i) { sf.L[i] = L9[i]; cf.L[i] = L9[i]; }
+    uint8_t* changed = scratch_.template alloc<uint8_t>(totS);
+    uint8_t* is_bound = scratch_.template alloc<uint8_t>(totS * 9);
+    int* work = scratch_.template alloc<int>(totS);
+    int* lists = scratch_.template alloc<int>(totS * 9);
+    int* counts = scratch_.template alloc<int>(16);  // [0..8] per-quantity list lengths, [9] changed segments
+    sf.changed = changed;
+    be_.dev_memset(is_bound, 0, totS * 9);
+    ExtremaScratch es = extrema_scratch(totS);
+    if (prune_extrema) {
+      // maxima for the first pass' stretch factors: bounds, then the one quantity that can bind, then whatever is left
+      double* rq = scratch_.template alloc<double>(totS * 9);
+      uint8_t* qstar = scratch_.template alloc<uint8_t>(totS);
+      be_.dev_memset(counts, 0, 16 * sizeof(int));
+      ExtremaPruneAFn pa{b, {}, rq, qstar, lists, counts, (int)totS};
+      ExtremaPruneCFn pc{b, {}, rq, qstar, lists, counts, (int)totS};
+      for (int i = 0; i < 9; ++i) { pa.L[i] = L9[i]; pc.L[i] = L9[i]; }
+      be_.for_each(totS, pa);
+      extrema_lists(b.coef, b.times, b.maxima, totS, lists, counts, es);
+      be_.dev_memset(counts, 0, 16 * sizeof(int));
+      be_.for_each(totS, pc);
+      extrema_lists(b.coef, b.times, b.maxima, totS, lists, counts, es);
+      launches(2);
+    } else {
+      extrema_segments(b.coef, b.times, b.maxima, totS, nullptr, nullptr, es);
+    }
+    for (int pass = 0; pass < 20; ++pass) {
+      be_.dev_memset(b.stats + 1, 0, sizeof(int));
+      be_.dev_memset(counts, 0, 16 * sizeof(int));
+      be_.for_each(totS, sf);
+      be_.for_each(totS, ExtremaWorkFn{b.prob_of_seg, b.ps, changed, work, counts + 9});
+      // global check (eth/trajectory.cpp:660-689): certificates first, exact root finding only where they do not decide
+      ExtremaBoundFn bf{b.coef, b.times, b.maxima, is_bound, work, counts + 9, lists, counts, (int)totS, {}, scale_tolerance};
+      for (int i = 0; i < 9; ++i) bf.L[i] = L9[i];
+      be_.for_each(totS, bf);
+      extrema_lists(b.coef, b.times, b.maxima, totS, lists, counts, es);
+      be_.for_each((size_t)b.B, cf);
+      launches(4);
+      int pending = 0;
+      be_.d2h(&pending, b.stats + 1, sizeof(int));
+      if (pending == 0) break;
+      // another pass follows for `pending` problems: their certified entries must be exact before ScaleFn reads them
+      be_.dev_memset(counts, 0, 16 * sizeof(int));
+      be_.for_each(totS, ExtremaCompleteFn{b.prob_of_seg, b.ps, is_bound, lists, counts, (int)totS});
+      extrema_lists(b.coef, b.times, b.maxima, totS, lists, counts, es);
+      launches(1);
+    }
+  }
+
+  // exact maxima for per-quantity work lists: lists[q * n_max ..], lengths counts[q] in device memory
+  void extrema_lists(const double* coef, const double* times, double* maxima, size_t n_max, const int* lists, const int* counts,
+                     const ExtremaScratch& es) {
+    if (n_max == 0) return;
+#if TG_JT_IMPL == 2
+    be_.dev_memset(es.counters, 0, 16 * sizeof(int));
+    extrema_quantity<0>(coef, times, maxima, n_max, VmBuffers{lists + 0 * n_max, counts + 0, es.polys, es.degree}, es.counters);
+    extrema_quantity<1>(coef, times, maxima, n_max, VmBuffers{lists + 1 * n_max, counts + 1, es.polys, es.degree}, es.counters);
+    extrema_quantity<2>(coef, times, maxima, n_max, VmBuffers{lists + 2 * n_max, counts + 2, es.polys, es.degree}, es.counters);
+    extrema_quantity<3>(coef, times, maxima, n_max, VmBuffers{lists + 3 * n_max, counts + 3, es.polys, es.degree}, es.counters);
+    extrema_quantity<4>(coef, times, maxima, n_max, VmBuffers{lists + 4 * n_max, counts + 4, es.polys, es.degree}, es.counters);
+    extrema_quantity<5>(coef, times, maxima, n_max, VmBuffers{lists + 5 * n_max, counts + 5, es.polys, es.degree}, es.counters);
+    extrema_quantity<6>(coef, times, maxima, n_max, VmBuffers{lists + 6 * n_max, counts + 6, es.polys, es.degree}, es.counters);
+    extrema_quantity<7>(coef, times, maxima, n_max, VmBuffers{lists + 7 * n_max, counts + 7, es.polys, es.degree}, es.counters);
+    extrema_quantity<8>(coef, times, maxima, n_max, VmBuffers{lists + 8 * n_max, counts + 8, es.polys, es.degree}, es.counters);
+    launches(18);
+#else
+    (void)es;
+    be_.for_each_scratch(n_max, ExtremaRawFn<0>{coef, times, maxima, lists + 0 * n_max, counts + 0});
+    be_.for_each_scratch(n_max, ExtremaRawFn<1>{coef, times, maxima, lists + 1 * n_max, counts + 1});
+    be_.for_each_scratch(n_max, ExtremaRawFn<2>{coef, times, maxima, lists + 2 * n_max, counts + 2});
+    be_.for_each_scratch(n_max, ExtremaRawFn<3>{coef, times, maxima, lists + 3 * n_max, counts + 3});
+    be_.for_each_scratch(n_max, ExtremaRawFn<4>{coef, times, maxima, lists + 4 * n_max, counts + 4});
+    be_.for_each_scratch(n_max, ExtremaRawFn<5>{coef, times, maxima, lists + 5 * n_max, counts + 5});
+    be_.for_each_scratch(n_max, ExtremaRawFn<6>{coef, times, maxima, lists + 6 * n_max, counts + 6});
+    be_.for_each_scratch(n_max, ExtremaRawFn<7>{coef, times, maxima, lists + 7 * n_max, counts + 7});
+    be_.for_each_scratch(n_max, ExtremaRawFn<8>{coef, times, maxima, lists + 8 * n_max, counts + 8});
+    launches(9);
+#endif
+  }
+
+  // per-segment maxima of the nine quantities for n_max work items (all segments, or the entries of a device work
+  // list whose length lives in device memory); one launch pair per quantity so that every kernel has one degree
   void extrema_segments(const double* coef, const double* times, double* maxima, size_t n_max, const int* work, const int* n_dev,
                         const ExtremaScratch& es) {
     if (n_max == 0) return;

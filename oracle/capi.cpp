@@ -44,6 +44,7 @@ static NodeParams to_node(const orc_params* p) {
 }
 
 void orc_set_math_mode(int mode) { set_math_mode(mode); }
+void orc_set_scale_tolerance(double tol) { g_scale_tolerance = tol; }
 int orc_get_math_mode() { return math_mode(); }
 
 double orc_math(int fn, double x, double y) {

@@ -117,6 +117,7 @@ double segment_max_magnitude(const Segment& s, int deriv, const int* dims, int n
 struct Limits {  // order matches scaleSegmentTimesToMeetConstraints' argument meaning
   double v_h, v_v, a_h, a_v, j_h, j_v, v_hdg, a_hdg, j_hdg;
 };
+extern double g_scale_tolerance;  // 1e-3 (eth/trajectory.cpp:604); a test hook may change it
 // eth/trajectory.cpp:598-692 ; returns number of passes executed, *within = final within_range
 int scale_times_to_meet_constraints(std::vector<Segment>& seg, const Limits& L, bool* within, long* root_calls);
 

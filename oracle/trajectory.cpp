@@ -110,10 +110,12 @@ static void nine_maxima(const Segment& s, double* m, long* rc) {
   for (int k = 1; k <= 3; ++k) m[6 + k - 1] = segment_max_magnitude(s, k, hdg, 1, rc);
 }
 
+double g_scale_tolerance = 1e-3;  // test hook (orc_set_scale_tolerance): lets tests force the rare multi-pass path
+
 // eth/trajectory.cpp:598-692
 int scale_times_to_meet_constraints(std::vector<Segment>& seg, const Limits& L, bool* within_out, long* rc) {
   constexpr int kMaxCounter = 20;
-  constexpr double kTolerance = 1e-3;
+  const double kTolerance = g_scale_tolerance;  // 1e-3 in the reference (eth/trajectory.cpp:604); tests may change it
   bool within = false;
   int passes = 0;
   for (int it = 0; it < kMaxCounter; ++it) {

@@ -132,6 +132,11 @@ def set_math_mode(mode):
     lib().orc_set_math_mode(int(mode))
 
 
+def set_scale_tolerance(tol):
+    lib().orc_set_scale_tolerance.argtypes = [C.c_double]
+    lib().orc_set_scale_tolerance(float(tol))
+
+
 def math_fn(fn, x, y=0.0):
     return lib().orc_math(fn, float(x), float(y))
 

@@ -289,6 +289,34 @@ def check_sweep(ctx, K=300, seed=7):
     return np.array_equal(costs, ref)
 
 
+def check_scaling_multi_pass(ctx, seed=17, B=24):
+    """The global check's certificates (tg_bound.cuh) and their completion before a further pass: with the reference's
+    tolerance a second pass practically never happens, so the tolerance is lowered (test hooks on both sides) to force up
+    to 20 passes; times, coefficients, pass counts and verdicts must still equal the oracle's bit for bit."""
+    rng = np.random.default_rng(seed)
+    ok = True
+    passes_seen = set()
+    try:
+        for tol in (-0.2, -0.6):
+            O.set_scale_tolerance(tol)
+            ctx.test_set_scale_tolerance(tol)
+            segs = [int(rng.integers(1, 7)) for _ in range(B)]
+            seg_off = np.cumsum([0] + segs).astype(np.int32)
+            coef = rng.standard_normal((seg_off[-1], 4, 10)) * np.exp(rng.uniform(-3, 1, (seg_off[-1], 1, 10)))
+            times = np.exp(rng.uniform(-1, 1.5, seg_off[-1]))
+            lim = np.array(O.DEFAULT_LIMITS) * np.exp(rng.uniform(-1, 1, 9))
+            c2, t2, passes, within = ctx.scale_times(seg_off, coef, times, lim)
+            for p in range(B):
+                s0, s1 = seg_off[p], seg_off[p + 1]
+                rc, rt, rp, rw = O.scale_times(coef[s0:s1], times[s0:s1], lim)
+                ok = ok and np.array_equal(c2[s0:s1], rc) and np.array_equal(t2[s0:s1], rt) and passes[p] == rp and bool(within[p]) == bool(rw)
+                passes_seen.add(int(rp))
+    finally:
+        O.set_scale_tolerance(1e-3)
+        ctx.test_set_scale_tolerance(1e-3)
+    return ok and max(passes_seen) > 1
+
+
 def check_path_side_steps(ctx, seed=31, B=40):
     """preprocessPath, findTrajectoryFallback and getWaypointInTrajectoryIdxs against the oracle, bit for bit."""
     rng = np.random.default_rng(seed)

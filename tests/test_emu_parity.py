@@ -21,6 +21,10 @@ def test_preprocess_fallback_and_waypoint_indices(emu_ctx, oracle):
     assert PC.check_path_side_steps(emu_ctx)
 
 
+def test_scaling_certificates_and_multi_pass(emu_ctx, oracle):
+    assert PC.check_scaling_multi_pass(emu_ctx)
+
+
 def test_sampling(emu_ctx, oracle):
     assert PC.check_sampling(emu_ctx)
 

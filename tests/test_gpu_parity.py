@@ -28,6 +28,10 @@ def test_preprocess_fallback_and_waypoint_indices(gpu_ctx, oracle):
     assert PC.check_path_side_steps(gpu_ctx)
 
 
+def test_scaling_certificates_and_multi_pass(gpu_ctx, oracle):
+    assert PC.check_scaling_multi_pass(gpu_ctx)
+
+
 def test_sampling(gpu_ctx, oracle):
     assert PC.check_sampling(gpu_ctx, B=32)
 
