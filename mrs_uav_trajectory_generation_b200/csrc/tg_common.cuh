@@ -51,6 +51,17 @@ TG_HD int imin(int a, int b) { return a < b ? a : b; }
 TG_HD int imax(int a, int b) { return a > b ? a : b; }
 TG_HD bool dfinite(double x) { return !(tgdm::disnan(x) || tgdm::disinf(x)); }
 
+// two doubles moved as one 16-byte access (every buffer this is used on is 16-byte aligned)
+struct alignas(16) Dbl2 {
+  double x, y;
+};
+TG_HD void store2(double* p, double a, double b) {
+  Dbl2 t;
+  t.x = a;
+  t.y = b;
+  *reinterpret_cast<Dbl2*>(p) = t;
+}
+
 // Parameters of one batch call; mirrors tg_params in include/tg_b200.h field by field.
 struct Params {
   int derivative_to_optimize;

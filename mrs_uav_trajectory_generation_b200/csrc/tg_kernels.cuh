@@ -76,7 +76,7 @@ struct BatchPtrs {
   int* vfree;
   int* np;
   int* hbw;
-  int* stats;            // [0] = max solve workspace doubles, [1] = problems still to scale, [2] = max octet-solve workspace doubles
+  int* stats;            // [0] max solve workspace doubles, [1] problems still to scale, [2] max octet-solve workspace doubles, [3] max np, [4] max S
   double *times, *baca, *xeval, *x, *g, *d, *hist_s, *hist_y;
   LbfgsScalars* lb;
   double* recs;
@@ -84,6 +84,9 @@ struct BatchPtrs {
   double* coef;
   double* maxima;
   ProbState* ps;
+  double* xs;            // [instances][xstride] solutions of the reduced systems (solve kernels -> CoefCostFn)
+  double* part;          // [instances][4 * smax] partial costs
+  int xstride, smax;
 };
 
 TG_HD int vtx_off(const BatchPtrs& b, int p) { return b.seg_off[p] + p; }
@@ -103,6 +106,8 @@ struct PrepareFn {
     b.np[p] = np;
     b.hbw[p] = hbw;
     TG_ATOMIC_MAX(&b.stats[0], solve_ws_doubles(S, np, hbw));
+    TG_ATOMIC_MAX(&b.stats[3], np);
+    TG_ATOMIC_MAX(&b.stats[4], S);
     if (hbw == kOctHbw && np > 0) TG_ATOMIC_MAX(&b.stats[2], octet_ws_doubles(S, np));
     ProbState& ps = b.ps[p];
     ps.status = kFindOk;
@@ -204,6 +209,7 @@ struct SolveProblemDesc {
     I.coef_out = (n == 0) ? b.coef + (size_t)s0 * TG_D * TG_N : nullptr;
     I.cost_out = mellinger ? b.costs + v0 + n : &b.ps[p].cost;
     I.dp_out = (dp_out && !mellinger) ? dp_out + (size_t)TG_D * dp_off[p] : nullptr;
+    I.x_out = b.xs ? b.xs + inst * (size_t)b.xstride : nullptr;
     return true;
   }
 };
@@ -227,6 +233,7 @@ struct SolveSweepDesc {
     I.coef_out = nullptr;
     I.cost_out = costs + k;
     I.dp_out = nullptr;
+    I.x_out = b.xs ? b.xs + k * (size_t)b.xstride : nullptr;
     return true;
   }
 };
@@ -235,6 +242,101 @@ struct SetupSweepFn {
   const double* cand;  // [K][S]
   double* recs;
   TG_HD void operator()(size_t item) const { setup_segment_record(cand[item], r, recs + item * TG_REC_SIZE); }
+};
+
+// ---- 4b. coefficients and cost from the solutions of the reduced systems ---------------------------------------------
+// One thread per (instance, segment, dimension): c = A^-1 [derivatives of vertex s ; vertex s+1] (lin_impl.h:271-280) and
+// the partial cost (c^T Q) c (lin_impl.h:135-137); then one thread per instance adds the partials in (segment, dimension)
+// order (lin_impl.h:131-140).  Same sums as the in-kernel versions (tg_solve.cuh phase 4-6).
+template <int R>
+TG_HD double cost_partial(const double (&c)[TG_N], const double* __restrict__ Qg) {
+  constexpr int nq = TG_N - R;
+  double Q[nq][8];  // the Q block of the record (row stride 8), fetched with 16-byte loads
+#pragma unroll
+  for (int k = 0; k < nq; ++k)
+#pragma unroll
+    for (int b = 0; b < 8; b += 2) {
+      if (b < nq) {
+        const Dbl2 t = *reinterpret_cast<const Dbl2*>(Qg + k * 8 + b);
+        Q[k][b] = t.x;
+        Q[k][b + 1] = t.y;
+      }
+    }
+  double partial = 0.0;
+#pragma unroll
+  for (int b = 0; b < nq; ++b) {
+    double sum = c[R] * Q[0][b];
+#pragma unroll
+    for (int k = 1; k < nq; ++k) sum = sum + c[R + k] * Q[k][b];
+    partial = (b == 0) ? sum * c[R + b] : partial + sum * c[R + b];
+  }
+  return partial;
+}
+template <class D>
+struct CoefCostFn {
+  D desc;
+  int per_inst;   // 4 * smax items per instance
+  double* part;   // [instances][per_inst]
+  TG_HD void operator()(size_t item) const {
+    const size_t inst = item / (size_t)per_inst;
+    const int it = (int)(item - inst * (size_t)per_inst);
+    SolveInst I;
+    if (!desc.instance(inst, I)) return;
+    if (it >= I.S * TG_D) return;
+    const int s = it >> 2, d = it & 3;
+    const double* rec = solve_rec(I, s);
+    double nd[TG_N], c[TG_N];
+#pragma unroll
+    for (int k = 0; k < TG_N; ++k) {
+      const int v = s + (k >= TG_HALF ? 1 : 0), sl = k - (k >= TG_HALF ? TG_HALF : 0);
+      const uint32_t m = I.vmask[v];
+      nd[k] = ((m >> sl) & 1u) ? I.vval[((size_t)v * TG_HALF + sl) * TG_D + d] : I.x_out[(size_t)(I.vfree[v] + free_rank(m, sl)) * 4 + d];
+    }
+    c[0] = 1.0 * nd[0];
+    c[1] = 1.0 * nd[1];
+    c[2] = (1.0 / 2.0) * nd[2];
+    c[3] = (1.0 / 6.0) * nd[3];
+    c[4] = (1.0 / 24.0) * nd[4];
+    double blk[50];  // Dinv (25) then X (25): the first 400 bytes of the record, fetched with 16-byte loads
+#pragma unroll
+    for (int e = 0; e < 50; e += 2) {
+      const Dbl2 t = *reinterpret_cast<const Dbl2*>(rec + e);
+      blk[e] = t.x;
+      blk[e + 1] = t.y;
+    }
+#pragma unroll
+    for (int a = 0; a < TG_HALF; ++a) {
+      double acc = blk[TG_REC_X + a * 5] * nd[0];
+#pragma unroll
+      for (int k = 1; k < 5; ++k) acc = acc + blk[TG_REC_X + a * 5 + k] * nd[k];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc = acc + blk[TG_REC_DINV + a * 5 + k] * nd[5 + k];
+      c[TG_HALF + a] = acc;
+    }
+    if (I.coef_out) {
+#pragma unroll
+      for (int a = 0; a < TG_N; a += 2) store2(I.coef_out + it * TG_N + a, c[a], c[a + 1]);
+    }
+    if (I.cost_out) {
+      const double* Q = rec + TG_REC_Q;
+      part[item] = (I.r == 2) ? cost_partial<2>(c, Q) : ((I.r == 3) ? cost_partial<3>(c, Q) : cost_partial<4>(c, Q));
+    }
+  }
+};
+template <class D>
+struct CostSumFn {
+  D desc;
+  int per_inst;
+  const double* part;
+  TG_HD void operator()(size_t inst) const {
+    SolveInst I;
+    if (!desc.instance(inst, I)) return;
+    if (!I.cost_out) return;
+    const double* pp = part + inst * (size_t)per_inst;
+    double total = 0.0;
+    for (int it = 0; it < I.S * TG_D; ++it) total += pp[it];
+    *I.cost_out = 0.5 * total;
+  }
 };
 
 // ---- 5. L-BFGS state machine: one thread per problem -----------------------------------------------------------------------

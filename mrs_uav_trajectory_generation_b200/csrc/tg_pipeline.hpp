@@ -128,21 +128,22 @@ class Pipeline {
     b.vfree = scratch_.template alloc<int>((size_t)totV + B);
     b.np = scratch_.template alloc<int>(B);
     b.hbw = scratch_.template alloc<int>(B);
-    b.stats = scratch_.template alloc<int>(4);
+    b.stats = scratch_.template alloc<int>(8);
     b.times = g.d_times;
     b.baca = scratch_.template alloc<double>(totS);
     b.coef = g.d_coef;
     b.ps = g.d_ps;
-    be_.dev_memset(b.stats, 0, 4 * sizeof(int));
+    be_.dev_memset(b.stats, 0, 8 * sizeof(int));
     be_.for_each(B, VtxProblemFn{g.d_seg_off, pov, pos}); launches(1);
     be_.for_each(B, PrepareFn{b, 1}); launches(1);
     TimesFn tf{b, {}};
     for (int i = 0; i < 9; ++i) tf.L[i] = P.limits[i];
     be_.for_each(totS, tf); launches(1);
     be_.for_each(B, BacaTotalFn{b}); launches(1);
-    int stats[4];
+    int stats[8];
     be_.d2h(stats, b.stats, sizeof(stats));
     const int ws = stats[0], ows = stats[2];
+    alloc_solution_buffers(b, (size_t)(P.run_time_alloc ? totV : B), stats);
     if (P.run_time_alloc) {
       time_alloc_core(b, P, ws, ows);
     } else {
@@ -150,7 +151,7 @@ class Pipeline {
     }
     // final linear solve at the (scaled) times (nl_impl.h:405-408 / lin_impl.h:340-373)
     be_.for_each(totS, SetupBaseFn{b, b.times});
-    be_.solve((size_t)B, ws, ows, SolveProblemDesc{b, 0, nullptr, nullptr});
+    solve_with_outputs((size_t)B, ws, ows, SolveProblemDesc{b, 0, nullptr, nullptr}, b);
     launches(2);
     // sampling (eth/trajectory_sampling.cpp:49-104)
     int* cap = scratch_.template alloc<int>((size_t)B + 1);
@@ -431,8 +432,8 @@ class Pipeline {
     int* pos = scratch_.template alloc<int>(std::max(b.totS, 1));
     b.prob_of_vtx = pov; b.prob_of_seg = pos;
     b.ps = scratch_.template alloc<ProbState>(B);
-    b.stats = scratch_.template alloc<int>(4);
-    be_.dev_memset(b.stats, 0, 4 * sizeof(int));
+    b.stats = scratch_.template alloc<int>(8);
+    be_.dev_memset(b.stats, 0, 8 * sizeof(int));
     be_.for_each(B, VtxProblemFn{o.d_seg_off, pov, pos});
     be_.for_each(B, InitStateFn{b.ps});
     launches(2);
@@ -461,10 +462,11 @@ class Pipeline {
     be_.h2d(b.vval, vval, sizeof(double) * (size_t)b.totV * TG_HALF * TG_D);
     be_.h2d(b.times, times, sizeof(double) * b.totS);
     be_.for_each(B, PrepareFn{b, 0});
-    int stats[4];
+    int stats[8];
     be_.d2h(stats, b.stats, sizeof(stats));
+    alloc_solution_buffers(b, (size_t)B, stats);
     be_.for_each(b.totS, SetupBaseFn{b, b.times});
-    be_.solve((size_t)B, stats[0], stats[2], SolveProblemDesc{b, 0, nullptr, nullptr});
+    solve_with_outputs((size_t)B, stats[0], stats[2], SolveProblemDesc{b, 0, nullptr, nullptr}, b);
     be_.for_each(B, CostOutFn{b.ps, d_cost});
     launches(4);
     counters.solves += B;
@@ -472,6 +474,23 @@ class Pipeline {
     if (coef) be_.d2h(coef, b.coef, sizeof(double) * (size_t)b.totS * TG_D * TG_N);
     if (cost) be_.d2h(cost, d_cost, sizeof(double) * B);
     return true;
+  }
+
+  // Solutions of the reduced systems and partial costs travel from the solve kernels to CoefCostFn / CostSumFn through
+  // these buffers (per instance: 4 * max n_p doubles and 4 * max S doubles).
+  void alloc_solution_buffers(BatchPtrs& b, size_t n_inst_max, const int* stats) {
+    b.xstride = 4 * std::max(stats[3], 1);
+    b.smax = std::max(stats[4], 1);
+    b.xs = scratch_.template alloc<double>(std::max<size_t>(n_inst_max, 1) * (size_t)b.xstride);
+    b.part = scratch_.template alloc<double>(std::max<size_t>(n_inst_max, 1) * 4 * (size_t)b.smax);
+  }
+  template <class D>
+  void solve_with_outputs(size_t n_inst, int ws, int ows, const D& desc, const BatchPtrs& b) {
+    be_.solve(n_inst, ws, ows, desc);
+    const int per = 4 * b.smax;
+    be_.for_each(n_inst * (size_t)per, CoefCostFn<D>{desc, per, b.part});
+    be_.for_each(n_inst, CostSumFn<D>{desc, per, b.part});
+    launches(2);
   }
 
   // PolynomialOptimizationNonLinear<10>::optimize() for every problem of the batch: Mellinger outer loop (nl_impl.h:159-234,
@@ -493,7 +512,7 @@ class Pipeline {
     be_.for_each(B, LbfgsBeginFn{b}); launches(1);
     for (int e = 0; e < P.max_evals; ++e) {
       be_.for_each((size_t)totS * 3, SetupMellingerFn{b});
-      be_.solve((size_t)totV, ws, ows, SolveProblemDesc{b, 1, nullptr, nullptr});
+      solve_with_outputs((size_t)totV, ws, ows, SolveProblemDesc{b, 1, nullptr, nullptr}, b);
       be_.for_each(B, LbfgsAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel});
       launches(3);
     }
@@ -524,11 +543,12 @@ class Pipeline {
     be_.h2d(b.vval, vval, sizeof(double) * (size_t)b.totV * TG_HALF * TG_D);
     be_.h2d(b.times, times, sizeof(double) * b.totS);
     be_.for_each(B, PrepareFn{b, 0}); launches(1);
-    int stats[4];
+    int stats[8];
     be_.d2h(stats, b.stats, sizeof(stats));
+    alloc_solution_buffers(b, (size_t)b.totV, stats);
     time_alloc_core(b, P, stats[0], stats[2]);
     be_.for_each(b.totS, SetupBaseFn{b, b.times});
-    be_.solve((size_t)B, stats[0], stats[2], SolveProblemDesc{b, 0, nullptr, nullptr});
+    solve_with_outputs((size_t)B, stats[0], stats[2], SolveProblemDesc{b, 0, nullptr, nullptr}, b);
     launches(2);
     std::vector<ProbState> ps(B);
     be_.d2h(ps.data(), b.ps, sizeof(ProbState) * B);
@@ -733,9 +753,10 @@ class Pipeline {
     be_.h2d(b.vmask, vmask, V);
     be_.h2d(b.vval, vval, sizeof(double) * (size_t)V * TG_HALF * TG_D);
     be_.for_each(1, PrepareFn{b, 0}); launches(1);
-    int stats[4];
+    int stats[8];
     be_.d2h(stats, b.stats, sizeof(stats));
     const long long chunk = std::min<long long>(K, (long long)sweep_chunk);
+    alloc_solution_buffers(b, (size_t)chunk, stats);
     double* d_recs = scratch_.template alloc<double>((size_t)chunk * S * TG_REC_SIZE);
     double* d_costs = scratch_.template alloc<double>((size_t)K);
     const double* d_cand = cand;
@@ -747,7 +768,7 @@ class Pipeline {
     for (long long k0 = 0; k0 < K; k0 += chunk) {
       const long long kc = std::min(chunk, K - k0);
       be_.for_each((size_t)kc * S, SetupSweepFn{S, r, d_cand + (size_t)k0 * S, d_recs});
-      be_.solve((size_t)kc, stats[0], stats[2], SolveSweepDesc{b, d_recs, d_costs + k0});
+      solve_with_outputs((size_t)kc, stats[0], stats[2], SolveSweepDesc{b, d_recs, d_costs + k0}, b);
       launches(2);
     }
     counters.solves += K;

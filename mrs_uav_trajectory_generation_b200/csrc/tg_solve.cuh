@@ -39,6 +39,8 @@ struct SolveInst {
   double* coef_out;       // [S][4][10] or null
   double* cost_out;       // or null
   double* dp_out;         // [4][np] or null
+  double* x_out;          // [np][4] or null: when set the routine stops after the back substitution and writes the solution here
+                          // (coefficients and cost are then computed by CoefCostFn / CostSumFn, one thread per (segment, dimension))
   // workspace (shared or global memory)
   int W;                  // row stride: 2*hbw+1 band entries + 4 right-hand sides + the reciprocal pivot
   double* rows;           // max(np*W, 40*S): banded rows; later the coefficient scratch
@@ -172,6 +174,12 @@ TG_HD void solve_warp(const SolveInst& I, int lane) {
         }
       }
     }
+  }
+  if (I.x_out) {
+    TG_PHASE(lane) {
+      for (int e = lane; e < TG_D * np; e += 32) I.x_out[e] = I.xs[e];
+    }
+    return;
   }
   // ---- phase 4: coefficients c = A^-1 [slots of vertex s ; slots of vertex s+1]  (lin_impl.h:271-280) -----------------
   TG_PHASE(lane) {

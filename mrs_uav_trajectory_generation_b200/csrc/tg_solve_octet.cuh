@@ -13,8 +13,9 @@
 //     __syncwarp() inside the factorisation or the back substitution;
 //   * shared memory holds the assembled rows until they enter the window, then (in place) the U rows for the back
 //     substitution, which runs the same window upwards;
-//   * coefficients and cost: the X / Dinv / Q blocks of a few segments at a time are staged into the (by then dead)
-//     band storage with coalesced 16-byte loads and consumed from shared memory per (segment, dimension).
+//   * the routine ends with the solution of the reduced system written to global memory; coefficients and cost are a
+//     separate flat kernel (CoefCostFn, one thread per (segment, dimension)) -- fused into this kernel they cost a third
+//     of its time at 8 warps per SM (profiles/r01_solve_octet.md).
 //
 // Eligibility: half bandwidth exactly 7 (every interior vertex has position fixed and v, a, j, s free -- the node's
 // recipe, node.cpp:931-977), at least 8 unknowns, and a workspace that fits shared memory; anything else takes
@@ -30,13 +31,11 @@ namespace tg {
 constexpr int kOctRow = 20;    // doubles per banded row: 16 column slots (column j at j & 15) + 4 right-hand sides
 constexpr int kOctHbw = 7;
 constexpr int kOctMinNp = 8;
-constexpr int kOctStage = TG_REC_H;  // doubles staged per segment in phase 4: Dinv, X, Q (everything before H)
-constexpr int kOctStageStride = 128;  // staging stride per segment (multiple of 16: static shared-memory offsets)
 
-// shared-memory doubles for one octet solve: rows | partial costs | slot table | row -> (vertex, slot) table.
+// shared-memory doubles for one octet solve: rows | slot table | row -> (vertex, slot) table.
 // Sized = 2 (mod 16) so that the four octets of a warp start in different banks.
 TG_HD int octet_ws_doubles(int S, int np) {
-  int n = np * kOctRow + 4 * S + (5 * (S + 1) + 3) / 4 + (np + 3) / 4;
+  int n = np * kOctRow + (5 * (S + 1) + 3) / 4 + (np + 3) / 4;
   n = (n + 1) & ~1;
   while ((n & 15) != 2) n += 2;
   return n;
@@ -45,15 +44,13 @@ TG_HD void octet_ws_bind(SolveInst& I, double* ws) {
   I.W = kOctRow;
   I.rows = ws;
   I.xs = nullptr;
-  I.part = ws + I.np * kOctRow;
-  I.slot = (int16_t*)(I.part + 4 * I.S);
+  I.part = nullptr;
+  I.slot = (int16_t*)(ws + I.np * kOctRow);
   I.rowva = I.slot + ((5 * (I.S + 1) + 3) / 4) * 4;
 }
-TG_HD bool octet_eligible(const SolveInst& I) { return I.hbw == kOctHbw && I.np >= kOctMinNp && I.dp_out == nullptr; }
+// the routine produces the solution of the reduced system only (x_out); coefficients and cost are CoefCostFn's job
+TG_HD bool octet_eligible(const SolveInst& I) { return I.hbw == kOctHbw && I.np >= kOctMinNp && I.dp_out == nullptr && I.x_out != nullptr; }
 
-struct alignas(16) Dbl2 {
-  double x, y;
-};
 
 struct OctLane {
   double reg[16];  // band entries of the row this lane holds, column j at index (j - block start) & 15
@@ -102,25 +99,6 @@ TG_HD void octet_swap_halves(OctLane& st) {
     st.reg[q] = st.reg[q + 8];
     st.reg[q + 8] = t;
   }
-}
-
-// index of staged double e inside the band storage: only the 16 column slots of every row are free, the
-// right-hand-side slots hold the solution
-TG_HD int octet_stage_index(int e) { return (e >> 4) * kOctRow + (e & 15); }
-
-// (c^T Q) c over the non-zero block; `q` points at the staged record of the segment (offsets are compile-time)
-template <int R>
-TG_HD double octet_cost_partial(const double (&c)[TG_N], const double* __restrict__ q) {
-  constexpr int nq = TG_N - R;
-  double partial = 0.0;
-#pragma unroll
-  for (int b = 0; b < nq; ++b) {
-    double sum = c[R] * q[octet_stage_index(TG_REC_Q + 0 * 8 + b)];
-#pragma unroll
-    for (int k = 1; k < nq; ++k) sum = sum + c[R + k] * q[octet_stage_index(TG_REC_Q + k * 8 + b)];
-    partial = (b == 0) ? sum * c[R + b] : partial + sum * c[R + b];
-  }
-  return partial;
 }
 
 // Device: `insts` points at the calling lane's own instance (lanes of one octet hold identical copies); an octet
@@ -310,9 +288,8 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
           OctLane& st = TG_OCT_STATE(st_all, lane);
           if (j < I.np) {
             if (st.myrow == j) {
-              double* rj = I.rows + j * kOctRow;
 #pragma unroll
-              for (int d = 0; d < 4; ++d) rj[16 + d] = st.x[d];
+              for (int d = 0; d < 4; ++d) I.x_out[j * 4 + d] = st.x[d];  // the solution leaves through global memory
               st.myrow = j - 8;
               if (st.myrow >= 0) {
                 const double* src = I.rows + st.myrow * kOctRow;
@@ -333,106 +310,6 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
       }
     }
     TG_PHASE_NS(lane) { octet_swap_halves(TG_OCT_STATE(st_all, lane)); }
-  }
-  // ---- phase 4: coefficients (lin_impl.h:271-280) and the partial costs (lin_impl.h:135-137) per (segment, dimension).
-  // Rounds of up to four segments: stage Dinv | X | Q of the round's segments into the dead band storage, then
-  // lane (dimension d = sub & 3, segment parity sub >> 2) computes its (segment, dimension) tasks from shared memory.
-  TG_PHASE(lane) {}  // the solution (right-hand-side slots of every row) becomes visible to all lanes
-  int nrounds = 0;
-  {
-    // rounds needed by the slowest octet of the warp (warp-uniform): every octet stages min(4, np*16/kOctStageStride) segments per round
-    int worst = 1;
-#if defined(__CUDA_ARCH__)
-    const SolveInst& I0 = insts[0];
-    const int per = (I0.np > 0) ? imin(4, (I0.np * 16) / kOctStageStride) : 4;
-    const int need = (I0.S + per - 1) / per;
-    worst = __reduce_max_sync(0xffffffffu, need);
-#else
-    for (int o = 0; o < 4; ++o) {
-      const SolveInst& I0 = insts[o];
-      const int per = (I0.np > 0) ? imin(4, (I0.np * 16) / kOctStageStride) : 4;
-      worst = imax(worst, (I0.S + per - 1) / per);
-    }
-#endif
-    nrounds = worst;
-  }
-  for (int round = 0; round < nrounds; ++round) {
-    TG_PHASE(lane) {  // stage
-      const SolveInst& I = TG_OCT_INST(insts, lane);
-      const int sub = lane & 7;
-      if (I.np > 0) {
-        const int per = imin(4, (I.np * 16) / kOctStageStride);
-        const int s_lo = round * per, s_hi = imin(I.S, s_lo + per);
-        for (int s = s_lo; s < s_hi; ++s) {
-          const double* rec = solve_rec(I, s);
-          const int base = (s - s_lo) * kOctStageStride;
-          for (int e = 2 * sub; e < kOctStage; e += 16) {
-            const Dbl2 t = *reinterpret_cast<const Dbl2*>(rec + e);
-            *reinterpret_cast<Dbl2*>(I.rows + octet_stage_index(base + e)) = t;
-          }
-        }
-      }
-    }
-    TG_PHASE(lane) {  // compute
-      const SolveInst& I = TG_OCT_INST(insts, lane);
-      const int sub = lane & 7;
-      if (I.np > 0) {
-        const int per = imin(4, (I.np * 16) / kOctStageStride);
-        const int s_lo = round * per, s_hi = imin(I.S, s_lo + per);
-        for (int it = s_lo * TG_D + sub; it < s_hi * TG_D; it += 8) {
-          const int s = it >> 2, d = it & 3;
-          const int base = (s - s_lo) * kOctStageStride;
-          double nd[TG_N], c[TG_N];
-#pragma unroll
-          for (int k = 0; k < TG_N; ++k) {
-            const int j = I.slot[s * TG_HALF + k];  // slots of vertex s then vertex s+1 are contiguous in the table
-            nd[k] = (j >= 0) ? I.rows[j * kOctRow + 16 + d] : I.vval[((size_t)s * TG_HALF + k) * TG_D + d];
-          }
-          c[0] = 1.0 * nd[0];
-          c[1] = 1.0 * nd[1];
-          c[2] = (1.0 / 2.0) * nd[2];
-          c[3] = (1.0 / 6.0) * nd[3];
-          c[4] = (1.0 / 24.0) * nd[4];
-#pragma unroll
-          for (int a = 0; a < TG_HALF; ++a) {
-            double xr[5], dr[5];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-              xr[k] = I.rows[octet_stage_index(base) + octet_stage_index(TG_REC_X + a * 5 + k)];
-              dr[k] = I.rows[octet_stage_index(base) + octet_stage_index(TG_REC_DINV + a * 5 + k)];
-            }
-            double acc = xr[0] * nd[0];
-#pragma unroll
-            for (int k = 1; k < 5; ++k) acc = acc + xr[k] * nd[k];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) acc = acc + dr[k] * nd[5 + k];
-            c[TG_HALF + a] = acc;
-          }
-          if (I.coef_out) {
-#pragma unroll
-            for (int a = 0; a < TG_N; a += 2) {
-              Dbl2 t;
-              t.x = c[a];
-              t.y = c[a + 1];
-              *reinterpret_cast<Dbl2*>(I.coef_out + it * TG_N + a) = t;
-            }
-          }
-          if (I.cost_out) {
-            const double* q = I.rows + octet_stage_index(base);
-            I.part[it] = (I.r == 2) ? octet_cost_partial<2>(c, q) : ((I.r == 3) ? octet_cost_partial<3>(c, q) : octet_cost_partial<4>(c, q));
-          }
-        }
-      }
-    }
-  }
-  // ---- phase 5: total in (segment, dimension) order (lin_impl.h:131-140) ----------------------------------------------
-  TG_PHASE(lane) {
-    const SolveInst& I = TG_OCT_INST(insts, lane);
-    if ((lane & 7) == 0 && I.cost_out && I.S > 0) {
-      double total = 0.0;
-      for (int it = 0; it < I.S * TG_D; ++it) total += I.part[it];
-      *I.cost_out = 0.5 * total;
-    }
   }
 }
 
