@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <cstdlib>
 #include <map>
 #include <stdexcept>
@@ -200,6 +202,9 @@ struct CudaBackend {
   bool force_general_solve = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  static constexpr int kSideStreams = 9;
+  cudaStream_t side[kSideStreams] = {};
+  cudaEvent_t ev_fork = nullptr, ev_side[kSideStreams] = {};
   void* scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
   double* solve_slab = nullptr;
@@ -226,6 +231,11 @@ struct CudaBackend {
     TG_CUDA_CHECK(cudaEventCreate(&ev1));
     TG_CUDA_CHECK(cudaEventCreate(&pev0));
     TG_CUDA_CHECK(cudaEventCreate(&pev1));
+    TG_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < kSideStreams; ++i) {
+      TG_CUDA_CHECK(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+      TG_CUDA_CHECK(cudaEventCreateWithFlags(&ev_side[i], cudaEventDisableTiming));
+    }
   }
   ~CudaBackend() {
     cudaSetDevice(device);
@@ -235,6 +245,11 @@ struct CudaBackend {
     if (ev1) cudaEventDestroy(ev1);
     if (pev0) cudaEventDestroy(pev0);
     if (pev1) cudaEventDestroy(pev1);
+    for (int i = 0; i < kSideStreams; ++i) {
+      if (side[i]) cudaStreamDestroy(side[i]);
+      if (ev_side[i]) cudaEventDestroy(ev_side[i]);
+    }
+    if (ev_fork) cudaEventDestroy(ev_fork);
     if (stream) cudaStreamDestroy(stream);
   }
   CudaBackend(const CudaBackend&) = delete;
@@ -315,6 +330,31 @@ struct CudaBackend {
     k_vm<F><<<(unsigned)grid, kVmThreads, smem, stream>>>(f, (int)n_max, n_dev, counter);
     TG_CUDA_CHECK(cudaGetLastError());
     prof_end(typeid(F).name(), n_max);
+  }
+  // fork / join of n side streams around independent launches (for_each_scratch_on); with per-kernel profiling on, everything
+  // stays on the main stream so that the event pairs measure single kernels
+  void fork(int n) {
+    if (profiling) return;
+    TG_CUDA_CHECK(cudaEventRecord(ev_fork, stream));
+    for (int i = 0; i < n && i < kSideStreams; ++i) TG_CUDA_CHECK(cudaStreamWaitEvent(side[i], ev_fork, 0));
+  }
+  void join(int n) {
+    if (profiling) return;
+    for (int i = 0; i < n && i < kSideStreams; ++i) {
+      TG_CUDA_CHECK(cudaEventRecord(ev_side[i], side[i]));
+      TG_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_side[i], 0));
+    }
+  }
+  template <class F>
+  void for_each_scratch_on(int k, size_t n, const F& f) {
+    if (profiling) return for_each_scratch(n, f);
+    if (n == 0) return;
+    const unsigned block = 128;
+    const size_t grid = (n + block - 1) / block;
+    const size_t smem = (size_t)F::kScratch * sizeof(double) * block;
+    TG_CUDA_CHECK(cudaFuncSetAttribute(k_for_each_scratch<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_for_each_scratch<F><<<(unsigned)grid, block, smem, side[k % kSideStreams]>>>(f, n);
+    TG_CUDA_CHECK(cudaGetLastError());
   }
   void prof_begin() {
     if (profiling) TG_CUDA_CHECK(cudaEventRecord(pev0, stream));
@@ -399,6 +439,25 @@ struct CudaBackend {
     prof_end(typeid(D).name(), n_inst);
   }
 
+  // out[0..count) = indices i < n with flags[i] != 0, ascending (order-preserving compaction); *count = how many (device)
+  void select_flagged(const uint8_t* flags, int* out, int* count, int n) {
+    if (n <= 0) {
+      TG_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), stream));
+      return;
+    }
+    cub::CountingInputIterator<int> idx(0);
+    size_t bytes = 0;
+    TG_CUDA_CHECK(cub::DeviceSelect::Flagged(nullptr, bytes, idx, flags, out, count, n, stream));
+    if (bytes > scan_tmp_bytes) {
+      if (scan_tmp) {
+        TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        TG_CUDA_CHECK(cudaFree(scan_tmp));
+      }
+      TG_CUDA_CHECK(cudaMalloc(&scan_tmp, bytes));
+      scan_tmp_bytes = bytes;
+    }
+    TG_CUDA_CHECK(cub::DeviceSelect::Flagged(scan_tmp, bytes, idx, flags, out, count, n, stream));
+  }
   // out[0..n] = exclusive prefix sums of in[0..n-1], out[n] = total.  `in` must have n+1 elements.
   void exclusive_scan(int* in, int* out, int n) {
     TG_CUDA_CHECK(cudaMemsetAsync(in + n, 0, sizeof(int), stream));

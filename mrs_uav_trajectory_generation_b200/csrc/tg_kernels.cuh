@@ -444,13 +444,8 @@ struct ExtremaWorkFn {
   const int* prob_of_seg;
   const ProbState* ps;
   const uint8_t* changed;  // [totS] written by ScaleFn
-  int* work;
-  int* count;
-  TG_HD void operator()(size_t gs) const {
-    if (ps[prob_of_seg[gs]].scale_done || !changed[gs]) return;
-    const int at = TG_ATOMIC_ADD_RET(count, 1);
-    work[at] = (int)gs;
-  }
+  uint8_t* flag;           // [totS] 1: recompute (the ordered work list is built from the flags by the backend's select)
+  TG_HD void operator()(size_t gs) const { flag[gs] = (!ps[prob_of_seg[gs]].scale_done && changed[gs]) ? 1 : 0; }
 };
 
 // Certificates for the global check (tg_bound.cuh): one thread per entry of the changed-segment work list.  A quantity
@@ -463,8 +458,7 @@ struct ExtremaBoundFn {
   uint8_t* is_bound;   // [totS * 9]
   const int* work;     // changed segments
   const int* n_work;   // device count
-  int* lists;          // [9][list_stride]
-  int* counts;         // [9]
+  uint8_t* need;       // [9][list_stride] 1: (segment, quantity) needs exact root finding
   int list_stride;
   double L[9];
   double tol;
@@ -480,8 +474,7 @@ struct ExtremaBoundFn {
         is_bound[gs * 9 + q] = 1;
       } else {
         is_bound[gs * 9 + q] = 0;
-        const int at = TG_ATOMIC_ADD_RET(&counts[q], 1);
-        lists[(size_t)q * list_stride + at] = (int)gs;
+        need[(size_t)q * list_stride + gs] = 1;
       }
     }
   }
@@ -505,8 +498,7 @@ struct ExtremaPruneAFn {
   double L[9];
   double* rq;          // [totS][9] transformed bounds
   uint8_t* qstar;      // [totS] quantity computed first, 0xff: none needed, 0xfe: all nine (bounds unusable)
-  int* lists;          // [9][list_stride]
-  int* counts;         // [9]
+  uint8_t* need;       // [9][list_stride] 1: (segment, quantity) needs exact root finding
   int list_stride;
   TG_HD void operator()(size_t gs) const {
     const double* coef = b.coef + gs * TG_D * TG_N;
@@ -550,10 +542,7 @@ struct ExtremaPruneAFn {
     }
     if (!usable) {
       qstar[gs] = 0xfe;
-      for (int q = 0; q < 9; ++q) {
-        const int at = TG_ATOMIC_ADD_RET(&counts[q], 1);
-        lists[(size_t)q * list_stride + at] = (int)gs;
-      }
+      for (int q = 0; q < 9; ++q) need[(size_t)q * list_stride + gs] = 1;
       return;
     }
     if (rmax <= 1.0) {
@@ -562,8 +551,7 @@ struct ExtremaPruneAFn {
       return;
     }
     qstar[gs] = (uint8_t)qs;
-    const int at = TG_ATOMIC_ADD_RET(&counts[qs], 1);
-    lists[(size_t)qs * list_stride + at] = (int)gs;
+    need[(size_t)qs * list_stride + gs] = 1;
   }
 };
 struct ExtremaPruneCFn {
@@ -571,8 +559,7 @@ struct ExtremaPruneCFn {
   double L[9];
   const double* rq;
   const uint8_t* qstar;
-  int* lists;
-  int* counts;
+  uint8_t* need;
   int list_stride;
   TG_HD void operator()(size_t gs) const {
     const int qs = qstar[gs];
@@ -589,12 +576,8 @@ struct ExtremaPruneCFn {
         const double thr = (d == 0 ? lim * M : (d == 1 ? lim * M * M : lim * M * M * M)) * (1.0 - 1e-9);
         drop = certify_quantity_le(b.coef + gs * TG_D * TG_N, b.times[gs], q, thr);
       }
-      if (drop) {
-        b.maxima[gs * 9 + q] = 0.0;
-      } else {
-        const int at = TG_ATOMIC_ADD_RET(&counts[q], 1);
-        lists[(size_t)q * list_stride + at] = (int)gs;
-      }
+      if (drop) b.maxima[gs * 9 + q] = 0.0;
+      else need[(size_t)q * list_stride + gs] = 1;
     }
   }
 };
@@ -604,16 +587,14 @@ struct ExtremaCompleteFn {
   const int* prob_of_seg;
   const ProbState* ps;
   uint8_t* is_bound;
-  int* lists;
-  int* counts;
+  uint8_t* need;
   int list_stride;
   TG_HD void operator()(size_t gs) const {
     if (ps[prob_of_seg[gs]].scale_done) return;
     for (int q = 0; q < 9; ++q)
       if (is_bound[gs * 9 + q]) {
         is_bound[gs * 9 + q] = 0;
-        const int at = TG_ATOMIC_ADD_RET(&counts[q], 1);
-        lists[(size_t)q * list_stride + at] = (int)gs;
+        need[(size_t)q * list_stride + gs] = 1;
       }
   }
 };

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -818,50 +819,70 @@ class Pipeline {
     for (int i = 0; i < 9; ++i) { sf.L[i] = L9[i]; cf.L[i] = L9[i]; }
     uint8_t* changed = scratch_.template alloc<uint8_t>(totS);
     uint8_t* is_bound = scratch_.template alloc<uint8_t>(totS * 9);
+    uint8_t* need = scratch_.template alloc<uint8_t>(totS * 9);   // [9][totS] flags -> ordered work lists
+    uint8_t* wflag = scratch_.template alloc<uint8_t>(totS);
     int* work = scratch_.template alloc<int>(totS);
     int* lists = scratch_.template alloc<int>(totS * 9);
     int* counts = scratch_.template alloc<int>(16);  // [0..8] per-quantity list lengths, [9] changed segments
     sf.changed = changed;
     be_.dev_memset(is_bound, 0, totS * 9);
     ExtremaScratch es = extrema_scratch(totS);
+    // work lists are built by an order-preserving select (deterministic order; measured no faster than atomic append)
+    auto run_lists = [&](const char* what) {
+      for (int q = 0; q < 9; ++q) be_.select_flagged(need + (size_t)q * totS, lists + (size_t)q * totS, counts + q, (int)totS);
+      trace_counts(what, counts, totS);
+      extrema_lists(b.coef, b.times, b.maxima, totS, lists, counts, es);
+    };
     if (prune_extrema) {
       // maxima for the first pass' stretch factors: bounds, then the one quantity that can bind, then whatever is left
       double* rq = scratch_.template alloc<double>(totS * 9);
       uint8_t* qstar = scratch_.template alloc<uint8_t>(totS);
-      be_.dev_memset(counts, 0, 16 * sizeof(int));
-      ExtremaPruneAFn pa{b, {}, rq, qstar, lists, counts, (int)totS};
-      ExtremaPruneCFn pc{b, {}, rq, qstar, lists, counts, (int)totS};
+      ExtremaPruneAFn pa{b, {}, rq, qstar, need, (int)totS};
+      ExtremaPruneCFn pc{b, {}, rq, qstar, need, (int)totS};
       for (int i = 0; i < 9; ++i) { pa.L[i] = L9[i]; pc.L[i] = L9[i]; }
+      be_.dev_memset(need, 0, totS * 9);
       be_.for_each(totS, pa);
-      extrema_lists(b.coef, b.times, b.maxima, totS, lists, counts, es);
-      be_.dev_memset(counts, 0, 16 * sizeof(int));
+      run_lists("prune A (first quantity)");
+      be_.dev_memset(need, 0, totS * 9);
       be_.for_each(totS, pc);
-      extrema_lists(b.coef, b.times, b.maxima, totS, lists, counts, es);
+      run_lists("prune C (not certified)");
       launches(2);
     } else {
       extrema_segments(b.coef, b.times, b.maxima, totS, nullptr, nullptr, es);
     }
     for (int pass = 0; pass < 20; ++pass) {
       be_.dev_memset(b.stats + 1, 0, sizeof(int));
-      be_.dev_memset(counts, 0, 16 * sizeof(int));
       be_.for_each(totS, sf);
-      be_.for_each(totS, ExtremaWorkFn{b.prob_of_seg, b.ps, changed, work, counts + 9});
+      be_.for_each(totS, ExtremaWorkFn{b.prob_of_seg, b.ps, changed, wflag});
+      be_.select_flagged(wflag, work, counts + 9, (int)totS);
       // global check (eth/trajectory.cpp:660-689): certificates first, exact root finding only where they do not decide
-      ExtremaBoundFn bf{b.coef, b.times, b.maxima, is_bound, work, counts + 9, lists, counts, (int)totS, {}, scale_tolerance};
+      be_.dev_memset(need, 0, totS * 9);
+      ExtremaBoundFn bf{b.coef, b.times, b.maxima, is_bound, work, counts + 9, need, (int)totS, {}, scale_tolerance};
       for (int i = 0; i < 9; ++i) bf.L[i] = L9[i];
       be_.for_each(totS, bf);
-      extrema_lists(b.coef, b.times, b.maxima, totS, lists, counts, es);
+      run_lists("global check (not certified)");
       be_.for_each((size_t)b.B, cf);
       launches(4);
       int pending = 0;
       be_.d2h(&pending, b.stats + 1, sizeof(int));
       if (pending == 0) break;
       // another pass follows for `pending` problems: their certified entries must be exact before ScaleFn reads them
-      be_.dev_memset(counts, 0, 16 * sizeof(int));
-      be_.for_each(totS, ExtremaCompleteFn{b.prob_of_seg, b.ps, is_bound, lists, counts, (int)totS});
-      extrema_lists(b.coef, b.times, b.maxima, totS, lists, counts, es);
+      be_.dev_memset(need, 0, totS * 9);
+      be_.for_each(totS, ExtremaCompleteFn{b.prob_of_seg, b.ps, is_bound, need, (int)totS});
+      run_lists("completion");
       launches(1);
     }
+  }
+
+  // TG_TRACE_PRUNE=1: prints how many (segment, quantity) pairs still need root finding after each certificate stage
+  void trace_counts(const char* what, const int* d_counts, size_t totS) {
+    static const bool on = std::getenv("TG_TRACE_PRUNE") != nullptr;
+    if (!on) return;
+    int c[16];
+    be_.d2h(c, d_counts, sizeof(c));
+    std::fprintf(stderr, "[prune] %-30s segments %zu  per quantity:", what, totS);
+    for (int q = 0; q < 9; ++q) std::fprintf(stderr, " %d", c[q]);
+    std::fprintf(stderr, "\n");
   }
 
   // exact maxima for per-quantity work lists: lists[q * n_max ..], lengths counts[q] in device memory
@@ -882,15 +903,18 @@ class Pipeline {
     launches(18);
 #else
     (void)es;
-    be_.for_each_scratch(n_max, ExtremaRawFn<0>{coef, times, maxima, lists + 0 * n_max, counts + 0});
-    be_.for_each_scratch(n_max, ExtremaRawFn<1>{coef, times, maxima, lists + 1 * n_max, counts + 1});
-    be_.for_each_scratch(n_max, ExtremaRawFn<2>{coef, times, maxima, lists + 2 * n_max, counts + 2});
-    be_.for_each_scratch(n_max, ExtremaRawFn<3>{coef, times, maxima, lists + 3 * n_max, counts + 3});
-    be_.for_each_scratch(n_max, ExtremaRawFn<4>{coef, times, maxima, lists + 4 * n_max, counts + 4});
-    be_.for_each_scratch(n_max, ExtremaRawFn<5>{coef, times, maxima, lists + 5 * n_max, counts + 5});
-    be_.for_each_scratch(n_max, ExtremaRawFn<6>{coef, times, maxima, lists + 6 * n_max, counts + 6});
-    be_.for_each_scratch(n_max, ExtremaRawFn<7>{coef, times, maxima, lists + 7 * n_max, counts + 7});
-    be_.for_each_scratch(n_max, ExtremaRawFn<8>{coef, times, maxima, lists + 8 * n_max, counts + 8});
+    // the nine quantities are independent: one side stream each, so that the long tails of the root finder overlap
+    be_.fork(9);
+    be_.for_each_scratch_on(0, n_max, ExtremaRawFn<0>{coef, times, maxima, lists + 0 * n_max, counts + 0});
+    be_.for_each_scratch_on(1, n_max, ExtremaRawFn<1>{coef, times, maxima, lists + 1 * n_max, counts + 1});
+    be_.for_each_scratch_on(2, n_max, ExtremaRawFn<2>{coef, times, maxima, lists + 2 * n_max, counts + 2});
+    be_.for_each_scratch_on(3, n_max, ExtremaRawFn<3>{coef, times, maxima, lists + 3 * n_max, counts + 3});
+    be_.for_each_scratch_on(4, n_max, ExtremaRawFn<4>{coef, times, maxima, lists + 4 * n_max, counts + 4});
+    be_.for_each_scratch_on(5, n_max, ExtremaRawFn<5>{coef, times, maxima, lists + 5 * n_max, counts + 5});
+    be_.for_each_scratch_on(6, n_max, ExtremaRawFn<6>{coef, times, maxima, lists + 6 * n_max, counts + 6});
+    be_.for_each_scratch_on(7, n_max, ExtremaRawFn<7>{coef, times, maxima, lists + 7 * n_max, counts + 7});
+    be_.for_each_scratch_on(8, n_max, ExtremaRawFn<8>{coef, times, maxima, lists + 8 * n_max, counts + 8});
+    be_.join(9);
     launches(9);
 #endif
   }

@@ -69,6 +69,10 @@ struct EmuBackend {
       f(i, scratch, 1);
     });
   }
+  void fork(int) {}
+  void join(int) {}
+  template <class F>
+  void for_each_scratch_on(int, size_t n, const F& f) { for_each_scratch(n, f); }
   // one "warp" per group of four instances (octet kernel) or per instance (general kernel): phases run lane by lane
   // (lanes own disjoint outputs within a phase).  Mirrors k_solve_oct / k_solve of cuda_backend.cu.
   template <class D>
@@ -122,6 +126,13 @@ struct EmuBackend {
       double scratch[F::kScratch];
       f.single(i, scratch, 1);
     });
+  }
+  // out[0..count) = indices i < n with flags[i] != 0, ascending; *count = how many
+  void select_flagged(const uint8_t* flags, int* out, int* count, int n) {
+    int c = 0;
+    for (int i = 0; i < n; ++i)
+      if (flags[i]) out[c++] = i;
+    *count = c;
   }
   void exclusive_scan(const int* in, int* out, int n) {
     int acc = 0;
