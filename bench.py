@@ -231,7 +231,9 @@ def main():
         prof_table = {k: {"ms": round(v[0], 3), "launches": v[1], "share": round(v[0] / tot_ms, 4)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
         top = max(prof.items(), key=lambda kv: kv[1][0])
         name, (ms, launches, items) = top
-        if "Solve" in name:
+        if "CoefCost" in name:
+            flops = cb["flops_coef"] - ca["flops_coef"]
+        elif "Solve" in name:
             flops = cb["flops_solve"] - ca["flops_solve"]
         elif "Setup" in name:
             flops = cb["flops_setup"] - ca["flops_setup"]
@@ -268,12 +270,13 @@ def main():
                 "timing": "CUDA events on the library's stream around each batch call (tg_last_device_ms), max over ranks",
                 "wall_ms_per_step": wall_ms_max / args.steps,
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stats": {"success_rate": float(res["success"].mean()), "safe_rate": float(res["safe"].mean()), "mean_rounds": float(res["rounds"].mean()),
                       "mean_final_segments": float(res["n_waypoints"].mean() - 1), "mean_samples": float(res["n_samples"].mean()),
-                      "solves_per_step": int((c1["solves"] - c0["solves"]) / args.steps), "root_finds_per_step": int((c1["root_finds"] - c0["root_finds"]) / args.steps)},
+                      "solves_per_step": int((c1["solves"] - c0["solves"]) / args.steps), "root_finds_reference_equivalent_per_step": int((c1["root_finds"] - c0["root_finds"]) / args.steps),
+                      "root_finds_executed_per_step": int((c1["root_finds_executed"] - c0["root_finds_executed"]) / args.steps)},
         }
         if roofline:
             line["roofline"] = roofline

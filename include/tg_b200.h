@@ -83,11 +83,13 @@ void tg_default_params(tg_params* p);
 int tg_ctx_create(int device, tg_ctx** out);
 void tg_ctx_destroy(tg_ctx* ctx);
 const char* tg_last_error(const tg_ctx* ctx);
-/* counters[8]: kernel launches, linear solves, objective evaluations, root finds, segment setups, samples,
- * solves inside the time-allocation loop, launches of that solve kernel (cumulative since the context was created). */
+/* counters[16] (9 used): kernel launches, linear solves, objective evaluations, root finds the REFERENCE would run for the
+ * same work, segment setups, samples, solves inside the time-allocation loop, launches of that solve kernel, Jenkins-Traub
+ * runs actually launched (after the exact pruning of tg_bound.cuh); cumulative since the context was created. */
 int tg_get_counters(const tg_ctx* ctx, long long* counters);
-/* flops[4]: ALGORITHMIC flops (SURVEY.md 8(d) formula) of the launched work: solve kernels, segment-setup
- * kernels, sampling, 0 -- the numerators of the roofline report. */
+/* flops[4]: ALGORITHMIC flops (SURVEY.md 8(d) formula) of the launched work: solve kernels (assembly, banded
+ * factorisation, back substitution), segment-setup kernels, sampling, coefficient + cost kernel -- the numerators of the
+ * roofline report. */
 int tg_get_flop_counters(const tg_ctx* ctx, double* flops);
 /* Milliseconds of device time (CUDA events on the context's stream) spent inside the last batch call. */
 double tg_last_device_ms(const tg_ctx* ctx);

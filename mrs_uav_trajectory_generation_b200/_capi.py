@@ -173,12 +173,13 @@ class Context:
             raise TgError(f"tg call failed ({rc}): {self.L.lib.tg_last_error(self.h).decode()}")
 
     def counters(self):
-        c = (C.c_longlong * 8)()
+        c = (C.c_longlong * 16)()
         self.L.lib.tg_get_counters(self.h, c)
         f = (C.c_double * 4)()
         self.L.lib.tg_get_flop_counters(self.h, f)
         return dict(launches=c[0], solves=c[1], evals=c[2], root_finds=c[3], segment_setups=c[4], samples=c[5],
-                    mellinger_solves=c[6], mellinger_launches=c[7], flops_solve=f[0], flops_setup=f[1], flops_sample=f[2])
+                    mellinger_solves=c[6], mellinger_launches=c[7], root_finds_executed=c[8], flops_solve=f[0], flops_setup=f[1], flops_sample=f[2],
+                    flops_coef=f[3])
 
     def set_profiling(self, on):
         self.L.lib.tg_set_profiling(self.h, 1 if on else 0)

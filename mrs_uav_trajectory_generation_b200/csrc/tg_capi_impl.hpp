@@ -85,7 +85,7 @@ const char* tg_last_error(const tg_ctx* ctx) { return ctx ? ctx->err.c_str() : "
 int tg_get_counters(const tg_ctx* ctx, long long* c) {
   if (!ctx || !c) return TG_ERR_INVALID;
   const tg::Counters& k = ctx->pipe.counters;
-  c[0] = k.launches; c[1] = k.solves; c[2] = k.evals; c[3] = k.root_finds; c[4] = k.segment_setups; c[5] = k.samples; c[6] = k.mellinger_solves; c[7] = k.mellinger_launches;
+  c[0] = k.launches; c[1] = k.solves; c[2] = k.evals; c[3] = k.root_finds; c[4] = k.segment_setups; c[5] = k.samples; c[6] = k.mellinger_solves; c[7] = k.mellinger_launches; c[8] = k.root_finds_executed;
   return TG_OK;
 }
 
@@ -94,7 +94,7 @@ double tg_last_device_ms(const tg_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
 int tg_get_flop_counters(const tg_ctx* ctx, double* f) {
   if (!ctx || !f) return TG_ERR_INVALID;
   const tg::Counters& k = ctx->pipe.counters;
-  f[0] = k.flops_solve; f[1] = k.flops_setup; f[2] = k.flops_sample; f[3] = 0.0;
+  f[0] = k.flops_solve; f[1] = k.flops_setup; f[2] = k.flops_sample; f[3] = k.flops_coef;
   return TG_OK;
 }
 

@@ -582,6 +582,15 @@ struct ExtremaPruneCFn {
   }
 };
 
+struct AccumCountsFn {  // adds the nine work-list lengths into a running total (Jenkins-Traub runs launched)
+  const int* counts;
+  int* total;
+  TG_HD void operator()(size_t) const {
+    int t = 0;
+    for (int q = 0; q < 9; ++q) t += counts[q];
+    *total += t;
+  }
+};
 // Before another scaling pass reads the maxima of a problem that failed the check: its flagged entries become exact.
 struct ExtremaCompleteFn {
   const int* prob_of_seg;

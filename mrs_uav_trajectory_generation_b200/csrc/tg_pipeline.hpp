@@ -97,7 +97,8 @@ struct Group {
 struct Counters {
   long long launches = 0, solves = 0, evals = 0, root_finds = 0, segment_setups = 0, samples = 0;
   // algorithmic flops (SURVEY.md 8(d) formula) of the work actually launched, per kernel family
-  double flops_solve = 0, flops_setup = 0, flops_sample = 0;
+  double flops_solve = 0, flops_setup = 0, flops_sample = 0, flops_coef = 0;
+  long long root_finds_executed = 0;  // Jenkins-Traub runs actually launched (root_finds counts what the reference would run)
   long long mellinger_solves = 0, mellinger_launches = 0;
 };
 
@@ -177,17 +178,26 @@ class Pipeline {
     std::vector<int> h_np(B), h_hbw(B);
     be_.d2h(h_np.data(), b.np, sizeof(int) * B);
     be_.d2h(h_hbw.data(), b.hbw, sizeof(int) * B);
-    if (P.run_time_alloc) counters.mellinger_launches += P.max_evals;
+    if (P.run_time_alloc) {
+      counters.mellinger_launches += P.max_evals;
+      int executed = 0;
+      be_.d2h(&executed, b.stats + 5, sizeof(int));
+      counters.root_finds_executed += executed;
+    }
     for (int p = 0; p < B; ++p) {
       const int S = g.seg_off[p + 1] - g.seg_off[p];
       const int ev = g.ps[p].n_evals;
       const long long nsolve = (long long)ev * (S == 1 ? 1 : S + 1) + 1;
       const long long nsetup = (long long)ev * S * (S == 1 ? 1 : 3) + S;
       const double np_ = h_np[p], bw = h_hbw[p];
-      const double f_solve = np_ * (bw * bw + 3.0 * bw) + 4.0 * (2.0 * np_ * 15.0 + 4.0 * np_ * bw + S * 200.0 + S * 220.0);
+      // SURVEY.md 8(d) formula, split by kernel: banded factorisation + right-hand sides + back substitution (solve kernel),
+      // coefficients + cost (CoefCostFn)
+      const double f_solve = np_ * (bw * bw + 3.0 * bw) + 4.0 * (2.0 * np_ * 15.0 + 4.0 * np_ * bw);
+      const double f_coef = 4.0 * (S * 200.0 + S * 220.0);
       const double nq = TG_N - P.derivative_to_optimize;
       const double f_setup = 3.0 * nq * nq + 525.0 + 4.0 * TG_N * TG_N * TG_N;
       counters.flops_solve += f_solve * (double)nsolve;
+      counters.flops_coef += f_coef * (double)nsolve;
       counters.flops_setup += f_setup * (double)nsetup;
       counters.flops_sample += 340.0 * g.ps[p].n_samples;
       counters.mellinger_solves += nsolve - 1;
@@ -830,6 +840,7 @@ class Pipeline {
     // work lists are built by an order-preserving select (deterministic order; measured no faster than atomic append)
     auto run_lists = [&](const char* what) {
       for (int q = 0; q < 9; ++q) be_.select_flagged(need + (size_t)q * totS, lists + (size_t)q * totS, counts + q, (int)totS);
+      be_.for_each(1, AccumCountsFn{counts, b.stats + 5});
       trace_counts(what, counts, totS);
       extrema_lists(b.coef, b.times, b.maxima, totS, lists, counts, es);
     };
@@ -849,6 +860,7 @@ class Pipeline {
       launches(2);
     } else {
       extrema_segments(b.coef, b.times, b.maxima, totS, nullptr, nullptr, es);
+      counters.root_finds_executed += (long long)totS * 9;
     }
     for (int pass = 0; pass < 20; ++pass) {
       be_.dev_memset(b.stats + 1, 0, sizeof(int));
