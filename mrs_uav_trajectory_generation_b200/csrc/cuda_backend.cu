@@ -48,12 +48,12 @@ __global__ void __launch_bounds__(128) k_for_each_scratch(const F f, const size_
 // (or in a global slab when it does not fit).  Phases are separated by __syncwarp() (see tg_solve.cuh).
 constexpr int kSolveWarps = 4;
 template <class D>
-__global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const size_t n_inst, const int ws_doubles, double* __restrict__ gws) {
+__global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const size_t inst_begin, const size_t n_inst, const int ws_doubles, double* __restrict__ gws) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t gw = (size_t)blockIdx.x * kSolveWarps + warp, nw = (size_t)gridDim.x * kSolveWarps;
   double* ws = gws ? gws + gw * (size_t)ws_doubles : smem + (size_t)warp * ws_doubles;
-  for (size_t inst = gw; inst < n_inst; inst += nw) {
+  for (size_t inst = inst_begin + gw; inst < n_inst; inst += nw) {
     tg::SolveInst I;
     if (!desc.instance(inst, I)) continue;  // warp-uniform
     tg::solve_ws_bind(I, ws);
@@ -64,14 +64,15 @@ __global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const 
 
 // Four solve instances per warp, eight lanes each (tg_solve_octet.cuh).  A warp whose four instances are not all eligible
 // for the octet routine runs them one after the other through the general warp routine in the same shared memory.
-constexpr int kOctWarps = 2;
+// One warp per CTA: the shared-memory workspace (four octets) is what limits residency, and single-warp CTAs let the
+// number of resident warps follow the workspace size in the finest steps.
 template <class D>
-__global__ void __launch_bounds__(kOctWarps * 32) k_solve_oct(const D desc, const size_t n_inst, const int oct_ws_doubles, const int warp_ws_doubles) {
+__global__ void __launch_bounds__(32) k_solve_oct(const D desc, const size_t inst_begin, const size_t n_inst, const int oct_ws_doubles) {
   extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, oct = lane >> 3;
-  const size_t gw = (size_t)blockIdx.x * kOctWarps + warp, nw = (size_t)gridDim.x * kOctWarps;
-  double* wws = smem + (size_t)warp * warp_ws_doubles;
-  for (size_t base = gw * 4; base < n_inst; base += nw * 4) {
+  const int lane = threadIdx.x & 31, oct = lane >> 3;
+  const size_t gw = blockIdx.x, nw = gridDim.x;
+  double* wws = smem;
+  for (size_t base = inst_begin + gw * 4; base < n_inst; base += nw * 4) {
     tg::SolveInst I;
     const size_t inst = base + oct;
     bool ok = inst < n_inst && desc.instance(inst, I);
@@ -200,6 +201,7 @@ struct CudaBackend {
   int sm_count = 148;
   size_t smem_optin = 0, smem_per_sm = 0;
   bool force_general_solve = false;
+  int oct_reg_warps = 8;  // resident single-warp CTAs of k_solve_oct per SM as far as registers allow
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   static constexpr int kSideStreams = 9;
@@ -226,6 +228,12 @@ struct CudaBackend {
     smem_optin = prop.sharedMemPerBlockOptin;
     smem_per_sm = prop.sharedMemPerMultiprocessor;
     force_general_solve = std::getenv("TG_NO_OCTET") != nullptr;
+    {
+      int a = 0, b = 0;
+      TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_solve_oct<tg::SolveProblemDesc>, 32, 0));
+      TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_solve_oct<tg::SolveSweepDesc>, 32, 0));
+      oct_reg_warps = std::max(1, std::min(a, b));
+    }
     TG_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     TG_CUDA_CHECK(cudaEventCreate(&ev0));
     TG_CUDA_CHECK(cudaEventCreate(&ev1));
@@ -391,21 +399,37 @@ struct CudaBackend {
     return best;
   }
 
+  // resident warps per SM of the octet kernel for a given per-octet workspace (0: does not fit / not eligible)
+  int octet_warps_per_sm(int ws_doubles, int oct_ws_doubles) const {
+    if (oct_ws_doubles <= 0 || force_general_solve) return 0;
+    const size_t smem = (size_t)std::max(4 * oct_ws_doubles, ws_doubles) * sizeof(double);
+    if (smem > smem_optin) return 0;
+    const int by_smem = (int)(smem_per_sm / (smem + 1024));  // 1 KB per CTA is reserved by the system
+    return std::min(by_smem, oct_reg_warps);
+  }
+  // Occupancy class of a problem's workspace: the pipeline cuts a batch into runs of equal class and launches each
+  // run with its own shared-memory size (tg_pipeline.hpp solve_buckets).  >0: octet kernel, that many warps per SM;
+  // 0: warp-per-instance kernel in shared memory; -1: warp-per-instance kernel, workspace in the global slab.
+  int solve_class(int ws_doubles, int oct_ws_doubles) const {
+    const int w = octet_warps_per_sm(ws_doubles, oct_ws_doubles);
+    if (w >= 2) return w;
+    return ((size_t)ws_doubles * sizeof(double) * kSolveWarps <= smem_optin) ? 0 : -1;
+  }
+
+  // solves instances [inst_begin, inst_end)
   template <class D>
-  void solve(size_t n_inst, int ws_doubles, int oct_ws_doubles, const D& desc) {
-    if (n_inst == 0) return;
+  void solve(size_t inst_begin, size_t inst_end, int ws_doubles, int oct_ws_doubles, const D& desc) {
+    if (inst_end <= inst_begin) return;
+    const size_t n_inst = inst_end - inst_begin;
     // octet kernel: four instances per warp in shared memory (the common case); otherwise one warp per instance
-    const size_t warp_ws = (size_t)std::max(4 * oct_ws_doubles, ws_doubles);
-    const size_t oct_smem = warp_ws * sizeof(double) * kOctWarps;
-    if (oct_ws_doubles > 0 && !force_general_solve && oct_smem * 2 + 2048 <= smem_per_sm) {
+    const int oct_warps = octet_warps_per_sm(ws_doubles, oct_ws_doubles);
+    if (oct_warps >= 2) {
+      const size_t oct_smem = (size_t)std::max(4 * oct_ws_doubles, ws_doubles) * sizeof(double);
       prof_begin();
       TG_CUDA_CHECK(cudaFuncSetAttribute(k_solve_oct<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oct_smem));
-      int per_sm = 0;
-      TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_oct<D>, kOctWarps * 32, oct_smem));
-      if (per_sm < 1) per_sm = 1;
-      const size_t blocks_needed = (n_inst + 4 * kOctWarps - 1) / (4 * kOctWarps);
-      const size_t grid = std::min(blocks_needed, (size_t)sm_count * per_sm);
-      k_solve_oct<D><<<(unsigned)grid, kOctWarps * 32, oct_smem, stream>>>(desc, n_inst, oct_ws_doubles, (int)warp_ws);
+      const size_t blocks_needed = (n_inst + 3) / 4;
+      const size_t grid = std::min(blocks_needed, (size_t)sm_count * oct_warps);
+      k_solve_oct<D><<<(unsigned)grid, 32, oct_smem, stream>>>(desc, inst_begin, inst_end, oct_ws_doubles);
       TG_CUDA_CHECK(cudaGetLastError());
       prof_end(typeid(D).name(), n_inst);
       return;
@@ -420,7 +444,7 @@ struct CudaBackend {
       TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve<D>, kSolveWarps * 32, smem));
       if (per_sm < 1) per_sm = 1;
       const size_t grid = std::min(blocks_needed, (size_t)sm_count * per_sm);
-      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, smem, stream>>>(desc, n_inst, ws_doubles, nullptr);
+      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, smem, stream>>>(desc, inst_begin, inst_end, ws_doubles, nullptr);
     } else {
       // long paths: per-warp workspace in a global slab (L2 resident), persistent grid
       const size_t grid = std::min(blocks_needed, (size_t)sm_count * 8);
@@ -433,7 +457,7 @@ struct CudaBackend {
         TG_CUDA_CHECK(cudaMalloc(&solve_slab, need * sizeof(double)));
         solve_slab_doubles = need;
       }
-      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, 0, stream>>>(desc, n_inst, ws_doubles, solve_slab);
+      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, 0, stream>>>(desc, inst_begin, inst_end, ws_doubles, solve_slab);
     }
     TG_CUDA_CHECK(cudaGetLastError());
     prof_end(typeid(D).name(), n_inst);

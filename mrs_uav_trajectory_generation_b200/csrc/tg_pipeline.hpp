@@ -146,14 +146,18 @@ class Pipeline {
     be_.d2h(stats, b.stats, sizeof(stats));
     const int ws = stats[0], ows = stats[2];
     alloc_solution_buffers(b, (size_t)(P.run_time_alloc ? totV : B), stats);
+    std::vector<int> h_np(B), h_hbw(B);
+    be_.d2h(h_np.data(), b.np, sizeof(int) * B);
+    be_.d2h(h_hbw.data(), b.hbw, sizeof(int) * B);
+    const std::vector<SolveBucket> buckets = make_buckets(B, g.seg_off.data(), h_np.data(), h_hbw.data(), ws, ows);
     if (P.run_time_alloc) {
-      time_alloc_core(b, P, ws, ows);
+      time_alloc_core(b, P, ws, ows, &buckets);
     } else {
       b.recs = scratch_.template alloc<double>((size_t)totS * TG_REC_SIZE);
     }
     // final linear solve at the (scaled) times (nl_impl.h:405-408 / lin_impl.h:340-373)
     be_.for_each(totS, SetupBaseFn{b, b.times});
-    solve_with_outputs((size_t)B, ws, ows, SolveProblemDesc{b, 0, nullptr, nullptr}, b);
+    solve_with_outputs((size_t)B, ws, ows, SolveProblemDesc{b, 0, nullptr, nullptr}, b, &buckets, false);
     launches(2);
     // sampling (eth/trajectory_sampling.cpp:49-104)
     int* cap = scratch_.template alloc<int>((size_t)B + 1);
@@ -175,9 +179,6 @@ class Pipeline {
     launches(4);
     g.ps.resize(B);
     be_.d2h(g.ps.data(), g.d_ps, sizeof(ProbState) * B);
-    std::vector<int> h_np(B), h_hbw(B);
-    be_.d2h(h_np.data(), b.np, sizeof(int) * B);
-    be_.d2h(h_hbw.data(), b.hbw, sizeof(int) * B);
     if (P.run_time_alloc) {
       counters.mellinger_launches += P.max_evals;
       int executed = 0;
@@ -331,6 +332,19 @@ class Pipeline {
         }
       }
       if (pending.empty()) break;
+      // members of a next-round group in order of their new segment count (the order inside a group is free: results
+      // go back through `orig`), so that problems of one workspace class are consecutive -> SolveBucket runs
+      {
+        size_t a = 0;
+        while (a < pending.size()) {
+          size_t e = a;
+          while (e < pending.size() && pending[e].first == pending[a].first) ++e;
+          std::stable_sort(pending.begin() + a, pending.begin() + e, [](const std::pair<Group*, int>& x, const std::pair<Group*, int>& y) {
+            return x.first->ps[x.second].next_V < y.first->ps[y.second].next_V;
+          });
+          a = e;
+        }
+      }
       // build the next round's groups by midpoint insertion on the device
       std::vector<Group*> next;
       size_t i = 0;
@@ -495,9 +509,50 @@ class Pipeline {
     b.xs = scratch_.template alloc<double>(std::max<size_t>(n_inst_max, 1) * (size_t)b.xstride);
     b.part = scratch_.template alloc<double>(std::max<size_t>(n_inst_max, 1) * 4 * (size_t)b.smax);
   }
+  // A run of consecutive problems whose solve workspaces fall into the same occupancy class of the backend
+  // (BE::solve_class): each run is launched with its own shared-memory size, so that a few long paths in a group do
+  // not take the resident warps away from all the short ones (profiles/r01_solve_octet_s3.md).
+  struct SolveBucket {
+    int p0, p1;      // problems [p0, p1)
+    size_t v0, v1;   // their vertices = Mellinger instances
+    int ws, ows;     // workspace sizes (doubles): warp-per-instance routine, octet routine (0: not eligible)
+  };
+  std::vector<SolveBucket> make_buckets(int B, const int* seg_off, const int* np, const int* hbw, int ws_all, int ows_all) const {
+    std::vector<SolveBucket> out;
+    int cls_prev = 0;
+    for (int p = 0; p < B; ++p) {
+      const int S = seg_off[p + 1] - seg_off[p];
+      const int ws = solve_ws_doubles(S, np[p], hbw[p]);
+      const int ows = (hbw[p] == kOctHbw && np[p] > 0) ? octet_ws_doubles(S, np[p]) : 0;
+      const int cls = be_.solve_class(ws, ows);
+      if (out.empty() || cls != cls_prev) {
+        if (out.size() >= 32) {  // ragged input in no particular order: one launch for everything, as sized by the batch maxima
+          out.assign(1, SolveBucket{0, B, 0, (size_t)seg_off[B] + B, ws_all, ows_all});
+          return out;
+        }
+        out.push_back(SolveBucket{p, p, (size_t)seg_off[p] + p, 0, 0, 0});
+        cls_prev = cls;
+      }
+      SolveBucket& k = out.back();
+      k.p1 = p + 1;
+      k.v1 = (size_t)seg_off[p + 1] + p + 1;
+      k.ws = std::max(k.ws, ws);
+      k.ows = std::max(k.ows, ows);
+    }
+    return out;
+  }
   template <class D>
-  void solve_with_outputs(size_t n_inst, int ws, int ows, const D& desc, const BatchPtrs& b) {
-    be_.solve(n_inst, ws, ows, desc);
+  void solve_with_outputs(size_t n_inst, int ws, int ows, const D& desc, const BatchPtrs& b, const std::vector<SolveBucket>* buckets = nullptr,
+                          bool per_vertex = false) {
+    if (buckets && !buckets->empty()) {
+      for (const SolveBucket& k : *buckets) {
+        if (per_vertex) be_.solve(k.v0, k.v1, k.ws, k.ows, desc);
+        else be_.solve((size_t)k.p0, (size_t)k.p1, k.ws, k.ows, desc);
+      }
+      launches((int)buckets->size() - 1);
+    } else {
+      be_.solve(0, n_inst, ws, ows, desc);
+    }
     const int per = 4 * b.smax;
     be_.for_each(n_inst * (size_t)per, CoefCostFn<D>{desc, per, b.part});
     be_.for_each(n_inst, CostSumFn<D>{desc, per, b.part});
@@ -508,7 +563,7 @@ class Pipeline {
   // objective + forward-difference gradient 256-333 as S+1 batched solves per evaluation) then the time scaling of
   // scaleSegmentTimesWithViolation (335-427).  Needs b.times (initial), vmask/vval/vfree/np/hbw, coef, ps; leaves the
   // stretched times in b.times (the caller runs the final solve).
-  void time_alloc_core(BatchPtrs& b, const Params& P, int ws, int ows) {
+  void time_alloc_core(BatchPtrs& b, const Params& P, int ws, int ows, const std::vector<SolveBucket>* buckets = nullptr) {
     const int B = b.B, totS = b.totS, totV = b.totV;
     b.xeval = scratch_.template alloc<double>(totS);
     b.x = scratch_.template alloc<double>(totS);
@@ -523,7 +578,7 @@ class Pipeline {
     be_.for_each(B, LbfgsBeginFn{b}); launches(1);
     for (int e = 0; e < P.max_evals; ++e) {
       be_.for_each((size_t)totS * 3, SetupMellingerFn{b});
-      solve_with_outputs((size_t)totV, ws, ows, SolveProblemDesc{b, 1, nullptr, nullptr}, b);
+      solve_with_outputs((size_t)totV, ws, ows, SolveProblemDesc{b, 1, nullptr, nullptr}, b, buckets, true);
       be_.for_each(B, LbfgsAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel});
       launches(3);
     }

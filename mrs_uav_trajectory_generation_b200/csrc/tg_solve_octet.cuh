@@ -101,12 +101,29 @@ TG_HD void octet_swap_halves(OctLane& st) {
   }
 }
 
+// asynchronous copy of one 10-entry row of H (global memory) into shared memory: five 16-byte cp.async on the device,
+// a plain copy in the host emulation
+TG_HD void octet_stage_row(double* dst, const double* __restrict__ src) {
+#if defined(__CUDA_ARCH__)
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll
+  for (int q = 0; q < TG_N / 2; ++q) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + 16u * q), "l"(src + 2 * q) : "memory");
+#else
+  for (int q = 0; q < TG_N; ++q) dst[q] = src[q];
+#endif
+}
+TG_HD void octet_stage_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+}
+
 // Device: `insts` points at the calling lane's own instance (lanes of one octet hold identical copies); an octet
 // without work has np == 0 and S == 0.  Host emulation: insts[4], one per octet.  nmax = max np over the warp.
 TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
   OctLane st_all[TG_OCT_LANES];
   (void)lane;
-  // ---- phase 0: slot tables, zeroed rows ---------------------------------------------------------------------
+  // ---- phase 0: slot tables ----------------------------------------------------------------------------------------
   TG_PHASE(lane) {
     const SolveInst& I = TG_OCT_INST(insts, lane);
     const int sub = lane & 7, V = I.S + 1;
@@ -119,11 +136,23 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
         I.slot[it] = fixed ? (int16_t)-1 : (int16_t)j;
         if (!fixed) I.rowva[j] = (int16_t)it;
       }
-      Dbl2 z;
-      z.x = 0.0;
-      z.y = 0.0;
-      for (int e = sub; e < I.np * (kOctRow / 2); e += 8) *reinterpret_cast<Dbl2*>(I.rows + 2 * e) = z;
     }
+  }
+  // ---- phase 0b: every lane stages the two rows of H that each of its rows of R is built from -- row (5+a) of H_{v-1}
+  // into slots 0..9, row a of H_v into slots 10..19 of the row's own storage -- as asynchronous 16-byte copies, ALL of
+  // them in flight before the first is awaited (profiles/r01_solve_octet_s3.md: with the loads inside the assembly loop
+  // every row cost one full memory latency, 30 % of the kernel).  A lane reads back only what it staged itself.
+  TG_PHASE_NS(lane) {
+    const SolveInst& I = TG_OCT_INST(insts, lane);
+    const int sub = lane & 7, S = I.S;
+    for (int i = sub; i < I.np; i += 8) {
+      const int it = I.rowva[i];
+      const int v = it / TG_HALF, a = it - v * TG_HALF;
+      double* row = I.rows + i * kOctRow;
+      if (v > 0) octet_stage_row(row, solve_rec(I, v - 1) + TG_REC_H + (TG_HALF + a) * TG_N);  // 16-byte aligned: TG_REC_H and TG_N are even
+      if (v < S) octet_stage_row(row + TG_N, solve_rec(I, v) + TG_REC_H + a * TG_N);
+    }
+    octet_stage_wait();
   }
   // ---- phase 1: assemble Rpp and rhs = (-Rpf) d_f, one lane per row (identical sums to solve_warp phase 1) -------
   TG_PHASE(lane) {
@@ -131,28 +160,23 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
     const int sub = lane & 7, S = I.S;
     for (int i = sub; i < I.np; i += 8) {
       const int it = I.rowva[i];
-      const int v = it / TG_HALF, a = it - v * TG_HALF;
+      const int v = it / TG_HALF;
       double hp[TG_N], hc[TG_N];
       const bool has_p = v > 0, has_c = v < S;
-      if (has_p) {
-        const double* src = solve_rec(I, v - 1) + TG_REC_H + (TG_HALF + a) * TG_N;  // 16-byte aligned: TG_REC_H and TG_N are even
-#pragma unroll
-        for (int q = 0; q < TG_N; q += 2) {
-          const Dbl2 t = *reinterpret_cast<const Dbl2*>(src + q);
-          hp[q] = t.x;
-          hp[q + 1] = t.y;
-        }
-      }
-      if (has_c) {
-        const double* src = solve_rec(I, v) + TG_REC_H + a * TG_N;
-#pragma unroll
-        for (int q = 0; q < TG_N; q += 2) {
-          const Dbl2 t = *reinterpret_cast<const Dbl2*>(src + q);
-          hc[q] = t.x;
-          hc[q + 1] = t.y;
-        }
-      }
       double* row = I.rows + i * kOctRow;
+#pragma unroll
+      for (int q = 0; q < TG_N; q += 2) {
+        const Dbl2 t = *reinterpret_cast<const Dbl2*>(row + q), u = *reinterpret_cast<const Dbl2*>(row + TG_N + q);
+        hp[q] = t.x;
+        hp[q + 1] = t.y;
+        hc[q] = u.x;
+        hc[q + 1] = u.y;
+      }
+      Dbl2 z;
+      z.x = 0.0;
+      z.y = 0.0;
+#pragma unroll
+      for (int q = 0; q < kOctRow; q += 2) *reinterpret_cast<Dbl2*>(row + q) = z;
       double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
 #pragma unroll
       for (int g = 0; g < 3; ++g) {

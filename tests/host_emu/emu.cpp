@@ -75,9 +75,26 @@ struct EmuBackend {
   void for_each_scratch_on(int, size_t n, const F& f) { for_each_scratch(n, f); }
   // one "warp" per group of four instances (octet kernel) or per instance (general kernel): phases run lane by lane
   // (lanes own disjoint outputs within a phase).  Mirrors k_solve_oct / k_solve of cuda_backend.cu.
+  // same classes as CudaBackend::solve_class on a B200 (228 KB shared memory per SM, 227 KB per CTA, 9 warps by registers)
+  int solve_class(int ws_doubles, int oct_ws_doubles) const {
+    const size_t per_sm = 233472, optin = 232448;
+    if (oct_ws_doubles > 0 && !std::getenv("TG_EMU_NO_OCTET")) {
+      const size_t smem = (size_t)std::max(4 * oct_ws_doubles, ws_doubles) * sizeof(double);
+      const int w = smem > optin ? 0 : std::min((int)(per_sm / (smem + 1024)), 9);
+      if (w >= 2) return w;
+    }
+    return ((size_t)ws_doubles * sizeof(double) * 4 <= optin) ? 0 : -1;
+  }
   template <class D>
-  void solve(size_t n_inst, int ws_doubles, int oct_ws_doubles, const D& desc) {
-    if (oct_ws_doubles <= 0 || std::getenv("TG_EMU_NO_OCTET")) {
+  void solve(size_t inst_begin, size_t inst_end, int ws_doubles, int oct_ws_doubles, const D& desc0) {
+    if (inst_end <= inst_begin) return;
+    const size_t n_inst = inst_end - inst_begin;
+    struct Shifted {  // instance numbering relative to the range
+      const D& d;
+      size_t off;
+      bool instance(size_t i, tg::SolveInst& I) const { return d.instance(i + off, I); }
+    } desc{desc0, inst_begin};
+    if (solve_class(ws_doubles, oct_ws_doubles) < 2) {
       parallel(n_inst, [&](size_t inst) {
         tg::SolveInst I;
         if (!desc.instance(inst, I)) return;
