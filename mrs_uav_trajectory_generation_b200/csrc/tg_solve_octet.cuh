@@ -112,6 +112,15 @@ TG_HD void octet_stage_row(double* dst, const double* __restrict__ src) {
   for (int q = 0; q < TG_N; ++q) dst[q] = src[q];
 #endif
 }
+// the four fixed values of one (vertex, derivative) are pulled into L1 ahead of their use (staging them in shared
+// memory costs one resident warp per SM at S = 10, measured slower: profiles/r01_solve_octet_s3.md)
+TG_HD void octet_prefetch_fixed(const double* __restrict__ src) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L1 [%0];\n" ::"l"(src));
+#else
+  (void)src;
+#endif
+}
 TG_HD void octet_stage_wait() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.wait_all;\n" ::: "memory");
@@ -135,6 +144,7 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
         const int j = I.vfree[v] + free_rank(m, a);
         I.slot[it] = fixed ? (int16_t)-1 : (int16_t)j;
         if (!fixed) I.rowva[j] = (int16_t)it;
+        else octet_prefetch_fixed(I.vval + (size_t)it * TG_D);  // read in phase 1 by the rows that have this column
       }
     }
   }
