@@ -123,7 +123,10 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=RESULT_OUT or sys.stdout, flush=True)
+
+
+RESULT_OUT = None
 
 
 def main():
@@ -141,7 +144,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line, the JSON result: anything libraries print on fd 1 meanwhile (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, for one) is sent to stderr
+    sys.stdout.flush()
+    result_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
+        global RESULT_OUT
+        RESULT_OUT = result_out
         run_reference(args, rank, world)
         return
 
@@ -284,7 +294,7 @@ def main():
             line["kernel_profile"] = prof_table
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        print(json.dumps(line), file=result_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
