@@ -115,6 +115,16 @@ class Vertex {
 };
 
 // ---- Segment / Trajectory (eth/segment.h, eth/trajectory.h) -------------------------------------------------------------
+struct Extremum {  // eth/extremum.h:31-55: ordered by value
+  Extremum() : time(0.0), value(0.0), segment_idx(0) {}
+  Extremum(double _time, double _value, int _segment_idx) : time(_time), value(_value), segment_idx(_segment_idx) {}
+  bool operator<(const Extremum& rhs) const { return value < rhs.value; }
+  bool operator>(const Extremum& rhs) const { return value > rhs.value; }
+  double time;      // time inside the segment
+  double value;
+  int segment_idx;
+};
+
 class Segment {
  public:
   typedef std::vector<Segment> Vector;
@@ -391,6 +401,21 @@ class PolynomialOptimization {
     if (!trajectory) return;
     trajectory->clear();
     if (solved_) trajectory->unpack(coef_, segment_times_);
+  }
+  // lin_impl.h:477-508 (the reference's optional list of all candidates is not produced)
+  Extremum computeMaximumOfMagnitude(int derivative, std::vector<Extremum>* candidates = nullptr) const {
+    if (candidates) candidates->clear();
+    Extremum e;
+    if (!solved_ || segment_times_.empty()) return e;
+    b200::Context& c = b200::Context::instance();
+    const int off[2] = {0, (int)segment_times_.size()};
+    c.check(tg_max_magnitude_batch(c.get(), 1, off, coef_.data(), segment_times_.data(), derivative, &e.value, &e.time, &e.segment_idx),
+            "tg_max_magnitude_batch");
+    return e;
+  }
+  template <int Derivative>
+  Extremum computeMaximumOfMagnitude(std::vector<Extremum>* candidates = nullptr) const {
+    return computeMaximumOfMagnitude(Derivative, candidates);
   }
   size_t getDimension() const { return dimension_; }
   size_t getNumberSegments() const { return segment_times_.size(); }

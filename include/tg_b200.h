@@ -140,6 +140,12 @@ int tg_evaluate_batch(tg_ctx* ctx, int S, const double* coef, const double* time
 /* tg_extrema_batch = Trajectory::computeMaxDerivatives{Horizontal,Vertical,Heading}(.., seg) (eth/trajectory.cpp:422-565)
  *   for totS segments: maxima[totS][9] = hor v,a,j ; ver v,a,j ; heading v,a,j. */
 int tg_extrema_batch(tg_ctx* ctx, int totS, const double* coef, const double* times, double* maxima);
+/* tg_max_magnitude_batch = PolynomialOptimization<N>::computeMaximumOfMagnitude(derivative, nullptr) (lin_impl.h:477-508,
+ *   used by evaluateMaximumMagnitudeConstraint, nl_impl.h:724-738) for B trajectories given as seg_off[B+1], coef, times:
+ *   the Extremum {time (inside its segment), value, segment_idx} of the magnitude of the derivative over ALL four
+ *   dimensions (the constraint's `dimension` is ignored by the reference, lin_impl.h:407-409).  derivative in 1..4. */
+int tg_max_magnitude_batch(tg_ctx* ctx, int B, const int* seg_off, const double* coef, const double* times, int derivative, double* value,
+                           double* time, int* segment_idx);
 /* tg_scale_times_batch = Trajectory::scaleSegmentTimesToMeetConstraints (eth/trajectory.cpp:598-692), in place on
  *   coef/times; passes[B], within[B]. */
 int tg_scale_times_batch(tg_ctx* ctx, int B, const int* seg_off, double* coef, double* times, const double* limits9, int* passes,

@@ -119,6 +119,7 @@ class Library:
         L.tg_sample_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_double, _ip, _dp, _dp]
         L.tg_evaluate_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, _dp, _u8p]
         L.tg_extrema_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+        L.tg_max_magnitude_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_int, _dp, _dp, _ip]
         L.tg_scale_times_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp, _ip, _u8p]
         L.tg_sweep_costs.argtypes = [C.c_void_p, C.c_int, _u8p, _dp, C.c_int, C.c_longlong, _dp, C.c_int, _dp, _llp, _dp]
         L.tg_default_params.argtypes = [C.POINTER(Params)]
@@ -361,6 +362,16 @@ class Context:
         m = np.empty((len(times), 9))
         self._check(self.L.lib.tg_extrema_batch(self.h, len(times), _p(coef), _p(times), _p(m)))
         return m
+
+    def max_magnitude(self, seg_off, coef, times, derivative):
+        """computeMaximumOfMagnitude(derivative) per trajectory (lin_impl.h:477-508) -> time[B], value[B], segment_idx[B]."""
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.int32)
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        B = len(seg_off) - 1
+        v, t, i = np.empty(B), np.empty(B), np.empty(B, dtype=np.int32)
+        self._check(self.L.lib.tg_max_magnitude_batch(self.h, B, _p(seg_off, _ip), _p(coef), _p(times), int(derivative), _p(v), _p(t), _p(i, _ip)))
+        return t, v, i
 
     def scale_times(self, seg_off, coef, times, limits):
         seg_off = np.ascontiguousarray(seg_off, dtype=np.int32)

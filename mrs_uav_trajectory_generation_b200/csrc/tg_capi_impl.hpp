@@ -231,6 +231,20 @@ int tg_extrema_batch(tg_ctx* ctx, int totS, const double* coef, const double* ti
   });
 }
 
+int tg_max_magnitude_batch(tg_ctx* ctx, int B, const int* seg_off, const double* coef, const double* times, int derivative, double* value,
+                           double* time, int* segment_idx) {
+  return tg_guard(ctx, [&]() -> int {
+    if (B < 1 || !seg_off || !coef || !times || !value || !time || !segment_idx) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    for (int p = 0; p < B; ++p)
+      if (seg_off[p + 1] - seg_off[p] < 1) { ctx->err = "every trajectory needs at least one segment"; return TG_ERR_INVALID; }
+    ctx->be.timer_start();
+    const bool ok = ctx->pipe.max_magnitude_batch(B, seg_off, coef, times, derivative, value, time, segment_idx);
+    ctx->last_ms = ctx->be.timer_stop();
+    if (!ok) { ctx->err = "derivative must be 1..4"; return TG_ERR_INVALID; }
+    return TG_OK;
+  });
+}
+
 int tg_scale_times_batch(tg_ctx* ctx, int B, const int* seg_off, double* coef, double* times, const double* limits9, int* passes,
                          uint8_t* within) {
   return tg_guard(ctx, [&]() -> int {

@@ -824,6 +824,41 @@ struct ExtremaRawFn {  // one thread per work item (segment, or entry of a devic
     maxima[gs * 9 + Q] = segment_max_impl<Q>(coef + gs * TG_D * TG_N, times[gs], scratch, stride, nullptr);
   }
 };
+// computeMaximumOfMagnitude (lin_impl.h:477-508), step 1: one thread per segment -> the segment's first-largest candidate
+template <int DERIV>
+struct MaxMagnitudeSegFn {
+  const double* coef;
+  const double* times;
+  double* seg_value;
+  double* seg_time;
+  static constexpr int kScratch = 4 * (MaxAllDegree<DERIV>::value + 1);  // always the stage machine of tg_poly.cuh
+  TG_HD void operator()(size_t gs, double* scratch, int stride) const {
+    segment_max_all_dims<DERIV>(coef + gs * TG_D * TG_N, times[gs], scratch, stride, seg_value + gs, seg_time + gs);
+  }
+};
+// step 2: one thread per trajectory walks its segments in order; the running Extremum starts at (0, 0, 0) (lin_impl.h:483)
+struct MaxMagnitudeReduceFn {
+  const int* seg_off;
+  const double* seg_value;
+  const double* seg_time;
+  double* value;
+  double* time;
+  int* segment_idx;
+  TG_HD void operator()(size_t p) const {
+    double best = 0.0, best_t = 0.0;
+    int best_i = 0;
+    const int s0 = seg_off[p], s1 = seg_off[p + 1];
+    for (int s = s0; s < s1; ++s)
+      if (best < seg_value[s]) {
+        best = seg_value[s];
+        best_t = seg_time[s];
+        best_i = s - s0;
+      }
+    value[p] = best;
+    time[p] = best_t;
+    segment_idx[p] = best_i;
+  }
+};
 struct CompactSamplesFn {  // one thread per sample slot: slot arrays (with per-problem slack) -> contiguous outputs
   const int* smp_off;
   const int* smp_prob;

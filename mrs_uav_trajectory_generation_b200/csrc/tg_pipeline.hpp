@@ -778,6 +778,39 @@ class Pipeline {
     be_.d2h(maxima, d_m, sizeof(double) * (size_t)totS * 9);
   }
 
+  // PolynomialOptimization<10>::computeMaximumOfMagnitude(derivative) for B trajectories (lin_impl.h:477-508)
+  bool max_magnitude_batch(int B, const int* seg_off, const double* coef, const double* times, int derivative, double* value, double* time,
+                           int* segment_idx) {
+    if (derivative < 1 || derivative > 4) return false;
+    scratch_.reset();
+    const int totS = seg_off[B];
+    int* d_off = scratch_.template alloc<int>((size_t)B + 1);
+    double* d_coef = scratch_.template alloc<double>((size_t)totS * TG_D * TG_N);
+    double* d_T = scratch_.template alloc<double>(totS);
+    double* d_sv = scratch_.template alloc<double>(totS);
+    double* d_st = scratch_.template alloc<double>(totS);
+    double* d_v = scratch_.template alloc<double>(B);
+    double* d_t = scratch_.template alloc<double>(B);
+    int* d_i = scratch_.template alloc<int>(B);
+    be_.h2d(d_off, seg_off, sizeof(int) * ((size_t)B + 1));
+    be_.h2d(d_coef, coef, sizeof(double) * (size_t)totS * TG_D * TG_N);
+    be_.h2d(d_T, times, sizeof(double) * totS);
+    switch (derivative) {
+      case 1: be_.for_each_scratch((size_t)totS, MaxMagnitudeSegFn<1>{d_coef, d_T, d_sv, d_st}); break;
+      case 2: be_.for_each_scratch((size_t)totS, MaxMagnitudeSegFn<2>{d_coef, d_T, d_sv, d_st}); break;
+      case 3: be_.for_each_scratch((size_t)totS, MaxMagnitudeSegFn<3>{d_coef, d_T, d_sv, d_st}); break;
+      default: be_.for_each_scratch((size_t)totS, MaxMagnitudeSegFn<4>{d_coef, d_T, d_sv, d_st}); break;
+    }
+    be_.for_each((size_t)B, MaxMagnitudeReduceFn{d_off, d_sv, d_st, d_v, d_t, d_i});
+    launches(2);
+    counters.root_finds += totS;
+    counters.root_finds_executed += totS;
+    be_.d2h(value, d_v, sizeof(double) * B);
+    be_.d2h(time, d_t, sizeof(double) * B);
+    be_.d2h(segment_idx, d_i, sizeof(int) * B);
+    return true;
+  }
+
   // Trajectory::scaleSegmentTimesToMeetConstraints in place
   void scale_times_batch(int B, const int* seg_off, double* coef, double* times, const double* L9, int* passes, uint8_t* within) {
     scratch_.reset();

@@ -750,6 +750,72 @@ TG_HD double segment_max_single(const double* __restrict__ coef, double T, doubl
   return sink.best;
 }
 
+// computeMaximumOfMagnitude (lin_impl.h:477-508) on one segment: magnitude of the DERIV-th derivative over ALL dimensions
+// (lin_impl.h:407-409) at t = 0, t = T and the real zeros of sum_d conv(p_d^(k), p_d^(k+1)) inside [0, T], in that order;
+// a candidate replaces the running one only when strictly larger, so the first of equal maxima wins (operator< of
+// Extremum compares values).  Leaves value = lowest() when the segment has no candidate (T < 0).
+template <int DERIV>
+struct MaxAllSink {
+  const double* coef;
+  double T;
+  double best, best_t;
+  TG_HD void consider(double t) {
+    double mag = 0.0;
+#pragma unroll
+    for (int dim = 0; dim < TG_D; ++dim) {
+      const double v = poly_eval_s<DERIV>(coef + dim * TG_N, t);
+      mag = mag + v * v;
+    }
+    mag = dsqrt(mag);
+    if (best < mag) {
+      best = mag;
+      best_t = t;
+    }
+  }
+  TG_HD void operator()(double re, double im) {
+    if (dabs(im) > TG_DBL_EPSILON) return;
+    if (re < 0.0 || re > T) return;
+    consider(re);
+  }
+};
+template <int DERIV>
+struct MaxAllDegree {
+  static constexpr int value = 2 * (TG_N - DERIV) - 3;
+};
+template <int DERIV>
+TG_HD void segment_max_all_dims(const double* __restrict__ coef, double T, double* scratch, int stride, double* value, double* time) {
+  constexpr int n_d = TG_N - DERIV, n_dd = n_d - 1, len = n_d + n_dd - 1, M = len - 1;
+  double acc[M + 1];
+#pragma unroll
+  for (int i = 0; i < len; ++i) acc[i] = 0.0;
+#pragma unroll 1
+  for (int dim = 0; dim < TG_D; ++dim) {
+    const double* c = coef + dim * TG_N;
+    double dc[n_d], ddc[n_dd];
+#pragma unroll
+    for (int jx = 0; jx < n_d; ++jx) dc[jx] = c[jx + DERIV] * bcoef(DERIV, jx + DERIV);
+#pragma unroll
+    for (int jx = 0; jx < n_dd; ++jx) ddc[jx] = c[jx + DERIV + 1] * bcoef(DERIV + 1, jx + DERIV + 1);
+#pragma unroll
+    for (int i = 0; i < len; ++i) {
+      double cv = 0.0;
+      const int data_idx = i - n_dd + 1;
+      const int lower = (0 > -data_idx) ? 0 : -data_idx, upper = (n_dd < n_d - data_idx) ? n_dd : n_d - data_idx;
+#pragma unroll
+      for (int kidx = lower; kidx < upper; ++kidx) cv = cv + ddc[n_dd - 1 - kidx] * dc[data_idx + kidx];
+      acc[i] = acc[i] + cv;
+    }
+  }
+  MaxAllSink<DERIV> sink{coef, T, TG_DBL_LOWEST, 0.0};
+  if (!(0.0 > T)) {
+    sink.consider(0.0);
+    sink.consider(T);
+    find_roots_jt<M>(acc, scratch, stride, sink, nullptr);
+  }
+  *value = sink.best;
+  *time = sink.best_t;
+}
+
 // Quantity Q in 0..8 : (group, derivative) = (horizontal|vertical|heading, velocity|acceleration|jerk) in the order
 // the reference asks for them (eth/trajectory.cpp:616-622).  coef: [4][10] of one segment.
 template <int Q>

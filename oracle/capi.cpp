@@ -188,6 +188,12 @@ void orc_segment_maxima(int S, const double* coeffs, const double* times, double
   }
 }
 
+// computeMaximumOfMagnitude(derivative) of one trajectory: Extremum {time, value, segment_idx}
+void orc_max_magnitude(int S, const double* coeffs, const double* times, int derivative, double* time, double* value, int* segment_idx) {
+  std::vector<Segment> seg = make_segments(S, coeffs, times);
+  max_of_magnitude(seg, derivative, time, value, segment_idx);
+}
+
 // in-place time scaling; returns passes
 int orc_scale_times(int S, double* coeffs, double* times, const double* limits, int* within) {
   std::vector<Segment> seg = make_segments(S, coeffs, times);

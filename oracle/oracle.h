@@ -112,6 +112,7 @@ int find_roots_jt(const double* coeffs_increasing, int n, double* re, double* im
 
 // extremum of |p^(deriv)| over dims on one segment (eth/segment.cpp:113-212, trajectory.cpp:211-243)
 double segment_max_magnitude(const Segment& s, int deriv, const int* dims, int ndims, long* root_calls);
+void max_of_magnitude(const std::vector<Segment>& seg, int deriv, double* time, double* value, int* segment_idx);  // lin_impl.h:477-508
 
 // ---- trajectory level ---------------------------------------------------------------------------------
 struct Limits {  // order matches scaleSegmentTimesToMeetConstraints' argument meaning

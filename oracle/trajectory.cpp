@@ -102,6 +102,54 @@ double segment_max_magnitude(const Segment& s, int deriv, const int* dims, int n
   return best;
 }
 
+// PolynomialOptimization<N>::computeMaximumOfMagnitude(derivative, nullptr) (lin_impl.h:477-508): the candidate list of a
+// segment is computeSegmentMaximumMagnitudeCandidates' output -- t_start, t_end, then the real zeros inside the segment
+// (the 0.0 pushed at lin_impl.h:487 is cleared again by segment.cpp:117) -- over ALL dimensions (lin_impl.h:407-409);
+// value = Segment::evaluate(t, k).norm(), summed here in dimension order (Eigen's reduction order for a 4-vector is
+// third-party arithmetic: parity unpinned, oracle.h); the running Extremum starts at (0, 0, 0) and is replaced on a
+// strictly larger value, so the first of equal maxima wins.  The closing candidate (end of the last segment,
+// lin_impl.h:501-505) repeats one already seen and cannot win.
+void max_of_magnitude(const std::vector<Segment>& seg, int deriv, double* time, double* value, int* segment_idx) {
+  double best = 0.0, best_t = 0.0;
+  int best_i = 0;
+  const int dims[4] = {0, 1, 2, 3};
+  for (size_t si = 0; si < seg.size(); ++si) {
+    const Segment& s = seg[si];
+    double cand[2 * kN + 2];
+    const int n = candidate_times(s, deriv, dims, kD, cand, nullptr);
+    for (int i = 0; i < n; ++i) {
+      double mag = 0.0;
+      for (int q = 0; q < kD; ++q) {
+        const double v = poly_eval(s.c[q], cand[i], deriv);
+        mag += v * v;
+      }
+      mag = std::sqrt(mag);
+      if (best < mag) {
+        best = mag;
+        best_t = cand[i];
+        best_i = (int)si;
+      }
+    }
+  }
+  if (!seg.empty()) {
+    const Segment& s = seg.back();
+    double mag = 0.0;
+    for (int q = 0; q < kD; ++q) {
+      const double v = poly_eval(s.c[q], s.T, deriv);
+      mag += v * v;
+    }
+    mag = std::sqrt(mag);
+    if (best < mag) {
+      best = mag;
+      best_t = s.T;
+      best_i = (int)seg.size() - 1;
+    }
+  }
+  *time = best_t;
+  *value = best;
+  *segment_idx = best_i;
+}
+
 static void nine_maxima(const Segment& s, double* m, long* rc) {
   const int hor[2] = {0, 1}, ver[1] = {2}, hdg[1] = {3};
   // order of calls: horizontal v,a,j ; vertical v,a,j ; heading v,a,j (trajectory.cpp:616-622)

@@ -100,6 +100,12 @@ int main(int argc, char** argv) {
   tn.computeMaxDerivativesHorizontal(&vmax, &amax, &jmax);
   const double mh[3] = {vmax, amax, jmax};
   dump(f, "nl_max_h", mh, 3);
+  // computeMaximumOfMagnitude (lin_impl.h:477-508) through the optimiser's linear part, as evaluateMaximumMagnitudeConstraint calls it
+  for (int k = 1; k <= 3; ++k) {
+    const Extremum e = opt.getPolynomialOptimizationRef().computeMaximumOfMagnitude(k, nullptr);
+    const double me[3] = {e.time, e.value, (double)e.segment_idx};
+    dump(f, "nl_maxmag", me, 3);
+  }
 
   // --- batch entry: two paths through optimize() (findTrajectory + validation + subdivision)
   TrajectoryGeneratorBatch gen;

@@ -213,6 +213,15 @@ def segment_maxima(coeffs, times):
     return out
 
 
+def max_magnitude(coeffs, times, derivative):
+    """computeMaximumOfMagnitude (lin_impl.h:477-508) of one trajectory -> (time, value, segment_idx)."""
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    t, v, i = C.c_double(), C.c_double(), C.c_int()
+    lib().orc_max_magnitude(len(times), _ptr(coeffs), _ptr(times), int(derivative), C.byref(t), C.byref(v), C.byref(i))
+    return t.value, v.value, i.value
+
+
 def scale_times(coeffs, times, limits=DEFAULT_LIMITS):
     coeffs = np.array(coeffs, dtype=np.float64, order="C")
     times = np.array(times, dtype=np.float64)

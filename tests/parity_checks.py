@@ -187,6 +187,43 @@ def check_extrema_and_scaling(ctx, seed=3, B=6):
     return exact
 
 
+def check_max_magnitude(ctx, seed=11, B=9):
+    """computeMaximumOfMagnitude (lin_impl.h:477-508): Extremum {time, value, segment} per trajectory, derivatives 1..4, against the
+    oracle; plus the identity the reference's own tests use (test_utils.h:40-50): analytic maximum >= densely sampled maximum."""
+    rng = np.random.default_rng(seed)
+    coefs, times, seg_off = [], [], [0]
+    for p in range(B):
+        V = int(rng.integers(2, 14))
+        m, v, t = random_linear_problem(rng, V, kind=p % 3)
+        c, _, _, _ = O.solve_linear(m, v, t, 2)
+        coefs.append(c)
+        times.append(t)
+        seg_off.append(seg_off[-1] + V - 1)
+    allc, allt = np.concatenate(coefs), np.concatenate(times)
+    exact = True
+    for k in (1, 2, 3, 4):
+        tt, vv, ii = ctx.max_magnitude(np.array(seg_off, np.int32), allc, allt, k)
+        for p in range(B):
+            rt, rv, ri = O.max_magnitude(coefs[p], times[p], k)
+            assert ii[p] == ri and abs(vv[p] - rv) <= 1e-9 * max(1.0, abs(rv)) and abs(tt[p] - rt) <= 1e-9 * max(1.0, abs(rt)), (k, p)
+            exact = exact and vv[p] == rv and tt[p] == rt
+            # sampled maximum over the whole trajectory never exceeds the analytic one (up to rounding)
+            smax = 0.0
+            for s in range(len(times[p])):
+                ts = np.linspace(0.0, times[p][s], 41)
+                val = np.zeros((41, 4))
+                for d in range(4):
+                    cd = coefs[p][s, d]
+                    for j in range(9, k - 1, -1):
+                        f = 1.0
+                        for q in range(k):
+                            f *= (j - q)
+                        val[:, d] = val[:, d] * ts + f * cd[j]
+                smax = max(smax, float(np.sqrt((val ** 2).sum(axis=1)).max()))
+            assert smax <= vv[p] * (1 + 1e-9) + 1e-12, (k, p, smax, vv[p])
+    return exact
+
+
 def compare_optimize(ctx, wp_off, wp, stop_at=None, init=None, params_kw=None, cap_wp=1400, cap_samples=6000):
     """Runs the full optimize() pipeline on both sides; asserts parity; returns (results, bit_exact, worst_coef_err)."""
     params_kw = params_kw or {}

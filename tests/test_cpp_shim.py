@@ -59,6 +59,9 @@ def _check(res):
     assert np.array_equal(got[:, 6].astype(np.int64), t_ns)
     mx = O.segment_maxima(ref["coef"], ref["times"])
     assert np.array_equal(res["nl_max_h"][0], mx[:, 0:3].max(axis=0))
+    for k in (1, 2, 3):
+        t, v, i = O.max_magnitude(ref["coef"], ref["times"], k)
+        assert np.array_equal(res["nl_maxmag"][k - 1], [t, v, float(i)])
     # TrajectoryGeneratorBatch: optimize() over two paths
     for p, path in enumerate([W.F1B_WAYPOINTS, W.F1A_WAYPOINTS]):
         o = O.optimize_path(path)

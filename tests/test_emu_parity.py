@@ -33,6 +33,10 @@ def test_evaluate(emu_ctx, oracle):
     assert PC.check_evaluate(emu_ctx)
 
 
+def test_max_magnitude(emu_ctx, oracle):
+    assert PC.check_max_magnitude(emu_ctx)
+
+
 def test_extrema_and_scaling(emu_ctx, oracle):
     assert PC.check_extrema_and_scaling(emu_ctx)
 

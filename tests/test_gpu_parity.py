@@ -40,6 +40,10 @@ def test_evaluate(gpu_ctx, oracle):
     assert PC.check_evaluate(gpu_ctx)
 
 
+def test_max_magnitude(gpu_ctx, oracle):
+    assert PC.check_max_magnitude(gpu_ctx)
+
+
 def test_extrema_and_scaling(gpu_ctx, oracle):
     assert PC.check_extrema_and_scaling(gpu_ctx, B=12)
 
