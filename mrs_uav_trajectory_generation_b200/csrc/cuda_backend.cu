@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(128) k_for_each_scratch(const F f, const size_
 // (or in a global slab when it does not fit).  Phases are separated by __syncwarp() (see tg_solve.cuh).
 constexpr int kSolveWarps = 4;
 template <class D>
-__global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const size_t inst_begin, const size_t n_inst, const int ws_doubles, double* __restrict__ gws) {
+__global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const size_t inst_begin, const size_t n_inst, const int ws_doubles, double* __restrict__ gws,
+                                                            const int skip_oct_ws) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t gw = (size_t)blockIdx.x * kSolveWarps + warp, nw = (size_t)gridDim.x * kSolveWarps;
@@ -56,42 +57,35 @@ __global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const 
   for (size_t inst = inst_begin + gw; inst < n_inst; inst += nw) {
     tg::SolveInst I;
     if (!desc.instance(inst, I)) continue;  // warp-uniform
+    // skip_oct_ws > 0: the octet kernel has taken every instance it can take (same test as in k_solve_oct)
+    if (skip_oct_ws > 0 && tg::octet_eligible(I) && tg::octet_ws_doubles(I.S, I.np) <= skip_oct_ws) continue;
     tg::solve_ws_bind(I, ws);
     tg::solve_warp(I, lane);
   }
 }
 
-
-// Four solve instances per warp, eight lanes each (tg_solve_octet.cuh).  A warp whose four instances are not all eligible
-// for the octet routine runs them one after the other through the general warp routine in the same shared memory.
-// One warp per CTA: the shared-memory workspace (four octets) is what limits residency, and single-warp CTAs let the
-// number of resident warps follow the workspace size in the finest steps.
+// Four solve instances per warp, eight lanes each (tg_solve_octet.cuh); instances the octet routine cannot take are left
+// to k_solve.  One warp per CTA.  uslab: per-CTA slab of 4 * u_cap rows of kOctRow doubles (the U rows between the
+// elimination and the back substitution; L2 resident).
 template <class D>
-__global__ void __launch_bounds__(32) k_solve_oct(const D desc, const size_t inst_begin, const size_t n_inst, const int oct_ws_doubles) {
+__global__ void __launch_bounds__(32) k_solve_oct(const D desc, const size_t inst_begin, const size_t n_inst, const int oct_ws_doubles, const int u_cap,
+                                                  double* __restrict__ uslab) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, oct = lane >> 3;
   const size_t gw = blockIdx.x, nw = gridDim.x;
-  double* wws = smem;
+  double* urows = uslab + ((size_t)blockIdx.x * 4 + oct) * (size_t)u_cap * tg::kOctRow;
   for (size_t base = inst_begin + gw * 4; base < n_inst; base += nw * 4) {
     tg::SolveInst I;
     const size_t inst = base + oct;
     bool ok = inst < n_inst && desc.instance(inst, I);
+    if (ok && !(tg::octet_eligible(I) && tg::octet_ws_doubles(I.S, I.np) <= oct_ws_doubles && I.np <= u_cap)) ok = false;
     if (!ok) {
       I.S = 0; I.np = 0; I.hbw = tg::kOctHbw; I.dp_out = nullptr; I.coef_out = nullptr; I.cost_out = nullptr;
     }
-    const bool fits = !ok || (tg::octet_eligible(I) && tg::octet_ws_doubles(I.S, I.np) <= oct_ws_doubles);
-    if (__all_sync(0xffffffffu, fits)) {
-      tg::octet_ws_bind(I, wws + (size_t)oct * oct_ws_doubles);
-      const int nmax = __reduce_max_sync(0xffffffffu, I.np);
+    const int nmax = __reduce_max_sync(0xffffffffu, I.np);
+    if (nmax > 0) {
+      tg::octet_ws_bind(I, smem + (size_t)oct * oct_ws_doubles, urows);
       tg::solve_octets(&I, lane, nmax);
-    } else {
-      for (int o = 0; o < 4; ++o) {
-        tg::SolveInst J;
-        if (base + o >= n_inst || !desc.instance(base + o, J)) continue;  // warp-uniform
-        tg::solve_ws_bind(J, wws);
-        tg::solve_warp(J, lane);
-        __syncwarp();
-      }
     }
     __syncwarp();
   }
@@ -209,8 +203,10 @@ struct CudaBackend {
   cudaEvent_t ev_fork = nullptr, ev_side[kSideStreams] = {};
   void* scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
-  double* solve_slab = nullptr;
+  double* solve_slab = nullptr;  // U rows of the octet kernel
   size_t solve_slab_doubles = 0;
+  double* gen_slab = nullptr;    // workspaces of the warp-per-instance kernel for very long paths
+  size_t gen_slab_doubles = 0;
   // optional per-kernel timing (bench.py roofline leg): events around every launch, accumulated per functor type
   bool profiling = false;
   cudaEvent_t pev0 = nullptr, pev1 = nullptr;
@@ -249,6 +245,7 @@ struct CudaBackend {
     cudaSetDevice(device);
     if (scan_tmp) cudaFree(scan_tmp);
     if (solve_slab) cudaFree(solve_slab);
+    if (gen_slab) cudaFree(gen_slab);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (pev0) cudaEventDestroy(pev0);
@@ -399,41 +396,61 @@ struct CudaBackend {
     return best;
   }
 
-  // resident warps per SM of the octet kernel for a given per-octet workspace (0: does not fit / not eligible)
-  int octet_warps_per_sm(int ws_doubles, int oct_ws_doubles) const {
+  // resident warps per SM of the octet kernel for a given per-octet workspace (0: not eligible)
+  int octet_warps_per_sm(int oct_ws_doubles) const {
     if (oct_ws_doubles <= 0 || force_general_solve) return 0;
-    const size_t smem = (size_t)std::max(4 * oct_ws_doubles, ws_doubles) * sizeof(double);
+    const size_t smem = (size_t)4 * oct_ws_doubles * sizeof(double);
     if (smem > smem_optin) return 0;
     const int by_smem = (int)(smem_per_sm / (smem + 1024));  // 1 KB per CTA is reserved by the system
     return std::min(by_smem, oct_reg_warps);
   }
-  // Occupancy class of a problem's workspace: the pipeline cuts a batch into runs of equal class and launches each
-  // run with its own shared-memory size (tg_pipeline.hpp solve_buckets).  >0: octet kernel, that many warps per SM;
-  // 0: warp-per-instance kernel in shared memory; -1: warp-per-instance kernel, workspace in the global slab.
+  // Class of a problem's solve workspace: the pipeline cuts a batch into runs of equal class (tg_pipeline.hpp
+  // make_buckets) so that each run is launched with its own shared-memory size and every instance of a run goes to the
+  // same kernel.  >0: octet kernel, that many warps per SM; 0: warp-per-instance kernel in shared memory; -1: warp-per-
+  // instance kernel with its workspace in the global slab.
   int solve_class(int ws_doubles, int oct_ws_doubles) const {
-    const int w = octet_warps_per_sm(ws_doubles, oct_ws_doubles);
-    if (w >= 2) return w;
+    const int w = octet_warps_per_sm(oct_ws_doubles);
+    if (w >= 1) return w;
     return ((size_t)ws_doubles * sizeof(double) * kSolveWarps <= smem_optin) ? 0 : -1;
   }
 
-  // solves instances [inst_begin, inst_end)
+  double* slab(size_t doubles) {
+    if (doubles > solve_slab_doubles) {
+      if (solve_slab) {
+        TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        TG_CUDA_CHECK(cudaFree(solve_slab));
+      }
+      TG_CUDA_CHECK(cudaMalloc(&solve_slab, doubles * sizeof(double)));
+      solve_slab_doubles = doubles;
+    }
+    return solve_slab;
+  }
+
+  // Solves instances [inst_begin, inst_end).  oct_ws_doubles > 0: instances the octet routine can take (half bandwidth
+  // 7, workspace <= oct_ws_doubles, at most np_cap unknowns) go to k_solve_oct; `mixed` says that others may be present,
+  // which then go to the warp-per-instance kernel (ws_doubles of workspace each).
   template <class D>
-  void solve(size_t inst_begin, size_t inst_end, int ws_doubles, int oct_ws_doubles, const D& desc) {
+  void solve(size_t inst_begin, size_t inst_end, int ws_doubles, int oct_ws_doubles, int np_cap, bool mixed, const D& desc) {
     if (inst_end <= inst_begin) return;
     const size_t n_inst = inst_end - inst_begin;
-    // octet kernel: four instances per warp in shared memory (the common case); otherwise one warp per instance
-    const int oct_warps = octet_warps_per_sm(ws_doubles, oct_ws_doubles);
-    if (oct_warps >= 2) {
-      const size_t oct_smem = (size_t)std::max(4 * oct_ws_doubles, ws_doubles) * sizeof(double);
+    const int oct_warps = octet_warps_per_sm(oct_ws_doubles);
+    if (oct_warps >= 1) {
+      const size_t oct_smem = (size_t)4 * oct_ws_doubles * sizeof(double);
       prof_begin();
       TG_CUDA_CHECK(cudaFuncSetAttribute(k_solve_oct<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oct_smem));
       const size_t blocks_needed = (n_inst + 3) / 4;
-      const size_t grid = std::min(blocks_needed, (size_t)sm_count * oct_warps);
-      k_solve_oct<D><<<(unsigned)grid, 32, oct_smem, stream>>>(desc, inst_begin, inst_end, oct_ws_doubles);
+      // the U slab of all resident warps should stay in L2 (126 MB): fewer warps for very long paths
+      const size_t per_cta = (size_t)4 * std::max(np_cap, 1) * tg::kOctRow;
+      size_t grid = std::min(blocks_needed, (size_t)sm_count * oct_warps);
+      const size_t l2_ctas = std::max<size_t>((size_t)sm_count, ((size_t)96 << 20) / (per_cta * sizeof(double)));
+      grid = std::min(grid, l2_ctas);
+      double* us = slab(grid * per_cta);
+      k_solve_oct<D><<<(unsigned)grid, 32, oct_smem, stream>>>(desc, inst_begin, inst_end, oct_ws_doubles, std::max(np_cap, 1), us);
       TG_CUDA_CHECK(cudaGetLastError());
       prof_end(typeid(D).name(), n_inst);
-      return;
+      if (!mixed) return;
     }
+    const int skip = oct_warps >= 1 ? oct_ws_doubles : 0;
     const size_t ws_bytes = (size_t)ws_doubles * sizeof(double);
     const size_t smem = ws_bytes * kSolveWarps;
     const size_t blocks_needed = (n_inst + kSolveWarps - 1) / kSolveWarps;
@@ -444,20 +461,20 @@ struct CudaBackend {
       TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve<D>, kSolveWarps * 32, smem));
       if (per_sm < 1) per_sm = 1;
       const size_t grid = std::min(blocks_needed, (size_t)sm_count * per_sm);
-      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, smem, stream>>>(desc, inst_begin, inst_end, ws_doubles, nullptr);
+      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, smem, stream>>>(desc, inst_begin, inst_end, ws_doubles, nullptr, skip);
     } else {
       // long paths: per-warp workspace in a global slab (L2 resident), persistent grid
       const size_t grid = std::min(blocks_needed, (size_t)sm_count * 8);
       const size_t need = grid * kSolveWarps * (size_t)ws_doubles;
-      if (need > solve_slab_doubles) {
-        if (solve_slab) {
+      if (need > gen_slab_doubles) {
+        if (gen_slab) {
           TG_CUDA_CHECK(cudaStreamSynchronize(stream));
-          TG_CUDA_CHECK(cudaFree(solve_slab));
+          TG_CUDA_CHECK(cudaFree(gen_slab));
         }
-        TG_CUDA_CHECK(cudaMalloc(&solve_slab, need * sizeof(double)));
-        solve_slab_doubles = need;
+        TG_CUDA_CHECK(cudaMalloc(&gen_slab, need * sizeof(double)));
+        gen_slab_doubles = need;
       }
-      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, 0, stream>>>(desc, inst_begin, inst_end, ws_doubles, solve_slab);
+      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, 0, stream>>>(desc, inst_begin, inst_end, ws_doubles, gen_slab, skip);
     }
     TG_CUDA_CHECK(cudaGetLastError());
     prof_end(typeid(D).name(), n_inst);

@@ -108,7 +108,8 @@ struct PrepareFn {
     TG_ATOMIC_MAX(&b.stats[0], solve_ws_doubles(S, np, hbw));
     TG_ATOMIC_MAX(&b.stats[3], np);
     TG_ATOMIC_MAX(&b.stats[4], S);
-    if (hbw == kOctHbw && np > 0) TG_ATOMIC_MAX(&b.stats[2], octet_ws_doubles(S, np));
+    if (hbw == kOctHbw && np >= kOctMinNp) TG_ATOMIC_MAX(&b.stats[2], octet_ws_doubles(S, np));
+    else TG_ATOMIC_ADD(&b.stats[6], 1);  // problems the octet routine cannot take
     ProbState& ps = b.ps[p];
     ps.status = kFindOk;
     ps.nlopt_code = 1;

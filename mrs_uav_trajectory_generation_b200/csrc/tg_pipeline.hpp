@@ -149,15 +149,15 @@ class Pipeline {
     std::vector<int> h_np(B), h_hbw(B);
     be_.d2h(h_np.data(), b.np, sizeof(int) * B);
     be_.d2h(h_hbw.data(), b.hbw, sizeof(int) * B);
-    const std::vector<SolveBucket> buckets = make_buckets(B, g.seg_off.data(), h_np.data(), h_hbw.data(), ws, ows);
+    const std::vector<SolveBucket> buckets = make_buckets(B, g.seg_off.data(), h_np.data(), h_hbw.data(), ws, ows, stats[3]);
     if (P.run_time_alloc) {
-      time_alloc_core(b, P, ws, ows, &buckets);
+      time_alloc_core(b, P, stats, &buckets);
     } else {
       b.recs = scratch_.template alloc<double>((size_t)totS * TG_REC_SIZE);
     }
     // final linear solve at the (scaled) times (nl_impl.h:405-408 / lin_impl.h:340-373)
     be_.for_each(totS, SetupBaseFn{b, b.times});
-    solve_with_outputs((size_t)B, ws, ows, SolveProblemDesc{b, 0, nullptr, nullptr}, b, &buckets, false);
+    solve_with_outputs((size_t)B, stats, SolveProblemDesc{b, 0, nullptr, nullptr}, b, &buckets, false);
     launches(2);
     // sampling (eth/trajectory_sampling.cpp:49-104)
     int* cap = scratch_.template alloc<int>((size_t)B + 1);
@@ -491,7 +491,7 @@ class Pipeline {
     be_.d2h(stats, b.stats, sizeof(stats));
     alloc_solution_buffers(b, (size_t)B, stats);
     be_.for_each(b.totS, SetupBaseFn{b, b.times});
-    solve_with_outputs((size_t)B, stats[0], stats[2], SolveProblemDesc{b, 0, nullptr, nullptr}, b);
+    solve_with_outputs((size_t)B, stats, SolveProblemDesc{b, 0, nullptr, nullptr}, b);
     be_.for_each(B, CostOutFn{b.ps, d_cost});
     launches(4);
     counters.solves += B;
@@ -516,21 +516,23 @@ class Pipeline {
     int p0, p1;      // problems [p0, p1)
     size_t v0, v1;   // their vertices = Mellinger instances
     int ws, ows;     // workspace sizes (doubles): warp-per-instance routine, octet routine (0: not eligible)
+    int np_cap;      // largest number of unknowns in the run
   };
-  std::vector<SolveBucket> make_buckets(int B, const int* seg_off, const int* np, const int* hbw, int ws_all, int ows_all) const {
+  std::vector<SolveBucket> make_buckets(int B, const int* seg_off, const int* np, const int* hbw, int ws_all, int ows_all, int np_all) const {
     std::vector<SolveBucket> out;
     int cls_prev = 0;
     for (int p = 0; p < B; ++p) {
       const int S = seg_off[p + 1] - seg_off[p];
       const int ws = solve_ws_doubles(S, np[p], hbw[p]);
-      const int ows = (hbw[p] == kOctHbw && np[p] > 0) ? octet_ws_doubles(S, np[p]) : 0;
+      const int ows = (hbw[p] == kOctHbw && np[p] >= kOctMinNp) ? octet_ws_doubles(S, np[p]) : 0;
       const int cls = be_.solve_class(ws, ows);
       if (out.empty() || cls != cls_prev) {
-        if (out.size() >= 32) {  // ragged input in no particular order: one launch for everything, as sized by the batch maxima
-          out.assign(1, SolveBucket{0, B, 0, (size_t)seg_off[B] + B, ws_all, ows_all});
+        if (out.size() >= 32) {  // ragged input in no particular order: one launch pair for everything, sized by the batch maxima
+          out.assign(1, SolveBucket{0, B, 0, (size_t)seg_off[B] + B, ws_all, ows_all, np_all});
+          mixed_single_ = true;
           return out;
         }
-        out.push_back(SolveBucket{p, p, (size_t)seg_off[p] + p, 0, 0, 0});
+        out.push_back(SolveBucket{p, p, (size_t)seg_off[p] + p, 0, 0, 0, 0});
         cls_prev = cls;
       }
       SolveBucket& k = out.back();
@@ -538,20 +540,25 @@ class Pipeline {
       k.v1 = (size_t)seg_off[p + 1] + p + 1;
       k.ws = std::max(k.ws, ws);
       k.ows = std::max(k.ows, ows);
+      k.np_cap = std::max(k.np_cap, np[p]);
     }
+    mixed_single_ = false;
     return out;
   }
+  mutable bool mixed_single_ = false;
+  // stats: b.stats read back (0: ws, 2: octet ws, 3: max np, 6: problems the octet routine cannot take)
   template <class D>
-  void solve_with_outputs(size_t n_inst, int ws, int ows, const D& desc, const BatchPtrs& b, const std::vector<SolveBucket>* buckets = nullptr,
+  void solve_with_outputs(size_t n_inst, const int* stats, const D& desc, const BatchPtrs& b, const std::vector<SolveBucket>* buckets = nullptr,
                           bool per_vertex = false) {
     if (buckets && !buckets->empty()) {
       for (const SolveBucket& k : *buckets) {
-        if (per_vertex) be_.solve(k.v0, k.v1, k.ws, k.ows, desc);
-        else be_.solve((size_t)k.p0, (size_t)k.p1, k.ws, k.ows, desc);
+        const bool mixed = mixed_single_;  // a run is homogeneous by construction unless it is the collapsed one
+        if (per_vertex) be_.solve(k.v0, k.v1, k.ws, k.ows, k.np_cap, mixed, desc);
+        else be_.solve((size_t)k.p0, (size_t)k.p1, k.ws, k.ows, k.np_cap, mixed, desc);
       }
       launches((int)buckets->size() - 1);
     } else {
-      be_.solve(0, n_inst, ws, ows, desc);
+      be_.solve(0, n_inst, stats[0], stats[2], stats[3], stats[6] > 0, desc);
     }
     const int per = 4 * b.smax;
     be_.for_each(n_inst * (size_t)per, CoefCostFn<D>{desc, per, b.part});
@@ -563,7 +570,7 @@ class Pipeline {
   // objective + forward-difference gradient 256-333 as S+1 batched solves per evaluation) then the time scaling of
   // scaleSegmentTimesWithViolation (335-427).  Needs b.times (initial), vmask/vval/vfree/np/hbw, coef, ps; leaves the
   // stretched times in b.times (the caller runs the final solve).
-  void time_alloc_core(BatchPtrs& b, const Params& P, int ws, int ows, const std::vector<SolveBucket>* buckets = nullptr) {
+  void time_alloc_core(BatchPtrs& b, const Params& P, const int* stats, const std::vector<SolveBucket>* buckets = nullptr) {
     const int B = b.B, totS = b.totS, totV = b.totV;
     b.xeval = scratch_.template alloc<double>(totS);
     b.x = scratch_.template alloc<double>(totS);
@@ -578,7 +585,7 @@ class Pipeline {
     be_.for_each(B, LbfgsBeginFn{b}); launches(1);
     for (int e = 0; e < P.max_evals; ++e) {
       be_.for_each((size_t)totS * 3, SetupMellingerFn{b});
-      solve_with_outputs((size_t)totV, ws, ows, SolveProblemDesc{b, 1, nullptr, nullptr}, b, buckets, true);
+      solve_with_outputs((size_t)totV, stats, SolveProblemDesc{b, 1, nullptr, nullptr}, b, buckets, true);
       be_.for_each(B, LbfgsAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel});
       launches(3);
     }
@@ -612,9 +619,9 @@ class Pipeline {
     int stats[8];
     be_.d2h(stats, b.stats, sizeof(stats));
     alloc_solution_buffers(b, (size_t)b.totV, stats);
-    time_alloc_core(b, P, stats[0], stats[2]);
+    time_alloc_core(b, P, stats);
     be_.for_each(b.totS, SetupBaseFn{b, b.times});
-    solve_with_outputs((size_t)B, stats[0], stats[2], SolveProblemDesc{b, 0, nullptr, nullptr}, b);
+    solve_with_outputs((size_t)B, stats, SolveProblemDesc{b, 0, nullptr, nullptr}, b);
     launches(2);
     std::vector<ProbState> ps(B);
     be_.d2h(ps.data(), b.ps, sizeof(ProbState) * B);
@@ -867,7 +874,7 @@ class Pipeline {
     for (long long k0 = 0; k0 < K; k0 += chunk) {
       const long long kc = std::min(chunk, K - k0);
       be_.for_each((size_t)kc * S, SetupSweepFn{S, r, d_cand + (size_t)k0 * S, d_recs});
-      solve_with_outputs((size_t)kc, stats[0], stats[2], SolveSweepDesc{b, d_recs, d_costs + k0}, b);
+      solve_with_outputs((size_t)kc, stats, SolveSweepDesc{b, d_recs, d_costs + k0}, b);
       launches(2);
     }
     counters.solves += K;

@@ -31,23 +31,28 @@ namespace tg {
 constexpr int kOctRow = 20;    // doubles per banded row: 16 column slots (column j at j & 15) + 4 right-hand sides
 constexpr int kOctHbw = 7;
 constexpr int kOctMinNp = 8;
+constexpr int kOctRing = 16;   // rows of the shared-memory ring: two blocks of eight (row i at ((i >> 3) & 1) * 8 + (i & 7))
 
-// shared-memory doubles for one octet solve: rows | slot table | row -> (vertex, slot) table.
+// Shared-memory doubles for one octet solve: row ring | slot table | row -> (vertex, slot) table.  Independent of the
+// problem size but for the two small tables: the rows themselves stream through the ring (assembled one block ahead of
+// the elimination) and the U rows wait for the back substitution in a per-warp slab of global memory that stays in L2.
 // Sized = 2 (mod 16) so that the four octets of a warp start in different banks.
 TG_HD int octet_ws_doubles(int S, int np) {
-  int n = np * kOctRow + (5 * (S + 1) + 3) / 4 + (np + 3) / 4;
+  int n = kOctRing * kOctRow + (5 * (S + 1) + 3) / 4 + (np + 3) / 4;
   n = (n + 1) & ~1;
   while ((n & 15) != 2) n += 2;
   return n;
 }
-TG_HD void octet_ws_bind(SolveInst& I, double* ws) {
+// urows: np * kOctRow doubles of global memory owned by this octet
+TG_HD void octet_ws_bind(SolveInst& I, double* ws, double* urows) {
   I.W = kOctRow;
   I.rows = ws;
-  I.xs = nullptr;
+  I.xs = urows;
   I.part = nullptr;
-  I.slot = (int16_t*)(ws + I.np * kOctRow);
+  I.slot = (int16_t*)(ws + kOctRing * kOctRow);
   I.rowva = I.slot + ((5 * (I.S + 1) + 3) / 4) * 4;
 }
+TG_HD int octet_ring_pos(int i) { return ((i >> 3) & 1) * 8 + (i & 7); }
 // the routine produces the solution of the reduced system only (x_out); coefficients and cost are CoefCostFn's job
 TG_HD bool octet_eligible(const SolveInst& I) { return I.hbw == kOctHbw && I.np >= kOctMinNp && I.dp_out == nullptr && I.x_out != nullptr; }
 
@@ -127,8 +132,87 @@ TG_HD void octet_stage_wait() {
 #endif
 }
 
+// One lane's part of a block of eight rows.  stage: the two rows of H that row i of R is built from -- row (5+a) of
+// H_{v-1} into slots 0..9, row a of H_v into slots 10..19 of the row's ring position -- as asynchronous 16-byte copies.
+TG_HD void octet_stage_block(const SolveInst& I, int sub, int blk) {
+  const int i = blk * 8 + sub;
+  if (i >= I.np) return;
+  const int it = I.rowva[i];
+  const int v = it / TG_HALF, a = it - v * TG_HALF;
+  double* row = I.rows + octet_ring_pos(i) * kOctRow;
+  if (v > 0) octet_stage_row(row, solve_rec(I, v - 1) + TG_REC_H + (TG_HALF + a) * TG_N);  // 16-byte aligned: TG_REC_H and TG_N are even
+  if (v < I.S) octet_stage_row(row + TG_N, solve_rec(I, v) + TG_REC_H + a * TG_N);
+}
+// assemble: row i of Rpp and of rhs = (-Rpf) d_f in place, from the staged H rows (identical sums to solve_warp phase 1)
+TG_HD void octet_assemble_block(const SolveInst& I, int sub, int blk) {
+  const int i = blk * 8 + sub, S = I.S;
+  if (i >= I.np) return;
+  const int it = I.rowva[i];
+  const int v = it / TG_HALF;
+  double hp[TG_N], hc[TG_N];
+  const bool has_p = v > 0, has_c = v < S;
+  double* row = I.rows + octet_ring_pos(i) * kOctRow;
+#pragma unroll
+  for (int q = 0; q < TG_N; q += 2) {
+    const Dbl2 t = *reinterpret_cast<const Dbl2*>(row + q), u = *reinterpret_cast<const Dbl2*>(row + TG_N + q);
+    hp[q] = t.x;
+    hp[q + 1] = t.y;
+    hc[q] = u.x;
+    hc[q + 1] = u.y;
+  }
+  Dbl2 z;
+  z.x = 0.0;
+  z.y = 0.0;
+#pragma unroll
+  for (int q = 0; q < kOctRow; q += 2) *reinterpret_cast<Dbl2*>(row + q) = z;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    const int w = v - 1 + g;
+    if (w < 0 || w > S) continue;
+#pragma unroll
+    for (int b = 0; b < TG_HALF; ++b) {
+      double rv;
+      if (g == 0) rv = hp[b];
+      else if (g == 2) rv = hc[TG_HALF + b];
+      else rv = has_p ? (has_c ? hp[TG_HALF + b] + hc[b] : hp[TG_HALF + b]) : hc[b];
+      const int j = I.slot[w * TG_HALF + b];
+      if (j >= 0) {
+        row[j & 15] = rv;
+      } else {
+        const double* f = I.vval + ((size_t)w * TG_HALF + b) * TG_D;
+        const double nr = -rv;
+        acc0 = acc0 + nr * f[0];
+        acc1 = acc1 + nr * f[1];
+        acc2 = acc2 + nr * f[2];
+        acc3 = acc3 + nr * f[3];
+      }
+    }
+  }
+  row[16] = acc0;
+  row[17] = acc1;
+  row[18] = acc2;
+  row[19] = acc3;
+}
+// back substitution: the stored U row i (global memory, L2) travels back into its ring position
+TG_HD void octet_stage_urow(const SolveInst& I, int i) {
+  if (i < 0 || i >= I.np) return;
+  double* dst = I.rows + octet_ring_pos(i) * kOctRow;
+  const double* src = I.xs + (size_t)i * kOctRow;
+  octet_stage_row(dst, src);
+  octet_stage_row(dst + TG_N, src + TG_N);
+}
+
 // Device: `insts` points at the calling lane's own instance (lanes of one octet hold identical copies); an octet
 // without work has np == 0 and S == 0.  Host emulation: insts[4], one per octet.  nmax = max np over the warp.
+//
+// Memory plan (profiles/r01_solve_octet_s3.md): the shared-memory ring holds two blocks of eight rows.  While the
+// elimination works on block b (its rows are in registers), block b+1 sits assembled in the ring -- each lane takes its
+// next row from there when the one it holds becomes final -- and the H rows of block b+2 are in flight (cp.async) into
+// the positions block b has just left.  A final row goes to the octet's slab in global memory (U part, right-hand sides,
+// reciprocal pivot: it stays in L2) and comes back the same way, one block ahead, for the back substitution.  Every ring
+// position is written and read by one lane only (row i <-> lane i mod 8), so the whole routine needs no __syncwarp()
+// after the slot tables; shared memory per problem no longer depends on its size.
 TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
   OctLane st_all[TG_OCT_LANES];
   (void)lane;
@@ -144,90 +228,25 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
         const int j = I.vfree[v] + free_rank(m, a);
         I.slot[it] = fixed ? (int16_t)-1 : (int16_t)j;
         if (!fixed) I.rowva[j] = (int16_t)it;
-        else octet_prefetch_fixed(I.vval + (size_t)it * TG_D);  // read in phase 1 by the rows that have this column
+        else octet_prefetch_fixed(I.vval + (size_t)it * TG_D);  // read during assembly by the rows that have this column
       }
     }
   }
-  // ---- phase 0b: every lane stages the two rows of H that each of its rows of R is built from -- row (5+a) of H_{v-1}
-  // into slots 0..9, row a of H_v into slots 10..19 of the row's own storage -- as asynchronous 16-byte copies, ALL of
-  // them in flight before the first is awaited (profiles/r01_solve_octet_s3.md: with the loads inside the assembly loop
-  // every row cost one full memory latency, 30 % of the kernel).  A lane reads back only what it staged itself.
-  TG_PHASE_NS(lane) {
-    const SolveInst& I = TG_OCT_INST(insts, lane);
-    const int sub = lane & 7, S = I.S;
-    for (int i = sub; i < I.np; i += 8) {
-      const int it = I.rowva[i];
-      const int v = it / TG_HALF, a = it - v * TG_HALF;
-      double* row = I.rows + i * kOctRow;
-      if (v > 0) octet_stage_row(row, solve_rec(I, v - 1) + TG_REC_H + (TG_HALF + a) * TG_N);  // 16-byte aligned: TG_REC_H and TG_N are even
-      if (v < S) octet_stage_row(row + TG_N, solve_rec(I, v) + TG_REC_H + a * TG_N);
-    }
-    octet_stage_wait();
-  }
-  // ---- phase 1: assemble Rpp and rhs = (-Rpf) d_f, one lane per row (identical sums to solve_warp phase 1) -------
-  TG_PHASE(lane) {
-    const SolveInst& I = TG_OCT_INST(insts, lane);
-    const int sub = lane & 7, S = I.S;
-    for (int i = sub; i < I.np; i += 8) {
-      const int it = I.rowva[i];
-      const int v = it / TG_HALF;
-      double hp[TG_N], hc[TG_N];
-      const bool has_p = v > 0, has_c = v < S;
-      double* row = I.rows + i * kOctRow;
-#pragma unroll
-      for (int q = 0; q < TG_N; q += 2) {
-        const Dbl2 t = *reinterpret_cast<const Dbl2*>(row + q), u = *reinterpret_cast<const Dbl2*>(row + TG_N + q);
-        hp[q] = t.x;
-        hp[q + 1] = t.y;
-        hc[q] = u.x;
-        hc[q + 1] = u.y;
-      }
-      Dbl2 z;
-      z.x = 0.0;
-      z.y = 0.0;
-#pragma unroll
-      for (int q = 0; q < kOctRow; q += 2) *reinterpret_cast<Dbl2*>(row + q) = z;
-      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        const int w = v - 1 + g;
-        if (w < 0 || w > S) continue;
-#pragma unroll
-        for (int b = 0; b < TG_HALF; ++b) {
-          double rv;
-          if (g == 0) rv = hp[b];
-          else if (g == 2) rv = hc[TG_HALF + b];
-          else rv = has_p ? (has_c ? hp[TG_HALF + b] + hc[b] : hp[TG_HALF + b]) : hc[b];
-          const int j = I.slot[w * TG_HALF + b];
-          if (j >= 0) {
-            row[j & 15] = rv;
-          } else {
-            const double* f = I.vval + ((size_t)w * TG_HALF + b) * TG_D;
-            const double nr = -rv;
-            acc0 = acc0 + nr * f[0];
-            acc1 = acc1 + nr * f[1];
-            acc2 = acc2 + nr * f[2];
-            acc3 = acc3 + nr * f[3];
-          }
-        }
-      }
-      row[16] = acc0;
-      row[17] = acc1;
-      row[18] = acc2;
-      row[19] = acc3;
-    }
-  }
-  // ---- phase 2: LU without pivoting.  Lane sub holds row `myrow` (== sub mod 8) while it is in the window. -------------
-  // (each lane reads back only rows it assembled itself, so no synchronisation is needed from here to phase 4)
+  // ---- phase 1: blocks 0 and 1 into the ring, block 0 assembled and taken into registers, block 2 in flight --------------
   TG_PHASE_NS(lane) {
     const SolveInst& I = TG_OCT_INST(insts, lane);
     OctLane& st = TG_OCT_STATE(st_all, lane);
-    st.myrow = lane & 7;
+    const int sub = lane & 7;
+    octet_stage_block(I, sub, 0);
+    octet_stage_block(I, sub, 1);
+    octet_stage_wait();
+    octet_assemble_block(I, sub, 0);
+    st.myrow = sub;
     st.rinv = 0.0;
 #pragma unroll
     for (int d = 0; d < 4; ++d) st.x[d] = 0.0;
     if (st.myrow < I.np) {
-      octet_load_row(st, I.rows + st.myrow * kOctRow, 0);
+      octet_load_row(st, I.rows + octet_ring_pos(st.myrow) * kOctRow, 0);
     } else {
 #pragma unroll
       for (int q = 0; q < 16; ++q) st.reg[q] = 0.0;
@@ -235,8 +254,18 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
       for (int d = 0; d < 4; ++d) st.rhs[d] = 0.0;
     }
   }
+  // ---- phase 2: LU without pivoting.  Lane sub holds row `myrow` (== sub mod 8) while it is in the window. -------------
   for (int k0 = 0; k0 < nmax; k0 += 8) {
-    const int flip = k0 & 8;
+    const int flip = k0 & 8, blk = k0 >> 3;
+    TG_PHASE_NS(lane) {
+      // block blk+1 has landed (its copies were issued one block ago): assemble it.  The rows of block blk are all in
+      // registers by now, so the H rows of block blk+2 may start flowing into the ring positions they came from.
+      const SolveInst& I = TG_OCT_INST(insts, lane);
+      const int sub = lane & 7;
+      octet_stage_wait();
+      octet_assemble_block(I, sub, blk + 1);
+      octet_stage_block(I, sub, blk + 2);
+    }
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
       const int k = k0 + m;
@@ -263,16 +292,16 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
           if (k < I.np) {
             const double rinv = 1.0 / st.f_diag;
             if (st.myrow == k) {
-              // row k is final: keep its U part, right-hand sides and reciprocal pivot (in the one slot outside its
-              // band) for the back substitution, then take row k+8 into the window
-              double* rk = I.rows + k * kOctRow;
+              // row k is final: its U part, right-hand sides and reciprocal pivot (in the one slot outside its band) go
+              // to the slab for the back substitution, then row k+8 comes out of the ring into the window
+              double* rk = I.xs + (size_t)k * kOctRow;
               rk[((m + 8) & 15) ^ flip] = rinv;
 #pragma unroll
               for (int c = 0; c < 7; ++c) rk[((m + 1 + c) & 15) ^ flip] = st.reg[(m + 1 + c) & 15];
 #pragma unroll
               for (int d = 0; d < 4; ++d) rk[16 + d] = st.rhs[d];
               st.myrow = k + 8;
-              if (st.myrow < I.np) octet_load_row(st, I.rows + st.myrow * kOctRow, flip);
+              if (st.myrow < I.np) octet_load_row(st, I.rows + octet_ring_pos(st.myrow) * kOctRow, flip);
             } else if (st.myrow < I.np) {  // rows k+1 .. min(np-1, k+7)
               const double l = st.reg[m] * rinv;
 #pragma unroll
@@ -287,14 +316,21 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
     TG_PHASE_NS(lane) { octet_swap_halves(TG_OCT_STATE(st_all, lane)); }
   }
   // ---- phase 3: back substitution, column oriented, the window moving upwards -----------------------------------
+  // Each lane starts with the highest row congruent to its index (rows np-8 .. np-1 span the octet's top two blocks) and
+  // afterwards takes row j-8 whenever its row j is done; U rows come back from the slab through the ring one block ahead.
   const int jtop = (nmax > 0) ? ((nmax - 1) & ~7) : 0;
   TG_PHASE_NS(lane) {
     const SolveInst& I = TG_OCT_INST(insts, lane);
     OctLane& st = TG_OCT_STATE(st_all, lane);
     const int sub = lane & 7, np = I.np;
+    octet_stage_wait();  // nothing of the elimination is still in flight
     st.myrow = (np > 0) ? (np - 1) - (((np - 1) - sub) & 7) : -1;
     if (st.myrow >= 0) {
-      const double* src = I.rows + st.myrow * kOctRow;
+      const int btop = (np - 1) >> 3;
+      octet_stage_urow(I, btop * 8 + sub);
+      octet_stage_urow(I, (btop - 1) * 8 + sub);
+      octet_stage_wait();
+      const double* src = I.rows + octet_ring_pos(st.myrow) * kOctRow;
       octet_load_row(st, src, jtop & 8);
       st.rinv = src[(st.myrow + 8) & 15];
       if (st.myrow == np - 1) {
@@ -304,7 +340,17 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
     }
   }
   for (int j0 = jtop; j0 >= 0; j0 -= 8) {
-    const int flip = j0 & 8;
+    const int flip = j0 & 8, blk = j0 >> 3;
+    TG_PHASE_NS(lane) {
+      // rows of block blk are in registers (or this octet ends below it); block blk-1 must have landed before the steps
+      // below take rows from it, and block blk-2 may now use the ring positions of block blk
+      const SolveInst& I = TG_OCT_INST(insts, lane);
+      const int sub = lane & 7;
+      octet_stage_wait();
+      // (the octet's own top block brought block blk-1 along in the prologue; every lane has taken its row of block blk
+      // out of the ring by now, whichever of the two top blocks it started in)
+      if (I.np > 0 && blk <= ((I.np - 1) >> 3)) octet_stage_urow(I, (blk - 2) * 8 + sub);
+    }
 #pragma unroll
     for (int mm = 0; mm < 8; ++mm) {
       const int m = 7 - mm;
@@ -326,7 +372,7 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
               for (int d = 0; d < 4; ++d) I.x_out[j * 4 + d] = st.x[d];  // the solution leaves through global memory
               st.myrow = j - 8;
               if (st.myrow >= 0) {
-                const double* src = I.rows + st.myrow * kOctRow;
+                const double* src = I.rows + octet_ring_pos(st.myrow) * kOctRow;
                 octet_load_row(st, src, flip);
                 st.rinv = src[m ^ flip];  // row j-8 keeps its reciprocal pivot at stored slot (j-8+8) & 15 = j & 15
               }

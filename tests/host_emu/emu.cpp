@@ -9,6 +9,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <thread>
+#include <limits>
 #include <vector>
 
 #define TG_VERSION_STRING "tg_emu (host emulation, tests only)"
@@ -75,18 +76,20 @@ struct EmuBackend {
   void for_each_scratch_on(int, size_t n, const F& f) { for_each_scratch(n, f); }
   // one "warp" per group of four instances (octet kernel) or per instance (general kernel): phases run lane by lane
   // (lanes own disjoint outputs within a phase).  Mirrors k_solve_oct / k_solve of cuda_backend.cu.
-  // same classes as CudaBackend::solve_class on a B200 (228 KB shared memory per SM, 227 KB per CTA, 9 warps by registers)
+  // same classes as CudaBackend::solve_class on a B200 (228 KB shared memory per SM, 227 KB per CTA, 12 warps by registers)
   int solve_class(int ws_doubles, int oct_ws_doubles) const {
     const size_t per_sm = 233472, optin = 232448;
     if (oct_ws_doubles > 0 && !std::getenv("TG_EMU_NO_OCTET")) {
-      const size_t smem = (size_t)std::max(4 * oct_ws_doubles, ws_doubles) * sizeof(double);
-      const int w = smem > optin ? 0 : std::min((int)(per_sm / (smem + 1024)), 9);
-      if (w >= 2) return w;
+      const size_t smem = (size_t)4 * oct_ws_doubles * sizeof(double);
+      const int w = smem > optin ? 0 : std::min((int)(per_sm / (smem + 1024)), 12);
+      if (w >= 1) return w;
     }
     return ((size_t)ws_doubles * sizeof(double) * 4 <= optin) ? 0 : -1;
   }
+  // Mirrors CudaBackend::solve: instances the octet routine can take go through solve_octets in groups of four (one
+  // "warp"), the others (when `mixed`) through solve_warp.
   template <class D>
-  void solve(size_t inst_begin, size_t inst_end, int ws_doubles, int oct_ws_doubles, const D& desc0) {
+  void solve(size_t inst_begin, size_t inst_end, int ws_doubles, int oct_ws_doubles, int np_cap, bool mixed, const D& desc0) {
     if (inst_end <= inst_begin) return;
     const size_t n_inst = inst_end - inst_begin;
     struct Shifted {  // instance numbering relative to the range
@@ -94,45 +97,38 @@ struct EmuBackend {
       size_t off;
       bool instance(size_t i, tg::SolveInst& I) const { return d.instance(i + off, I); }
     } desc{desc0, inst_begin};
-    if (solve_class(ws_doubles, oct_ws_doubles) < 2) {
-      parallel(n_inst, [&](size_t inst) {
-        tg::SolveInst I;
-        if (!desc.instance(inst, I)) return;
-        std::vector<double> ws((size_t)ws_doubles);
-        tg::solve_ws_bind(I, ws.data());
-        tg::solve_warp(I, 0);  // TG_PHASE runs the 32 lanes of every phase one after the other
+    const bool use_oct = solve_class(ws_doubles, oct_ws_doubles) >= 1;
+    np_cap = std::max(np_cap, 1);
+    auto takes = [&](const tg::SolveInst& I) { return use_oct && tg::octet_eligible(I) && tg::octet_ws_doubles(I.S, I.np) <= oct_ws_doubles && I.np <= np_cap; };
+    if (use_oct) {
+      if (std::getenv("TG_EMU_TRACE")) std::fprintf(stderr, "[emu] octet solve path: %zu instances\n", n_inst);
+      parallel((n_inst + 3) / 4, [&](size_t grp) {
+        tg::SolveInst I[4];
+        int nmax = 0;
+        // NaN-filled: on the device neither the shared-memory ring nor the slab is initialised
+        const double nan = std::numeric_limits<double>::quiet_NaN();
+        std::vector<double> ws((size_t)4 * oct_ws_doubles, nan), us((size_t)4 * np_cap * tg::kOctRow, nan);
+        for (int o = 0; o < 4; ++o) {
+          const size_t inst = grp * 4 + o;
+          const bool ok = inst < n_inst && desc.instance(inst, I[o]) && takes(I[o]);
+          if (!ok) {
+            I[o] = tg::SolveInst{};
+            I[o].hbw = tg::kOctHbw;
+          }
+          tg::octet_ws_bind(I[o], ws.data() + (size_t)o * oct_ws_doubles, us.data() + (size_t)o * np_cap * tg::kOctRow);
+          nmax = std::max(nmax, I[o].np);
+        }
+        if (nmax > 0) tg::solve_octets(I, 0, nmax);
       });
-      return;
+      if (!mixed) return;
     }
-    const size_t warp_ws = (size_t)std::max(4 * oct_ws_doubles, ws_doubles);
-    if (std::getenv("TG_EMU_TRACE")) std::fprintf(stderr, "[emu] octet solve path: %zu instances\n", n_inst);
-    parallel((n_inst + 3) / 4, [&](size_t grp) {
-      tg::SolveInst I[4];
-      bool ok[4], all_oct = true;
-      int nmax = 0;
-      std::vector<double> ws(warp_ws);
-      for (int o = 0; o < 4; ++o) {
-        const size_t inst = grp * 4 + o;
-        ok[o] = inst < n_inst && desc.instance(inst, I[o]);
-        if (!ok[o]) {
-          I[o] = tg::SolveInst{};
-          continue;
-        }
-        if (!tg::octet_eligible(I[o]) || tg::octet_ws_doubles(I[o].S, I[o].np) > oct_ws_doubles) all_oct = false;
-      }
-      if (all_oct) {
-        for (int o = 0; o < 4; ++o) {
-          tg::octet_ws_bind(I[o], ws.data() + (size_t)o * oct_ws_doubles);
-          if (ok[o]) nmax = std::max(nmax, I[o].np);
-        }
-        tg::solve_octets(I, 0, nmax);
-      } else {
-        for (int o = 0; o < 4; ++o) {
-          if (!ok[o]) continue;
-          tg::solve_ws_bind(I[o], ws.data());
-          tg::solve_warp(I[o], 0);
-        }
-      }
+    parallel(n_inst, [&](size_t inst) {
+      tg::SolveInst I;
+      if (!desc.instance(inst, I)) return;
+      if (takes(I)) return;
+      std::vector<double> ws((size_t)ws_doubles);
+      tg::solve_ws_bind(I, ws.data());
+      tg::solve_warp(I, 0);  // TG_PHASE runs the 32 lanes of every phase one after the other
     });
   }
   // the micro-op Jenkins-Traub machine, item by item (the CUDA build schedules it warp-wide with lane refill)
