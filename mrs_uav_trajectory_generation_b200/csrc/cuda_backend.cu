@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const 
 }
 
 // Four solve instances per warp, eight lanes each (tg_solve_octet.cuh); instances the octet routine cannot take are left
-// to k_solve.  One warp per CTA.  uslab: per-CTA slab of 4 * u_cap rows of kOctRow doubles (the U rows between the
+// to k_solve.  One warp per CTA.  uslab: per-CTA slab of 4 * u_cap rows of kOctURow doubles (the U rows between the
 // elimination and the back substitution; L2 resident).
 template <class D>
 __global__ void __launch_bounds__(32) k_solve_oct(const D desc, const size_t inst_begin, const size_t n_inst, const int oct_ws_doubles, const int u_cap,
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(32) k_solve_oct(const D desc, const size_t ins
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, oct = lane >> 3;
   const size_t gw = blockIdx.x, nw = gridDim.x;
-  double* urows = uslab + ((size_t)blockIdx.x * 4 + oct) * (size_t)u_cap * tg::kOctRow;
+  double* urows = uslab + ((size_t)blockIdx.x * 4 + oct) * (size_t)u_cap * tg::kOctURow;
   for (size_t base = inst_begin + gw * 4; base < n_inst; base += nw * 4) {
     tg::SolveInst I;
     const size_t inst = base + oct;
@@ -440,7 +440,7 @@ struct CudaBackend {
       TG_CUDA_CHECK(cudaFuncSetAttribute(k_solve_oct<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oct_smem));
       const size_t blocks_needed = (n_inst + 3) / 4;
       // the U slab of all resident warps should stay in L2 (126 MB): fewer warps for very long paths
-      const size_t per_cta = (size_t)4 * std::max(np_cap, 1) * tg::kOctRow;
+      const size_t per_cta = (size_t)4 * std::max(np_cap, 1) * tg::kOctURow;
       size_t grid = std::min(blocks_needed, (size_t)sm_count * oct_warps);
       const size_t l2_ctas = std::max<size_t>((size_t)sm_count, ((size_t)96 << 20) / (per_cta * sizeof(double)));
       grid = std::min(grid, l2_ctas);

@@ -32,6 +32,7 @@ constexpr int kOctRow = 20;    // doubles per banded row: 16 column slots (colum
 constexpr int kOctHbw = 7;
 constexpr int kOctMinNp = 8;
 constexpr int kOctRing = 16;   // rows of the shared-memory ring: two blocks of eight (row i at ((i >> 3) & 1) * 8 + (i & 7))
+constexpr int kOctURow = 12;   // doubles of a finished row kept for the back substitution: 1/pivot, U[i][i+1..i+7], 4 right-hand sides
 
 // Shared-memory doubles for one octet solve: row ring | slot table | row -> (vertex, slot) table.  Independent of the
 // problem size but for the two small tables: the rows themselves stream through the ring (assembled one block ahead of
@@ -43,7 +44,7 @@ TG_HD int octet_ws_doubles(int S, int np) {
   while ((n & 15) != 2) n += 2;
   return n;
 }
-// urows: np * kOctRow doubles of global memory owned by this octet
+// urows: np * kOctURow doubles of global memory owned by this octet
 TG_HD void octet_ws_bind(SolveInst& I, double* ws, double* urows) {
   I.W = kOctRow;
   I.rows = ws;
@@ -194,13 +195,48 @@ TG_HD void octet_assemble_block(const SolveInst& I, int sub, int blk) {
   row[18] = acc2;
   row[19] = acc3;
 }
-// back substitution: the stored U row i (global memory, L2) travels back into its ring position
+// back substitution: the stored U row i (global memory, L2) travels back into its ring position (first kOctURow doubles)
 TG_HD void octet_stage_urow(const SolveInst& I, int i) {
   if (i < 0 || i >= I.np) return;
   double* dst = I.rows + octet_ring_pos(i) * kOctRow;
-  const double* src = I.xs + (size_t)i * kOctRow;
-  octet_stage_row(dst, src);
-  octet_stage_row(dst + TG_N, src + TG_N);
+  const double* src = I.xs + (size_t)i * kOctURow;
+#if defined(__CUDA_ARCH__)
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll
+  for (int q = 0; q < kOctURow / 2; ++q) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + 16u * q), "l"(src + 2 * q) : "memory");
+#else
+  for (int q = 0; q < kOctURow; ++q) dst[q] = src[q];
+#endif
+}
+// A U row in the ring -> the lane's registers.  rel = (row index) - (first column of the current block of steps): column
+// i+1+c sits at register index (rel + 1 + c) & 15.  Called from fully unrolled code with a literal rel, so that every
+// register index is static after inlining.
+TG_HD void octet_load_urow_static(OctLane& st, const double* __restrict__ src, const int REL) {
+  const Dbl2 a = *reinterpret_cast<const Dbl2*>(src), b = *reinterpret_cast<const Dbl2*>(src + 2), c = *reinterpret_cast<const Dbl2*>(src + 4),
+             d = *reinterpret_cast<const Dbl2*>(src + 6), e = *reinterpret_cast<const Dbl2*>(src + 8), f = *reinterpret_cast<const Dbl2*>(src + 10);
+  st.rinv = a.x;
+  st.reg[(REL + 1) & 15] = a.y;
+  st.reg[(REL + 2) & 15] = b.x;
+  st.reg[(REL + 3) & 15] = b.y;
+  st.reg[(REL + 4) & 15] = c.x;
+  st.reg[(REL + 5) & 15] = c.y;
+  st.reg[(REL + 6) & 15] = d.x;
+  st.reg[(REL + 7) & 15] = d.y;
+  st.rhs[0] = e.x;
+  st.rhs[1] = e.y;
+  st.rhs[2] = f.x;
+  st.rhs[3] = f.y;
+}
+// the same with rel known only at run time (start of the back substitution): register index q static, source index computed
+TG_HD void octet_load_urow_dyn(OctLane& st, const double* __restrict__ src, int rel) {
+  st.rinv = src[0];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int c = (q - rel - 1) & 15;  // column offset held by register q
+    st.reg[q] = (c < 7) ? src[1 + c] : 0.0;
+  }
+#pragma unroll
+  for (int d = 0; d < 4; ++d) st.rhs[d] = src[8 + d];
 }
 
 // Device: `insts` points at the calling lane's own instance (lanes of one octet hold identical copies); an octet
@@ -232,31 +268,13 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
       }
     }
   }
-  // ---- phase 1: blocks 0 and 1 into the ring, block 0 assembled and taken into registers, block 2 in flight --------------
-  TG_PHASE_NS(lane) {
-    const SolveInst& I = TG_OCT_INST(insts, lane);
-    OctLane& st = TG_OCT_STATE(st_all, lane);
-    const int sub = lane & 7;
-    octet_stage_block(I, sub, 0);
-    octet_stage_block(I, sub, 1);
-    octet_stage_wait();
-    octet_assemble_block(I, sub, 0);
-    st.myrow = sub;
-    st.rinv = 0.0;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) st.x[d] = 0.0;
-    if (st.myrow < I.np) {
-      octet_load_row(st, I.rows + octet_ring_pos(st.myrow) * kOctRow, 0);
-    } else {
-#pragma unroll
-      for (int q = 0; q < 16; ++q) st.reg[q] = 0.0;
-#pragma unroll
-      for (int d = 0; d < 4; ++d) st.rhs[d] = 0.0;
-    }
-  }
+  // ---- phase 1: the H rows of block 0 start flowing into the ring -------------------------------------------------------
+  TG_PHASE_NS(lane) { octet_stage_block(TG_OCT_INST(insts, lane), lane & 7, 0); }
   // ---- phase 2: LU without pivoting.  Lane sub holds row `myrow` (== sub mod 8) while it is in the window. -------------
-  for (int k0 = 0; k0 < nmax; k0 += 8) {
-    const int flip = k0 & 8, blk = k0 >> 3;
+  // The loop starts one block early (k0 = -8): that pass only assembles block 0 and takes it into registers, so that the
+  // assembly code exists once (instruction cache: profiles/r01_solve_octet_s3.md).
+  for (int k0 = -8; k0 < nmax; k0 += 8) {
+    const int flip = k0 & 8, blk = k0 >> 3;  // blk = -1 in the first pass
     TG_PHASE_NS(lane) {
       // block blk+1 has landed (its copies were issued one block ago): assemble it.  The rows of block blk are all in
       // registers by now, so the H rows of block blk+2 may start flowing into the ring positions they came from.
@@ -265,7 +283,23 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
       octet_stage_wait();
       octet_assemble_block(I, sub, blk + 1);
       octet_stage_block(I, sub, blk + 2);
+      if (blk < 0) {
+        OctLane& st = TG_OCT_STATE(st_all, lane);
+        st.myrow = sub;
+        st.rinv = 0.0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) st.x[d] = 0.0;
+        if (st.myrow < I.np) {
+          octet_load_row(st, I.rows + octet_ring_pos(st.myrow) * kOctRow, 0);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) st.reg[q] = 0.0;
+#pragma unroll
+          for (int d = 0; d < 4; ++d) st.rhs[d] = 0.0;
+        }
+      }
     }
+    if (blk < 0) continue;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
       const int k = k0 + m;
@@ -294,12 +328,13 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
             if (st.myrow == k) {
               // row k is final: its U part, right-hand sides and reciprocal pivot (in the one slot outside its band) go
               // to the slab for the back substitution, then row k+8 comes out of the ring into the window
-              double* rk = I.xs + (size_t)k * kOctRow;
-              rk[((m + 8) & 15) ^ flip] = rinv;
-#pragma unroll
-              for (int c = 0; c < 7; ++c) rk[((m + 1 + c) & 15) ^ flip] = st.reg[(m + 1 + c) & 15];
-#pragma unroll
-              for (int d = 0; d < 4; ++d) rk[16 + d] = st.rhs[d];
+              double* rk = I.xs + (size_t)k * kOctURow;
+              store2(rk, rinv, st.reg[(m + 1) & 15]);
+              store2(rk + 2, st.reg[(m + 2) & 15], st.reg[(m + 3) & 15]);
+              store2(rk + 4, st.reg[(m + 4) & 15], st.reg[(m + 5) & 15]);
+              store2(rk + 6, st.reg[(m + 6) & 15], st.reg[(m + 7) & 15]);
+              store2(rk + 8, st.rhs[0], st.rhs[1]);
+              store2(rk + 10, st.rhs[2], st.rhs[3]);
               st.myrow = k + 8;
               if (st.myrow < I.np) octet_load_row(st, I.rows + octet_ring_pos(st.myrow) * kOctRow, flip);
             } else if (st.myrow < I.np) {  // rows k+1 .. min(np-1, k+7)
@@ -330,9 +365,7 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
       octet_stage_urow(I, btop * 8 + sub);
       octet_stage_urow(I, (btop - 1) * 8 + sub);
       octet_stage_wait();
-      const double* src = I.rows + octet_ring_pos(st.myrow) * kOctRow;
-      octet_load_row(st, src, jtop & 8);
-      st.rinv = src[(st.myrow + 8) & 15];
+      octet_load_urow_dyn(st, I.rows + octet_ring_pos(st.myrow) * kOctRow, st.myrow - jtop);
       if (st.myrow == np - 1) {
 #pragma unroll
         for (int d = 0; d < 4; ++d) st.x[d] = st.rhs[d] * st.rinv;
@@ -340,7 +373,7 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
     }
   }
   for (int j0 = jtop; j0 >= 0; j0 -= 8) {
-    const int flip = j0 & 8, blk = j0 >> 3;
+    const int blk = j0 >> 3;
     TG_PHASE_NS(lane) {
       // rows of block blk are in registers (or this octet ends below it); block blk-1 must have landed before the steps
       // below take rows from it, and block blk-2 may now use the ring positions of block blk
@@ -371,11 +404,7 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
 #pragma unroll
               for (int d = 0; d < 4; ++d) I.x_out[j * 4 + d] = st.x[d];  // the solution leaves through global memory
               st.myrow = j - 8;
-              if (st.myrow >= 0) {
-                const double* src = I.rows + octet_ring_pos(st.myrow) * kOctRow;
-                octet_load_row(st, src, flip);
-                st.rinv = src[m ^ flip];  // row j-8 keeps its reciprocal pivot at stored slot (j-8+8) & 15 = j & 15
-              }
+              if (st.myrow >= 0) octet_load_urow_static(st, I.rows + octet_ring_pos(st.myrow) * kOctRow, m - 8);  // row j-8: rel = m - 8
             } else if (st.myrow >= 0 && st.myrow < j) {  // rows j-7 .. j-1
               const double a = st.reg[m];
 #pragma unroll

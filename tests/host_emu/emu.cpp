@@ -107,7 +107,7 @@ struct EmuBackend {
         int nmax = 0;
         // NaN-filled: on the device neither the shared-memory ring nor the slab is initialised
         const double nan = std::numeric_limits<double>::quiet_NaN();
-        std::vector<double> ws((size_t)4 * oct_ws_doubles, nan), us((size_t)4 * np_cap * tg::kOctRow, nan);
+        std::vector<double> ws((size_t)4 * oct_ws_doubles, nan), us((size_t)4 * np_cap * tg::kOctURow, nan);
         for (int o = 0; o < 4; ++o) {
           const size_t inst = grp * 4 + o;
           const bool ok = inst < n_inst && desc.instance(inst, I[o]) && takes(I[o]);
@@ -115,7 +115,7 @@ struct EmuBackend {
             I[o] = tg::SolveInst{};
             I[o].hbw = tg::kOctHbw;
           }
-          tg::octet_ws_bind(I[o], ws.data() + (size_t)o * oct_ws_doubles, us.data() + (size_t)o * np_cap * tg::kOctRow);
+          tg::octet_ws_bind(I[o], ws.data() + (size_t)o * oct_ws_doubles, us.data() + (size_t)o * np_cap * tg::kOctURow);
           nmax = std::max(nmax, I[o].np);
         }
         if (nmax > 0) tg::solve_octets(I, 0, nmax);
