@@ -32,6 +32,7 @@ constexpr int kOctRow = 20;    // doubles per banded row: 16 column slots (colum
 constexpr int kOctHbw = 7;
 constexpr int kOctMinNp = 8;
 constexpr int kOctRing = 16;   // rows of the shared-memory ring: two blocks of eight (row i at ((i >> 3) & 1) * 8 + (i & 7))
+constexpr int kOctStride = 22;  // doubles between ring rows: 176 B, so that the eight lanes of an octet hit eight different 16-byte bank groups
 constexpr int kOctURow = 12;   // doubles of a finished row kept for the back substitution: 1/pivot, U[i][i+1..i+7], 4 right-hand sides
 
 // Shared-memory doubles for one octet solve: row ring | slot table | row -> (vertex, slot) table.  Independent of the
@@ -39,7 +40,7 @@ constexpr int kOctURow = 12;   // doubles of a finished row kept for the back su
 // the elimination) and the U rows wait for the back substitution in a per-warp slab of global memory that stays in L2.
 // Sized = 2 (mod 16) so that the four octets of a warp start in different banks.
 TG_HD int octet_ws_doubles(int S, int np) {
-  int n = kOctRing * kOctRow + (5 * (S + 1) + 3) / 4 + (np + 3) / 4;
+  int n = kOctRing * kOctStride + (5 * (S + 1) + 3) / 4 + (np + 3) / 4;
   n = (n + 1) & ~1;
   while ((n & 15) != 2) n += 2;
   return n;
@@ -50,7 +51,7 @@ TG_HD void octet_ws_bind(SolveInst& I, double* ws, double* urows) {
   I.rows = ws;
   I.xs = urows;
   I.part = nullptr;
-  I.slot = (int16_t*)(ws + kOctRing * kOctRow);
+  I.slot = (int16_t*)(ws + kOctRing * kOctStride);
   I.rowva = I.slot + ((5 * (I.S + 1) + 3) / 4) * 4;
 }
 TG_HD int octet_ring_pos(int i) { return ((i >> 3) & 1) * 8 + (i & 7); }
@@ -140,7 +141,7 @@ TG_HD void octet_stage_block(const SolveInst& I, int sub, int blk) {
   if (i >= I.np) return;
   const int it = I.rowva[i];
   const int v = it / TG_HALF, a = it - v * TG_HALF;
-  double* row = I.rows + octet_ring_pos(i) * kOctRow;
+  double* row = I.rows + octet_ring_pos(i) * kOctStride;
   if (v > 0) octet_stage_row(row, solve_rec(I, v - 1) + TG_REC_H + (TG_HALF + a) * TG_N);  // 16-byte aligned: TG_REC_H and TG_N are even
   if (v < I.S) octet_stage_row(row + TG_N, solve_rec(I, v) + TG_REC_H + a * TG_N);
 }
@@ -152,7 +153,7 @@ TG_HD void octet_assemble_block(const SolveInst& I, int sub, int blk) {
   const int v = it / TG_HALF;
   double hp[TG_N], hc[TG_N];
   const bool has_p = v > 0, has_c = v < S;
-  double* row = I.rows + octet_ring_pos(i) * kOctRow;
+  double* row = I.rows + octet_ring_pos(i) * kOctStride;
 #pragma unroll
   for (int q = 0; q < TG_N; q += 2) {
     const Dbl2 t = *reinterpret_cast<const Dbl2*>(row + q), u = *reinterpret_cast<const Dbl2*>(row + TG_N + q);
@@ -198,7 +199,7 @@ TG_HD void octet_assemble_block(const SolveInst& I, int sub, int blk) {
 // back substitution: the stored U row i (global memory, L2) travels back into its ring position (first kOctURow doubles)
 TG_HD void octet_stage_urow(const SolveInst& I, int i) {
   if (i < 0 || i >= I.np) return;
-  double* dst = I.rows + octet_ring_pos(i) * kOctRow;
+  double* dst = I.rows + octet_ring_pos(i) * kOctStride;
   const double* src = I.xs + (size_t)i * kOctURow;
 #if defined(__CUDA_ARCH__)
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
@@ -290,7 +291,7 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
 #pragma unroll
         for (int d = 0; d < 4; ++d) st.x[d] = 0.0;
         if (st.myrow < I.np) {
-          octet_load_row(st, I.rows + octet_ring_pos(st.myrow) * kOctRow, 0);
+          octet_load_row(st, I.rows + octet_ring_pos(st.myrow) * kOctStride, 0);
         } else {
 #pragma unroll
           for (int q = 0; q < 16; ++q) st.reg[q] = 0.0;
@@ -336,7 +337,7 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
               store2(rk + 8, st.rhs[0], st.rhs[1]);
               store2(rk + 10, st.rhs[2], st.rhs[3]);
               st.myrow = k + 8;
-              if (st.myrow < I.np) octet_load_row(st, I.rows + octet_ring_pos(st.myrow) * kOctRow, flip);
+              if (st.myrow < I.np) octet_load_row(st, I.rows + octet_ring_pos(st.myrow) * kOctStride, flip);
             } else if (st.myrow < I.np) {  // rows k+1 .. min(np-1, k+7)
               const double l = st.reg[m] * rinv;
 #pragma unroll
@@ -365,7 +366,7 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
       octet_stage_urow(I, btop * 8 + sub);
       octet_stage_urow(I, (btop - 1) * 8 + sub);
       octet_stage_wait();
-      octet_load_urow_dyn(st, I.rows + octet_ring_pos(st.myrow) * kOctRow, st.myrow - jtop);
+      octet_load_urow_dyn(st, I.rows + octet_ring_pos(st.myrow) * kOctStride, st.myrow - jtop);
       if (st.myrow == np - 1) {
 #pragma unroll
         for (int d = 0; d < 4; ++d) st.x[d] = st.rhs[d] * st.rinv;
@@ -404,7 +405,7 @@ TG_HD void solve_octets(const SolveInst* insts, int lane, int nmax) {
 #pragma unroll
               for (int d = 0; d < 4; ++d) I.x_out[j * 4 + d] = st.x[d];  // the solution leaves through global memory
               st.myrow = j - 8;
-              if (st.myrow >= 0) octet_load_urow_static(st, I.rows + octet_ring_pos(st.myrow) * kOctRow, m - 8);  // row j-8: rel = m - 8
+              if (st.myrow >= 0) octet_load_urow_static(st, I.rows + octet_ring_pos(st.myrow) * kOctStride, m - 8);  // row j-8: rel = m - 8
             } else if (st.myrow >= 0 && st.myrow < j) {  // rows j-7 .. j-1
               const double a = st.reg[m];
 #pragma unroll
