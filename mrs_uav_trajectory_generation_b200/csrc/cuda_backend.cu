@@ -36,9 +36,9 @@ __global__ void __launch_bounds__(128) k_for_each(const F f, const size_t n) {
 
 // one thread per work item with F::kScratch doubles of per-thread scratch in dynamic shared memory, element i of thread
 // t at smem[i * blockDim.x + t] (bank-conflict free; used by the Jenkins-Traub work arrays)
-static_assert(TG_WARR_DEVICE_STRIDE == 128, "strided scratch kernels run 128 threads per block");
+static_assert(TG_WARR_DEVICE_STRIDE == 32, "strided scratch kernels run one warp per block");
 template <class F>
-__global__ void __launch_bounds__(128) k_for_each_scratch(const F f, const size_t n) {
+__global__ void __launch_bounds__(TG_WARR_DEVICE_STRIDE) k_for_each_scratch(const F f, const size_t n) {
   extern __shared__ double smem[];
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) f(i, smem + threadIdx.x, (int)blockDim.x);
@@ -310,7 +310,7 @@ struct CudaBackend {
   template <class F>
   void for_each_scratch(size_t n, const F& f) {
     if (n == 0) return;
-    const unsigned block = 128;
+    const unsigned block = TG_WARR_DEVICE_STRIDE;
     const size_t grid = (n + block - 1) / block;
     const size_t smem = (size_t)F::kScratch * sizeof(double) * block;
     TG_CUDA_CHECK(cudaFuncSetAttribute(k_for_each_scratch<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -354,7 +354,7 @@ struct CudaBackend {
   void for_each_scratch_on(int k, size_t n, const F& f) {
     if (profiling) return for_each_scratch(n, f);
     if (n == 0) return;
-    const unsigned block = 128;
+    const unsigned block = TG_WARR_DEVICE_STRIDE;
     const size_t grid = (n + block - 1) / block;
     const size_t smem = (size_t)F::kScratch * sizeof(double) * block;
     TG_CUDA_CHECK(cudaFuncSetAttribute(k_for_each_scratch<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -44,9 +44,11 @@ TG_HD double poly_eval_s(const double* __restrict__ c, double t) {
 #if defined(TG_JT_STATS)
 static thread_local long long tg_jt_stats[16];
 #endif
-// The device kernels that use it run 128 threads per block (cuda_backend.cu asserts it), so the stride is a
-// compile-time constant there and an element address is one shift-add.
-#define TG_WARR_DEVICE_STRIDE 128
+// The device kernels that use it run ONE WARP per block (cuda_backend.cu asserts it), so the stride is a compile-time
+// constant there and an element address is one shift-add.  One warp per block because a block keeps its shared memory
+// until its slowest thread is done, and Jenkins-Traub run times vary 3x between polynomials: with 128-thread blocks the
+// SMs averaged 3.4 resident warps out of 12 (profiles/r01_extrema_s10.md).
+#define TG_WARR_DEVICE_STRIDE 32
 struct WArr {
   double* b;
   int st;
