@@ -276,11 +276,14 @@ TG_HD double cost_partial(const double (&c)[TG_N], const double* __restrict__ Qg
 template <class D>
 struct CoefCostFn {
   D desc;
-  int per_inst;   // 4 * smax items per instance
+  int per_inst;   // 4 * smax: stride of `part` per instance
   double* part;   // [instances][per_inst]
-  TG_HD void operator()(size_t item) const {
-    const size_t inst = item / (size_t)per_inst;
-    const int it = (int)(item - inst * (size_t)per_inst);
+  size_t inst0;   // this launch covers instances inst0 .. with per_items (<= per_inst) items each: 4 * (largest S among them)
+  int per_items;
+  TG_HD void operator()(size_t item0) const {
+    const size_t inst = inst0 + item0 / (size_t)per_items;
+    const int it = (int)(item0 % (size_t)per_items);
+    const size_t item = inst * (size_t)per_inst + it;
     SolveInst I;
     if (!desc.instance(inst, I)) return;
     if (it >= I.S * TG_D) return;

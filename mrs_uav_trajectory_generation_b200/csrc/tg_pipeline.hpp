@@ -517,6 +517,8 @@ class Pipeline {
     size_t v0, v1;   // their vertices = Mellinger instances
     int ws, ows;     // workspace sizes (doubles): warp-per-instance routine, octet routine (0: not eligible)
     int np_cap;      // largest number of unknowns in the run
+    int s_cap;       // largest number of segments in the run
+    int kernel_cls;  // BE::solve_class of its members: consecutive runs of one class share a solve launch
   };
   std::vector<SolveBucket> make_buckets(int B, const int* seg_off, const int* np, const int* hbw, int ws_all, int ows_all, int np_all) const {
     std::vector<SolveBucket> out;
@@ -525,14 +527,16 @@ class Pipeline {
       const int S = seg_off[p + 1] - seg_off[p];
       const int ws = solve_ws_doubles(S, np[p], hbw[p]);
       const int ows = (hbw[p] == kOctHbw && np[p] >= kOctMinNp) ? octet_ws_doubles(S, np[p]) : 0;
-      const int cls = be_.solve_class(ws, ows);
+      // same kernel and resident warps (solve_class), and segment counts within one group of four: the U slab and the
+      // coefficient kernel's thread count are sized by the largest member of a run
+      const int cls = be_.solve_class(ws, ows) * 4096 + (S + 3) / 4;
       if (out.empty() || cls != cls_prev) {
         if (out.size() >= 32) {  // ragged input in no particular order: one launch pair for everything, sized by the batch maxima
-          out.assign(1, SolveBucket{0, B, 0, (size_t)seg_off[B] + B, ws_all, ows_all, np_all});
+          out.assign(1, SolveBucket{0, B, 0, (size_t)seg_off[B] + B, ws_all, ows_all, np_all, 0, 0});
           mixed_single_ = true;
           return out;
         }
-        out.push_back(SolveBucket{p, p, (size_t)seg_off[p] + p, 0, 0, 0, 0});
+        out.push_back(SolveBucket{p, p, (size_t)seg_off[p] + p, 0, 0, 0, 0, 0, cls / 4096});
         cls_prev = cls;
       }
       SolveBucket& k = out.back();
@@ -541,6 +545,7 @@ class Pipeline {
       k.ws = std::max(k.ws, ws);
       k.ows = std::max(k.ows, ows);
       k.np_cap = std::max(k.np_cap, np[p]);
+      k.s_cap = std::max(k.s_cap, S);
     }
     mixed_single_ = false;
     return out;
@@ -551,17 +556,45 @@ class Pipeline {
   void solve_with_outputs(size_t n_inst, const int* stats, const D& desc, const BatchPtrs& b, const std::vector<SolveBucket>* buckets = nullptr,
                           bool per_vertex = false) {
     if (buckets && !buckets->empty()) {
-      for (const SolveBucket& k : *buckets) {
-        const bool mixed = mixed_single_;  // a run is homogeneous by construction unless it is the collapsed one
-        if (per_vertex) be_.solve(k.v0, k.v1, k.ws, k.ows, k.np_cap, mixed, desc);
-        else be_.solve((size_t)k.p0, (size_t)k.p1, k.ws, k.ows, k.np_cap, mixed, desc);
+      // one solve launch per stretch of runs that go to the same kernel at the same residency (many small launches cost more
+      // in tails than tighter slabs gain: measured); a run is homogeneous by construction unless it is the collapsed one
+      const bool mixed = mixed_single_;
+      size_t a = 0;
+      int n_launch = 0;
+      while (a < buckets->size()) {
+        SolveBucket m = (*buckets)[a];
+        size_t e = a + 1;
+        while (e < buckets->size() && (*buckets)[e].kernel_cls == m.kernel_cls) {
+          const SolveBucket& k = (*buckets)[e];
+          m.p1 = k.p1;
+          m.v1 = k.v1;
+          m.ws = std::max(m.ws, k.ws);
+          m.ows = std::max(m.ows, k.ows);
+          m.np_cap = std::max(m.np_cap, k.np_cap);
+          ++e;
+        }
+        if (per_vertex) be_.solve(m.v0, m.v1, m.ws, m.ows, m.np_cap, mixed, desc);
+        else be_.solve((size_t)m.p0, (size_t)m.p1, m.ws, m.ows, m.np_cap, mixed, desc);
+        ++n_launch;
+        a = e;
       }
-      launches((int)buckets->size() - 1);
+      launches(n_launch - 1);
     } else {
       be_.solve(0, n_inst, stats[0], stats[2], stats[3], stats[6] > 0, desc);
     }
+    // coefficients + partial costs: one thread per (instance, segment, dimension); with runs, each run is launched over
+    // its own largest segment count instead of the group's
     const int per = 4 * b.smax;
-    be_.for_each(n_inst * (size_t)per, CoefCostFn<D>{desc, per, b.part});
+    if (buckets && buckets->size() > 1) {
+      for (const SolveBucket& k : *buckets) {
+        const size_t i0 = per_vertex ? k.v0 : (size_t)k.p0, i1 = per_vertex ? k.v1 : (size_t)k.p1;
+        const int items = 4 * std::max(k.s_cap, 1);
+        be_.for_each((i1 - i0) * (size_t)items, CoefCostFn<D>{desc, per, b.part, i0, items});
+      }
+      launches((int)buckets->size() - 1);
+    } else {
+      be_.for_each(n_inst * (size_t)per, CoefCostFn<D>{desc, per, b.part, 0, per});
+    }
     be_.for_each(n_inst, CostSumFn<D>{desc, per, b.part});
     launches(2);
   }
