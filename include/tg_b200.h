@@ -156,6 +156,18 @@ int tg_scale_times_batch(tg_ctx* ctx, int B, const int* seg_off, double* coef, d
 int tg_sweep_costs(tg_ctx* ctx, int V, const uint8_t* vmask, const double* vval, int r, long long K, const double* cand,
                    int cand_on_device, double* costs, long long* best_index, double* best_cost);
 
+/* tg_objective_batch = the objective functions of the time-allocation methods other than Mellinger's,
+ *   PolynomialOptimizationNonLinear<N>::objectiveFunctionTime (nl_impl.h:567-614; methods 0 kSquaredTime, 1 kRichterTime) and
+ *   objectiveFunctionTimeAndConstraints (nl_impl.h:651-722; methods 3, 4), with evaluateMaximumMagnitudeAsSoftConstraint
+ *   (nl_impl.h:740-762) over computeMaximumOfMagnitude, at K candidate vectors of ONE problem -- the batch a derivative-free
+ *   optimiser (the reference drives NLopt LN_BOBYQA, nl_impl.h:68-79) evaluates per iteration.  x[K][nvar]: S segment times,
+ *   then for methods 3/4 the free derivatives, dimension-major (4 x n_free) as getFreeConstraints returns them.
+ *   total[K] = cost_trajectory + cost_time + cost_soft_constraints; parts (optional) [K][3] = the three terms;
+ *   coef (optional) [K][S][4][10] = the segments of every candidate (getSegments after the objective call). */
+int tg_objective_batch(tg_ctx* ctx, int V, const uint8_t* vmask, const double* vval, int r, int time_alloc_method, long long K, const double* x,
+                       int nvar, double time_penalty, int use_soft_constraints, double soft_constraint_weight, int n_constraints,
+                       const int* con_derivative, const double* con_value, double* total, double* parts, double* coef);
+
 /* The steps either side of the path, batched, one path per thread --------------------------------
  * tg_preprocess_paths = MrsTrajectoryGeneration::preprocessPath (src/mrs_trajectory_generation.cpp:431-500): optional path
  *   straightener (config/public/trajectory_generation.yaml:20-23) then the min_waypoint_distance filter (:27).

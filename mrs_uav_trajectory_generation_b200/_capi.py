@@ -119,6 +119,8 @@ class Library:
         L.tg_sample_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_double, _ip, _dp, _dp]
         L.tg_evaluate_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, _dp, _u8p]
         L.tg_extrema_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+        L.tg_objective_batch.argtypes = [C.c_void_p, C.c_int, _u8p, _dp, C.c_int, C.c_int, C.c_longlong, _dp, C.c_int, C.c_double, C.c_int, C.c_double,
+                                         C.c_int, _ip, _dp, _dp, _dp, _dp]
         L.tg_max_magnitude_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_int, _dp, _dp, _ip]
         L.tg_scale_times_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp, _ip, _u8p]
         L.tg_sweep_costs.argtypes = [C.c_void_p, C.c_int, _u8p, _dp, C.c_int, C.c_longlong, _dp, C.c_int, _dp, _llp, _dp]
@@ -362,6 +364,22 @@ class Context:
         m = np.empty((len(times), 9))
         self._check(self.L.lib.tg_extrema_batch(self.h, len(times), _p(coef), _p(times), _p(m)))
         return m
+
+    def objective(self, mask, vals, r, method, x, time_penalty=500.0, use_soft=True, soft_weight=100.0, con_deriv=(), con_value=(),
+                  want_coef=False):
+        """objectiveFunctionTime / objectiveFunctionTimeAndConstraints (nl_impl.h:567-722) at K candidates -> total[K], parts[K][3]."""
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        K, nvar = x.shape
+        cd = np.ascontiguousarray(con_deriv, dtype=np.int32)
+        cv = np.ascontiguousarray(con_value, dtype=np.float64)
+        total, parts = np.empty(K), np.empty((K, 3))
+        coef = np.empty((K, len(mask) - 1, 4, 10)) if want_coef else None
+        self._check(self.L.lib.tg_objective_batch(self.h, len(mask), _p(mask, _u8p), _p(vals), int(r), int(method), K, _p(x), nvar, float(time_penalty),
+                                                  int(bool(use_soft)), float(soft_weight), len(cd), _p(cd, _ip), _p(cv), _p(total), _p(parts),
+                                                  _p(coef) if want_coef else None))
+        return (total, parts, coef) if want_coef else (total, parts)
 
     def max_magnitude(self, seg_off, coef, times, derivative):
         """computeMaximumOfMagnitude(derivative) per trajectory (lin_impl.h:477-508) -> time[B], value[B], segment_idx[B]."""

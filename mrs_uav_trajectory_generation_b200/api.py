@@ -185,13 +185,120 @@ class PolynomialOptimization:
 
 
 class NonlinearOptimizationParameters:
-    """nl.h:35-110 (the fields the Mellinger path reads)."""
+    """nl.h:35-110."""
+
+    kSquaredTime, kRichterTime, kMellingerOuterLoop, kSquaredTimeAndConstraints, kRichterTimeAndConstraints = 0, 1, 2, 3, 4
 
     def __init__(self):
         self.f_rel = 0.05
         self.x_rel = 0.1
         self.max_iterations = 10
-        self.time_alloc_method = 2  # kMellingerOuterLoop
+        self.time_alloc_method = 2  # kMellingerOuterLoop (the node's choice, node.cpp:881)
+        self.initial_stepsize_rel = 0.1  # nl.h:58
+        self.time_penalty = 500.0  # nl.h:73
+        self.use_soft_constraints = True  # nl.h:88
+        self.soft_constraint_weight = 100.0  # nl.h:91
+
+
+class DerivativeFreeTimeAllocation:
+    """PolynomialOptimizationNonLinear<10>::optimizeTime / optimizeTimeAndFreeConstraints (nl_impl.h:120-157, 429-536) for the
+    time-allocation methods 0, 1, 3, 4.
+
+    The reference hands objectiveFunctionTime / objectiveFunctionTimeAndConstraints to NLopt's LN_BOBYQA (nl_impl.h:68-79); NLopt is
+    not vendored, so -- as for LD_LBFGS on the Mellinger path ("parity unpinned") -- the objective, bounds, initial steps
+    and stopping rules are the reference's and the search itself is ours: a bound-constrained coordinate pattern search whose 2n trial
+    points per iteration are ONE batched objective call on the GPU (tg_objective_batch).  max_iterations counts those batched
+    iterations, not single evaluations.  Result codes as NLopt: 3 ftol_rel, 4 xtol_rel, 5 maxeval.
+    """
+
+    kTimeLowerBound = 0.01  # kOptimizationTimeLowerBound (nl.h:143)
+
+    def __init__(self, vertices, times, derivative_to_optimize, parameters, constraints, ctx=None):
+        self.ctx = ctx or default_context()
+        self.P = parameters
+        self.r = max(2, derivative_to_optimize)
+        _, self.mask, self.vals = pack_vertices([vertices])
+        self.times0 = np.asarray(times, dtype=np.float64)
+        self.S = len(self.times0)
+        self.constraints = list(constraints)  # (dimension, derivative, value) in the order they were added
+        self.with_free = parameters.time_alloc_method in (3, 4)
+
+    def _objective(self, x, want_coef=False):
+        cd = [c[1] for c in self.constraints]
+        cv = [c[2] for c in self.constraints]
+        return self.ctx.objective(self.mask, self.vals, self.r, self.P.time_alloc_method, x, self.P.time_penalty, self.P.use_soft_constraints,
+                                  self.P.soft_constraint_weight, cd, cv, want_coef=want_coef)
+
+    def _bounds(self, x0, free_slots):
+        n = len(x0)
+        lo, hi = np.full(n, -np.finfo(np.float64).max), np.full(n, np.finfo(np.float64).max)
+        lo[: self.S] = self.kTimeLowerBound
+        if self.with_free:  # setFreeEndpointDerivativeHardConstraints (nl_impl.h:764-805)
+            n_free = len(free_slots)
+            for dim, deriv, value in self.constraints:
+                for j, (_, slot_deriv) in enumerate(free_slots):
+                    if slot_deriv == deriv:
+                        lo[self.S + dim * n_free + j] = -abs(value)
+                        hi[self.S + dim * n_free + j] = abs(value)
+        # "Check if initial solution isn't already out of bounds" (nl_impl.h:497-503)
+        lo = np.minimum(lo, x0)
+        hi = np.maximum(hi, x0)
+        return lo, hi
+
+    def optimize(self):
+        x = self.times0.copy()
+        free_slots = []
+        if self.with_free:
+            # initial solution: solveLinear + getFreeConstraints (nl_impl.h:436-462), dimension-major
+            # (read off the solved segments: derivative k at a vertex = k! c_k of the segment that starts there, or the
+            # last segment's polynomial at its end)
+            vtx_off = np.array([0, len(self.mask)], dtype=np.int32)
+            coef, _ = self.ctx.solve_linear_batch(vtx_off, self.mask, self.vals, self.times0, self.r)
+            fact = [1.0, 1.0, 2.0, 6.0, 24.0]
+            for v in range(len(self.mask)):
+                for k in range(5):
+                    if not (self.mask[v] >> k) & 1:
+                        free_slots.append((v, k))
+            dp = np.zeros((D, len(free_slots)))
+            for j, (v, k) in enumerate(free_slots):
+                for d in range(D):
+                    if v < self.S:
+                        dp[d, j] = fact[k] * coef[v, d, k]
+                    else:
+                        c, T, acc = coef[self.S - 1, d], self.times0[-1], 0.0
+                        for i in range(N - 1, k - 1, -1):
+                            acc = acc * T + np.prod(np.arange(i - k + 1, i + 1, dtype=np.float64)) * c[i]
+                        dp[d, j] = acc
+            x = np.concatenate([x, dp.reshape(-1)])
+        n = len(x)
+        lo, hi = self._bounds(x, free_slots)
+        step = np.where(np.abs(x) <= np.finfo(np.float64).eps, 1e-13, self.P.initial_stepsize_rel * np.abs(x))  # nl_impl.h:488-495
+        f = float(self._objective(x[None, :])[0][0])
+        self.n_iterations, code = 0, 5
+        while self.n_iterations < self.P.max_iterations:
+            self.n_iterations += 1
+            cand = np.repeat(x[None, :], 2 * n, axis=0)
+            idx = np.arange(n)
+            cand[idx, idx] = np.minimum(x + step, hi)
+            cand[n + idx, idx] = np.maximum(x - step, lo)
+            tot, _ = self._objective(cand)
+            k = int(np.argmin(tot))  # first minimum
+            if tot[k] < f:
+                f_old, f = f, float(tot[k])
+                x = cand[k].copy()
+                if abs(f_old - f) <= self.P.f_rel * abs(f):  # NLopt ftol_rel
+                    code = 3
+                    break
+            else:
+                step *= 0.5
+                if np.all(step <= self.P.x_rel * np.abs(x)):  # NLopt xtol_rel
+                    code = 4
+                    break
+        self.x, self.cost = x, f
+        tot, parts, coef = self._objective(x[None, :], want_coef=True)
+        self.cost_parts = parts[0]
+        self.coef, self.times = coef[0], x[: self.S].copy()
+        return code
 
 
 class PolynomialOptimizationNonLinear:
@@ -215,9 +322,22 @@ class PolynomialOptimizationNonLinear:
         group = 0 if dimension <= 1 else (1 if dimension == 2 else 2)
         idx = {(0, 1): 0, (1, 1): 1, (0, 2): 2, (1, 2): 3, (0, 3): 4, (1, 3): 5, (2, 1): 6, (2, 2): 7, (2, 3): 8}[(group, derivative)]
         self._limits[idx] = float(maximum_value)
+        if hasattr(self, "_constraints"):
+            self._constraints.append((int(dimension), int(derivative), float(maximum_value)))
         return True
 
+    def setupFromVertices(self, vertices, times, derivative_to_optimize):  # nl_impl.h:51-82
+        """Vertices + initial segment times, for the derivative-free methods 0/1/3/4 (optimizeTime, optimizeTimeAndFreeConstraints)."""
+        self._vertices, self._times0, self._r = list(vertices), np.asarray(times, dtype=np.float64), derivative_to_optimize
+        self._constraints = []
+        return len(self._vertices) == len(self._times0) + 1
+
     def optimize(self):  # nl_impl.h:89-118 -> returns the nlopt-style code
+        if self.params.time_alloc_method != NonlinearOptimizationParameters.kMellingerOuterLoop:
+            self._dfo = DerivativeFreeTimeAllocation(self._vertices, self._times0, self._r, self.params, self._constraints, ctx=self._gen.ctx)
+            code = self._dfo.optimize()
+            self._dfo_trajectory = Trajectory(self._dfo.coef, self._dfo.times, self._gen.ctx)
+            return code
         p = self._gen.params(derivative_to_optimize=self._r, max_evals=self.params.max_iterations, f_rel=self.params.f_rel,
                              x_rel=self.params.x_rel, check_deviation=0,
                              limits=[l if l is not None else 3.4028234663852886e38 for l in self._limits])
@@ -225,6 +345,8 @@ class PolynomialOptimizationNonLinear:
         return int(self.result.results["nlopt_code"][0])
 
     def getTrajectory(self):
+        if self.params.time_alloc_method != NonlinearOptimizationParameters.kMellingerOuterLoop:
+            return self._dfo_trajectory
         return self.result.trajectory(0)
 
 

@@ -245,6 +245,27 @@ int tg_max_magnitude_batch(tg_ctx* ctx, int B, const int* seg_off, const double*
   });
 }
 
+int tg_objective_batch(tg_ctx* ctx, int V, const uint8_t* vmask, const double* vval, int r, int time_alloc_method, long long K, const double* x,
+                       int nvar, double time_penalty, int use_soft_constraints, double soft_constraint_weight, int n_constraints,
+                       const int* con_derivative, const double* con_value, double* total, double* parts, double* coef) {
+  return tg_guard(ctx, [&]() -> int {
+    if (V < 2 || !vmask || !vval || r < 2 || r > 4 || K < 1 || !x || !total || (n_constraints > 0 && (!con_derivative || !con_value))) {
+      ctx->err = "invalid argument";
+      return TG_ERR_INVALID;
+    }
+    ctx->be.timer_start();
+    const int rc = ctx->pipe.objective_batch(V, vmask, vval, r, time_alloc_method, K, x, nvar, time_penalty, use_soft_constraints,
+                                             soft_constraint_weight, n_constraints, con_derivative, con_value, total, parts, coef);
+    ctx->last_ms = ctx->be.timer_stop();
+    if (rc != 0) {
+      ctx->err = rc == -2 ? "nvar must be S (methods 0, 1) or S + 4 * n_free (methods 3, 4)"
+                          : (rc == -3 ? "at most 16 constraints, derivatives 1..4, non-zero values" : "time_alloc_method must be 0, 1, 3 or 4");
+      return TG_ERR_INVALID;
+    }
+    return TG_OK;
+  });
+}
+
 int tg_scale_times_batch(tg_ctx* ctx, int B, const int* seg_off, double* coef, double* times, const double* limits9, int* passes,
                          uint8_t* within) {
   return tg_guard(ctx, [&]() -> int {

@@ -219,6 +219,7 @@ struct SolveSweepDesc {
   BatchPtrs b;  // a batch holding the single problem
   const double* recs;
   double* costs;
+  double* coefs = nullptr;  // optional [K][S][4][10]
   TG_HD bool instance(size_t k, SolveInst& I) const {
     const int S = b.seg_off[1] - b.seg_off[0];
     I.S = S;
@@ -231,7 +232,7 @@ struct SolveSweepDesc {
     I.vfree = b.vfree;
     I.vval = b.vval;
     I.recs = recs + k * (size_t)S * TG_REC_SIZE;
-    I.coef_out = nullptr;
+    I.coef_out = coefs ? coefs + k * (size_t)S * TG_D * TG_N : nullptr;
     I.cost_out = costs + k;
     I.dp_out = nullptr;
     I.x_out = b.xs ? b.xs + k * (size_t)b.xstride : nullptr;
@@ -243,6 +244,69 @@ struct SetupSweepFn {
   const double* cand;  // [K][S]
   double* recs;
   TG_HD void operator()(size_t item) const { setup_segment_record(cand[item], r, recs + item * TG_REC_SIZE); }
+};
+
+// objective functions of the time-allocation methods 0/1/3/4 (nl_impl.h:567-722), K candidates x[K][nvar] of one problem:
+// records and contiguous segment times from the first S entries of every candidate
+struct SetupObjFn {
+  int S, r, nvar;
+  const double* x;
+  double* recs;   // [K][S]
+  double* times;  // [K][S]
+  TG_HD void operator()(size_t item) const {
+    const size_t k = item / (size_t)S;
+    const int s = (int)(item - k * (size_t)S);
+    const double T = x[k * (size_t)nvar + s];
+    times[item] = T;
+    setup_segment_record(T, r, recs + item * TG_REC_SIZE);
+  }
+};
+// setFreeConstraints (lin_impl.h:513-522): the free derivatives of candidate k, x[k][S + d * n_free + j], into the solution
+// layout [j][d] that CoefCostFn reads
+struct FillFreeFn {
+  int S, nvar, n_free, xstride;
+  const double* x;
+  double* xs;
+  TG_HD void operator()(size_t item) const {
+    const size_t k = item / (size_t)(n_free * TG_D);
+    const int rem = (int)(item - k * (size_t)(n_free * TG_D)), j = rem / TG_D, d = rem - j * TG_D;
+    xs[k * (size_t)xstride + j * TG_D + d] = x[k * (size_t)nvar + S + (size_t)d * n_free + j];
+  }
+};
+// total = cost_trajectory + cost_time + cost_soft_constraints (nl_impl.h:613, 721); soft constraints as
+// min(maximum_cost, exp(relative_violation * weight)) summed in constraint order (nl_impl.h:740-762), the maxima of the
+// distinct derivatives precomputed per candidate (maxval[derivative - 1][k])
+struct ObjCombineFn {
+  int S, method, ncon;
+  double time_penalty, soft_weight;
+  int use_soft;
+  const double* times;   // [K][S]
+  const double* costs;   // [K] trajectory cost
+  const double* maxval;  // [4][K]
+  size_t K;
+  int con_deriv[16];
+  double con_value[16];
+  double* total;
+  double* parts;  // optional [K][3]
+  TG_HD void operator()(size_t k) const {
+    const double cost_traj = costs[k];
+    double total_time = 0.0;
+    for (int s = 0; s < S; ++s) total_time = total_time + times[k * (size_t)S + s];
+    const double cost_time = (method == 1 || method == 4) ? total_time * time_penalty : total_time * total_time * time_penalty;
+    double cost_con = 0.0;
+    if (use_soft)
+      for (int c = 0; c < ncon; ++c) {
+        const double abs_violation = maxval[(size_t)(con_deriv[c] - 1) * K + k] - con_value[c];
+        const double relative_violation = abs_violation / con_value[c];
+        cost_con = cost_con + dmin(1.0e12, tgdm::dexp(relative_violation * soft_weight));
+      }
+    if (parts) {
+      parts[3 * k + 0] = cost_traj;
+      parts[3 * k + 1] = cost_time;
+      parts[3 * k + 2] = cost_con;
+    }
+    total[k] = cost_traj + cost_time + cost_con;
+  }
 };
 
 // ---- 4b. coefficients and cost from the solutions of the reduced systems ---------------------------------------------

@@ -929,6 +929,103 @@ class Pipeline {
     if (costs) be_.d2h(costs, d_costs, sizeof(double) * (size_t)K);
     return true;
   }
+  // objectiveFunctionTime / objectiveFunctionTimeAndConstraints (nl_impl.h:567-722) of ONE problem at K candidate vectors.
+  // method 0/1: x = S times (update + solve); 3/4: x = S times + 4 * n_free free derivatives (update + setFreeConstraints).
+  // Returns 0, or a negative value: -1 bad sizes / method, -2 nvar does not match the problem, -3 too many / bad constraints.
+  int objective_batch(int V, const uint8_t* vmask, const double* vval, int r, int method, long long K, const double* x, int nvar,
+                      double time_penalty, int use_soft, double soft_weight, int ncon, const int* con_deriv, const double* con_value,
+                      double* total, double* parts, double* coef) {
+    scratch_.reset();
+    const int S = V - 1;
+    if (S < 1 || K < 1 || !(method == 0 || method == 1 || method == 3 || method == 4)) return -1;
+    if (ncon < 0 || ncon > 16) return -3;
+    bool need[4] = {false, false, false, false};
+    for (int c = 0; c < ncon; ++c) {
+      if (con_deriv[c] < 1 || con_deriv[c] > 4 || !(con_value[c] != 0.0)) return -3;
+      need[con_deriv[c] - 1] = true;
+    }
+    const int so[2] = {0, S};
+    Bare bb = bare_batch(1, so, r);
+    BatchPtrs& b = bb.b;
+    b.vmask = scratch_.template alloc<uint8_t>(V);
+    b.vval = scratch_.template alloc<double>((size_t)V * TG_HALF * TG_D);
+    b.vfree = scratch_.template alloc<int>((size_t)V + 1);
+    b.np = scratch_.template alloc<int>(1);
+    b.hbw = scratch_.template alloc<int>(1);
+    be_.h2d(b.vmask, vmask, V);
+    be_.h2d(b.vval, vval, sizeof(double) * (size_t)V * TG_HALF * TG_D);
+    be_.for_each(1, PrepareFn{b, 0}); launches(1);
+    int stats[8];
+    be_.d2h(stats, b.stats, sizeof(stats));
+    const int n_free = stats[3];
+    if (nvar != ((method >= 3) ? S + TG_D * n_free : S)) return -2;
+    const long long chunk = std::min<long long>(K, (long long)objective_chunk);
+    alloc_solution_buffers(b, (size_t)chunk, stats);
+    double* d_recs = scratch_.template alloc<double>((size_t)chunk * S * TG_REC_SIZE);
+    double* d_T = scratch_.template alloc<double>((size_t)chunk * S);
+    double* d_coef = scratch_.template alloc<double>((size_t)chunk * S * TG_D * TG_N);
+    double* d_x = scratch_.template alloc<double>((size_t)chunk * nvar);
+    double* d_costs = scratch_.template alloc<double>((size_t)chunk);
+    double* d_sv = scratch_.template alloc<double>((size_t)chunk * S);
+    double* d_st = scratch_.template alloc<double>((size_t)chunk * S);
+    double* d_max = scratch_.template alloc<double>((size_t)4 * chunk);
+    double* d_mt = scratch_.template alloc<double>((size_t)chunk);
+    int* d_mi = scratch_.template alloc<int>((size_t)chunk);
+    int* d_off = scratch_.template alloc<int>((size_t)chunk + 1);
+    double* d_total = scratch_.template alloc<double>((size_t)chunk);
+    double* d_parts = parts ? scratch_.template alloc<double>((size_t)chunk * 3) : nullptr;
+    {
+      std::vector<int> off((size_t)chunk + 1);
+      for (long long k = 0; k <= chunk; ++k) off[(size_t)k] = (int)(k * S);
+      be_.h2d(d_off, off.data(), sizeof(int) * ((size_t)chunk + 1));
+    }
+    for (long long k0 = 0; k0 < K; k0 += chunk) {
+      const long long kc = std::min(chunk, K - k0);
+      be_.h2d(d_x, x + (size_t)k0 * nvar, sizeof(double) * (size_t)kc * nvar);
+      be_.for_each((size_t)kc * S, SetupObjFn{S, r, nvar, d_x, d_recs, d_T});
+      launches(1);
+      SolveSweepDesc desc{b, d_recs, d_costs, d_coef};
+      if (method >= 3) {
+        if (n_free > 0) be_.for_each((size_t)kc * n_free * TG_D, FillFreeFn{S, nvar, n_free, b.xstride, d_x, b.xs});
+        const int per = 4 * b.smax;
+        be_.for_each((size_t)kc * (size_t)per, CoefCostFn<SolveSweepDesc>{desc, per, b.part, 0, per});
+        be_.for_each((size_t)kc, CostSumFn<SolveSweepDesc>{desc, per, b.part});
+        launches(3);
+      } else {
+        solve_with_outputs((size_t)kc, stats, desc, b);
+        launches(1);
+        counters.solves += kc;
+      }
+      counters.segment_setups += kc * S;
+      if (use_soft)
+        for (int kd = 1; kd <= 4; ++kd) {
+          if (!need[kd - 1]) continue;
+          const size_t n = (size_t)kc * S;
+          switch (kd) {
+            case 1: be_.for_each_scratch(n, MaxMagnitudeSegFn<1>{d_coef, d_T, d_sv, d_st}); break;
+            case 2: be_.for_each_scratch(n, MaxMagnitudeSegFn<2>{d_coef, d_T, d_sv, d_st}); break;
+            case 3: be_.for_each_scratch(n, MaxMagnitudeSegFn<3>{d_coef, d_T, d_sv, d_st}); break;
+            default: be_.for_each_scratch(n, MaxMagnitudeSegFn<4>{d_coef, d_T, d_sv, d_st}); break;
+          }
+          be_.for_each((size_t)kc, MaxMagnitudeReduceFn{d_off, d_sv, d_st, d_max + (size_t)(kd - 1) * chunk, d_mt, d_mi});
+          launches(2);
+          counters.root_finds += (long long)n;
+          counters.root_finds_executed += (long long)n;
+        }
+      ObjCombineFn cf{S, method, ncon, time_penalty, soft_weight, use_soft, d_T, d_costs, d_max, (size_t)chunk, {}, {}, d_total, d_parts};
+      for (int c = 0; c < ncon; ++c) {
+        cf.con_deriv[c] = con_deriv[c];
+        cf.con_value[c] = con_value[c];
+      }
+      be_.for_each((size_t)kc, cf);
+      launches(1);
+      be_.d2h(total + k0, d_total, sizeof(double) * (size_t)kc);
+      if (parts) be_.d2h(parts + 3 * (size_t)k0, d_parts, sizeof(double) * 3 * (size_t)kc);
+      if (coef) be_.d2h(coef + (size_t)k0 * S * TG_D * TG_N, d_coef, sizeof(double) * (size_t)kc * S * TG_D * TG_N);
+    }
+    return 0;
+  }
+  size_t objective_chunk = (size_t)1 << 15;
   size_t sweep_chunk = (size_t)1 << 17;
 
  private:

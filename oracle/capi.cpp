@@ -388,4 +388,65 @@ void orc_sweep_costs(int V, const uint8_t* mask, const double* vals, int r, int 
   for (auto& t : th) t.join();
 }
 
+
+// The objective functions of the time-allocation methods other than Mellinger's (nl_impl.h:567-614 objectiveFunctionTime,
+// 651-722 objectiveFunctionTimeAndConstraints, 740-762 evaluateMaximumMagnitudeAsSoftConstraint, 724-738
+// evaluateMaximumMagnitudeConstraint -> computeMaximumOfMagnitude over all dimensions), for K candidate vectors x of ONE
+// problem.  method: 0 kSquaredTime, 1 kRichterTime (x = S segment times: updateSegmentTimes + solveLinear), 3 / 4 the
+// ...AndConstraints variants (x = S times then kD * n_free free constraints: updateSegmentTimes + setFreeConstraints).
+// parts[k] = {cost_trajectory, cost_time, cost_soft_constraints}; total = their sum in that order (nl_impl.h:613, 721).
+void orc_objective(int V, const uint8_t* mask, const double* vals, int r, int method, int K, const double* x, int nvar, double time_penalty,
+                   int use_soft, double soft_weight, int ncon, const int* con_deriv, const double* con_value, double* total, double* parts,
+                   int nthreads) {
+  if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+  const int S = V - 1;
+  std::atomic<int> next(0);
+  const std::vector<Vertex> vs = make_vertices(V, mask, vals);
+  auto work = [&]() {
+    LinearSolver ls;
+    bool ready = false;
+    for (;;) {
+      const int k0 = next.fetch_add(16);
+      if (k0 >= K) break;
+      for (int k = k0; k < std::min(K, k0 + 16); ++k) {
+        const double* xk = x + (size_t)k * nvar;
+        std::vector<double> t(xk, xk + S);
+        if (!ready) { ls.setup(vs, t, r); ready = true; } else ls.update_times(t);
+        if (method >= 3) {
+          for (int d = 0; d < kD; ++d)
+            for (int i = 0; i < ls.n_free; ++i) ls.d_p[(size_t)d * ls.n_free + i] = xk[S + (size_t)d * ls.n_free + i];
+          ls.segments_from_compact();
+        } else {
+          ls.solve();
+        }
+        const double cost_traj = ls.cost();
+        double total_time = 0;
+        for (int i = 0; i < S; ++i) total_time += t[i];
+        const double cost_time = (method == 1 || method == 4) ? total_time * time_penalty : total_time * total_time * time_penalty;
+        double cost_con = 0;
+        if (use_soft) {
+          for (int c = 0; c < ncon; ++c) {
+            double tm, val;
+            int idx;
+            max_of_magnitude(ls.seg, con_deriv[c], &tm, &val, &idx);
+            const double abs_violation = val - con_value[c];
+            const double relative_violation = abs_violation / con_value[c];
+            cost_con += std::min(1.0e12, m_exp(relative_violation * soft_weight));
+          }
+        }
+        if (parts) {
+          parts[(size_t)k * 3 + 0] = cost_traj;
+          parts[(size_t)k * 3 + 1] = cost_time;
+          parts[(size_t)k * 3 + 2] = cost_con;
+        }
+        total[k] = cost_traj + cost_time + cost_con;
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < nthreads; ++i) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+}
+
 }  // extern "C"

@@ -337,6 +337,21 @@ def optimize_batch(wp_off, wp, stop_at=None, init=None, params=None, cap_wp=64, 
     return dict(res=res, wp=wp_out, times=times, coeffs=coeffs, samples=smp, threads=used)
 
 
+def objective(mask, vals, r, method, x, time_penalty=500.0, use_soft=True, soft_weight=100.0, con_deriv=(), con_value=(), nthreads=0):
+    """objectiveFunctionTime / objectiveFunctionTimeAndConstraints (nl_impl.h:567-722) at K candidate vectors -> total[K], parts[K][3]."""
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    K, nvar = x.shape
+    cd = np.ascontiguousarray(con_deriv, dtype=np.int32)
+    cv = np.ascontiguousarray(con_value, dtype=np.float64)
+    total, parts = np.zeros(K), np.zeros((K, 3))
+    lib().orc_objective(len(mask), _ptr(mask, C.POINTER(C.c_uint8)), _ptr(vals), int(r), int(method), K, _ptr(x), nvar, C.c_double(time_penalty),
+                        int(bool(use_soft)), C.c_double(soft_weight), len(cd), _ptr(cd, C.POINTER(C.c_int)), _ptr(cv), _ptr(total), _ptr(parts),
+                        int(nthreads))
+    return total, parts
+
+
 def sweep_costs(mask, vals, r, cand_times, nthreads=0):
     mask = np.ascontiguousarray(mask, dtype=np.uint8)
     vals = np.ascontiguousarray(vals, dtype=np.float64)

@@ -224,6 +224,84 @@ def check_max_magnitude(ctx, seed=11, B=9):
     return exact
 
 
+def check_objectives(ctx, seed=5, K=24):
+    """Objective functions of the time-allocation methods 0/1/3/4 (nl_impl.h:567-722) at K candidates, soft constraints through
+    computeMaximumOfMagnitude: total and the three terms against the oracle."""
+    rng = np.random.default_rng(seed)
+    exact = True
+    con_deriv = [1, 2, 3, 1, 2, 3]           # the node adds (dimension, derivative) pairs; only the derivative matters (lin_impl.h:407-409)
+    con_value = [4.0, 2.0, 20.0, 2.0, 1.0, 20.0]
+    for kind, V in ((0, 6), (1, 11), (2, 4)):
+        m, v, t = random_linear_problem(rng, V, kind=kind)
+        S = V - 1
+        c0, _, dp0, _ = O.solve_linear(m, v, t, 2)
+        n_free = dp0.shape[1]
+        for method in (0, 1, 3, 4):
+            xt = t[None, :] * np.exp(rng.uniform(-0.3, 0.3, size=(K, S)))
+            if method >= 3:
+                xf = dp0.reshape(1, -1) * (1.0 + 0.05 * rng.standard_normal((K, 4 * n_free)))
+                x = np.concatenate([xt, xf], axis=1)
+            else:
+                x = xt
+            for soft in (True, False):
+                tot, parts = ctx.objective(m, v, 2, method, x, 500.0, soft, 100.0, con_deriv, con_value)
+                rtot, rparts = O.objective(m, v, 2, method, x, 500.0, soft, 100.0, con_deriv, con_value)
+                assert np.allclose(tot, rtot, rtol=1e-9, atol=0), (kind, method, soft)
+                assert np.allclose(parts, rparts, rtol=1e-9, atol=1e-300)
+                exact = exact and np.array_equal(tot, rtot) and np.array_equal(parts, rparts)
+        # the unperturbed solution of solveLinear is a stationary point of the trajectory cost in the free derivatives:
+        # method 3 at (t, d_p*) has the same trajectory cost as method 0 at t
+        x0 = t[None, :]
+        x3 = np.concatenate([x0, dp0.reshape(1, -1)], axis=1)
+        a, pa = ctx.objective(m, v, 2, 0, x0, 500.0, False)
+        b, pb = ctx.objective(m, v, 2, 3, x3, 500.0, False)
+        assert abs(pa[0, 0] - pb[0, 0]) <= 1e-9 * abs(pa[0, 0])
+    return exact
+
+
+def check_derivative_free_time_allocation(ctx):
+    """Methods 0/1/3/4 through the reference-shaped class: the search only ever accepts improvements of the reference's objective, stays
+    inside the bounds, and returns the segments of its final point (checked against the oracle's objective at that point)."""
+    import mrs_uav_trajectory_generation_b200.api as A
+
+    wps = [(0, 0, 1, 0), (2, 0.5, 1.2, 0.1), (4, -0.5, 1.0, 0.2), (6, 0.5, 1.1, 0.1), (8, 0, 1, 0)]
+    verts = []
+    for i, w in enumerate(wps):
+        v = A.Vertex(4)
+        if i in (0, len(wps) - 1):
+            v.makeStartOrEnd(np.array(w, dtype=np.float64), 2)
+        else:
+            v.addConstraint(0, np.array(w, dtype=np.float64))
+        verts.append(v)
+    t0 = np.full(len(wps) - 1, 1.5)
+    for method in (0, 1, 3, 4):
+        P = A.NonlinearOptimizationParameters()
+        P.time_alloc_method = method
+        P.max_iterations = 12
+        P.f_rel = 1e-4
+        opt = A.PolynomialOptimizationNonLinear(4, P, ctx=ctx)
+        assert opt.setupFromVertices(verts, t0, 2)
+        for dim in range(3):
+            opt.addMaximumMagnitudeConstraint(dim, 1, 3.0)
+            opt.addMaximumMagnitudeConstraint(dim, 2, 2.0)
+        code = opt.optimize()
+        assert code in (3, 4, 5)
+        dfo = opt._dfo
+        _, mask, vals = A.pack_vertices([verts])
+        cd = [c[1] for c in dfo.constraints]
+        cv = [c[2] for c in dfo.constraints]
+        x0 = t0 if method < 3 else None
+        rt, rp = O.objective(mask, vals, 2, method, dfo.x[None, :], P.time_penalty, True, P.soft_constraint_weight, cd, cv)
+        assert abs(rt[0] - dfo.cost) <= 1e-9 * abs(rt[0])
+        if x0 is not None:
+            r0, _ = O.objective(mask, vals, 2, method, x0[None, :], P.time_penalty, True, P.soft_constraint_weight, cd, cv)
+            assert dfo.cost <= r0[0]
+        assert np.all(dfo.x[: len(t0)] >= 0.01)
+        traj = opt.getTrajectory()
+        assert traj.coef.shape == (len(t0), 4, 10) and np.array_equal(traj.times, dfo.x[: len(t0)])
+    return True
+
+
 def compare_optimize(ctx, wp_off, wp, stop_at=None, init=None, params_kw=None, cap_wp=1400, cap_samples=6000):
     """Runs the full optimize() pipeline on both sides; asserts parity; returns (results, bit_exact, worst_coef_err)."""
     params_kw = params_kw or {}

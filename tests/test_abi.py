@@ -18,7 +18,7 @@ def _declared_symbols():
 def test_header_declares_the_expected_surface():
     syms = _declared_symbols()
     for s in ("tg_ctx_create", "tg_optimize_batch", "tg_fetch_outputs", "tg_solve_linear_batch", "tg_time_alloc_batch", "tg_sample_batch",
-              "tg_evaluate_batch", "tg_extrema_batch", "tg_max_magnitude_batch", "tg_scale_times_batch", "tg_sweep_costs"):
+              "tg_evaluate_batch", "tg_extrema_batch", "tg_max_magnitude_batch", "tg_objective_batch", "tg_scale_times_batch", "tg_sweep_costs"):
         assert s in syms
 
 

@@ -33,6 +33,14 @@ def test_evaluate(emu_ctx, oracle):
     assert PC.check_evaluate(emu_ctx)
 
 
+def test_objectives_of_the_other_time_allocation_methods(emu_ctx, oracle):
+    assert PC.check_objectives(emu_ctx)
+
+
+def test_derivative_free_time_allocation(emu_ctx, oracle):
+    assert PC.check_derivative_free_time_allocation(emu_ctx)
+
+
 def test_max_magnitude(emu_ctx, oracle):
     assert PC.check_max_magnitude(emu_ctx)
 

@@ -40,6 +40,14 @@ def test_evaluate(gpu_ctx, oracle):
     assert PC.check_evaluate(gpu_ctx)
 
 
+def test_objectives_of_the_other_time_allocation_methods(gpu_ctx, oracle):
+    assert PC.check_objectives(gpu_ctx)
+
+
+def test_derivative_free_time_allocation(gpu_ctx, oracle):
+    assert PC.check_derivative_free_time_allocation(gpu_ctx)
+
+
 def test_max_magnitude(gpu_ctx, oracle):
     assert PC.check_max_magnitude(gpu_ctx)
 
