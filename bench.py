@@ -250,10 +250,18 @@ def main():
         else:
             flops = None
         hbm_peak, how = load_peaks()
+        traffic, traffic_note = None, None
+        try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (never measured under the bench itself)
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+                tr = json.load(f).get(name)
+            if tr:
+                traffic, traffic_note = tr["bytes_per_launch"], "ncu dram__bytes_read.sum + dram__bytes_write.sum, " + tr["launch"] + " (profiles/r01_final_ncu_kernels.md)"
+        except Exception:
+            pass
         if flops is not None:
             achieved = flops / (ms * 1e-3) / 1e12
             roofline = {"bound": "fp64", "kernel": name, "achieved": achieved, "peak": fp64_nofma, "unit": "TFLOP/s",
-                        "frac": achieved / fp64_nofma if fp64_nofma else None, "traffic": None,
+                        "frac": achieved / fp64_nofma if fp64_nofma else None, "traffic": traffic, "traffic_note": traffic_note,
                         "avg_launch_ms": ms / launches, "launches": launches, "share_of_step": ms / tot_ms,
                         "peak_note": f"FP64 pipe measured live: DMUL+DADD (-fmad=false mix) {fp64_nofma:.2f} TFLOP/s, DFMA {fp64_fma:.2f} TFLOP/s; "
                                      f"HBM {hbm_peak} GB/s ({how}) is not the bound for this path (SURVEY.md 8d)",

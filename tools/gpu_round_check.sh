@@ -1,10 +1,21 @@
-set -x
+# Full evidence run on one B200 (under gpurun): parity tests, both bench arms, the ncu launch list of the bench command and
+# ncu --set full captures of the dominant kernels.  usage: bash tools/gpu_round_check.sh <tag>
+tag=${1:-final}
 nproc
-(time timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/s3_pytest.log 2>&1; tail -3 gpurun_out/s3_pytest.log
-timeout 600 python bench.py > gpurun_out/s3_bench.json 2> gpurun_out/s3_bench.err; tail -c 600 gpurun_out/s3_bench.json
-timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/s3_bench_ref.json 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/s3_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-profile > gpurun_out/s3_ncu_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_solve_oct -s 30 -c 2 -o gpurun_out/s3_solve python tools/prof_driver.py 65536 > gpurun_out/s3_ncu_solve.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:ExtremaRawFn.1 -s 3 -c 2 -o gpurun_out/s3_extrema python tools/prof_driver.py 65536 > gpurun_out/s3_ncu_extrema.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"CoefCostFn|SetupMellingerFn" -s 20 -c 2 -o gpurun_out/s3_coef python tools/prof_driver.py 65536 > gpurun_out/s3_ncu_coef.log 2>&1
-ls -la gpurun_out
+(time timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/${tag}_pytest.log 2>&1; tail -3 gpurun_out/${tag}_pytest.log
+timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 400 gpurun_out/${tag}_bench.json
+timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-profile > gpurun_out/${tag}_ncu_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_solve_oct -s 3 -c 1 -o gpurun_out/${tag}_solve_r0 python tools/prof_driver.py 65536 > gpurun_out/${tag}_ncu_solve_r0.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_solve_oct -s 13 -c 1 -o gpurun_out/${tag}_solve_r1 python tools/prof_driver.py 65536 > gpurun_out/${tag}_ncu_solve_r1.log 2>&1
+for pat in "CoefCostFn" "SetupMellingerFn" "ExtremaRawFn<.int.1>" "ExtremaRawFn<.int.2>"; do
+  name=$(echo $pat | tr -cd 'A-Za-z0-9')
+  timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$pat" -s 2 -c 1 -o gpurun_out/${tag}_$name python tools/prof_driver.py 65536 > gpurun_out/${tag}_ncu_$name.log 2>&1
+done
+# gpurun brings back at most 64 MiB: keep the CSV pages of every report, drop the reports themselves
+for rep in gpurun_out/${tag}_*.ncu-rep; do
+  ncu -i $rep --page raw --csv > ${rep%.ncu-rep}_raw.csv 2>/dev/null
+  ncu -i $rep --page source --csv --print-source sass > ${rep%.ncu-rep}_sass.csv 2>/dev/null
+  rm -f $rep
+done
+ls -la gpurun_out | grep ${tag}

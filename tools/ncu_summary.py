@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Prints the metrics that matter from an .ncu-rep (per kernel launch): duration, occupancy, pipe use, stall mix, traffic.
-usage: ncu_summary.py report.ncu-rep [kernel-substring]"""
+usage: ncu_summary.py report.ncu-rep|raw_page.csv [kernel-substring]"""
 import csv
 import io
 import subprocess
@@ -27,7 +27,10 @@ KEYS = [
 def main():
     rep = sys.argv[1]
     sub = sys.argv[2] if len(sys.argv) > 2 else ""
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):  # already exported with `ncu -i rep --page raw --csv`
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")
