@@ -229,6 +229,7 @@ struct CudaBackend {
       TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_solve_oct<tg::SolveProblemDesc>, 32, 0));
       TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_solve_oct<tg::SolveSweepDesc>, 32, 0));
       oct_reg_warps = std::max(1, std::min(a, b));
+      if (const char* e = std::getenv("TG_OCT_WARPS")) oct_reg_warps = std::max(1, std::min(oct_reg_warps, std::atoi(e)));  // experiments
     }
     TG_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     TG_CUDA_CHECK(cudaEventCreate(&ev0));
@@ -525,6 +526,7 @@ extern "C" {
 int tg_set_profiling(tg_ctx* ctx, int on) {
   if (!ctx) return TG_ERR_INVALID;
   ctx->be.profiling = on != 0;
+  ctx->profiling = on != 0;  // per-kernel timing runs the whole batch on lane 0
   ctx->be.prof.clear();
   return TG_OK;
 }

@@ -6,20 +6,48 @@
 
 #include <cstdlib>
 #include <exception>
+#include <memory>
+#include <stdexcept>
 #include <string>
+#include <thread>
 
 #include "../../include/tg_b200.h"
 #include "tg_pipeline.hpp"
 
+// A context owns one backend + pipeline ("lane 0", which serves every entry point) and, created on first use, a second
+// pair ("lane 1") with its own streams and arenas.  With TG_LANES=2, tg_optimize_batch gives the two halves of a large batch
+// to the two lanes on two host threads, so that one half's solves could fill the GPU while the other half sits in the tail
+// of a Jenkins-Traub launch.  MEASURED on the bench workload (profiles/r01_lanes_sweep.md): no gain -- 137.0 k vs 141.7 k
+// trajectories/s, at every residency cap of the solve kernel -- because the halves' launches are half as large and their tails
+// relatively longer.  OFF by default; kept because the results are identical however the batch is cut (tests: two lanes, batch
+// independence) and a caller with two unrelated batches can use it.
 struct tg_ctx {
   TG_BACKEND be;
   tg::Pipeline<TG_BACKEND> pipe;
+  std::unique_ptr<TG_BACKEND> be2;
+  std::unique_ptr<tg::Pipeline<TG_BACKEND>> pipe2;
+  int device;
+  int lanes = 1;               // TG_LANES=2 switches the second lane on
+  int lane_min_batch = 4096;   // smaller batches stay on one lane (TG_LANE_MIN_BATCH)
+  bool profiling = false;      // per-kernel timing keeps everything on lane 0
+  int split = 0;               // last tg_optimize_batch: problems [0, split) on lane 0, [split, B) on lane 1; 0 = one lane
   std::string err;
   std::vector<tg::Result> last;
   int last_B = 0;
   double last_ms = 0.0;
-  explicit tg_ctx(int device) : be(device), pipe(be) {
+  explicit tg_ctx(int dev) : be(dev), pipe(be), device(dev) {
     if (std::getenv("TG_NO_PRUNE")) pipe.prune_extrema = false;
+    if (const char* e = std::getenv("TG_LANES")) lanes = std::atoi(e);
+    if (const char* e = std::getenv("TG_LANE_MIN_BATCH")) lane_min_batch = std::atoi(e);
+  }
+  tg::Pipeline<TG_BACKEND>& lane1() {
+    if (!pipe2) {
+      be2.reset(new TG_BACKEND(device));
+      pipe2.reset(new tg::Pipeline<TG_BACKEND>(*be2));
+      pipe2->prune_extrema = pipe.prune_extrema;
+    }
+    pipe2->scale_tolerance = pipe.scale_tolerance;
+    return *pipe2;
   }
 };
 
@@ -86,6 +114,10 @@ int tg_get_counters(const tg_ctx* ctx, long long* c) {
   if (!ctx || !c) return TG_ERR_INVALID;
   const tg::Counters& k = ctx->pipe.counters;
   c[0] = k.launches; c[1] = k.solves; c[2] = k.evals; c[3] = k.root_finds; c[4] = k.segment_setups; c[5] = k.samples; c[6] = k.mellinger_solves; c[7] = k.mellinger_launches; c[8] = k.root_finds_executed;
+  if (ctx->pipe2) {
+    const tg::Counters& q = ctx->pipe2->counters;
+    c[0] += q.launches; c[1] += q.solves; c[2] += q.evals; c[3] += q.root_finds; c[4] += q.segment_setups; c[5] += q.samples; c[6] += q.mellinger_solves; c[7] += q.mellinger_launches; c[8] += q.root_finds_executed;
+  }
   return TG_OK;
 }
 
@@ -95,6 +127,10 @@ int tg_get_flop_counters(const tg_ctx* ctx, double* f) {
   if (!ctx || !f) return TG_ERR_INVALID;
   const tg::Counters& k = ctx->pipe.counters;
   f[0] = k.flops_solve; f[1] = k.flops_setup; f[2] = k.flops_sample; f[3] = k.flops_coef;
+  if (ctx->pipe2) {
+    const tg::Counters& q = ctx->pipe2->counters;
+    f[0] += q.flops_solve; f[1] += q.flops_setup; f[2] += q.flops_sample; f[3] += q.flops_coef;
+  }
   return TG_OK;
 }
 
@@ -115,11 +151,49 @@ int tg_optimize_batch(tg_ctx* ctx, int B, const int* wp_off, const double* wp, c
     std::memcpy(&P, params, sizeof(P));
     ctx->last.assign(B, tg::Result());
     ctx->last_B = B;
+    ctx->split = 0;
+    if (ctx->lanes >= 2 && !ctx->profiling && B >= ctx->lane_min_batch && B >= 2) ctx->split = B / 2;
     ctx->be.timer_start();
-    if (B > 0) ctx->pipe.optimize_batch(B, wp_off, wp, stop_at, init14, P, inputs_on_device != 0, ctx->last.data());
-    ctx->last_ms = ctx->be.timer_stop();
+    if (ctx->split > 0) {
+      const int B0 = ctx->split, B1 = B - B0;
+      tg::Pipeline<TG_BACKEND>& p1 = ctx->lane1();
+      std::vector<int> off1((size_t)B1 + 1);
+      for (int i = 0; i <= B1; ++i) off1[i] = wp_off[B0 + i] - wp_off[B0];
+      const size_t v0 = (size_t)wp_off[B0];
+      std::string err1;
+      std::thread t([&]() {
+        try {
+          ctx->be2->bind();
+          p1.optimize_batch(B1, off1.data(), wp + 4 * v0, stop_at ? stop_at + v0 : nullptr, init14 ? init14 + 14 * (size_t)B0 : nullptr, P,
+                            inputs_on_device != 0, ctx->last.data() + B0);
+        } catch (const std::exception& e) {
+          err1 = e.what();
+        } catch (...) {
+          err1 = "unknown error";
+        }
+      });
+      std::string err0;
+      try {
+        ctx->pipe.optimize_batch(B0, wp_off, wp, stop_at, init14, P, inputs_on_device != 0, ctx->last.data());
+      } catch (const std::exception& e) {
+        err0 = e.what();
+      }
+      t.join();
+      if (!err0.empty() || !err1.empty()) throw std::runtime_error(err0.empty() ? err1 : err0);
+    } else if (B > 0) {
+      ctx->pipe.optimize_batch(B, wp_off, wp, stop_at, init14, P, inputs_on_device != 0, ctx->last.data());
+    }
+    ctx->last_ms = ctx->be.timer_stop();  // both lanes have drained (their last calls were synchronous read-backs)
     std::memcpy(results, ctx->last.data(), sizeof(tg_result) * (size_t)B);
-    if (totals) ctx->pipe.output_sizes(totals, ctx->last.data());
+    if (totals) {
+      ctx->pipe.output_sizes(totals, ctx->last.data());
+      if (ctx->split > 0) {
+        long long t1[2];
+        ctx->pipe2->output_sizes(t1, ctx->last.data() + ctx->split);
+        totals[0] += t1[0];
+        totals[1] += t1[1];
+      }
+    }
     return TG_OK;
   });
 }
@@ -127,7 +201,43 @@ int tg_optimize_batch(tg_ctx* ctx, int B, const int* wp_off, const double* wp, c
 int tg_fetch_outputs(tg_ctx* ctx, int* seg_off, double* wp, double* times, double* coef, int* smp_off, double* samples) {
   return tg_guard(ctx, [&]() -> int {
     if (ctx->last_B <= 0) { ctx->err = "no batch result to fetch"; return TG_ERR_NO_RESULT; }
-    ctx->pipe.fetch_outputs(ctx->last.data(), seg_off, wp, times, coef, smp_off, samples);
+    if (ctx->split <= 0) {
+      ctx->pipe.fetch_outputs(ctx->last.data(), seg_off, wp, times, coef, smp_off, samples);
+      return TG_OK;
+    }
+    // two lanes: lane 1's ragged outputs follow lane 0's; its offsets are shifted by lane 0's totals
+    const int B0 = ctx->split, B1 = ctx->last_B - B0;
+    long long t0[2];
+    ctx->pipe.output_sizes(t0, ctx->last.data());
+    const size_t S0 = (size_t)t0[0], M0 = (size_t)t0[1];
+    std::vector<int> so1, mo1;
+    if (seg_off) so1.resize((size_t)B1 + 1);
+    if (smp_off) mo1.resize((size_t)B1 + 1);
+    std::string err1;
+    std::thread t([&]() {
+      try {
+        ctx->be2->bind();
+        ctx->pipe2->fetch_outputs(ctx->last.data() + B0, seg_off ? so1.data() : nullptr, wp ? wp + 4 * (S0 + (size_t)B0) : nullptr,
+                                  times ? times + S0 : nullptr, coef ? coef + S0 * TG_D * TG_N : nullptr, smp_off ? mo1.data() : nullptr,
+                                  samples ? samples + 4 * M0 : nullptr);
+      } catch (const std::exception& e) {
+        err1 = e.what();
+      } catch (...) {
+        err1 = "unknown error";
+      }
+    });
+    std::string err0;
+    try {
+      ctx->pipe.fetch_outputs(ctx->last.data(), seg_off, wp, times, coef, smp_off, samples);
+    } catch (const std::exception& e) {
+      err0 = e.what();
+    }
+    t.join();
+    if (!err0.empty() || !err1.empty()) throw std::runtime_error(err0.empty() ? err1 : err0);
+    if (seg_off)
+      for (int i = 0; i <= B1; ++i) seg_off[B0 + i] = so1[i] + (int)S0;
+    if (smp_off)
+      for (int i = 0; i <= B1; ++i) smp_off[B0 + i] = mo1[i] + (int)M0;
     return TG_OK;
   });
 }

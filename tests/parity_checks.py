@@ -302,6 +302,44 @@ def check_derivative_free_time_allocation(ctx):
     return True
 
 
+def check_two_lanes(lib, n=96):
+    """tg_optimize_batch cuts a large batch in two and runs the halves on two lanes (two host threads, two sets of streams); the
+    merged results and ragged outputs must equal the single-lane ones bit for bit, and the oracle's."""
+    import os
+
+    from mrs_uav_trajectory_generation_b200 import Context
+    from mrs_uav_trajectory_generation_b200 import workloads as W
+
+    wp_off, wp = W.random_flier_paths_fast(n, first_index=21)
+    outs = []
+    for lanes, min_batch in ((1, 1 << 30), (2, 2)):
+        old = {k: os.environ.get(k) for k in ("TG_LANES", "TG_LANE_MIN_BATCH")}
+        os.environ["TG_LANES"], os.environ["TG_LANE_MIN_BATCH"] = str(lanes), str(min_batch)
+        try:
+            ctx = Context(lib, 0)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        res, totals = ctx.optimize_batch(wp_off, wp, None, None, ctx.L.default_params())
+        outs.append((res, totals, ctx.fetch_outputs(), ctx.counters()))
+    (r1, t1, o1, c1), (r2, t2, o2, c2) = outs
+    assert np.array_equal(t1, t2)
+    for f in r1.dtype.names:
+        assert np.array_equal(r1[f], r2[f]), f
+    for k in ("seg_off", "wp", "times", "coef", "smp_off", "samples"):
+        assert np.array_equal(o1[k], o2[k]), k
+    assert c1["solves"] == c2["solves"] and c1["root_finds"] == c2["root_finds"]
+    ref = O.optimize_batch(wp_off, wp, params=O.default_params(), cap_wp=1400, cap_samples=6000)
+    for p in (0, n // 2 - 1, n // 2, n - 1):  # either side of the cut
+        s0, s1 = o2["seg_off"][p], o2["seg_off"][p + 1]
+        nw = ref["res"][p].n_waypoints
+        assert s1 - s0 == nw - 1 and np.array_equal(o2["coef"][s0:s1], ref["coeffs"][p][: nw - 1])
+    return True
+
+
 def compare_optimize(ctx, wp_off, wp, stop_at=None, init=None, params_kw=None, cap_wp=1400, cap_samples=6000):
     """Runs the full optimize() pipeline on both sides; asserts parity; returns (results, bit_exact, worst_coef_err)."""
     params_kw = params_kw or {}

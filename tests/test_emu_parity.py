@@ -41,6 +41,10 @@ def test_derivative_free_time_allocation(emu_ctx, oracle):
     assert PC.check_derivative_free_time_allocation(emu_ctx)
 
 
+def test_two_lanes(emu_lib, oracle):
+    assert PC.check_two_lanes(emu_lib, n=48)
+
+
 def test_max_magnitude(emu_ctx, oracle):
     assert PC.check_max_magnitude(emu_ctx)
 

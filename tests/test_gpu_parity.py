@@ -48,6 +48,10 @@ def test_derivative_free_time_allocation(gpu_ctx, oracle):
     assert PC.check_derivative_free_time_allocation(gpu_ctx)
 
 
+def test_two_lanes(gpu_ctx, oracle):
+    assert PC.check_two_lanes(gpu_ctx.L, n=512)
+
+
 def test_max_magnitude(gpu_ctx, oracle):
     assert PC.check_max_magnitude(gpu_ctx)
 
@@ -101,13 +105,15 @@ def test_long_path_global_workspace(gpu_ctx, oracle):
 
 
 def test_properties_at_full_size(gpu_ctx):
-    """BASELINE config 2 size (4096 paths) and a config-3 slice (8192 paths): size-independent properties.
+    """BASELINE config 2 size (4096 paths) and config 3 at its full size (65 536 paths): size-independent properties.
     - C^4 continuity of every trajectory at interior vertices (the reduced system enforces it, lin_impl.h:202-220)
     - fixed constraints reproduced: position at every waypoint
     - sampling: counts consistent with total time, samples start at the first waypoint
     - feasibility: after time scaling every per-segment maximum is within (1 + 1e-3) of its limit
-    - verdict consistency: safe trajectories measured max deviation <= max_deviation."""
-    B = 8192
+    - verdict consistency: safe trajectories measured max deviation <= max_deviation
+    - batch independence: a problem's result does not depend on the batch around it (grouping, S-sorted subdivision rounds,
+      launch runs): the first 512 paths solved on their own give bit-identical outputs."""
+    B = 65536
     wp_off, wp = W.random_flier_paths_fast(B, first_index=3)
     P = gpu_ctx.L.default_params()
     res, totals = gpu_ctx.optimize_batch(wp_off, wp, None, None, P)
@@ -137,6 +143,13 @@ def test_properties_at_full_size(gpu_ctx):
         M = smp_off[p + 1] - smp_off[p]
         assert abs(M - T.sum() / P.dt) <= 1.0 + 1e-9
         assert np.abs(out["samples"][smp_off[p], :3] - wps[0][:3]).max() < 1e-9
+    sub_off = wp_off[:513].copy()
+    rs, _ = gpu_ctx.optimize_batch(sub_off, wp[: sub_off[-1]], None, None, P)
+    os_ = gpu_ctx.fetch_outputs()
+    for f in ("status", "nlopt_code", "n_evals", "rounds", "safe", "n_waypoints", "n_samples", "n_scale_passes"):
+        assert np.array_equal(rs[f], res[f][:512]), f
+    assert np.array_equal(os_["coef"], coef[: seg_off[512]]) and np.array_equal(os_["times"], times[: seg_off[512]])
+    assert np.array_equal(os_["samples"], out["samples"][: smp_off[512]])
     # NB: the FINAL trajectories need not satisfy the dynamics limits: the reference stretches a copy of the segments
     # (eth/trajectory.cpp:598-692) and then re-solves the QP at the stretched times (nl_impl.h:405-408), which moves
     # the maxima again.  Feasibility of the stretched copy itself is asserted in check_extrema_and_scaling.
