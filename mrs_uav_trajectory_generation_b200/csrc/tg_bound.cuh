@@ -14,7 +14,7 @@
 // for the check.  The bound is stored in place of the maximum and flagged; if the problem needs another pass after all
 // (rare), flagged entries are recomputed exactly before they are read (ExtremaCompleteFn).  Decisions, pass counts and
 // every number that leaves the routine are unchanged; measured on the round-1 workload 85 % of the check's root finding
-// disappears (profiles/r01_extrema.md).
+// disappears (bench counters root_finds_reference_equivalent vs root_finds_executed, profiles/r01_final_bench_65536.json).
 //
 // Rounding: the power->Bernstein conversion and the Horner evaluation behind the exact maximum each err by at most a few
 // n*eps*sum_j |c_j T^j|; the bound adds 1024 eps times that sum and a relative 1e-12, orders of magnitude above both.

@@ -21,9 +21,9 @@
 // per-(segment, time) record produced by setup_segment_record(), consumed by the solve warp
 #define TG_REC_DINV 0    // 5x5 inverse of the lower-right block of A
 #define TG_REC_X 25      // 5x5 lower-left block of A^-1 : (-Dinv*C)*diag(1/k!)
-#define TG_REC_Q 50      // (N-r)^2 non-zero block of Q, row stride 8
-#define TG_REC_H 114     // 10x10 H = (A^-T Q) A^-1
-#define TG_REC_SIZE 216  // doubles (1728 B, 64 B aligned)
+#define TG_REC_Q 50      // non-zero block of Q, (N-r) x (N-r), SYMMETRIC bit for bit (B_i B_j commute): packed upper triangle, tg_qtri()
+#define TG_REC_H 86      // 10x10 H = (A^-T Q) A^-1
+#define TG_REC_SIZE 186  // doubles (1488 B, 16 B aligned)
 
 #define TG_DBL_EPSILON 2.2204460492503131e-16
 #define TG_DBL_MIN 2.2250738585072014e-308
@@ -44,6 +44,10 @@ TG_HD double bcoef(int k, int i) {
   for (int m = 0; m < k; ++m) p *= (i - m);
   return (double)p;
 }
+
+// index of Q[k][b], k <= b < 8, in the packed upper triangle (row k starts at 8k - k(k-1)/2; the same layout for every r)
+TG_HD constexpr int tg_qtri(int k, int b) { return k * 8 - (k * (k - 1)) / 2 + (b - k); }
+TG_HD constexpr int tg_qsym(int k, int b) { return k <= b ? tg_qtri(k, b) : tg_qtri(b, k); }
 
 TG_HD double dmax(double a, double b) { return (a < b) ? b : a; }  // std::max(a, b)
 TG_HD double dmin(double a, double b) { return (b < a) ? b : a; }  // std::min(a, b)

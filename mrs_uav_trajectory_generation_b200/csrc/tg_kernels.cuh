@@ -5,7 +5,7 @@
 //   seg_off[B+1]             first segment of problem p; vertices start at seg_off[p] + p (V = S + 1)
 //   wp[totV][4], stop[totV]  waypoints x y z heading, stop_at flags
 //   vmask[totV], vval[totV][5][4], vfree[totV + B]   vertex constraints and free-unknown index (V+1 per problem)
-//   times/xeval/x/g/d[totS], hist_s/hist_y[11][totS], coef[totS][4][10], recs[totS*{1,3}][216], maxima[totS][9]
+//   times/xeval/x/g/d[totS], hist_s/hist_y[11][totS], coef[totS][4][10], recs[totS*{1,3}][186], maxima[totS][9]
 //   costs[totV]              cost of solve instance (p, n): n = 0 base, n >= 1 perturbed segment n-1
 #ifndef TG_KERNELS_CUH_
 #define TG_KERNELS_CUH_
@@ -316,23 +316,19 @@ struct ObjCombineFn {
 template <int R>
 TG_HD double cost_partial(const double (&c)[TG_N], const double* __restrict__ Qg) {
   constexpr int nq = TG_N - R;
-  double Q[nq][8];  // the Q block of the record (row stride 8), fetched with 16-byte loads
+  double qt[36];  // the packed Q block of the record (tg_qtri), fetched with 16-byte loads
 #pragma unroll
-  for (int k = 0; k < nq; ++k)
-#pragma unroll
-    for (int b = 0; b < 8; b += 2) {
-      if (b < nq) {
-        const Dbl2 t = *reinterpret_cast<const Dbl2*>(Qg + k * 8 + b);
-        Q[k][b] = t.x;
-        Q[k][b + 1] = t.y;
-      }
-    }
+  for (int e = 0; e < 36; e += 2) {
+    const Dbl2 t = *reinterpret_cast<const Dbl2*>(Qg + e);
+    qt[e] = t.x;
+    qt[e + 1] = t.y;
+  }
   double partial = 0.0;
 #pragma unroll
   for (int b = 0; b < nq; ++b) {
-    double sum = c[R] * Q[0][b];
+    double sum = c[R] * qt[tg_qsym(0, b)];
 #pragma unroll
-    for (int k = 1; k < nq; ++k) sum = sum + c[R + k] * Q[k][b];
+    for (int k = 1; k < nq; ++k) sum = sum + c[R + k] * qt[tg_qsym(k, b)];
     partial = (b == 0) ? sum * c[R + b] : partial + sum * c[R + b];
   }
   return partial;

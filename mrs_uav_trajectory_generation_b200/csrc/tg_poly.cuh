@@ -837,7 +837,7 @@ TG_HD double segment_max_q(const double* __restrict__ coef, double T, double* sc
 #include "tg_poly_naive.cuh"
 namespace tg {
 #ifndef TG_JT_IMPL
-#define TG_JT_IMPL 1  // 0: direct transcription, work arrays in local memory; 1: warp-scheduled stage machine, shared-memory work arrays (fastest measured, profiles/r01_extrema.md); 2: micro-op machine with lane refill (tg_poly_vm.cuh)
+#define TG_JT_IMPL 1  // 0: direct transcription, work arrays in local memory; 1: warp-scheduled stage machine, shared-memory work arrays (fastest measured); 2: micro-op machine with lane refill (tg_poly_vm.cuh)
 #endif
 template <int Q>
 TG_HD double segment_max_impl(const double* __restrict__ coef, double T, double* scratch, int stride, int* shifts) {

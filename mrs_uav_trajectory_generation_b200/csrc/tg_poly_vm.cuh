@@ -2,7 +2,7 @@
 // Third formulation of the extremum kernels (TG_JT_IMPL=2); same arithmetic, bit for bit, as tg_poly_naive.cuh (0)
 // and the stage-level state machine of tg_poly.cuh (1), and therefore as the oracle.
 //
-// What the round-1 measurements said (profiles/r01_extrema.md):
+// What the round-1 measurements said (sessions 1-2 of round 1, summarised in DESIGN.md 4.2):
 //   * one thread per polynomial, direct transcription: 3.8 of 32 lanes active per instruction;
 //   * stage-level state machine: 6.6 lanes, fewer instructions, but 9 k SASS instructions of code (calc_sc inlined five
 //     times, ~40 IEEE divisions at ~25 instructions each) and `no_instruction` the top stall -- the L1.5 I-cache holds 32 KB;

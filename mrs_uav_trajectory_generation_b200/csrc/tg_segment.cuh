@@ -118,7 +118,7 @@ TG_HD void setup_segment_record_r(double T, double* __restrict__ rec) {
       for (int k = 1; k <= j; ++k) m = m + (-Dinv[i][k]) * Cm[k][j];  // C[k][j] == 0 for k > j
       X[i][j] = m * a_inv[j];
     }
-  // the record is written with 16-byte stores: one thread owns 1728 contiguous bytes, and the kernel is bound by the
+  // the record is written with 16-byte stores: one thread owns 1488 contiguous bytes, and the kernel is bound by the
   // number of store requests, not by bytes (round-1 measurement: 2.9 TB/s with 8-byte stores)
   static_assert(TG_REC_DINV == 0 && TG_REC_X == 25 && TG_REC_Q == 50 && (TG_REC_H % 2) == 0, "record layout");
 #pragma unroll
@@ -127,13 +127,17 @@ TG_HD void setup_segment_record_r(double T, double* __restrict__ rec) {
     const double v1 = (e + 1 < 25) ? Dinv[(e + 1) / 5][(e + 1) % 5] : X[(e + 1 - 25) / 5][(e + 1 - 25) % 5];
     store2(rec + e, v0, v1);
   }
+  {
+    double qt[36];  // packed upper triangle (tg_qtri); entries beyond NQ stay zero
 #pragma unroll
-  for (int i = 0; i < NQ; ++i)
+    for (int e = 0; e < 36; ++e) qt[e] = 0.0;
 #pragma unroll
-    for (int j = 0; j < NQ; j += 2) {
-      if (j + 1 < NQ) store2(rec + TG_REC_Q + i * 8 + j, Q[i][j], Q[i][j + 1]);
-      else rec[TG_REC_Q + i * 8 + j] = Q[i][j];
-    }
+    for (int i = 0; i < NQ; ++i)
+#pragma unroll
+      for (int j = i; j < NQ; ++j) qt[tg_qtri(i, j)] = Q[i][j];
+#pragma unroll
+    for (int e = 0; e < 36; e += 2) store2(rec + TG_REC_Q + e, qt[e], qt[e + 1]);
+  }
   // --- H = (A^-T Q) A^-1 (lin_impl.h:320), inner sums over ascending k, zero terms skipped
   // A^-1 = [ diag(a_inv) 0 ; X Dinv ].  Row a of W = A^-T Q :  W[a][b] = sum_k Ainv[k][a] Q[k][b]
 #pragma unroll

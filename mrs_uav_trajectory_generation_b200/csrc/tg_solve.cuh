@@ -9,7 +9,7 @@
 //
 // The routine is a sequence of PHASES (TG_PHASE): inside a phase every lane owns disjoint outputs and reads only data
 // written in earlier phases; on the device a phase ends with __syncwarp(), tests/host_emu runs the lanes of a phase
-// one after the other.  Round-1 profile of the first version (profiles/r01_solve_v1.md): 19 k warp instructions per
+// one after the other.  Round-1 profile of the first version (ncu in session 1 of round 1): 19 k warp instructions per
 // solve, most of them index arithmetic and phase dispatch; this version precomputes the slot table once per solve,
 // loads whole 10-entry rows of H with independent loads, and runs the factorisation as a tight loop.
 #ifndef TG_SOLVE_CUH_
@@ -224,8 +224,8 @@ TG_HD void solve_warp(const SolveInst& I, int lane) {
       const double* c = I.rows + it * TG_N;
       double partial = 0.0;
       for (int b = 0; b < nq; ++b) {
-        double sum = c[r] * Q[0 * 8 + b];
-        for (int k = 1; k < nq; ++k) sum = sum + c[r + k] * Q[k * 8 + b];
+        double sum = c[r] * Q[tg_qsym(0, b)];
+        for (int k = 1; k < nq; ++k) sum = sum + c[r + k] * Q[tg_qsym(k, b)];
         partial = (b == 0) ? sum * c[r + b] : partial + sum * c[r + b];
       }
       I.part[it] = partial;

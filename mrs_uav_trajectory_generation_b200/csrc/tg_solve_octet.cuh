@@ -2,7 +2,7 @@
 // Same job and the same arithmetic, element for element, as solve_warp() in tg_solve.cuh (reference:
 // lin_impl.h:310-334, 340-373, 263-282, 127-141); a different mapping onto the SM.
 //
-// Why: the round-1 profile of the warp-per-problem kernel (profiles/r01_solve_v2.md) showed 13.5 k warp instructions
+// Why: the round-1 profile of the warp-per-problem kernel (ncu in session 1 of round 1, figures in DESIGN.md 4.1) showed 13.5 k warp instructions
 // per solve, issue-bound, with 8 of 32 lanes useful in the factorisation (half bandwidth 7 => 7 rows change per
 // elimination step).  Here the band's natural width IS the lane group:
 //   * row i of the banded system lives in the REGISTERS of lane (i mod 8) of the octet while it is inside the
@@ -15,7 +15,7 @@
 //     substitution, which runs the same window upwards;
 //   * the routine ends with the solution of the reduced system written to global memory; coefficients and cost are a
 //     separate flat kernel (CoefCostFn, one thread per (segment, dimension)) -- fused into this kernel they cost a third
-//     of its time at 8 warps per SM (profiles/r01_solve_octet.md).
+//     of its time at 8 warps per SM (measured in session 2 of round 1).
 //
 // Eligibility: half bandwidth exactly 7 (every interior vertex has position fixed and v, a, j, s free -- the node's
 // recipe, node.cpp:931-977), at least 8 unknowns, and a workspace that fits shared memory; anything else takes
