@@ -100,6 +100,20 @@ class Trajectory:
             t += float(x)
         return t
 
+    def toYaml(self):  # trajectoryToYaml / segmentsToFile (eth/io.cpp:66-70, 125-168)
+        from . import segment_io
+
+        return segment_io.segments_to_yaml(self.coef, self.times)
+
+    @classmethod
+    def fromYaml(cls, text, ctx=None):  # trajectoryFromYaml / segmentsFromFile (eth/io.cpp:114-122, 169-218); None when malformed
+        from . import segment_io
+
+        r = segment_io.segments_from_yaml(text)
+        if r is None or r[0].shape[1:] != (D, N):
+            return None
+        return cls(r[0], r[1], ctx)
+
     def getSegmentTimes(self):
         return self.times.copy()
 
