@@ -2,8 +2,8 @@
 // Same job and the same arithmetic, element for element, as solve_warp() in tg_solve.cuh (reference:
 // lin_impl.h:310-334, 340-373, 263-282, 127-141); a different mapping onto the SM.
 //
-// Why: the round-1 profile of the warp-per-problem kernel (ncu in session 1 of round 1, figures in DESIGN.md 4.1) showed 13.5 k warp instructions
-// per solve, issue-bound, with 8 of 32 lanes useful in the factorisation (half bandwidth 7 => 7 rows change per
+// Why: the round-1 profile of the warp-per-problem kernel (ncu in session 1 of round 1, figures in DESIGN.md 4.1) showed
+// 13.5 k warp instructions per solve, issue-bound, with 8 of 32 lanes useful in the factorisation (half bandwidth 7 => 7 rows change per
 // elimination step).  Here the band's natural width IS the lane group:
 //   * row i of the banded system lives in the REGISTERS of lane (i mod 8) of the octet while it is inside the
 //     elimination window (steps i-7 .. i-1).  Column j is kept at register index (j - k0) mod 16, k0 = first step of
@@ -11,15 +11,16 @@
 //     compile-time constant; between blocks the two register halves swap;
 //   * the pivot row reaches the other seven lanes by warp SHUFFLES -- no shared-memory round trip and no
 //     __syncwarp() inside the factorisation or the back substitution;
-//   * shared memory holds the assembled rows until they enter the window, then (in place) the U rows for the back
-//     substitution, which runs the same window upwards;
+//   * the rows STREAM through shared memory: a ring of two blocks of eight rows holds the block that is about to enter
+//     the window (assembled) and the H rows of the block after it (cp.async in flight); finished rows (1/pivot, U part,
+//     right-hand sides: 96 bytes) wait for the back substitution in a per-warp slab of global memory that stays in L2 and
+//     return through the same ring.  Shared memory per problem is 2.9 KB whatever its size (see solve_octets);
 //   * the routine ends with the solution of the reduced system written to global memory; coefficients and cost are a
 //     separate flat kernel (CoefCostFn, one thread per (segment, dimension)) -- fused into this kernel they cost a third
 //     of its time at 8 warps per SM (measured in session 2 of round 1).
 //
 // Eligibility: half bandwidth exactly 7 (every interior vertex has position fixed and v, a, j, s free -- the node's
-// recipe, node.cpp:931-977), at least 8 unknowns, and a workspace that fits shared memory; anything else takes
-// solve_warp().  Written in the TG_PHASE style of tg_solve.cuh so that tests/host_emu can run it lane by lane: a
+// recipe, node.cpp:931-977) and at least 8 unknowns; anything else takes solve_warp() in a second launch (k_solve).  Written in the TG_PHASE style of tg_solve.cuh so that tests/host_emu can run it lane by lane: a
 // shuffle becomes a read of the source lane's state in a phase of its own.
 #ifndef TG_SOLVE_OCTET_CUH_
 #define TG_SOLVE_OCTET_CUH_
