@@ -56,7 +56,7 @@ struct ProbState {
   int sample_cap;
   int safe;
   int next_V;          // vertex count after subdivision (0: no re-solve needed)
-  int pad;
+  int n_grads;         // Mellinger evaluations whose gradient was computed (<= n_evals)
   double final_cost;   // cost reported by the optimiser (f at the last accepted point)
   double cost;         // cost of the final linear solve
   double baca_total;
@@ -87,6 +87,7 @@ struct BatchPtrs {
   double* xs;            // [instances][xstride] solutions of the reduced systems (solve kernels -> CoefCostFn)
   double* part;          // [instances][4 * smax] partial costs
   int xstride, smax;
+  uint8_t* need_grad;   // [B] set by LbfgsPeekFn: this evaluation's gradient (the S perturbed solves) is needed
 };
 
 TG_HD int vtx_off(const BatchPtrs& b, int p) { return b.seg_off[p] + p; }
@@ -114,6 +115,7 @@ struct PrepareFn {
     ps.status = kFindOk;
     ps.nlopt_code = 1;
     ps.n_evals = 0;
+    ps.n_grads = 0;
     ps.n_scale_passes = 0;
     ps.scale_done = 0;
     ps.n_samples = 0;
@@ -159,11 +161,25 @@ struct SetupBaseFn {
 };
 struct SetupMellingerFn {
   BatchPtrs b;
-  TG_HD void operator()(size_t item) const {
-    const size_t gs = item / 3;
-    const int which = (int)(item - gs * 3);
+  int phase;  // 0: all three records of every segment; 1: the base record only (item = segment); 2: the +0.1 / -corr records
+              // of the problems whose gradient is needed (item = 2 * segment + {0, 1})
+  TG_HD void operator()(size_t item0) const {
+    size_t gs;
+    int which;
+    if (phase == 1) {
+      gs = item0;
+      which = 0;
+    } else if (phase == 2) {
+      gs = item0 >> 1;
+      which = 1 + (int)(item0 & 1);
+    } else {
+      gs = item0 / 3;
+      which = (int)(item0 - gs * 3);
+    }
+    const size_t item = gs * 3 + which;
     const int p = b.prob_of_seg[gs];
     if (b.lb[p].done) return;
+    if (phase == 2 && !b.need_grad[p]) return;
     const int S = b.seg_off[p + 1] - b.seg_off[p];
     if (S == 1 && which != 0) return;
     double T = b.xeval[gs];
@@ -182,18 +198,24 @@ struct SetupMellingerFn {
 // ---- 4. warp solves ----------------------------------------------------------------------------------------------------
 struct SolveProblemDesc {
   BatchPtrs b;
-  int mellinger;  // 1: instance = vertex index (problem, variant); 0: instance = problem, base times, rec_stride 1
+  // 0: instance = problem, base times, one record per segment (final solve, linear batch)
+  // 1: instance = vertex index = (problem, variant), every variant of every running problem (one Mellinger evaluation)
+  // 2: instance = problem, variant 0 of a Mellinger evaluation (the base point; three records per segment)
+  // 3: instance = vertex index, variants >= 1 of the problems whose gradient is needed (b.need_grad)
+  int mellinger;
   double* dp_out; // optional [sum np][4]-> per problem offset by 4*vfree base (only base mode), may be null
   const int* dp_off;
   TG_HD bool instance(size_t inst, SolveInst& I) const {
     int p, n;
-    if (mellinger) {
+    if (mellinger == 1 || mellinger == 3) {
       p = b.prob_of_vtx[inst];
       n = (int)inst - vtx_off(b, p);
       if (b.lb[p].done) return false;
+      if (mellinger == 3 && (n == 0 || !b.need_grad[p])) return false;
     } else {
       p = (int)inst;
       n = 0;
+      if (mellinger == 2 && b.lb[p].done) return false;
     }
     const int s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0, v0 = s0 + p;
     if (mellinger && S == 1 && n > 0) return false;
@@ -210,7 +232,8 @@ struct SolveProblemDesc {
     I.coef_out = (n == 0) ? b.coef + (size_t)s0 * TG_D * TG_N : nullptr;
     I.cost_out = mellinger ? b.costs + v0 + n : &b.ps[p].cost;
     I.dp_out = (dp_out && !mellinger) ? dp_out + (size_t)TG_D * dp_off[p] : nullptr;
-    I.x_out = b.xs ? b.xs + inst * (size_t)b.xstride : nullptr;
+    // the solution slot of (problem, variant) is the same whichever way the instance was numbered
+    I.x_out = b.xs ? b.xs + (mellinger ? (size_t)(v0 + n) : inst) * (size_t)b.xstride : nullptr;
     return true;
   }
 };
@@ -423,6 +446,23 @@ struct LbfgsBeginFn {
     lbfgs_begin(S, b.lb[p], lbfgs_vectors(b, p), b.times + s0);
   }
 };
+// after the base solve of an evaluation: problems that do not need this evaluation's gradient advance at once
+struct LbfgsPeekFn {
+  BatchPtrs b;
+  int max_evals;
+  double f_rel, x_rel;
+  TG_HD void operator()(size_t pi) const {
+    const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
+    LbfgsScalars& st = b.lb[p];
+    b.need_grad[p] = 0;
+    if (st.done) return;
+    const double* costs = b.costs + vtx_off(b, p);
+    const LbfgsVectors v = lbfgs_vectors(b, p);
+    if (lbfgs_needs_gradient(S, st, v, costs[0], max_evals, f_rel, x_rel, -1.0, -1.0)) b.need_grad[p] = 1;
+    else lbfgs_advance(S, st, v, costs, max_evals, f_rel, x_rel, -1.0, -1.0, false);
+  }
+};
+// after the perturbed solves: the others advance with the full gradient
 struct LbfgsAdvanceFn {
   BatchPtrs b;
   int max_evals;
@@ -430,8 +470,8 @@ struct LbfgsAdvanceFn {
   TG_HD void operator()(size_t pi) const {
     const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
     LbfgsScalars& st = b.lb[p];
-    if (st.done) return;
-    lbfgs_advance(S, st, lbfgs_vectors(b, p), b.costs + vtx_off(b, p), max_evals, f_rel, x_rel, -1.0, -1.0);
+    if (st.done || !b.need_grad[p]) return;
+    lbfgs_advance(S, st, lbfgs_vectors(b, p), b.costs + vtx_off(b, p), max_evals, f_rel, x_rel, -1.0, -1.0, true);
   }
 };
 // after the loop: times <- last evaluated point (what poly_opt_ holds when nlopt returns, nl_impl.h:210-215)
@@ -443,6 +483,7 @@ struct LbfgsFinishFn {
     ProbState& ps = b.ps[p];
     ps.nlopt_code = b.lb[p].code;
     ps.n_evals = b.lb[p].n_evals;
+    ps.n_grads = b.lb[p].n_grads;
     ps.final_cost = b.lb[p].f;
     const int code = ps.nlopt_code;
     if (!((code >= 1 && code != 6) || code == -1)) ps.status = kFindNloptRejected;  // node.cpp:1138-1149
@@ -815,7 +856,7 @@ struct InitStateFn {  // ProbState reset for bare batches (no vertex recipe)
   TG_HD void operator()(size_t p) const {
     ProbState z;
     z.status = kFindOk; z.nlopt_code = 1; z.n_evals = 0; z.n_scale_passes = 0; z.scale_done = 0; z.n_samples = 0;
-    z.sample_cap = 0; z.safe = 0; z.next_V = 0; z.pad = 0; z.final_cost = 0.0; z.cost = 0.0; z.baca_total = 0.0; z.max_dev = 0.0;
+    z.sample_cap = 0; z.safe = 0; z.next_V = 0; z.n_grads = 0; z.final_cost = 0.0; z.cost = 0.0; z.baca_total = 0.0; z.max_dev = 0.0;
     ps[p] = z;
   }
 };

@@ -21,6 +21,7 @@ struct LbfgsScalars {
   double f, gd, step;
   double rho[kLbfgsMem + 1];
   int npairs, n_evals, iter, ls_it, stage, code, done;
+  int n_grads;  // evaluations whose gradient (the S perturbed solves) was actually computed
 };
 
 struct LbfgsVectors {  // all of length S for this problem; hist_* hold kLbfgsMem + 1 pairs, stride `hstride`
@@ -115,6 +116,7 @@ TG_HD void lbfgs_begin(int S, LbfgsScalars& st, const LbfgsVectors& v, const dou
   st.step = 0.0;
   st.npairs = 0;
   st.n_evals = 0;
+  st.n_grads = 0;
   st.iter = 0;
   st.ls_it = 0;
   st.stage = 0;
@@ -122,17 +124,38 @@ TG_HD void lbfgs_begin(int S, LbfgsScalars& st, const LbfgsVectors& v, const dou
   st.done = 0;
 }
 
-// Advance after one evaluation at xeval whose S+1 costs are `costs` (base first).
+// Does the evaluation whose base cost `fe` has just arrived need its gradient?  The S perturbed solves of an evaluation
+// (nl_impl.h:282-323) are consumed only by the first evaluation and by an ACCEPTED line-search trial after which the
+// iteration continues: a rejected trial reads the base cost alone, and so does an accepted one that ends the run (ftol,
+// xtol, maxeval).  On the round-1 workload two evaluations out of three need no gradient, so the caller solves the base
+// point first, asks this function, and runs the perturbed solves only where the answer is yes.  Same tests, in the same
+// order, as lbfgs_advance below; the state is not touched.
+TG_HD bool lbfgs_needs_gradient(int S, const LbfgsScalars& st, const LbfgsVectors& v, double fe, int max_evals, double f_rel, double x_rel,
+                                double f_abs, double x_abs) {
+  const int n_evals = st.n_evals + 1;
+  if (st.stage == 0) return n_evals < max_evals;
+  if (!(dfinite(fe) && fe <= st.f + 1e-4 * st.step * st.gd)) return false;  // rejected trial
+  if (relstop(st.f, fe, f_rel, f_abs)) return false;
+  bool x_stop = true;
+  for (int i = 0; i < S; ++i)
+    if (!relstop(v.x[i], v.xeval[i], x_rel, x_abs)) x_stop = false;
+  if (x_stop) return false;
+  return n_evals < max_evals;
+}
+
+// Advance after one evaluation at xeval.  have_grad: all S+1 costs are in `costs` (base first); otherwise only costs[0] is
+// valid, which lbfgs_needs_gradient has shown to be enough for this step.
 TG_HD_NOINLINE void lbfgs_advance(int S, LbfgsScalars& st, const LbfgsVectors& v, const double* __restrict__ costs, int max_evals,
-                         double f_rel, double x_rel, double f_abs, double x_abs) {
+                         double f_rel, double x_rel, double f_abs, double x_abs, bool have_grad) {
   if (st.done) return;
   st.n_evals += 1;
+  if (have_grad) st.n_grads += 1;
   const double fe = costs[0];
   if (st.stage == 0) {
     st.f = fe;
     for (int i = 0; i < S; ++i) {
       v.x[i] = v.xeval[i];
-      v.g[i] = mellinger_grad(S, costs, i);
+      if (have_grad) v.g[i] = mellinger_grad(S, costs, i);
     }
     if (st.n_evals >= max_evals) { st.code = 5; st.done = 1; return; }
     st.stage = 1;
@@ -150,19 +173,21 @@ TG_HD_NOINLINE void lbfgs_advance(int S, LbfgsScalars& st, const LbfgsVectors& v
     double* hy = v.hist_y + (size_t)slot * v.hstride;
     bool x_stop = true;
     for (int i = 0; i < S; ++i) {
-      const double gn = mellinger_grad(S, costs, i);
-      const double sv = v.xeval[i] - v.x[i];
-      const double yv = gn - v.g[i];
-      hs[i] = sv;
-      hy[i] = yv;
-      sy = sy + sv * yv;
-      ss = ss + sv * sv;
-      yy = yy + yv * yv;
       if (!relstop(v.x[i], v.xeval[i], x_rel, x_abs)) x_stop = false;
+      if (have_grad) {
+        const double gn = mellinger_grad(S, costs, i);
+        const double sv = v.xeval[i] - v.x[i];
+        const double yv = gn - v.g[i];
+        hs[i] = sv;
+        hy[i] = yv;
+        sy = sy + sv * yv;
+        ss = ss + sv * sv;
+        yy = yy + yv * yv;
+        v.g[i] = gn;
+      }
       v.x[i] = v.xeval[i];
-      v.g[i] = gn;
     }
-    if (sy > 1e-10 * dsqrt(ss) * dsqrt(yy)) {
+    if (have_grad && sy > 1e-10 * dsqrt(ss) * dsqrt(yy)) {
       st.rho[slot] = 1.0 / sy;
       if (slot == kLbfgsMem) {  // memory full: drop the oldest pair
         for (int k = 1; k <= kLbfgsMem; ++k) {

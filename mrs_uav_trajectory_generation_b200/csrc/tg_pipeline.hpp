@@ -188,8 +188,9 @@ class Pipeline {
     for (int p = 0; p < B; ++p) {
       const int S = g.seg_off[p + 1] - g.seg_off[p];
       const int ev = g.ps[p].n_evals;
-      const long long nsolve = (long long)ev * (S == 1 ? 1 : S + 1) + 1;
-      const long long nsetup = (long long)ev * S * (S == 1 ? 1 : 3) + S;
+      const int ng = g.ps[p].n_grads;  // evaluations whose S perturbed solves were run
+      const long long nsolve = (long long)ev + (S == 1 ? 0 : (long long)ng * S) + 1;
+      const long long nsetup = (long long)ev * S + (S == 1 ? 0 : (long long)ng * 2 * S) + S;
       const double np_ = h_np[p], bw = h_hbw[p];
       // SURVEY.md 8(d) formula, split by kernel: banded factorisation + right-hand sides + back substitution (solve kernel),
       // coefficients + cost (CoefCostFn)
@@ -615,12 +616,20 @@ class Pipeline {
     b.recs = scratch_.template alloc<double>((size_t)totS * 3 * TG_REC_SIZE);
     b.costs = scratch_.template alloc<double>(totV);
     b.maxima = scratch_.template alloc<double>((size_t)totS * 9);
+    b.need_grad = scratch_.template alloc<uint8_t>(B);
     be_.for_each(B, LbfgsBeginFn{b}); launches(1);
+    // One evaluation = the base solve of every running problem, then -- only where the optimiser will consume a gradient
+    // (lbfgs_needs_gradient: first evaluation, or an accepted trial after which the iteration goes on) -- the S perturbed
+    // solves of nl_impl.h:282-323.  Rejected trials and final evaluations read the base cost alone: two evaluations out of
+    // three on the bench workload.  The costs that are consumed are the same numbers as before, so are all results.
     for (int e = 0; e < P.max_evals; ++e) {
-      be_.for_each((size_t)totS * 3, SetupMellingerFn{b});
-      solve_with_outputs((size_t)totV, stats, SolveProblemDesc{b, 1, nullptr, nullptr}, b, buckets, true);
+      be_.for_each((size_t)totS, SetupMellingerFn{b, 1});
+      solve_with_outputs((size_t)B, stats, SolveProblemDesc{b, 2, nullptr, nullptr}, b, buckets, false);
+      be_.for_each(B, LbfgsPeekFn{b, P.max_evals, P.f_rel, P.x_rel});
+      be_.for_each((size_t)totS * 2, SetupMellingerFn{b, 2});
+      solve_with_outputs((size_t)totV, stats, SolveProblemDesc{b, 3, nullptr, nullptr}, b, buckets, true);
       be_.for_each(B, LbfgsAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel});
-      launches(3);
+      launches(6);
     }
     be_.for_each(B, LbfgsFinishFn{b}); launches(1);
     // time scaling (nl_impl.h:335-427 -> eth/trajectory.cpp:598-692)
