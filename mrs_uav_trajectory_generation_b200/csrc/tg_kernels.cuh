@@ -623,10 +623,10 @@ struct ExtremaPruneAFn {
       rq[gs * 9 + q] = r;
       if (r > rmax) rmax = r;
     }
+    double best = -1.0;
     if (usable && rmax > 1.0) {
       // which of the remaining quantities to compute first: the one that most likely binds, judged by curve values at five
       // points (a LOWER estimate of each maximum); the choice affects only how much is pruned afterwards, never the result
-      double best = -1.0;
       for (int q = 0; q < 9; ++q) {
         if (!(rq[gs * 9 + q] > 1.0)) continue;
         const int group = q / 3, deriv = q % 3 + 1;
@@ -657,6 +657,23 @@ struct ExtremaPruneAFn {
     }
     qstar[gs] = (uint8_t)qs;
     need[(size_t)qs * list_stride + gs] = 1;
+    // The other quantities are decided after the exact maximum of qs is known (ExtremaPruneCFn): certified below it, or
+    // computed exactly in a SECOND launch -- which holds a handful of polynomials and lasts as long as the slowest of them
+    // (a Jenkins-Traub launch is bound by its slowest warp: profiles/r01_final_ncu_launches_step.csv).  `best` is a LOWER
+    // estimate of what that exact maximum will be; a quantity that cannot be certified even against it would not be
+    // certified against the exact value in most cases either, so its root finding joins this first launch.  Marked with a
+    // negative rq; computing a maximum exactly instead of certifying it never changes a stretch factor.
+    const double Mlo = (1.0 < best) ? best : 1.0;
+    for (int q = 0; q < 9; ++q) {
+      if (q == qs || !(rq[gs * 9 + q] > Mlo)) continue;
+      const int d = q % 3;
+      const double lim = L[limit_index(q)];
+      const double thr = (d == 0 ? lim * Mlo : (d == 1 ? lim * Mlo * Mlo : lim * Mlo * Mlo * Mlo)) * (1.0 - 1e-9);
+      if (!certify_quantity_le(coef, T, q, thr)) {
+        rq[gs * 9 + q] = -1.0;
+        need[(size_t)q * list_stride + gs] = 1;
+      }
+    }
   }
 };
 struct ExtremaPruneCFn {
@@ -673,6 +690,7 @@ struct ExtremaPruneCFn {
     const double M = (1.0 < m) ? m : 1.0;
     for (int q = 0; q < 9; ++q) {
       if (q == qs) continue;
+      if (rq[gs * 9 + q] < 0.0) continue;  // already exact (first launch)
       bool drop = rq[gs * 9 + q] <= M;
       if (!drop) {
         // largest maximum of q whose transformed ratio stays below M: L*M, L*M^2, L*M^3 (with a margin)
