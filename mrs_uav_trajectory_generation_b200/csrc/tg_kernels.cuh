@@ -366,6 +366,9 @@ struct CoefCostFn {
   TG_HD void operator()(size_t item0) const {
     const size_t inst = inst0 + item0 / (size_t)per_items;
     const int it = (int)(item0 % (size_t)per_items);
+    run(inst, it);
+  }
+  TG_HD void run(size_t inst, int it) const {
     const size_t item = inst * (size_t)per_inst + it;
     SolveInst I;
     if (!desc.instance(inst, I)) return;
@@ -407,6 +410,26 @@ struct CoefCostFn {
     if (I.cost_out) {
       const double* Q = rec + TG_REC_Q;
       part[item] = (I.r == 2) ? cost_partial<2>(c, Q) : ((I.r == 3) ? cost_partial<3>(c, Q) : cost_partial<4>(c, Q));
+    }
+  }
+};
+// The same for the perturbed points of a Mellinger evaluation (SolveProblemDesc mode 3), organised by PROBLEM: 128
+// consecutive items (one CTA of k_for_each) belong to one problem and share its (variant, segment, dimension) items among
+// them, so that a problem that needs no gradient costs one flag test per thread instead of a scan of all its items --
+// late evaluations need gradients for a few per cent of the problems (profiles/r01_final_ncu_launches_step.csv).
+struct CoefCostGradFn {
+  CoefCostFn<SolveProblemDesc> f;
+  int p0;  // first problem of this launch
+  TG_HD void operator()(size_t item0) const {
+    const BatchPtrs& b = f.desc.b;
+    const int p = p0 + (int)(item0 >> 7), t = (int)(item0 & 127);
+    if (!b.need_grad[p] || b.lb[p].done) return;
+    const int s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0, v0 = s0 + p;
+    if (S == 1) return;
+    const int per = S * TG_D, total = S * per;  // variants 1..S
+    for (int k = t; k < total; k += 128) {
+      const int n = 1 + k / per, it = k - (n - 1) * per;
+      f.run((size_t)(v0 + n), it);
     }
   }
 };

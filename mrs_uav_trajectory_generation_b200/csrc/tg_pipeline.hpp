@@ -586,7 +586,9 @@ class Pipeline {
     // coefficients + partial costs: one thread per (instance, segment, dimension); with runs, each run is launched over
     // its own largest segment count instead of the group's
     const int per = 4 * b.smax;
-    if (buckets && buckets->size() > 1) {
+    if (coef_cost_by_problem(n_inst, desc, b, buckets, per)) {
+      // perturbed points of a Mellinger evaluation: one CTA per problem (CoefCostGradFn)
+    } else if (buckets && buckets->size() > 1) {
       for (const SolveBucket& k : *buckets) {
         const size_t i0 = per_vertex ? k.v0 : (size_t)k.p0, i1 = per_vertex ? k.v1 : (size_t)k.p1;
         const int items = 4 * std::max(k.s_cap, 1);
@@ -598,6 +600,13 @@ class Pipeline {
     }
     be_.for_each(n_inst, CostSumFn<D>{desc, per, b.part});
     launches(2);
+  }
+
+  bool coef_cost_by_problem(size_t, const SolveSweepDesc&, const BatchPtrs&, const std::vector<SolveBucket>*, int) { return false; }
+  bool coef_cost_by_problem(size_t, const SolveProblemDesc& desc, const BatchPtrs& b, const std::vector<SolveBucket>*, int per) {
+    if (desc.mellinger != 3) return false;
+    be_.for_each((size_t)b.B * 128, CoefCostGradFn{CoefCostFn<SolveProblemDesc>{desc, per, b.part, 0, per}, 0});
+    return true;
   }
 
   // PolynomialOptimizationNonLinear<10>::optimize() for every problem of the batch: Mellinger outer loop (nl_impl.h:159-234,
