@@ -449,6 +449,10 @@ struct NonlinearOptimizationParameters {
   double f_abs = -1, f_rel = 0.05, x_rel = 0.1, x_abs = -1;  // node.cpp:884-887
   int max_iterations = 10;                                   // NLopt maxeval (config/private/trajectory_generation.yaml:10)
   TimeAllocMethod time_alloc_method = kMellingerOuterLoop;   // config/private/trajectory_generation.yaml:7
+  double initial_stepsize_rel = 0.1;                         // nl.h:58
+  double time_penalty = 500.0;                               // nl.h:73
+  bool use_soft_constraints = true;                          // nl.h:88
+  double soft_constraint_weight = 100.0;                     // nl.h:91
   bool print_debug_info = false, print_debug_info_time_allocation = false;
 };
 
@@ -485,12 +489,46 @@ class PolynomialOptimizationNonLinear {
     else if (dimension == 2) idx = 2 * d + 1;
     else idx = 6 + d;
     limits_[idx] = maximum_value;
+    constraint_derivative_.push_back(derivative);
+    constraint_value_.push_back(maximum_value);
+    return true;
+  }
+  // The objective of the derivative-free methods at K candidate vectors in ONE batched call: objectiveFunctionTime
+  // (nl_impl.h:567-614; kSquaredTime, kRichterTime: x = the S segment times) / objectiveFunctionTimeAndConstraints
+  // (nl_impl.h:651-722; the ...AndConstraints methods: x = S times, then the free derivatives dimension-major), with
+  // evaluateMaximumMagnitudeAsSoftConstraint (740-762) over the constraints added so far.  The reference evaluates one x per
+  // NLopt callback; a derivative-free optimiser on the B200 evaluates a whole iteration's trial points here.
+  // parts (optional): K x {cost_trajectory, cost_time, cost_soft_constraints}.
+  bool evaluateObjectives(const std::vector<std::vector<double>>& x, std::vector<double>* total, std::vector<double>* parts = nullptr) const {
+    const int method = (int)optimization_parameters_.time_alloc_method;
+    if (!total || x.empty() || method == NonlinearOptimizationParameters::kMellingerOuterLoop || method > 4) return false;
+    const size_t nvar = x.front().size();
+    std::vector<double> flat;
+    flat.reserve(x.size() * nvar);
+    for (const std::vector<double>& xi : x) {
+      if (xi.size() != nvar) return false;
+      flat.insert(flat.end(), xi.begin(), xi.end());
+    }
+    total->assign(x.size(), 0.0);
+    if (parts) parts->assign(3 * x.size(), 0.0);
+    const int V = (int)poly_opt_.vertexMasks().size();
+    b200::Context& c = b200::Context::instance();
+    const int r = poly_opt_.getDerivativeToOptimize() < 2 ? 2 : poly_opt_.getDerivativeToOptimize();
+    const int rc = tg_objective_batch(c.get(), V, poly_opt_.vertexMasks().data(), poly_opt_.vertexValues().data(), r, method, (long long)x.size(),
+                                      flat.data(), (int)nvar, optimization_parameters_.time_penalty, optimization_parameters_.use_soft_constraints ? 1 : 0,
+                                      optimization_parameters_.soft_constraint_weight, (int)constraint_derivative_.size(),
+                                      constraint_derivative_.data(), constraint_value_.data(), total->data(), parts ? parts->data() : nullptr, nullptr);
+    if (rc != TG_OK) {
+      std::printf("[PolynomialOptimizationNonLinear]: evaluateObjectives failed: %s\n", tg_last_error(c.get()));
+      return false;
+    }
     return true;
   }
   // nl_impl.h:89-118: returns the NLopt-style result code (the node accepts >= 1 except 6, and -1; node.cpp:1138-1149)
   int optimize() {
     if (optimization_parameters_.time_alloc_method != NonlinearOptimizationParameters::kMellingerOuterLoop) {
-      std::printf("[PolynomialOptimizationNonLinear]: only kMellingerOuterLoop (the production default) runs on the B200 path\n");
+      std::printf("[PolynomialOptimizationNonLinear]: optimize() runs kMellingerOuterLoop (the production default); for the derivative-free methods "
+                  "evaluateObjectives() provides the batched objective (Python: api.DerivativeFreeTimeAllocation drives it)\n");
       return -1;
     }
     std::vector<double> times;
@@ -532,6 +570,8 @@ class PolynomialOptimizationNonLinear {
   NonlinearOptimizationParameters optimization_parameters_;
   OptimizationInfo optimization_info_;
   double limits_[9];
+  std::vector<int> constraint_derivative_;   // in the order the constraints were added (inequality_constraints_, nl.h:223)
+  std::vector<double> constraint_value_;
 };
 
 // ---- batch entry: the numeric core of optimize() / findTrajectory for many paths (node.cpp:620-851, 857-1209) -------------

@@ -107,6 +107,22 @@ int main(int argc, char** argv) {
     dump(f, "nl_maxmag", me, 3);
   }
 
+  // --- objective of the derivative-free methods at three candidate time vectors (kSquaredTime, soft constraints on)
+  {
+    NonlinearOptimizationParameters po;
+    po.time_alloc_method = NonlinearOptimizationParameters::kSquaredTime;
+    PolynomialOptimizationNonLinear<10> oo(4, po);
+    oo.setupFromVertices(vertices, times, derivative_to_optimize);
+    oo.addMaximumMagnitudeConstraint(0, derivative_order::VELOCITY, 4.0);
+    oo.addMaximumMagnitudeConstraint(0, derivative_order::ACCELERATION, 2.0);
+    std::vector<std::vector<double>> xs(3, times);
+    for (size_t i = 0; i < times.size(); ++i) { xs[1][i] *= 1.25; xs[2][i] *= 0.8; }
+    std::vector<double> total, parts;
+    if (!oo.evaluateObjectives(xs, &total, &parts)) return 6;
+    dump(f, "obj_total", total.data(), total.size());
+    dump(f, "obj_parts", parts.data(), parts.size());
+  }
+
   // --- batch entry: two paths through optimize() (findTrajectory + validation + subdivision)
   TrajectoryGeneratorBatch gen;
   std::vector<std::vector<Waypoint>> paths(2);

@@ -62,6 +62,10 @@ def _check(res):
     for k in (1, 2, 3):
         t, v, i = O.max_magnitude(ref["coef"], ref["times"], k)
         assert np.array_equal(res["nl_maxmag"][k - 1], [t, v, float(i)])
+    # evaluateObjectives: objectiveFunctionTime (kSquaredTime) with two soft constraints at three candidate time vectors
+    xs = np.stack([times, times * 1.25, times * 0.8])
+    rt, rp = O.objective(mask, vals, r, 0, xs, 500.0, True, 100.0, [1, 2], [4.0, 2.0])
+    assert np.array_equal(res["obj_total"][0], rt) and np.array_equal(res["obj_parts"][0].reshape(3, 3), rp)
     # TrajectoryGeneratorBatch: optimize() over two paths
     for p, path in enumerate([W.F1B_WAYPOINTS, W.F1A_WAYPOINTS]):
         o = O.optimize_path(path)
