@@ -5,14 +5,14 @@
 //   seg_off[B+1]             first segment of problem p; vertices start at seg_off[p] + p (V = S + 1)
 //   wp[totV][4], stop[totV]  waypoints x y z heading, stop_at flags
 //   vmask[totV], vval[totV][5][4], vfree[totV + B]   vertex constraints and free-unknown index (V+1 per problem)
-//   times/xeval/x/g/d[totS], hist_s/hist_y[11][totS], coef[totS][4][10], recs[totS*{1,3}][186], maxima[totS][9]
+//   times/xeval/x/g/d[totS], ix[totS], hist_s/hist_y[mf][totS], coef[totS][4][10], recs[totS*{1,3}][186], maxima[totS][9]
 //   costs[totV]              cost of solve instance (p, n): n = 0 base, n >= 1 perturbed segment n-1
 #ifndef TG_KERNELS_CUH_
 #define TG_KERNELS_CUH_
 
 #include "tg_common.cuh"
 #include "tg_bound.cuh"
-#include "tg_lbfgs.cuh"
+#include "tg_plis.cuh"
 #include "tg_node.cuh"
 #include "tg_poly.cuh"
 #include "tg_poly_vm.cuh"
@@ -56,7 +56,7 @@ struct ProbState {
   int sample_cap;
   int safe;
   int next_V;          // vertex count after subdivision (0: no re-solve needed)
-  int n_grads;         // Mellinger evaluations whose gradient was computed (<= n_evals)
+  int n_grads;         // Mellinger evaluations whose gradient was computed (PLIS consumes every one: == n_evals)
   double final_cost;   // cost reported by the optimiser (f at the last accepted point)
   double cost;         // cost of the final linear solve
   double baca_total;
@@ -78,7 +78,8 @@ struct BatchPtrs {
   int* hbw;
   int* stats;            // [0] max solve workspace doubles, [1] problems still to scale, [2] max octet-solve workspace doubles, [3] max np, [4] max S
   double *times, *baca, *xeval, *x, *g, *d, *hist_s, *hist_y;
-  LbfgsScalars* lb;
+  PlisScalars* opt;      // [B] optimiser state (tg_plis.cuh)
+  int* ix;               // [totS] PLIS bound codes / active set
   double* recs;
   double* costs;
   double* coef;
@@ -87,7 +88,6 @@ struct BatchPtrs {
   double* xs;            // [instances][xstride] solutions of the reduced systems (solve kernels -> CoefCostFn)
   double* part;          // [instances][4 * smax] partial costs
   int xstride, smax;
-  uint8_t* need_grad;   // [B] set by LbfgsPeekFn: this evaluation's gradient (the S perturbed solves) is needed
 };
 
 TG_HD int vtx_off(const BatchPtrs& b, int p) { return b.seg_off[p] + p; }
@@ -161,25 +161,11 @@ struct SetupBaseFn {
 };
 struct SetupMellingerFn {
   BatchPtrs b;
-  int phase;  // 0: all three records of every segment; 1: the base record only (item = segment); 2: the +0.1 / -corr records
-              // of the problems whose gradient is needed (item = 2 * segment + {0, 1})
-  TG_HD void operator()(size_t item0) const {
-    size_t gs;
-    int which;
-    if (phase == 1) {
-      gs = item0;
-      which = 0;
-    } else if (phase == 2) {
-      gs = item0 >> 1;
-      which = 1 + (int)(item0 & 1);
-    } else {
-      gs = item0 / 3;
-      which = (int)(item0 - gs * 3);
-    }
-    const size_t item = gs * 3 + which;
+  TG_HD void operator()(size_t item) const {  // item = 3 * segment + which
+    const size_t gs = item / 3;
+    const int which = (int)(item - gs * 3);
     const int p = b.prob_of_seg[gs];
-    if (b.lb[p].done) return;
-    if (phase == 2 && !b.need_grad[p]) return;
+    if (b.opt[p].done) return;
     const int S = b.seg_off[p + 1] - b.seg_off[p];
     if (S == 1 && which != 0) return;
     double T = b.xeval[gs];
@@ -199,23 +185,20 @@ struct SetupMellingerFn {
 struct SolveProblemDesc {
   BatchPtrs b;
   // 0: instance = problem, base times, one record per segment (final solve, linear batch)
-  // 1: instance = vertex index = (problem, variant), every variant of every running problem (one Mellinger evaluation)
-  // 2: instance = problem, variant 0 of a Mellinger evaluation (the base point; three records per segment)
-  // 3: instance = vertex index, variants >= 1 of the problems whose gradient is needed (b.need_grad)
+  // 1: instance = vertex index = (problem, variant), every variant of every running problem (one Mellinger evaluation:
+  //    variant 0 the point itself, variant n >= 1 the point perturbed along segment n-1; three records per segment)
   int mellinger;
   double* dp_out; // optional [sum np][4]-> per problem offset by 4*vfree base (only base mode), may be null
   const int* dp_off;
   TG_HD bool instance(size_t inst, SolveInst& I) const {
     int p, n;
-    if (mellinger == 1 || mellinger == 3) {
+    if (mellinger == 1) {
       p = b.prob_of_vtx[inst];
       n = (int)inst - vtx_off(b, p);
-      if (b.lb[p].done) return false;
-      if (mellinger == 3 && (n == 0 || !b.need_grad[p])) return false;
+      if (b.opt[p].done) return false;
     } else {
       p = (int)inst;
       n = 0;
-      if (mellinger == 2 && b.lb[p].done) return false;
     }
     const int s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0, v0 = s0 + p;
     if (mellinger && S == 1 && n > 0) return false;
@@ -413,22 +396,21 @@ struct CoefCostFn {
     }
   }
 };
-// The same for the perturbed points of a Mellinger evaluation (SolveProblemDesc mode 3), organised by PROBLEM: 128
-// consecutive items (one CTA of k_for_each) belong to one problem and share its (variant, segment, dimension) items among
-// them, so that a problem that needs no gradient costs one flag test per thread instead of a scan of all its items --
-// late evaluations need gradients for a few per cent of the problems (profiles/r01_final_ncu_launches_step.csv).
+// The same for all points of a Mellinger evaluation (SolveProblemDesc mode 1), organised by PROBLEM: 128 consecutive items
+// (one CTA of k_for_each) belong to one problem and share its (variant, segment, dimension) items among them, so that a
+// problem whose optimiser has finished costs one flag test per thread instead of a scan of all its items -- late
+// evaluations run for a few per cent of the problems.
 struct CoefCostGradFn {
   CoefCostFn<SolveProblemDesc> f;
   int p0;  // first problem of this launch
   TG_HD void operator()(size_t item0) const {
     const BatchPtrs& b = f.desc.b;
     const int p = p0 + (int)(item0 >> 7), t = (int)(item0 & 127);
-    if (!b.need_grad[p] || b.lb[p].done) return;
+    if (b.opt[p].done) return;
     const int s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0, v0 = s0 + p;
-    if (S == 1) return;
-    const int per = S * TG_D, total = S * per;  // variants 1..S
+    const int per = S * TG_D, total = (S == 1) ? per : (S + 1) * per;  // variants 0..S
     for (int k = t; k < total; k += 128) {
-      const int n = 1 + k / per, it = k - (n - 1) * per;
+      const int n = k / per, it = k - n * per;
       f.run((size_t)(v0 + n), it);
     }
   }
@@ -449,65 +431,54 @@ struct CostSumFn {
   }
 };
 
-// ---- 5. L-BFGS state machine: one thread per problem -----------------------------------------------------------------------
-TG_HD LbfgsVectors lbfgs_vectors(const BatchPtrs& b, int p) {
-  LbfgsVectors v;
+// ---- 5. PLIS state machine (tg_plis.cuh): one thread per problem ---------------------------------------------------------
+TG_HD PlisVectors plis_vectors(const BatchPtrs& b, int p) {
+  PlisVectors v;
   const int s0 = b.seg_off[p];
   v.x = b.x + s0;
-  v.g = b.g + s0;
-  v.d = b.d + s0;
+  v.gf = b.g + s0;
+  v.s = b.d + s0;
   v.xeval = b.xeval + s0;
-  v.hist_s = b.hist_s + s0;
-  v.hist_y = b.hist_y + s0;
+  v.xo = b.hist_s + s0;
+  v.go = b.hist_y + s0;
+  v.ix = b.ix + s0;
   v.hstride = (size_t)b.totS;
   return v;
 }
-struct LbfgsBeginFn {
+struct PlisBeginFn {
   BatchPtrs b;
+  int max_evals;
   TG_HD void operator()(size_t pi) const {
     const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
-    lbfgs_begin(S, b.lb[p], lbfgs_vectors(b, p), b.times + s0);
+    plis_begin(S, b.opt[p], plis_vectors(b, p), b.times + s0, max_evals);
   }
 };
-// after the base solve of an evaluation: problems that do not need this evaluation's gradient advance at once
-struct LbfgsPeekFn {
+// after the S+1 solves of one evaluation; stats[7] counts the problems that still run
+struct PlisAdvanceFn {
   BatchPtrs b;
   int max_evals;
   double f_rel, x_rel;
   TG_HD void operator()(size_t pi) const {
     const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
-    LbfgsScalars& st = b.lb[p];
-    b.need_grad[p] = 0;
+    PlisScalars& st = b.opt[p];
     if (st.done) return;
-    const double* costs = b.costs + vtx_off(b, p);
-    const LbfgsVectors v = lbfgs_vectors(b, p);
-    if (lbfgs_needs_gradient(S, st, v, costs[0], max_evals, f_rel, x_rel, -1.0, -1.0)) b.need_grad[p] = 1;
-    else lbfgs_advance(S, st, v, costs, max_evals, f_rel, x_rel, -1.0, -1.0, false);
-  }
-};
-// after the perturbed solves: the others advance with the full gradient
-struct LbfgsAdvanceFn {
-  BatchPtrs b;
-  int max_evals;
-  double f_rel, x_rel;
-  TG_HD void operator()(size_t pi) const {
-    const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
-    LbfgsScalars& st = b.lb[p];
-    if (st.done || !b.need_grad[p]) return;
-    lbfgs_advance(S, st, lbfgs_vectors(b, p), b.costs + vtx_off(b, p), max_evals, f_rel, x_rel, -1.0, -1.0, true);
+    plis_advance(S, st, plis_vectors(b, p), b.costs + vtx_off(b, p), max_evals, f_rel, x_rel, -1.0);
+    if (!st.done) TG_ATOMIC_ADD(&b.stats[7], 1);
   }
 };
 // after the loop: times <- last evaluated point (what poly_opt_ holds when nlopt returns, nl_impl.h:210-215)
-struct LbfgsFinishFn {
+struct PlisFinishFn {
   BatchPtrs b;
   TG_HD void operator()(size_t pi) const {
     const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
     for (int i = 0; i < S; ++i) b.times[s0 + i] = b.xeval[s0 + i];
     ProbState& ps = b.ps[p];
-    ps.nlopt_code = b.lb[p].code;
-    ps.n_evals = b.lb[p].n_evals;
-    ps.n_grads = b.lb[p].n_grads;
-    ps.final_cost = b.lb[p].f;
+    const PlisScalars& st = b.opt[p];
+    ps.nlopt_code = st.code;
+    ps.n_evals = st.n_evals;
+    ps.n_grads = st.n_evals;
+    ps.final_cost = st.f;
+    if (st.n_evals == 0) ps.scale_done = 1;  // start point outside the bounds: nlopt throws before any evaluation, no scaling (nl_impl.h:192-194)
     const int code = ps.nlopt_code;
     if (!((code >= 1 && code != 6) || code == -1)) ps.status = kFindNloptRejected;  // node.cpp:1138-1149
   }

@@ -180,7 +180,6 @@ class Pipeline {
     g.ps.resize(B);
     be_.d2h(g.ps.data(), g.d_ps, sizeof(ProbState) * B);
     if (P.run_time_alloc) {
-      counters.mellinger_launches += P.max_evals;
       int executed = 0;
       be_.d2h(&executed, b.stats + 5, sizeof(int));
       counters.root_finds_executed += executed;
@@ -587,7 +586,7 @@ class Pipeline {
     // its own largest segment count instead of the group's
     const int per = 4 * b.smax;
     if (coef_cost_by_problem(n_inst, desc, b, buckets, per)) {
-      // perturbed points of a Mellinger evaluation: one CTA per problem (CoefCostGradFn)
+      // all points of a Mellinger evaluation: one CTA per problem (CoefCostGradFn)
     } else if (buckets && buckets->size() > 1) {
       for (const SolveBucket& k : *buckets) {
         const size_t i0 = per_vertex ? k.v0 : (size_t)k.p0, i1 = per_vertex ? k.v1 : (size_t)k.p1;
@@ -604,7 +603,7 @@ class Pipeline {
 
   bool coef_cost_by_problem(size_t, const SolveSweepDesc&, const BatchPtrs&, const std::vector<SolveBucket>*, int) { return false; }
   bool coef_cost_by_problem(size_t, const SolveProblemDesc& desc, const BatchPtrs& b, const std::vector<SolveBucket>*, int per) {
-    if (desc.mellinger != 3) return false;
+    if (desc.mellinger != 1) return false;
     be_.for_each((size_t)b.B * 128, CoefCostGradFn{CoefCostFn<SolveProblemDesc>{desc, per, b.part, 0, per}, 0});
     return true;
   }
@@ -615,32 +614,36 @@ class Pipeline {
   // stretched times in b.times (the caller runs the final solve).
   void time_alloc_core(BatchPtrs& b, const Params& P, const int* stats, const std::vector<SolveBucket>* buckets = nullptr) {
     const int B = b.B, totS = b.totS, totV = b.totV;
+    const int mf = (P.max_evals > 0) ? std::min(std::max(P.max_evals, 1), kPlisMfMax) : kPlisMfMax;
     b.xeval = scratch_.template alloc<double>(totS);
     b.x = scratch_.template alloc<double>(totS);
     b.g = scratch_.template alloc<double>(totS);
     b.d = scratch_.template alloc<double>(totS);
-    b.hist_s = scratch_.template alloc<double>((size_t)(kLbfgsMem + 1) * totS);
-    b.hist_y = scratch_.template alloc<double>((size_t)(kLbfgsMem + 1) * totS);
-    b.lb = scratch_.template alloc<LbfgsScalars>(B);
+    b.ix = scratch_.template alloc<int>(totS);
+    b.hist_s = scratch_.template alloc<double>((size_t)mf * totS);
+    b.hist_y = scratch_.template alloc<double>((size_t)mf * totS);
+    b.opt = scratch_.template alloc<PlisScalars>(B);
     b.recs = scratch_.template alloc<double>((size_t)totS * 3 * TG_REC_SIZE);
     b.costs = scratch_.template alloc<double>(totV);
     b.maxima = scratch_.template alloc<double>((size_t)totS * 9);
-    b.need_grad = scratch_.template alloc<uint8_t>(B);
-    be_.for_each(B, LbfgsBeginFn{b}); launches(1);
-    // One evaluation = the base solve of every running problem, then -- only where the optimiser will consume a gradient
-    // (lbfgs_needs_gradient: first evaluation, or an accepted trial after which the iteration goes on) -- the S perturbed
-    // solves of nl_impl.h:282-323.  Rejected trials and final evaluations read the base cost alone: two evaluations out of
-    // three on the bench workload.  The costs that are consumed are the same numbers as before, so are all results.
-    for (int e = 0; e < P.max_evals; ++e) {
-      be_.for_each((size_t)totS, SetupMellingerFn{b, 1});
-      solve_with_outputs((size_t)B, stats, SolveProblemDesc{b, 2, nullptr, nullptr}, b, buckets, false);
-      be_.for_each(B, LbfgsPeekFn{b, P.max_evals, P.f_rel, P.x_rel});
-      be_.for_each((size_t)totS * 2, SetupMellingerFn{b, 2});
-      solve_with_outputs((size_t)totV, stats, SolveProblemDesc{b, 3, nullptr, nullptr}, b, buckets, true);
-      be_.for_each(B, LbfgsAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel});
-      launches(6);
+    be_.for_each(B, PlisBeginFn{b, P.max_evals}); launches(1);
+    // One evaluation = S+1 linear solves per running problem: the point itself and its S perturbed neighbours
+    // (nl_impl.h:282-323).  PLIS consumes the gradient of EVERY evaluation (the directional derivative at each line-search
+    // trial decides between acceptance, extrapolation and interpolation), so all of them are computed.  maxeval is tested
+    // between iterations only, so a line search may overrun it: loop until no problem is left running.
+    const int eval_cap = (P.max_evals > 0 ? P.max_evals : 1000) + 64;
+    for (int e = 0; e < eval_cap; ++e) {
+      be_.dev_memset(b.stats + 7, 0, sizeof(int));
+      be_.for_each((size_t)totS * 3, SetupMellingerFn{b});
+      solve_with_outputs((size_t)totV, stats, SolveProblemDesc{b, 1, nullptr, nullptr}, b, buckets, true);
+      be_.for_each(B, PlisAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel});
+      launches(3);
+      counters.mellinger_launches += 1;
+      int running = 0;
+      be_.d2h(&running, b.stats + 7, sizeof(int));
+      if (running == 0) break;
     }
-    be_.for_each(B, LbfgsFinishFn{b}); launches(1);
+    be_.for_each(B, PlisFinishFn{b}); launches(1);
     // time scaling (nl_impl.h:335-427 -> eth/trajectory.cpp:598-692)
     scale_loop(b, P.limits);
   }

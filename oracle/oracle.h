@@ -29,6 +29,7 @@
 #ifndef ORACLE_ORACLE_H_
 #define ORACLE_ORACLE_H_
 
+#include <cmath>
 #include <cstdint>
 #include <array>
 #include <vector>
@@ -161,7 +162,17 @@ struct NlInfo {
 };
 // nl_impl.h:256-333 ; leaves the solver at `times`
 double mellinger_cost_and_grad(LinearSolver& ls, std::vector<double>* grad, int* n_solves);
-// nl_impl.h:159-234 (LD_LBFGS replaced by the documented deterministic L-BFGS)
+// NLopt LD_LBFGS = Luksan's PLIS, restated from the published algorithm (oracle/plis.cpp; NLopt is not vendored).
+typedef double (*PlisObjective)(int n, const double* x, double* grad, void* data);
+struct PlisStop {
+  int maxeval = 0;          // 0 = no limit; tested between iterations only
+  double xtol_rel = 0, ftol_rel = 0;
+  double xtol_abs = -1;     // nlopt_stop_dx's absolute tolerance (one value for all variables)
+  double minf_max = -HUGE_VAL;  // stopval
+  int nevals = 0;
+};
+int luksan_plis(int n, PlisObjective f, void* data, const double* lb, const double* ub, double* x, double* minf, PlisStop* stop);
+// nl_impl.h:159-234 with nlopt::LD_LBFGS -> luksan_plis
 int optimize_time_mellinger(LinearSolver& ls, const NlParams& p, const Limits& L, NlInfo* info);
 
 // ---- node level (src/mrs_trajectory_generation.cpp) --------------------------------------------------------
