@@ -71,7 +71,7 @@ typedef struct tg_result {
   int n_scale_passes;  /* passes of scaleSegmentTimesToMeetConstraints in the last findTrajectory */
   int overflow;        /* reserved (always 0: outputs are sized by the library) */
   double max_dev;      /* last measured path deviation [m] */
-  double final_cost;   /* objective at the optimiser's last accepted point */
+  double final_cost;   /* OptimizationInfo::cost_trajectory: objective at the last point the optimiser evaluated (nl_impl.h:646) */
   double baca_total;   /* sum of estimateSegmentTimesBaca (node.cpp:1048-1056) */
   long long total_solves, total_root_calls, total_evals; /* reference-equivalent work over all rounds */
 } tg_result;

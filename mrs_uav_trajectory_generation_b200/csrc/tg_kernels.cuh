@@ -57,7 +57,7 @@ struct ProbState {
   int safe;
   int next_V;          // vertex count after subdivision (0: no re-solve needed)
   int n_grads;         // Mellinger evaluations whose gradient was computed (PLIS consumes every one: == n_evals)
-  double final_cost;   // cost reported by the optimiser (f at the last accepted point)
+  double final_cost;   // OptimizationInfo::cost_trajectory: the cost at the last point the optimiser evaluated
   double cost;         // cost of the final linear solve
   double baca_total;
   double max_dev;
@@ -477,7 +477,7 @@ struct PlisFinishFn {
     ps.nlopt_code = st.code;
     ps.n_evals = st.n_evals;
     ps.n_grads = st.n_evals;
-    ps.final_cost = st.f;
+    ps.final_cost = st.f_last;
     if (st.n_evals == 0) ps.scale_done = 1;  // start point outside the bounds: nlopt throws before any evaluation, no scaling (nl_impl.h:192-194)
     const int code = ps.nlopt_code;
     if (!((code >= 1 && code != 6) || code == -1)) ps.status = kFindNloptRejected;  // node.cpp:1138-1149

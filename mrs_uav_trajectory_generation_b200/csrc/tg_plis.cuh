@@ -25,6 +25,7 @@ constexpr double kPlisHuge = 1e120;       // eta9
 struct PlisScalars {
   // plis_() locals that live across evaluations
   double f, fo, fp, p, po, pp, r, rp, rmin, rmax, dmax, umax, gmax, gnorm, snorm;
+  double f_last;  // cost at the last evaluated point = OptimizationInfo::cost_trajectory (nl_impl.h:646)
   // ps1l01 state
   double fl, fu, pl, pu, rl, ru;
   double uo[kPlisMfMax], vo[kPlisMfMax];
@@ -298,6 +299,7 @@ TG_HD bool plis_begin(int S, PlisScalars& st, const PlisVectors& v, const double
   st.mf = (max_evals > 0) ? imin(imax(max_evals, 1), kPlisMfMax) : kPlisMfMax;
   st.f = st.fp = st.p = st.po = st.pp = st.r = st.rp = st.rmin = st.umax = st.gmax = st.gnorm = st.snorm = 0.0;
   st.fl = st.fu = st.pl = st.pu = st.rl = st.ru = 0.0;
+  st.f_last = 0.0;
   st.fo = -1.0 / 0.0;  // minf_est
   st.rmax = kPlisHuge;
   st.dmax = kPlisHuge;
@@ -327,6 +329,7 @@ TG_HD bool plis_begin(int S, PlisScalars& st, const PlisVectors& v, const double
     st.done = 1;
     st.code = -1;
     st.f = TG_DBL_MAX;
+    st.f_last = 0.0;  // OptimizationInfo::cost_trajectory keeps its initial value
     return false;
   }
   plis_snap(S, v.x, v.ix);
@@ -347,6 +350,7 @@ TG_HD_NOINLINE void plis_advance(int S, PlisScalars& st, const PlisVectors& v, c
   int* ix = v.ix;
   st.n_evals += 1;
   st.f = costs[0];
+  st.f_last = costs[0];
   for (int i = 0; i < nf; ++i) v.gf[i] = mellinger_grad(S, costs, i);
   // where to resume: 0 = top of the iteration (L11120), 1 = direction (L11130), 2 = line search (L11170), 3 = L11175
   int at;

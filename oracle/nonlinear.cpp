@@ -66,12 +66,14 @@ struct ObjCtx {
   LinearSolver* ls;
   NlInfo* info;
   std::vector<double> x, g;
+  double last_f = 0.0;  // OptimizationInfo::cost_trajectory: written by every objective call (nl_impl.h:646)
 };
 // the C callback nlopt::opt hands to the algorithm (nlopt.hpp myvfunc): vectors in, vectors out
 double plis_objective(int n, const double* x, double* grad, void* data) {
   ObjCtx* c = static_cast<ObjCtx*>(data);
   c->x.assign(x, x + n);
   const double f = objective(*c->ls, c->x, &c->g, c->info);
+  c->last_f = f;
   for (int i = 0; i < n; ++i) grad[i] = c->g[i];
   return f;
 }
@@ -104,10 +106,10 @@ int optimize_time_mellinger(LinearSolver& ls, const NlParams& P, const Limits& L
       ls.solve();
       info->n_solves++;
       info->code = -1;
-      info->final_cost = DBL_MAX;
+      info->final_cost = 0.0;  // OptimizationInfo::cost_trajectory keeps its initial value
       return -1;
     }
-  ObjCtx ctx{&ls, info, {}, {}};
+  ObjCtx ctx{&ls, info, {}, {}, 0.0};
   PlisStop stop;
   stop.maxeval = P.max_evals;
   stop.xtol_rel = P.x_rel;
@@ -116,7 +118,9 @@ int optimize_time_mellinger(LinearSolver& ls, const NlParams& P, const Limits& L
   double fbest = DBL_MAX;
   int code = luksan_plis(S, plis_objective, &ctx, lb.data(), ub.data(), x.data(), &fbest, &stop);
   if (code < 0) code = -1;  // every exception lands in the same catch block (nl_impl.h:190-208)
-  info->final_cost = fbest;
+  // what a caller of the reference can observe is getOptimizationInfo().cost_trajectory = the cost at the LAST EVALUATED point
+  // (nlopt's own optimum `final_cost` is a local of optimizeTimeMellingerOuterLoop, printed in debug mode only)
+  info->final_cost = ctx.last_f;
   scale_with_violation(ls, L, info);
   info->code = code;
   return code;
