@@ -6,11 +6,19 @@
                         oracle/Makefile into oracle/_ref/libref_rpoly.so) for 600 polynomials of the kinds the path meets:
                         extremum polynomials of real trajectory segments (degrees 15/13/11/7/6/5), random polynomials
                         with exact zeros at the origin, vanishing leading coefficients, clustered zeros.
+  ref_eth.npz           outputs of the REFERENCE's own eth_trajectory_generation classes (every translation unit of the
+                        library compiled unmodified by oracle/Makefile into oracle/_ref/libref_eth.so against the stand-ins of
+                        oracle/ref_shim/) for eight random-flier problems: linear solve (coefficients, cost), Euclidean / Baca
+                        segment times, per-segment maxima, scaleSegmentTimesToMeetConstraints, sampleWholeTrajectory,
+                        PolynomialOptimizationNonLinear::optimize (Mellinger + LD_LBFGS stand-in).  The oracle must
+                        reproduce them bit for bit in glibc math mode (tests/test_golden.py); the GPU is compared with them
+                        within the published numeric floor (tests/test_gpu_parity.py).
   pipeline_oracle.npz   outputs of the oracle's full pipeline (findTrajectory + validation + subdivision) for the two
                         config-1 fixtures and eight random-flier paths: final waypoints, segment
-                        times, coefficients, samples, verdicts and counts.  A regression pin of the restatement itself
-                        (the reference cannot be built here: Eigen / NLopt / ROS absent).
+                        times, coefficients, samples, verdicts and counts.  A regression pin of the node-level restatement
+                        (src/mrs_trajectory_generation.cpp needs ROS and cannot be compiled here).
 """
+import ctypes as C
 import os
 import sys
 
@@ -45,6 +53,47 @@ def extremum_polys(coef):
                 v[j] = c[j + k + 1] * fact(k + 1, j + k + 1)
             out.append(v)
     return out
+
+
+def ref_eth_fixtures():
+    """Class-level input / output pairs computed by the reference's own code (oracle/_ref/libref_eth.so)."""
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_eth.so"))
+    dp, u8p = C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+    P = lambda a, t=dp: a.ctypes.data_as(t)
+    L = np.array(O.DEFAULT_LIMITS, dtype=np.float64)
+    store = {"n": np.array(8), "limits": L}
+    for q in range(8):
+        V = 11 if q < 6 else 4 + q
+        r = 2 if q % 3 != 2 else 4
+        wp = np.ascontiguousarray(W.random_flier_path(700 + q, V))
+        m = np.ones(V, np.uint8)
+        m[0] = m[-1] = (1 << (r + 1)) - 1
+        v = np.zeros((V, 5, 4))
+        v[:, 0, :] = wp
+        S = V - 1
+        e, b = np.zeros(S), np.zeros(S)
+        ref.ref_estimate_times(V, P(wp), P(L), P(e), P(b))
+        coef = np.zeros((S, 4, 10))
+        cost = C.c_double()
+        assert ref.ref_solve_linear(V, P(m, u8p), P(v), P(e), r, P(coef), C.byref(cost), None, None) == 0
+        mx = np.zeros((S, 9))
+        ref.ref_segment_maxima(S, P(coef), P(e), P(mx))
+        sc, st = coef.copy(), e.copy()
+        within = C.c_int()
+        ref.ref_scale_times(S, P(sc), P(st), P(L), C.byref(within))
+        smp = np.zeros((4096, 19))
+        tns = np.zeros(4096, np.int64)
+        n = ref.ref_sample(S, P(sc), P(st), C.c_double(0.2), 4096, P(smp), tns.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert n > 0
+        at, ac = e.copy(), np.zeros((S, 4, 10))
+        code, ne, fc = C.c_int(), C.c_int(), C.c_double()
+        ref.ref_time_alloc(V, P(m, u8p), P(v), P(at), r, 10, C.c_double(0.05), C.c_double(0.1), P(L), P(ac), C.byref(code), C.byref(ne), C.byref(fc))
+        store.update({f"wp_{q}": wp, f"mask_{q}": m, f"vals_{q}": v, f"r_{q}": np.array(r), f"euclid_{q}": e, f"baca_{q}": b, f"coef_{q}": coef,
+                      f"cost_{q}": np.array(cost.value), f"maxima_{q}": mx, f"scaled_coef_{q}": sc, f"scaled_times_{q}": st,
+                      f"within_{q}": np.array(within.value), f"samples_{q}": smp[:n].copy(), f"tns_{q}": tns[:n].copy(), f"alloc_times_{q}": at,
+                      f"alloc_coef_{q}": ac, f"alloc_meta_{q}": np.array([code.value, ne.value]), f"alloc_cost_{q}": np.array(fc.value)})
+    np.savez_compressed(os.path.join(HERE, "ref_eth.npz"), **store)
+    print("ref_eth.npz: 8 problems")
 
 
 def main():
@@ -88,6 +137,8 @@ def main():
         ok[i] = success
     np.savez_compressed(os.path.join(HERE, "rpoly_reference.npz"), coeffs=P, n_coeffs=n_c, re=RE, im=IM, n_roots=n_r, ok=ok)
     print("rpoly_reference.npz:", len(polys), "polynomials,", int(n_r.sum()), "zeros")
+
+    ref_eth_fixtures()
 
     paths = [W.F1A_WAYPOINTS, W.F1B_WAYPOINTS] + [W.random_flier_path(100 + p, 11) for p in range(8)]
     inits = [W.init14(W.F1A_INIT_HEADING), W.init14(W.F1B_INIT_HEADING)] + [None] * 8

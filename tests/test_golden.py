@@ -55,6 +55,36 @@ def test_oracle_rpoly_matches_live_reference_build(oracle):
         O.set_math_mode(O.MATH_DET)
 
 
+def _ref_eth_cases():
+    z = np.load(os.path.join(G, "ref_eth.npz"))
+    for q in range(int(z["n"])):
+        yield q, {k[: -len(f"_{q}")]: z[k] for k in z.files if k.endswith(f"_{q}")}, z["limits"]
+
+
+def test_oracle_matches_reference_class_vectors(oracle):
+    """ref_eth.npz holds outputs of the REFERENCE's own classes (compiled unmodified, oracle/_ref/libref_eth.so); the
+    restatement reproduces every one bit for bit in glibc math mode: segment-time estimates, linear solve + cost, per-segment
+    maxima, time scaling, sampling (count, time_from_start_ns, all 19 fields), Mellinger time allocation."""
+    O.set_math_mode(O.MATH_LIBM)
+    try:
+        for q, g, L in _ref_eth_cases():
+            r = int(g["r"])
+            e, b = O.estimate_times(g["wp"], L)
+            assert np.array_equal(e, g["euclid"]) and np.array_equal(b, g["baca"]), q
+            c, cost, _, _ = O.solve_linear(g["mask"], g["vals"], e, r)
+            assert np.array_equal(c, g["coef"]) and cost == float(g["cost"]), q
+            assert np.array_equal(O.segment_maxima(c, e), g["maxima"]), q
+            sc, st, _, within = O.scale_times(c, e, L)
+            assert np.array_equal(sc, g["scaled_coef"]) and np.array_equal(st, g["scaled_times"]) and int(within) == int(g["within"]), q
+            smp, tns = O.sample(sc, st, 0.2)
+            assert np.array_equal(tns, g["tns"]) and np.array_equal(smp, g["samples"]), q
+            a = O.time_alloc(g["mask"], g["vals"], e, r, O.default_params(derivative_to_optimize=r))
+            assert [a["nlopt_code"], a["n_evals"]] == list(g["alloc_meta"]) and a["final_cost"] == float(g["alloc_cost"]), q
+            assert np.array_equal(a["times"], g["alloc_times"]) and np.array_equal(a["coef"], g["alloc_coef"]), q
+    finally:
+        O.set_math_mode(O.MATH_DET)
+
+
 def _pipeline_cases():
     z = np.load(os.path.join(G, "pipeline_oracle.npz"))
     for p in range(int(z["n"])):
