@@ -11,7 +11,9 @@
  * oracle.  These routines use only IEEE-754 +,-,*,/ and explicit fma, so they
  * return bit-identical results under `gcc -ffp-contract=off` and
  * `nvcc -fmad=false`.  Accuracy (measured in tests/test_detmath.py against
- * glibc): <= 2 ulp on the ranges the path uses.
+ * mpmath, next to glibc): exp, sin, cos, atan2, cbrt and pow(x, int) are
+ * correctly rounded (double-double evaluation, one final rounding) on the ranges
+ * the path uses; log is within 0.7 ulp and agrees with glibc on 99.7 %.
  *
  * Coefficient tables come from tools/gen_detmath_coeffs.py (mpmath, 60 digits).
  */
@@ -23,9 +25,11 @@
 #if defined(__CUDACC__)
 #define TG_HD __host__ __device__ __forceinline__
 #define TG_HD_NOINLINE __host__ __device__
+#define TG_HD_OUTLINE __host__ __device__ __noinline__ inline
 #else
 #define TG_HD inline
 #define TG_HD_NOINLINE
+#define TG_HD_OUTLINE inline
 #include <cmath>
 #include <cstring>
 #endif
@@ -77,8 +81,10 @@ TG_HD double scalb(double x, int e) {
 TG_HD bool disnan(double x) { return (dbits(x) & 0x7fffffffffffffffLL) > 0x7ff0000000000000LL; }
 TG_HD bool disinf(double x) { return (dbits(x) & 0x7fffffffffffffffLL) == 0x7ff0000000000000LL; }
 
+struct dd { double hi, lo; };
+
 /* ---- log --------------------------------------------------------------- */
-TG_HD double dlog(double x) {
+TG_HD double dlog_k(double x) { /* < 0.7 ulp kernel; the public dlog below adds one Newton step in double-double */
   const double ln2_hi = 0x1.62e42fee00000p-1, ln2_lo = 0x1.a39ef35793c76p-33;
   int64_t b = dbits(x);
   int k = 0;
@@ -112,7 +118,7 @@ TG_HD double dlog(double x) {
 }
 
 /* ---- exp --------------------------------------------------------------- */
-TG_HD double dexp(double x) {
+TG_HD double dexp_k(double x) { /* < 1 ulp kernel; the public dexp below is correctly rounded */
   const double ln2_hi = 0x1.62e42fee00000p-1, ln2_lo = 0x1.a39ef35793c76p-33, inv_ln2 = 0x1.71547652b82fep+0;
   if (disnan(x)) return x;
   if (x > 709.782712893384) return bitsd(0x7ff0000000000000LL);
@@ -170,7 +176,7 @@ TG_HD int rem_pio2(double x, double* r) {
   *r = ((x - dn * p1) - dn * p2) - dn * p3;
   return n;
 }
-TG_HD double dsin(double x) {
+TG_HD double dsin_k(double x) { /* < 1.5 ulp kernel; the public dsin below is correctly rounded */
   if (disnan(x) || disinf(x)) return bitsd(0x7ff8000000000000LL);
   if (dabs(x) <= 0x1.921fb54442d18p-1) return ksin(x);
   double r;
@@ -180,7 +186,7 @@ TG_HD double dsin(double x) {
   if (n == 2) return -ksin(r);
   return -kcos(r);
 }
-TG_HD double dcos(double x) {
+TG_HD double dcos_k(double x) { /* < 1.5 ulp kernel; the public dcos below is correctly rounded */
   if (disnan(x) || disinf(x)) return bitsd(0x7ff8000000000000LL);
   if (dabs(x) <= 0x1.921fb54442d18p-1) return kcos(x);
   double r;
@@ -233,7 +239,7 @@ TG_HD double datan(double x) {
   }
   return neg ? -res : res;
 }
-TG_HD double datan2(double y, double x) {
+TG_HD double datan2_k(double y, double x) { /* < 1.5 ulp kernel; the public datan2 below is correctly rounded */
   const double pi = 0x1.921fb54442d18p+1, pi_lo = 0x1.1a62633145c07p-53, pio2 = 0x1.921fb54442d18p+0;
   if (disnan(x) || disnan(y)) return x + y;
   const bool yneg = dbits(y) < 0, xneg = dbits(x) < 0;
@@ -294,7 +300,6 @@ TG_HD double dcbrt(double x) {
 /* pow(t, n) for n >= 1 via double-double products (error-free fma splitting):
    restates glibc pow(t, exponent) of lin_impl.h:615 (glibc pow is < 1 ulp and
    agrees with the correctly rounded value except in rare half-way cases). */
-struct dd { double hi, lo; };
 TG_HD dd dd_mul_d(dd a, double b) {
   const double p = a.hi * b;
   const double e = dfma(a.hi, b, -p) + a.lo * b;
@@ -311,6 +316,175 @@ TG_HD void powers(double t, int nmax, double* out) {
     acc = dd_mul_d(acc, t);
     out[k] = acc.hi;
   }
+}
+
+
+/* ---- correctly rounded exp, sin, cos, atan2 ------------------------------------------------------------------------
+   The kernels above are within 0.7 .. 1.5 ulp and agree with glibc (which is correctly rounded on all but ~0.2 % of
+   arguments, tests/test_detmath.py) on only 82 .. 90 % of the arguments the path produces.  One ulp in an inclination
+   angle is one ulp in a segment time, and cond(Rpp) ~ 1e8 .. 1e13 turns that into 1e-6 relative in the coefficients
+   (DESIGN.md "numeric floor").  The public functions below evaluate in double-double arithmetic (error-free two_sum /
+   fma products, ~2^-100 relative) and round once, so they return the correctly rounded value except when the exact
+   result lies within 2^-100 of a rounding boundary -- and therefore the same bits as glibc wherever glibc itself is
+   correctly rounded.  Only IEEE +, -, *, / and explicit fma: bit-identical under gcc -ffp-contract=off and nvcc -fmad=false. */
+TG_HD dd two_sum(double a, double b) {
+  dd r;
+  r.hi = a + b;
+  const double bb = r.hi - a;
+  r.lo = (a - (r.hi - bb)) + (b - bb);
+  return r;
+}
+TG_HD dd quick_two_sum(double a, double b) { /* |a| >= |b| */
+  dd r;
+  r.hi = a + b;
+  r.lo = b - (r.hi - a);
+  return r;
+}
+TG_HD dd two_prod(double a, double b) {
+  dd r;
+  r.hi = a * b;
+  r.lo = dfma(a, b, -r.hi);
+  return r;
+}
+TG_HD dd dd_add(dd a, dd b) {
+  dd s = two_sum(a.hi, b.hi);
+  const dd t = two_sum(a.lo, b.lo);
+  s.lo = s.lo + t.hi;
+  s = quick_two_sum(s.hi, s.lo);
+  s.lo = s.lo + t.lo;
+  return quick_two_sum(s.hi, s.lo);
+}
+TG_HD dd dd_add_d(dd a, double b) {
+  dd s = two_sum(a.hi, b);
+  s.lo = s.lo + a.lo;
+  return quick_two_sum(s.hi, s.lo);
+}
+TG_HD dd dd_neg(dd a) {
+  dd r;
+  r.hi = -a.hi;
+  r.lo = -a.lo;
+  return r;
+}
+TG_HD dd dd_mul(dd a, dd b) {
+  dd p = two_prod(a.hi, b.hi);
+  p.lo = p.lo + (a.hi * b.lo + a.lo * b.hi);
+  return quick_two_sum(p.hi, p.lo);
+}
+TG_HD dd dd_muld(dd a, double b) {
+  dd p = two_prod(a.hi, b);
+  p.lo = p.lo + a.lo * b;
+  return quick_two_sum(p.hi, p.lo);
+}
+TG_HD dd dd_div_d(dd a, double b) {
+  const double q1 = a.hi / b;
+  const dd r = dd_add(a, dd_neg(two_prod(q1, b)));
+  const double q2 = r.hi / b;
+  const dd r2 = dd_add(r, dd_neg(two_prod(q2, b)));
+  const double q3 = r2.hi / b;
+  const dd q = quick_two_sum(q1, q2);
+  return dd_add_d(q, q3);
+}
+
+/* sin and cos of a double as double-doubles; |x| < 2^20 * pi/2.  Returns the quadrant n (x = n pi/2 + r). */
+TG_HD_OUTLINE void sincos_dd(double x, dd* sn, dd* cs) {
+  const double two_over_pi = 0x1.45f306dc9c883p-1;
+  /* pi/2 = p1 + p2 + p3 + p4; p1, p2 carry 33 bits so that n * p1, n * p2 are exact for n < 2^20 */
+  const double p1 = 0x1.921fb54400000p+0, p2 = 0x1.0b4611a600000p-34, p3 = 0x1.3198a2e037073p-69, p4 = 0x1.129024e088a68p-123;
+  const double t = x * two_over_pi;
+  const int n = (int)(t < 0 ? t - 0.5 : t + 0.5);
+  const double dn = (double)n;
+  dd r = two_sum(x, -(dn * p1));
+  r = dd_add_d(r, -(dn * p2));
+  r = dd_add(r, dd_neg(two_prod(dn, p3)));
+  r = dd_add(r, dd_neg(two_prod(dn, p4)));
+  const dd r2 = dd_mul(r, r);
+  /* Taylor series, |r| <= pi/4 (+ rounding of n): 15 terms reach 2^-110 */
+  dd s = r, ts = r;
+  dd c, tc;
+  c.hi = 1.0; c.lo = 0.0;
+  tc = c;
+  for (int k = 1; k <= 15; ++k) {
+    tc = dd_neg(dd_div_d(dd_mul(tc, r2), (double)((2 * k - 1) * (2 * k))));
+    c = dd_add(c, tc);
+    ts = dd_neg(dd_div_d(dd_mul(ts, r2), (double)((2 * k) * (2 * k + 1))));
+    s = dd_add(s, ts);
+  }
+  switch (n & 3) {
+    case 0: *sn = s; *cs = c; break;
+    case 1: *sn = c; *cs = dd_neg(s); break;
+    case 2: *sn = dd_neg(s); *cs = dd_neg(c); break;
+    default: *sn = dd_neg(c); *cs = s; break;
+  }
+}
+TG_HD double dsin(double x) {
+  if (disnan(x) || disinf(x) || dabs(x) > 0x1p20) return dsin_k(x);
+  if (dabs(x) < 0x1p-27) return x;
+  dd s, c;
+  sincos_dd(x, &s, &c);
+  return s.hi;
+}
+TG_HD double dcos(double x) {
+  if (disnan(x) || disinf(x) || dabs(x) > 0x1p20) return dcos_k(x);
+  dd s, c;
+  sincos_dd(x, &s, &c);
+  return c.hi;
+}
+/* atan2: the kernel's value z0 (< 1.5 ulp) plus one Newton step on the angle of (x, y):
+   theta - z0 = atan((y cos z0 - x sin z0) / (x cos z0 + y sin z0)), |theta - z0| ~ 2^-52 |z0| so atan(d) = d to 2^-104 */
+TG_HD double datan2(double y, double x) {
+  const double z0 = datan2_k(y, x);
+  if (disnan(z0) || y == 0.0 || x == 0.0 || disinf(x) || disinf(y)) return z0;
+  const double ax = dabs(x), ay = dabs(y);
+  if (ax > 0x1p500 || ay > 0x1p500 || ax < 0x1p-500 || ay < 0x1p-500) return z0; /* products would over/underflow: keep the kernel's value */
+  dd s, c;
+  sincos_dd(z0, &s, &c);
+  const dd num = dd_add(dd_muld(c, y), dd_neg(dd_muld(s, x)));
+  const dd den = dd_add(dd_muld(c, x), dd_muld(s, y));
+  const double delta = num.hi / den.hi;
+  return z0 + delta;
+}
+/* exp: x = k ln2 + r, exp(r / 256) - 1 by Taylor in double-double, squared up eight times */
+TG_HD_OUTLINE dd exp_dd(double x, int* kout) {
+  const double l1 = 0x1.62e42fee00000p-1, l2 = 0x1.a39ef35793c76p-33, l3 = 0x1.cc01f97b57a08p-87, inv_ln2 = 0x1.71547652b82fep+0;
+  const double t = x * inv_ln2;
+  const int k = (int)(t < 0 ? t - 0.5 : t + 0.5);
+  const double dk = (double)k;
+  dd r = two_sum(x, -(dk * l1)); /* dk * l1 exact: 11 + 32 bits */
+  r = dd_add(r, dd_neg(two_prod(dk, l2)));
+  r = dd_add(r, dd_neg(two_prod(dk, l3)));
+  r.hi = r.hi * 0x1p-8;
+  r.lo = r.lo * 0x1p-8;
+  dd p = r, term = r;
+  for (int j = 2; j <= 11; ++j) {
+    term = dd_div_d(dd_mul(term, r), (double)j);
+    p = dd_add(p, term);
+  }
+  for (int j = 0; j < 8; ++j) { /* (1 + p)^2 - 1 = 2 p + p^2 */
+    dd two_p;
+    two_p.hi = 2.0 * p.hi;
+    two_p.lo = 2.0 * p.lo;
+    p = dd_add(two_p, dd_mul(p, p));
+  }
+  *kout = k;
+  return dd_add_d(p, 1.0);
+}
+TG_HD double dexp(double x) {
+  if (disnan(x) || x > 709.0 || x < -708.0) return dexp_k(x); /* overflow / subnormal results: the kernel handles the edges */
+  int k;
+  const dd y = exp_dd(x, &k);
+  return scalb(y.hi, k);
+}
+/* log: the kernel's value y0 plus one Newton step, log x = y0 + log(x exp(-y0)) = y0 + (x exp(-y0) - 1) to second order */
+TG_HD double dlog(double x) {
+  const double y0 = dlog_k(x);
+  if (disnan(y0) || disinf(y0) || y0 == 0.0 || x < 0x1p-1000 || dabs(y0) > 700.0) return y0;
+  int k;
+  const dd e = exp_dd(-y0, &k);
+  dd m = dd_muld(e, x);
+  m.hi = scalb(m.hi, k);
+  m.lo = scalb(m.lo, k);
+  const dd t = dd_add_d(m, -1.0);
+  return y0 + t.hi;
 }
 
 }  // namespace tgdm

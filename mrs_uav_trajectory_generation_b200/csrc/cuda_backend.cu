@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(TG_WARR_DEVICE_STRIDE) k_for_each_scratch(cons
 constexpr int kSolveWarps = 4;
 template <class D>
 __global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const size_t inst_begin, const size_t n_inst, const int ws_doubles, double* __restrict__ gws,
-                                                            const int skip_oct_ws) {
+                                                            const int skip_oct_ws, const bool skip_thread) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t gw = (size_t)blockIdx.x * kSolveWarps + warp, nw = (size_t)gridDim.x * kSolveWarps;
@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const 
   for (size_t inst = inst_begin + gw; inst < n_inst; inst += nw) {
     tg::SolveInst I;
     if (!desc.instance(inst, I)) continue;  // warp-uniform
+    if (skip_thread && tg::thread_eligible(I)) continue;  // k_solve_thread has taken it
     // skip_oct_ws > 0: the octet kernel has taken every instance it can take (same test as in k_solve_oct)
     if (skip_oct_ws > 0 && tg::octet_eligible(I) && tg::octet_ws_doubles(I.S, I.np) <= skip_oct_ws) continue;
     tg::solve_ws_bind(I, ws);
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) k_solve(const D desc, const 
 // elimination and the back substitution; L2 resident).
 template <class D>
 __global__ void __launch_bounds__(32) k_solve_oct(const D desc, const size_t inst_begin, const size_t n_inst, const int oct_ws_doubles, const int u_cap,
-                                                  double* __restrict__ uslab) {
+                                                  double* __restrict__ uslab, const bool skip_thread) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, oct = lane >> 3;
   const size_t gw = blockIdx.x, nw = gridDim.x;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(32) k_solve_oct(const D desc, const size_t ins
     tg::SolveInst I;
     const size_t inst = base + oct;
     bool ok = inst < n_inst && desc.instance(inst, I);
+    if (ok && skip_thread && tg::thread_eligible(I)) ok = false;  // k_solve_thread has taken it
     if (ok && !(tg::octet_eligible(I) && tg::octet_ws_doubles(I.S, I.np) <= oct_ws_doubles && I.np <= u_cap)) ok = false;
     if (!ok) {
       I.S = 0; I.np = 0; I.hbw = tg::kOctHbw; I.dp_out = nullptr; I.coef_out = nullptr; I.cost_out = nullptr;
@@ -88,6 +90,21 @@ __global__ void __launch_bounds__(32) k_solve_oct(const D desc, const size_t ins
       tg::solve_octets(&I, lane, nmax);
     }
     __syncwarp();
+  }
+}
+
+// One thread per solve instance (tg_solve_thread.cuh), grid-stride over instances.  slab: rows_cap rows of kThrRow doubles
+// per thread, interleaved by thread (element e of row r of thread t at slab[(r * kThrRow + e) * nthreads + t]) so that the
+// accesses of a warp coalesce.
+constexpr int kThreadSolveCta = 128;
+template <class D>
+__global__ void __launch_bounds__(kThreadSolveCta) k_solve_thread(const D desc, const size_t inst_begin, const size_t inst_end, double* __restrict__ slab) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t inst = inst_begin + tid; inst < inst_end; inst += nthreads) {
+    tg::SolveInst I;
+    if (!desc.instance(inst, I)) continue;
+    if (!tg::thread_eligible(I)) continue;
+    tg::solve_thread(I, slab + tid, nthreads);
   }
 }
 
@@ -246,6 +263,7 @@ struct CudaBackend {
     cudaSetDevice(device);
     if (scan_tmp) cudaFree(scan_tmp);
     if (solve_slab) cudaFree(solve_slab);
+    if (thread_slab) cudaFree(thread_slab);
     if (gen_slab) cudaFree(gen_slab);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -427,6 +445,38 @@ struct CudaBackend {
     return solve_slab;
   }
 
+  bool skip_thread_eligible = false;  // set by the pipeline after solve_thread(): the older kernels leave those instances alone
+  double* thread_slab = nullptr;
+  size_t thread_slab_doubles = 0;
+  int thread_ctas_per_sm = 0;
+  // Thread-per-instance solve of every eligible instance of [inst_begin, inst_end); rows_cap = slab rows per instance.
+  template <class D>
+  void solve_thread(size_t inst_begin, size_t inst_end, int rows_cap, const D& desc) {
+    if (inst_end <= inst_begin) return;
+    const size_t n_inst = inst_end - inst_begin;
+    if (thread_ctas_per_sm == 0) {
+      int a = 0;
+      TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_solve_thread<tg::SolveProblemDesc>, kThreadSolveCta, 0));
+      thread_ctas_per_sm = std::max(a, 1);
+      if (const char* e = std::getenv("TG_THREAD_CTAS")) thread_ctas_per_sm = std::max(1, std::atoi(e));
+    }
+    const size_t blocks_needed = (n_inst + kThreadSolveCta - 1) / kThreadSolveCta;
+    const size_t grid = std::min(blocks_needed, (size_t)sm_count * thread_ctas_per_sm);
+    const size_t need = grid * kThreadSolveCta * (size_t)rows_cap * tg::kThrRow;
+    if (need > thread_slab_doubles) {
+      if (thread_slab) {
+        TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        TG_CUDA_CHECK(cudaFree(thread_slab));
+      }
+      TG_CUDA_CHECK(cudaMalloc(&thread_slab, need * sizeof(double)));
+      thread_slab_doubles = need;
+    }
+    prof_begin();
+    k_solve_thread<D><<<(unsigned)grid, kThreadSolveCta, 0, stream>>>(desc, inst_begin, inst_end, thread_slab);
+    TG_CUDA_CHECK(cudaGetLastError());
+    prof_end((std::string("thread:") + typeid(D).name()).c_str(), n_inst);
+  }
+
   // Solves instances [inst_begin, inst_end).  oct_ws_doubles > 0: instances the octet routine can take (half bandwidth
   // 7, workspace <= oct_ws_doubles, at most np_cap unknowns) go to k_solve_oct; `mixed` says that others may be present,
   // which then go to the warp-per-instance kernel (ws_doubles of workspace each).
@@ -446,7 +496,7 @@ struct CudaBackend {
       const size_t l2_ctas = std::max<size_t>((size_t)sm_count, ((size_t)96 << 20) / (per_cta * sizeof(double)));
       grid = std::min(grid, l2_ctas);
       double* us = slab(grid * per_cta);
-      k_solve_oct<D><<<(unsigned)grid, 32, oct_smem, stream>>>(desc, inst_begin, inst_end, oct_ws_doubles, std::max(np_cap, 1), us);
+      k_solve_oct<D><<<(unsigned)grid, 32, oct_smem, stream>>>(desc, inst_begin, inst_end, oct_ws_doubles, std::max(np_cap, 1), us, skip_thread_eligible);
       TG_CUDA_CHECK(cudaGetLastError());
       prof_end(typeid(D).name(), n_inst);
       if (!mixed) return;
@@ -462,7 +512,7 @@ struct CudaBackend {
       TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve<D>, kSolveWarps * 32, smem));
       if (per_sm < 1) per_sm = 1;
       const size_t grid = std::min(blocks_needed, (size_t)sm_count * per_sm);
-      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, smem, stream>>>(desc, inst_begin, inst_end, ws_doubles, nullptr, skip);
+      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, smem, stream>>>(desc, inst_begin, inst_end, ws_doubles, nullptr, skip, skip_thread_eligible);
     } else {
       // long paths: per-warp workspace in a global slab (L2 resident), persistent grid
       const size_t grid = std::min(blocks_needed, (size_t)sm_count * 8);
@@ -475,7 +525,7 @@ struct CudaBackend {
         TG_CUDA_CHECK(cudaMalloc(&gen_slab, need * sizeof(double)));
         gen_slab_doubles = need;
       }
-      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, 0, stream>>>(desc, inst_begin, inst_end, ws_doubles, gen_slab, skip);
+      k_solve<D><<<(unsigned)grid, kSolveWarps * 32, 0, stream>>>(desc, inst_begin, inst_end, ws_doubles, gen_slab, skip, skip_thread_eligible);
     }
     TG_CUDA_CHECK(cudaGetLastError());
     prof_end(typeid(D).name(), n_inst);

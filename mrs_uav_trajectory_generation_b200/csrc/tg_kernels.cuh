@@ -19,6 +19,7 @@
 #include "tg_segment.cuh"
 #include "tg_solve.cuh"
 #include "tg_solve_octet.cuh"
+#include "tg_solve_thread.cuh"
 
 #if defined(__CUDA_ARCH__)
 #define TG_ATOMIC_MAX(p, v) atomicMax((p), (v))
@@ -76,7 +77,10 @@ struct BatchPtrs {
   int* vfree;
   int* np;
   int* hbw;
-  int* stats;            // [0] max solve workspace doubles, [1] problems still to scale, [2] max octet-solve workspace doubles, [3] max np, [4] max S
+  int* fmax;             // [B] largest number of free derivatives at one vertex
+  int* stats;            // [16]: [0] max solve workspace doubles, [1] problems still to scale, [2] max octet-solve workspace doubles, [3] max np, [4] max S,
+                         // [5] root findings executed, [6] problems the octet routine cannot take, [7] problems whose optimiser still runs,
+                         // [8] problems the thread-per-instance solve cannot take
   double *times, *baca, *xeval, *x, *g, *d, *hist_s, *hist_y;
   PlisScalars* opt;      // [B] optimiser state (tg_plis.cuh)
   int* ix;               // [totS] PLIS bound codes / active set
@@ -106,6 +110,13 @@ struct PrepareFn {
       np = index_vertices(V, b.vmask + v0, b.vfree + v0 + p, &hbw);
     b.np[p] = np;
     b.hbw[p] = hbw;
+    int fmax = 0;
+    for (int v = 0; v < V; ++v) {
+      const uint32_t m = b.vmask[v0 + v];
+      fmax = imax(fmax, TG_HALF - (int)((m & 1u) + ((m >> 1) & 1u) + ((m >> 2) & 1u) + ((m >> 3) & 1u) + ((m >> 4) & 1u)));
+    }
+    b.fmax[p] = fmax;
+    if (fmax > kThrB || np == 0) TG_ATOMIC_ADD(&b.stats[8], 1);
     TG_ATOMIC_MAX(&b.stats[0], solve_ws_doubles(S, np, hbw));
     TG_ATOMIC_MAX(&b.stats[3], np);
     TG_ATOMIC_MAX(&b.stats[4], S);
@@ -205,6 +216,7 @@ struct SolveProblemDesc {
     I.S = S;
     I.np = b.np[p];
     I.hbw = b.hbw[p];
+    I.fmax = b.fmax[p];
     I.variant = n;
     I.rec_stride = mellinger ? 3 : 1;
     I.r = b.r;
@@ -231,6 +243,7 @@ struct SolveSweepDesc {
     I.S = S;
     I.np = b.np[0];
     I.hbw = b.hbw[0];
+    I.fmax = b.fmax[0];
     I.variant = 0;
     I.rec_stride = 1;
     I.r = b.r;

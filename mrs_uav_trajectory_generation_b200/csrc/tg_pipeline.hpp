@@ -110,6 +110,7 @@ class Pipeline {
   BE& backend() { return be_; }
   Counters counters;
   bool prune_extrema = true;            // tg_bound.cuh certificates (exact); off only for A/B measurements (TG_NO_PRUNE)
+  bool use_thread_solve = std::getenv("TG_NO_THREAD_SOLVE") == nullptr;  // tg_solve_thread.cuh; off only for A/B measurements
   double scale_tolerance = 1e-3;        // eth/trajectory.cpp:604; tg_test_set_scale_tolerance changes it (tests only)
   size_t seg_budget = (size_t)1 << 21;  // max segments per group (bounds scratch memory: ~5.6 kB per segment)
 
@@ -130,19 +131,20 @@ class Pipeline {
     b.vfree = scratch_.template alloc<int>((size_t)totV + B);
     b.np = scratch_.template alloc<int>(B);
     b.hbw = scratch_.template alloc<int>(B);
-    b.stats = scratch_.template alloc<int>(8);
+    b.fmax = scratch_.template alloc<int>(B);
+    b.stats = scratch_.template alloc<int>(16);
     b.times = g.d_times;
     b.baca = scratch_.template alloc<double>(totS);
     b.coef = g.d_coef;
     b.ps = g.d_ps;
-    be_.dev_memset(b.stats, 0, 8 * sizeof(int));
+    be_.dev_memset(b.stats, 0, 16 * sizeof(int));
     be_.for_each(B, VtxProblemFn{g.d_seg_off, pov, pos}); launches(1);
     be_.for_each(B, PrepareFn{b, 1}); launches(1);
     TimesFn tf{b, {}};
     for (int i = 0; i < 9; ++i) tf.L[i] = P.limits[i];
     be_.for_each(totS, tf); launches(1);
     be_.for_each(B, BacaTotalFn{b}); launches(1);
-    int stats[8];
+    int stats[16];
     be_.d2h(stats, b.stats, sizeof(stats));
     const int ws = stats[0], ows = stats[2];
     alloc_solution_buffers(b, (size_t)(P.run_time_alloc ? totV : B), stats);
@@ -457,8 +459,8 @@ class Pipeline {
     int* pos = scratch_.template alloc<int>(std::max(b.totS, 1));
     b.prob_of_vtx = pov; b.prob_of_seg = pos;
     b.ps = scratch_.template alloc<ProbState>(B);
-    b.stats = scratch_.template alloc<int>(8);
-    be_.dev_memset(b.stats, 0, 8 * sizeof(int));
+    b.stats = scratch_.template alloc<int>(16);
+    be_.dev_memset(b.stats, 0, 16 * sizeof(int));
     be_.for_each(B, VtxProblemFn{o.d_seg_off, pov, pos});
     be_.for_each(B, InitStateFn{b.ps});
     launches(2);
@@ -479,6 +481,7 @@ class Pipeline {
     b.vfree = scratch_.template alloc<int>((size_t)b.totV + B);
     b.np = scratch_.template alloc<int>(B);
     b.hbw = scratch_.template alloc<int>(B);
+    b.fmax = scratch_.template alloc<int>(B);
     b.times = scratch_.template alloc<double>(b.totS);
     b.coef = scratch_.template alloc<double>((size_t)b.totS * TG_D * TG_N);
     b.recs = scratch_.template alloc<double>((size_t)b.totS * TG_REC_SIZE);
@@ -487,7 +490,7 @@ class Pipeline {
     be_.h2d(b.vval, vval, sizeof(double) * (size_t)b.totV * TG_HALF * TG_D);
     be_.h2d(b.times, times, sizeof(double) * b.totS);
     be_.for_each(B, PrepareFn{b, 0});
-    int stats[8];
+    int stats[16];
     be_.d2h(stats, b.stats, sizeof(stats));
     alloc_solution_buffers(b, (size_t)B, stats);
     be_.for_each(b.totS, SetupBaseFn{b, b.times});
@@ -555,7 +558,17 @@ class Pipeline {
   template <class D>
   void solve_with_outputs(size_t n_inst, const int* stats, const D& desc, const BatchPtrs& b, const std::vector<SolveBucket>* buckets = nullptr,
                           bool per_vertex = false) {
-    if (buckets && !buckets->empty()) {
+    // thread-per-instance kernel for every instance it can take (at most four free derivatives per vertex: the node's
+    // recipe always); the older kernels below then only see the rest (stats[8] = how many problems that is)
+    const bool thread_all = use_thread_solve && stats[8] == 0;
+    if (use_thread_solve) {
+      be_.solve_thread(0, n_inst, kThrB * (std::max(b.smax, 1) + 1), desc);
+      launches(1);
+    }
+    be_.skip_thread_eligible = use_thread_solve;
+    if (thread_all) {
+      // nothing left for the lane-parallel kernels
+    } else if (buckets && !buckets->empty()) {
       // one solve launch per stretch of runs that go to the same kernel at the same residency (many small launches cost more
       // in tails than tighter slabs gain: measured); a run is homogeneous by construction unless it is the collapsed one
       const bool mixed = mixed_single_;
@@ -664,13 +677,14 @@ class Pipeline {
     b.vfree = scratch_.template alloc<int>((size_t)b.totV + B);
     b.np = scratch_.template alloc<int>(B);
     b.hbw = scratch_.template alloc<int>(B);
+    b.fmax = scratch_.template alloc<int>(B);
     b.times = scratch_.template alloc<double>(b.totS);
     b.coef = scratch_.template alloc<double>((size_t)b.totS * TG_D * TG_N);
     be_.h2d(b.vmask, vmask, b.totV);
     be_.h2d(b.vval, vval, sizeof(double) * (size_t)b.totV * TG_HALF * TG_D);
     be_.h2d(b.times, times, sizeof(double) * b.totS);
     be_.for_each(B, PrepareFn{b, 0}); launches(1);
-    int stats[8];
+    int stats[16];
     be_.d2h(stats, b.stats, sizeof(stats));
     alloc_solution_buffers(b, (size_t)b.totV, stats);
     time_alloc_core(b, P, stats);
@@ -910,10 +924,11 @@ class Pipeline {
     b.vfree = scratch_.template alloc<int>((size_t)V + 1);
     b.np = scratch_.template alloc<int>(1);
     b.hbw = scratch_.template alloc<int>(1);
+    b.fmax = scratch_.template alloc<int>(1);
     be_.h2d(b.vmask, vmask, V);
     be_.h2d(b.vval, vval, sizeof(double) * (size_t)V * TG_HALF * TG_D);
     be_.for_each(1, PrepareFn{b, 0}); launches(1);
-    int stats[8];
+    int stats[16];
     be_.d2h(stats, b.stats, sizeof(stats));
     const long long chunk = std::min<long long>(K, (long long)sweep_chunk);
     alloc_solution_buffers(b, (size_t)chunk, stats);
@@ -973,10 +988,11 @@ class Pipeline {
     b.vfree = scratch_.template alloc<int>((size_t)V + 1);
     b.np = scratch_.template alloc<int>(1);
     b.hbw = scratch_.template alloc<int>(1);
+    b.fmax = scratch_.template alloc<int>(1);
     be_.h2d(b.vmask, vmask, V);
     be_.h2d(b.vval, vval, sizeof(double) * (size_t)V * TG_HALF * TG_D);
     be_.for_each(1, PrepareFn{b, 0}); launches(1);
-    int stats[8];
+    int stats[16];
     be_.d2h(stats, b.stats, sizeof(stats));
     const int n_free = stats[3];
     if (nvar != ((method >= 3) ? S + TG_D * n_free : S)) return -2;

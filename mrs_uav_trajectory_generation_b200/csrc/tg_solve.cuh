@@ -29,6 +29,7 @@ struct SolveInst {
   int S;                  // segments
   int np;                 // free unknowns per dimension
   int hbw;                // half bandwidth of Rpp
+  int fmax;               // largest number of free derivatives at one vertex (<= 4: the thread-per-instance kernel can take it)
   int variant;            // 0: base times; n >= 1: Mellinger perturbation of segment n-1 (nl_impl.h:282-311)
   int rec_stride;         // records per segment (1: base only, 3: base / +0.1 / -corr)
   int r;                  // derivative whose squared integral is minimised

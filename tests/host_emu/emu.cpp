@@ -86,6 +86,19 @@ struct EmuBackend {
     }
     return ((size_t)ws_doubles * sizeof(double) * 4 <= optin) ? 0 : -1;
   }
+  bool skip_thread_eligible = false;
+  // Mirrors CudaBackend::solve_thread: one work item per instance, slab rows contiguous (element stride 1)
+  template <class D>
+  void solve_thread(size_t inst_begin, size_t inst_end, int rows_cap, const D& desc) {
+    if (inst_end <= inst_begin) return;
+    parallel(inst_end - inst_begin, [&](size_t k) {
+      tg::SolveInst I;
+      if (!desc.instance(inst_begin + k, I) || !tg::thread_eligible(I)) return;
+      const double nan = std::numeric_limits<double>::quiet_NaN();
+      std::vector<double> slab((size_t)rows_cap * tg::kThrRow, nan);
+      tg::solve_thread(I, slab.data(), 1);
+    });
+  }
   // Mirrors CudaBackend::solve: instances the octet routine can take go through solve_octets in groups of four (one
   // "warp"), the others (when `mixed`) through solve_warp.
   template <class D>
@@ -110,7 +123,7 @@ struct EmuBackend {
         std::vector<double> ws((size_t)4 * oct_ws_doubles, nan), us((size_t)4 * np_cap * tg::kOctURow, nan);
         for (int o = 0; o < 4; ++o) {
           const size_t inst = grp * 4 + o;
-          const bool ok = inst < n_inst && desc.instance(inst, I[o]) && takes(I[o]);
+          const bool ok = inst < n_inst && desc.instance(inst, I[o]) && !(skip_thread_eligible && tg::thread_eligible(I[o])) && takes(I[o]);
           if (!ok) {
             I[o] = tg::SolveInst{};
             I[o].hbw = tg::kOctHbw;
@@ -125,6 +138,7 @@ struct EmuBackend {
     parallel(n_inst, [&](size_t inst) {
       tg::SolveInst I;
       if (!desc.instance(inst, I)) return;
+      if (skip_thread_eligible && tg::thread_eligible(I)) return;
       if (takes(I)) return;
       std::vector<double> ws((size_t)ws_doubles);
       tg::solve_ws_bind(I, ws.data());
