@@ -23,10 +23,12 @@
 #include <stdint.h>
 
 #if defined(__CUDACC__)
+#define TG_UNROLL _Pragma("unroll")
 #define TG_HD __host__ __device__ __forceinline__
 #define TG_HD_NOINLINE __host__ __device__
 #define TG_HD_OUTLINE __host__ __device__ __noinline__ inline
 #else
+#define TG_UNROLL
 #define TG_HD inline
 #define TG_HD_NOINLINE
 #define TG_HD_OUTLINE inline
@@ -385,8 +387,10 @@ TG_HD dd dd_div_d(dd a, double b) {
   return dd_add_d(q, q3);
 }
 
-/* sin and cos of a double as double-doubles; |x| < 2^20 * pi/2.  Returns the quadrant n (x = n pi/2 + r). */
-TG_HD_OUTLINE void sincos_dd(double x, dd* sn, dd* cs) {
+/* sin and cos of a double as double-doubles; |x| < 2^20 * pi/2.  x = n pi/2 + r, |r| <= pi/4; with z = r^2,
+   sin r = r + r z (S1 + S2 z + ...), cos r = 1 + z (C1 + C2 z + ...): the first eight coefficients are double-doubles
+   (Horner in double-double), the tail beyond z^8 contributes < 2^-54 and is evaluated in double.  which: 1 sin, 2 cos, 3 both. */
+TG_HD_OUTLINE void sincos_dd(double x, dd* sn, dd* cs, int which) {
   const double two_over_pi = 0x1.45f306dc9c883p-1;
   /* pi/2 = p1 + p2 + p3 + p4; p1, p2 carry 33 bits so that n * p1, n * p2 are exact for n < 2^20 */
   const double p1 = 0x1.921fb54400000p+0, p2 = 0x1.0b4611a600000p-34, p3 = 0x1.3198a2e037073p-69, p4 = 0x1.129024e088a68p-123;
@@ -397,17 +401,59 @@ TG_HD_OUTLINE void sincos_dd(double x, dd* sn, dd* cs) {
   r = dd_add_d(r, -(dn * p2));
   r = dd_add(r, dd_neg(two_prod(dn, p3)));
   r = dd_add(r, dd_neg(two_prod(dn, p4)));
-  const dd r2 = dd_mul(r, r);
-  /* Taylor series, |r| <= pi/4 (+ rounding of n): 15 terms reach 2^-110 */
-  dd s = r, ts = r;
-  dd c, tc;
-  c.hi = 1.0; c.lo = 0.0;
-  tc = c;
-  for (int k = 1; k <= 15; ++k) {
-    tc = dd_neg(dd_div_d(dd_mul(tc, r2), (double)((2 * k - 1) * (2 * k))));
-    c = dd_add(c, tc);
-    ts = dd_neg(dd_div_d(dd_mul(ts, r2), (double)((2 * k) * (2 * k + 1))));
-    s = dd_add(s, ts);
+  const dd z = dd_mul(r, r);
+  const bool odd = (n & 1) != 0;
+  const bool need_s = odd ? (which & 2) != 0 : (which & 1) != 0;  /* sin r feeds sin x in even quadrants, cos x in odd ones */
+  const bool need_c = odd ? (which & 1) != 0 : (which & 2) != 0;
+  dd s, c;
+  s.hi = s.lo = c.hi = c.lo = 0.0;
+  if (need_s) {
+    double tail = -0x1.434d2e783f5bcp-113;
+    tail = tail * z.hi + 0x1.259f98b4358adp-103;
+    tail = tail * z.hi + -0x1.d1ab1c2dccea3p-94;
+    tail = tail * z.hi + 0x1.3f3ccdd165fa9p-84;
+    tail = tail * z.hi + -0x1.761b41316381ap-75;
+    tail = tail * z.hi + 0x1.71b8ef6dcf572p-66;
+    tail = tail * z.hi + -0x1.2f49b46814157p-57;
+    const double shi[8] = {-0x1.5555555555555p-3, 0x1.1111111111111p-7, -0x1.a01a01a01a01ap-13, 0x1.71de3a556c734p-19,
+                           -0x1.ae64567f544e4p-26, 0x1.6124613a86d09p-33, -0x1.ae7f3e733b81fp-41, 0x1.952c77030ad4ap-49};
+    const double slo[8] = {-0x1.5555555555555p-57, 0x1.1111111111111p-63, -0x1.a01a01a01a01ap-73, -0x1.c154f8ddc6c00p-73,
+                           0x1.c062e06d1f209p-80, 0x1.f28e0cc748ebep-87, -0x1.1d8656b0ee8cbp-97, 0x1.ac981465ddc6cp-103};
+    dd acc;
+    acc.hi = tail;
+    acc.lo = 0.0;
+TG_UNROLL
+    for (int k = 7; k >= 0; --k) {
+      dd ck;
+      ck.hi = shi[k];
+      ck.lo = slo[k];
+      acc = dd_add(dd_mul(acc, z), ck);
+    }
+    s = dd_add(r, dd_mul(dd_mul(r, z), acc));
+  }
+  if (need_c) {
+    double tail = -0x1.3932c5047d60ep-108;
+    tail = tail * z.hi + 0x1.0a18a2635085dp-98;
+    tail = tail * z.hi + -0x1.88e85fc6a4e5ap-89;
+    tail = tail * z.hi + 0x1.f2cf01972f578p-80;
+    tail = tail * z.hi + -0x1.0ce396db7f853p-70;
+    tail = tail * z.hi + 0x1.e542ba4020225p-62;
+    tail = tail * z.hi + -0x1.6827863b97d97p-53;
+    const double chi[8] = {-0x1.0000000000000p-1, 0x1.5555555555555p-5, -0x1.6c16c16c16c17p-10, 0x1.a01a01a01a01ap-16,
+                           -0x1.27e4fb7789f5cp-22, 0x1.1eed8eff8d898p-29, -0x1.93974a8c07c9dp-37, 0x1.ae7f3e733b81fp-45};
+    const double clo[8] = {0.0, 0x1.5555555555555p-59, 0x1.f49f49f49f49fp-65, 0x1.a01a01a01a01ap-76,
+                           -0x1.cbbc05b4fa99ap-76, -0x1.2aec959e14c06p-83, -0x1.05d6f8a2efd1fp-92, 0x1.1d8656b0ee8cbp-101};
+    dd acc;
+    acc.hi = tail;
+    acc.lo = 0.0;
+TG_UNROLL
+    for (int k = 7; k >= 0; --k) {
+      dd ck;
+      ck.hi = chi[k];
+      ck.lo = clo[k];
+      acc = dd_add(dd_mul(acc, z), ck);
+    }
+    c = dd_add_d(dd_mul(z, acc), 1.0);
   }
   switch (n & 3) {
     case 0: *sn = s; *cs = c; break;
@@ -420,13 +466,13 @@ TG_HD double dsin(double x) {
   if (disnan(x) || disinf(x) || dabs(x) > 0x1p20) return dsin_k(x);
   if (dabs(x) < 0x1p-27) return x;
   dd s, c;
-  sincos_dd(x, &s, &c);
+  sincos_dd(x, &s, &c, 1);
   return s.hi;
 }
 TG_HD double dcos(double x) {
   if (disnan(x) || disinf(x) || dabs(x) > 0x1p20) return dcos_k(x);
   dd s, c;
-  sincos_dd(x, &s, &c);
+  sincos_dd(x, &s, &c, 2);
   return c.hi;
 }
 /* atan2: the kernel's value z0 (< 1.5 ulp) plus one Newton step on the angle of (x, y):
@@ -437,7 +483,7 @@ TG_HD double datan2(double y, double x) {
   const double ax = dabs(x), ay = dabs(y);
   if (ax > 0x1p500 || ay > 0x1p500 || ax < 0x1p-500 || ay < 0x1p-500) return z0; /* products would over/underflow: keep the kernel's value */
   dd s, c;
-  sincos_dd(z0, &s, &c);
+  sincos_dd(z0, &s, &c, 3);
   const dd num = dd_add(dd_muld(c, y), dd_neg(dd_muld(s, x)));
   const dd den = dd_add(dd_muld(c, x), dd_muld(s, y));
   const double delta = num.hi / den.hi;

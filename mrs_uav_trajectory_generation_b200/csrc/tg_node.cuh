@@ -268,8 +268,8 @@ TG_HD void sample_eval(const double* __restrict__ coef, double tin, double* __re
   const double px = poly_eval(coef + 0 * TG_N, tin, 0), py = poly_eval(coef + 1 * TG_N, tin, 0);
   const double pz = poly_eval(coef + 2 * TG_N, tin, 0), ph = poly_eval(coef + 3 * TG_N, tin, 0);
   const double ha = 0.5 * ph;
-  const double qw = tgdm::dcos(ha), qz = tgdm::dsin(ha);
-  const double yaw = tgdm::datan2(2.0 * (qw * qz + 0.0 * 0.0), 1.0 - 2.0 * (0.0 * 0.0 + qz * qz));
+  const double qw = tgdm::dcos_k(ha), qz = tgdm::dsin_k(ha);
+  const double yaw = tgdm::datan2_k(2.0 * (qw * qz + 0.0 * 0.0), 1.0 - 2.0 * (0.0 * 0.0 + qz * qz));
   xyzh[0] = px;
   xyzh[1] = py;
   xyzh[2] = pz;
@@ -443,8 +443,8 @@ TG_HD_NOINLINE int fallback_samples(int V, const double* __restrict__ wp, const 
         const double x = a[0] + c * (b[0] - a[0]), y = a[1] + c * (b[1] - a[1]), z = a[2] + c * (b[2] - a[2]);
         const double h = rad_interp(a[3], b[3], c);
         const double ha = 0.5 * h;
-        const double qw = tgdm::dcos(ha), qz = tgdm::dsin(ha);
-        const double yaw = tgdm::datan2(2.0 * (qw * qz + 0.0 * 0.0), 1.0 - 2.0 * (0.0 * 0.0 + qz * qz));
+        const double qw = tgdm::dcos_k(ha), qz = tgdm::dsin_k(ha);
+        const double yaw = tgdm::datan2_k(2.0 * (qw * qz + 0.0 * 0.0), 1.0 - 2.0 * (0.0 * 0.0 + qz * qz));
         for (int k = 0; k < reps; ++k) {
           double* o = out + 4 * (size_t)(n + k);
           o[0] = x;

@@ -344,7 +344,7 @@ TG_HD_NOINLINE void rpoly_dyn(const double* op, int* degree, double* zeror, doub
     double sc = lo / moduli_min;
     if (((sc <= 1.0) && (moduli_max >= 10)) || ((sc > 1.0) && (TG_FLT_MAX / sc >= moduli_max))) {
       sc = ((sc == 0) ? TG_FLT_MIN : sc);
-      const int l = (int)(tgdm::dlog(sc) / lb2 + 0.5);
+      const int l = (int)(tgdm::dlog_k(sc) / lb2 + 0.5);
       const double factor = tgdm::scalb(1.0, l);
       if (factor != 1.0)
         for (int i = 0; i < NN; i++) jt.p[i] = jt.p[i] * factor;
@@ -352,7 +352,7 @@ TG_HD_NOINLINE void rpoly_dyn(const double* op, int* degree, double* zeror, doub
     for (int i = 0; i < NN; i++) pt[i] = dabs(jt.p[i]);
     pt[N] = -(pt[N]);
     const int NM1 = N - 1;
-    double x = tgdm::dexp((tgdm::dlog(-pt[N]) - tgdm::dlog(pt[0])) / (double)N);
+    double x = tgdm::dexp_k((tgdm::dlog_k(-pt[N]) - tgdm::dlog_k(pt[0])) / (double)N);
     if (pt[NM1] != 0) {
       const double xm = -pt[N] / pt[NM1];
       x = ((xm < x) ? xm : x);

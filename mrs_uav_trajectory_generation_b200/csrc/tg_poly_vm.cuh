@@ -570,7 +570,7 @@ struct JtVm {
         double sc = TG_DIV(lo, moduli_min);
         if (((sc <= 1.0) && (moduli_max >= 10)) || ((sc > 1.0) && (TG_DIV(TG_FLT_MAX, sc) >= moduli_max))) {
           sc = ((sc == 0) ? TG_FLT_MIN : sc);
-          const int l = (int)(TG_DIV(tgdm::dlog(sc), lb2) + 0.5);
+          const int l = (int)(TG_DIV(tgdm::dlog_k(sc), lb2) + 0.5);
           const double factor = tgdm::scalb(1.0, l);
           if (factor != 1.0) {
 #pragma unroll 1
@@ -579,7 +579,7 @@ struct JtVm {
         }
         // upper estimate of the lower bound on the zero moduli; pt[i] = |p[i]|, pt[N] = -|p[N]|
         const double ptN = -dabs(p[N]), pt0 = dabs(p[0]), ptNM1 = dabs(p[N - 1]);
-        x = tgdm::dexp(TG_DIV(tgdm::dlog(-ptN) - tgdm::dlog(pt0), (double)N));
+        x = tgdm::dexp_k(TG_DIV(tgdm::dlog_k(-ptN) - tgdm::dlog_k(pt0), (double)N));
         if (ptNM1 != 0) {
           const double xm_ = TG_DIV(-ptN, ptNM1);
           x = ((xm_ < x) ? xm_ : x);

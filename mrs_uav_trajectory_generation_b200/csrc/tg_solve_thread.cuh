@@ -33,6 +33,24 @@ TG_HD bool thread_eligible(const SolveInst& I) { return I.fmax <= kThrB && I.np 
 // rows of slab one instance needs
 TG_HD int thread_slab_rows(int S) { return kThrB * (S + 1); }
 
+// software prefetch (device only): the H block of a record (800 bytes) / one slab element, into L1
+TG_HD void thr_prefetch_H(const double* __restrict__ rec) {
+#if defined(__CUDA_ARCH__)
+  const char* p = reinterpret_cast<const char*>(rec + TG_REC_H);
+#pragma unroll
+  for (int o = 0; o < 800 + 127; o += 128) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p + o));
+#else
+  (void)rec;
+#endif
+}
+TG_HD void thr_prefetch(const double* __restrict__ p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 struct ThrVertex {
   int f;        // real free unknowns (<= 4)
   int a[kThrB]; // derivative index of free unknown q (q < f)
@@ -112,6 +130,7 @@ TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t es
   const int S = I.S, V = S + 1;
   double D[kThrB][kThrB], U[kThrB][kThrB], L[kThrB][kThrB], Dn[kThrB][kThrB], b[kThrB][TG_D], bn[kThrB][TG_D];
   ThrVertex tv = thr_vertex(I.vmask[0]);
+  if (S > 1) thr_prefetch_H(solve_rec(I, 1));
   {
     const double* Hc = solve_rec(I, 0) + TG_REC_H;
     thr_diag(tv, nullptr, Hc, D);
@@ -121,7 +140,38 @@ TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t es
   for (int v = 0; v < V; ++v) {
     const bool has_next = v < S;
     ThrVertex tn = tv;
-    if (has_next) {
+    if (v + 2 < S) thr_prefetch_H(solve_rec(I, v + 2));  // needed one step from now (Hn of step v+1)
+    if (has_next && v + 2 <= S && tv.m == 1u && (I.vmask[v + 1] & 31u) == 1u && (I.vmask[v + 2] & 31u) == 1u) {
+      // the common interior step: vertices v, v+1, v+2 fix the position only (free derivatives 1..4 at static indices)
+      tn = tv;
+      const double* Hv = solve_rec(I, v) + TG_REC_H;
+      const double* Hn = solve_rec(I, v + 1) + TG_REC_H;
+#pragma unroll
+      for (int i = 0; i < kThrB; ++i)
+#pragma unroll
+        for (int j = 0; j < kThrB; ++j) {
+          U[i][j] = Hv[(i + 1) * TG_N + (TG_HALF + j + 1)];
+          L[i][j] = Hv[(TG_HALF + i + 1) * TG_N + (j + 1)];
+          Dn[i][j] = Hv[(TG_HALF + i + 1) * TG_N + (TG_HALF + j + 1)] + Hn[(i + 1) * TG_N + (j + 1)];
+        }
+      const double* f0 = I.vval + (size_t)v * TG_HALF * TG_D;         // fixed position of vertex v, v+1, v+2
+      const double* f1 = f0 + TG_HALF * TG_D;
+      const double* f2 = f1 + TG_HALF * TG_D;
+#pragma unroll
+      for (int i = 0; i < kThrB; ++i) {
+        const double r0 = -Hv[(TG_HALF + i + 1) * TG_N];
+        const double r1 = -(Hv[(TG_HALF + i + 1) * TG_N + TG_HALF] + Hn[(i + 1) * TG_N]);
+        const double r2 = -Hn[(i + 1) * TG_N + TG_HALF];
+#pragma unroll
+        for (int d = 0; d < TG_D; ++d) {
+          double acc = 0.0;
+          acc = acc + r0 * f0[d];
+          acc = acc + r1 * f1[d];
+          acc = acc + r2 * f2[d];
+          bn[i][d] = acc;
+        }
+      }
+    } else if (has_next) {
       tn = thr_vertex(I.vmask[v + 1]);
       const double* Hv = solve_rec(I, v) + TG_REC_H;                                   // segment v: couples v and v+1
       const double* Hn = (v + 1 < S) ? solve_rec(I, v + 1) + TG_REC_H : nullptr;        // segment v+1
@@ -194,6 +244,11 @@ TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t es
     }
   for (int v = V - 1; v >= 0; --v) {
     const bool has_next = v < S;
+    if (v > 0) {  // the rows of vertex v-1 start travelling towards L1
+      const double* nx = slab + (size_t)((v - 1) * kThrB * kThrRow) * estride;
+#pragma unroll
+      for (int e = 0; e < kThrB * kThrRow; ++e) thr_prefetch(nx + (size_t)e * estride);
+    }
 #pragma unroll
     for (int qq = 0; qq < kThrB; ++qq) {
       const int q = kThrB - 1 - qq;

@@ -19,6 +19,11 @@ double m_exp(double x) { return g_math_mode == kMathDet ? tgdm::dexp(x) : std::e
 double m_sin(double x) { return g_math_mode == kMathDet ? tgdm::dsin(x) : std::sin(x); }
 double m_cos(double x) { return g_math_mode == kMathDet ? tgdm::dcos(x) : std::cos(x); }
 double m_atan2(double y, double x) { return g_math_mode == kMathDet ? tgdm::datan2(y, x) : std::atan2(y, x); }
+double m_log_k(double x) { return g_math_mode == kMathDet ? tgdm::dlog_k(x) : std::log(x); }
+double m_exp_k(double x) { return g_math_mode == kMathDet ? tgdm::dexp_k(x) : std::exp(x); }
+double m_sin_k(double x) { return g_math_mode == kMathDet ? tgdm::dsin_k(x) : std::sin(x); }
+double m_cos_k(double x) { return g_math_mode == kMathDet ? tgdm::dcos_k(x) : std::cos(x); }
+double m_atan2_k(double y, double x) { return g_math_mode == kMathDet ? tgdm::datan2_k(y, x) : std::atan2(y, x); }
 double m_cbrt(double x) { return g_math_mode == kMathDet ? tgdm::dcbrt(x) : std::cbrt(x); }
 double m_pow_int(double t, int e) {
   if (g_math_mode == kMathDet) {

@@ -217,8 +217,8 @@ void fallback_sample(const std::vector<Waypoint>& wp, const Limits& L, double dt
       const Waypoint pt = interpolate_point(wp[i], wp[i + 1], (double)j * interp_step);
       // setFromYaw -> quaternion -> the heading getTrajectoryReference reads back (eth_mav_msgs/common.h:130-140)
       const double ha = 0.5 * pt.c[3];
-      const double qw = m_cos(ha), qz = m_sin(ha);
-      const double yaw = m_atan2(2.0 * (qw * qz + 0.0 * 0.0), 1.0 - 2.0 * (0.0 * 0.0 + qz * qz));
+      const double qw = m_cos_k(ha), qz = m_sin_k(ha);
+      const double yaw = m_atan2_k(2.0 * (qw * qz + 0.0 * 0.0), 1.0 - 2.0 * (0.0 * 0.0 + qz * qz));
       const std::array<double, 4> smp = {pt.c[0], pt.c[1], pt.c[2], yaw};
       out->push_back(smp);
       if (j == 0 && i > 0 && wp[i].stop_at) {

@@ -50,6 +50,13 @@ double m_sin(double x);
 double m_cos(double x);
 double m_atan2(double y, double x);
 double m_cbrt(double x);
+// the < 1.5 ulp kernels (not the correctly rounded versions) where a last-bit difference cannot reach a result the path reads:
+// Jenkins-Traub's starting radius (rpoly_ak1.cpp:227-246) and the heading's quaternion round trip (eth_mav_msgs/common.h:130-140)
+double m_log_k(double x);
+double m_exp_k(double x);
+double m_sin_k(double x);
+double m_cos_k(double x);
+double m_atan2_k(double y, double x);
 
 // base_coefficients_(k, i) = i!/(i-k)!  (eth/polynomial.cpp:155-170)
 double base_coeff(int k, int i);

@@ -356,7 +356,7 @@ void rpoly(const double* op, int* degree, double* zeror, double* zeroi) {
     double sc = lo / moduli_min;
     if (((sc <= 1.0) && (moduli_max >= 10)) || ((sc > 1.0) && (FLT_MAX / sc >= moduli_max))) {
       sc = ((sc == 0) ? FLT_MIN : sc);
-      const int l = (int)(m_log(sc) / lb2 + 0.5);
+      const int l = (int)(m_log_k(sc) / lb2 + 0.5);
       const double factor = std::ldexp(1.0, l);  // pow(2.0, l), exact
       if (factor != 1.0)
         for (int i = 0; i < NN; i++) jt.p[i] *= factor;
@@ -364,7 +364,7 @@ void rpoly(const double* op, int* degree, double* zeror, double* zeroi) {
     for (int i = 0; i < NN; i++) pt[i] = std::fabs(jt.p[i]);
     pt[N] = -(pt[N]);
     const int NM1 = N - 1;
-    double x = m_exp((m_log(-pt[N]) - m_log(pt[0])) / (double)N);
+    double x = m_exp_k((m_log_k(-pt[N]) - m_log_k(pt[0])) / (double)N);
     if (pt[NM1] != 0) {
       const double xm = -pt[N] / pt[NM1];
       x = ((xm < x) ? xm : x);

@@ -265,8 +265,8 @@ bool sample_whole(const std::vector<Segment>& seg, double dt, std::vector<Sample
     // quaternionFromYaw -> AngleAxis about z: w = cos(yaw/2), z = sin(yaw/2), x = y = 0;
     // yawFromQuaternion = atan2(2(wz + xy), 1 - 2(yy + zz))   (eth_mav_msgs/common.h:130-140)
     const double ha = 0.5 * sm.p[3];
-    const double qw = m_cos(ha), qz = m_sin(ha);
-    sm.yaw_out = m_atan2(2.0 * (qw * qz + 0.0 * 0.0), 1.0 - 2.0 * (0.0 * 0.0 + qz * qz));
+    const double qw = m_cos_k(ha), qz = m_sin_k(ha);
+    sm.yaw_out = m_atan2_k(2.0 * (qw * qz + 0.0 * 0.0), 1.0 - 2.0 * (0.0 * 0.0 + qz * qz));
     const size_t idx = out->size();
     sm.t_ns = (int64_t)((t_start + dt * (double)idx) * 1.e9);  // trajectory_sampling.cpp:83
     out->push_back(sm);
