@@ -241,6 +241,15 @@ struct CudaBackend {
     smem_optin = prop.sharedMemPerBlockOptin;
     smem_per_sm = prop.sharedMemPerMultiprocessor;
     force_general_solve = std::getenv("TG_NO_OCTET") != nullptr;
+    if (std::getenv("TG_NO_L2_PERSIST") == nullptr && prop.persistingL2CacheMaxSize > 0) {
+      size_t want = (size_t)prop.persistingL2CacheMaxSize;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+        cudaDeviceGetLimit(&l2_persist_bytes, cudaLimitPersistingL2CacheSize);
+        l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+      } else {
+        cudaGetLastError();
+      }
+    }
     {
       int a = 0, b = 0;
       TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_solve_oct<tg::SolveProblemDesc>, 32, 0));
@@ -446,6 +455,7 @@ struct CudaBackend {
   }
 
   bool skip_thread_eligible = false;  // set by the pipeline after solve_thread(): the older kernels leave those instances alone
+  size_t l2_persist_bytes = 0, l2_window_max = 0;  // persisting L2 set-aside and the largest access-policy window (0: unsupported / disabled)
   double* thread_slab = nullptr;
   size_t thread_slab_doubles = 0;
   int thread_ctas_per_sm = 0;
@@ -471,10 +481,30 @@ struct CudaBackend {
       TG_CUDA_CHECK(cudaMalloc(&thread_slab, need * sizeof(double)));
       thread_slab_doubles = need;
     }
+    // the slab is written and read back by the same resident threads over and over: keep as much of it as the device allows
+    // in the persisting part of L2, so that it does not stream through HBM (profiles/r02_solve_thread.md)
+    const bool persist = l2_persist_bytes > 0 && n_inst > (size_t)4096;
+    if (persist) {
+      cudaStreamAttrValue av;
+      std::memset(&av, 0, sizeof(av));
+      const size_t bytes = std::min(need * sizeof(double), (size_t)l2_window_max);
+      av.accessPolicyWindow.base_ptr = thread_slab;
+      av.accessPolicyWindow.num_bytes = bytes;
+      av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)l2_persist_bytes / (double)bytes);
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      TG_CUDA_CHECK(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     prof_begin();
     k_solve_thread<D><<<(unsigned)grid, kThreadSolveCta, 0, stream>>>(desc, inst_begin, inst_end, thread_slab);
     TG_CUDA_CHECK(cudaGetLastError());
     prof_end((std::string("thread:") + typeid(D).name()).c_str(), n_inst);
+    if (persist) {
+      cudaStreamAttrValue av;
+      std::memset(&av, 0, sizeof(av));
+      av.accessPolicyWindow.num_bytes = 0;
+      TG_CUDA_CHECK(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
   }
 
   // Solves instances [inst_begin, inst_end).  oct_ws_doubles > 0: instances the octet routine can take (half bandwidth

@@ -84,6 +84,11 @@ struct BatchPtrs {
   double *times, *baca, *xeval, *x, *g, *d, *hist_s, *hist_y;
   PlisScalars* opt;      // [B] optimiser state (tg_plis.cuh)
   int* ix;               // [totS] PLIS bound codes / active set
+  // work lists of the problems whose optimiser still runs, appended by PlisBeginFn / PlisAdvanceFn for the NEXT evaluation
+  // (two alternating buffers; lengths in stats[9 + 3 * buf .. 11 + 3 * buf]: problems, vertices = solve instances, segments)
+  int* act_prob[2];
+  int* act_vtx[2];
+  int* act_seg[2];
   double* recs;
   double* costs;
   double* coef;
@@ -172,9 +177,12 @@ struct SetupBaseFn {
 };
 struct SetupMellingerFn {
   BatchPtrs b;
-  TG_HD void operator()(size_t item) const {  // item = 3 * segment + which
-    const size_t gs = item / 3;
-    const int which = (int)(item - gs * 3);
+  const int* seg_list;  // null: item = 3 * segment + which over all segments; else over the listed segments
+  TG_HD void operator()(size_t item0) const {
+    const size_t k = item0 / 3;
+    const int which = (int)(item0 - k * 3);
+    const size_t gs = seg_list ? (size_t)seg_list[k] : k;
+    const size_t item = gs * 3 + which;
     const int p = b.prob_of_seg[gs];
     if (b.opt[p].done) return;
     const int S = b.seg_off[p + 1] - b.seg_off[p];
@@ -231,6 +239,12 @@ struct SolveProblemDesc {
     I.x_out = b.xs ? b.xs + (mellinger ? (size_t)(v0 + n) : inst) * (size_t)b.xstride : nullptr;
     return true;
   }
+};
+// the same instances taken from a work list (instance k of the launch = list[k])
+struct SolveProblemListDesc {
+  SolveProblemDesc d;
+  const int* list;
+  TG_HD bool instance(size_t k, SolveInst& I) const { return d.instance((size_t)list[k], I); }
 };
 // time-vector sweep (BASELINE config 5): K candidates for ONE problem, records laid out [candidate][segment]
 struct SolveSweepDesc {
@@ -416,9 +430,10 @@ struct CoefCostFn {
 struct CoefCostGradFn {
   CoefCostFn<SolveProblemDesc> f;
   int p0;  // first problem of this launch
+  const int* prob_list;  // or the listed problems
   TG_HD void operator()(size_t item0) const {
     const BatchPtrs& b = f.desc.b;
-    const int p = p0 + (int)(item0 >> 7), t = (int)(item0 & 127);
+    const int p = prob_list ? prob_list[item0 >> 7] : p0 + (int)(item0 >> 7), t = (int)(item0 & 127);
     if (b.opt[p].done) return;
     const int s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0, v0 = s0 + p;
     const int per = S * TG_D, total = (S == 1) ? per : (S + 1) * per;  // variants 0..S
@@ -433,7 +448,9 @@ struct CostSumFn {
   D desc;
   int per_inst;
   const double* part;
-  TG_HD void operator()(size_t inst) const {
+  const int* inst_list = nullptr;  // null: every instance; else the listed ones
+  TG_HD void operator()(size_t k) const {
+    const size_t inst = inst_list ? (size_t)inst_list[k] : k;
     SolveInst I;
     if (!desc.instance(inst, I)) return;
     if (!I.cost_out) return;
@@ -458,12 +475,23 @@ TG_HD PlisVectors plis_vectors(const BatchPtrs& b, int p) {
   v.hstride = (size_t)b.totS;
   return v;
 }
+// a running problem enters the work lists of the next evaluation (buffer `buf`)
+TG_HD void plis_enlist(const BatchPtrs& b, int p, int buf) {
+  const int s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0, v0 = s0 + p;
+  int* cnt = b.stats + 9 + 3 * buf;
+  const int jp = TG_ATOMIC_ADD_RET(&cnt[0], 1);
+  b.act_prob[buf][jp] = p;
+  const int jv = TG_ATOMIC_ADD_RET(&cnt[1], S + 1);
+  for (int n = 0; n <= S; ++n) b.act_vtx[buf][jv + n] = v0 + n;
+  const int js = TG_ATOMIC_ADD_RET(&cnt[2], S);
+  for (int i = 0; i < S; ++i) b.act_seg[buf][js + i] = s0 + i;
+}
 struct PlisBeginFn {
   BatchPtrs b;
   int max_evals;
   TG_HD void operator()(size_t pi) const {
     const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
-    plis_begin(S, b.opt[p], plis_vectors(b, p), b.times + s0, max_evals);
+    if (plis_begin(S, b.opt[p], plis_vectors(b, p), b.times + s0, max_evals)) plis_enlist(b, p, 0);
   }
 };
 // after the S+1 solves of one evaluation; stats[7] counts the problems that still run
@@ -471,12 +499,17 @@ struct PlisAdvanceFn {
   BatchPtrs b;
   int max_evals;
   double f_rel, x_rel;
-  TG_HD void operator()(size_t pi) const {
-    const int p = (int)pi, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
+  const int* prob_list;  // null: every problem; else the listed ones
+  int next_buf;          // work-list buffer of the next evaluation
+  TG_HD void operator()(size_t k) const {
+    const int p = prob_list ? prob_list[k] : (int)k, s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0;
     PlisScalars& st = b.opt[p];
     if (st.done) return;
     plis_advance(S, st, plis_vectors(b, p), b.costs + vtx_off(b, p), max_evals, f_rel, x_rel, -1.0);
-    if (!st.done) TG_ATOMIC_ADD(&b.stats[7], 1);
+    if (!st.done) {
+      TG_ATOMIC_ADD(&b.stats[7], 1);
+      plis_enlist(b, p, next_buf);
+    }
   }
 };
 // after the loop: times <- last evaluated point (what poly_opt_ holds when nlopt returns, nl_impl.h:210-215)

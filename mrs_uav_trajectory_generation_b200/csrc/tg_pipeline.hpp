@@ -610,14 +610,14 @@ class Pipeline {
     } else {
       be_.for_each(n_inst * (size_t)per, CoefCostFn<D>{desc, per, b.part, 0, per});
     }
-    be_.for_each(n_inst, CostSumFn<D>{desc, per, b.part});
+    be_.for_each(n_inst, CostSumFn<D>{desc, per, b.part, nullptr});
     launches(2);
   }
 
   bool coef_cost_by_problem(size_t, const SolveSweepDesc&, const BatchPtrs&, const std::vector<SolveBucket>*, int) { return false; }
   bool coef_cost_by_problem(size_t, const SolveProblemDesc& desc, const BatchPtrs& b, const std::vector<SolveBucket>*, int per) {
     if (desc.mellinger != 1) return false;
-    be_.for_each((size_t)b.B * 128, CoefCostGradFn{CoefCostFn<SolveProblemDesc>{desc, per, b.part, 0, per}, 0});
+    be_.for_each((size_t)b.B * 128, CoefCostGradFn{CoefCostFn<SolveProblemDesc>{desc, per, b.part, 0, per}, 0, nullptr});
     return true;
   }
 
@@ -639,22 +639,50 @@ class Pipeline {
     b.recs = scratch_.template alloc<double>((size_t)totS * 3 * TG_REC_SIZE);
     b.costs = scratch_.template alloc<double>(totV);
     b.maxima = scratch_.template alloc<double>((size_t)totS * 9);
+    for (int k = 0; k < 2; ++k) {
+      b.act_prob[k] = scratch_.template alloc<int>(B);
+      b.act_vtx[k] = scratch_.template alloc<int>(totV);
+      b.act_seg[k] = scratch_.template alloc<int>(totS);
+    }
+    be_.dev_memset(b.stats + 9, 0, 6 * sizeof(int));
     be_.for_each(B, PlisBeginFn{b, P.max_evals}); launches(1);
     // One evaluation = S+1 linear solves per running problem: the point itself and its S perturbed neighbours
     // (nl_impl.h:282-323).  PLIS consumes the gradient of EVERY evaluation (the directional derivative at each line-search
     // trial decides between acceptance, extrapolation and interpolation), so all of them are computed.  maxeval is tested
     // between iterations only, so a line search may overrun it: loop until no problem is left running.
+    // Most problems stop after three or four evaluations; the tail runs for up to ~30.  Once fewer than half of the
+    // problems are left, the launches walk the work lists that PlisAdvanceFn wrote for them (problems, solve instances,
+    // segments still running) instead of scanning the whole batch for the few that are.
     const int eval_cap = (P.max_evals > 0 ? P.max_evals : 1000) + 64;
+    int cnt[3] = {B, totV, totS};
+    const bool lists_ok = use_thread_solve && stats[8] == 0;  // the lane-parallel kernels scan (done problems drop out at once)
     for (int e = 0; e < eval_cap; ++e) {
+      const int buf = e & 1, nbuf = buf ^ 1;
+      const bool sparse = lists_ok && e > 0 && (size_t)cnt[0] * 2 < (size_t)B;
       be_.dev_memset(b.stats + 7, 0, sizeof(int));
-      be_.for_each((size_t)totS * 3, SetupMellingerFn{b});
-      solve_with_outputs((size_t)totV, stats, SolveProblemDesc{b, 1, nullptr, nullptr}, b, buckets, true);
-      be_.for_each(B, PlisAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel});
-      launches(3);
+      be_.dev_memset(b.stats + 9 + 3 * nbuf, 0, 3 * sizeof(int));
+      if (sparse) {
+        const SolveProblemDesc desc{b, 1, nullptr, nullptr};
+        const int per = 4 * b.smax;
+        be_.for_each((size_t)cnt[2] * 3, SetupMellingerFn{b, b.act_seg[buf]});
+        be_.solve_thread(0, (size_t)cnt[1], kThrB * (std::max(b.smax, 1) + 1), SolveProblemListDesc{desc, b.act_vtx[buf]});
+        be_.for_each((size_t)cnt[0] * 128, CoefCostGradFn{CoefCostFn<SolveProblemDesc>{desc, per, b.part, 0, per}, 0, b.act_prob[buf]});
+        be_.for_each((size_t)cnt[1], CostSumFn<SolveProblemDesc>{desc, per, b.part, b.act_vtx[buf]});
+        be_.for_each((size_t)cnt[0], PlisAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel, b.act_prob[buf], nbuf});
+        launches(5);
+      } else {
+        be_.for_each((size_t)totS * 3, SetupMellingerFn{b, nullptr});
+        solve_with_outputs((size_t)totV, stats, SolveProblemDesc{b, 1, nullptr, nullptr}, b, buckets, true);
+        be_.for_each(B, PlisAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel, nullptr, nbuf});
+        launches(3);
+      }
       counters.mellinger_launches += 1;
-      int running = 0;
-      be_.d2h(&running, b.stats + 7, sizeof(int));
-      if (running == 0) break;
+      int back[8];  // stats[7 .. 14]
+      be_.d2h(back, b.stats + 7, sizeof(back));
+      if (back[0] == 0) break;
+      cnt[0] = back[2 + 3 * nbuf];
+      cnt[1] = back[3 + 3 * nbuf];
+      cnt[2] = back[4 + 3 * nbuf];
     }
     be_.for_each(B, PlisFinishFn{b}); launches(1);
     // time scaling (nl_impl.h:335-427 -> eth/trajectory.cpp:598-692)

@@ -129,6 +129,7 @@ TG_HD void thr_diag(const ThrVertex& tv, const double* __restrict__ Hp, const do
 TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t estride) {
   const int S = I.S, V = S + 1;
   double D[kThrB][kThrB], U[kThrB][kThrB], L[kThrB][kThrB], Dn[kThrB][kThrB], b[kThrB][TG_D], bn[kThrB][TG_D];
+  thr_prefetch_H(solve_rec(I, 0));
   ThrVertex tv = thr_vertex(I.vmask[0]);
   if (S > 1) thr_prefetch_H(solve_rec(I, 1));
   {
@@ -244,8 +245,8 @@ TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t es
     }
   for (int v = V - 1; v >= 0; --v) {
     const bool has_next = v < S;
-    if (v > 0) {  // the rows of vertex v-1 start travelling towards L1
-      const double* nx = slab + (size_t)((v - 1) * kThrB * kThrRow) * estride;
+    if (v > 1) {  // the rows of vertex v-2 start travelling towards L1 (two vertices ahead of their use)
+      const double* nx = slab + (size_t)((v - 2) * kThrB * kThrRow) * estride;
 #pragma unroll
       for (int e = 0; e < kThrB * kThrRow; ++e) thr_prefetch(nx + (size_t)e * estride);
     }
