@@ -151,14 +151,7 @@ TG_HD double thr_cost_partial(const double (&c)[TG_N], const double* __restrict_
 // the thread has the derivatives of both ends of segment v in registers when the back substitution reaches vertex v.  The
 // partial costs wait in the part of the slab that the back substitution has already consumed and are added in ascending
 // (segment, dimension) order at the end, as computeCost does.
-#if defined(__CUDA_ARCH__)
-#define TG_THR_PHASE __device__ __noinline__
-#else
-#define TG_THR_PHASE static inline
-#endif
-// forward elimination and back substitution are separate out-of-line functions: nothing but the slab passes between them,
-// and the register allocation of one (96 doubles of window) does not squeeze the other (coefficients and cost)
-TG_THR_PHASE void solve_thread_forward(const SolveInst& I, double* __restrict__ slab, size_t estride) {
+TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t estride, bool fuse) {
   const int S = I.S, V = S + 1;
   double D[kThrB][kThrB], U[kThrB][kThrB], L[kThrB][kThrB], Dn[kThrB][kThrB], b[kThrB][TG_D], bn[kThrB][TG_D];
   thr_prefetch_H(solve_rec(I, 0));
@@ -266,9 +259,6 @@ TG_THR_PHASE void solve_thread_forward(const SolveInst& I, double* __restrict__ 
       tv = tn;
     }
   }
-}
-TG_THR_PHASE void solve_thread_backward(const SolveInst& I, double* __restrict__ slab, size_t estride, bool fuse) {
-  const int S = I.S, V = S + 1;
   // ---- back substitution: far columns first (vertex v+1's unknowns 3..0, then this vertex's 3..q+1), x = s * (1/pivot) -----
   double xn[kThrB][TG_D], x[kThrB][TG_D];
 #pragma unroll
@@ -323,7 +313,7 @@ TG_THR_PHASE void solve_thread_backward(const SolveInst& I, double* __restrict__
         const double* fv = I.vval + (size_t)v * TG_HALF * TG_D;
         const double* fn = fv + TG_HALF * TG_D;
         double* pslot = slab + (size_t)((v + 1) * kThrB * kThrRow) * estride;  // rows of vertex v+1: consumed
-#pragma unroll
+#pragma unroll 1
         for (int d = 0; d < TG_D; ++d) {
           double nd[TG_N], c[TG_N];
 #pragma unroll
@@ -380,10 +370,6 @@ TG_THR_PHASE void solve_thread_backward(const SolveInst& I, double* __restrict__
     }
     *I.cost_out = 0.5 * total;
   }
-}
-TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t estride, bool fuse) {
-  solve_thread_forward(I, slab, estride);
-  solve_thread_backward(I, slab, estride, fuse);
 }
 
 }  // namespace tg
