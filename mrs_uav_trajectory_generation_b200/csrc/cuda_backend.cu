@@ -98,13 +98,13 @@ __global__ void __launch_bounds__(32) k_solve_oct(const D desc, const size_t ins
 // accesses of a warp coalesce.
 constexpr int kThreadSolveCta = 128;
 template <class D>
-__global__ void __launch_bounds__(kThreadSolveCta) k_solve_thread(const D desc, const size_t inst_begin, const size_t inst_end, double* __restrict__ slab, const bool fuse) {
+__global__ void __launch_bounds__(kThreadSolveCta) k_solve_thread(const D desc, const size_t inst_begin, const size_t inst_end, double* __restrict__ slab) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
   for (size_t inst = inst_begin + tid; inst < inst_end; inst += nthreads) {
     tg::SolveInst I;
     if (!desc.instance(inst, I)) continue;
     if (!tg::thread_eligible(I)) continue;
-    tg::solve_thread(I, slab + tid, nthreads, fuse);
+    tg::solve_thread(I, slab + tid, nthreads);
   }
 }
 
@@ -241,7 +241,7 @@ struct CudaBackend {
     smem_optin = prop.sharedMemPerBlockOptin;
     smem_per_sm = prop.sharedMemPerMultiprocessor;
     force_general_solve = std::getenv("TG_NO_OCTET") != nullptr;
-    if (std::getenv("TG_L2_PERSIST") != nullptr && prop.persistingL2CacheMaxSize > 0) {  // opt-in: measured slower (profiles/r02_solve_thread.md)
+    if (std::getenv("TG_NO_L2_PERSIST") == nullptr && prop.persistingL2CacheMaxSize > 0) {
       size_t want = (size_t)prop.persistingL2CacheMaxSize;
       if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
         cudaDeviceGetLimit(&l2_persist_bytes, cudaLimitPersistingL2CacheSize);
@@ -461,7 +461,7 @@ struct CudaBackend {
   int thread_ctas_per_sm = 0;
   // Thread-per-instance solve of every eligible instance of [inst_begin, inst_end); rows_cap = slab rows per instance.
   template <class D>
-  void solve_thread(size_t inst_begin, size_t inst_end, int rows_cap, const D& desc, bool fuse) {
+  void solve_thread(size_t inst_begin, size_t inst_end, int rows_cap, const D& desc) {
     if (inst_end <= inst_begin) return;
     const size_t n_inst = inst_end - inst_begin;
     if (thread_ctas_per_sm == 0) {
@@ -496,7 +496,7 @@ struct CudaBackend {
       TG_CUDA_CHECK(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
     }
     prof_begin();
-    k_solve_thread<D><<<(unsigned)grid, kThreadSolveCta, 0, stream>>>(desc, inst_begin, inst_end, thread_slab, fuse);
+    k_solve_thread<D><<<(unsigned)grid, kThreadSolveCta, 0, stream>>>(desc, inst_begin, inst_end, thread_slab);
     TG_CUDA_CHECK(cudaGetLastError());
     prof_end((std::string("thread:") + typeid(D).name()).c_str(), n_inst);
     if (persist) {

@@ -562,10 +562,8 @@ class Pipeline {
     // recipe always); the older kernels below then only see the rest (stats[8] = how many problems that is)
     const bool thread_all = use_thread_solve && stats[8] == 0;
     if (use_thread_solve) {
-      // when it takes everything it also computes coefficients and costs (the separate kernels below are skipped)
-      be_.solve_thread(0, n_inst, kThrB * (std::max(b.smax, 1) + 1), desc, thread_all);
+      be_.solve_thread(0, n_inst, kThrB * (std::max(b.smax, 1) + 1), desc);
       launches(1);
-      if (thread_all) return;
     }
     be_.skip_thread_eligible = use_thread_solve;
     if (thread_all) {
@@ -667,10 +665,11 @@ class Pipeline {
         const SolveProblemDesc desc{b, 1, nullptr, nullptr};
         const int per = 4 * b.smax;
         be_.for_each((size_t)cnt[2] * 3, SetupMellingerFn{b, b.act_seg[buf]});
-        be_.solve_thread(0, (size_t)cnt[1], kThrB * (std::max(b.smax, 1) + 1), SolveProblemListDesc{desc, b.act_vtx[buf]}, true);
+        be_.solve_thread(0, (size_t)cnt[1], kThrB * (std::max(b.smax, 1) + 1), SolveProblemListDesc{desc, b.act_vtx[buf]});
+        be_.for_each((size_t)cnt[0] * 128, CoefCostGradFn{CoefCostFn<SolveProblemDesc>{desc, per, b.part, 0, per}, 0, b.act_prob[buf]});
+        be_.for_each((size_t)cnt[1], CostSumFn<SolveProblemDesc>{desc, per, b.part, b.act_vtx[buf]});
         be_.for_each((size_t)cnt[0], PlisAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel, b.act_prob[buf], nbuf});
-        launches(3);
-        (void)per;
+        launches(5);
       } else {
         be_.for_each((size_t)totS * 3, SetupMellingerFn{b, nullptr});
         solve_with_outputs((size_t)totV, stats, SolveProblemDesc{b, 1, nullptr, nullptr}, b, buckets, true);

@@ -125,33 +125,8 @@ TG_HD void thr_diag(const ThrVertex& tv, const double* __restrict__ Hp, const do
     }
 }
 
-// derivative value of slot sl of a vertex with mask m in dimension d: the fixed value, or the solution of its free unknown
-TG_HD double thr_slot_value(uint32_t m, int sl, const double* __restrict__ fixed, const double (&x)[kThrB][TG_D], int d) {
-  if ((m >> sl) & 1u) return fixed[sl * TG_D + d];
-  const int rk = free_rank(m, sl);
-  return rk == 0 ? x[0][d] : (rk == 1 ? x[1][d] : (rk == 2 ? x[2][d] : x[3][d]));
-}
-// partial cost (c^T Q) c of one polynomial from the packed Q block of the record (same sums as cost_partial in tg_kernels.cuh)
-template <int R>
-TG_HD double thr_cost_partial(const double (&c)[TG_N], const double* __restrict__ Qg) {
-  constexpr int nq = TG_N - R;
-  double partial = 0.0;
-#pragma unroll
-  for (int b = 0; b < nq; ++b) {
-    double sum = c[R] * Qg[tg_qsym(0, b)];
-#pragma unroll
-    for (int k = 1; k < nq; ++k) sum = sum + c[R + k] * Qg[tg_qsym(k, b)];
-    partial = (b == 0) ? sum * c[R + b] : partial + sum * c[R + b];
-  }
-  return partial;
-}
-
-// slab: element e of row r of this thread at slab[(r * kThrRow + e) * estride].
-// fuse: also compute the polynomial coefficients (lin_impl.h:263-282) and the cost (lin_impl.h:127-141) of the instance --
-// the thread has the derivatives of both ends of segment v in registers when the back substitution reaches vertex v.  The
-// partial costs wait in the part of the slab that the back substitution has already consumed and are added in ascending
-// (segment, dimension) order at the end, as computeCost does.
-TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t estride, bool fuse) {
+// slab: element e of row r of this thread at slab[(r * kThrRow + e) * estride]
+TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t estride) {
   const int S = I.S, V = S + 1;
   double D[kThrB][kThrB], U[kThrB][kThrB], L[kThrB][kThrB], Dn[kThrB][kThrB], b[kThrB][TG_D], bn[kThrB][TG_D];
   thr_prefetch_H(solve_rec(I, 0));
@@ -304,71 +279,19 @@ TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t es
 #pragma unroll
       for (int d = 0; d < TG_D; ++d) x[q][d] = s[d] * rinv;
     }
+    // the real unknowns of vertex v leave through global memory (CoefCostFn reads them)
     const uint32_t m = I.vmask[v];
-    if (fuse) {
-      if (has_next) {
-        // segment v: c = A^-1 [derivatives of vertex v ; vertex v+1], partial cost (c^T Q) c, per dimension
-        const uint32_t mn = I.vmask[v + 1];
-        const double* rec = solve_rec(I, v);
-        const double* fv = I.vval + (size_t)v * TG_HALF * TG_D;
-        const double* fn = fv + TG_HALF * TG_D;
-        double* pslot = slab + (size_t)((v + 1) * kThrB * kThrRow) * estride;  // rows of vertex v+1: consumed
-#pragma unroll 1
-        for (int d = 0; d < TG_D; ++d) {
-          double nd[TG_N], c[TG_N];
+    const int f = TG_HALF - (int)((m & 1u) + ((m >> 1) & 1u) + ((m >> 2) & 1u) + ((m >> 3) & 1u) + ((m >> 4) & 1u));
+    const int j0 = I.vfree[v];
 #pragma unroll
-          for (int sl = 0; sl < TG_HALF; ++sl) {
-            nd[sl] = thr_slot_value(m, sl, fv, x, d);
-            nd[TG_HALF + sl] = thr_slot_value(mn, sl, fn, xn, d);
-          }
-          c[0] = 1.0 * nd[0];
-          c[1] = 1.0 * nd[1];
-          c[2] = (1.0 / 2.0) * nd[2];
-          c[3] = (1.0 / 6.0) * nd[3];
-          c[4] = (1.0 / 24.0) * nd[4];
+    for (int q = 0; q < kThrB; ++q) {
+      if (q < f) {
 #pragma unroll
-          for (int a = 0; a < TG_HALF; ++a) {
-            double acc = rec[TG_REC_X + a * 5] * nd[0];
-#pragma unroll
-            for (int k = 1; k < 5; ++k) acc = acc + rec[TG_REC_X + a * 5 + k] * nd[k];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) acc = acc + rec[TG_REC_DINV + a * 5 + k] * nd[5 + k];
-            c[TG_HALF + a] = acc;
-          }
-          if (I.coef_out) {
-#pragma unroll
-            for (int a = 0; a < TG_N; a += 2) store2(I.coef_out + ((size_t)v * TG_D + d) * TG_N + a, c[a], c[a + 1]);
-          }
-          if (I.cost_out) {
-            const double* Q = rec + TG_REC_Q;
-            pslot[(size_t)d * estride] = (I.r == 2) ? thr_cost_partial<2>(c, Q) : ((I.r == 3) ? thr_cost_partial<3>(c, Q) : thr_cost_partial<4>(c, Q));
-          }
-        }
+        for (int d = 0; d < TG_D; d += 2) store2(I.x_out + (size_t)(j0 + q) * 4 + d, x[q][d], x[q][d + 1]);
       }
-    } else {
-      // the real unknowns of vertex v leave through global memory (CoefCostFn reads them)
-      const int f = TG_HALF - (int)((m & 1u) + ((m >> 1) & 1u) + ((m >> 2) & 1u) + ((m >> 3) & 1u) + ((m >> 4) & 1u));
-      const int j0 = I.vfree[v];
-#pragma unroll
-      for (int q = 0; q < kThrB; ++q) {
-        if (q < f) {
-#pragma unroll
-          for (int d = 0; d < TG_D; d += 2) store2(I.x_out + (size_t)(j0 + q) * 4 + d, x[q][d], x[q][d + 1]);
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < kThrB; ++q)
 #pragma unroll
       for (int d = 0; d < TG_D; ++d) xn[q][d] = x[q][d];
-  }
-  if (fuse && I.cost_out) {
-    double total = 0.0;
-    for (int sgm = 0; sgm < S; ++sgm) {
-      const double* pslot = slab + (size_t)((sgm + 1) * kThrB * kThrRow) * estride;
-      for (int d = 0; d < TG_D; ++d) total += pslot[(size_t)d * estride];
     }
-    *I.cost_out = 0.5 * total;
   }
 }
 

@@ -89,14 +89,14 @@ struct EmuBackend {
   bool skip_thread_eligible = false;
   // Mirrors CudaBackend::solve_thread: one work item per instance, slab rows contiguous (element stride 1)
   template <class D>
-  void solve_thread(size_t inst_begin, size_t inst_end, int rows_cap, const D& desc, bool fuse) {
+  void solve_thread(size_t inst_begin, size_t inst_end, int rows_cap, const D& desc) {
     if (inst_end <= inst_begin) return;
     parallel(inst_end - inst_begin, [&](size_t k) {
       tg::SolveInst I;
       if (!desc.instance(inst_begin + k, I) || !tg::thread_eligible(I)) return;
       const double nan = std::numeric_limits<double>::quiet_NaN();
       std::vector<double> slab((size_t)rows_cap * tg::kThrRow, nan);
-      tg::solve_thread(I, slab.data(), 1, fuse);
+      tg::solve_thread(I, slab.data(), 1);
     });
   }
   // Mirrors CudaBackend::solve: instances the octet routine can take go through solve_octets in groups of four (one
