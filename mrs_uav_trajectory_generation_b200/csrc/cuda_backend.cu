@@ -16,6 +16,9 @@
 
 #define TG_VERSION_STRING "tg_b200 0.1.0 (sm_100a, fp64, -fmad=false)"
 
+#ifndef TG_JT_REFILL_REP
+#define TG_JT_REFILL_REP 2
+#endif
 #include "tg_kernels.cuh"
 
 namespace {
@@ -90,6 +93,147 @@ __global__ void __launch_bounds__(32) k_solve_oct(const D desc, const size_t ins
       tg::solve_octets(&I, lane, nmax);
     }
     __syncwarp();
+  }
+}
+
+// Exact per-segment maxima of quantity Q for the entries of a device work list, by PERSISTENT warps with lane refill
+// (profiles/r02_extrema_refill.md).  The plain launch (k_for_each_scratch<ExtremaRawFn<Q>>) gives every thread one
+// polynomial: Jenkins-Traub run times vary 3x between polynomials, so a warp idles 60 % of its lanes while the slowest
+// finishes, and the launch lasts as long as its slowest warp.  Here a lane whose polynomial is done stores its maximum
+// and takes the next work item at once; every pass of the loop executes one block of the stage machine (tg_poly.cuh),
+// the one most lanes are waiting for.  Lanes are independent, so the order of execution cannot change a result.
+// Loading a work item is kept out of line (the unrolled convolution needs ~100 registers that the stage machine's loop should
+// not pay for): candidates t = 0 and t = T, the polynomial into the lane's shared-memory array p (decreasing powers, trimmed
+// as findRootsJenkinsTraub does, rpoly_ak1.cpp:76-120, 174-180).  Returns the degree to iterate on (-1: nothing) and the
+// best magnitude so far.
+struct RefillLoad {
+  int degree;
+  double best;
+};
+template <int Q>
+__device__ __noinline__ RefillLoad extrema_load_item(const double* __restrict__ c, const double T, double* __restrict__ p_lane) {
+  typedef tg::QuantityJob<Q> Job;
+  constexpr int M = Job::M;
+  typename Job::Sink sink{c, T, TG_DBL_LOWEST};
+  RefillLoad r{-1, TG_DBL_LOWEST};
+  if (0.0 > T) return r;
+  sink.consider(0.0);
+  sink.consider(T);
+  // same sums as QuantityJob<Q>::poly, with rolled loops over arrays in local memory (this path runs once per polynomial;
+  // unrolled it would set the register count of the whole kernel)
+  double ci[M + 1];
+  if constexpr (Job::kPair) {
+    constexpr int n_d = TG_N - Job::kDeriv, n_dd = n_d - 1, len = n_d + n_dd - 1;
+#pragma unroll 1
+    for (int i = 0; i < len; ++i) ci[i] = 0.0;
+#pragma unroll 1
+    for (int dim = 0; dim < 2; ++dim) {
+      const double* cc = c + dim * TG_N;
+      double dc[n_d], ddc[n_dd];
+#pragma unroll 1
+      for (int jx = 0; jx < n_d; ++jx) dc[jx] = cc[jx + Job::kDeriv] * tg::bcoef(Job::kDeriv, jx + Job::kDeriv);
+#pragma unroll 1
+      for (int jx = 0; jx < n_dd; ++jx) ddc[jx] = cc[jx + Job::kDeriv + 1] * tg::bcoef(Job::kDeriv + 1, jx + Job::kDeriv + 1);
+#pragma unroll 1
+      for (int i = 0; i < len; ++i) {
+        double cv = 0.0;
+        const int data_idx = i - n_dd + 1;
+        const int lower = (0 > -data_idx) ? 0 : -data_idx, upper = (n_dd < n_d - data_idx) ? n_dd : n_d - data_idx;
+#pragma unroll 1
+        for (int kidx = lower; kidx < upper; ++kidx) cv = cv + ddc[n_dd - 1 - kidx] * dc[data_idx + kidx];
+        ci[i] = ci[i] + cv;
+      }
+    }
+  } else {
+    const double* cc = c + Job::kD0 * TG_N;
+#pragma unroll 1
+    for (int jx = 0; jx <= M; ++jx) ci[jx] = cc[jx + Job::kDeriv + 1] * tg::bcoef(Job::kDeriv + 1, jx + Job::kDeriv + 1);
+  }
+  int last = -1;
+#pragma unroll 1
+  for (int i = 0; i <= M; i++)
+    if (tg::dabs(ci[i]) >= TG_DBL_MIN) last = i;
+  if (last >= 1) {
+    int low = last;
+#pragma unroll 1
+    for (int i = M; i >= 0; i--)
+      if (i <= last && ci[i] != 0.0) low = i;
+    for (int z = 0; z < low; ++z) sink(0.0, 0.0);
+    r.degree = last - low;
+#pragma unroll 1
+    for (int i = 0; i <= M; i++) {
+      const int dst = last - i;
+      if (dst >= 0 && dst <= r.degree) p_lane[dst * 32] = ci[i];
+    }
+  }
+  r.best = sink.best;
+  return r;
+}
+
+template <int Q>
+__global__ void __launch_bounds__(32) k_extrema_refill(const double* __restrict__ coef, const double* __restrict__ times, double* __restrict__ maxima,
+                                                       const int* __restrict__ work, const int* __restrict__ n_dev, const int n_max, int* __restrict__ counter) {
+  extern __shared__ double smem[];
+  typedef tg::QuantityJob<Q> Job;
+  typedef typename Job::Sink Sink;
+  constexpr int M = Job::M;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int n = n_dev ? min(n_max, *n_dev) : n_max;
+  double* scratch = smem + lane;
+  double svk[M + 1], tmp[M + 1];
+  tg::JtMachine m;
+  m.p = tg::WArr{scratch, 32};
+  m.qp = tg::WArr{scratch + (size_t)(M + 1) * 32, 32};
+  m.K = tg::WArr{scratch + (size_t)2 * (M + 1) * 32, 32};
+  m.qk = tg::WArr{scratch + (size_t)3 * (M + 1) * 32, 32};
+  m.svk = svk;
+  m.tmp = tmp;
+  m.state = tg::JtMachine::kDone;
+  Sink sink{nullptr, 0.0, TG_DBL_LOWEST};
+  size_t seg = 0;
+  bool has = false, exhausted = false;
+  for (;;) {
+    const bool idle = (m.state == tg::JtMachine::kDone);
+    const unsigned idle_mask = __ballot_sync(full, idle);
+    if (idle_mask) {
+      if (idle && has) {
+        maxima[seg * 9 + Q] = sink.best;
+        has = false;
+      }
+      if (!exhausted) {
+        const int cnt = __popc(idle_mask), leader = __ffs(idle_mask) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(counter, cnt);
+        base = __shfl_sync(full, base, leader);
+        if (base + cnt >= n) exhausted = true;
+        if (idle) {
+          const int my = base + __popc(idle_mask & ((1u << lane) - 1u));
+          if (my < n) {
+            seg = work ? (size_t)work[my] : (size_t)my;
+            const double* c = coef + seg * TG_D * TG_N;
+            const double T = times[seg];
+            const RefillLoad ld = extrema_load_item<Q>(c, T, scratch);
+            sink = Sink{c, T, ld.best};
+            has = true;
+            if (ld.degree >= 0) m.begin(ld.degree);
+          }
+        }
+      }
+    }
+    const int st = m.state;
+    const unsigned same = __match_any_sync(full, st);
+    const unsigned key = (st == tg::JtMachine::kDone) ? 0u : (((unsigned)__popc(same) << 8) | (unsigned)(st + 1));
+    const unsigned win = __reduce_max_sync(full, key);
+    if (win == 0u) {
+      if (exhausted && !__any_sync(full, has)) break;
+      continue;
+    }
+    const int cur = (int)(win & 0xffu) - 1;
+    if (st == cur) {
+#pragma unroll 1
+      for (int rep = 0; rep < TG_JT_REFILL_REP && m.state == cur; ++rep) m.step(cur, sink, nullptr);
+    }
   }
 }
 
@@ -388,6 +532,32 @@ struct CudaBackend {
     TG_CUDA_CHECK(cudaFuncSetAttribute(k_for_each_scratch<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_for_each_scratch<F><<<(unsigned)grid, block, smem, side[k % kSideStreams]>>>(f, n);
     TG_CUDA_CHECK(cudaGetLastError());
+  }
+  // exact maxima of quantity Q for a device work list through the persistent refill kernel, on side stream k
+  int refill_ctas_per_sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  bool use_refill = std::getenv("TG_NO_JT_REFILL") == nullptr;
+  template <int Q>
+  void extrema_refill(int k, size_t n_max, const double* coef, const double* times, double* maxima, const int* work, const int* n_dev, int* counter) {
+    if (n_max == 0) return;
+    if (!use_refill) {
+      tg::ExtremaRawFn<Q> f{coef, times, maxima, work, n_dev};
+      if (profiling) return for_each_scratch(n_max, f);
+      return for_each_scratch_on(k, n_max, f);
+    }
+    constexpr int M = tg::QuantityJob<Q>::M;
+    const size_t smem = (size_t)4 * (M + 1) * sizeof(double) * 32;
+    if (refill_ctas_per_sm[Q] == 0) {
+      TG_CUDA_CHECK(cudaFuncSetAttribute(k_extrema_refill<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int a = 0;
+      TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_extrema_refill<Q>, 32, smem));
+      refill_ctas_per_sm[Q] = std::max(a, 1);
+    }
+    const size_t grid = std::min((n_max + 31) / 32, (size_t)sm_count * refill_ctas_per_sm[Q]);
+    cudaStream_t st = profiling ? stream : side[k % kSideStreams];
+    prof_begin();
+    k_extrema_refill<Q><<<(unsigned)grid, 32, smem, st>>>(coef, times, maxima, work, n_dev, (int)n_max, counter);
+    TG_CUDA_CHECK(cudaGetLastError());
+    prof_end((std::string("refill:ExtremaRawFn<") + std::to_string(Q) + ">").c_str(), n_max);
   }
   void prof_begin() {
     if (profiling) TG_CUDA_CHECK(cudaEventRecord(pev0, stream));

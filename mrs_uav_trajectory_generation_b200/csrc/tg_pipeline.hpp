@@ -1107,6 +1107,7 @@ class Pipeline {
     es.counters = scratch_.template alloc<int>(16);
 #else
     (void)n_max;
+    es.counters = scratch_.template alloc<int>(16);  // work-item counters of the persistent extrema kernels
 #endif
     return es;
   }
@@ -1204,18 +1205,18 @@ class Pipeline {
     extrema_quantity<8>(coef, times, maxima, n_max, VmBuffers{lists + 8 * n_max, counts + 8, es.polys, es.degree}, es.counters);
     launches(18);
 #else
-    (void)es;
     // the nine quantities are independent: one side stream each, so that the long tails of the root finder overlap
+    be_.dev_memset(es.counters, 0, 16 * sizeof(int));
     be_.fork(9);
-    be_.for_each_scratch_on(0, n_max, ExtremaRawFn<0>{coef, times, maxima, lists + 0 * n_max, counts + 0});
-    be_.for_each_scratch_on(1, n_max, ExtremaRawFn<1>{coef, times, maxima, lists + 1 * n_max, counts + 1});
-    be_.for_each_scratch_on(2, n_max, ExtremaRawFn<2>{coef, times, maxima, lists + 2 * n_max, counts + 2});
-    be_.for_each_scratch_on(3, n_max, ExtremaRawFn<3>{coef, times, maxima, lists + 3 * n_max, counts + 3});
-    be_.for_each_scratch_on(4, n_max, ExtremaRawFn<4>{coef, times, maxima, lists + 4 * n_max, counts + 4});
-    be_.for_each_scratch_on(5, n_max, ExtremaRawFn<5>{coef, times, maxima, lists + 5 * n_max, counts + 5});
-    be_.for_each_scratch_on(6, n_max, ExtremaRawFn<6>{coef, times, maxima, lists + 6 * n_max, counts + 6});
-    be_.for_each_scratch_on(7, n_max, ExtremaRawFn<7>{coef, times, maxima, lists + 7 * n_max, counts + 7});
-    be_.for_each_scratch_on(8, n_max, ExtremaRawFn<8>{coef, times, maxima, lists + 8 * n_max, counts + 8});
+    be_.template extrema_refill<0>(0, n_max, coef, times, maxima, lists + 0 * n_max, counts + 0, es.counters + 0);
+    be_.template extrema_refill<1>(1, n_max, coef, times, maxima, lists + 1 * n_max, counts + 1, es.counters + 1);
+    be_.template extrema_refill<2>(2, n_max, coef, times, maxima, lists + 2 * n_max, counts + 2, es.counters + 2);
+    be_.template extrema_refill<3>(3, n_max, coef, times, maxima, lists + 3 * n_max, counts + 3, es.counters + 3);
+    be_.template extrema_refill<4>(4, n_max, coef, times, maxima, lists + 4 * n_max, counts + 4, es.counters + 4);
+    be_.template extrema_refill<5>(5, n_max, coef, times, maxima, lists + 5 * n_max, counts + 5, es.counters + 5);
+    be_.template extrema_refill<6>(6, n_max, coef, times, maxima, lists + 6 * n_max, counts + 6, es.counters + 6);
+    be_.template extrema_refill<7>(7, n_max, coef, times, maxima, lists + 7 * n_max, counts + 7, es.counters + 7);
+    be_.template extrema_refill<8>(8, n_max, coef, times, maxima, lists + 8 * n_max, counts + 8, es.counters + 8);
     be_.join(9);
     launches(9);
 #endif

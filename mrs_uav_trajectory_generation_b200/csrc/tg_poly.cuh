@@ -294,20 +294,309 @@ struct JtMachine {
     state = kRootBegin;
   }
 
-  // Runs the machine to completion.  p[0..degree] holds the coefficients (decreasing powers, p[0] != 0 and zeros at the
-  // origin already stripped by the caller).
+  // One pass of the block of state `cur` (the caller guarantees state == cur).
   template <class Sink>
-  TG_HD void run(int degree, Sink& sink, int* shifts) {
+  TG_HD void step(int cur, Sink& sink, int* shifts) {
     const double lb2 = 0x1.62e42fefa39efp-1;   // log(2.0)
     const double lo = TG_FLT_MIN / TG_DBL_EPSILON;
     const double cosr = -0x1.1db8f6d6a512ap-4;  // cos(94 deg) as glibc returns it for 94.0 * (3.14159265358979323846 / 180)
     const double sinr = 0x1.fec0b7170fff6p-1;   // sin(94 deg)
+    if (cur == kRootBegin) {
+      if (N < 1) {
+        state = kDone;
+      } else if (N <= 2) {
+        if (N < 2) {
+          sink(-TG_DIV(p[1], p[0]), 0.0);
+        } else {
+          double sr_, si_, lr_, li_;
+          quad(p[0], p[1], p[2], &sr_, &si_, &lr_, &li_);
+          sink(sr_, si_);
+          sink(lr_, li_);
+        }
+        state = kDone;
+      } else {
+        double moduli_max = 0.0, moduli_min = TG_FLT_MAX;
+#pragma unroll 1
+        for (int i = 0; i < NN; i++) {
+          const double xa = dabs(p[i]);
+          if (xa > moduli_max) moduli_max = xa;
+          if ((xa != 0) && (xa < moduli_min)) moduli_min = xa;
+        }
+        double sc = TG_DIV(lo, moduli_min);
+        if (((sc <= 1.0) && (moduli_max >= 10)) || ((sc > 1.0) && (TG_DIV(TG_FLT_MAX, sc) >= moduli_max))) {
+          sc = ((sc == 0) ? TG_FLT_MIN : sc);
+          const int l = (int)(TG_DIV(tgdm::dlog_k(sc), lb2) + 0.5);
+          const double factor = tgdm::scalb(1.0, l);
+          if (factor != 1.0)
+#pragma unroll 1
+            for (int i = 0; i < NN; i++) p[i] = p[i] * factor;
+        }
+        // upper estimate of the lower bound on the zero moduli; pt[i] = |p[i]|, pt[N] = -|p[N]|
+        const double ptN = -dabs(p[N]), pt0 = dabs(p[0]), ptNM1 = dabs(p[N - 1]);
+        x = tgdm::dexp_k(TG_DIV(tgdm::dlog_k(-ptN) - tgdm::dlog_k(pt0), (double)N));
+        if (ptNM1 != 0) {
+          const double xm_ = TG_DIV(-ptN, ptNM1);
+          x = ((xm_ < x) ? xm_ : x);
+        }
+        xm = x;
+        state = kChop;
+      }
+    }
+    else if (cur == kChop) {  // one pass of: do { x = xm; xm = 0.1 x; ff = pt(xm) } while (ff > 0)
+      x = xm;
+      xm = 0.1 * x;
+      ff = dabs(p[0]);
+#pragma unroll 1
+      for (int i = 1; i < N; i++) ff = ff * xm + dabs(p[i]);
+      ff = ff * xm + (-dabs(p[N]));
+      if (!(ff > 0)) {
+        dx = x;
+        state = kNewton;
+      }
+    }
+    else if (cur == kNewton) {  // one pass of: while (|dx/x| > 0.005) { Newton step }
+      if (dabs(TG_DIV(dx, x)) > 0.005) {
+        double df;
+        df = ff = dabs(p[0]);
+#pragma unroll 1
+        for (int i = 1; i < N; i++) {
+          ff = x * ff + dabs(p[i]);
+          df = x * df + ff;
+        }
+        ff = x * ff + (-dabs(p[N]));
+        dx = TG_DIV(ff, df);
+        x = x - dx;
+      } else {
+        bnd = x;
+        state = kKInit;
+      }
+    }
+    else if (cur == kKInit) {  // K = p'/N and five no-shift steps (rpoly_ak1.cpp:285-320)
+      const int NM1 = N - 1;
+#pragma unroll 1
+      for (int i = 1; i < N; i++) K[i] = TG_DIV((double)(N - i) * p[i], (double)N);
+      K[0] = p[0];
+      const double aa = p[N], bb = p[NM1];
+      int zerok = ((K[NM1] == 0) ? 1 : 0);
+#pragma unroll 1
+      for (int q = 0; q < 5; q++) {
+        const double cc = K[NM1];
+        if (zerok) {
+#pragma unroll 1
+          for (int i = 0; i < NM1; i++) {
+            const int jx = NM1 - i;
+            K[jx] = K[jx - 1];
+          }
+          K[0] = 0;
+          zerok = ((K[NM1] == 0) ? 1 : 0);
+        } else {
+          const double t = TG_DIV(-aa, cc);
+#pragma unroll 1
+          for (int i = 0; i < NM1; i++) {
+            const int jx = NM1 - i;
+            K[jx] = t * K[jx - 1] + p[jx];
+          }
+          K[0] = p[0];
+          zerok = ((dabs(K[NM1]) <= dabs(bb) * TG_DBL_EPSILON * 10.0) ? 1 : 0);
+        }
+      }
+#pragma unroll 1
+      for (int i = 0; i < N; i++) tmp[i] = K[i];
+      jj = 1;
+      state = kShiftBegin;
+    }
+    else if (cur == kShiftBegin) {  // next shift of the jj loop (rpoly_ak1.cpp:324-336) + Fxshfr prologue (404-411)
+      if (jj > 20) {
+        state = kDone;  // no convergence after 20 shifts: the zeros found so far stand
+      } else {
+        const double xxx = -(sinr * yy) + cosr * xx;
+        yy = sinr * xx + cosr * yy;
+        xx = xxx;
+        const double sr = bnd * xx;
+        if (shifts) ++*shifts;
+        betav = betas = 0.25;
+        u = -(2.0 * sr);
+        oss = sr;
+        ovv = v = bnd;
+        ots = otv = 0.0;
+        j = 0;
+        L2 = 20 * jj;
+        prep_tail = 0;
+        state = kFsPrep;
+      }
+    }
+    else if (cur == kFsPrep) {  // quad_sd on p + calc_sc: Fxshfr prologue (411-413) and stage-3 epilogue (527-528)
+      quad_sd(NN, u, v, p, qp, &a, &b);
+      tFlag = calc_sc(u, v);
+      if (prep_tail) {
+        ovv = vv;
+        oss = ss;
+        otv = tv;
+        ots = ts;
+        j++;
+      }
+      state = kFixedStep;
+    }
+    else if (cur == kFixedStep) {  // one pass of the fixed-shift loop (rpoly_ak1.cpp:415-538)
+      if (j >= L2) {
+#pragma unroll 1
+        for (int i = 0; i < N; i++) K[i] = tmp[i];  // unsuccessful shift: restore K, next jj
+        jj++;
+        state = kShiftBegin;
+      } else {
+        next_k(tFlag);
+        tFlag = calc_sc(u, v);
+        newest(tFlag, u, v, &ui, &vi);
+        vv = vi;
+        const double kN1 = K[N - 1];
+        ss = ((kN1 != 0.0) ? -TG_DIV(p[N], kN1) : 0.0);
+        ts = tv = 1.0;
+        bool stage3 = false;
+        if ((j != 0) && (tFlag != 3)) {
+          tv = ((vv != 0.0) ? dabs(TG_DIV(vv - ovv, vv)) : tv);
+          ts = ((ss != 0.0) ? dabs(TG_DIV(ss - oss, ss)) : ts);
+          tvv = ((tv < otv) ? tv * otv : 1.0);
+          tss = ((ts < ots) ? ts * ots : 1.0);
+          vpass = ((tvv < betav) ? 1 : 0);
+          spass = ((tss < betas) ? 1 : 0);
+          if ((spass) || (vpass)) {
+#pragma unroll 1
+            for (int i = 0; i < N; i++) svk[i] = K[i];
+            s = ss;
+            stry = vtry = 0;
+            first = 1;
+            stage3 = true;
+            stage3_top();
+          }
+        }
+        if (!stage3) {
+          ovv = vv;
+          oss = ss;
+          otv = tv;
+          ots = ts;
+          j++;
+        }
+      }
+    }
+    else if (cur == kQuadStep) {  // one pass of QuadIT_ak1's do-while (rpoly_ak1.cpp:698-779)
+      int nz = -1;  // -1: keep iterating
+      quad(1.0, qu, qv, &szr, &szi, &lzr, &lzi);
+      if (dabs(dabs(szr) - dabs(lzr)) > 0.01 * dabs(lzr)) {
+        nz = 0;
+      } else {
+        quad_sd(NN, qu, qv, p, qp, &a, &b);
+        const double mp = dabs(-(szr * b) + a) + dabs(szi * b);
+        const double zm = TG_SQRT(dabs(qv));
+        double ee = 2.0 * dabs(qp[0]);
+        const double t = -(szr * b);
+#pragma unroll 1
+        for (int i = 1; i < N; i++) ee = ee * zm + dabs(qp[i]);
+        ee = ee * zm + dabs(a + t);
+        ee = (9.0 * ee + 2.0 * dabs(t) - 7.0 * (dabs(a + t) + zm * dabs(b))) * TG_DBL_EPSILON;
+        if (mp <= 20.0 * ee) {
+          nz = 2;
+        } else {
+          qj++;
+          if (qj > 20) {
+            nz = 0;
+          } else {
+            if (qj >= 2) {
+              if ((qrelstp <= 0.01) && (mp >= qomp) && (!qtried)) {
+                // a cluster stalls the convergence: five fixed-shift steps close to it
+                qrelstp = ((qrelstp < TG_DBL_EPSILON) ? TG_SQRT(TG_DBL_EPSILON) : TG_SQRT(qrelstp));
+                qu = qu - qu * qrelstp;
+                qv = qv + qv * qrelstp;
+                quad_sd(NN, qu, qv, p, qp, &a, &b);
+#pragma unroll 1
+                for (int i = 0; i < 5; i++) {
+                  const int tf = calc_sc(qu, qv);
+                  next_k(tf);
+                }
+                qtried = 1;
+                qj = 0;
+              }
+            }
+            qomp = mp;
+            int tf = calc_sc(qu, qv);
+            next_k(tf);
+            tf = calc_sc(qu, qv);
+            double qui, qvi;
+            newest(tf, qu, qv, &qui, &qvi);
+            if (qvi != 0) {
+              qrelstp = dabs(TG_DIV(-qv + qvi, qvi));
+              qu = qui;
+              qv = qvi;
+            } else {
+              nz = 0;
+            }
+          }
+        }
+      }
+      if (nz > 0) root_found(nz, sink);
+      else if (nz == 0) quad_failed();
+    }
+    else if (cur == kRealStep) {  // one pass of RealIT_ak1's loop (rpoly_ak1.cpp:798-875)
+      const int nm1 = N - 1;
+      double pv;
+      qp[0] = pv = p[0];
+#pragma unroll 1
+      for (int i = 1; i < NN; i++) qp[i] = pv = pv * rs + p[i];
+      const double mp = dabs(pv);
+      const double ms = dabs(rs);
+      double ee = 0.5 * dabs(qp[0]);
+#pragma unroll 1
+      for (int i = 1; i < NN; i++) ee = ee * ms + dabs(qp[i]);
+      if (mp <= 20.0 * TG_DBL_EPSILON * (2.0 * ee - mp)) {
+        szr = rs;
+        szi = 0.0;
+        root_found(1, sink);
+      } else {
+        rj++;
+        if (rj > 10) {
+          real_failed(0);
+        } else if ((rj >= 2) && ((dabs(rt) <= 0.001 * dabs(-rt + rs)) && (mp > romp))) {
+          s = rs;  // a cluster near the real axis: hand the iterate to the quadratic iteration
+          real_failed(1);
+        } else {
+          romp = mp;
+          double kv;
+          qk[0] = kv = K[0];
+#pragma unroll 1
+          for (int i = 1; i < N; i++) qk[i] = kv = kv * rs + K[i];
+          if (dabs(kv) > dabs(K[nm1]) * 10.0 * TG_DBL_EPSILON) {
+            rt = -TG_DIV(pv, kv);
+            K[0] = qp[0];
+#pragma unroll 1
+            for (int i = 1; i < N; i++) K[i] = rt * qk[i - 1] + qp[i];
+          } else {
+            K[0] = 0.0;
+#pragma unroll 1
+            for (int i = 1; i < N; i++) K[i] = qk[i - 1];
+          }
+          kv = K[0];
+#pragma unroll 1
+          for (int i = 1; i < N; i++) kv = kv * rs + K[i];
+          rt = ((dabs(kv) > (dabs(K[nm1]) * 10.0 * TG_DBL_EPSILON)) ? -TG_DIV(pv, kv) : 0.0);
+          rs = rs + rt;
+        }
+      }
+    }
+  }
+  // start of a polynomial of the given degree whose coefficients are already in p[0..degree]
+  TG_HD void begin(int degree) {
     N = degree;
     NN = N + 1;
     xx = 0x1.6a09e667f3bcdp-1;  // sqrt(0.5)
     yy = -xx;
     state = kRootBegin;
     nfound = 0;
+  }
+
+  // Runs the machine to completion.  p[0..degree] holds the coefficients (decreasing powers, p[0] != 0 and zeros at the
+  // origin already stripped by the caller).
+  template <class Sink>
+  TG_HD void run(int degree, Sink& sink, int* shifts) {
+    begin(degree);
 #if defined(__CUDA_ARCH__)
     const unsigned lanes = __activemask();  // the lanes that run this machine together
 #endif
@@ -348,286 +637,7 @@ struct JtMachine {
 #if defined(TG_JT_TRACE)
       tg_jt_trace(cur, N);
 #endif
-      if (cur == kRootBegin) {
-        if (N < 1) {
-          state = kDone;
-        } else if (N <= 2) {
-          if (N < 2) {
-            sink(-TG_DIV(p[1], p[0]), 0.0);
-          } else {
-            double sr_, si_, lr_, li_;
-            quad(p[0], p[1], p[2], &sr_, &si_, &lr_, &li_);
-            sink(sr_, si_);
-            sink(lr_, li_);
-          }
-          state = kDone;
-        } else {
-          double moduli_max = 0.0, moduli_min = TG_FLT_MAX;
-#pragma unroll 1
-          for (int i = 0; i < NN; i++) {
-            const double xa = dabs(p[i]);
-            if (xa > moduli_max) moduli_max = xa;
-            if ((xa != 0) && (xa < moduli_min)) moduli_min = xa;
-          }
-          double sc = TG_DIV(lo, moduli_min);
-          if (((sc <= 1.0) && (moduli_max >= 10)) || ((sc > 1.0) && (TG_DIV(TG_FLT_MAX, sc) >= moduli_max))) {
-            sc = ((sc == 0) ? TG_FLT_MIN : sc);
-            const int l = (int)(TG_DIV(tgdm::dlog_k(sc), lb2) + 0.5);
-            const double factor = tgdm::scalb(1.0, l);
-            if (factor != 1.0)
-#pragma unroll 1
-              for (int i = 0; i < NN; i++) p[i] = p[i] * factor;
-          }
-          // upper estimate of the lower bound on the zero moduli; pt[i] = |p[i]|, pt[N] = -|p[N]|
-          const double ptN = -dabs(p[N]), pt0 = dabs(p[0]), ptNM1 = dabs(p[N - 1]);
-          x = tgdm::dexp_k(TG_DIV(tgdm::dlog_k(-ptN) - tgdm::dlog_k(pt0), (double)N));
-          if (ptNM1 != 0) {
-            const double xm_ = TG_DIV(-ptN, ptNM1);
-            x = ((xm_ < x) ? xm_ : x);
-          }
-          xm = x;
-          state = kChop;
-        }
-      }
-      else if (cur == kChop) {  // one pass of: do { x = xm; xm = 0.1 x; ff = pt(xm) } while (ff > 0)
-        x = xm;
-        xm = 0.1 * x;
-        ff = dabs(p[0]);
-#pragma unroll 1
-        for (int i = 1; i < N; i++) ff = ff * xm + dabs(p[i]);
-        ff = ff * xm + (-dabs(p[N]));
-        if (!(ff > 0)) {
-          dx = x;
-          state = kNewton;
-        }
-      }
-      else if (cur == kNewton) {  // one pass of: while (|dx/x| > 0.005) { Newton step }
-        if (dabs(TG_DIV(dx, x)) > 0.005) {
-          double df;
-          df = ff = dabs(p[0]);
-#pragma unroll 1
-          for (int i = 1; i < N; i++) {
-            ff = x * ff + dabs(p[i]);
-            df = x * df + ff;
-          }
-          ff = x * ff + (-dabs(p[N]));
-          dx = TG_DIV(ff, df);
-          x = x - dx;
-        } else {
-          bnd = x;
-          state = kKInit;
-        }
-      }
-      else if (cur == kKInit) {  // K = p'/N and five no-shift steps (rpoly_ak1.cpp:285-320)
-        const int NM1 = N - 1;
-#pragma unroll 1
-        for (int i = 1; i < N; i++) K[i] = TG_DIV((double)(N - i) * p[i], (double)N);
-        K[0] = p[0];
-        const double aa = p[N], bb = p[NM1];
-        int zerok = ((K[NM1] == 0) ? 1 : 0);
-#pragma unroll 1
-        for (int q = 0; q < 5; q++) {
-          const double cc = K[NM1];
-          if (zerok) {
-#pragma unroll 1
-            for (int i = 0; i < NM1; i++) {
-              const int jx = NM1 - i;
-              K[jx] = K[jx - 1];
-            }
-            K[0] = 0;
-            zerok = ((K[NM1] == 0) ? 1 : 0);
-          } else {
-            const double t = TG_DIV(-aa, cc);
-#pragma unroll 1
-            for (int i = 0; i < NM1; i++) {
-              const int jx = NM1 - i;
-              K[jx] = t * K[jx - 1] + p[jx];
-            }
-            K[0] = p[0];
-            zerok = ((dabs(K[NM1]) <= dabs(bb) * TG_DBL_EPSILON * 10.0) ? 1 : 0);
-          }
-        }
-#pragma unroll 1
-        for (int i = 0; i < N; i++) tmp[i] = K[i];
-        jj = 1;
-        state = kShiftBegin;
-      }
-      else if (cur == kShiftBegin) {  // next shift of the jj loop (rpoly_ak1.cpp:324-336) + Fxshfr prologue (404-411)
-        if (jj > 20) {
-          state = kDone;  // no convergence after 20 shifts: the zeros found so far stand
-        } else {
-          const double xxx = -(sinr * yy) + cosr * xx;
-          yy = sinr * xx + cosr * yy;
-          xx = xxx;
-          const double sr = bnd * xx;
-          if (shifts) ++*shifts;
-          betav = betas = 0.25;
-          u = -(2.0 * sr);
-          oss = sr;
-          ovv = v = bnd;
-          ots = otv = 0.0;
-          j = 0;
-          L2 = 20 * jj;
-          prep_tail = 0;
-          state = kFsPrep;
-        }
-      }
-      else if (cur == kFsPrep) {  // quad_sd on p + calc_sc: Fxshfr prologue (411-413) and stage-3 epilogue (527-528)
-        quad_sd(NN, u, v, p, qp, &a, &b);
-        tFlag = calc_sc(u, v);
-        if (prep_tail) {
-          ovv = vv;
-          oss = ss;
-          otv = tv;
-          ots = ts;
-          j++;
-        }
-        state = kFixedStep;
-      }
-      else if (cur == kFixedStep) {  // one pass of the fixed-shift loop (rpoly_ak1.cpp:415-538)
-        if (j >= L2) {
-#pragma unroll 1
-          for (int i = 0; i < N; i++) K[i] = tmp[i];  // unsuccessful shift: restore K, next jj
-          jj++;
-          state = kShiftBegin;
-        } else {
-          next_k(tFlag);
-          tFlag = calc_sc(u, v);
-          newest(tFlag, u, v, &ui, &vi);
-          vv = vi;
-          const double kN1 = K[N - 1];
-          ss = ((kN1 != 0.0) ? -TG_DIV(p[N], kN1) : 0.0);
-          ts = tv = 1.0;
-          bool stage3 = false;
-          if ((j != 0) && (tFlag != 3)) {
-            tv = ((vv != 0.0) ? dabs(TG_DIV(vv - ovv, vv)) : tv);
-            ts = ((ss != 0.0) ? dabs(TG_DIV(ss - oss, ss)) : ts);
-            tvv = ((tv < otv) ? tv * otv : 1.0);
-            tss = ((ts < ots) ? ts * ots : 1.0);
-            vpass = ((tvv < betav) ? 1 : 0);
-            spass = ((tss < betas) ? 1 : 0);
-            if ((spass) || (vpass)) {
-#pragma unroll 1
-              for (int i = 0; i < N; i++) svk[i] = K[i];
-              s = ss;
-              stry = vtry = 0;
-              first = 1;
-              stage3 = true;
-              stage3_top();
-            }
-          }
-          if (!stage3) {
-            ovv = vv;
-            oss = ss;
-            otv = tv;
-            ots = ts;
-            j++;
-          }
-        }
-      }
-      else if (cur == kQuadStep) {  // one pass of QuadIT_ak1's do-while (rpoly_ak1.cpp:698-779)
-        int nz = -1;  // -1: keep iterating
-        quad(1.0, qu, qv, &szr, &szi, &lzr, &lzi);
-        if (dabs(dabs(szr) - dabs(lzr)) > 0.01 * dabs(lzr)) {
-          nz = 0;
-        } else {
-          quad_sd(NN, qu, qv, p, qp, &a, &b);
-          const double mp = dabs(-(szr * b) + a) + dabs(szi * b);
-          const double zm = TG_SQRT(dabs(qv));
-          double ee = 2.0 * dabs(qp[0]);
-          const double t = -(szr * b);
-#pragma unroll 1
-          for (int i = 1; i < N; i++) ee = ee * zm + dabs(qp[i]);
-          ee = ee * zm + dabs(a + t);
-          ee = (9.0 * ee + 2.0 * dabs(t) - 7.0 * (dabs(a + t) + zm * dabs(b))) * TG_DBL_EPSILON;
-          if (mp <= 20.0 * ee) {
-            nz = 2;
-          } else {
-            qj++;
-            if (qj > 20) {
-              nz = 0;
-            } else {
-              if (qj >= 2) {
-                if ((qrelstp <= 0.01) && (mp >= qomp) && (!qtried)) {
-                  // a cluster stalls the convergence: five fixed-shift steps close to it
-                  qrelstp = ((qrelstp < TG_DBL_EPSILON) ? TG_SQRT(TG_DBL_EPSILON) : TG_SQRT(qrelstp));
-                  qu = qu - qu * qrelstp;
-                  qv = qv + qv * qrelstp;
-                  quad_sd(NN, qu, qv, p, qp, &a, &b);
-#pragma unroll 1
-                  for (int i = 0; i < 5; i++) {
-                    const int tf = calc_sc(qu, qv);
-                    next_k(tf);
-                  }
-                  qtried = 1;
-                  qj = 0;
-                }
-              }
-              qomp = mp;
-              int tf = calc_sc(qu, qv);
-              next_k(tf);
-              tf = calc_sc(qu, qv);
-              double qui, qvi;
-              newest(tf, qu, qv, &qui, &qvi);
-              if (qvi != 0) {
-                qrelstp = dabs(TG_DIV(-qv + qvi, qvi));
-                qu = qui;
-                qv = qvi;
-              } else {
-                nz = 0;
-              }
-            }
-          }
-        }
-        if (nz > 0) root_found(nz, sink);
-        else if (nz == 0) quad_failed();
-      }
-      else if (cur == kRealStep) {  // one pass of RealIT_ak1's loop (rpoly_ak1.cpp:798-875)
-        const int nm1 = N - 1;
-        double pv;
-        qp[0] = pv = p[0];
-#pragma unroll 1
-        for (int i = 1; i < NN; i++) qp[i] = pv = pv * rs + p[i];
-        const double mp = dabs(pv);
-        const double ms = dabs(rs);
-        double ee = 0.5 * dabs(qp[0]);
-#pragma unroll 1
-        for (int i = 1; i < NN; i++) ee = ee * ms + dabs(qp[i]);
-        if (mp <= 20.0 * TG_DBL_EPSILON * (2.0 * ee - mp)) {
-          szr = rs;
-          szi = 0.0;
-          root_found(1, sink);
-        } else {
-          rj++;
-          if (rj > 10) {
-            real_failed(0);
-          } else if ((rj >= 2) && ((dabs(rt) <= 0.001 * dabs(-rt + rs)) && (mp > romp))) {
-            s = rs;  // a cluster near the real axis: hand the iterate to the quadratic iteration
-            real_failed(1);
-          } else {
-            romp = mp;
-            double kv;
-            qk[0] = kv = K[0];
-#pragma unroll 1
-            for (int i = 1; i < N; i++) qk[i] = kv = kv * rs + K[i];
-            if (dabs(kv) > dabs(K[nm1]) * 10.0 * TG_DBL_EPSILON) {
-              rt = -TG_DIV(pv, kv);
-              K[0] = qp[0];
-#pragma unroll 1
-              for (int i = 1; i < N; i++) K[i] = rt * qk[i - 1] + qp[i];
-            } else {
-              K[0] = 0.0;
-#pragma unroll 1
-              for (int i = 1; i < N; i++) K[i] = qk[i - 1];
-            }
-            kv = K[0];
-#pragma unroll 1
-            for (int i = 1; i < N; i++) kv = kv * rs + K[i];
-            rt = ((dabs(kv) > (dabs(K[nm1]) * 10.0 * TG_DBL_EPSILON)) ? -TG_DIV(pv, kv) : 0.0);
-            rs = rs + rt;
-          }
-        }
-      }
+      step(cur, sink, shifts);
       }  // rep
     }
   }
@@ -677,6 +687,30 @@ TG_HD void find_roots_jt(const double (&ci)[M + 1], double* scratch, int stride,
 #if defined(TG_JT_STATS)
   for (int i = 0; i < 10; ++i) tg_jt_stats[i] += m.npass[i];
 #endif
+}
+
+// The same preparation without running the machine: m's work arrays are bound already; on return m.state is kRootBegin
+// (polynomial loaded) or kDone (no zeros to iterate for).  Used by the persistent kernel that refills idle lanes.
+template <int M, class Sink>
+TG_HD void jt_load(const double (&ci)[M + 1], JtMachine& m, Sink& sink) {
+  m.state = JtMachine::kDone;
+  int last = -1;
+#pragma unroll
+  for (int i = 0; i <= M; i++)
+    if (dabs(ci[i]) >= TG_DBL_MIN) last = i;
+  if (last < 1) return;
+  int low = last;
+#pragma unroll
+  for (int i = M; i >= 0; i--)
+    if (i <= last && ci[i] != 0.0) low = i;
+  for (int z = 0; z < low; ++z) sink(0.0, 0.0);
+  const int degree = last - low;
+#pragma unroll
+  for (int i = 0; i <= M; i++) {
+    const int dst = last - i;
+    if (dst >= 0 && dst <= degree) m.p[dst] = ci[i];
+  }
+  m.begin(degree);
 }
 
 // candidate sink: magnitude of the DERIV-th derivative over dims [D0, D0+ND) at every real zero inside [0, T]
@@ -855,6 +889,49 @@ template <int Q>
 struct QuantityDegree {
   static constexpr int kDeriv = Q % 3 + 1;
   static constexpr int value = (Q < 3) ? 2 * (TG_N - kDeriv) - 3 : TG_N - kDeriv - 2;
+};
+
+// What the persistent extrema kernel needs to know about quantity Q: the polynomial whose real zeros are the candidate
+// times (eth/segment.cpp:122-145 for the horizontal pair, eth/polynomial.cpp:69-85 for one dimension) and the sink that
+// evaluates the magnitude at them.
+template <int Q>
+struct QuantityJob {
+  static constexpr int kDeriv = Q % 3 + 1;
+  static constexpr bool kPair = Q < 3;
+  static constexpr int kD0 = kPair ? 0 : (Q < 6 ? 2 : 3);
+  static constexpr int kND = kPair ? 2 : 1;
+  static constexpr int M = QuantityDegree<Q>::value;
+  typedef MaxSink<kDeriv, kD0, kND> Sink;
+  TG_HD static void poly(const double* __restrict__ coef, double (&ci)[M + 1]) {
+    if constexpr (kPair) {
+      constexpr int n_d = TG_N - kDeriv, n_dd = n_d - 1, len = n_d + n_dd - 1;
+      static_assert(len == M + 1, "degree");
+#pragma unroll
+      for (int i = 0; i < len; ++i) ci[i] = 0.0;
+#pragma unroll
+      for (int dim = 0; dim < 2; ++dim) {
+        const double* c = coef + dim * TG_N;
+        double dc[n_d], ddc[n_dd];
+#pragma unroll
+        for (int jx = 0; jx < n_d; ++jx) dc[jx] = c[jx + kDeriv] * bcoef(kDeriv, jx + kDeriv);
+#pragma unroll
+        for (int jx = 0; jx < n_dd; ++jx) ddc[jx] = c[jx + kDeriv + 1] * bcoef(kDeriv + 1, jx + kDeriv + 1);
+#pragma unroll
+        for (int i = 0; i < len; ++i) {
+          double cv = 0.0;
+          const int data_idx = i - n_dd + 1;
+          const int lower = (0 > -data_idx) ? 0 : -data_idx, upper = (n_dd < n_d - data_idx) ? n_dd : n_d - data_idx;
+#pragma unroll
+          for (int kidx = lower; kidx < upper; ++kidx) cv = cv + ddc[n_dd - 1 - kidx] * dc[data_idx + kidx];
+          ci[i] = ci[i] + cv;
+        }
+      }
+    } else {
+      const double* c = coef + kD0 * TG_N;
+#pragma unroll
+      for (int jx = 0; jx <= M; ++jx) ci[jx] = c[jx + kDeriv + 1] * bcoef(kDeriv + 1, jx + kDeriv + 1);
+    }
+  }
 };
 
 }  // namespace tg

@@ -70,6 +70,11 @@ struct EmuBackend {
       f(i, scratch, 1);
     });
   }
+  // Mirrors CudaBackend::extrema_refill (persistent warps with lane refill): item by item here
+  template <int Q>
+  void extrema_refill(int, size_t n_max, const double* coef, const double* times, double* maxima, const int* work, const int* n_dev, int*) {
+    for_each_scratch(n_max, tg::ExtremaRawFn<Q>{coef, times, maxima, work, n_dev});
+  }
   void fork(int) {}
   void join(int) {}
   template <class F>
