@@ -382,6 +382,23 @@ def check_random_flier(ctx, B, first_index=0, **params_kw):
     return compare_optimize(ctx, wp_off, wp, params_kw=params_kw)
 
 
+def check_acceptance_rejects(ctx, B=48):
+    """The acceptance logic of findTrajectory (node.cpp:1138-1149, 1178-1199): with max_len_factor = 1.9 some of these paths are
+    rejected as 'too long' (FindStatus 2), with min_len_factor = 1.9 most as 'too short' (3); a rejected findTrajectory makes
+    optimize() fail for that path without touching its neighbours.  Status 1 (an NLopt code outside {>= 1 except 6, -1}) cannot
+    occur on either side: every failure of the optimiser surfaces as -1 (nlopt::opt throws, nl_impl.h:190-208) and MAXTIME (6)
+    needs a wall clock, which neither the oracle nor the kernels have."""
+    seen = set()
+    for kw in (dict(max_len_factor=1.9), dict(min_len_factor=1.8), dict(max_len_factor=1.75, min_len_factor=1.65)):
+        res, out, exact, worst = check_random_flier(ctx, B, first_index=700, **kw)
+        assert exact
+        st = set(int(x) for x in res["status"])
+        assert (res["success"][res["status"] != 0] == 0).all() and (res["success"][res["status"] == 0] == 1).all()
+        seen |= st
+    assert seen == {0, 2, 3}, seen
+    return True
+
+
 def check_fixtures(ctx):
     """F1a (the reference tests' 4-waypoint path + prepended start) and F1b (10-waypoint zig-zag)."""
     paths = [W.F1A_WAYPOINTS, W.F1B_WAYPOINTS]

@@ -129,3 +129,7 @@ def test_extrema_random_polynomials(emu_ctx, oracle):
     coef[::13, :, 8:] = 0.0
     times = np.exp(rng.uniform(-2, 2, S))
     assert np.array_equal(emu_ctx.extrema(coef, times), O.segment_maxima(coef, times))
+
+
+def test_acceptance_reject_branches(emu_ctx, oracle):
+    assert PC.check_acceptance_rejects(emu_ctx, B=24)

@@ -165,3 +165,8 @@ def test_properties_at_full_size(gpu_ctx):
     assert np.array_equal(o1["coef"], o2["coef"]) and np.array_equal(o1["samples"], o2["samples"])
     counts, samples, _ = gpu_ctx.sample_batch(o1["seg_off"], o1["coef"], o1["times"], P2.dt)
     assert np.array_equal(counts, np.diff(o1["smp_off"])) and np.array_equal(samples, o1["samples"])
+
+
+@pytest.mark.gpu
+def test_acceptance_reject_branches(gpu_ctx, oracle):
+    assert PC.check_acceptance_rejects(gpu_ctx, B=48)
