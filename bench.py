@@ -84,7 +84,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(n_paths, first_index, nthreads=0):
+def cpu_baseline(n_paths, first_index, nthreads=0, keep=False):
     """The oracle (CPU restatement of the reference, `kind: port`) on a bounded sample of the same workload."""
     import oracle_lib as O
     from mrs_uav_trajectory_generation_b200 import workloads as W
@@ -96,7 +96,60 @@ def cpu_baseline(n_paths, first_index, nthreads=0):
     r = O.optimize_batch(wp_off, wp, cap_wp=700, cap_samples=4000, nthreads=nthreads, want_outputs=True)
     dt = time.perf_counter() - t0
     ok = sum(1 for x in r["res"] if x.success)
+    if keep:
+        return n_paths / dt, r["threads"], dt, ok, (wp_off, wp, r)
     return n_paths / dt, r["threads"], dt, ok
+
+
+def parity_on_sample(ctx, P, sample):
+    """Outside the timed region: the GPU's outputs for the cpu_baseline sample (the first paths of the bench batch) against the
+    oracle outputs that leg has just computed -- verdicts and counts exactly, coefficients / samples bit for bit."""
+    import parity_checks as PC
+
+    wp_off, wp, ref = sample
+    res, _ = ctx.optimize_batch(wp_off, wp, None, None, P)
+    out = ctx.fetch_outputs()
+    n = len(wp_off) - 1
+    ints = ("status", "success", "nlopt_code", "n_evals", "rounds", "safe", "n_waypoints", "n_samples", "n_scale_passes")
+    verdicts, exact, worst_c, worst_s = 0, 0, 0.0, 0.0
+    for p in range(n):
+        r, g = ref["res"][p], res[p]
+        same = all(getattr(r, k) == g[k] for k in ints)
+        verdicts += int(same)
+        if not same or not g["success"]:
+            exact += int(same)
+            continue
+        s0, s1 = out["seg_off"][p], out["seg_off"][p + 1]
+        m0, m1 = out["smp_off"][p], out["smp_off"][p + 1]
+        S, M = s1 - s0, m1 - m0
+        rc, rt, rs = ref["coeffs"][p, :S], ref["times"][p, :S], ref["samples"][p, :M]
+        worst_c = max(worst_c, PC.coef_rel_err(out["coef"][s0:s1], rc, rt))
+        worst_s = max(worst_s, float(np.abs(out["samples"][m0:m1, :3] - rs[:, :3]).max()))
+        exact += int(np.array_equal(out["coef"][s0:s1], rc) and np.array_equal(out["times"][s0:s1], rt) and np.array_equal(out["samples"][m0:m1], rs))
+    return {"paths": n, "verdicts_and_counts_equal": verdicts, "bit_exact": exact, "worst_coef_rel": worst_c, "worst_sample_pos_m": worst_s,
+            "against": "oracle (CPU restatement, pinned bit for bit to the reference's own eth_trajectory_generation sources compiled with stand-in "
+                       "Eigen/NLopt: tests/test_ref_eth.py); a build of the reference with real glibc/Eigen/NLopt differs by the numeric floor "
+                       "(~1e-6 relative on coefficients, DESIGN.md)"}
+
+
+def single_path_latency(ctx, P, n=101):
+    """BASELINE metric's 'p50 latency': one 11-waypoint path at a time through the host-buffer API (waypoints in, samples and the
+    result record out), n different paths; median / p90 of the wall time per call."""
+    from mrs_uav_trajectory_generation_b200 import workloads as W
+
+    ts = []
+    for i in range(n + 5):
+        wp = W.random_flier_path(90000 + i, 11)
+        off = np.array([0, len(wp)], np.int32)
+        t0 = time.perf_counter()
+        res, _ = ctx.optimize_batch(off, wp, None, None, P)
+        ctx.fetch_outputs(want=("smp_off", "samples"))
+        dt = time.perf_counter() - t0
+        if i >= 5:
+            ts.append(1e3 * dt)
+    ts = np.sort(np.array(ts))
+    return {"p50_ms": float(np.median(ts)), "p90_ms": float(ts[int(0.9 * len(ts))]), "n": n,
+            "what": "single 11-waypoint random-flier path per call, host waypoints in -> samples + result record on the host (configs[0]-style single problem)"}
 
 
 def run_reference(args, rank, world):
@@ -239,40 +292,65 @@ def main():
         ctx.set_profiling(False)
         tot_ms = sum(v[0] for v in prof.values())
         prof_table = {k: {"ms": round(v[0], 3), "launches": v[1], "share": round(v[0] / tot_ms, 4)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
-        top = max(prof.items(), key=lambda kv: kv[1][0])
-        name, (ms, launches, items) = top
-        if "CoefCost" in name:
-            flops = cb["flops_coef"] - ca["flops_coef"]
-        elif "Solve" in name:
-            flops = cb["flops_solve"] - ca["flops_solve"]
-        elif "Setup" in name:
-            flops = cb["flops_setup"] - ca["flops_setup"]
-        else:
-            flops = None
         hbm_peak, how = load_peaks()
-        traffic, traffic_note = None, None
-        try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (never measured under the bench itself)
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
-                tr = json.load(f).get(name)
-            if tr:
-                traffic, traffic_note = tr["bytes_per_launch"], "ncu dram__bytes_read.sum + dram__bytes_write.sum, " + tr["launch"] + " (profiles/r01_final_ncu_kernels.md)"
+        traffic_db = {}
+        try:  # DRAM bytes per launch from the committed ncu --set full captures (never measured under the bench itself)
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
+                traffic_db = json.load(f)
         except Exception:
             pass
-        if flops is not None:
-            achieved = flops / (ms * 1e-3) / 1e12
-            roofline = {"bound": "fp64", "kernel": name, "achieved": achieved, "peak": fp64_nofma, "unit": "TFLOP/s",
-                        "frac": achieved / fp64_nofma if fp64_nofma else None, "traffic": traffic, "traffic_note": traffic_note,
-                        "avg_launch_ms": ms / launches, "launches": launches, "share_of_step": ms / tot_ms,
-                        "peak_note": f"FP64 pipe measured live: DMUL+DADD (-fmad=false mix) {fp64_nofma:.2f} TFLOP/s, DFMA {fp64_fma:.2f} TFLOP/s; "
-                                     f"HBM {hbm_peak} GB/s ({how}) is not the bound for this path (SURVEY.md 8d)",
-                        "algorithmic_flops_per_launch": flops / launches}
+
+        def kernel_flops(name, items):
+            if name.startswith("refill:ExtremaRawFn"):
+                return float(items)  # counted in the kernel: stage-machine blocks executed x their operation counts
+            if "CoefCost" in name:
+                return cb["flops_coef"] - ca["flops_coef"]
+            if "Solve" in name:
+                return None  # split below between the solve launches by their instance counts
+            if "SetupMellinger" in name or "SetupBase" in name:
+                return None
+            return None
+
+        solve_names = [k for k in prof if "Solve" in k and "CoefCost" not in k and "CostSum" not in k]
+        solve_items = sum(prof[k][2] for k in solve_names) or 1
+        setup_names = [k for k in prof if "Setup" in k]
+        setup_items = sum(prof[k][2] for k in setup_names) or 1
+        rooflines = {}
+        for name, (ms, launches, items) in prof.items():
+            fl = kernel_flops(name, items)
+            if fl is None and name in solve_names:
+                fl = (cb["flops_solve"] - ca["flops_solve"]) * items / solve_items
+            if fl is None and name in setup_names:
+                fl = (cb["flops_setup"] - ca["flops_setup"]) * items / setup_items
+            if not fl or ms <= 0:
+                continue
+            achieved = fl / (ms * 1e-3) / 1e12
+            tr = traffic_db.get(name)
+            rooflines[name] = {"bound": "fp64", "kernel": name, "achieved": achieved, "peak": fp64_nofma, "unit": "TFLOP/s",
+                               "frac": achieved / fp64_nofma if fp64_nofma else None,
+                               "traffic": tr["bytes_per_launch"] if tr else None, "traffic_note": ("ncu dram__bytes_read.sum + dram__bytes_write.sum, " + tr["launch"]) if tr else None,
+                               "avg_launch_ms": ms / launches, "launches": launches, "share_of_step": ms / tot_ms, "algorithmic_flops_per_launch": fl / launches}
+        if rooflines:
+            top_name = max(rooflines, key=lambda k: rooflines[k]["share_of_step"])
+            roofline = dict(rooflines[top_name])
+            roofline["peak_note"] = (f"FP64 pipe measured live: DMUL+DADD (-fmad=false mix) {fp64_nofma:.2f} TFLOP/s, DFMA {fp64_fma:.2f} TFLOP/s; "
+                                     f"HBM {hbm_peak} GB/s ({how}) is not the bound for this path (SURVEY.md 8d)")
+            roofline["flops_note"] = ("Jenkins-Traub kernels: operations counted in the kernel per executed stage-machine block; solve / setup / coefficient kernels: "
+                                      "SURVEY.md 8(d) formulas x the instances launched")
+            roofline["others"] = {k: {"frac": round(v["frac"], 4), "achieved": round(v["achieved"], 3), "share_of_step": round(v["share_of_step"], 4)}
+                                  for k, v in sorted(rooflines.items(), key=lambda kv: -kv[1]["share_of_step"]) if k != top_name}
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
     cpu = None
+    parity = None
+    latency = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, dt, ok = cpu_baseline(args.cpu_sample, 0)
+        v, cores, dt, ok, sample = cpu_baseline(args.cpu_sample, 0, keep=True)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {args.cpu_sample} paths of the same workload, oracle (Eigen-free C++ restatement, -O3, no FMA), {cores} host threads, {dt:.1f} s"}
+        parity = parity_on_sample(ctx, P, sample)
+    if rank == 0:
+        latency = single_path_latency(ctx, P)
 
     if rank == 0:
         launches = (c1["launches"] - c0["launches"])
@@ -281,7 +359,7 @@ def main():
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {
-                "workload": "configs[2]: 65536 random-flier paths (11 waypoints = 10 segments) per GPU, full optimize(): Mellinger/L-BFGS time allocation (<=10 evals), "
+                "workload": "configs[2]: 65536 random-flier paths (11 waypoints = 10 segments) per GPU, full optimize(): Mellinger time allocation by NLopt-LD_LBFGS-style PLIS (maxeval 10, every evaluation with its gradient), "
                             "Jenkins-Traub time scaling, deviation check 0.05 m with <=6 midpoint-subdivision rounds, dt=0.2 s sampling",
                 "paths_per_gpu_per_step": B, "parallelism": f"problem-index sharding x{world}, no data-path collective",
                 "l2": "per-step working set (segment records ~3.4 GB per evaluation) >> 126 MB L2, no explicit flush needed",
@@ -302,6 +380,11 @@ def main():
             line["kernel_profile"] = prof_table
         if cpu:
             line["cpu_baseline"] = cpu
+        if parity:
+            line["parity"] = parity
+        if latency:
+            line["p50_latency_ms"] = latency["p50_ms"]
+            line["latency"] = latency
         print(json.dumps(line), file=result_out, flush=True)
     if world > 1:
         dist.destroy_process_group()

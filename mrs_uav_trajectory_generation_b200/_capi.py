@@ -200,11 +200,12 @@ class Context:
         out = {}
         mangled = names.value.decode().split("\n")[:max(n, 0)]
         for i, m in enumerate(mangled):
+            prefix, _, core = m.rpartition(":")  # "thread:<typeid>" / "refill:ExtremaRawFn<1>" / "<typeid>"
             try:
-                nm = subprocess.run(["c++filt", "-t", m], capture_output=True, text=True).stdout.strip() or m
+                nm = subprocess.run(["c++filt", "-t", core], capture_output=True, text=True).stdout.strip() or core
             except Exception:
-                nm = m
-            out[nm.replace("tg::", "")] = (ms[i], ln[i], it[i])
+                nm = core
+            out[(prefix + ":" if prefix else "") + nm.replace("tg::", "")] = (ms[i], ln[i], it[i])
         return out
 
     def test_set_scale_tolerance(self, tol):

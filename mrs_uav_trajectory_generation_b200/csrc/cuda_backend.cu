@@ -172,7 +172,8 @@ __device__ __noinline__ RefillLoad extrema_load_item(const double* __restrict__ 
 
 template <int Q>
 __global__ void __launch_bounds__(32) k_extrema_refill(const double* __restrict__ coef, const double* __restrict__ times, double* __restrict__ maxima,
-                                                       const int* __restrict__ work, const int* __restrict__ n_dev, const int n_max, int* __restrict__ counter) {
+                                                       const int* __restrict__ work, const int* __restrict__ n_dev, const int n_max, int* __restrict__ counter,
+                                                       unsigned long long* __restrict__ flop_counter) {
   extern __shared__ double smem[];
   typedef tg::QuantityJob<Q> Job;
   typedef typename Job::Sink Sink;
@@ -193,6 +194,10 @@ __global__ void __launch_bounds__(32) k_extrema_refill(const double* __restrict_
   Sink sink{nullptr, 0.0, TG_DBL_LOWEST};
   size_t seg = 0;
   bool has = false, exhausted = false;
+  m.fl = 0;
+  // counted floating-point operations of this lane (stage-machine blocks + the item loads), reported when profiling
+  constexpr int kLoadFlops = Job::kPair ? 4 * (TG_N - Job::kDeriv) * (TG_N - Job::kDeriv - 1) + 8 * (TG_N - Job::kDeriv) : (M + 1) + 4 * (TG_N - Job::kDeriv);
+  unsigned long long lane_fl = 0;
   for (;;) {
     const bool idle = (m.state == tg::JtMachine::kDone);
     const unsigned idle_mask = __ballot_sync(full, idle);
@@ -200,6 +205,8 @@ __global__ void __launch_bounds__(32) k_extrema_refill(const double* __restrict_
       if (idle && has) {
         maxima[seg * 9 + Q] = sink.best;
         has = false;
+        lane_fl += (unsigned long long)(m.fl + kLoadFlops);
+        m.fl = 0;
       }
       if (!exhausted) {
         const int cnt = __popc(idle_mask), leader = __ffs(idle_mask) - 1;
@@ -234,6 +241,10 @@ __global__ void __launch_bounds__(32) k_extrema_refill(const double* __restrict_
 #pragma unroll 1
       for (int rep = 0; rep < TG_JT_REFILL_REP && m.state == cur; ++rep) m.step(cur, sink, nullptr);
     }
+  }
+  if (flop_counter) {
+    for (int o = 16; o > 0; o >>= 1) lane_fl += __shfl_xor_sync(full, lane_fl, o);
+    if (lane == 0) atomicAdd(flop_counter, lane_fl);
   }
 }
 
@@ -535,6 +546,7 @@ struct CudaBackend {
   }
   // exact maxima of quantity Q for a device work list through the persistent refill kernel, on side stream k
   int refill_ctas_per_sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long* d_jt_flops = nullptr;
   bool use_refill = std::getenv("TG_NO_JT_REFILL") == nullptr;
   template <int Q>
   void extrema_refill(int k, size_t n_max, const double* coef, const double* times, double* maxima, const int* work, const int* n_dev, int* counter) {
@@ -554,10 +566,21 @@ struct CudaBackend {
     }
     const size_t grid = std::min((n_max + 31) / 32, (size_t)sm_count * refill_ctas_per_sm[Q]);
     cudaStream_t st = profiling ? stream : side[k % kSideStreams];
+    if (profiling) {
+      if (!d_jt_flops) TG_CUDA_CHECK(cudaMalloc(&d_jt_flops, sizeof(unsigned long long)));
+      TG_CUDA_CHECK(cudaMemsetAsync(d_jt_flops, 0, sizeof(unsigned long long), stream));
+    }
     prof_begin();
-    k_extrema_refill<Q><<<(unsigned)grid, 32, smem, st>>>(coef, times, maxima, work, n_dev, (int)n_max, counter);
+    k_extrema_refill<Q><<<(unsigned)grid, 32, smem, st>>>(coef, times, maxima, work, n_dev, (int)n_max, counter, profiling ? d_jt_flops : nullptr);
     TG_CUDA_CHECK(cudaGetLastError());
-    prof_end((std::string("refill:ExtremaRawFn<") + std::to_string(Q) + ">").c_str(), n_max);
+    if (profiling) {
+      // `items` of these entries = counted floating-point operations (the kernel adds them up per polynomial)
+      const std::string name = std::string("refill:ExtremaRawFn<") + std::to_string(Q) + ">";
+      prof_end(name.c_str(), 0);
+      unsigned long long fl = 0;
+      TG_CUDA_CHECK(cudaMemcpy(&fl, d_jt_flops, sizeof(fl), cudaMemcpyDeviceToHost));
+      prof[name].items += (long long)fl;
+    }
   }
   void prof_begin() {
     if (profiling) TG_CUDA_CHECK(cudaEventRecord(pev0, stream));

@@ -91,6 +91,7 @@ struct JtMachine {
   double* svk;        // per-thread save areas (rarely touched): svk[0..M], tmp[0..M]
   double* tmp;
   int N, NN, state, nfound;
+  int fl;  // floating-point operations executed for the current polynomial (counted per block, see step(); feeds the roofline)
   // calcSC scalars
   double a, b, c, d, e, f, g, h, a1, a3, a7;
   double szr, szi, lzr, lzi;
@@ -302,6 +303,7 @@ struct JtMachine {
     const double cosr = -0x1.1db8f6d6a512ap-4;  // cos(94 deg) as glibc returns it for 94.0 * (3.14159265358979323846 / 180)
     const double sinr = 0x1.fec0b7170fff6p-1;   // sin(94 deg)
     if (cur == kRootBegin) {
+      fl += 2 * N + 90;   // moduli scan, scaling, log / exp of the starting radius
       if (N < 1) {
         state = kDone;
       } else if (N <= 2) {
@@ -342,7 +344,9 @@ struct JtMachine {
         state = kChop;
       }
     }
-    else if (cur == kChop) {  // one pass of: do { x = xm; xm = 0.1 x; ff = pt(xm) } while (ff > 0)
+    else if (cur == kChop) {
+      fl += 2 * N + 1;
+       // one pass of: do { x = xm; xm = 0.1 x; ff = pt(xm) } while (ff > 0)
       x = xm;
       xm = 0.1 * x;
       ff = dabs(p[0]);
@@ -354,7 +358,9 @@ struct JtMachine {
         state = kNewton;
       }
     }
-    else if (cur == kNewton) {  // one pass of: while (|dx/x| > 0.005) { Newton step }
+    else if (cur == kNewton) {
+      fl += 4 * N + 3;
+       // one pass of: while (|dx/x| > 0.005) { Newton step }
       if (dabs(TG_DIV(dx, x)) > 0.005) {
         double df;
         df = ff = dabs(p[0]);
@@ -371,7 +377,9 @@ struct JtMachine {
         state = kKInit;
       }
     }
-    else if (cur == kKInit) {  // K = p'/N and five no-shift steps (rpoly_ak1.cpp:285-320)
+    else if (cur == kKInit) {
+      fl += 12 * N;
+       // K = p'/N and five no-shift steps (rpoly_ak1.cpp:285-320)
       const int NM1 = N - 1;
 #pragma unroll 1
       for (int i = 1; i < N; i++) K[i] = TG_DIV((double)(N - i) * p[i], (double)N);
@@ -405,7 +413,9 @@ struct JtMachine {
       jj = 1;
       state = kShiftBegin;
     }
-    else if (cur == kShiftBegin) {  // next shift of the jj loop (rpoly_ak1.cpp:324-336) + Fxshfr prologue (404-411)
+    else if (cur == kShiftBegin) {
+      fl += 10;
+       // next shift of the jj loop (rpoly_ak1.cpp:324-336) + Fxshfr prologue (404-411)
       if (jj > 20) {
         state = kDone;  // no convergence after 20 shifts: the zeros found so far stand
       } else {
@@ -425,7 +435,9 @@ struct JtMachine {
         state = kFsPrep;
       }
     }
-    else if (cur == kFsPrep) {  // quad_sd on p + calc_sc: Fxshfr prologue (411-413) and stage-3 epilogue (527-528)
+    else if (cur == kFsPrep) {
+      fl += 8 * N + 7;    // quad_sd on p (4 per coefficient) + calc_sc
+       // quad_sd on p + calc_sc: Fxshfr prologue (411-413) and stage-3 epilogue (527-528)
       quad_sd(NN, u, v, p, qp, &a, &b);
       tFlag = calc_sc(u, v);
       if (prep_tail) {
@@ -437,7 +449,9 @@ struct JtMachine {
       }
       state = kFixedStep;
     }
-    else if (cur == kFixedStep) {  // one pass of the fixed-shift loop (rpoly_ak1.cpp:415-538)
+    else if (cur == kFixedStep) {
+      fl += 8 * N + 49;   // next_k + calc_sc + newest + convergence tests
+       // one pass of the fixed-shift loop (rpoly_ak1.cpp:415-538)
       if (j >= L2) {
 #pragma unroll 1
         for (int i = 0; i < N; i++) K[i] = tmp[i];  // unsuccessful shift: restore K, next jj
@@ -478,7 +492,9 @@ struct JtMachine {
         }
       }
     }
-    else if (cur == kQuadStep) {  // one pass of QuadIT_ak1's do-while (rpoly_ak1.cpp:698-779)
+    else if (cur == kQuadStep) {
+      fl += 18 * N + 100; // quad, quad_sd, error bound, 2 x calc_sc, next_k, newest
+       // one pass of QuadIT_ak1's do-while (rpoly_ak1.cpp:698-779)
       int nz = -1;  // -1: keep iterating
       quad(1.0, qu, qv, &szr, &szi, &lzr, &lzi);
       if (dabs(dabs(szr) - dabs(lzr)) > 0.01 * dabs(lzr)) {
@@ -535,7 +551,9 @@ struct JtMachine {
       if (nz > 0) root_found(nz, sink);
       else if (nz == 0) quad_failed();
     }
-    else if (cur == kRealStep) {  // one pass of RealIT_ak1's loop (rpoly_ak1.cpp:798-875)
+    else if (cur == kRealStep) {
+      fl += 10 * N + 10;  // two synthetic divisions, error bound, K update, K evaluation
+       // one pass of RealIT_ak1's loop (rpoly_ak1.cpp:798-875)
       const int nm1 = N - 1;
       double pv;
       qp[0] = pv = p[0];
@@ -590,6 +608,7 @@ struct JtMachine {
     yy = -xx;
     state = kRootBegin;
     nfound = 0;
+    fl = 0;
   }
 
   // Runs the machine to completion.  p[0..degree] holds the coefficients (decreasing powers, p[0] != 0 and zeros at the
