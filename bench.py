@@ -301,10 +301,10 @@ def main():
             pass
 
         def kernel_flops(name, items):
-            if name.startswith("refill:ExtremaRawFn"):
+            if name.startswith("refill:ExtremaRawFn") or name.startswith("jt:"):
                 return float(items)  # counted in the kernel: stage-machine blocks executed x their operation counts
             if "CoefCost" in name:
-                return cb["flops_coef"] - ca["flops_coef"]
+                return None
             if "Solve" in name:
                 return None  # split below between the solve launches by their instance counts
             if "SetupMellinger" in name or "SetupBase" in name:
@@ -314,12 +314,16 @@ def main():
         solve_names = [k for k in prof if "Solve" in k and "CoefCost" not in k and "CostSum" not in k]
         solve_items = sum(prof[k][2] for k in solve_names) or 1
         setup_names = [k for k in prof if "Setup" in k]
+        coef_names = [k for k in prof if "CoefCost" in k]
+        coef_items = sum(prof[k][2] for k in coef_names) or 1
         setup_items = sum(prof[k][2] for k in setup_names) or 1
         rooflines = {}
         for name, (ms, launches, items) in prof.items():
             fl = kernel_flops(name, items)
             if fl is None and name in solve_names:
                 fl = (cb["flops_solve"] - ca["flops_solve"]) * items / solve_items
+            if fl is None and name in coef_names:
+                fl = (cb["flops_coef"] - ca["flops_coef"]) * items / coef_items
             if fl is None and name in setup_names:
                 fl = (cb["flops_setup"] - ca["flops_setup"]) * items / setup_items
             if not fl or ms <= 0:

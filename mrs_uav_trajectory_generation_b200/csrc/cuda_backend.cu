@@ -396,7 +396,7 @@ struct CudaBackend {
     smem_optin = prop.sharedMemPerBlockOptin;
     smem_per_sm = prop.sharedMemPerMultiprocessor;
     force_general_solve = std::getenv("TG_NO_OCTET") != nullptr;
-    if (std::getenv("TG_NO_L2_PERSIST") == nullptr && prop.persistingL2CacheMaxSize > 0) {
+    if (std::getenv("TG_L2_PERSIST") != nullptr && prop.persistingL2CacheMaxSize > 0) {  // opt-in: measured slower (profiles/r02_solve_thread.md)
       size_t want = (size_t)prop.persistingL2CacheMaxSize;
       if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
         cudaDeviceGetLimit(&l2_persist_bytes, cudaLimitPersistingL2CacheSize);
@@ -547,7 +547,7 @@ struct CudaBackend {
   // exact maxima of quantity Q for a device work list through the persistent refill kernel, on side stream k
   int refill_ctas_per_sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long* d_jt_flops = nullptr;
-  bool use_refill = std::getenv("TG_NO_JT_REFILL") == nullptr;
+  bool use_refill = std::getenv("TG_JT_REFILL") != nullptr;  // opt-in: measured no faster than one polynomial per thread (profiles/r02_extrema_refill.md)
   template <int Q>
   void extrema_refill(int k, size_t n_max, const double* coef, const double* times, double* maxima, const int* work, const int* n_dev, int* counter) {
     if (n_max == 0) return;
