@@ -12,14 +12,21 @@
 // kernels of libtg_b200.so; one object = a batch of one.  There is no CPU arithmetic here and no fallback: constructing
 // the first object fails (std::runtime_error) when no CUDA device is usable.
 //
-// Types: the reference passes Eigen::VectorXd; Eigen is not a dependency of this header.  `Vector` below is
-// std::vector<double>; when <Eigen/Core> was included first, overloads taking / returning Eigen::VectorXd are enabled.
+// Types: the reference passes and returns Eigen::VectorXd.  When <Eigen/Core> can be found (or TG_B200_USE_EIGEN is defined)
+// this header includes it and `Vector` IS Eigen::VectorXd, so call sites written against the reference compile unchanged
+// (vertex.makeStartOrEnd(Eigen::Vector4d(x, y, z, heading), r), Eigen::VectorXd p = trajectory.evaluate(t), ...); every
+// setter is a template over the vector type, so Eigen::Vector4d, Eigen::VectorXd, std::vector<double> and std::array all
+// work.  Without Eigen (define TG_B200_NO_EIGEN to force it) `Vector` is std::vector<double>.  sampleWholeTrajectory fills any
+// point type with the fields of eth_mav_msgs::EigenTrajectoryPoint (eth_mav_msgs/eigen_mav_msgs.h:188-240) -- the reference's
+// own struct when that header is included, or the plain TrajectoryPoint below.
 //
 // Additions that the one-problem-per-object reference API cannot express: TrajectoryGeneratorBatch (the numeric core of
 // optimize()/findTrajectory for many paths in one call).
 #ifndef ETH_TRAJECTORY_GENERATION_B200_HPP_
 #define ETH_TRAJECTORY_GENERATION_B200_HPP_
 
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -29,6 +36,14 @@
 #include <vector>
 
 #include "tg_b200.h"
+
+#if !defined(TG_B200_NO_EIGEN) && (defined(TG_B200_USE_EIGEN) || (defined(__has_include) && __has_include(<Eigen/Core>)))
+#include <Eigen/Core>
+#define TG_B200_HAVE_EIGEN 1
+#endif
+#include <thread>
+#include <type_traits>
+#include <utility>
 
 namespace eth_trajectory_generation {
 
@@ -41,9 +56,27 @@ static constexpr int SNAP = 4;
 static constexpr int INVALID = -1;
 }  // namespace derivative_order
 
+#if defined(TG_B200_HAVE_EIGEN)
+typedef Eigen::VectorXd Vector;
+#else
 typedef std::vector<double> Vector;
+#endif
 
 namespace b200 {
+// a Vector of n copies of `value`, and a copy of any indexable vector type (Eigen fixed / dynamic, std::vector, std::array)
+inline Vector make_vector(size_t n, double value) {
+#if defined(TG_B200_HAVE_EIGEN)
+  return Vector::Constant((long)n, value);
+#else
+  return Vector(n, value);
+#endif
+}
+template <class V>
+inline Vector to_vector(const V& v) {
+  Vector out = make_vector((size_t)v.size(), 0.0);
+  for (size_t i = 0; i < (size_t)v.size(); ++i) out[i] = v[i];
+  return out;
+}
 constexpr int kN = 10;    // coefficients per segment and dimension (node.cpp:1063)
 constexpr int kD = 4;     // x, y, z, heading (node.cpp:902)
 constexpr int kHalf = 5;  // derivative slots per vertex (lin_impl.h:206)
@@ -51,9 +84,10 @@ constexpr int kHalf = 5;  // derivative slots per vertex (lin_impl.h:206)
 // One tg_ctx per device for the process, created on first use.
 class Context {
  public:
-  static Context& instance(int device = 0) {
-    static std::map<int, std::unique_ptr<Context>> all;
-    std::unique_ptr<Context>& c = all[device];
+  // slot > 0: a further, independent context on the same device (a tg_ctx serves one host thread at a time)
+  static Context& instance(int device = 0, int slot = 0) {
+    static std::map<std::pair<int, int>, std::unique_ptr<Context>> all;
+    std::unique_ptr<Context>& c = all[std::make_pair(device, slot)];
     if (!c) c.reset(new Context(device));
     return *c;
   }
@@ -84,20 +118,23 @@ class Vertex {
   explicit Vertex(size_t dimension) : D_(dimension) {}
   size_t D() const { return D_; }
 
-  void addConstraint(int derivative_order, double value) { constraints_[derivative_order] = ConstraintValue(D_, value); }
-  void addConstraint(int type, const ConstraintValue& constraint) {
-    if (constraint.size() != D_) {
+  void addConstraint(int derivative_order, double value) { constraints_[derivative_order] = b200::make_vector(D_, value); }
+  // any vector type: Eigen::VectorXd / Vector4d as in the reference's call sites, std::vector<double>, std::array
+  template <class V, class = typename std::enable_if<!std::is_arithmetic<V>::value>::type>
+  void addConstraint(int type, const V& constraint) {
+    if ((size_t)constraint.size() != D_) {
       std::printf("[Vertex]: dimension of the constraint does not match the vertex\n");  // CHECK prints and continues
       return;
     }
-    constraints_[type] = constraint;
+    constraints_[type] = b200::to_vector(constraint);
   }
   // start or end vertex: position fixed, derivatives 1 .. up_to_derivative fixed at zero (eth/vertex.cpp:158-163)
-  void makeStartOrEnd(const ConstraintValue& constraint, int up_to_derivative) {
+  template <class V, class = typename std::enable_if<!std::is_arithmetic<V>::value>::type>
+  void makeStartOrEnd(const V& constraint, int up_to_derivative) {
     addConstraint(derivative_order::POSITION, constraint);
-    for (int i = 1; i <= up_to_derivative; ++i) constraints_[i] = ConstraintValue(D_, 0.0);
+    for (int i = 1; i <= up_to_derivative; ++i) constraints_[i] = b200::make_vector(D_, 0.0);
   }
-  void makeStartOrEnd(double value, int up_to_derivative) { makeStartOrEnd(ConstraintValue(D_, value), up_to_derivative); }
+  void makeStartOrEnd(double value, int up_to_derivative) { makeStartOrEnd(b200::make_vector(D_, value), up_to_derivative); }
   bool hasConstraint(int derivative_order) const { return constraints_.find(derivative_order) != constraints_.end(); }
   bool getConstraint(int derivative_order, ConstraintValue* constraint) const {
     const auto it = constraints_.find(derivative_order);
@@ -169,18 +206,21 @@ class Trajectory {
   }
   // Trajectory::evaluate(t, derivative) (eth/trajectory.cpp:55-87); past the end: prints, returns zeros.
   Vector evaluate(double t, int derivative = derivative_order::POSITION) const {
-    Vector out(b200::kD, 0.0);
+    Vector out = b200::make_vector(b200::kD, 0.0);
     if (segments_.empty()) return out;
     std::vector<double> coef, times;
     pack(&coef, &times);
     uint8_t ok = 0;
+    double v4[b200::kD] = {0, 0, 0, 0};
     b200::Context& c = b200::Context::instance();
-    c.check(tg_evaluate_batch(c.get(), K(), coef.data(), times.data(), 1, &t, derivative, out.data(), &ok), "tg_evaluate_batch");
+    c.check(tg_evaluate_batch(c.get(), K(), coef.data(), times.data(), 1, &t, derivative, v4, &ok), "tg_evaluate_batch");
     if (!ok) std::printf("[Trajectory]: time out of range, returning zeros\n");
+    for (int d = 0; d < b200::kD; ++d) out[d] = v4[d];
     return out;
   }
   // evaluateRange (eth/trajectory.cpp:93-151): the dt walk of the sampler, derivative `derivative` only
-  void evaluateRange(double t_start, double t_end, double dt, int derivative, std::vector<Vector>* result) const;
+  void evaluateRange(double t_start, double t_end, double dt, int derivative, std::vector<Vector>* result,
+                     std::vector<double>* sampling_times = nullptr) const;
   // maxima of |v|, |a|, |j| over the whole trajectory for the three dimension groups (eth/trajectory.cpp:422-565)
   void computeMaxDerivativesHorizontal(double* v_max, double* a_max, double* j_max) const { max_of_group(0, v_max, a_max, j_max); }
   void computeMaxDerivativesVertical(double* v_max, double* a_max, double* j_max) const { max_of_group(1, v_max, a_max, j_max); }
@@ -251,7 +291,31 @@ struct TrajectoryPoint {
   double heading_raw;         // p[3] before the quaternion round trip
 };
 
-inline bool sampleWholeTrajectory(const Trajectory& trajectory, double sampling_interval, TrajectoryPoint::Vector* states) {
+namespace b200 {
+// does the point type carry EigenTrajectoryPoint's setFromYaw() (eth_mav_msgs/eigen_mav_msgs.h:226-238)?
+template <class P, class = void>
+struct has_set_from_yaw : std::false_type {};
+template <class P>
+struct has_set_from_yaw<P, decltype(std::declval<P&>().setFromYaw(0.0), void())> : std::true_type {};
+template <class P>
+inline typename std::enable_if<has_set_from_yaw<P>::value>::type fill_heading(P& s, const double* f) {
+  s.setFromYaw(f[3]);       // the quaternion is built on the host by the reference's own inline code, as in the reference
+  s.setFromYawRate(f[7]);
+  s.setFromYawAcc(f[11]);
+}
+template <class P>
+inline typename std::enable_if<!has_set_from_yaw<P>::value>::type fill_heading(P& s, const double* f) {
+  s.heading_raw = f[3];
+  s.yaw_rate = f[7];
+  s.yaw_acc = f[11];
+  s.yaw = f[18];
+}
+}  // namespace b200
+
+// sampleWholeTrajectory (eth/trajectory_sampling.cpp:119-124 -> 49-104).  PointVector: std::vector of TrajectoryPoint, or of
+// the reference's eth_mav_msgs::EigenTrajectoryPoint (any allocator) -- same call as in the reference (node.cpp:1166).
+template <class PointVector>
+inline bool sampleWholeTrajectory(const Trajectory& trajectory, double sampling_interval, PointVector* states) {
   if (!states) return false;
   states->clear();
   if (trajectory.empty() || !(sampling_interval > 0.0)) {
@@ -269,7 +333,7 @@ inline bool sampleWholeTrajectory(const Trajectory& trajectory, double sampling_
   c.check(tg_sample_batch(c.get(), 1, seg_off, coef.data(), times.data(), sampling_interval, &count, xyzh.data(), full.data()), "tg_sample_batch");
   states->resize(count);
   for (int i = 0; i < count; ++i) {
-    TrajectoryPoint& s = (*states)[i];
+    auto& s = (*states)[i];
     const double* f = &full[(size_t)i * 19];  // p4 v4 a4 j3 s3 yaw
     s.time_from_start_ns = (int64_t)((0.0 + sampling_interval * (double)i) * 1.e9);  // eth/trajectory_sampling.cpp:98
     for (int k = 0; k < 3; ++k) {
@@ -279,30 +343,63 @@ inline bool sampleWholeTrajectory(const Trajectory& trajectory, double sampling_
       s.jerk_W[k] = f[12 + k];
       s.snap_W[k] = f[15 + k];
     }
-    s.heading_raw = f[3];
-    s.yaw_rate = f[7];
-    s.yaw_acc = f[11];
-    s.yaw = f[18];
+    b200::fill_heading(s, f);
   }
   return true;
 }
 
-inline void Trajectory::evaluateRange(double t_start, double t_end, double dt, int derivative, std::vector<Vector>* result) const {
-  // the node only ever samples the whole trajectory from 0 (eth/trajectory_sampling.cpp:119-124)
+inline void Trajectory::evaluateRange(double t_start, double t_end, double dt, int derivative, std::vector<Vector>* result,
+                                      std::vector<double>* sampling_times) const {
+  // eth/trajectory.cpp:93-151: the accumulated walk t_start, t_start + dt, ... (< t_end), every sample evaluated in ALL
+  // dimensions for any derivative 0..N-1 on the device (tg_evaluate_batch); out-of-range start: prints and returns nothing
   if (!result) return;
   result->clear();
-  if (t_start != 0.0 || derivative < 0 || derivative > 4) {
-    std::printf("[Trajectory]: evaluateRange is supported from t_start = 0 for derivatives 0..4\n");
+  if (sampling_times) sampling_times->clear();
+  if (segments_.empty() || !(dt > 0.0)) return;
+  if (t_start > getMaxTime() || t_start < 0.0) {
+    std::printf("[Trajectory]: start time out of range of the trajectory!\n");
     return;
   }
-  TrajectoryPoint::Vector pts;
-  if (!sampleWholeTrajectory(*this, dt, &pts)) return;
-  for (const TrajectoryPoint& p : pts) {
-    if ((double)p.time_from_start_ns * 1e-9 > t_end) break;
-    const double* src = derivative == 0 ? p.position_W : derivative == 1 ? p.velocity_W : derivative == 2 ? p.acceleration_W : derivative == 3 ? p.jerk_W : p.snap_W;
-    Vector v(b200::kD, 0.0);
-    for (int k = 0; k < 3; ++k) v[k] = src[k];
-    v[3] = derivative == 0 ? p.heading_raw : derivative == 1 ? p.yaw_rate : derivative == 2 ? p.yaw_acc : 0.0;
+  // the reference keeps two running sums, accumulated_time and time_in_segment, and evaluates segment i at time_in_segment
+  std::vector<double> ts;
+  std::vector<int> seg_of;
+  double acc = 0.0;
+  size_t i = 0;
+  for (i = 0; i < segments_.size(); ++i) {
+    acc += segments_[i].getTime();
+    if (acc > t_start) break;
+  }
+  if (i >= segments_.size()) i = segments_.size() - 1;
+  acc -= segments_[i].getTime();
+  double in_seg = t_start - acc;
+  while (acc < t_end) {
+    if (in_seg > segments_[i].getTime()) {
+      in_seg = in_seg - segments_[i].getTime();
+      if (++i >= segments_.size()) break;
+      continue;
+    }
+    ts.push_back(in_seg);
+    seg_of.push_back((int)i);
+    if (sampling_times) sampling_times->push_back(acc);
+    in_seg += dt;
+    acc += dt;
+  }
+  if (ts.empty()) return;
+  std::vector<double> out(ts.size() * b200::kD);
+  std::vector<uint8_t> ok(ts.size());
+  b200::Context& c = b200::Context::instance();
+  // one device call per run of samples that fall into the same segment: that segment alone, evaluated at time_in_segment
+  for (size_t k0 = 0; k0 < ts.size();) {
+    size_t k1 = k0;
+    while (k1 < ts.size() && seg_of[k1] == seg_of[k0]) ++k1;
+    const Segment& sg = segments_[seg_of[k0]];
+    const double T = sg.getTime();
+    c.check(tg_evaluate_batch(c.get(), 1, sg.data(), &T, (int)(k1 - k0), ts.data() + k0, derivative, out.data() + k0 * b200::kD, ok.data() + k0), "tg_evaluate_batch");
+    k0 = k1;
+  }
+  for (size_t k = 0; k < ts.size(); ++k) {
+    Vector v = b200::make_vector(b200::kD, 0.0);
+    for (int d = 0; d < b200::kD; ++d) v[d] = out[k * b200::kD + d];
     result->push_back(v);
   }
 }
@@ -346,6 +443,12 @@ class PolynomialOptimization {
       std::printf("[PolynomialOptimization]: you tried to optimize a derivative that is not possible\n");
       return false;
     }
+    if (derivative_to_optimize < derivative_order::ACCELERATION) {
+      // the reference accepts 0 and 1 as well (lin_impl.h:61-70); the kernels integrate the squared 2nd, 3rd or 4th derivative
+      // (the node's three choices, node.cpp:907-921).  Refuse loudly instead of optimising something else.
+      std::printf("[PolynomialOptimization]: derivative_to_optimize = %d is not supported by the B200 path (2, 3 or 4)\n", derivative_to_optimize);
+      return false;
+    }
     if (dimension_ != (size_t)b200::kD) {
       std::printf("[PolynomialOptimization]: the B200 path is built for 4 dimensions (x, y, z, heading)\n");
       return false;
@@ -376,7 +479,7 @@ class PolynomialOptimization {
     const int vtx_off[2] = {0, V};
     coef_.resize((size_t)(V - 1) * b200::kD * b200::kN);
     b200::Context& c = b200::Context::instance();
-    const int r = derivative_to_optimize_ < 2 ? 2 : derivative_to_optimize_;  // the kernels integrate r in {2, 3, 4}
+    const int r = derivative_to_optimize_;  // 2, 3 or 4 (setupFromVertices refuses anything else)
     const int rc = tg_solve_linear_batch(c.get(), 1, vtx_off, mask_.data(), vals_.data(), segment_times_.data(), r, coef_.data(), &cost_);
     if (rc != TG_OK) {
       std::printf("[PolynomialOptimization]: solveLinear failed: %s\n", tg_last_error(c.get()));
@@ -460,6 +563,8 @@ struct OptimizationInfo {  // nl.h:112-130
   int n_iterations = 0;
   int stopping_reason = -1;  // NLopt-style code
   double cost_trajectory = 0.0;
+  double cost_time = 0.0;
+  double cost_soft_constraints = 0.0;
   int n_scale_passes = 0;
 };
 
@@ -479,16 +584,19 @@ class PolynomialOptimizationNonLinear {
   // nl_impl.h:538-565; the (dimension, derivative) -> limit mapping of scaleSegmentTimesWithViolation (355-381):
   // dimensions 0,1 -> horizontal, 2 -> vertical, 3 -> heading; a later call overwrites an earlier one
   bool addMaximumMagnitudeConstraint(int dimension, int derivative, double maximum_value) {
-    if (derivative < derivative_order::VELOCITY || derivative > derivative_order::JERK || dimension < 0 || dimension > 3) {
+    if (derivative < derivative_order::VELOCITY || derivative > derivative_order::SNAP || dimension < 0 || dimension > 3) {
       std::printf("[PolynomialOptimizationNonLinear]: constraint (dimension %d, derivative %d) has no effect on this path\n", dimension, derivative);
       return false;
     }
-    const int d = derivative - 1;  // 0 v, 1 a, 2 j
-    int idx;                       // tg_params::limits order: v_h v_v a_h a_v j_h j_v v_hdg a_hdg j_hdg
-    if (dimension <= 1) idx = 2 * d;
-    else if (dimension == 2) idx = 2 * d + 1;
-    else idx = 6 + d;
-    limits_[idx] = maximum_value;
+    if (derivative <= derivative_order::JERK) {  // snap limits only enter the soft-constraint objectives
+      const int d = derivative - 1;  // 0 v, 1 a, 2 j
+      int idx;                       // tg_params::limits order: v_h v_v a_h a_v j_h j_v v_hdg a_hdg j_hdg
+      if (dimension <= 1) idx = 2 * d;
+      else if (dimension == 2) idx = 2 * d + 1;
+      else idx = 6 + d;
+      limits_[idx] = maximum_value;
+    }
+    constraint_dimension_.push_back(dimension);
     constraint_derivative_.push_back(derivative);
     constraint_value_.push_back(maximum_value);
     return true;
@@ -513,7 +621,7 @@ class PolynomialOptimizationNonLinear {
     if (parts) parts->assign(3 * x.size(), 0.0);
     const int V = (int)poly_opt_.vertexMasks().size();
     b200::Context& c = b200::Context::instance();
-    const int r = poly_opt_.getDerivativeToOptimize() < 2 ? 2 : poly_opt_.getDerivativeToOptimize();
+    const int r = poly_opt_.getDerivativeToOptimize();
     const int rc = tg_objective_batch(c.get(), V, poly_opt_.vertexMasks().data(), poly_opt_.vertexValues().data(), r, method, (long long)x.size(),
                                       flat.data(), (int)nvar, optimization_parameters_.time_penalty, optimization_parameters_.use_soft_constraints ? 1 : 0,
                                       optimization_parameters_.soft_constraint_weight, (int)constraint_derivative_.size(),
@@ -526,18 +634,14 @@ class PolynomialOptimizationNonLinear {
   }
   // nl_impl.h:89-118: returns the NLopt-style result code (the node accepts >= 1 except 6, and -1; node.cpp:1138-1149)
   int optimize() {
-    if (optimization_parameters_.time_alloc_method != NonlinearOptimizationParameters::kMellingerOuterLoop) {
-      std::printf("[PolynomialOptimizationNonLinear]: optimize() runs kMellingerOuterLoop (the production default); for the derivative-free methods "
-                  "evaluateObjectives() provides the batched objective (Python: api.DerivativeFreeTimeAllocation drives it)\n");
-      return -1;
-    }
+    if (optimization_parameters_.time_alloc_method != NonlinearOptimizationParameters::kMellingerOuterLoop) return optimizeDerivativeFree();
     std::vector<double> times;
     poly_opt_.getSegmentTimes(&times);
     const int S = (int)times.size(), V = S + 1;
     if (S < 1) return -1;
     tg_params P;
     tg_default_params(&P);
-    P.derivative_to_optimize = poly_opt_.getDerivativeToOptimize() < 2 ? 2 : poly_opt_.getDerivativeToOptimize();
+    P.derivative_to_optimize = poly_opt_.getDerivativeToOptimize();
     P.max_evals = optimization_parameters_.max_iterations;
     P.f_rel = optimization_parameters_.f_rel;
     P.x_rel = optimization_parameters_.x_rel;
@@ -560,6 +664,134 @@ class PolynomialOptimizationNonLinear {
     optimization_info_.n_scale_passes = passes;
     return code;
   }
+  // optimizeTime / optimizeTimeAndFreeConstraints (nl_impl.h:120-157, 429-536) for kSquaredTime, kRichterTime and the two
+  // ...AndConstraints methods.  The reference hands the objective to NLopt's LN_BOBYQA, which is not vendored and not restated:
+  // the objective (evaluateObjectives above), the bounds (kOptimizationTimeLowerBound; setFreeEndpointDerivativeHardConstraints,
+  // nl_impl.h:764-805, including its free_deriv_counter that only advances for derivatives <= derivative_to_optimize), the
+  // initial steps (initial_stepsize_rel |x|, 1e-13 for zeros) and the stopping rules (ftol_rel -> 3, xtol_rel -> 4, maxeval -> 5)
+  // are the reference's; the search is a bound-constrained coordinate pattern search whose 2n trial points per iteration are
+  // ONE batched objective call.  max_iterations counts those iterations.  PARITY UNPINNED against BOBYQA's iterates.
+  int optimizeDerivativeFree() {
+    const int method = (int)optimization_parameters_.time_alloc_method;
+    if (!(method == 0 || method == 1 || method == 3 || method == 4)) return -1;
+    std::vector<double> times;
+    poly_opt_.getSegmentTimes(&times);
+    const int S = (int)times.size();
+    if (S < 1) return -1;
+    const bool with_free = method >= 3;
+    std::vector<double> x(times);
+    const std::vector<uint8_t>& mask = poly_opt_.vertexMasks();
+    const int V = (int)mask.size();
+    int n_free = 0;
+    if (with_free) {
+      // initial solution: solveLinear + getFreeConstraints, dimension-major (nl_impl.h:436-462)
+      if (!poly_opt_.solveLinear()) return -1;
+      Trajectory tr;
+      poly_opt_.getTrajectory(&tr);
+      std::vector<std::pair<int, int>> slots;  // (vertex, derivative) of every free slot, in column order
+      for (int v = 0; v < V; ++v)
+        for (int k = 0; k < b200::kHalf; ++k)
+          if (!((mask[v] >> k) & 1u)) slots.push_back(std::make_pair(v, k));
+      n_free = (int)slots.size();
+      x.resize((size_t)S + (size_t)b200::kD * n_free, 0.0);
+      // the value of a free derivative = that derivative of the solved trajectory at the vertex (start of segment v, or the end
+      // of the last segment), evaluated on the device
+      for (int j = 0; j < n_free; ++j) {
+        const int v = slots[j].first, k = slots[j].second;
+        const Segment& sg = tr.segments()[v < S ? v : S - 1];
+        const double T = sg.getTime(), tq = (v < S) ? 0.0 : T;
+        double out4[b200::kD];
+        uint8_t ok = 0;
+        b200::Context& c = b200::Context::instance();
+        c.check(tg_evaluate_batch(c.get(), 1, sg.data(), &T, 1, &tq, k, out4, &ok), "tg_evaluate_batch");
+        for (int d = 0; d < b200::kD; ++d) x[(size_t)S + (size_t)d * n_free + j] = out4[d];
+      }
+    }
+    const size_t n = x.size();
+    std::vector<double> lo(n, -1.7976931348623157e308), hi(n, 1.7976931348623157e308), step(n);
+    for (int i = 0; i < S; ++i) lo[i] = 0.01;  // kOptimizationTimeLowerBound (nl.h:32)
+    if (with_free) {
+      const int r = poly_opt_.getDerivativeToOptimize();
+      Vertex::Vector vertices;
+      poly_opt_.getVertices(&vertices);
+      for (size_t ci = 0; ci < constraint_derivative_.size(); ++ci) {
+        unsigned int free_deriv_counter = 0;
+        const int dim = constraint_dimension_[ci];
+        for (int v = 0; v < V; ++v)
+          for (int deriv = 0; deriv <= r; ++deriv)
+            if (!vertices[v].hasConstraint(deriv)) {
+              if (deriv == constraint_derivative_[ci]) {
+                const size_t at = (size_t)S + (size_t)dim * n_free + free_deriv_counter;
+                if (at < n) {
+                  lo[at] = -std::abs(constraint_value_[ci]);
+                  hi[at] = std::abs(constraint_value_[ci]);
+                }
+              }
+              free_deriv_counter++;
+            }
+      }
+    }
+    for (size_t i = 0; i < n; ++i) {
+      const double ax = std::abs(x[i]);
+      step[i] = (ax <= 2.220446049250313e-16) ? 1e-13 : optimization_parameters_.initial_stepsize_rel * ax;  // nl_impl.h:488-495
+      if (x[i] < lo[i]) lo[i] = x[i];  // "check if initial solution isn't already out of bounds" (nl_impl.h:497-503)
+      else if (x[i] > hi[i]) hi[i] = x[i];
+    }
+    std::vector<std::vector<double>> cand;
+    std::vector<double> tot;
+    cand.assign(1, x);
+    if (!evaluateObjectives(cand, &tot)) return -1;
+    double f = tot[0];
+    int iterations = 0, code = 5;
+    while (iterations < optimization_parameters_.max_iterations) {
+      ++iterations;
+      cand.assign(2 * n, x);
+      for (size_t i = 0; i < n; ++i) {
+        cand[i][i] = std::min(x[i] + step[i], hi[i]);
+        cand[n + i][i] = std::max(x[i] - step[i], lo[i]);
+      }
+      if (!evaluateObjectives(cand, &tot)) return -1;
+      size_t k = 0;
+      for (size_t i = 1; i < tot.size(); ++i)
+        if (tot[i] < tot[k]) k = i;  // first minimum
+      if (tot[k] < f) {
+        const double f_old = f;
+        f = tot[k];
+        x = cand[k];
+        if (std::abs(f_old - f) <= optimization_parameters_.f_rel * std::abs(f)) {
+          code = 3;
+          break;
+        }
+      } else {
+        bool small = true;
+        for (size_t i = 0; i < n; ++i) {
+          step[i] *= 0.5;
+          if (!(step[i] <= optimization_parameters_.x_rel * std::abs(x[i]))) small = false;
+        }
+        if (small) {
+          code = 4;
+          break;
+        }
+      }
+    }
+    // final state = the optimum: coefficients from one more objective evaluation that also returns them
+    {
+      std::vector<double> total(1), parts(3), coef((size_t)S * b200::kD * b200::kN);
+      b200::Context& c = b200::Context::instance();
+      const int rc = tg_objective_batch(c.get(), V, mask.data(), poly_opt_.vertexValues().data(), poly_opt_.getDerivativeToOptimize(), method, 1, x.data(), (int)n,
+                                        optimization_parameters_.time_penalty, optimization_parameters_.use_soft_constraints ? 1 : 0,
+                                        optimization_parameters_.soft_constraint_weight, (int)constraint_derivative_.size(), constraint_derivative_.data(),
+                                        constraint_value_.data(), total.data(), parts.data(), coef.data());
+      if (rc != TG_OK) return -1;
+      poly_opt_.adopt(std::vector<double>(x.begin(), x.begin() + S), coef, parts[0]);
+      optimization_info_.cost_trajectory = parts[0];
+      optimization_info_.cost_time = parts[1];
+      optimization_info_.cost_soft_constraints = parts[2];
+    }
+    optimization_info_.n_iterations = iterations;
+    optimization_info_.stopping_reason = code;
+    return code;
+  }
   void getTrajectory(Trajectory* trajectory) const { poly_opt_.getTrajectory(trajectory); }
   const PolynomialOptimization<_N>& getPolynomialOptimizationRef() const { return poly_opt_; }
   PolynomialOptimization<_N>& getPolynomialOptimizationRef() { return poly_opt_; }
@@ -570,6 +802,7 @@ class PolynomialOptimizationNonLinear {
   NonlinearOptimizationParameters optimization_parameters_;
   OptimizationInfo optimization_info_;
   double limits_[9];
+  std::vector<int> constraint_dimension_;
   std::vector<int> constraint_derivative_;   // in the order the constraints were added (inequality_constraints_, nl.h:223)
   std::vector<double> constraint_value_;
 };
@@ -592,14 +825,54 @@ struct PathResult {
 
 class TrajectoryGeneratorBatch {
  public:
-  explicit TrajectoryGeneratorBatch(int device = 0) : device_(device) { tg_default_params(&params); }
+  explicit TrajectoryGeneratorBatch(int device = 0) : device_(device), devices_(1, device) { tg_default_params(&params); }
+  // several GPUs of one box: the paths of a call are sharded by index over the devices (contiguous blocks, one context and one
+  // host thread per device, no exchange between them -- SURVEY.md 8e)
+  explicit TrajectoryGeneratorBatch(const std::vector<int>& devices) : device_(devices.empty() ? 0 : devices[0]), devices_(devices.empty() ? std::vector<int>(1, 0) : devices) {
+    tg_default_params(&params);
+  }
   tg_params params;  // production defaults; edit before optimize()
+  const std::vector<int>& devices() const { return devices_; }
 
   // initial_states: empty (no prepended state, node.cpp:508-510) or one per path
   bool optimize(const std::vector<std::vector<Waypoint>>& paths, const std::vector<InitialState>& initial_states, std::vector<PathResult>* out) {
     if (!out) return false;
     const int B = (int)paths.size();
     if (B < 1 || (!initial_states.empty() && (int)initial_states.size() != B)) return false;
+    const int G = (int)std::min<size_t>(devices_.size(), (size_t)B);
+    if (G <= 1) return optimize_on(device_, paths, initial_states, 0, B, out, true);
+    std::vector<int> slot(G, 0);  // a device listed twice gets two contexts (two host threads on one GPU)
+    for (int g = 0; g < G; ++g) {
+      for (int h = 0; h < g; ++h)
+        if (devices_[h] == devices_[g]) ++slot[g];
+      b200::Context::instance(devices_[g], slot[g]);  // create the contexts before the threads start
+    }
+    out->assign(B, PathResult());
+    std::vector<int> ok(G, 0);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < G; ++g) {
+      const int p0 = (int)((long long)B * g / G), p1 = (int)((long long)B * (g + 1) / G);
+      workers.emplace_back([this, &paths, &initial_states, out, &ok, &slot, g, p0, p1]() {
+        ok[g] = optimize_on(devices_[g], paths, initial_states, p0, p1, out, false, slot[g]) ? 1 : 0;
+      });
+    }
+    for (std::thread& t : workers) t.join();
+    for (int g = 0; g < G; ++g)
+      if (!ok[g]) return false;
+    return true;
+  }
+
+ private:
+  // paths [p0, p1) on one device; results into (*out)[p0 .. p1)
+  bool optimize_on(int device, const std::vector<std::vector<Waypoint>>& all_paths, const std::vector<InitialState>& all_states, int p0, int p1,
+                   std::vector<PathResult>* out_all, bool resize_out, int slot = 0) {
+    const std::vector<std::vector<Waypoint>> paths(all_paths.begin() + p0, all_paths.begin() + p1);
+    const std::vector<InitialState> initial_states(all_states.empty() ? all_states.begin() : all_states.begin() + p0,
+                                                   all_states.empty() ? all_states.begin() : all_states.begin() + p1);
+    std::vector<PathResult> local;
+    std::vector<PathResult>* out = &local;
+    const int device_ = device;
+    const int B = (int)paths.size();
     std::vector<int> wp_off(B + 1, 0);
     for (int p = 0; p < B; ++p) wp_off[p + 1] = wp_off[p] + (int)paths[p].size();
     std::vector<double> wp((size_t)wp_off[B] * 4);
@@ -621,7 +894,7 @@ class TrajectoryGeneratorBatch {
         for (int k = 0; k < 4; ++k) { d[2 + k] = initial_states[p].velocity[k]; d[6 + k] = initial_states[p].acceleration[k]; d[10 + k] = initial_states[p].jerk[k]; }
       }
     }
-    b200::Context& c = b200::Context::instance(device_);
+    b200::Context& c = b200::Context::instance(device_, slot);
     std::vector<tg_result> res(B);
     long long totals[2] = {0, 0};
     int rc = tg_optimize_batch(c.get(), B, wp_off.data(), wp.data(), stop.data(), init14.empty() ? nullptr : init14.data(), &params, 0, res.data(), totals);
@@ -645,9 +918,12 @@ class TrajectoryGeneratorBatch {
       }
       r.samples_xyzh.assign(samples.begin() + (size_t)smp_off[p] * 4, samples.begin() + (size_t)smp_off[p + 1] * 4);
     }
+    if (resize_out) out_all->assign(all_paths.size(), PathResult());
+    for (int p = 0; p < B; ++p) (*out_all)[p0 + p] = std::move(local[p]);
     return true;
   }
 
+ public:
   // MrsTrajectoryGeneration::preprocessPath (node.cpp:431-500) for one path
   std::vector<Waypoint> preprocessPath(const std::vector<Waypoint>& in, double min_waypoint_distance = 0.05, bool straightener = false,
                                        double max_deviation = 0.05, double max_hdg_deviation = 0.1) const {
@@ -710,6 +986,7 @@ class TrajectoryGeneratorBatch {
 
  private:
   int device_;
+  std::vector<int> devices_;
 };
 
 }  // namespace eth_trajectory_generation

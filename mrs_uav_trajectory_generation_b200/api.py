@@ -159,6 +159,10 @@ class PolynomialOptimization:
         return self._ctx or default_context()
 
     def setupFromVertices(self, vertices, times, derivative_to_optimize):  # lin_impl.h:61-106
+        if 0 <= derivative_to_optimize < 2:
+            # the reference accepts 0 and 1 as well (lin_impl.h:61-70); the kernels integrate the squared 2nd, 3rd or 4th derivative
+            print("[PolynomialOptimization]: derivative_to_optimize = %d is not supported by the B200 path (2, 3 or 4)" % derivative_to_optimize)
+            return False
         if not (0 <= derivative_to_optimize <= 4):
             print("You tried to optimize a derivative that is not possible")  # CHECK prints and continues (eth/misc.h)
             return False
@@ -180,7 +184,7 @@ class PolynomialOptimization:
         vtx_off, masks, vals = pack_vertices(self._lists)
         self._seg_off = vtx_off - np.arange(len(vtx_off), dtype=np.int32)
         self.coef, self.cost = self._c().solve_linear_batch(vtx_off, masks, vals, np.concatenate(self._times),
-                                                            max(2, self.derivative_to_optimize))
+                                                            self.derivative_to_optimize)
         return True
 
     def computeCost(self):  # lin_impl.h:127-141
@@ -230,7 +234,8 @@ class DerivativeFreeTimeAllocation:
     def __init__(self, vertices, times, derivative_to_optimize, parameters, constraints, ctx=None):
         self.ctx = ctx or default_context()
         self.P = parameters
-        self.r = max(2, derivative_to_optimize)
+        self.r = derivative_to_optimize
+        self.vertices = list(vertices)
         _, self.mask, self.vals = pack_vertices([vertices])
         self.times0 = np.asarray(times, dtype=np.float64)
         self.S = len(self.times0)
@@ -247,13 +252,22 @@ class DerivativeFreeTimeAllocation:
         n = len(x0)
         lo, hi = np.full(n, -np.finfo(np.float64).max), np.full(n, np.finfo(np.float64).max)
         lo[: self.S] = self.kTimeLowerBound
-        if self.with_free:  # setFreeEndpointDerivativeHardConstraints (nl_impl.h:764-805)
+        if self.with_free:
+            # setFreeEndpointDerivativeHardConstraints (nl_impl.h:764-805), INCLUDING its index arithmetic: free_deriv_counter
+            # advances only for derivatives <= derivative_to_optimize while the variables hold every free slot (0..4), so for
+            # derivative_to_optimize < 4 the bounds land where the reference puts them, not on the slots one would expect
             n_free = len(free_slots)
             for dim, deriv, value in self.constraints:
-                for j, (_, slot_deriv) in enumerate(free_slots):
-                    if slot_deriv == deriv:
-                        lo[self.S + dim * n_free + j] = -abs(value)
-                        hi[self.S + dim * n_free + j] = abs(value)
+                counter = 0
+                for v in range(len(self.mask)):
+                    for k in range(self.r + 1):
+                        if not (self.mask[v] >> k) & 1:
+                            if k == deriv:
+                                at = self.S + dim * n_free + counter
+                                if at < n:
+                                    lo[at] = -abs(value)
+                                    hi[at] = abs(value)
+                            counter += 1
         # "Check if initial solution isn't already out of bounds" (nl_impl.h:497-503)
         lo = np.minimum(lo, x0)
         hi = np.maximum(hi, x0)
@@ -322,6 +336,7 @@ class PolynomialOptimizationNonLinear:
         self.params = parameters or NonlinearOptimizationParameters()
         self._gen = TrajectoryGenerator(ctx=ctx)
         self._limits = [None] * 9
+        self._constraints = []  # (dimension, derivative, value) in the order they were added (inequality_constraints_, nl.h:223)
 
     def setupFromWaypoints(self, waypoints, initial_state=None, derivative_to_optimize=2):
         """The node builds the vertices from waypoints (node.cpp:923-977); the batched kernel does the same on device."""
@@ -331,19 +346,21 @@ class PolynomialOptimizationNonLinear:
         return True
 
     def addMaximumMagnitudeConstraint(self, dimension, derivative, maximum_value):  # nl_impl.h:538-565, mapping 355-381
-        if derivative not in (1, 2, 3) or dimension not in (0, 1, 2, 3):
+        if derivative not in (1, 2, 3, 4) or dimension not in (0, 1, 2, 3):
             return False
-        group = 0 if dimension <= 1 else (1 if dimension == 2 else 2)
-        idx = {(0, 1): 0, (1, 1): 1, (0, 2): 2, (1, 2): 3, (0, 3): 4, (1, 3): 5, (2, 1): 6, (2, 2): 7, (2, 3): 8}[(group, derivative)]
-        self._limits[idx] = float(maximum_value)
-        if hasattr(self, "_constraints"):
-            self._constraints.append((int(dimension), int(derivative), float(maximum_value)))
+        if derivative <= 3:  # snap limits only enter the soft-constraint objectives
+            group = 0 if dimension <= 1 else (1 if dimension == 2 else 2)
+            idx = {(0, 1): 0, (1, 1): 1, (0, 2): 2, (1, 2): 3, (0, 3): 4, (1, 3): 5, (2, 1): 6, (2, 2): 7, (2, 3): 8}[(group, derivative)]
+            self._limits[idx] = float(maximum_value)
+        self._constraints.append((int(dimension), int(derivative), float(maximum_value)))
         return True
 
     def setupFromVertices(self, vertices, times, derivative_to_optimize):  # nl_impl.h:51-82
         """Vertices + initial segment times, for the derivative-free methods 0/1/3/4 (optimizeTime, optimizeTimeAndFreeConstraints)."""
         self._vertices, self._times0, self._r = list(vertices), np.asarray(times, dtype=np.float64), derivative_to_optimize
-        self._constraints = []
+        if 0 <= derivative_to_optimize < 2:
+            print("[PolynomialOptimizationNonLinear]: derivative_to_optimize = %d is not supported by the B200 path (2, 3 or 4)" % derivative_to_optimize)
+            return False
         return len(self._vertices) == len(self._times0) + 1
 
     def optimize(self):  # nl_impl.h:89-118 -> returns the nlopt-style code
@@ -365,13 +382,14 @@ class PolynomialOptimizationNonLinear:
 
 
 class BatchResult:
-    def __init__(self, results, out):
+    def __init__(self, results, out, ctx=None):
         self.results = results
         self.out = out
+        self.ctx = ctx  # the generator's context: later evaluate / sample calls on a trajectory stay on its device
 
     def trajectory(self, p):
         s0, s1 = self.out["seg_off"][p], self.out["seg_off"][p + 1]
-        return Trajectory(self.out["coef"][s0:s1], self.out["times"][s0:s1])
+        return Trajectory(self.out["coef"][s0:s1], self.out["times"][s0:s1], self.ctx)
 
     def samples(self, p):
         m0, m1 = self.out["smp_off"][p], self.out["smp_off"][p + 1]
@@ -399,7 +417,7 @@ class TrajectoryGenerator:
         stop = None if stop_at is None else np.concatenate([np.asarray(s, dtype=np.uint8) for s in stop_at])
         init = None if initial_states is None else np.stack([np.asarray(i, dtype=np.float64) for i in initial_states])
         res, _ = self.ctx.optimize_batch(wp_off, wp, stop, init, params)
-        return BatchResult(res, self.ctx.fetch_outputs())
+        return BatchResult(res, self.ctx.fetch_outputs(), self.ctx)
 
     def findTrajectory(self, waypoints, initial_state=None, params=None):
         """One findTrajectory pass without the deviation loop (node.cpp:857-1209)."""

@@ -14,10 +14,10 @@ from mrs_uav_trajectory_generation_b200 import workloads as W
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run_shim(libdir, libname, tmp_path):
-    exe = str(tmp_path / "test_shim")
-    out = str(tmp_path / "shim.txt")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"),
+def _run_shim(libdir, libname, tmp_path, source="test_shim.cpp", extra=()):
+    exe = str(tmp_path / source.replace(".cpp", ""))
+    out = str(tmp_path / source.replace(".cpp", ".txt"))
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-pthread", *extra, "-o", exe, os.path.join(ROOT, "tests", "cpp", source),
                            "-L" + libdir, "-l" + libname, "-Wl,-rpath," + libdir])
     subprocess.check_call([exe, out])
     res = {}
@@ -89,6 +89,104 @@ def _check_side_steps(res):
     fb = O.fallback_sample(pw, ps, lim, 0.2, 2.0)
     assert np.array_equal(res["fallback"][0].reshape(-1, 4), fb)
     assert np.array_equal(res["idxs"][0].astype(np.int32), O.waypoint_idxs(fb, pw))
+
+
+def _eigen_flags():
+    # the Eigen stand-in (test infrastructure; Eigen is absent from this image) and, in the build container, the reference's own
+    # eth_mav_msgs/eigen_mav_msgs.h for the EigenTrajectoryPoint type
+    flags = ["-I" + os.path.join(ROOT, "oracle", "ref_shim")]
+    if os.path.isdir("/root/reference/include"):
+        flags.append("-I/root/reference/include")
+    return flags
+
+
+def _check_eigen(res, ctx):
+    """tests/cpp/test_shim_eigen.cpp: reference-typed call sites (Eigen::Vector4d in, Eigen::VectorXd / EigenTrajectoryPoint out),
+    evaluateRange, optimize() of the derivative-free methods, two contexts side by side."""
+    import mrs_uav_trajectory_generation_b200.api as A
+
+    n_wp, r = 7, 2
+    wp = np.array([[1.5 * i, 0.4 if i % 2 == 0 else -0.6, 4.0 + 0.1 * i, 0.2 * i] for i in range(n_wp)])
+    mask = np.ones(n_wp, np.uint8)
+    mask[0], mask[-1] = 0b1111, 0b111
+    vals = np.zeros((n_wp, O.HALF, O.D))
+    vals[:, 0] = wp
+    vals[0, 1], vals[0, 2] = (0.3, -0.1, 0.05, 0.02), (0.0, 0.1, 0.0, 0.0)
+    times = np.array([0.9 + 0.2 * (i % 3) for i in range(n_wp - 1)])
+    assert np.array_equal(res["vtx0_vel"][0], vals[0, 1])
+    ref = O.time_alloc(mask, vals, times, r)
+    code, evals, cost = res["nl_meta"][0]
+    assert (int(code), int(evals)) == (ref["nlopt_code"], ref["n_evals"]) and cost == ref["final_cost"]
+    assert np.array_equal(res["nl_times"][0], ref["times"]) and np.array_equal(res["nl_coef"][0].reshape(-1, 4, 10), ref["coef"])
+    tq = 0.37 * float(np.add.accumulate(ref["times"])[-1])  # getMaxTime(): accumulated in segment order
+    tot = 0.0
+    for t in ref["times"]:
+        tot += t
+    tq = 0.37 * tot
+    assert np.array_equal(res["eval_p"][0], O.trajectory_evaluate(ref["coef"], ref["times"], tq, 0)[0])
+    assert np.array_equal(res["eval_s"][0], O.trajectory_evaluate(ref["coef"], ref["times"], tq, 4)[0])
+    full, t_ns = O.sample(ref["coef"], ref["times"], 0.2)
+    got = res["samples"][0].reshape(-1, 8)
+    assert got.shape[0] == full.shape[0]
+    assert np.array_equal(got[:, :3], full[:, :3]) and np.array_equal(got[:, 5], full[:, 7]) and np.array_equal(got[:, 6], full[:, 16])
+    assert np.array_equal(got[:, 7].astype(np.int64), t_ns)
+    # the quaternion is built on the host by the (stand-in) Eigen from the raw heading: w = cos(yaw / 2), z = sin(yaw / 2)
+    assert np.allclose(got[:, 3], np.cos(0.5 * full[:, 3]), rtol=0, atol=2e-16) and np.allclose(got[:, 4], np.sin(0.5 * full[:, 3]), rtol=0, atol=2e-16)
+    # evaluateRange(t_start inside segment 1, dt 0.3, jerk): the reference's walk (eth/trajectory.cpp:93-151) restated here
+    T = ref["times"]
+    t_start, t_end, dt = T[0] + 0.05, tot, 0.3
+    acc, i = 0.0, 0
+    for i in range(len(T)):
+        acc += T[i]
+        if acc > t_start:
+            break
+    acc -= T[i]
+    in_seg = t_start - acc
+    want, want_t = [], []
+    while acc < t_end:
+        if in_seg > T[i]:
+            in_seg = in_seg - T[i]
+            i += 1
+            if i >= len(T):
+                break
+            continue
+        want.append(O.trajectory_evaluate(ref["coef"][i:i + 1], T[i:i + 1], in_seg, 3)[0])
+        want_t.append(acc)
+        in_seg += dt
+        acc += dt
+    assert np.array_equal(res["range_t"][0], np.array(want_t)) and np.array_equal(res["range_jerk"][0].reshape(-1, 4), np.array(want))
+    # optimize() of the derivative-free methods == the Python mirror of the same search over the same batched objective
+    verts = []
+    for v in range(n_wp):
+        vx = A.Vertex(4)
+        for k in range(5):
+            if (mask[v] >> k) & 1:
+                vx.addConstraint(k, vals[v, k].copy())
+        verts.append(vx)
+    for key, method, iters, cons in (("df", 0, 6, [(0, 1, 4.0), (0, 2, 2.0)]), ("df4", 4, 3, [(0, 1, 4.0), (2, 2, 1.0)])):
+        P = A.NonlinearOptimizationParameters()
+        P.time_alloc_method, P.max_iterations = method, iters
+        opt = A.PolynomialOptimizationNonLinear(4, P, ctx=ctx)
+        assert opt.setupFromVertices(verts, times, r)
+        for c in cons:
+            opt.addMaximumMagnitudeConstraint(*c)
+        pcode = opt.optimize()
+        m = res[key + "_meta"][0]
+        assert (int(m[0]), int(m[1])) == (pcode, opt._dfo.n_iterations), (key, m, pcode, opt._dfo.n_iterations)
+        assert np.array_equal(res[key + "_times"][0], opt._dfo.times) and np.array_equal(res[key + "_coef"][0].reshape(-1, 4, 10), opt._dfo.coef)
+        assert np.array_equal(m[2:5], opt._dfo.cost_parts)
+    assert res["r1_refused"][0][0] == 1.0 and res["multi_ctx_same"][0][0] == 1.0
+
+
+def test_cpp_shim_eigen_types_on_host_emulation(oracle, emu_lib, emu_ctx, tmp_path):
+    res = _run_shim(os.path.join(ROOT, "tests", "host_emu"), "tg_emu", tmp_path, "test_shim_eigen.cpp", _eigen_flags())
+    _check_eigen(res, emu_ctx)
+
+
+@pytest.mark.gpu
+def test_cpp_shim_eigen_types_on_gpu(oracle, gpu_ctx, tmp_path):
+    res = _run_shim(os.path.join(ROOT, "mrs_uav_trajectory_generation_b200"), "tg_b200", tmp_path, "test_shim_eigen.cpp", _eigen_flags())
+    _check_eigen(res, gpu_ctx)
 
 
 def test_cpp_shim_on_host_emulation(oracle, emu_lib, tmp_path):
