@@ -199,6 +199,12 @@ double tg_measure_fp64_peak(tg_ctx* ctx, int mode);
  * reference's value a second pass practically never happens; tests lower it to drive the multi-pass path. */
 int tg_test_set_scale_tolerance(tg_ctx* ctx, double tolerance);
 
+/* Test hook: the device Jenkins-Traub root finder = findRootsJenkinsTraub (eth/rpoly/rpoly_ak1.cpp:76-120) on n arbitrary
+ * polynomials.  coeffs[n][16]: increasing powers, ncoef[n] <= 16 of them used; re / im [n][16]: the zeros in the order the
+ * reference stores them (zeros at the origin first, then as found); nroots[n]: how many (fewer than the degree = no
+ * convergence after 20 shifts, as in the reference).  The production path only ever reads maxima at these zeros. */
+int tg_test_find_roots_batch(tg_ctx* ctx, int n, const double* coeffs, const int* ncoef, double* re, double* im, int* nroots);
+
 /* Host-side evaluation of the deterministic math layer (include/tg_detmath.h), for tests:
  *   fn 0 log, 1 exp, 2 sin, 3 cos, 4 atan2(x, y), 5 cbrt, 6 pow(x, (int)y). */
 double tg_detmath_eval(int fn, double x, double y);

@@ -208,6 +208,18 @@ class Context:
             out[(prefix + ":" if prefix else "") + nm.replace("tg::", "")] = (ms[i], ln[i], it[i])
         return out
 
+    def test_find_roots(self, coeffs, ncoef):
+        """Test hook: the device Jenkins-Traub on polynomials coeffs[n][16] (increasing powers, ncoef[n] used) -> re, im [n][16], nroots[n]."""
+        c = np.ascontiguousarray(coeffs, dtype=np.float64)
+        nc = np.ascontiguousarray(ncoef, dtype=np.int32)
+        n = len(nc)
+        assert c.shape == (n, 16)
+        re, im, nr = np.zeros((n, 16)), np.zeros((n, 16)), np.zeros(n, dtype=np.int32)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        self._check(self.L.lib.tg_test_find_roots_batch(self.h, n, c.ctypes.data_as(dp), nc.ctypes.data_as(ip), re.ctypes.data_as(dp), im.ctypes.data_as(dp),
+                                                        nr.ctypes.data_as(ip)))
+        return re, im, nr
+
     def test_set_scale_tolerance(self, tol):
         self.L.lib.tg_test_set_scale_tolerance.argtypes = [C.c_void_p, C.c_double]
         self._check(self.L.lib.tg_test_set_scale_tolerance(self.h, float(tol)))

@@ -278,6 +278,16 @@ int tg_test_set_scale_tolerance(tg_ctx* ctx, double tolerance) {
   return TG_OK;
 }
 
+int tg_test_find_roots_batch(tg_ctx* ctx, int n, const double* coeffs, const int* ncoef, double* re, double* im, int* nroots) {
+  return tg_guard(ctx, [&]() -> int {
+    if (n < 1 || !coeffs || !ncoef || !re || !im || !nroots) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    for (int i = 0; i < n; ++i)
+      if (ncoef[i] < 0 || ncoef[i] > 16) { ctx->err = "at most 16 coefficients per polynomial"; return TG_ERR_INVALID; }
+    ctx->pipe.find_roots_batch(n, coeffs, ncoef, re, im, nroots);
+    return TG_OK;
+  });
+}
+
 int tg_preprocess_paths(tg_ctx* ctx, int B, const int* wp_off, const double* wp, const uint8_t* stop_at, double min_waypoint_distance, int straightener_enabled,
                         double straightener_max_deviation, double straightener_max_hdg_deviation, int* out_count, double* out_wp, uint8_t* out_stop_at) {
   return tg_guard(ctx, [&]() -> int {

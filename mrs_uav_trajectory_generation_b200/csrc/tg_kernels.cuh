@@ -987,6 +987,34 @@ struct ExtremaRawFn {  // one thread per work item (segment, or entry of a devic
     maxima[gs * 9 + Q] = segment_max_impl<Q>(coef + gs * TG_D * TG_N, times[gs], scratch, stride, nullptr);
   }
 };
+// Test hook (tg_test_find_roots_batch): findRootsJenkinsTraub (rpoly_ak1.cpp:76-120) on arbitrary polynomials of up to 16
+// coefficients, zeros written in the order the reference stores them (zeros at the origin, then as found)
+struct RootSink {
+  double* re;
+  double* im;
+  int n;
+  TG_HD void operator()(double r, double i) {
+    re[n] = r;
+    im[n] = i;
+    ++n;
+  }
+};
+struct FindRootsFn {
+  const double* coeffs;  // [n][16] increasing powers, zero padded
+  const int* ncoef;
+  double* re;            // [n][16]
+  double* im;
+  int* nroots;
+  static constexpr int kScratch = 4 * 16;
+  TG_HD void operator()(size_t i, double* scratch, int stride) const {
+    double ci[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) ci[k] = (k < ncoef[i]) ? coeffs[i * 16 + k] : 0.0;
+    RootSink sink{re + i * 16, im + i * 16, 0};
+    find_roots_jt<15>(ci, scratch, stride, sink, nullptr);
+    nroots[i] = sink.n;
+  }
+};
 // computeMaximumOfMagnitude (lin_impl.h:477-508), step 1: one thread per segment -> the segment's first-largest candidate
 template <int DERIV>
 struct MaxMagnitudeSegFn {

@@ -881,6 +881,25 @@ class Pipeline {
     be_.d2h(maxima, d_m, sizeof(double) * (size_t)totS * 9);
   }
 
+  // test hook: the device Jenkins-Traub on n arbitrary polynomials (<= 16 coefficients each, increasing powers)
+  void find_roots_batch(int n, const double* coeffs, const int* ncoef, double* re, double* im, int* nroots) {
+    scratch_.reset();
+    double* d_c = scratch_.template alloc<double>((size_t)n * 16);
+    int* d_n = scratch_.template alloc<int>(n);
+    double* d_re = scratch_.template alloc<double>((size_t)n * 16);
+    double* d_im = scratch_.template alloc<double>((size_t)n * 16);
+    int* d_nr = scratch_.template alloc<int>(n);
+    be_.h2d(d_c, coeffs, sizeof(double) * (size_t)n * 16);
+    be_.h2d(d_n, ncoef, sizeof(int) * n);
+    be_.dev_memset(d_re, 0, sizeof(double) * (size_t)n * 16);
+    be_.dev_memset(d_im, 0, sizeof(double) * (size_t)n * 16);
+    be_.for_each_scratch((size_t)n, FindRootsFn{d_c, d_n, d_re, d_im, d_nr});
+    launches(1);
+    be_.d2h(re, d_re, sizeof(double) * (size_t)n * 16);
+    be_.d2h(im, d_im, sizeof(double) * (size_t)n * 16);
+    be_.d2h(nroots, d_nr, sizeof(int) * n);
+  }
+
   // PolynomialOptimization<10>::computeMaximumOfMagnitude(derivative) for B trajectories (lin_impl.h:477-508)
   bool max_magnitude_batch(int B, const int* seg_off, const double* coef, const double* times, int derivative, double* value, double* time,
                            int* segment_idx) {

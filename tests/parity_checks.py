@@ -382,6 +382,49 @@ def check_random_flier(ctx, B, first_index=0, **params_kw):
     return compare_optimize(ctx, wp_off, wp, params_kw=params_kw)
 
 
+def check_roots_against_reference_vectors(ctx):
+    """The device Jenkins-Traub (tg_poly.cuh) against tests/golden/rpoly_reference.npz -- 600 polynomials whose zeros were computed by the
+    REFERENCE's own rpoly_ak1.cpp (compiled unmodified, tests/golden/gen_golden.py): every zero, in the reference's order, bit for bit."""
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rpoly_reference.npz"))
+    n = len(z["n_coeffs"])
+    assert z["coeffs"].shape[1] == 16
+    re, im, nr = ctx.test_find_roots(z["coeffs"], z["n_coeffs"])
+    bad = 0
+    for i in range(n):
+        k = int(z["n_roots"][i])
+        if nr[i] != k or not np.array_equal(re[i, :k], z["re"][i, :k]) or not np.array_equal(im[i, :k], z["im"][i, :k]):
+            bad += 1
+    assert bad == 0, bad
+    return n
+
+
+def check_roots_adversarial(ctx, n=1500, seed=77):
+    """Random polynomials of every degree 1..15 with wide coefficient ranges, exact zeros at the origin, vanishing leading coefficients,
+    clustered zeros: device zeros == oracle zeros (the oracle itself is pinned to the reference's file)."""
+    rng = np.random.default_rng(seed)
+    C16 = np.zeros((n, 16))
+    nc = np.zeros(n, np.int32)
+    for i in range(n):
+        k = int(rng.integers(2, 17))
+        c = rng.standard_normal(k) * np.exp(rng.uniform(-5, 5, k))
+        if i % 5 == 0:
+            c[: int(rng.integers(1, 3))] = 0.0
+        if i % 7 == 0:
+            c[-int(rng.integers(1, 3)):] = 0.0
+        if i % 11 == 0 and k > 5:
+            roots = np.concatenate([np.full(3, rng.uniform(-2, 2)), rng.uniform(-3, 3, k - 4)])
+            c = np.poly(roots)[::-1][:k]
+        C16[i, : len(c)] = c
+        nc[i] = len(c)
+    re, im, nr = ctx.test_find_roots(C16, nc)
+    for i in range(n):
+        r2, i2, ok = O.find_roots(C16[i, : nc[i]])
+        assert nr[i] == len(r2) and np.array_equal(re[i, : nr[i]], r2) and np.array_equal(im[i, : nr[i]], i2), i
+    return True
+
+
 def check_acceptance_rejects(ctx, B=48):
     """The acceptance logic of findTrajectory (node.cpp:1138-1149, 1178-1199): with max_len_factor = 1.9 some of these paths are
     rejected as 'too long' (FindStatus 2), with min_len_factor = 1.9 most as 'too short' (3); a rejected findTrajectory makes

@@ -133,3 +133,8 @@ def test_extrema_random_polynomials(emu_ctx, oracle):
 
 def test_acceptance_reject_branches(emu_ctx, oracle):
     assert PC.check_acceptance_rejects(emu_ctx, B=24)
+
+
+def test_device_jenkins_traub_against_reference_vectors(emu_ctx, oracle):
+    assert PC.check_roots_against_reference_vectors(emu_ctx) == 600
+    assert PC.check_roots_adversarial(emu_ctx, n=300)

@@ -170,3 +170,38 @@ def test_properties_at_full_size(gpu_ctx):
 @pytest.mark.gpu
 def test_acceptance_reject_branches(gpu_ctx, oracle):
     assert PC.check_acceptance_rejects(gpu_ctx, B=48)
+
+
+@pytest.mark.gpu
+def test_device_jenkins_traub_against_reference_vectors(gpu_ctx, oracle):
+    assert PC.check_roots_against_reference_vectors(gpu_ctx) == 600
+    assert PC.check_roots_adversarial(gpu_ctx, n=1500)
+
+
+@pytest.mark.gpu
+def test_full_bench_batch_against_oracle(gpu_ctx, oracle):
+    """All 65 536 paths of ONE bench batch (bench.py's generator, rank 0) through the GPU in a single call, every path compared with the
+    multi-threaded oracle: verdicts, rounds, evaluation / pass / waypoint / sample counts exactly; times, coefficients, samples and
+    final waypoints bit for bit."""
+    B, chunk = 65536, 4096
+    wp_off, wp = W.random_flier_paths_fast(B, first_index=0)
+    P = gpu_ctx.L.default_params()
+    res, totals = gpu_ctx.optimize_batch(wp_off, wp, None, None, P)
+    out = gpu_ctx.fetch_outputs()
+    ints = ("status", "success", "nlopt_code", "n_evals", "rounds", "safe", "n_waypoints", "n_samples", "n_scale_passes")
+    for c0 in range(0, B, chunk):
+        off = wp_off[c0: c0 + chunk + 1] - wp_off[c0]
+        ref = O.optimize_batch(off, wp[wp_off[c0]: wp_off[c0 + chunk]], cap_wp=200, cap_samples=1600)
+        for q in range(chunk):
+            p = c0 + q
+            r, g = ref["res"][q], res[p]
+            assert not r.overflow
+            for k in ints:
+                assert getattr(r, k) == g[k], (p, k, getattr(r, k), g[k])
+            s0, s1 = out["seg_off"][p], out["seg_off"][p + 1]
+            m0, m1 = out["smp_off"][p], out["smp_off"][p + 1]
+            S, M = s1 - s0, m1 - m0
+            assert np.array_equal(out["times"][s0:s1], ref["times"][q, :S]), p
+            assert np.array_equal(out["coef"][s0:s1], ref["coeffs"][q, :S]), p
+            assert np.array_equal(out["samples"][m0:m1], ref["samples"][q, :M]), p
+            assert np.array_equal(out["wp"][s0 + p: s1 + p + 1], ref["wp"][q, : S + 1]), p
