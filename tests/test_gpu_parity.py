@@ -3,6 +3,7 @@ inputs, plus size-independent properties at BASELINE sizes.  Run on the B200 box
 import numpy as np
 import pytest
 
+import oracle_lib as O
 import parity_checks as PC
 from mrs_uav_trajectory_generation_b200 import workloads as W
 
