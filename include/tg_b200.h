@@ -56,6 +56,7 @@ typedef struct tg_params {
   int first_segment_checked;    /* max_deviation_first_segment_ (node.cpp:874-878) */
   double max_len_factor, min_len_factor; /* 3.0, 0.33 (node.cpp:1178-1199) */
   int run_time_alloc;           /* 1: full findTrajectory; 0: linear solve at the Euclidean times + sampling */
+  int override_heading_atan2;   /* getTrajectoryReference: heading of a sample = direction to the next one (node.cpp:1586-1599); default 0 */
 } tg_params;
 
 /* Per-problem outcome of tg_optimize_batch. */

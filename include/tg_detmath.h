@@ -489,6 +489,18 @@ TG_HD double datan2(double y, double x) {
   const double delta = num.hi / den.hi;
   return z0 + delta;
 }
+/* hypot for moderate magnitudes (sample spacings): x^2 + y^2 in double-double, square root with one double-double Newton
+   correction, one rounding */
+TG_HD double dhypot(double x, double y) {
+  if (disnan(x) || disnan(y) || disinf(x) || disinf(y)) return dabs(x) + dabs(y);
+  const double ax = dabs(x), ay = dabs(y);
+  if (ax > 0x1p500 || ay > 0x1p500 || (ax < 0x1p-500 && ay < 0x1p-500)) return dsqrt(x * x + y * y);
+  const dd s = dd_add(two_prod(x, x), two_prod(y, y));
+  const double r = dsqrt(s.hi);
+  if (r == 0.0) return r;
+  const dd res = dd_add(s, dd_neg(two_prod(r, r)));  /* s - r^2 */
+  return r + res.hi / (2.0 * r);
+}
 /* exp: x = k ln2 + r, exp(r / 256) - 1 by Taylor in double-double, squared up eight times */
 TG_HD_OUTLINE dd exp_dd(double x, int* kout) {
   const double l1 = 0x1.62e42fee00000p-1, l2 = 0x1.a39ef35793c76p-33, l3 = 0x1.cc01f97b57a08p-87, inv_ln2 = 0x1.71547652b82fep+0;

@@ -31,6 +31,7 @@ class Params(C.Structure):
         ("max_len_factor", C.c_double),
         ("min_len_factor", C.c_double),
         ("run_time_alloc", C.c_int),
+        ("override_heading_atan2", C.c_int),
     ]
 
 

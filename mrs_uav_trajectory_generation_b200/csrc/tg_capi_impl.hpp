@@ -92,6 +92,7 @@ void tg_default_params(tg_params* p) {
   p->max_len_factor = 3.0;
   p->min_len_factor = 0.33;
   p->run_time_alloc = 1;
+  p->override_heading_atan2 = 0;
 }
 
 int tg_ctx_create(int device, tg_ctx** out) {

@@ -79,6 +79,7 @@ struct Params {
   int first_segment_checked;
   double max_len_factor, min_len_factor;
   int run_time_alloc;
+  int override_heading_atan2;
 };
 
 }  // namespace tg

@@ -987,6 +987,24 @@ struct ExtremaRawFn {  // one thread per work item (segment, or entry of a devic
     maxima[gs * 9 + Q] = segment_max_impl<Q>(coef + gs * TG_D * TG_N, times[gs], scratch, stride, nullptr);
   }
 };
+// getTrajectoryReference with override_heading_atan2 (node.cpp:1586-1599): the heading of sample i becomes the direction towards
+// sample i+1, or the previous sample's (already overridden) heading when that step is shorter than 0.05 m; the last sample
+// keeps getYaw().  Sequential in the previous heading: one thread per problem.
+struct HeadingAtan2Fn {
+  const int* smp_off;
+  const ProbState* ps;
+  double* xyzh;
+  TG_HD void operator()(size_t p) const {
+    const int n = ps[p].n_samples;
+    double* s = xyzh + (size_t)smp_off[p] * 4;
+    for (int it = 0; it + 1 < n; ++it) {
+      const double dy = s[4 * (it + 1) + 1] - s[4 * it + 1], dx = s[4 * (it + 1)] - s[4 * it];
+      const double dist = tgdm::dhypot(dy, dx);
+      if (dist < 0.05 && it > 0) s[4 * it + 3] = s[4 * (it - 1) + 3];
+      else s[4 * it + 3] = tgdm::datan2(dy, dx);
+    }
+  }
+};
 // Test hook (tg_test_find_roots_batch): findRootsJenkinsTraub (rpoly_ak1.cpp:76-120) on arbitrary polynomials of up to 16
 // coefficients, zeros written in the order the reference stores them (zeros at the origin, then as found)
 struct RootSink {

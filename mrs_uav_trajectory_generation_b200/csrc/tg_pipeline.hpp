@@ -179,6 +179,10 @@ class Pipeline {
     be_.for_each((size_t)g.totSlots, SampleEvalFn{b, g.d_smp_off, smp_prob, seg_idx, t_in, g.d_xyzh, nullptr});
     be_.for_each(B, LengthCheckFn{b, P.dt, P.max_len_factor, P.min_len_factor});
     launches(4);
+    if (P.override_heading_atan2) {  // validation reads positions only, so the override may happen here
+      be_.for_each(B, HeadingAtan2Fn{g.d_smp_off, g.d_ps, g.d_xyzh});
+      launches(1);
+    }
     g.ps.resize(B);
     be_.d2h(g.ps.data(), g.d_ps, sizeof(ProbState) * B);
     if (P.run_time_alloc) {

@@ -22,6 +22,7 @@ struct orc_params {
   int first_segment_checked;
   double max_len_factor, min_len_factor;
   int run_time_alloc;
+  int override_heading_atan2;
 };
 
 static NodeParams to_node(const orc_params* p) {
@@ -40,6 +41,7 @@ static NodeParams to_node(const orc_params* p) {
   P.max_len_factor = p->max_len_factor;
   P.min_len_factor = p->min_len_factor;
   P.run_time_alloc = p->run_time_alloc != 0;
+  P.override_heading_atan2 = p->override_heading_atan2 != 0;
   return P;
 }
 
@@ -56,6 +58,7 @@ double orc_math(int fn, double x, double y) {
     case 4: return m_atan2(x, y);
     case 5: return m_cbrt(x);
     case 6: return m_pow_int(x, (int)y);
+    case 7: return m_hypot(x, y);
   }
   return 0;
 }
@@ -323,14 +326,11 @@ int orc_optimize_path(int V, const double* wp, const uint8_t* stop_at, const dou
   if (coeffs)
     for (int i = 0; i < Sf; ++i)
       for (int d = 0; d < kD; ++d) std::memcpy(coeffs + ((size_t)i * kD + d) * kN, O.find.seg[i].c[d], sizeof(double) * kN);
-  if (samples_xyzh)
-    for (size_t i = 0; i < O.find.samples.size(); ++i) {
-      const Sample& s = O.find.samples[i];
-      samples_xyzh[4 * i + 0] = s.p[0];
-      samples_xyzh[4 * i + 1] = s.p[1];
-      samples_xyzh[4 * i + 2] = s.p[2];
-      samples_xyzh[4 * i + 3] = s.yaw_out;
-    }
+  if (samples_xyzh) {
+    const std::vector<std::array<double, 4>> ref = trajectory_reference(O.find.samples, to_node(prm).override_heading_atan2);
+    for (size_t i = 0; i < ref.size(); ++i)
+      for (int d = 0; d < 4; ++d) samples_xyzh[4 * i + d] = ref[i][d];
+  }
   return 0;
 }
 

@@ -24,6 +24,7 @@ double m_exp_k(double x) { return g_math_mode == kMathDet ? tgdm::dexp_k(x) : st
 double m_sin_k(double x) { return g_math_mode == kMathDet ? tgdm::dsin_k(x) : std::sin(x); }
 double m_cos_k(double x) { return g_math_mode == kMathDet ? tgdm::dcos_k(x) : std::cos(x); }
 double m_atan2_k(double y, double x) { return g_math_mode == kMathDet ? tgdm::datan2_k(y, x) : std::atan2(y, x); }
+double m_hypot(double x, double y) { return g_math_mode == kMathDet ? tgdm::dhypot(x, y) : std::hypot(x, y); }
 double m_cbrt(double x) { return g_math_mode == kMathDet ? tgdm::dcbrt(x) : std::cbrt(x); }
 double m_pow_int(double t, int e) {
   if (g_math_mode == kMathDet) {

@@ -83,6 +83,23 @@ FindResult find_trajectory(const std::vector<Waypoint>& wp, const InitialState& 
   return R;
 }
 
+// node.cpp:1560-1606
+std::vector<std::array<double, 4>> trajectory_reference(const std::vector<Sample>& traj, bool override_heading_atan2) {
+  std::vector<std::array<double, 4>> out;
+  for (size_t it = 0; it < traj.size(); it++) {
+    std::array<double, 4> pt{traj[it].p[0], traj[it].p[1], traj[it].p[2], 0.0};
+    if (override_heading_atan2 && it < (traj.size() - 1)) {
+      const double points_dist = m_hypot(traj[it + 1].p[1] - pt[1], traj[it + 1].p[0] - pt[0]);
+      if (points_dist < 0.05 && it > 0) pt[3] = out[it - 1][3];
+      else pt[3] = m_atan2(traj[it + 1].p[1] - pt[1], traj[it + 1].p[0] - pt[0]);
+    } else {
+      pt[3] = traj[it].yaw_out;
+    }
+    out.push_back(pt);
+  }
+  return out;
+}
+
 static double norm3(const double* a) { return std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
 
 // node.cpp:1533-1554

@@ -50,6 +50,7 @@ double m_sin(double x);
 double m_cos(double x);
 double m_atan2(double y, double x);
 double m_cbrt(double x);
+double m_hypot(double x, double y);
 // the < 1.5 ulp kernels (not the correctly rounded versions) where a last-bit difference cannot reach a result the path reads:
 // Jenkins-Traub's starting radius (rpoly_ak1.cpp:227-246) and the heading's quaternion round trip (eth_mav_msgs/common.h:130-140)
 double m_log_k(double x);
@@ -203,6 +204,7 @@ struct NodeParams {
   bool first_segment_checked = true;  // max_deviation_first_segment_ (node.cpp:874-878)
   double max_len_factor = 3.0, min_len_factor = 0.33;
   bool run_time_alloc = true;  // false => config-2 style: linear solve at the Euclidean times + sampling
+  bool override_heading_atan2 = false;  // getTrajectoryReference: heading = direction to the next sample (node.cpp:1586-1599)
 };
 enum FindStatus { kFindOk = 0, kFindNloptRejected = 1, kFindTooLong = 2, kFindTooShort = 3, kFindSampleFail = 4 };
 struct FindResult {
@@ -215,6 +217,9 @@ struct FindResult {
 };
 // node.cpp:857-1209
 FindResult find_trajectory(const std::vector<Waypoint>& wp, const InitialState& init, const NodeParams& P);
+// getTrajectoryReference (node.cpp:1560-1606): x, y, z, heading of every sample; heading = getYaw(), or with
+// override_heading_atan2 the direction towards the next sample (the previous heading when that step is shorter than 0.05 m)
+std::vector<std::array<double, 4>> trajectory_reference(const std::vector<Sample>& traj, bool override_heading_atan2);
 // node.cpp:1401-1455
 struct Validation {
   bool safe = true;

@@ -425,6 +425,34 @@ def check_roots_adversarial(ctx, n=1500, seed=77):
     return True
 
 
+def check_heading_override(ctx, B=16):
+    """getTrajectoryReference with override_heading_atan2 (node.cpp:1586-1599): heading = direction to the next sample, previous heading
+    when the step is shorter than 0.05 m (a path with a stop_at waypoint produces such steps), last sample keeps getYaw()."""
+    paths, stops = [], []
+    for p in range(B):
+        path = W.random_flier_path(4000 + p, 6 + p % 5)
+        st = np.zeros(len(path), np.uint8)
+        if p % 2 == 0:
+            st[len(path) // 2] = 1  # the vehicle stops there: consecutive samples closer than 0.05 m
+        paths.append(path)
+        stops.append(st)
+    wp_off = np.concatenate([[0], np.cumsum([len(q) for q in paths])]).astype(np.int32)
+    res, out, exact, worst = compare_optimize(ctx, wp_off, np.concatenate(paths), stop_at=np.concatenate(stops), params_kw=dict(override_heading_atan2=1))
+    assert exact
+    # the override really happened: headings follow the direction of travel, and some short steps reused the previous heading
+    smp, off = out["samples"], out["smp_off"]
+    reused = 0
+    for p in range(B):
+        s = smp[off[p]: off[p + 1]]
+        d = s[1:, :2] - s[:-1, :2]
+        dist = np.hypot(d[:, 1], d[:, 0])
+        far = dist >= 0.05
+        assert np.allclose(s[:-1, 3][far], np.arctan2(d[:, 1], d[:, 0])[far], rtol=0, atol=1e-12)
+        reused += int((~far[1:]).sum())
+    assert reused > 0
+    return True
+
+
 def check_acceptance_rejects(ctx, B=48):
     """The acceptance logic of findTrajectory (node.cpp:1138-1149, 1178-1199): with max_len_factor = 1.9 some of these paths are
     rejected as 'too long' (FindStatus 2), with min_len_factor = 1.9 most as 'too short' (3); a rejected findTrajectory makes

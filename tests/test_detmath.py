@@ -15,7 +15,7 @@ import oracle_lib as O
 
 mp.mp.dps = 60
 
-FN = {"log": 0, "exp": 1, "sin": 2, "cos": 3, "atan2": 4, "cbrt": 5, "pow_int": 6}
+FN = {"log": 0, "exp": 1, "sin": 2, "cos": 3, "atan2": 4, "cbrt": 5, "pow_int": 6, "hypot": 7}
 
 
 def ulp(x):
@@ -73,6 +73,9 @@ def test_detmath_accuracy(det, record_property):
     # pow(T, e), e = 1..15 (lin_impl.h:612-615)
     pts = [(float(t), float(e)) for t, e in zip(np.exp(rng.uniform(-4.6, 4.0, N)), rng.integers(1, 16, N))]
     rows["pow_int"] = _scan("pow_int", pts, lambda t, e: mp.mpf(t) ** int(e), lambda t, e: math.pow(t, e))
+    # hypot: spacing of consecutive samples (node.cpp:1588)
+    pts = [(float(a), float(b)) for a, b in zip(rng.uniform(-2, 2, N) * np.exp(rng.uniform(-8, 0, N)), rng.uniform(-2, 2, N) * np.exp(rng.uniform(-8, 0, N)))]
+    rows["hypot"] = _scan("hypot", pts, lambda a, b: mp.sqrt(mp.mpf(a) ** 2 + mp.mpf(b) ** 2), math.hypot)
     for k, (wd, wl, ag, cr) in rows.items():
         print(f"detmath {k:8s}: worst {wd:.3f} ulp (glibc {wl:.3f} ulp), bit-identical to glibc on {100 * ag:.2f} %, correctly rounded on {100 * cr:.2f} %")
         record_property(f"detmath_{k}", (wd, wl, ag, cr))

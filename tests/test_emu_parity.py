@@ -138,3 +138,7 @@ def test_acceptance_reject_branches(emu_ctx, oracle):
 def test_device_jenkins_traub_against_reference_vectors(emu_ctx, oracle):
     assert PC.check_roots_against_reference_vectors(emu_ctx) == 600
     assert PC.check_roots_adversarial(emu_ctx, n=300)
+
+
+def test_override_heading_atan2(emu_ctx, oracle):
+    assert PC.check_heading_override(emu_ctx)

@@ -206,3 +206,8 @@ def test_full_bench_batch_against_oracle(gpu_ctx, oracle):
             assert np.array_equal(out["coef"][s0:s1], ref["coeffs"][q, :S]), p
             assert np.array_equal(out["samples"][m0:m1], ref["samples"][q, :M]), p
             assert np.array_equal(out["wp"][s0 + p: s1 + p + 1], ref["wp"][q, : S + 1]), p
+
+
+@pytest.mark.gpu
+def test_override_heading_atan2(gpu_ctx, oracle):
+    assert PC.check_heading_override(gpu_ctx)
