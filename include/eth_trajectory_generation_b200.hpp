@@ -29,6 +29,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <limits>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -816,6 +817,33 @@ struct InitialState {  // the TrackerCommand fields findTrajectory reads (node.c
   double heading;
   double velocity[4], acceleration[4], jerk[4];  // x y z heading-rate
 };
+// The DynamicsConstraints fields findTrajectory / findTrajectoryFallback read (node.cpp:972-994, 1256-1280)
+struct DynamicsConstraints {
+  double horizontal_speed, vertical_ascending_speed, vertical_descending_speed;
+  double horizontal_acceleration, vertical_ascending_acceleration, vertical_descending_acceleration;
+  double horizontal_jerk, vertical_ascending_jerk, vertical_descending_jerk;
+  double heading_speed, heading_acceleration, heading_jerk;
+};
+// The mrs_msgs::Path fields callbackPath / callbackPathSrv / callbackGetPathSrv act on (node.cpp:1847-1902, 2061-2118, 2294-2351).
+// use_heading and fly_now only travel into the outgoing TrajectoryReference (node.cpp:1573-1575) and are carried along unchanged.
+struct PathRequest {
+  struct Point { double x, y, z, heading; };
+  std::vector<Point> points;
+  bool use_heading = true, fly_now = false, stop_at_waypoints = false, loop = false;
+  bool override_constraints = false;
+  double override_max_velocity_horizontal = 0, override_max_acceleration_horizontal = 0, override_max_jerk_horizontal = 0;
+  double override_max_velocity_vertical = 0, override_max_acceleration_vertical = 0, override_max_jerk_vertical = 0;
+  bool relax_heading = false;
+  double max_deviation_from_path = 0;   // <= 0: the configured max_deviation
+  bool dont_prepend_current_state = false;
+  double max_execution_time = 0;        // wall-clock budget of the node's retry loop; not a numeric input of the path
+};
+struct ResolvedRequest {
+  std::vector<Waypoint> waypoints;
+  tg_params params;
+  bool prepend_state;
+  bool constraints_overridden;  // false when the override was refused (node.cpp:1002-1026)
+};
 struct PathResult {
   tg_result info;
   std::vector<Waypoint> waypoints;    // after subdivision
@@ -862,7 +890,94 @@ class TrajectoryGeneratorBatch {
     return true;
   }
 
+  // What the path callback turns one message into before optimize() runs: the waypoint list (stop_at on every point, the first
+  // point appended again for a loop, node.cpp:1885-1906), the limits findTrajectory will use (node.cpp:972-1040) and the deviation
+  // bound (node.cpp:1875-1879).  `base` carries everything the message does not touch.  The caller applies checkNaN itself.
+  static ResolvedRequest resolveRequest(const PathRequest& req, const DynamicsConstraints& constraints, const tg_params& base, const InitialState* state) {
+    ResolvedRequest out;
+    out.params = base;
+    out.prepend_state = state != nullptr && !req.dont_prepend_current_state;  // node.cpp:508-510
+    out.constraints_overridden = false;
+    for (const PathRequest::Point& q : req.points) out.waypoints.push_back(Waypoint{q.x, q.y, q.z, q.heading, req.stop_at_waypoints});
+    if (req.loop && !out.waypoints.empty()) out.waypoints.push_back(out.waypoints.front());
+    double* L = out.params.limits;  // v_h, v_v, a_h, a_v, j_h, j_v, v_hdg, a_hdg, j_hdg
+    L[0] = constraints.horizontal_speed;
+    L[1] = std::min(constraints.vertical_ascending_speed, constraints.vertical_descending_speed);
+    L[2] = constraints.horizontal_acceleration;
+    L[3] = std::min(constraints.vertical_ascending_acceleration, constraints.vertical_descending_acceleration);
+    L[4] = constraints.horizontal_jerk;
+    L[5] = std::min(constraints.vertical_ascending_jerk, constraints.vertical_descending_jerk);
+    if (req.override_constraints) {
+      // the callbacks store override_max_jerk_HORIZONTAL into the vertical slot (node.cpp:1856, 2070, 2303); the message's own
+      // override_max_jerk_vertical is never read
+      const double o_jv = req.override_max_jerk_horizontal;
+      bool can_change = true;
+      if (out.prepend_state) {  // findTrajectory's initial_state is the prepended one (node.cpp:1002-1009)
+        const InitialState& s = *state;
+        can_change = (std::hypot(s.velocity[0], s.velocity[1]) < req.override_max_velocity_horizontal) &&
+                     (std::hypot(s.acceleration[0], s.acceleration[1]) < req.override_max_acceleration_horizontal) &&
+                     (std::hypot(s.jerk[0], s.jerk[1]) < req.override_max_jerk_horizontal) && (std::fabs(s.velocity[2]) < req.override_max_velocity_vertical) &&
+                     (std::fabs(s.acceleration[2]) < req.override_max_acceleration_vertical) && (std::fabs(s.jerk[2]) < o_jv);
+      }
+      if (can_change) {
+        L[0] = req.override_max_velocity_horizontal; L[2] = req.override_max_acceleration_horizontal; L[4] = req.override_max_jerk_horizontal;
+        L[1] = req.override_max_velocity_vertical;   L[3] = req.override_max_acceleration_vertical;   L[5] = o_jv;
+        out.constraints_overridden = true;
+      }
+    }
+    if (req.relax_heading) {
+      L[6] = L[7] = L[8] = (double)std::numeric_limits<float>::max();  // node.cpp:1030-1034
+    } else {
+      L[6] = constraints.heading_speed; L[7] = constraints.heading_acceleration; L[8] = constraints.heading_jerk;
+    }
+    if (req.max_deviation_from_path > 0) out.params.max_deviation = req.max_deviation_from_path;
+    return out;
+  }
+  // Many path messages in one go: requests whose resolved parameters agree share one batch call (one call when no message overrides
+  // anything).  states: empty, or the current tracker state per request (ignored where dont_prepend_current_state is set).
+  bool optimizeRequests(const std::vector<PathRequest>& requests, const DynamicsConstraints& constraints, const std::vector<InitialState>& states,
+                        std::vector<PathResult>* out, std::vector<ResolvedRequest>* resolved_out = nullptr) {
+    if (!out) return false;
+    const int R = (int)requests.size();
+    if (R < 1 || (!states.empty() && (int)states.size() != R)) return false;
+    std::vector<ResolvedRequest> resolved;
+    for (int i = 0; i < R; ++i) resolved.push_back(resolveRequest(requests[i], constraints, params, states.empty() ? nullptr : &states[i]));
+    out->assign(R, PathResult());
+    std::vector<char> done(R, 0);
+    const tg_params saved = params;
+    bool ok = true;
+    for (int i = 0; i < R && ok; ++i) {
+      if (done[i]) continue;
+      std::vector<int> members;
+      for (int j = i; j < R; ++j)
+        if (!done[j] && resolved[j].prepend_state == resolved[i].prepend_state && same_params(resolved[j].params, resolved[i].params)) members.push_back(j);
+      std::vector<std::vector<Waypoint>> paths;
+      std::vector<InitialState> group_states;
+      for (int j : members) {
+        done[j] = 1;
+        paths.push_back(resolved[j].waypoints);
+        if (resolved[i].prepend_state) group_states.push_back(states[j]);
+      }
+      std::vector<PathResult> part;
+      params = resolved[i].params;
+      ok = optimize(paths, group_states, &part);
+      params = saved;
+      if (ok)
+        for (size_t k = 0; k < members.size(); ++k) (*out)[members[k]] = std::move(part[k]);
+    }
+    if (resolved_out) *resolved_out = std::move(resolved);
+    return ok;
+  }
+
  private:
+  static bool same_params(const tg_params& a, const tg_params& b) {
+    bool same = a.derivative_to_optimize == b.derivative_to_optimize && a.max_evals == b.max_evals && a.f_rel == b.f_rel && a.x_rel == b.x_rel && a.dt == b.dt &&
+                a.check_deviation == b.check_deviation && a.max_deviation == b.max_deviation && a.max_deviation_iters == b.max_deviation_iters &&
+                a.first_segment_checked == b.first_segment_checked && a.max_len_factor == b.max_len_factor && a.min_len_factor == b.min_len_factor &&
+                a.run_time_alloc == b.run_time_alloc && a.override_heading_atan2 == b.override_heading_atan2;
+    for (int k = 0; k < 9; ++k) same = same && a.limits[k] == b.limits[k];
+    return same;
+  }
   // paths [p0, p1) on one device; results into (*out)[p0 .. p1)
   bool optimize_on(int device, const std::vector<std::vector<Waypoint>>& all_paths, const std::vector<InitialState>& all_states, int p0, int p1,
                    std::vector<PathResult>* out_all, bool resize_out, int slot = 0) {

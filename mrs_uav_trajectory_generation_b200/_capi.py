@@ -145,6 +145,12 @@ class Library:
                 setattr(p, k, v)
         return p
 
+    @staticmethod
+    def copy_params(p):
+        q = Params()
+        C.memmove(C.byref(q), C.byref(p), C.sizeof(Params))
+        return q
+
     def detmath(self, fn, x, y=0.0):
         return self.lib.tg_detmath_eval(int(fn), float(x), float(y))
 

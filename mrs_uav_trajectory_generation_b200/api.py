@@ -4,6 +4,8 @@ the C++ classes of include/eth_trajectory_generation/*.h), implemented on the C 
 The reference API is one-object-per-problem; every class here also accepts batches because the GPU path is batched
 (SURVEY.md H7).  The C++ shim with the same class names is include/eth_trajectory_generation_b200.hpp.
 """
+import math
+
 import numpy as np
 
 from ._capi import Context, Library, N, D, HALF
@@ -400,6 +402,78 @@ class BatchResult:
         return self.out["wp"][s0 + p: s1 + p + 1]
 
 
+class DynamicsConstraints:
+    """The DynamicsConstraints fields findTrajectory / findTrajectoryFallback read (node.cpp:972-994, 1256-1280)."""
+
+    FIELDS = ("horizontal_speed", "vertical_ascending_speed", "vertical_descending_speed", "horizontal_acceleration",
+              "vertical_ascending_acceleration", "vertical_descending_acceleration", "horizontal_jerk", "vertical_ascending_jerk",
+              "vertical_descending_jerk", "heading_speed", "heading_acceleration", "heading_jerk")
+
+    def __init__(self, **kw):
+        for f in self.FIELDS:
+            setattr(self, f, float(kw.pop(f)))
+        if kw:
+            raise TypeError(f"unknown constraint fields {sorted(kw)}")
+
+
+class PathRequest:
+    """The mrs_msgs::Path fields the path callbacks act on (node.cpp:1847-1902, 2061-2118, 2294-2351).  use_heading and fly_now only
+    travel into the outgoing TrajectoryReference (node.cpp:1573-1575); max_execution_time bounds the node's retry loop."""
+
+    def __init__(self, points, use_heading=True, fly_now=False, stop_at_waypoints=False, loop=False, override_constraints=False,
+                 override_max_velocity_horizontal=0.0, override_max_acceleration_horizontal=0.0, override_max_jerk_horizontal=0.0,
+                 override_max_velocity_vertical=0.0, override_max_acceleration_vertical=0.0, override_max_jerk_vertical=0.0,
+                 relax_heading=False, max_deviation_from_path=0.0, dont_prepend_current_state=False, max_execution_time=0.0):
+        self.points = np.asarray(points, dtype=np.float64).reshape(-1, 4)
+        self.use_heading, self.fly_now, self.stop_at_waypoints, self.loop = use_heading, fly_now, stop_at_waypoints, loop
+        self.override_constraints = override_constraints
+        self.override_max_velocity_horizontal = override_max_velocity_horizontal
+        self.override_max_acceleration_horizontal = override_max_acceleration_horizontal
+        self.override_max_jerk_horizontal = override_max_jerk_horizontal
+        self.override_max_velocity_vertical = override_max_velocity_vertical
+        self.override_max_acceleration_vertical = override_max_acceleration_vertical
+        self.override_max_jerk_vertical = override_max_jerk_vertical
+        self.relax_heading = relax_heading
+        self.max_deviation_from_path = max_deviation_from_path
+        self.dont_prepend_current_state = dont_prepend_current_state
+        self.max_execution_time = max_execution_time
+
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def resolve_request(req, constraints, base_params, initial_state=None):
+    """What a path callback turns one message into before optimize() runs.  Returns (waypoints [V,4], stop_at [V], limits[9],
+    max_deviation, prepend_state, overridden).  initial_state: a 14-vector (workloads.init14) or None."""
+    wp = req.points.copy()
+    if req.loop and len(wp):
+        wp = np.vstack([wp, wp[:1]])  # node.cpp:1904-1906
+    stop = np.full(len(wp), 1 if req.stop_at_waypoints else 0, np.uint8)
+    prepend = initial_state is not None and not req.dont_prepend_current_state  # node.cpp:508-510
+    c = constraints
+    L = [c.horizontal_speed, min(c.vertical_ascending_speed, c.vertical_descending_speed), c.horizontal_acceleration,
+         min(c.vertical_ascending_acceleration, c.vertical_descending_acceleration), c.horizontal_jerk,
+         min(c.vertical_ascending_jerk, c.vertical_descending_jerk), c.heading_speed, c.heading_acceleration, c.heading_jerk]
+    overridden = False
+    if req.override_constraints:
+        o_jv = req.override_max_jerk_horizontal  # the callbacks copy the HORIZONTAL jerk into the vertical slot (node.cpp:1856, 2070, 2303)
+        can_change = True
+        if prepend:  # node.cpp:1002-1009
+            s = np.asarray(initial_state, dtype=np.float64)
+            v, a, j = s[2:6], s[6:10], s[10:14]
+            can_change = (math.hypot(v[0], v[1]) < req.override_max_velocity_horizontal and math.hypot(a[0], a[1]) < req.override_max_acceleration_horizontal
+                          and math.hypot(j[0], j[1]) < req.override_max_jerk_horizontal and abs(v[2]) < req.override_max_velocity_vertical
+                          and abs(a[2]) < req.override_max_acceleration_vertical and abs(j[2]) < o_jv)
+        if can_change:
+            L[0], L[2], L[4] = req.override_max_velocity_horizontal, req.override_max_acceleration_horizontal, req.override_max_jerk_horizontal
+            L[1], L[3], L[5] = req.override_max_velocity_vertical, req.override_max_acceleration_vertical, o_jv
+            overridden = True
+    if req.relax_heading:
+        L[6] = L[7] = L[8] = FLT_MAX  # node.cpp:1030-1034
+    max_dev = req.max_deviation_from_path if req.max_deviation_from_path > 0 else base_params.max_deviation  # node.cpp:1875-1879
+    return wp, stop, L, max_dev, prepend, overridden
+
+
 class TrajectoryGenerator:
     """The numeric core of MrsTrajectoryGeneration::optimize() / findTrajectory() (node.cpp:620-851, 857-1209) for batches."""
 
@@ -418,6 +492,26 @@ class TrajectoryGenerator:
         init = None if initial_states is None else np.stack([np.asarray(i, dtype=np.float64) for i in initial_states])
         res, _ = self.ctx.optimize_batch(wp_off, wp, stop, init, params)
         return BatchResult(res, self.ctx.fetch_outputs(), self.ctx)
+
+    def optimize_requests(self, requests, constraints, initial_states=None, params=None):
+        """Many path messages at once: requests whose resolved limits / deviation bound / state use agree share one batch call.
+        Returns a list of (BatchResult, index inside it), one per request, plus the resolved tuples."""
+        base = params or self.params()
+        resolved = [resolve_request(r, constraints, base, None if initial_states is None else initial_states[i]) for i, r in enumerate(requests)]
+        groups = {}
+        for i, (wp, stop, L, max_dev, prepend, _) in enumerate(resolved):
+            groups.setdefault((tuple(L), max_dev, prepend), []).append(i)
+        placed = [None] * len(requests)
+        for (L, max_dev, prepend), members in groups.items():
+            p = self.ctx.L.copy_params(base)
+            for k in range(9):
+                p.limits[k] = L[k]
+            p.max_deviation = max_dev
+            br = self.optimize([resolved[i][0] for i in members], [resolved[i][1] for i in members],
+                               [initial_states[i] for i in members] if prepend else None, p)
+            for k, i in enumerate(members):
+                placed[i] = (br, k)
+        return placed, resolved
 
     def findTrajectory(self, waypoints, initial_state=None, params=None):
         """One findTrajectory pass without the deviation loop (node.cpp:857-1209)."""

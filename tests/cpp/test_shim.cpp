@@ -151,6 +151,38 @@ int main(int argc, char** argv) {
   const std::vector<int> ix = gen.getWaypointInTrajectoryIdxs(fb, pre);
   std::vector<double> ixd(ix.begin(), ix.end());
   dump(f, "idxs", ixd.data(), ixd.size());
+  // --- path messages with override fields (node.cpp:1847-1902): three requests, two parameter groups + one refused override
+  {
+    DynamicsConstraints dc{4.0, 2.5, 2.0, 3.0, 2.0, 1.5, 30.0, 25.0, 20.0, 1.0, 2.0, 10.0};
+    std::vector<PathRequest> reqs(3);
+    for (int q = 0; q < 3; ++q)
+      for (int i = 0; i < 5; ++i) reqs[q].points.push_back(PathRequest::Point{p1[i][0] + q, p1[i][1], p1[i][2], p1[i][3]});
+    reqs[0].loop = true;
+    reqs[0].relax_heading = true;
+    reqs[0].max_deviation_from_path = 0.4;
+    for (int q = 1; q < 3; ++q) {
+      reqs[q].override_constraints = true;
+      reqs[q].override_max_velocity_horizontal = 6.0; reqs[q].override_max_acceleration_horizontal = 3.5; reqs[q].override_max_jerk_horizontal = 35.0;
+      reqs[q].override_max_velocity_vertical = 3.0;   reqs[q].override_max_acceleration_vertical = 2.5;   reqs[q].override_max_jerk_vertical = 99.0;
+    }
+    reqs[1].stop_at_waypoints = true;
+    std::vector<InitialState> st(3);
+    for (int q = 0; q < 3; ++q) {
+      st[q] = InitialState{p1[0][3], {0.4, -0.3, 0.1, 0.0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+    }
+    st[2].velocity[0] = 7.0;  // faster than the override allows: refused, the tracker constraints stay
+    std::vector<PathResult> rr;
+    std::vector<ResolvedRequest> rs;
+    if (!gen.optimizeRequests(reqs, dc, st, &rr, &rs)) return 6;
+    for (int q = 0; q < 3; ++q) {
+      std::vector<double> m(rs[q].params.limits, rs[q].params.limits + 9);
+      m.push_back(rs[q].params.max_deviation); m.push_back(rs[q].prepend_state); m.push_back(rs[q].constraints_overridden); m.push_back((double)rs[q].waypoints.size());
+      m.push_back(rs[q].waypoints.back().stop_at);
+      m.push_back((double)rr[q].info.success); m.push_back((double)rr[q].info.rounds); m.push_back((double)rr[q].info.n_waypoints); m.push_back((double)rr[q].info.n_samples);
+      dump(f, "req_meta", m.data(), m.size());
+      dump(f, "req_samples", rr[q].samples_xyzh.data(), rr[q].samples_xyzh.size());
+    }
+  }
   std::fclose(f);
   std::printf("shim test wrote %s (%s)\n", argv[1], tg_version());
   return 0;

@@ -77,6 +77,28 @@ def _check(res):
         assert np.array_equal(res["batch_samples"][p].reshape(-1, 4), o["samples"])
 
 
+def _check_requests(res):
+    """optimizeRequests: the resolved limits follow node.cpp:972-1040 / 1847-1881 and each request's samples equal the oracle's at them."""
+    p1 = np.array([[10, 20, 3.5, 1.2], [-5, -5, 5, 1], [-5, 5, 5, 2], [5, -5, 5, 3], [5, 5, 5, 4]], float)
+    FM = float(np.finfo(np.float32).max)
+    base = [4.0, 2.0, 3.0, 1.5, 30.0, 20.0, 1.0, 2.0, 10.0]
+    over = [6.0, 3.0, 3.5, 2.5, 35.0, 35.0, 1.0, 2.0, 10.0]
+    want = [(base[:6] + [FM] * 3, 0.4, 1, 0, 6, 0), (over, 0.05, 1, 1, 5, 1), (base, 0.05, 1, 0, 5, 0)]
+    for q in range(3):
+        m = res["req_meta"][q]
+        L, dev, prepend, overridden, V, stop = want[q]
+        assert list(m[:9]) == L and m[9] == dev and (m[10], m[11], m[12], m[13]) == (prepend, overridden, V, stop)
+        wp = p1 + np.array([q, 0, 0, 0.0])
+        if q == 0:
+            wp = np.vstack([wp, wp[:1]])
+        vel = (7.0 if q == 2 else 0.4, -0.3, 0.1, 0.0)
+        ref = O.optimize_batch(np.array([0, len(wp)], np.int32), wp, stop_at=np.full(len(wp), stop, np.uint8), init=np.asarray([W.init14(1.2, vel=vel)]),
+                               params=O.default_params(limits=L, max_deviation=dev), cap_wp=400, cap_samples=4000)
+        r = ref["res"][0]
+        assert (int(m[14]), int(m[15]), int(m[16]), int(m[17])) == (r.success, r.rounds, r.n_waypoints, r.n_samples)
+        assert np.array_equal(res["req_samples"][q].reshape(-1, 4), ref["samples"][0, : r.n_samples])
+
+
 def _check_side_steps(res):
     raw = W.F1B_WAYPOINTS.copy()
     raw = np.insert(raw, 3, raw[2] + np.array([0.01, 0, 0, 0]), axis=0)
@@ -193,6 +215,7 @@ def test_cpp_shim_on_host_emulation(oracle, emu_lib, tmp_path):
     res = _run_shim(os.path.join(ROOT, "tests", "host_emu"), "tg_emu", tmp_path)
     _check(res)
     _check_side_steps(res)
+    _check_requests(res)
 
 
 @pytest.mark.gpu
@@ -200,3 +223,4 @@ def test_cpp_shim_on_gpu(oracle, gpu_ctx, tmp_path):
     res = _run_shim(os.path.join(ROOT, "mrs_uav_trajectory_generation_b200"), "tg_b200", tmp_path)
     _check(res)
     _check_side_steps(res)
+    _check_requests(res)
