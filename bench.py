@@ -255,6 +255,14 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_ms_max = float(tmax[0]), float(tmax[1])
+    # per-rank breakdown (what the scaling residual is made of): device ms, wall ms and median SM clock of every rank
+    mine = torch.tensor([dev_ms / args.steps, wall_ms / args.steps, clocks.get("sm_mhz") or 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    per_rank = [{"rank": i, "dev_ms": round(float(t[0]), 3), "wall_ms": round(float(t[1]), 3), "sm_mhz": float(t[2])} for i, t in enumerate(allr)]
     value = world * B * args.steps / (dev_ms_max * 1e-3)
 
     # ---- e2e: host (pinned) inputs, H2D inside the call, samples + per-problem results read back every step
@@ -373,6 +381,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "per_rank": per_rank,
             "stats": {"success_rate": float(res["success"].mean()), "safe_rate": float(res["safe"].mean()), "mean_rounds": float(res["rounds"].mean()),
                       "mean_final_segments": float(res["n_waypoints"].mean() - 1), "mean_samples": float(res["n_samples"].mean()),
                       "solves_per_step": int((c1["solves"] - c0["solves"]) / args.steps), "root_finds_reference_equivalent_per_step": int((c1["root_finds"] - c0["root_finds"]) / args.steps),

@@ -15,7 +15,6 @@ NVCC_FLAGS = [
     "-fmad=false",            # numeric contract: no FMA contraction (the reference build has none)
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
-] + [f"-DTG_JT_IMPL={os.environ.get('TG_JT_IMPL', '1')}"
 ]
 
 

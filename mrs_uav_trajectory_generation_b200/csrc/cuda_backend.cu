@@ -9,6 +9,7 @@
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -263,82 +264,6 @@ __global__ void __launch_bounds__(kThreadSolveCta) k_solve_thread(const D desc, 
   }
 }
 
-// The micro-op Jenkins-Traub machine (tg_poly_vm.cuh), warp-scheduled with lane refill.  Every lane works on one prepared
-// polynomial; each pass of the loop runs ONE micro-op, the one most lanes are waiting for; a lane whose polynomial is
-// finished stores its maximum and takes the next work item of the warp's chunk (chunks of kVmChunk items come from a
-// global counter).  Work arrays: shared memory, element i of thread t at smem[i * blockDim.x + t].
-constexpr int kVmChunk = 64;
-constexpr int kVmThreads = TG_WARR_DEVICE_STRIDE;
-template <class F>
-__global__ void __launch_bounds__(kVmThreads) k_vm(const F f, const int n_max, const int* __restrict__ n_dev, int* __restrict__ counter) {
-  extern __shared__ double smem[];
-  constexpr int Q = F::kQuantity;
-  constexpr int M = tg::VmQuantity<Q>::kMaxDegree;
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int n = n_dev ? min(n_max, *n_dev) : n_max;
-  double* scratch = smem + threadIdx.x;
-  const int stride = blockDim.x;
-  double svk[M + 1], tmp[M + 1];
-  tg::JtVm m;
-  m.p = tg::WArr{scratch, stride};
-  m.qp = tg::WArr{scratch + (size_t)(M + 1) * stride, stride};
-  m.K = tg::WArr{scratch + (size_t)2 * (M + 1) * stride, stride};
-  m.qk = tg::WArr{scratch + (size_t)3 * (M + 1) * stride, stride};
-  m.svk = svk;
-  m.tmp = tmp;
-  m.state = tg::JtVm::kDone;
-  tg::VmEmit<Q> emit{nullptr, 0.0, 0.0};
-  int item = -1;          // work item the lane is iterating on
-  size_t seg = 0;
-  int next = 0, end = 0;  // the warp's chunk of work items
-  bool exhausted = false;
-  for (;;) {
-    const bool idle = (m.state == tg::JtVm::kDone);
-    const unsigned idle_mask = __ballot_sync(full, idle);
-    if (idle_mask) {
-      if (idle && item >= 0) {
-        f.maxima[seg * 9 + Q] = emit.best;
-        item = -1;
-      }
-      if (!exhausted && next >= end) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(counter, kVmChunk);
-        base = __shfl_sync(full, base, 0);
-        next = base;
-        end = min(base + kVmChunk, n);
-        if (next >= n) exhausted = true;
-      }
-      if (!exhausted) {
-        const int rank = __popc(idle_mask & ((1u << lane) - 1u));
-        const int avail = end - next;
-        if (idle && rank < avail) {
-          item = next + rank;
-          const int degree = f.vb.degree[item];
-          seg = f.segment((size_t)item);
-          emit.coef = f.coef + seg * TG_D * TG_N;
-          emit.T = f.times[seg];
-          emit.best = f.maxima[seg * 9 + Q];
-          const double* poly = f.vb.polys + (size_t)item * tg::kVmPolyStride;
-          for (int i = 0; i <= degree; ++i) m.p[i] = poly[i];
-          m.begin(degree);
-        }
-        next += min(__popc(idle_mask), avail);
-      }
-    }
-    const int st = m.state;
-    const unsigned same = __match_any_sync(full, st);
-    const unsigned key = (st == tg::JtVm::kDone) ? 0u : (((unsigned)__popc(same) << 8) | (unsigned)(st + 1));
-    const unsigned win = __reduce_max_sync(full, key);
-    if (win == 0u) {
-      if (exhausted) break;
-      continue;
-    }
-    const int cur = (int)(win & 0xffu) - 1;
-    if (st == cur) m.step(cur, emit);
-  }
-}
-
 // FP64 pipe peak probes (the roofline denominator for this path; MEASURED_PEAKS.json has HBM and bf16 only).
 // mode 0: DFMA chains; mode 1: DMUL+DADD pairs as generated under -fmad=false (what the product kernels issue).
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, int mode) {
@@ -375,6 +300,9 @@ struct CudaBackend {
   cudaEvent_t ev_fork = nullptr, ev_side[kSideStreams] = {};
   void* scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
+  static constexpr size_t kStageBytes = 64 * 1024;
+  void* h_stage = nullptr;                       // pinned landing block of the small device-to-host reads
+  std::map<const void*, size_t> smem_allowed;   // dynamic shared memory already opted into, per kernel
   double* solve_slab = nullptr;  // U rows of the octet kernel
   size_t solve_slab_doubles = 0;
   double* gen_slab = nullptr;    // workspaces of the warp-per-instance kernel for very long paths
@@ -413,6 +341,7 @@ struct CudaBackend {
       if (const char* e = std::getenv("TG_OCT_WARPS")) oct_reg_warps = std::max(1, std::min(oct_reg_warps, std::atoi(e)));  // experiments
     }
     TG_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    TG_CUDA_CHECK(cudaHostAlloc(&h_stage, kStageBytes, cudaHostAllocDefault));
     TG_CUDA_CHECK(cudaEventCreate(&ev0));
     TG_CUDA_CHECK(cudaEventCreate(&ev1));
     TG_CUDA_CHECK(cudaEventCreate(&pev0));
@@ -426,6 +355,7 @@ struct CudaBackend {
   ~CudaBackend() {
     cudaSetDevice(device);
     if (scan_tmp) cudaFree(scan_tmp);
+    if (h_stage) cudaFreeHost(h_stage);
     if (solve_slab) cudaFree(solve_slab);
     if (thread_slab) cudaFree(thread_slab);
     if (gen_slab) cudaFree(gen_slab);
@@ -457,9 +387,23 @@ struct CudaBackend {
   void h2d(void* d, const void* s, size_t n) {
     if (n) TG_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream));
   }
+  // small read-backs (counters, list sizes) land in a pinned staging block: a pageable destination makes the driver stage and block
   void d2h(void* d, const void* s, size_t n) {
+    if (n && n <= kStageBytes && h_stage) {
+      TG_CUDA_CHECK(cudaMemcpyAsync(h_stage, s, n, cudaMemcpyDeviceToHost, stream));
+      TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+      std::memcpy(d, h_stage, n);
+      return;
+    }
     if (n) TG_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream));
     TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+  }
+  // dynamic shared memory opt-in, once per kernel and size (not on every launch)
+  void allow_smem(const void* fn, size_t smem) {
+    size_t& have = smem_allowed[fn];
+    if (smem <= have) return;
+    TG_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
   }
   void d2d(void* d, const void* s, size_t n) {
     if (n) TG_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream));
@@ -496,28 +440,11 @@ struct CudaBackend {
     const unsigned block = TG_WARR_DEVICE_STRIDE;
     const size_t grid = (n + block - 1) / block;
     const size_t smem = (size_t)F::kScratch * sizeof(double) * block;
-    TG_CUDA_CHECK(cudaFuncSetAttribute(k_for_each_scratch<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    allow_smem((const void*)k_for_each_scratch<F>, smem);
     prof_begin();
     k_for_each_scratch<F><<<(unsigned)grid, block, smem, stream>>>(f, n);
     TG_CUDA_CHECK(cudaGetLastError());
     prof_end(typeid(F).name(), n);
-  }
-  // micro-op Jenkins-Traub machine over n_max work items (or *n_dev of them); `counter` must be zero at launch
-  template <class F>
-  void vm_run(size_t n_max, const int* n_dev, int* counter, const F& f) {
-    if (n_max == 0) return;
-    const size_t smem = (size_t)F::kScratch * sizeof(double) * kVmThreads;
-    TG_CUDA_CHECK(cudaFuncSetAttribute(k_vm<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vm<F>, kVmThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    const size_t warps_needed = (n_max + kVmChunk - 1) / kVmChunk;
-    const size_t blocks_needed = (warps_needed + kVmThreads / 32 - 1) / (kVmThreads / 32);
-    const size_t grid = std::min(blocks_needed, (size_t)sm_count * per_sm);
-    prof_begin();
-    k_vm<F><<<(unsigned)grid, kVmThreads, smem, stream>>>(f, (int)n_max, n_dev, counter);
-    TG_CUDA_CHECK(cudaGetLastError());
-    prof_end(typeid(F).name(), n_max);
   }
   // fork / join of n side streams around independent launches (for_each_scratch_on); with per-kernel profiling on, everything
   // stays on the main stream so that the event pairs measure single kernels
@@ -540,7 +467,7 @@ struct CudaBackend {
     const unsigned block = TG_WARR_DEVICE_STRIDE;
     const size_t grid = (n + block - 1) / block;
     const size_t smem = (size_t)F::kScratch * sizeof(double) * block;
-    TG_CUDA_CHECK(cudaFuncSetAttribute(k_for_each_scratch<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    allow_smem((const void*)k_for_each_scratch<F>, smem);
     k_for_each_scratch<F><<<(unsigned)grid, block, smem, side[k % kSideStreams]>>>(f, n);
     TG_CUDA_CHECK(cudaGetLastError());
   }
@@ -553,13 +480,26 @@ struct CudaBackend {
     if (n_max == 0) return;
     if (!use_refill) {
       tg::ExtremaRawFn<Q> f{coef, times, maxima, work, n_dev};
-      if (profiling) return for_each_scratch(n_max, f);
-      return for_each_scratch_on(k, n_max, f);
+      if (!profiling) return for_each_scratch_on(k, n_max, f);
+      // profile step: the same launch with its executed operations counted (`items` of the "jt:" entries = FP64 operations)
+      if (!d_jt_flops) TG_CUDA_CHECK(cudaMalloc(&d_jt_flops, sizeof(unsigned long long)));
+      TG_CUDA_CHECK(cudaMemsetAsync(d_jt_flops, 0, sizeof(unsigned long long), stream));
+      const std::string name = std::string("jt:ExtremaRawFn<") + std::to_string(Q) + ">";
+      const size_t smem = (size_t)tg::ExtremaRawFn<Q>::kScratch * sizeof(double) * TG_WARR_DEVICE_STRIDE;
+      allow_smem((const void*)k_for_each_scratch<tg::ExtremaRawCountFn<Q>>, smem);
+      prof_begin();
+      k_for_each_scratch<tg::ExtremaRawCountFn<Q>><<<(unsigned)((n_max + 31) / 32), TG_WARR_DEVICE_STRIDE, smem, stream>>>(tg::ExtremaRawCountFn<Q>{f, d_jt_flops}, n_max);
+      TG_CUDA_CHECK(cudaGetLastError());
+      prof_end(name.c_str(), 0);
+      unsigned long long fl = 0;
+      TG_CUDA_CHECK(cudaMemcpy(&fl, d_jt_flops, sizeof(fl), cudaMemcpyDeviceToHost));
+      prof[name].items += (long long)fl;
+      return;
     }
     constexpr int M = tg::QuantityJob<Q>::M;
     const size_t smem = (size_t)4 * (M + 1) * sizeof(double) * 32;
     if (refill_ctas_per_sm[Q] == 0) {
-      TG_CUDA_CHECK(cudaFuncSetAttribute(k_extrema_refill<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      allow_smem((const void*)k_extrema_refill<Q>, smem);
       int a = 0;
       TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_extrema_refill<Q>, 32, smem));
       refill_ctas_per_sm[Q] = std::max(a, 1);
@@ -711,7 +651,7 @@ struct CudaBackend {
     if (oct_warps >= 1) {
       const size_t oct_smem = (size_t)4 * oct_ws_doubles * sizeof(double);
       prof_begin();
-      TG_CUDA_CHECK(cudaFuncSetAttribute(k_solve_oct<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oct_smem));
+      allow_smem((const void*)k_solve_oct<D>, oct_smem);
       const size_t blocks_needed = (n_inst + 3) / 4;
       // the U slab of all resident warps should stay in L2 (126 MB): fewer warps for very long paths
       const size_t per_cta = (size_t)4 * std::max(np_cap, 1) * tg::kOctURow;
@@ -730,7 +670,7 @@ struct CudaBackend {
     const size_t blocks_needed = (n_inst + kSolveWarps - 1) / kSolveWarps;
     prof_begin();
     if (smem <= smem_optin) {
-      TG_CUDA_CHECK(cudaFuncSetAttribute(k_solve<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      allow_smem((const void*)k_solve<D>, smem);
       int per_sm = 0;
       TG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve<D>, kSolveWarps * 32, smem));
       if (per_sm < 1) per_sm = 1;

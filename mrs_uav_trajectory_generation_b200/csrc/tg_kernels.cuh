@@ -15,7 +15,6 @@
 #include "tg_plis.cuh"
 #include "tg_node.cuh"
 #include "tg_poly.cuh"
-#include "tg_poly_vm.cuh"
 #include "tg_segment.cuh"
 #include "tg_solve.cuh"
 #include "tg_solve_octet.cuh"
@@ -544,44 +543,6 @@ struct ExtremaFn {  // one thread per segment for quantity Q (one launch per qua
     if (shift_count) TG_ATOMIC_ADD(shift_count, shifts);
   }
 };
-// ---- 6b. extrema through the micro-op machine (tg_poly_vm.cuh): a prepare kernel and a machine kernel per quantity ----
-// Work items are entries of an optional work list (segments whose polynomial changed since their maxima were computed).
-struct VmBuffers {
-  const int* work;   // [n] segment indices, or null for the identity
-  const int* n_dev;  // number of work items when it lives in device memory (work-list length), or null
-  double* polys;     // [n][kVmPolyStride]
-  int* degree;       // [n]
-};
-template <int Q>
-struct ExtremaPrepFn {  // one thread per work item
-  const double* coef;
-  const double* times;
-  double* maxima;
-  VmBuffers vb;
-  TG_HD void operator()(size_t item) const {
-    if (vb.n_dev && item >= (size_t)*vb.n_dev) return;
-    const size_t gs = vb.work ? (size_t)vb.work[item] : item;
-    double best;
-    vb.degree[item] = extrema_prepare<Q>(coef + gs * TG_D * TG_N, times[gs], vb.polys + item * kVmPolyStride, &best);
-    maxima[gs * 9 + Q] = best;
-  }
-};
-template <int Q>
-struct ExtremaVmFn {  // the machine: cuda_backend.cu runs it warp-scheduled with lane refill, the emulator item by item
-  const double* coef;
-  const double* times;
-  double* maxima;
-  VmBuffers vb;
-  static constexpr int kQuantity = Q;
-  static constexpr int kScratch = VmScratch<Q>::kShared;
-  TG_HD size_t segment(size_t item) const { return vb.work ? (size_t)vb.work[item] : item; }
-  TG_HD void single(size_t item, double* scratch, int stride) const {
-    const int degree = vb.degree[item];
-    if (degree < 1) return;
-    const size_t gs = segment(item);
-    maxima[gs * 9 + Q] = vm_run_single<Q>(coef + gs * TG_D * TG_N, times[gs], vb.polys + item * kVmPolyStride, degree, maxima[gs * 9 + Q], scratch, stride);
-  }
-};
 // work list of the segments whose maxima must be recomputed after a scaling pass: the problem is still being scaled
 // and the segment was stretched by a factor other than exactly 1 (a factor of 1 leaves every coefficient bit-identical,
 // eth/polynomial.cpp:218-224, so its zeros and maxima are unchanged)
@@ -985,6 +946,20 @@ struct ExtremaRawFn {  // one thread per work item (segment, or entry of a devic
     if (n_dev && item >= (size_t)*n_dev) return;
     const size_t gs = work ? (size_t)work[item] : item;
     maxima[gs * 9 + Q] = segment_max_impl<Q>(coef + gs * TG_D * TG_N, times[gs], scratch, stride, nullptr);
+  }
+};
+// The same launch with the operations of the executed stage-machine blocks added up (bench.py's per-kernel profile step only)
+template <int Q>
+struct ExtremaRawCountFn {
+  ExtremaRawFn<Q> f;
+  unsigned long long* flops;
+  static constexpr int kScratch = ExtremaRawFn<Q>::kScratch;
+  TG_HD void operator()(size_t item, double* scratch, int stride) const {
+    if (f.n_dev && item >= (size_t)*f.n_dev) return;
+    const size_t gs = f.work ? (size_t)f.work[item] : item;
+    int fl = 0;
+    f.maxima[gs * 9 + Q] = segment_max_impl<Q>(f.coef + gs * TG_D * TG_N, f.times[gs], scratch, stride, nullptr, &fl);
+    TG_ATOMIC_ADD(flops, (unsigned long long)fl);
   }
 };
 // getTrajectoryReference with override_heading_atan2 (node.cpp:1586-1599): the heading of sample i becomes the direction towards

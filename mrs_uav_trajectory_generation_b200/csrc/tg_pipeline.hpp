@@ -1124,14 +1124,8 @@ class Pipeline {
   };
   ExtremaScratch extrema_scratch(size_t n_max) {
     ExtremaScratch es;
-#if TG_JT_IMPL == 2
-    es.polys = scratch_.template alloc<double>(std::max<size_t>(n_max, 1) * kVmPolyStride);
-    es.degree = scratch_.template alloc<int>(std::max<size_t>(n_max, 1));
-    es.counters = scratch_.template alloc<int>(16);
-#else
     (void)n_max;
     es.counters = scratch_.template alloc<int>(16);  // work-item counters of the persistent extrema kernels
-#endif
     return es;
   }
   // Trajectory::scaleSegmentTimesToMeetConstraints over a batch (eth/trajectory.cpp:598-692): maxima of every segment,
@@ -1215,19 +1209,6 @@ class Pipeline {
   void extrema_lists(const double* coef, const double* times, double* maxima, size_t n_max, const int* lists, const int* counts,
                      const ExtremaScratch& es) {
     if (n_max == 0) return;
-#if TG_JT_IMPL == 2
-    be_.dev_memset(es.counters, 0, 16 * sizeof(int));
-    extrema_quantity<0>(coef, times, maxima, n_max, VmBuffers{lists + 0 * n_max, counts + 0, es.polys, es.degree}, es.counters);
-    extrema_quantity<1>(coef, times, maxima, n_max, VmBuffers{lists + 1 * n_max, counts + 1, es.polys, es.degree}, es.counters);
-    extrema_quantity<2>(coef, times, maxima, n_max, VmBuffers{lists + 2 * n_max, counts + 2, es.polys, es.degree}, es.counters);
-    extrema_quantity<3>(coef, times, maxima, n_max, VmBuffers{lists + 3 * n_max, counts + 3, es.polys, es.degree}, es.counters);
-    extrema_quantity<4>(coef, times, maxima, n_max, VmBuffers{lists + 4 * n_max, counts + 4, es.polys, es.degree}, es.counters);
-    extrema_quantity<5>(coef, times, maxima, n_max, VmBuffers{lists + 5 * n_max, counts + 5, es.polys, es.degree}, es.counters);
-    extrema_quantity<6>(coef, times, maxima, n_max, VmBuffers{lists + 6 * n_max, counts + 6, es.polys, es.degree}, es.counters);
-    extrema_quantity<7>(coef, times, maxima, n_max, VmBuffers{lists + 7 * n_max, counts + 7, es.polys, es.degree}, es.counters);
-    extrema_quantity<8>(coef, times, maxima, n_max, VmBuffers{lists + 8 * n_max, counts + 8, es.polys, es.degree}, es.counters);
-    launches(18);
-#else
     // the nine quantities are independent: one side stream each, so that the long tails of the root finder overlap
     be_.dev_memset(es.counters, 0, 16 * sizeof(int));
     be_.fork(9);
@@ -1242,7 +1223,6 @@ class Pipeline {
     be_.template extrema_refill<8>(8, n_max, coef, times, maxima, lists + 8 * n_max, counts + 8, es.counters + 8);
     be_.join(9);
     launches(9);
-#endif
   }
 
   // per-segment maxima of the nine quantities for n_max work items (all segments, or the entries of a device work
@@ -1250,25 +1230,6 @@ class Pipeline {
   void extrema_segments(const double* coef, const double* times, double* maxima, size_t n_max, const int* work, const int* n_dev,
                         const ExtremaScratch& es) {
     if (n_max == 0) return;
-#if TG_JT_IMPL == 2
-    VmBuffers vb;
-    vb.work = work;
-    vb.n_dev = n_dev;
-    vb.polys = es.polys;
-    vb.degree = es.degree;
-    int* counters = es.counters;
-    be_.dev_memset(counters, 0, 16 * sizeof(int));
-    extrema_quantity<0>(coef, times, maxima, n_max, vb, counters);
-    extrema_quantity<1>(coef, times, maxima, n_max, vb, counters);
-    extrema_quantity<2>(coef, times, maxima, n_max, vb, counters);
-    extrema_quantity<3>(coef, times, maxima, n_max, vb, counters);
-    extrema_quantity<4>(coef, times, maxima, n_max, vb, counters);
-    extrema_quantity<5>(coef, times, maxima, n_max, vb, counters);
-    extrema_quantity<6>(coef, times, maxima, n_max, vb, counters);
-    extrema_quantity<7>(coef, times, maxima, n_max, vb, counters);
-    extrema_quantity<8>(coef, times, maxima, n_max, vb, counters);
-    launches(18);
-#else
     (void)es;
     be_.for_each_scratch(n_max, ExtremaRawFn<0>{coef, times, maxima, work, n_dev});
     be_.for_each_scratch(n_max, ExtremaRawFn<1>{coef, times, maxima, work, n_dev});
@@ -1280,15 +1241,7 @@ class Pipeline {
     be_.for_each_scratch(n_max, ExtremaRawFn<7>{coef, times, maxima, work, n_dev});
     be_.for_each_scratch(n_max, ExtremaRawFn<8>{coef, times, maxima, work, n_dev});
     launches(9);
-#endif
   }
-#if TG_JT_IMPL == 2
-  template <int Q>
-  void extrema_quantity(const double* coef, const double* times, double* maxima, size_t n_max, const VmBuffers& vb, int* counters) {
-    be_.for_each(n_max, ExtremaPrepFn<Q>{coef, times, maxima, vb});
-    be_.vm_run(n_max, vb.n_dev, counters + Q, ExtremaVmFn<Q>{coef, times, maxima, vb});
-  }
-#endif
   int group_index(const Group* g) const {
     for (size_t i = 0; i < groups_.size(); ++i)
       if (groups_[i].get() == g) return (int)i;

@@ -75,7 +75,9 @@ struct WArr {
 #define TG_JT_SCHED 1  // 0: majority state first, 1: oldest first
 #endif
 // FP64 division, square root and the sign-preserving helpers are the bulk of the machine's code when inlined at ~40
-// sites (an IEEE division is ~25 SASS instructions); one out-of-line copy keeps the kernel inside the instruction cache.
+// sites (an IEEE division is ~25 SASS instructions); one out-of-line copy measured fastest.  Measured and rejected in round 2
+// (profiles/r02_extrema_jt.md): the compiler's fast division path written out inline with the reciprocal of a shared denominator
+// computed once (calcSC divides three numerators by the same d) -- 42.8 vs 39.7 ms for the horizontal-acceleration launches.
 #if defined(__CUDA_ARCH__) && !defined(TG_JT_INLINE_DIV)
 __device__ __noinline__ double tg_jt_div(double a, double b) { return a / b; }
 __device__ __noinline__ double tg_jt_sqrt(double a) { return tgdm::dsqrt(a); }
@@ -144,7 +146,7 @@ struct JtMachine {
     f = TG_DIV(d, c);
     g = e * uu;
     a3 = e * a + (g + TG_DIV(h, c)) * b;
-    a1 = -(a * TG_DIV(d, c)) + b;
+    a1 = -(a * f) + b;  // f is TG_DIV(d, c), the quotient the reference computes a second time here
     a7 = g * d + h * f + a;
     return 1;
   }
@@ -665,17 +667,13 @@ struct JtMachine {
 // doubles of strided scratch a thread needs for polynomials of degree <= M
 template <int M>
 struct JtScratch {
-#if defined(TG_JT_IMPL) && TG_JT_IMPL == 0
-  static constexpr int kShared = 1;
-#else
   static constexpr int kShared = 4 * (M + 1);  // p, qp, K, qk
-#endif
 };
 
 // findRootsJenkinsTraub (rpoly_ak1.cpp:76-120) on INCREASING coefficients ci[0..M]: trims trailing |c| < DBL_MIN,
 // reverses, strips the zeros at the origin (rpoly_ak1.cpp:174-180) and runs the machine.
 template <int M, class Sink>
-TG_HD void find_roots_jt(const double (&ci)[M + 1], double* scratch, int stride, Sink& sink, int* shifts) {
+TG_HD void find_roots_jt(const double (&ci)[M + 1], double* scratch, int stride, Sink& sink, int* shifts, int* flops = nullptr) {
   int last = -1;
 #pragma unroll
   for (int i = 0; i <= M; i++)
@@ -703,6 +701,7 @@ TG_HD void find_roots_jt(const double (&ci)[M + 1], double* scratch, int stride,
     if (dst >= 0 && dst <= degree) m.p[dst] = ci[i];
   }
   m.run(degree, sink, shifts);
+  if (flops) *flops += m.fl;  // operations of the executed stage-machine blocks (profiling launches only)
 #if defined(TG_JT_STATS)
   for (int i = 0; i < 10; ++i) tg_jt_stats[i] += m.npass[i];
 #endif
@@ -758,7 +757,7 @@ struct MaxSink {
 
 // horizontal pair (dims 0,1): zeros of sum_d conv(p_d^(k), p_d^(k+1))  (eth/segment.cpp:122-145)
 template <int DERIV>
-TG_HD double segment_max_horizontal(const double* __restrict__ coef, double T, double* scratch, int stride, int* shifts) {
+TG_HD double segment_max_horizontal(const double* __restrict__ coef, double T, double* scratch, int stride, int* shifts, int* flops = nullptr) {
   constexpr int n_d = TG_N - DERIV, n_dd = n_d - 1, len = n_d + n_dd - 1, M = len - 1;
   double acc[M + 1];
 #pragma unroll
@@ -785,13 +784,13 @@ TG_HD double segment_max_horizontal(const double* __restrict__ coef, double T, d
   if (0.0 > T) return sink.best;
   sink.consider(0.0);
   sink.consider(T);
-  find_roots_jt<M>(acc, scratch, stride, sink, shifts);
+  find_roots_jt<M>(acc, scratch, stride, sink, shifts, flops);
   return sink.best;
 }
 
 // single dimension DIM: zeros of p^(k+1) (eth/polynomial.cpp:69-85)
 template <int DERIV, int DIM>
-TG_HD double segment_max_single(const double* __restrict__ coef, double T, double* scratch, int stride, int* shifts) {
+TG_HD double segment_max_single(const double* __restrict__ coef, double T, double* scratch, int stride, int* shifts, int* flops = nullptr) {
   constexpr int M = TG_N - DERIV - 2;  // degree of the (k+1)-th derivative
   const double* c = coef + DIM * TG_N;
   double ddc[M + 1];
@@ -801,7 +800,7 @@ TG_HD double segment_max_single(const double* __restrict__ coef, double T, doubl
   if (0.0 > T) return sink.best;
   sink.consider(0.0);
   sink.consider(T);
-  find_roots_jt<M>(ddc, scratch, stride, sink, shifts);
+  find_roots_jt<M>(ddc, scratch, stride, sink, shifts, flops);
   return sink.best;
 }
 
@@ -874,33 +873,21 @@ TG_HD void segment_max_all_dims(const double* __restrict__ coef, double T, doubl
 // Quantity Q in 0..8 : (group, derivative) = (horizontal|vertical|heading, velocity|acceleration|jerk) in the order
 // the reference asks for them (eth/trajectory.cpp:616-622).  coef: [4][10] of one segment.
 template <int Q>
-TG_HD double segment_max_q(const double* __restrict__ coef, double T, double* scratch, int stride, int* shifts) {
-  if constexpr (Q == 0) return segment_max_horizontal<1>(coef, T, scratch, stride, shifts);
-  else if constexpr (Q == 1) return segment_max_horizontal<2>(coef, T, scratch, stride, shifts);
-  else if constexpr (Q == 2) return segment_max_horizontal<3>(coef, T, scratch, stride, shifts);
-  else if constexpr (Q == 3) return segment_max_single<1, 2>(coef, T, scratch, stride, shifts);
-  else if constexpr (Q == 4) return segment_max_single<2, 2>(coef, T, scratch, stride, shifts);
-  else if constexpr (Q == 5) return segment_max_single<3, 2>(coef, T, scratch, stride, shifts);
-  else if constexpr (Q == 6) return segment_max_single<1, 3>(coef, T, scratch, stride, shifts);
-  else if constexpr (Q == 7) return segment_max_single<2, 3>(coef, T, scratch, stride, shifts);
-  else return segment_max_single<3, 3>(coef, T, scratch, stride, shifts);
+TG_HD double segment_max_q(const double* __restrict__ coef, double T, double* scratch, int stride, int* shifts, int* flops = nullptr) {
+  if constexpr (Q == 0) return segment_max_horizontal<1>(coef, T, scratch, stride, shifts, flops);
+  else if constexpr (Q == 1) return segment_max_horizontal<2>(coef, T, scratch, stride, shifts, flops);
+  else if constexpr (Q == 2) return segment_max_horizontal<3>(coef, T, scratch, stride, shifts, flops);
+  else if constexpr (Q == 3) return segment_max_single<1, 2>(coef, T, scratch, stride, shifts, flops);
+  else if constexpr (Q == 4) return segment_max_single<2, 2>(coef, T, scratch, stride, shifts, flops);
+  else if constexpr (Q == 5) return segment_max_single<3, 2>(coef, T, scratch, stride, shifts, flops);
+  else if constexpr (Q == 6) return segment_max_single<1, 3>(coef, T, scratch, stride, shifts, flops);
+  else if constexpr (Q == 7) return segment_max_single<2, 3>(coef, T, scratch, stride, shifts, flops);
+  else return segment_max_single<3, 3>(coef, T, scratch, stride, shifts, flops);
 }
 
-}  // namespace tg
-#include "tg_poly_naive.cuh"
-namespace tg {
-#ifndef TG_JT_IMPL
-#define TG_JT_IMPL 1  // 0: direct transcription, work arrays in local memory; 1: warp-scheduled stage machine, shared-memory work arrays (fastest measured); 2: micro-op machine with lane refill (tg_poly_vm.cuh)
-#endif
 template <int Q>
-TG_HD double segment_max_impl(const double* __restrict__ coef, double T, double* scratch, int stride, int* shifts) {
-#if TG_JT_IMPL == 0
-  (void)scratch;
-  (void)stride;
-  return segment_max_magnitude_dyn(coef, T, Q, shifts);
-#else
-  return segment_max_q<Q>(coef, T, scratch, stride, shifts);
-#endif
+TG_HD double segment_max_impl(const double* __restrict__ coef, double T, double* scratch, int stride, int* shifts, int* flops = nullptr) {
+  return segment_max_q<Q>(coef, T, scratch, stride, shifts, flops);
 }
 
 // maximum polynomial degree met by quantity Q (scratch sizing)

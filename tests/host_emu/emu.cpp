@@ -150,15 +150,6 @@ struct EmuBackend {
       tg::solve_warp(I, 0);  // TG_PHASE runs the 32 lanes of every phase one after the other
     });
   }
-  // the micro-op Jenkins-Traub machine, item by item (the CUDA build schedules it warp-wide with lane refill)
-  template <class F>
-  void vm_run(size_t n_max, const int* n_dev, int*, const F& f) {
-    const size_t n = n_dev ? std::min<size_t>(n_max, (size_t)*n_dev) : n_max;
-    parallel(n, [&](size_t i) {
-      double scratch[F::kScratch];
-      f.single(i, scratch, 1);
-    });
-  }
   // out[0..count) = indices i < n with flags[i] != 0, ascending; *count = how many
   void select_flagged(const uint8_t* flags, int* out, int* count, int n) {
     int c = 0;

@@ -91,33 +91,6 @@ def test_jerk_and_snap_full_pipeline(emu_ctx, oracle):
         assert exact
 
 
-@pytest.mark.parametrize("variant", ["jt0", "jt2"])
-def test_jenkins_traub_other_variants(oracle, emu_lib, variant):
-    """The library builds with one of three formulations of the Jenkins-Traub iteration (TG_JT_IMPL): 1 = stage machine
-    (default, covered by every other test), 0 = direct per-thread transcription, 2 = micro-op machine with work lists.
-    All must stay bit-identical to the oracle, including on polynomials with zeros at the origin, vanishing leading
-    coefficients and repeated structure, and through the time-scaling loop and the full pipeline."""
-    import os
-
-    import oracle_lib as O
-    from mrs_uav_trajectory_generation_b200 import Context, Library
-
-    here = os.path.dirname(os.path.abspath(__file__))
-    ctx = Context(Library(os.path.join(here, "host_emu", f"libtg_emu_{variant}.so")), 0)
-    assert PC.check_extrema_and_scaling(ctx)
-    rng = np.random.default_rng(3)
-    S = 1500
-    coef = rng.standard_normal((S, 4, 10)) * np.exp(rng.uniform(-6, 3, (S, 1, 10)))
-    coef[::7, :, 1:3] = 0.0
-    coef[::11, :, 9] = 0.0
-    coef[::13, :, 8:] = 0.0
-    coef[5::17, 1] = coef[5::17, 0]
-    times = np.exp(rng.uniform(-2, 2, S))
-    assert np.array_equal(ctx.extrema(coef, times), O.segment_maxima(coef, times))
-    res, out, exact, worst = PC.check_random_flier(ctx, 16, first_index=40)
-    assert exact
-
-
 def test_extrema_random_polynomials(emu_ctx, oracle):
     import oracle_lib as O
 
