@@ -157,6 +157,14 @@ int tg_scale_times_batch(tg_ctx* ctx, int B, const int* seg_off, double* coef, d
 int tg_sweep_costs(tg_ctx* ctx, int V, const uint8_t* vmask, const double* vval, int r, long long K, const double* cand,
                    int cand_on_device, double* costs, long long* best_index, double* best_cost);
 
+/* tg_sweep_best (BASELINE config 5 on several GPUs of one box): the K candidates are cut into n_ctx contiguous shards,
+ *   shard g runs tg_sweep_costs on ctxs[g] (one context per device, one host thread per context), and the first minimum of the whole
+ *   list is returned: best_index (global), best_cost, best_times[S] (optional).  No device-to-device exchange: each shard returns
+ *   16 bytes.  Across processes (one rank per GPU) the same reduction is one all_gather of (cost, index, S times) per rank:
+ *   mrs_uav_trajectory_generation_b200/sharding.py sweep_best_distributed (NCCL). */
+int tg_sweep_best(tg_ctx* const* ctxs, int n_ctx, int V, const uint8_t* vmask, const double* vval, int r, long long K, const double* cand,
+                  long long* best_index, double* best_cost, double* best_times);
+
 /* tg_objective_batch = the objective functions of the time-allocation methods other than Mellinger's,
  *   PolynomialOptimizationNonLinear<N>::objectiveFunctionTime (nl_impl.h:567-614; methods 0 kSquaredTime, 1 kRichterTime) and
  *   objectiveFunctionTimeAndConstraints (nl_impl.h:651-722; methods 3, 4), with evaluateMaximumMagnitudeAsSoftConstraint

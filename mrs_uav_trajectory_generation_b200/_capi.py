@@ -422,6 +422,22 @@ class Context:
         self._check(self.L.lib.tg_scale_times_batch(self.h, B, _p(seg_off, _ip), _p(coef), _p(times), _p(lim), _p(passes, _ip), _p(within, _u8p)))
         return coef, times, passes, within.astype(bool)
 
+    @staticmethod
+    def sweep_best(contexts, vmask, vval, cand, r=2):
+        """tg_sweep_best: candidates sharded over several contexts (one per device) of this process -> (best_cost, best_index, best_times)."""
+        vmask = np.ascontiguousarray(vmask, dtype=np.uint8)
+        vval = np.ascontiguousarray(vval, dtype=np.float64)
+        cand = np.ascontiguousarray(cand, dtype=np.float64)
+        K, S = cand.shape
+        lib = contexts[0].L.lib
+        hs = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+        bi, bc = C.c_longlong(), C.c_double()
+        bt = np.empty(S)
+        lib.tg_sweep_best.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, _u8p, _dp, C.c_int, C.c_longlong, _dp, C.POINTER(C.c_longlong), C.POINTER(C.c_double), _dp]
+        lib.tg_sweep_best.restype = C.c_int
+        contexts[0]._check(lib.tg_sweep_best(hs, len(contexts), len(vmask), _p(vmask, _u8p), _p(vval), int(r), int(K), _p(cand), C.byref(bi), C.byref(bc), _p(bt)))
+        return bc.value, bi.value, bt
+
     def sweep_costs(self, vmask, vval, cand, r=2, want_costs=True, cand_on_device=False, K=None):
         vmask = np.ascontiguousarray(vmask, dtype=np.uint8)
         vval = np.ascontiguousarray(vval, dtype=np.float64)

@@ -4,12 +4,14 @@
 #ifndef TG_CAPI_IMPL_HPP_
 #define TG_CAPI_IMPL_HPP_
 
+#include <algorithm>
 #include <cstdlib>
 #include <exception>
 #include <memory>
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include "../../include/tg_b200.h"
 #include "tg_pipeline.hpp"
@@ -405,6 +407,52 @@ int tg_sweep_costs(tg_ctx* ctx, int V, const uint8_t* vmask, const double* vval,
     ctx->last_ms = ctx->be.timer_stop();
     return ok ? TG_OK : TG_ERR_INVALID;
   });
+}
+
+int tg_sweep_best(tg_ctx* const* ctxs, int n_ctx, int V, const uint8_t* vmask, const double* vval, int r, long long K, const double* cand,
+                  long long* best_index, double* best_cost, double* best_times) {
+  if (!ctxs || n_ctx < 1 || !ctxs[0]) return TG_ERR_INVALID;
+  for (int g = 0; g < n_ctx; ++g)
+    if (!ctxs[g]) return TG_ERR_INVALID;
+  if (V < 2 || !vmask || !vval || !cand || K < 1 || r < 2 || r > 4 || !best_index || !best_cost) {
+    ctxs[0]->err = "invalid argument";
+    return TG_ERR_INVALID;
+  }
+  const int S = V - 1;
+  const int G = (int)std::min<long long>(n_ctx, K);
+  std::vector<int> rc(G, TG_OK);
+  std::vector<long long> idx(G, 0);
+  std::vector<double> cost(G, 0.0);
+  // contiguous shards of the candidate list, one host thread per context (each context owns its device and stream); the only
+  // exchange is the (cost, index) pair each shard returns
+  auto shard = [&](int g) {
+    const long long k0 = K * g / G, k1 = K * (g + 1) / G;
+    long long bi = 0;
+    rc[g] = tg_sweep_costs(ctxs[g], V, vmask, vval, r, k1 - k0, cand + (size_t)k0 * S, 0, nullptr, &bi, &cost[g]);
+    idx[g] = k0 + bi;
+  };
+  if (G == 1) {
+    shard(0);
+  } else {
+    std::vector<std::thread> workers;
+    for (int g = 0; g < G; ++g) workers.emplace_back(shard, g);
+    for (std::thread& t : workers) t.join();
+  }
+  int best = -1;
+  for (int g = 0; g < G; ++g) {
+    if (rc[g] != TG_OK) {
+      if (g != 0) ctxs[0]->err = ctxs[g]->err;
+      return rc[g];
+    }
+    // first minimum of the whole list: shards are in index order, so a strictly smaller cost is required to move on;
+    // a NaN cost never wins against a number (a serial `cost < best` scan behaves the same)
+    if (best < 0 || cost[g] < cost[best] || (cost[best] != cost[best] && cost[g] == cost[g])) best = g;
+  }
+  *best_index = idx[best];
+  *best_cost = cost[best];
+  if (best_times)
+    for (int i = 0; i < S; ++i) best_times[i] = cand[(size_t)idx[best] * S + i];
+  return TG_OK;
 }
 
 double tg_detmath_eval(int fn, double x, double y) {

@@ -530,6 +530,33 @@ def check_sweep(ctx, K=300, seed=7):
     return np.array_equal(costs, ref)
 
 
+def check_sweep_best(ctx, K=1001, seed=8, n_ctx=3):
+    """tg_sweep_best: the candidates sharded over several contexts of one process (here: contexts on the same device); the first
+    minimum of the whole list, its cost bit for bit and its time vector must be what a serial scan of the oracle's costs gives, also
+    when the minimum is duplicated in a later shard."""
+    from mrs_uav_trajectory_generation_b200 import Context
+
+    rng = np.random.default_rng(seed)
+    path = W.random_flier_path(1)
+    V = len(path)
+    m = np.ones(V, np.uint8)
+    m[0] = m[-1] = 7
+    v = np.zeros((V, 5, 4))
+    v[:, 0, :] = path
+    T0, _ = O.estimate_times(path)
+    cand = np.maximum(0.01, T0[None, :] * np.exp(rng.uniform(-0.5, 0.5, (K, V - 1))))
+    ref = O.sweep_costs(m, v, 2, cand)
+    first = int(np.argmin(ref))
+    cand[(first + K // 2) % K] = cand[first]  # a tie in another shard: the lower index must win
+    ref = O.sweep_costs(m, v, 2, cand)
+    ctxs = [ctx] + [Context(ctx.L, ctx.device if hasattr(ctx, "device") else 0) for _ in range(n_ctx - 1)]
+    bc, bi, bt = Context.sweep_best(ctxs, m, v, cand, r=2)
+    assert bi == int(np.argmin(ref)) and bc == ref.min() and np.array_equal(bt, cand[bi])
+    bc1, bi1, _ = Context.sweep_best(ctxs[:1], m, v, cand, r=2)
+    assert (bc1, bi1) == (bc, bi)
+    return True
+
+
 def check_scaling_multi_pass(ctx, seed=17, B=24):
     """The global check's certificates (tg_bound.cuh) and their completion before a further pass: with the reference's
     tolerance a second pass practically never happens, so the tolerance is lowered (test hooks on both sides) to force up

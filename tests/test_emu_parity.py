@@ -115,3 +115,7 @@ def test_device_jenkins_traub_against_reference_vectors(emu_ctx, oracle):
 
 def test_override_heading_atan2(emu_ctx, oracle):
     assert PC.check_heading_override(emu_ctx)
+
+
+def test_sweep_best_over_several_contexts(emu_ctx, oracle):
+    assert PC.check_sweep_best(emu_ctx)

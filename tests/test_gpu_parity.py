@@ -211,3 +211,8 @@ def test_full_bench_batch_against_oracle(gpu_ctx, oracle):
 @pytest.mark.gpu
 def test_override_heading_atan2(gpu_ctx, oracle):
     assert PC.check_heading_override(gpu_ctx)
+
+
+@pytest.mark.gpu
+def test_sweep_best_over_several_contexts(gpu_ctx, oracle):
+    assert PC.check_sweep_best(gpu_ctx)
