@@ -111,6 +111,11 @@ class Pipeline {
   Counters counters;
   bool prune_extrema = true;            // tg_bound.cuh certificates (exact); off only for A/B measurements (TG_NO_PRUNE)
   bool use_thread_solve = std::getenv("TG_NO_THREAD_SOLVE") == nullptr;  // tg_solve_thread.cuh; off only for A/B measurements
+  // The thread-per-instance solve is a throughput kernel: one thread walks a whole system (50 us at S = 10, 1.3 ms at S = 264), so it
+  // only pays when the instances fill the machine (148 SMs x 256 threads).  Smaller launches -- single paths, the 200-waypoint path
+  // of BASELINE config 4 -- go to the lane-parallel kernels (8 lanes or a warp per system), whose results are bit-identical.
+  size_t thread_min_inst = std::getenv("TG_THREAD_MIN_INST") ? (size_t)std::atoll(std::getenv("TG_THREAD_MIN_INST")) : (size_t)16384;
+  bool thread_solve_for(size_t n_inst) const { return use_thread_solve && n_inst >= thread_min_inst; }
   double scale_tolerance = 1e-3;        // eth/trajectory.cpp:604; tg_test_set_scale_tolerance changes it (tests only)
   size_t seg_budget = (size_t)1 << 21;  // max segments per group (bounds scratch memory: ~5.6 kB per segment)
 
@@ -564,12 +569,13 @@ class Pipeline {
                           bool per_vertex = false) {
     // thread-per-instance kernel for every instance it can take (at most four free derivatives per vertex: the node's
     // recipe always); the older kernels below then only see the rest (stats[8] = how many problems that is)
-    const bool thread_all = use_thread_solve && stats[8] == 0;
-    if (use_thread_solve) {
+    const bool use_thr = thread_solve_for(n_inst);
+    const bool thread_all = use_thr && stats[8] == 0;
+    if (use_thr) {
       be_.solve_thread(0, n_inst, kThrB * (std::max(b.smax, 1) + 1), desc);
       launches(1);
     }
-    be_.skip_thread_eligible = use_thread_solve;
+    be_.skip_thread_eligible = use_thr;
     if (thread_all) {
       // nothing left for the lane-parallel kernels
     } else if (buckets && !buckets->empty()) {
@@ -659,7 +665,7 @@ class Pipeline {
     // segments still running) instead of scanning the whole batch for the few that are.
     const int eval_cap = (P.max_evals > 0 ? P.max_evals : 1000) + 64;
     int cnt[3] = {B, totV, totS};
-    const bool lists_ok = use_thread_solve && stats[8] == 0;  // the lane-parallel kernels scan (done problems drop out at once)
+    const bool lists_ok = thread_solve_for((size_t)totV) && stats[8] == 0;  // the lane-parallel kernels scan (done problems drop out at once)
     for (int e = 0; e < eval_cap; ++e) {
       const int buf = e & 1, nbuf = buf ^ 1;
       const bool sparse = lists_ok && e > 0 && (size_t)cnt[0] * 2 < (size_t)B;

@@ -33,16 +33,37 @@ def emu_lib():
     return Library(os.path.join(d, "libtg_emu.so"))
 
 
-@pytest.fixture(scope="session")
-def emu_ctx(emu_lib):
+def _context(library, solve_kernels):
+    """The library sends a solve launch to the thread-per-instance kernel when it has at least TG_THREAD_MIN_INST instances (default
+    16384) and to the lane-parallel kernels otherwise; the knob is read when a context is created.  Every parity test runs both ways:
+    "by-size" = the shipped dispatch (test batches are small: lane-parallel kernels, the large-batch tests reach the thread kernel),
+    "thread" = thread-per-instance kernel for everything it can take."""
     from mrs_uav_trajectory_generation_b200 import Context
 
-    return Context(emu_lib, 0)
+    old = os.environ.get("TG_THREAD_MIN_INST")
+    if solve_kernels == "thread":
+        os.environ["TG_THREAD_MIN_INST"] = "0"
+    else:
+        os.environ.pop("TG_THREAD_MIN_INST", None)
+    try:
+        ctx = Context(library, 0)
+        ctx.solve_kernels = solve_kernels
+        return ctx
+    finally:
+        if old is None:
+            os.environ.pop("TG_THREAD_MIN_INST", None)
+        else:
+            os.environ["TG_THREAD_MIN_INST"] = old
 
 
-@pytest.fixture(scope="session")
-def gpu_ctx():
+@pytest.fixture(scope="session", params=["by-size", "thread"])
+def emu_ctx(emu_lib, request):
+    return _context(emu_lib, request.param)
+
+
+@pytest.fixture(scope="session", params=["by-size", "thread"])
+def gpu_ctx(request):
     """The product: libtg_b200.so on cuda:0.  No fallback: the fixture fails if the library or the GPU is missing."""
-    from mrs_uav_trajectory_generation_b200 import Context, Library
+    from mrs_uav_trajectory_generation_b200 import Library
 
-    return Context(Library(), 0)
+    return _context(Library(), request.param)
