@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <typeinfo>
@@ -302,7 +304,6 @@ struct CudaBackend {
   size_t scan_tmp_bytes = 0;
   static constexpr size_t kStageBytes = 64 * 1024;
   void* h_stage = nullptr;                       // pinned landing block of the small device-to-host reads
-  std::map<const void*, size_t> smem_allowed;   // dynamic shared memory already opted into, per kernel
   double* solve_slab = nullptr;  // U rows of the octet kernel
   size_t solve_slab_doubles = 0;
   double* gen_slab = nullptr;    // workspaces of the warp-per-instance kernel for very long paths
@@ -399,8 +400,13 @@ struct CudaBackend {
     TG_CUDA_CHECK(cudaStreamSynchronize(stream));
   }
   // dynamic shared memory opt-in, once per kernel and size (not on every launch)
+  // (the attribute belongs to the function on a device, not to a context: the record is shared by all contexts of the process and
+  // only ever raised, otherwise a second context would lower what the first one relies on)
   void allow_smem(const void* fn, size_t smem) {
-    size_t& have = smem_allowed[fn];
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> allowed;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = allowed[std::make_pair(device, fn)];
     if (smem <= have) return;
     TG_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     have = smem;

@@ -8,19 +8,31 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load liboracle.so.
  *
- * PARITY STATUS: "parity unpinned" at the third-party boundaries.  The reference cannot be
- * compiled here (Eigen, NLopt, ROS, mrs_lib are absent) and its own tests hold no numeric
- * golden vectors.  What IS pinned:
- *   - the Jenkins-Traub root finder: oracle/_ref builds the reference's own
- *     src/eth_trajectory_generation/rpoly/rpoly_ak1.cpp and tests compare bit-for-bit;
- *   - the linear QP against an independent numpy/mpmath mirror (tests/test_oracle_linear.py);
- *   - identities from eth/test_utils.h (analytic cost vs numeric integral, analytic maximum
- *     >= sampled maximum), continuity and fixed-constraint reproduction;
- *   - the reference tests' geometric predicate (0.5 m / 0.2 rad waypoint pass-through,
- *     test/include/get_path_test.h:10-11,45-68).
- * Where Eigen's internal operation order or NLopt's LD_LBFGS iterate sequence cannot be known,
- * the order used here is written down in DESIGN.md ("numeric contract") and the CUDA library
- * follows the same contract.
+ * PARITY STATUS: pinned to the reference's own SOURCES, bit for bit, for everything the reference's repository contains; unpinned
+ * only where the reference calls third-party BINARIES that are not in its tree.
+ *   - oracle/Makefile target _ref/libref_eth.so compiles, unmodified and from where they lie under /root/reference,
+ *     src/eth_trajectory_generation/{motion_defines,polynomial,segment,trajectory,trajectory_sampling,vertex,timing,
+ *     rpoly/rpoly_ak1}.cpp and the templates impl/polynomial_optimization_{linear,nonlinear}_impl.h, against stand-in headers for
+ *     Eigen (oracle/ref_shim/Eigen: eager dense/sparse subset with the summation orders written down), NLopt (ref_shim/nlopt.hpp),
+ *     mrs_lib's cyclic angle helpers, geometry_msgs and boost::clamp.  tests/test_ref_eth.py compares this restatement (math mode
+ *     LIBM) with that build bit for bit: Q / A / A^-1 / R, solveLinear, coefficients and cost, both time estimates, per-segment
+ *     maxima through Jenkins-Traub, computeMaximumOfMagnitude, scaleSegmentTimesToMeetConstraints, sampleWholeTrajectory,
+ *     Trajectory::evaluate, the Mellinger time allocation end to end (optimize -> scaleSegmentTimesWithViolation) and the objective
+ *     functions of methods 0/1/3/4.  tests/golden/ref_eth.npz holds outputs of that build (generator: tests/golden/gen_golden.py)
+ *     so that the pin travels to machines without /root/reference.
+ *   - What the stand-ins stand in for is NOT in the reference tree and cannot be pinned: (i) Eigen::SparseQR<COLAMD> on Rpp
+ *     (lin_impl.h:362-369) -- the stand-in's solve is LU without pivoting on the full band (the contract the GPU follows); a
+ *     Householder-QR variant of the stand-in (_ref/libref_eth_qr.so) and a 50-digit mpmath solve bound the difference
+ *     (tests/test_numeric_floor.py: 5.9e-7 relative on coefficients at cond(Rpp) up to 4.9e15); (ii) NLopt 2.x LD_LBFGS
+ *     (nl_impl.h:178-191) -- oracle/plis.cpp restates Luksan's PLIS as NLopt ships it (plis.c / pssubs.c / mssubs.c) from the
+ *     published algorithm, call for call; NLopt's binary is absent, so its iterate sequence is restated, not compared;
+ *     (iii) glibc's libm -- math mode DET replaces it by include/tg_detmath.h (correctly rounded; glibc is not, so the two modes
+ *     differ by the floor measured in tests/test_numeric_floor.py: counts and verdicts identical, coefficients 1.4e-6 relative,
+ *     sample positions 1.1e-7 m).
+ *   - The node-level steps (mrs_trajectory_generation.cpp: vertex recipe, validation, subdivision, acceptance, sampling into the
+ *     tracker's format) need ROS to compile; they are restated in node.cpp with file:line citations and checked through the
+ *     reference tests' geometric predicate (0.5 m / 0.2 rad pass-through, test/include/get_path_test.h:10-11,45-68) and the
+ *     identities of eth/test_utils.h.
  *
  * Math modes: kMathLibm calls glibc (the pure restatement: pow, exp, log, atan2, sin, cos, cbrt
  * exactly where the reference calls them); kMathDet swaps those calls for include/tg_detmath.h so
