@@ -256,13 +256,16 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_ms_max = float(tmax[0]), float(tmax[1])
     # per-rank breakdown (what the scaling residual is made of): device ms, wall ms and median SM clock of every rank
-    mine = torch.tensor([dev_ms / args.steps, wall_ms / args.steps, clocks.get("sm_mhz") or 0.0], dtype=torch.float64, device="cuda")
+    mine = torch.tensor([dev_ms / args.steps, wall_ms / args.steps, clocks.get("sm_mhz") or 0.0, float(res["rounds"].max()), float(res["n_waypoints"].sum() - B)],
+                        dtype=torch.float64, device="cuda")
     if world > 1:
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
     else:
         allr = [mine]
-    per_rank = [{"rank": i, "dev_ms": round(float(t[0]), 3), "wall_ms": round(float(t[1]), 3), "sm_mhz": float(t[2])} for i, t in enumerate(allr)]
+    # every rank draws its own batch (first_index = rank): subdivision rounds and final segments say how much work it happened to get
+    per_rank = [{"rank": i, "dev_ms": round(float(t[0]), 3), "wall_ms": round(float(t[1]), 3), "sm_mhz": float(t[2]), "max_rounds": int(t[3]), "final_segments": int(t[4])}
+                for i, t in enumerate(allr)]
     value = world * B * args.steps / (dev_ms_max * 1e-3)
 
     # ---- e2e: host (pinned) inputs, H2D inside the call, samples + per-problem results read back every step
