@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--ref-paths", type=int, default=2048, help="paths per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="paths of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--same-batch", action="store_true", help="diagnostic: every rank gets rank 0's batch (separates batch-to-batch work variance from the box)")
     ap.add_argument("--no-profile", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -226,7 +227,7 @@ def main():
     ctx = tg.Context(tg.Library(os.environ.get("TG_LIB") or None), local_rank)
     P = ctx.L.default_params()
     B = args.batch
-    wp_off, wp = W.random_flier_paths_fast(B, first_index=rank)
+    wp_off, wp = W.random_flier_paths_fast(B, first_index=0 if args.same_batch else rank)
     d_wp = torch.from_numpy(wp).cuda()
     h_wp = torch.from_numpy(wp).pin_memory()
     wp_pinned = h_wp.numpy()
@@ -380,6 +381,7 @@ def main():
                 "l2": "per-step working set (segment records ~3.4 GB per evaluation) >> 126 MB L2, no explicit flush needed",
                 "timing": "CUDA events on the library's stream around each batch call (tg_last_device_ms), max over ranks",
                 "wall_ms_per_step": wall_ms_max / args.steps,
+                "batches": "every rank gets rank 0's batch (--same-batch diagnostic)" if args.same_batch else "rank r draws its own batch (generator stream r)",
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world},
             "gpu_launches": int(launches),
