@@ -65,7 +65,6 @@ TG_HD void store2(double* p, double a, double b) {
   t.y = b;
   *reinterpret_cast<Dbl2*>(p) = t;
 }
-
 // Parameters of one batch call; mirrors tg_params in include/tg_b200.h field by field.
 struct Params {
   int derivative_to_optimize;

@@ -43,6 +43,14 @@ TG_HD void thr_prefetch_H(const double* __restrict__ rec) {
   (void)rec;
 #endif
 }
+// a slab element read for the last time (back substitution): evict-first, so that it does not push out rows still waiting
+TG_HD double thr_last_use(const double* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
 TG_HD void thr_prefetch(const double* __restrict__ p) {
 #if defined(__CUDA_ARCH__)
   asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p));
@@ -217,9 +225,11 @@ TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t es
       double* row = slab + (size_t)((v * kThrB + q) * kThrRow) * estride;
       row[0] = rinv;
 #pragma unroll
-      for (int j = 1; j < kThrB; ++j) row[(size_t)j * estride] = (j > q) ? D[q][j] : 0.0;
+      for (int j = 1; j < kThrB; ++j)
+        if (j > q) row[(size_t)j * estride] = D[q][j];  // the back substitution never reads the entries left of the diagonal ...
+      if (has_next)                                     // ... nor the coupling block of the last vertex
 #pragma unroll
-      for (int j = 0; j < kThrB; ++j) row[(size_t)(4 + j) * estride] = has_next ? U[q][j] : 0.0;
+        for (int j = 0; j < kThrB; ++j) row[(size_t)(4 + j) * estride] = U[q][j];
 #pragma unroll
       for (int d = 0; d < TG_D; ++d) row[(size_t)(8 + d) * estride] = b[q][d];
     }
@@ -254,15 +264,15 @@ TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t es
     for (int qq = 0; qq < kThrB; ++qq) {
       const int q = kThrB - 1 - qq;
       const double* row = slab + (size_t)((v * kThrB + q) * kThrRow) * estride;
-      const double rinv = row[0];
+      const double rinv = thr_last_use(row);
       double s[TG_D];
 #pragma unroll
-      for (int d = 0; d < TG_D; ++d) s[d] = row[(size_t)(8 + d) * estride];
+      for (int d = 0; d < TG_D; ++d) s[d] = thr_last_use(row + (size_t)(8 + d) * estride);
       if (has_next) {
 #pragma unroll
         for (int jj = 0; jj < kThrB; ++jj) {
           const int j = kThrB - 1 - jj;
-          const double u = row[(size_t)(4 + j) * estride];
+          const double u = thr_last_use(row + (size_t)(4 + j) * estride);
 #pragma unroll
           for (int d = 0; d < TG_D; ++d) s[d] = s[d] - u * xn[j][d];
         }
@@ -271,7 +281,7 @@ TG_HD void solve_thread(const SolveInst& I, double* __restrict__ slab, size_t es
       for (int jj = 0; jj < kThrB; ++jj) {
         const int j = kThrB - 1 - jj;
         if (j > q) {
-          const double u = row[(size_t)j * estride];
+          const double u = thr_last_use(row + (size_t)j * estride);
 #pragma unroll
           for (int d = 0; d < TG_D; ++d) s[d] = s[d] - u * x[j][d];
         }
