@@ -6,16 +6,18 @@ nproc
 timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 400 gpurun_out/${tag}_bench.json
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-profile > gpurun_out/${tag}_ncu_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_solve_oct -s 3 -c 1 -o gpurun_out/${tag}_solve_r0 python tools/prof_driver.py 65536 > gpurun_out/${tag}_ncu_solve_r0.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_solve_oct -s 13 -c 1 -o gpurun_out/${tag}_solve_r1 python tools/prof_driver.py 65536 > gpurun_out/${tag}_ncu_solve_r1.log 2>&1
-for pat in "CoefCostFn" "SetupMellingerFn" "ExtremaRawFn<.int.1>" "ExtremaRawFn<.int.2>"; do
-  name=$(echo $pat | tr -cd 'A-Za-z0-9')
-  timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$pat" -s 2 -c 1 -o gpurun_out/${tag}_$name python tools/prof_driver.py 65536 > gpurun_out/${tag}_ncu_$name.log 2>&1
+# ncu --set full of one LOADED launch of each main kernel (launch-skip counts launches of that kernel only)
+for spec in "k_solve_thread:2:solve_thread" "SetupMellingerFn:2:SetupMellingerFn" "CoefCostGradFn:2:CoefCostGradFn" "ExtremaRawFn<.int.1>:0:ExtremaRawFn1" "PlisAdvanceFn:2:PlisAdvanceFn"; do
+  pat=${spec%%:*}; rest=${spec#*:}; skip=${rest%%:*}; name=${rest#*:}
+  timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$pat" -s $skip -c 1 -o gpurun_out/${tag}_$name python tools/prof_driver.py 65536 1 > gpurun_out/${tag}_ncu_$name.log 2>&1
 done
 # gpurun brings back at most 64 MiB: keep the CSV pages of every report, drop the reports themselves
 for rep in gpurun_out/${tag}_*.ncu-rep; do
   ncu -i $rep --page raw --csv > ${rep%.ncu-rep}_raw.csv 2>/dev/null
-  ncu -i $rep --page source --csv --print-source sass > ${rep%.ncu-rep}_sass.csv 2>/dev/null
+  ncu -i $rep --page source --csv --print-source cuda,sass > ${rep%.ncu-rep}_sass.csv 2>/dev/null
   rm -f $rep
 done
+(timeout 900 compute-sanitizer --tool memcheck python tools/prof_driver.py 256 2>&1 | tail -3) > gpurun_out/${tag}_memcheck.log
+(timeout 900 compute-sanitizer --tool racecheck python tools/prof_driver.py 64 2 2>&1 | tail -3) > gpurun_out/${tag}_racecheck.log
+cat gpurun_out/${tag}_memcheck.log gpurun_out/${tag}_racecheck.log
 ls -la gpurun_out | grep ${tag}
