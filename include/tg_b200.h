@@ -61,7 +61,8 @@ typedef struct tg_params {
 
 /* Per-problem outcome of tg_optimize_batch. */
 typedef struct tg_result {
-  int status;          /* 0 ok, 1 optimiser code rejected (node.cpp:1138-1149), 2 too long, 3 too short (node.cpp:1178-1199), 4 sampling failed */
+  int status;          /* 0 ok, 1 optimiser code rejected (node.cpp:1138-1149), 2 too long, 3 too short (node.cpp:1178-1199), 4 sampling failed, 5 fewer than two waypoints ("the path is empty", node.cpp:676-681),
+                          6 a non-finite waypoint or initial-state value (the callbacks' checkNaN, node.cpp:1896-1900; host inputs only) */
   int success;         /* optimize() produced a trajectory */
   int nlopt_code;      /* NLopt-style result code of the last findTrajectory (1,3,4,5 success codes, -1 generic failure) */
   int n_evals;         /* objective evaluations of the last findTrajectory (OptimizationInfo::n_iterations) */

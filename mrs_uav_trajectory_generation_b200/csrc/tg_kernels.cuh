@@ -43,7 +43,7 @@ static inline void tg_host_atomic_max(int* p, int v) {
 
 namespace tg {
 
-enum FindStatus { kFindOk = 0, kFindNloptRejected = 1, kFindTooLong = 2, kFindTooShort = 3, kFindSampleFail = 4 };
+enum FindStatus { kFindOk = 0, kFindNloptRejected = 1, kFindTooLong = 2, kFindTooShort = 3, kFindSampleFail = 4, kFindEmptyPath = 5, kFindNotFinite = 6 };
 
 // per-problem record of one findTrajectory pass (device side)
 struct ProbState {

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -287,9 +288,24 @@ class Pipeline {
       size_t segs = 0;
       for (int p = 0; p < B; ++p) {
         const int S = wp_off[p + 1] - wp_off[p] - 1;
+        // the path callbacks drop a message with a non-finite waypoint before optimize() runs (checkNaN, node.cpp:1896-1900); a batch
+        // cannot drop its caller's message, so the path is excluded and flagged (host inputs only: device-resident inputs are the
+        // caller's contract)
+        bool finite = true;
+        if (!on_device_inputs && S >= 1) {
+          for (int v = wp_off[p]; v < wp_off[p + 1] && finite; ++v)
+            for (int k = 0; k < 4; ++k) finite = finite && std::isfinite(wp[(size_t)v * 4 + k]);
+          if (finite && init14 && init14[(size_t)p * 14] != 0.0)
+            for (int k = 1; k < 14; ++k) finite = finite && std::isfinite(init14[(size_t)p * 14 + k]);
+        }
+        if (!finite) {
+          if (!members.empty()) { current.push_back(make_group_from_host(members, wp_off, wp, stop, init14, on_device_inputs)); members.clear(); segs = 0; }
+          results[p].status = kFindNotFinite;
+          continue;
+        }
         if (S < 1) {  // "the path is empty (after postprocessing)" (node.cpp:676-681)
           if (!members.empty()) { current.push_back(make_group_from_host(members, wp_off, wp, stop, init14, on_device_inputs)); members.clear(); segs = 0; }
-          results[p].status = kFindSampleFail;
+          results[p].status = kFindEmptyPath;
           continue;
         }
         if (!members.empty() && segs + S > seg_budget) {

@@ -295,7 +295,11 @@ int orc_optimize_path(int V, const double* wp, const uint8_t* stop_at, const dou
     w[i].stop_at = stop_at ? stop_at[i] != 0 : false;
   }
   const NodeParams P = to_node(prm);
-  const OptimizeResult O = optimize_path(w, to_init(init14), P);
+  OptimizeResult O = optimize_path(w, to_init(init14), P);
+  if (O.find.status == kFindEmptyPath || O.find.status == kFindNotFinite) {  // no trajectory: nothing is returned for the path
+    O.wp.clear();
+    O.find.nl.code = -1;
+  }
   std::memset(res, 0, sizeof(*res));
   res->status = O.find.status;
   res->success = O.success;

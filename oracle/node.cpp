@@ -266,7 +266,24 @@ std::vector<int> waypoint_trajectory_idxs(const std::vector<std::array<double, 4
 OptimizeResult optimize_path(const std::vector<Waypoint>& wp_in, const InitialState& init, const NodeParams& P) {
   OptimizeResult O;
   O.wp = wp_in;
-  if (O.wp.size() <= 1) return O;  // "the path is empty (after postprocessing)"
+  // checkNaN (node.cpp:1896-1900, isnan / isinf on the four coordinates): the callbacks drop such a message before optimize() runs
+  bool finite = true;
+  if (O.wp.size() > 1) {
+    for (const Waypoint& w : O.wp)
+      for (int k = 0; k < 4; ++k) finite = finite && std::isfinite(w.c[k]);
+    if (init.present) {
+      finite = finite && std::isfinite(init.heading);
+      for (int k = 0; k < 4; ++k) finite = finite && std::isfinite(init.vel[k]) && std::isfinite(init.acc[k]) && std::isfinite(init.jerk[k]);
+    }
+  }
+  if (!finite) {
+    O.find.status = kFindNotFinite;
+    return O;
+  }
+  if (O.wp.size() <= 1) {  // "the path is empty (after postprocessing)" (node.cpp:676-681)
+    O.find.status = kFindEmptyPath;
+    return O;
+  }
   O.find = find_trajectory(O.wp, init, P);
   auto tally = [&]() {
     O.total_solves += O.find.nl.n_solves;

@@ -218,7 +218,7 @@ struct NodeParams {
   bool run_time_alloc = true;  // false => config-2 style: linear solve at the Euclidean times + sampling
   bool override_heading_atan2 = false;  // getTrajectoryReference: heading = direction to the next sample (node.cpp:1586-1599)
 };
-enum FindStatus { kFindOk = 0, kFindNloptRejected = 1, kFindTooLong = 2, kFindTooShort = 3, kFindSampleFail = 4 };
+enum FindStatus { kFindOk = 0, kFindNloptRejected = 1, kFindTooLong = 2, kFindTooShort = 3, kFindSampleFail = 4, kFindEmptyPath = 5, kFindNotFinite = 6 };
 struct FindResult {
   int status = kFindOk;
   NlInfo nl;

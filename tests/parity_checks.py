@@ -360,7 +360,7 @@ def compare_optimize(ctx, wp_off, wp, stop_at=None, init=None, params_kw=None, c
         s0, s1 = out["seg_off"][p], out["seg_off"][p + 1]
         m0, m1 = out["smp_off"][p], out["smp_off"][p + 1]
         S = s1 - s0
-        assert S == g["n_waypoints"] - 1 and m1 - m0 == g["n_samples"]
+        assert S == max(g["n_waypoints"] - 1, 0) and m1 - m0 == g["n_samples"]  # a path without a trajectory (status 5, 6) owns nothing
         if not g["success"]:
             continue
         rt, rc = ref["times"][p, :S], ref["coeffs"][p, :S]
@@ -450,6 +450,34 @@ def check_heading_override(ctx, B=16):
         assert np.allclose(s[:-1, 3][far], np.arctan2(d[:, 1], d[:, 0])[far], rtol=0, atol=1e-12)
         reused += int((~far[1:]).sum())
     assert reused > 0
+    return True
+
+
+def check_degenerate_inputs(ctx):
+    """Inputs at the edge of the contract, every one against the oracle (verdicts, counts and outputs bit for bit):
+    the shortest path (two waypoints), a repeated waypoint (zero-length segment: rejected by the length filter), waypoints 1 km apart
+    (six subdivision rounds), 6 cm apart, a single waypoint ("the path is empty", node.cpp:676-681 -> status 5), a non-finite waypoint
+    (checkNaN, node.cpp:1896-1900 -> status 6), all mixed with ordinary paths in one ragged batch; an empty batch; a negative count."""
+    two = np.array([[0, 0, 1, 0], [3, 0, 1, 0.0]])
+    dup = np.array([[0, 0, 1, 0], [3, 0, 1, 0.0], [3, 0, 1, 0.0], [6, 1, 1, 0.5]])
+    far = np.array([[0, 0, 1, 0], [1000, 0, 1, 0.0], [1000, 500, 30, 3.0]])
+    near = np.array([[0, 0, 1, 0], [0.06, 0, 1, 0.0], [0.12, 0.01, 1, 0.0]])
+    one = np.array([[0, 0, 1, 0.0]])
+    nanp = np.array([[0, 0, 1, 0], [np.nan, 0, 1, 0.0], [3, 3, 1, 0]])
+    infp = np.array([[0, 0, 1, 0], [1, 0, 1, np.inf], [3, 3, 1, 0]])
+    usual = [W.random_flier_path(7000 + i, 4 + i) for i in range(3)]
+    paths = [two, usual[0], dup, one, far, nanp, usual[1], near, infp, usual[2]]
+    wp_off = np.concatenate([[0], np.cumsum([len(p) for p in paths])]).astype(np.int32)
+    res, out, exact, worst = compare_optimize(ctx, wp_off, np.concatenate(paths), cap_wp=400, cap_samples=20000)
+    assert exact
+    assert list(res["status"]) == [0, 0, 2, 5, 0, 6, 0, 0, 6, 0], list(res["status"])
+    assert list(res["success"]) == [1, 1, 0, 0, 1, 0, 1, 1, 0, 1]
+    assert res["rounds"][4] == 6 and res["n_samples"][3] == 0 and res["n_samples"][5] == 0
+    # an empty batch is not an error and returns nothing; a negative waypoint count flags that problem only
+    r0, t0 = ctx.optimize_batch(np.array([0], np.int32), np.zeros((0, 4)), None, None, ctx.L.default_params())
+    assert len(r0) == 0 and tuple(t0) == (0, 0) or len(r0) == 0
+    r1, _ = ctx.optimize_batch(np.array([0, 3, 2], np.int32), np.concatenate([usual[0][:3]]), None, None, ctx.L.default_params())
+    assert r1["success"][0] == 1 and r1["success"][1] == 0 and r1["status"][1] == 5
     return True
 
 

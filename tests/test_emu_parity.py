@@ -119,3 +119,7 @@ def test_override_heading_atan2(emu_ctx, oracle):
 
 def test_sweep_best_over_several_contexts(emu_ctx, oracle):
     assert PC.check_sweep_best(emu_ctx)
+
+
+def test_degenerate_inputs(emu_ctx, oracle):
+    assert PC.check_degenerate_inputs(emu_ctx)

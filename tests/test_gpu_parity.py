@@ -220,3 +220,8 @@ def test_override_heading_atan2(gpu_ctx, oracle):
 @pytest.mark.gpu
 def test_sweep_best_over_several_contexts(gpu_ctx, oracle):
     assert PC.check_sweep_best(gpu_ctx)
+
+
+@pytest.mark.gpu
+def test_degenerate_inputs(gpu_ctx, oracle):
+    assert PC.check_degenerate_inputs(gpu_ctx)
