@@ -986,7 +986,6 @@ class TrajectoryGeneratorBatch {
                                                    all_states.empty() ? all_states.begin() : all_states.begin() + p1);
     std::vector<PathResult> local;
     std::vector<PathResult>* out = &local;
-    const int device_ = device;
     const int B = (int)paths.size();
     std::vector<int> wp_off(B + 1, 0);
     for (int p = 0; p < B; ++p) wp_off[p + 1] = wp_off[p] + (int)paths[p].size();
@@ -1009,7 +1008,7 @@ class TrajectoryGeneratorBatch {
         for (int k = 0; k < 4; ++k) { d[2 + k] = initial_states[p].velocity[k]; d[6 + k] = initial_states[p].acceleration[k]; d[10 + k] = initial_states[p].jerk[k]; }
       }
     }
-    b200::Context& c = b200::Context::instance(device_, slot);
+    b200::Context& c = b200::Context::instance(device, slot);
     std::vector<tg_result> res(B);
     long long totals[2] = {0, 0};
     int rc = tg_optimize_batch(c.get(), B, wp_off.data(), wp.data(), stop.data(), init14.empty() ? nullptr : init14.data(), &params, 0, res.data(), totals);
