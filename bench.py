@@ -328,7 +328,11 @@ def main():
         setup_names = [k for k in prof if "Setup" in k]
         coef_names = [k for k in prof if "CoefCost" in k]
         coef_items = sum(prof[k][2] for k in coef_names) or 1
-        setup_items = sum(prof[k][2] for k in setup_names) or 1
+        # record setup runs in two stages: heads (Q, Dinv, X: 3(N-r)^2 + 525 = 717 flop per item) and rows of H (4 N^2 = 400 flop per item)
+        def setup_weight(k):
+            return 400.0 if "SetupMellingerFn<1>" in k else (717.0 if "SetupMellingerFn<0>" in k else 4717.0)
+
+        setup_items = sum(prof[k][2] * setup_weight(k) for k in setup_names) or 1
         rooflines = {}
         for name, (ms, launches, items) in prof.items():
             fl = kernel_flops(name, items)
@@ -337,7 +341,7 @@ def main():
             if fl is None and name in coef_names:
                 fl = (cb["flops_coef"] - ca["flops_coef"]) * items / coef_items
             if fl is None and name in setup_names:
-                fl = (cb["flops_setup"] - ca["flops_setup"]) * items / setup_items
+                fl = (cb["flops_setup"] - ca["flops_setup"]) * items * setup_weight(name) / setup_items
             if not fl or ms <= 0:
                 continue
             achieved = fl / (ms * 1e-3) / 1e12

@@ -33,9 +33,17 @@ namespace {
       throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e__));                     \
   } while (0)
 
-// one thread per work item
+// one thread per work item.  F::kMinBlocks (optional): resident 128-thread blocks per SM the register allocation must allow
+template <class F, class = void>
+struct MinBlocksOf {
+  static constexpr int value = 1;
+};
 template <class F>
-__global__ void __launch_bounds__(128) k_for_each(const F f, const size_t n) {
+struct MinBlocksOf<F, decltype((void)F::kMinBlocks)> {
+  static constexpr int value = F::kMinBlocks;
+};
+template <class F>
+__global__ void __launch_bounds__(128, MinBlocksOf<F>::value) k_for_each(const F f, const size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) f(i);
 }

@@ -174,10 +174,19 @@ struct SetupBaseFn {
   const double* T;
   TG_HD void operator()(size_t gs) const { setup_segment_record(T[gs], b.r, b.recs + gs * TG_REC_SIZE); }
 };
+// Two launches (tg_segment.cuh, "two stages"): SetupMellingerFn<0> over the records writes Q, Dinv, X; SetupMellingerFn<1>
+// over (record, row) writes the ten rows of H.
+template <int STAGE>  // 0: heads, one item per record; 1: rows of H, ten items per record
 struct SetupMellingerFn {
   BatchPtrs b;
   const int* seg_list;  // null: item = 3 * segment + which over all segments; else over the listed segments
-  TG_HD void operator()(size_t item0) const {
+  static constexpr int stage = STAGE;
+#ifndef TG_SETUP_ROW_BLOCKS
+#define TG_SETUP_ROW_BLOCKS 8
+#endif
+  static constexpr int kMinBlocks = STAGE ? TG_SETUP_ROW_BLOCKS : 2;  // the row stage is small: resident warps instead of registers
+  TG_HD void operator()(size_t item00) const {
+    const size_t item0 = stage ? item00 / TG_N : item00;
     const size_t k = item0 / 3;
     const int which = (int)(item0 - k * 3);
     const size_t gs = seg_list ? (size_t)seg_list[k] : k;
@@ -186,6 +195,11 @@ struct SetupMellingerFn {
     if (b.opt[p].done) return;
     const int S = b.seg_off[p + 1] - b.seg_off[p];
     if (S == 1 && which != 0) return;
+    double* rec = b.recs + item * TG_REC_SIZE;
+    if (stage) {
+      setup_record_hrow(b.r, rec, (int)(item00 - item0 * TG_N));
+      return;
+    }
     double T = b.xeval[gs];
     if (which == 1) {
       T = T + 0.1;
@@ -195,7 +209,7 @@ struct SetupMellingerFn {
       T = T - corr;
       T = dmax(kTimeLowerBound, T);
     }
-    setup_segment_record(T, b.r, b.recs + item * TG_REC_SIZE);
+    setup_record_head(T, b.r, rec);
   }
 };
 
@@ -378,10 +392,13 @@ struct CoefCostFn {
     run(inst, it);
   }
   TG_HD void run(size_t inst, int it) const {
-    const size_t item = inst * (size_t)per_inst + it;
     SolveInst I;
     if (!desc.instance(inst, I)) return;
     if (it >= I.S * TG_D) return;
+    run_instance(I, inst * (size_t)per_inst + it, it);
+  }
+  // item `it` = (segment, dimension) of the prepared instance I; `item` = its slot in `part`
+  TG_HD void run_instance(const SolveInst& I, size_t item, int it) const {
     const int s = it >> 2, d = it & 3;
     const double* rec = solve_rec(I, s);
     double nd[TG_N], c[TG_N];
@@ -427,6 +444,10 @@ struct CoefCostFn {
 // problem whose optimiser has finished costs one flag test per thread instead of a scan of all its items -- late
 // evaluations run for a few per cent of the problems.
 struct CoefCostGradFn {
+#ifndef TG_COEF_MIN_BLOCKS
+#define TG_COEF_MIN_BLOCKS 5
+#endif
+  static constexpr int kMinBlocks = TG_COEF_MIN_BLOCKS;  // 96 registers: measured 20.3 ms per step against 23.1 at 158
   CoefCostFn<SolveProblemDesc> f;
   int p0;  // first problem of this launch
   const int* prob_list;  // or the listed problems
@@ -436,9 +457,28 @@ struct CoefCostGradFn {
     if (b.opt[p].done) return;
     const int s0 = b.seg_off[p], S = b.seg_off[p + 1] - s0, v0 = s0 + p;
     const int per = S * TG_D, total = (S == 1) ? per : (S + 1) * per;  // variants 0..S
+    // the instance of (problem, variant) built from what this thread already holds: SolveProblemDesc::instance would walk
+    // prob_of_vtx -> seg_off -> opt again for every item, three dependent loads in front of 420 flop (ncu: 13.7 stall cycles per
+    // issued instruction on the long scoreboard)
+    SolveInst I;
+    I.S = S;
+    I.np = 0;  // np, hbw, fmax: not read by the coefficient stage
+    I.hbw = 0;
+    I.fmax = 0;
+    I.rec_stride = 3;
+    I.r = b.r;
+    I.vmask = b.vmask + v0;
+    I.vfree = b.vfree + v0 + p;
+    I.vval = b.vval + (size_t)v0 * TG_HALF * TG_D;
+    I.recs = b.recs + (size_t)s0 * 3 * TG_REC_SIZE;
+    I.dp_out = nullptr;
     for (int k = t; k < total; k += 128) {
       const int n = k / per, it = k - n * per;
-      f.run((size_t)(v0 + n), it);
+      I.variant = n;
+      I.coef_out = (n == 0) ? b.coef + (size_t)s0 * TG_D * TG_N : nullptr;
+      I.cost_out = b.costs + v0 + n;
+      I.x_out = b.xs + (size_t)(v0 + n) * (size_t)b.xstride;
+      f.run_instance(I, (size_t)(v0 + n) * (size_t)f.per_inst + it, it);
     }
   }
 };

@@ -690,17 +690,19 @@ class Pipeline {
       if (sparse) {
         const SolveProblemDesc desc{b, 1, nullptr, nullptr};
         const int per = 4 * b.smax;
-        be_.for_each((size_t)cnt[2] * 3, SetupMellingerFn{b, b.act_seg[buf]});
+        be_.for_each((size_t)cnt[2] * 3, SetupMellingerFn<0>{b, b.act_seg[buf]});
+        be_.for_each((size_t)cnt[2] * 3 * TG_N, SetupMellingerFn<1>{b, b.act_seg[buf]});
         be_.solve_thread(0, (size_t)cnt[1], kThrB * (std::max(b.smax, 1) + 1), SolveProblemListDesc{desc, b.act_vtx[buf]});
         be_.for_each((size_t)cnt[0] * 128, CoefCostGradFn{CoefCostFn<SolveProblemDesc>{desc, per, b.part, 0, per}, 0, b.act_prob[buf]});
         be_.for_each((size_t)cnt[1], CostSumFn<SolveProblemDesc>{desc, per, b.part, b.act_vtx[buf]});
         be_.for_each((size_t)cnt[0], PlisAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel, b.act_prob[buf], nbuf});
-        launches(5);
+        launches(6);
       } else {
-        be_.for_each((size_t)totS * 3, SetupMellingerFn{b, nullptr});
+        be_.for_each((size_t)totS * 3, SetupMellingerFn<0>{b, nullptr});
+        be_.for_each((size_t)totS * 3 * TG_N, SetupMellingerFn<1>{b, nullptr});
         solve_with_outputs((size_t)totV, stats, SolveProblemDesc{b, 1, nullptr, nullptr}, b, buckets, true);
         be_.for_each(B, PlisAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel, nullptr, nbuf});
-        launches(3);
+        launches(4);
       }
       counters.mellinger_launches += 1;
       int back[8];  // stats[7 .. 14]

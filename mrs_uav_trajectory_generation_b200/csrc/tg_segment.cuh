@@ -191,6 +191,137 @@ TG_HD void setup_segment_record_r(double T, double* __restrict__ rec) {
   }
 }
 
+// ---- the same record in two stages (Mellinger evaluations: 3 records per segment per evaluation, the bulk of the setup work) ----
+// One thread per record needs the whole of Q, Dinv and X in registers next to the 10x10 product: 254 registers, two blocks per SM,
+// and every thread walks 4.7 kflop of dependent arithmetic (ncu, round 2: issue slots 10 % busy, 29 % of the HBM roofline).
+// Stage 1 (setup_record_head, one thread per record) computes Q, Dinv and X -- the serial part, 28 % of the flops -- and writes the
+// first 86 doubles of the record.  Stage 2 (setup_record_hrow, one thread per (record, row a)) reads them back (the ten threads of a
+// record sit in one warp and read the same addresses: broadcast loads from L1) and computes row a of H = (A^-T Q) A^-1: 400 flop
+// and ~60 live values per thread, so eight blocks per SM, and the ten rows of a record leave the warp as 800 contiguous bytes.
+// Every element is computed by exactly the expression the one-thread version uses (same operands, same order), so the records are
+// bit-identical; Q is read back through its packed triangle, which is what the coefficient stage does too.
+template <int R>
+TG_HD void setup_record_head_r(double T, double* __restrict__ rec) {
+  constexpr int NQ = TG_N - R;
+  constexpr int EMAX = (TG_N - 1 - R) * 2 + 1;
+  double pw[EMAX];
+  tgdm::powers(T, EMAX, pw);
+  {
+    double qt[36];  // packed upper triangle (tg_qtri); entries beyond NQ stay zero
+#pragma unroll
+    for (int e = 0; e < 36; ++e) qt[e] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i)
+#pragma unroll
+      for (int j = i; j < NQ; ++j) {
+        const int e = i + j + 1;
+        qt[tg_qtri(i, j)] = bcoef(R, i + R) * bcoef(R, j + R) * pw[e - 1] * 2.0 / (double)e;
+      }
+#pragma unroll
+    for (int e = 0; e < 36; e += 2) store2(rec + TG_REC_Q + e, qt[e], qt[e + 1]);
+  }
+  double tp[TG_N];
+  tp[0] = 1.0;
+  tp[1] = T;
+#pragma unroll
+  for (int m = 2; m < TG_N; ++m) tp[m] = tp[m - 1] * T;
+  const bool tzero = dabs(T) < TG_DBL_EPSILON;
+  double Dm[5][5], Cm[5][5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      Dm[k][j] = tzero ? 0.0 : bcoef(k, 5 + j) * tp[5 + j - k];
+      Cm[k][j] = (j < k) ? 0.0 : ((j == k) ? bcoef(k, k) : (tzero ? 0.0 : bcoef(k, j) * tp[j - k]));
+    }
+  double Dinv[5][5];
+  inverse5(Dm, Dinv);
+  const double a_inv[5] = {1.0 / 1.0, 1.0 / 1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0};
+  double X[5][5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      double m = (-Dinv[i][0]) * Cm[0][j];
+#pragma unroll
+      for (int k = 1; k <= j; ++k) m = m + (-Dinv[i][k]) * Cm[k][j];
+      X[i][j] = m * a_inv[j];
+    }
+#pragma unroll
+  for (int e = 0; e < 50; e += 2) {
+    const double v0 = (e < 25) ? Dinv[e / 5][e % 5] : X[(e - 25) / 5][(e - 25) % 5];
+    const double v1 = (e + 1 < 25) ? Dinv[(e + 1) / 5][(e + 1) % 5] : X[(e + 1 - 25) / 5][(e + 1 - 25) % 5];
+    store2(rec + e, v0, v1);
+  }
+}
+// row a of H from the head of the record; AROW = a when known at compile time is not needed: a is uniform per thread and the
+// two cases (a < 5, a >= 5) are the two code paths of the one-thread version
+template <int R>
+TG_HD void setup_record_hrow_r(double* __restrict__ rec, int a) {
+  constexpr int NQ = TG_N - R;
+  const double a_inv[5] = {1.0 / 1.0, 1.0 / 1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0};
+  const double* __restrict__ Dinv = rec + TG_REC_DINV;  // [5][5]
+  const double* __restrict__ X = rec + TG_REC_X;        // [5][5]
+  const double* __restrict__ Qt = rec + TG_REC_Q;       // packed upper triangle, bitwise symmetric
+  // column a of A^-1 below the diagonal block: X[k-5][a] (a < 5) or Dinv[k-5][a-5] (a >= 5), k = 5..9
+  double col[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) col[k] = (a < 5) ? X[k * 5 + a] : Dinv[k * 5 + (a - 5)];
+  const double ainv_a = (a < 5) ? a_inv[a < 5 ? a : 0] : 0.0;
+  double W[NQ];
+#pragma unroll
+  for (int b = 0; b < NQ; ++b) {
+    // rows a < 5 start with the k = a term when a >= R (Q rows below R are zero); every row then adds k = 5..9 in ascending order.
+    // Written once for both halves: the first term present becomes the initial value, as in the one-thread version.
+    bool have = false;
+    double s = 0.0;
+    if (a < 5 && a >= R) {
+      s = ainv_a * Qt[tg_qsym(a - R, b)];
+      have = true;
+    }
+#pragma unroll
+    for (int k = 5; k < TG_N; ++k) {
+      const double t = col[k - 5] * Qt[tg_qsym(k - R, b)];
+      s = have ? s + t : t;
+      have = true;
+    }
+    W[b] = s;
+  }
+  double hrow[TG_N];
+#pragma unroll
+  for (int b = 0; b < TG_N; ++b) {
+    double s;
+    if (b < 5) {
+      bool have = false;
+      s = 0.0;
+      if (b >= R) { s = W[(b >= R) ? b - R : 0] * a_inv[b]; have = true; }
+#pragma unroll
+      for (int k = 5; k < TG_N; ++k) {
+        const double t = W[k - R] * X[(k - 5) * 5 + b];
+        s = have ? s + t : t;
+        have = true;
+      }
+    } else {
+      s = W[5 - R] * Dinv[0 * 5 + (b - 5)];
+#pragma unroll
+      for (int k = 6; k < TG_N; ++k) s = s + W[k - R] * Dinv[(k - 5) * 5 + (b - 5)];
+    }
+    hrow[b] = s;
+  }
+#pragma unroll
+  for (int b = 0; b < TG_N; b += 2) store2(rec + TG_REC_H + a * TG_N + b, hrow[b], hrow[b + 1]);
+}
+TG_HD void setup_record_head(double T, int r, double* __restrict__ rec) {
+  if (r == 2) setup_record_head_r<2>(T, rec);
+  else if (r == 3) setup_record_head_r<3>(T, rec);
+  else setup_record_head_r<4>(T, rec);
+}
+TG_HD void setup_record_hrow(int r, double* __restrict__ rec, int a) {
+  if (r == 2) setup_record_hrow_r<2>(rec, a);
+  else if (r == 3) setup_record_hrow_r<3>(rec, a);
+  else setup_record_hrow_r<4>(rec, a);
+}
+
 TG_HD_NOINLINE void setup_segment_record(double T, int r, double* __restrict__ rec) {
   if (r == 2) setup_segment_record_r<2>(T, rec);
   else if (r == 3) setup_segment_record_r<3>(T, rec);

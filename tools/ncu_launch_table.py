@@ -10,9 +10,18 @@ import sys
 
 txt = open(sys.argv[1]).read()
 rows = [x for x in csv.DictReader(io.StringIO(txt[txt.index('"ID"'):])) if x['Metric Name'] == 'gpu__time_duration.sum']
-nsteps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-n = len(rows) // nsteps
-step = rows[n:2 * n]
+# A batch call starts with VtxProblemFn over the whole batch (the launch with the largest grid of that kernel): the capture holds the
+# warm-up step, the timed step and the e2e step, followed by bench.py's single-path latency calls (tiny launches, not part of a step).
+def grid0(x):
+    return int(x['Grid Size'].strip('()').split(',')[0].strip())
+
+
+vtx = [i for i, x in enumerate(rows) if 'VtxProblemFn' in x['Kernel Name']]
+big = max(grid0(rows[i]) for i in vtx)
+starts = [i for i in vtx if grid0(rows[i]) == big]
+nsteps = len(starts)
+n = starts[1] - starts[0]
+step = rows[starts[1]:starts[1] + n]
 
 
 def short(name):
@@ -34,7 +43,7 @@ for x in step:
 tot = sum(v[1] for v in agg.values())
 with open(sys.argv[2] + '_summary.md', 'w') as f:
     f.write(f"ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`) of `python bench.py --steps 1 --warmup 1 --no-cpu --no-profile`: "
-            f"{len(rows)} launches in the capture = {nsteps} steps (warm-up, timed, e2e) of {n}; the table is the timed step. "
+            f"{len(rows)} launches in the capture = {nsteps} steps (warm-up, timed, e2e) of {n} launches each, then the single-path latency calls; the table is the timed step. "
             f"Durations under ncu are serialised and cold-cache: compare SHARES with bench.py's `kernel_profile`, not absolutes.\n\n")
     f.write(f"| kernel | launches | ms | share |\n|---|---:|---:|---:|\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
