@@ -192,6 +192,7 @@ struct SetupMellingerFn {
     const size_t gs = seg_list ? (size_t)seg_list[k] : k;
     const size_t item = gs * 3 + which;
     const int p = b.prob_of_seg[gs];
+    double T = stage ? 0.0 : b.xeval[gs];  // issued next to the problem lookup, not behind the two early-outs that depend on it
     if (b.opt[p].done) return;
     const int S = b.seg_off[p + 1] - b.seg_off[p];
     if (S == 1 && which != 0) return;
@@ -200,7 +201,6 @@ struct SetupMellingerFn {
       setup_record_hrow(b.r, rec, (int)(item00 - item0 * TG_N));
       return;
     }
-    double T = b.xeval[gs];
     if (which == 1) {
       T = T + 0.1;
       T = dmax(kTimeLowerBound, T);
