@@ -117,6 +117,9 @@ class Pipeline {
   // of BASELINE config 4 -- go to the lane-parallel kernels (8 lanes or a warp per system), whose results are bit-identical.
   size_t thread_min_inst = std::getenv("TG_THREAD_MIN_INST") ? (size_t)std::atoll(std::getenv("TG_THREAD_MIN_INST")) : (size_t)16384;
   bool thread_solve_for(size_t n_inst) const { return use_thread_solve && n_inst >= thread_min_inst; }
+  // the same rule inside the evaluation tail: a work list shorter than this goes to the lane-parallel kernels (measured: list
+  // launches 13.1 -> 9.5 ms per step; default = thread_min_inst)
+  size_t list_octet_below = std::getenv("TG_LIST_OCTET_BELOW") ? (size_t)std::atoll(std::getenv("TG_LIST_OCTET_BELOW")) : thread_min_inst;
   double scale_tolerance = 1e-3;        // eth/trajectory.cpp:604; tg_test_set_scale_tolerance changes it (tests only)
   size_t seg_budget = (size_t)1 << 21;  // max segments per group (bounds scratch memory: ~5.6 kB per segment)
 
@@ -692,7 +695,13 @@ class Pipeline {
         const int per = 4 * b.smax;
         be_.for_each((size_t)cnt[2] * 3, SetupMellingerFn<0>{b, b.act_seg[buf]});
         be_.for_each((size_t)cnt[2] * 3 * TG_N, SetupMellingerFn<1>{b, b.act_seg[buf]});
-        be_.solve_thread(0, (size_t)cnt[1], kThrB * (std::max(b.smax, 1) + 1), SolveProblemListDesc{desc, b.act_vtx[buf]});
+        if ((size_t)cnt[1] >= list_octet_below) {
+          be_.solve_thread(0, (size_t)cnt[1], kThrB * (std::max(b.smax, 1) + 1), SolveProblemListDesc{desc, b.act_vtx[buf]});
+        } else {
+          // a short list is latency bound: eight lanes per system finish sooner than one thread per system
+          be_.skip_thread_eligible = false;
+          be_.solve(0, (size_t)cnt[1], stats[0], stats[2], stats[3], stats[6] > 0, SolveProblemListDesc{desc, b.act_vtx[buf]});
+        }
         be_.for_each((size_t)cnt[0] * 128, CoefCostGradFn{CoefCostFn<SolveProblemDesc>{desc, per, b.part, 0, per}, 0, b.act_prob[buf]});
         be_.for_each((size_t)cnt[1], CostSumFn<SolveProblemDesc>{desc, per, b.part, b.act_vtx[buf]});
         be_.for_each((size_t)cnt[0], PlisAdvanceFn{b, P.max_evals, P.f_rel, P.x_rel, b.act_prob[buf], nbuf});

@@ -37,26 +37,31 @@ def _context(library, solve_kernels):
     """The library sends a solve launch to the thread-per-instance kernel when it has at least TG_THREAD_MIN_INST instances (default
     16384) and to the lane-parallel kernels otherwise; the knob is read when a context is created.  Every parity test runs both ways:
     "by-size" = the shipped dispatch (test batches are small: lane-parallel kernels, the large-batch tests reach the thread kernel),
-    "thread" = thread-per-instance kernel for everything it can take."""
+    "thread" = thread-per-instance kernel for everything it can take, dense launches and work lists alike,
+    "thread+octet-lists" (emulator only) = thread kernel for the dense launches, lane-parallel kernels over the work lists of the
+    evaluation tail (what a large batch does once a list is shorter than TG_LIST_OCTET_BELOW)."""
     from mrs_uav_trajectory_generation_b200 import Context
 
-    old = os.environ.get("TG_THREAD_MIN_INST")
-    if solve_kernels == "thread":
-        os.environ["TG_THREAD_MIN_INST"] = "0"
-    else:
-        os.environ.pop("TG_THREAD_MIN_INST", None)
+    knobs = {"by-size": {}, "thread": {"TG_THREAD_MIN_INST": "0", "TG_LIST_OCTET_BELOW": "0"},
+             "thread+octet-lists": {"TG_THREAD_MIN_INST": "0", "TG_LIST_OCTET_BELOW": "1000000000"}}[solve_kernels]
+    names = ("TG_THREAD_MIN_INST", "TG_LIST_OCTET_BELOW")
+    old = {k: os.environ.get(k) for k in names}
+    for k in names:
+        os.environ.pop(k, None)
+    os.environ.update(knobs)
     try:
         ctx = Context(library, 0)
         ctx.solve_kernels = solve_kernels
         return ctx
     finally:
-        if old is None:
-            os.environ.pop("TG_THREAD_MIN_INST", None)
-        else:
-            os.environ["TG_THREAD_MIN_INST"] = old
+        for k in names:
+            if old[k] is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = old[k]
 
 
-@pytest.fixture(scope="session", params=["by-size", "thread"])
+@pytest.fixture(scope="session", params=["by-size", "thread", "thread+octet-lists"])
 def emu_ctx(emu_lib, request):
     return _context(emu_lib, request.param)
 
