@@ -7,7 +7,7 @@ timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-profile > gpurun_out/${tag}_ncu_bench.log 2>&1
 # ncu --set full of one LOADED launch of each main kernel (launch-skip counts launches of that kernel only)
-for spec in "k_solve_thread:2:solve_thread" "SetupMellingerFn:2:SetupMellingerFn" "CoefCostGradFn:2:CoefCostGradFn" "ExtremaRawFn<.int.1>:0:ExtremaRawFn1" "PlisAdvanceFn:2:PlisAdvanceFn"; do
+for spec in "k_solve_thread:2:solve_thread" "SetupMellingerFn<.int.0>:2:SetupHead" "SetupMellingerFn<.int.1>:2:SetupRow" "CoefCostGradFn:2:CoefCostGradFn" "ExtremaRawFn<.int.1>:0:ExtremaRawFn1"; do
   pat=${spec%%:*}; rest=${spec#*:}; skip=${rest%%:*}; name=${rest#*:}
   timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$pat" -s $skip -c 1 -o gpurun_out/${tag}_$name python tools/prof_driver.py 65536 1 > gpurun_out/${tag}_ncu_$name.log 2>&1
 done
