@@ -121,7 +121,9 @@ class Pipeline {
   // launches 13.1 -> 9.5 ms per step; default = thread_min_inst)
   size_t list_octet_below = std::getenv("TG_LIST_OCTET_BELOW") ? (size_t)std::atoll(std::getenv("TG_LIST_OCTET_BELOW")) : thread_min_inst;
   double scale_tolerance = 1e-3;        // eth/trajectory.cpp:604; tg_test_set_scale_tolerance changes it (tests only)
-  size_t seg_budget = (size_t)1 << 21;  // max segments per group (bounds scratch memory: ~5.6 kB per segment)
+  // max segments per group (bounds scratch memory: ~5.6 kB per segment); TG_SEG_BUDGET lowers it so that tests can drive the
+  // several-groups path of a huge batch with a small one
+  size_t seg_budget = std::getenv("TG_SEG_BUDGET") ? (size_t)std::max(1LL, std::atoll(std::getenv("TG_SEG_BUDGET"))) : ((size_t)1 << 21);
 
   // ---------------------------------------------------------------------------------------------------------------
   // findTrajectory over one group.  Inputs (wp/stop/init14) already in device memory inside `g`.

@@ -453,6 +453,33 @@ def check_heading_override(ctx, B=16):
     return True
 
 
+def check_several_groups(library, device=0, B=40):
+    """A batch larger than the per-group segment budget is cut into several groups in round 0 and again in every subdivision round
+    (TG_SEG_BUDGET lowers the 2 M-segment budget so that 40 paths already need ~8 groups): results must not depend on the cut."""
+    import os
+
+    from mrs_uav_trajectory_generation_b200 import Context
+
+    old = os.environ.get("TG_SEG_BUDGET")
+    os.environ["TG_SEG_BUDGET"] = "48"
+    try:
+        ctx = Context(library, device)
+    finally:
+        if old is None:
+            os.environ.pop("TG_SEG_BUDGET", None)
+        else:
+            os.environ["TG_SEG_BUDGET"] = old
+    paths, stops = [], []
+    for p in range(B):
+        path = W.random_flier_path(8000 + p, 3 + p % 9)
+        paths.append(path)
+        stops.append(np.array([(p + i) % 7 == 0 for i in range(len(path))], np.uint8))
+    wp_off = np.concatenate([[0], np.cumsum([len(q) for q in paths])]).astype(np.int32)
+    res, out, exact, worst = compare_optimize(ctx, wp_off, np.concatenate(paths), stop_at=np.concatenate(stops))
+    assert exact and res["success"].all() and res["rounds"].max() >= 1
+    return True
+
+
 def check_degenerate_inputs(ctx):
     """Inputs at the edge of the contract, every one against the oracle (verdicts, counts and outputs bit for bit):
     the shortest path (two waypoints), a repeated waypoint (zero-length segment: rejected by the length filter), waypoints 1 km apart

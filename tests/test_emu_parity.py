@@ -123,3 +123,7 @@ def test_sweep_best_over_several_contexts(emu_ctx, oracle):
 
 def test_degenerate_inputs(emu_ctx, oracle):
     assert PC.check_degenerate_inputs(emu_ctx)
+
+
+def test_batch_cut_into_several_groups(emu_lib, oracle):
+    assert PC.check_several_groups(emu_lib)

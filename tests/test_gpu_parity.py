@@ -225,3 +225,10 @@ def test_sweep_best_over_several_contexts(gpu_ctx, oracle):
 @pytest.mark.gpu
 def test_degenerate_inputs(gpu_ctx, oracle):
     assert PC.check_degenerate_inputs(gpu_ctx)
+
+
+@pytest.mark.gpu
+def test_batch_cut_into_several_groups(gpu_ctx, oracle):
+    if gpu_ctx.solve_kernels == "thread":
+        pytest.skip("the cut does not depend on the solve dispatch")
+    assert PC.check_several_groups(gpu_ctx.L)
