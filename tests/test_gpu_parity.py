@@ -232,3 +232,30 @@ def test_batch_cut_into_several_groups(gpu_ctx, oracle):
     if gpu_ctx.solve_kernels == "thread":
         pytest.skip("the cut does not depend on the solve dispatch")
     assert PC.check_several_groups(gpu_ctx.L)
+
+
+@pytest.mark.gpu
+def test_quarter_million_paths_in_two_groups(gpu_ctx):
+    """262 144 paths = 2.6 M segments: more than the 2 M-segment budget of one group, so round 0 runs as two groups at real size
+    (≈ 28 GB of workspace).  The first and the last 2048 paths must equal the oracle bit for bit, and every path must succeed."""
+    if gpu_ctx.solve_kernels == "thread":
+        pytest.skip("one dispatch is enough at this size")
+    B, n = 262144, 2048
+    wp_off, wp = W.random_flier_paths_fast(B, first_index=21)
+    P = gpu_ctx.L.default_params()
+    res, totals = gpu_ctx.optimize_batch(wp_off, wp, None, None, P)
+    out = gpu_ctx.fetch_outputs()
+    assert res["success"].all() and int(totals[0]) > (1 << 21)
+    for c0 in (0, B - n):
+        off = wp_off[c0: c0 + n + 1] - wp_off[c0]
+        ref = O.optimize_batch(off, wp[wp_off[c0]: wp_off[c0 + n]], cap_wp=200, cap_samples=1600)
+        for q in range(n):
+            p = c0 + q
+            r, g = ref["res"][q], res[p]
+            for k in ("status", "success", "nlopt_code", "n_evals", "rounds", "safe", "n_waypoints", "n_samples", "n_scale_passes"):
+                assert getattr(r, k) == g[k], (p, k)
+            s0, s1 = out["seg_off"][p], out["seg_off"][p + 1]
+            m0, m1 = out["smp_off"][p], out["smp_off"][p + 1]
+            assert np.array_equal(out["times"][s0:s1], ref["times"][q, : s1 - s0]), p
+            assert np.array_equal(out["coef"][s0:s1], ref["coeffs"][q, : s1 - s0]), p
+            assert np.array_equal(out["samples"][m0:m1], ref["samples"][q, : m1 - m0]), p
