@@ -152,6 +152,21 @@ int tg_max_magnitude_batch(tg_ctx* ctx, int B, const int* seg_off, const double*
  *   coef/times; passes[B], within[B]. */
 int tg_scale_times_batch(tg_ctx* ctx, int B, const int* seg_off, double* coef, double* times, const double* limits9, int* passes,
                          uint8_t* within);
+/* General shape: the reference's classes are templates over the number of coefficients N (lin.h:46-55: even; Polynomial::kMaxN = 12,
+ *   eth/polynomial.h:45-48) and take the dimension D at run time (Vertex(D), PolynomialOptimization<N>(D), Trajectory::D()).
+ *   The three entry points below are tg_solve_linear_batch / tg_evaluate_batch / tg_sample_batch for N in {6, 8, 10, 12},
+ *   D in 1..4 and derivative_to_optimize r in 0 .. N/2-1 (lin_impl.h:61-70 accepts exactly that range):
+ *   vmask bit k (k < N/2) = derivative k fixed; vval[totV][N/2][D]; coef[totS][D][N]; out[n][D].
+ *   tg_sample_batch_nd needs D >= 3 as sampleTrajectoryInRange does (eth/trajectory_sampling.cpp:58-61); with D = 3 the heading
+ *   entries of samples / full are zero (the reference leaves the orientation at identity).
+ *   The tuned kernels serve N = 10, D = 4, r in 2..4 (the node's only shape, node.cpp:902, 1063) through the entry points above;
+ *   these go through the general-shape kernels of csrc/tg_generic.cuh for every shape, N = 10 included. */
+int tg_solve_linear_batch_nd(tg_ctx* ctx, int N, int D, int B, const int* vtx_off, const uint8_t* vmask, const double* vval, const double* times,
+                             int r, double* coef, double* cost);
+int tg_evaluate_batch_nd(tg_ctx* ctx, int N, int D, int S, const double* coef, const double* times, int n, const double* t, int derivative,
+                         double* out, uint8_t* ok);
+int tg_sample_batch_nd(tg_ctx* ctx, int N, int D, int B, const int* seg_off, const double* coef, const double* times, double dt, int* counts,
+                       double* samples, double* full);
 /* tg_sweep_costs (BASELINE config 5) = updateSegmentTimes + solveLinear + computeCost for K candidate time vectors
  *   of ONE problem (lin_impl.h:288-304, 340-373, 127-141).  cand[K][S] host (or device when cand_on_device).
  *   costs (optional) [K] host; best_index / best_cost = argmin (first minimum). */

@@ -120,6 +120,9 @@ class Library:
         L.tg_sample_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_double, _ip, _dp, _dp]
         L.tg_evaluate_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, _dp, _u8p]
         L.tg_extrema_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+        L.tg_solve_linear_batch_nd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, _u8p, _dp, _dp, C.c_int, _dp, _dp]
+        L.tg_evaluate_batch_nd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, _dp, _u8p]
+        L.tg_sample_batch_nd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, C.c_double, _ip, _dp, _dp]
         L.tg_objective_batch.argtypes = [C.c_void_p, C.c_int, _u8p, _dp, C.c_int, C.c_int, C.c_longlong, _dp, C.c_int, C.c_double, C.c_int, C.c_double,
                                          C.c_int, _ip, _dp, _dp, _dp, _dp]
         L.tg_max_magnitude_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_int, _dp, _dp, _ip]
@@ -377,6 +380,49 @@ class Context:
         ok = np.zeros(len(t), dtype=np.uint8)
         self._check(self.L.lib.tg_evaluate_batch(self.h, len(times), _p(coef), _p(times), len(t), _p(t), int(derivative), _p(out), _p(ok, _u8p)))
         return out, ok.astype(bool)
+
+    # ---- general shape: N in {6, 8, 10, 12} coefficients, D in 1..4 dimensions (tg_*_nd, csrc/tg_generic.cuh) ----
+    def solve_linear_batch_nd(self, n_coef, dim, vtx_off, vmask, vval, times, r=2):
+        """PolynomialOptimization<n_coef>(dim): vval [totV][n_coef/2][dim] -> coef [totS][dim][n_coef], cost [B]."""
+        vtx_off = np.ascontiguousarray(vtx_off, dtype=np.int32)
+        vmask = np.ascontiguousarray(vmask, dtype=np.uint8)
+        vval = np.ascontiguousarray(vval, dtype=np.float64)
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        B = len(vtx_off) - 1
+        totS = int(vtx_off[-1]) - B
+        assert vval.size == int(vtx_off[-1]) * (n_coef // 2) * dim and times.size == totS
+        coef = np.empty((totS, dim, n_coef))
+        cost = np.empty(B)
+        self._check(self.L.lib.tg_solve_linear_batch_nd(self.h, int(n_coef), int(dim), B, _p(vtx_off, _ip), _p(vmask, _u8p), _p(vval), _p(times),
+                                                        int(r), _p(coef), _p(cost)))
+        return coef, cost
+
+    def evaluate_nd(self, n_coef, dim, coef, times, t, derivative=0):
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        t = np.ascontiguousarray(np.atleast_1d(t), dtype=np.float64)
+        assert coef.size == len(times) * dim * n_coef
+        out = np.empty((len(t), dim))
+        ok = np.zeros(len(t), dtype=np.uint8)
+        self._check(self.L.lib.tg_evaluate_batch_nd(self.h, int(n_coef), int(dim), len(times), _p(coef), _p(times), len(t), _p(t), int(derivative),
+                                                    _p(out), _p(ok, _u8p)))
+        return out, ok.astype(bool)
+
+    def sample_batch_nd(self, n_coef, dim, seg_off, coef, times, dt, full=False):
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.int32)
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        B = len(seg_off) - 1
+        assert coef.size == int(seg_off[-1]) * dim * n_coef
+        counts = np.zeros(B, dtype=np.int32)
+        lib = self.L.lib
+        self._check(lib.tg_sample_batch_nd(self.h, int(n_coef), int(dim), B, _p(seg_off, _ip), _p(coef), _p(times), float(dt), _p(counts, _ip), None, None))
+        tot = int(counts.sum())
+        samples = np.empty((tot, 4))
+        fullv = np.empty((tot, 19)) if full else None
+        self._check(lib.tg_sample_batch_nd(self.h, int(n_coef), int(dim), B, _p(seg_off, _ip), _p(coef), _p(times), float(dt), _p(counts, _ip),
+                                           _p(samples), _p(fullv)))
+        return counts, samples, fullv
 
     def extrema(self, coef, times):
         coef = np.ascontiguousarray(coef, dtype=np.float64)

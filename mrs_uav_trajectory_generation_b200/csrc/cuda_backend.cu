@@ -48,6 +48,13 @@ __global__ void __launch_bounds__(128, MinBlocksOf<F>::value) k_for_each(const F
   if (i < n) f(i);
 }
 
+// one warp per work item (four warps per CTA); f(item, lane) separates its phases with __syncwarp() (TG_PHASE)
+template <class F>
+__global__ void __launch_bounds__(128) k_for_each_warp(const F f, const size_t n) {
+  const size_t w = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (w < n) f(w, (int)(threadIdx.x & 31));  // warp-uniform
+}
+
 // one thread per work item with F::kScratch doubles of per-thread scratch in dynamic shared memory, element i of thread
 // t at smem[i * blockDim.x + t] (bank-conflict free; used by the Jenkins-Traub work arrays)
 static_assert(TG_WARR_DEVICE_STRIDE == 32, "strided scratch kernels run one warp per block");
@@ -445,6 +452,15 @@ struct CudaBackend {
     const size_t grid = (n + block - 1) / block;
     prof_begin();
     k_for_each<F><<<(unsigned)grid, block, 0, stream>>>(f, n);
+    TG_CUDA_CHECK(cudaGetLastError());
+    prof_end(typeid(F).name(), n);
+  }
+  template <class F>
+  void for_each_warp(size_t n, const F& f) {
+    if (n == 0) return;
+    const size_t grid = (n + 3) / 4;
+    prof_begin();
+    k_for_each_warp<F><<<(unsigned)grid, 128, 0, stream>>>(f, n);
     TG_CUDA_CHECK(cudaGetLastError());
     prof_end(typeid(F).name(), n);
   }

@@ -11,6 +11,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/tg_b200.h"
@@ -253,6 +254,85 @@ int tg_solve_linear_batch(tg_ctx* ctx, int B, const int* vtx_off, const uint8_t*
     const bool ok = ctx->pipe.linear_batch(B, vtx_off, vmask, vval, times, r, coef, cost);
     ctx->last_ms = ctx->be.timer_stop();
     if (!ok) { ctx->err = "every problem needs at least two vertices"; return TG_ERR_INVALID; }
+    return TG_OK;
+  });
+}
+
+// ---- general shape (N in {6, 8, 10, 12}, D in 1..4): zero-padded to the 4 dimensions the kernels carry ------------------------
+extern "C++" {
+namespace {
+inline bool tg_shape_ok(int N, int D) { return (N == 6 || N == 8 || N == 10 || N == 12) && D >= 1 && D <= TG_D; }
+// [rows][D] -> [rows][4], missing dimensions zero
+inline std::vector<double> tg_pad_dims(const double* src, size_t rows, int D) {
+  std::vector<double> out(rows * TG_D, 0.0);
+  for (size_t i = 0; i < rows; ++i)
+    for (int d = 0; d < D; ++d) out[i * TG_D + d] = src[i * D + d];
+  return out;
+}
+// [S][D][N] -> [S][4][N]
+inline std::vector<double> tg_pad_coef(const double* coef, size_t S, int N, int D) {
+  std::vector<double> out(S * TG_D * N, 0.0);
+  for (size_t s = 0; s < S; ++s)
+    for (int d = 0; d < D; ++d) std::memcpy(&out[(s * TG_D + d) * N], coef + (s * D + d) * N, sizeof(double) * N);
+  return out;
+}
+template <class F>
+inline void tg_dispatch_n(int N, F&& f) {
+  switch (N) {
+    case 6: f(std::integral_constant<int, 6>()); break;
+    case 8: f(std::integral_constant<int, 8>()); break;
+    case 10: f(std::integral_constant<int, 10>()); break;
+    default: f(std::integral_constant<int, 12>()); break;
+  }
+}
+}  // namespace
+}  // extern "C++"
+
+int tg_solve_linear_batch_nd(tg_ctx* ctx, int N, int D, int B, const int* vtx_off, const uint8_t* vmask, const double* vval, const double* times,
+                             int r, double* coef, double* cost) {
+  return tg_guard(ctx, [&]() -> int {
+    if (!tg_shape_ok(N, D)) { ctx->err = "supported shapes: N in {6, 8, 10, 12}, D in 1..4"; return TG_ERR_INVALID; }
+    if (B < 1 || !vtx_off || !vmask || !vval || !times || r < 0 || r > N / 2 - 1) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    const size_t totV = (size_t)vtx_off[B], totS = totV - (size_t)B;
+    const std::vector<double> vv = tg_pad_dims(vval, totV * (size_t)(N / 2), D);
+    std::vector<double> c4(coef ? totS * TG_D * N : 0);
+    bool ok = false;
+    ctx->be.timer_start();
+    tg_dispatch_n(N, [&](auto n) { ok = ctx->pipe.template linear_batch_n<decltype(n)::value>(B, vtx_off, vmask, vv.data(), times, r, coef ? c4.data() : nullptr, cost); });
+    ctx->last_ms = ctx->be.timer_stop();
+    if (!ok) { ctx->err = "every problem needs at least two vertices"; return TG_ERR_INVALID; }
+    if (coef)
+      for (size_t s = 0; s < totS; ++s)
+        for (int d = 0; d < D; ++d) std::memcpy(coef + (s * D + d) * N, &c4[(s * TG_D + d) * N], sizeof(double) * N);
+    return TG_OK;
+  });
+}
+
+int tg_evaluate_batch_nd(tg_ctx* ctx, int N, int D, int S, const double* coef, const double* times, int n, const double* t, int derivative,
+                         double* out, uint8_t* ok) {
+  return tg_guard(ctx, [&]() -> int {
+    if (!tg_shape_ok(N, D)) { ctx->err = "supported shapes: N in {6, 8, 10, 12}, D in 1..4"; return TG_ERR_INVALID; }
+    if (S < 1 || n < 0 || !coef || !times || !t || !out || derivative < 0) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    if (n == 0) return TG_OK;
+    const std::vector<double> c4 = tg_pad_coef(coef, (size_t)S, N, D);
+    std::vector<double> o4((size_t)n * TG_D);
+    tg_dispatch_n(N, [&](auto nn) { ctx->pipe.template evaluate_batch_n<decltype(nn)::value>(S, c4.data(), times, n, t, derivative, o4.data(), ok); });
+    for (size_t i = 0; i < (size_t)n; ++i)
+      for (int d = 0; d < D; ++d) out[i * D + d] = o4[i * TG_D + d];
+    return TG_OK;
+  });
+}
+
+int tg_sample_batch_nd(tg_ctx* ctx, int N, int D, int B, const int* seg_off, const double* coef, const double* times, double dt, int* counts,
+                       double* samples, double* full) {
+  return tg_guard(ctx, [&]() -> int {
+    if (!tg_shape_ok(N, D)) { ctx->err = "supported shapes: N in {6, 8, 10, 12}, D in 1..4"; return TG_ERR_INVALID; }
+    if (D < 3) { ctx->err = "Dimension has to be at least 3"; return TG_ERR_INVALID; }  // eth/trajectory_sampling.cpp:58-61
+    if (B < 1 || !seg_off || !coef || !times || !counts || !(dt > 0.0)) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+    const std::vector<double> c4 = tg_pad_coef(coef, (size_t)seg_off[B], N, D);
+    ctx->be.timer_start();
+    tg_dispatch_n(N, [&](auto nn) { ctx->pipe.template sample_batch_n<decltype(nn)::value>(B, seg_off, c4.data(), times, dt, counts, samples, full); });
+    ctx->last_ms = ctx->be.timer_stop();
     return TG_OK;
   });
 }

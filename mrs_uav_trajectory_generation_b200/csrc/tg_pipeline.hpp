@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "tg_kernels.cuh"
+#include "tg_generic.cuh"
 
 namespace tg {
 
@@ -1148,6 +1149,126 @@ class Pipeline {
     }
     return 0;
   }
+  // ---- general-shape path (tg_generic.cuh): PolynomialOptimization<N> for N = 6, 8, 10, 12 on 4 (zero-padded) dimensions ----------
+  // setupFromVertices + solveLinear + getSegments + computeCost for B problems.  The vertex bookkeeping (first free unknown per
+  // vertex, half bandwidth, workspace offsets) is host logic here: the inputs arrive from the host and this path is not the
+  // benchmarked one.  vval: [totV][N/2][4]; coef out: [totS][4][N].
+  template <int N>
+  bool linear_batch_n(int B, const int* vtx_off, const uint8_t* vmask, const double* vval, const double* times, int r, double* coef, double* cost) {
+    constexpr int H = N / 2;
+    scratch_.reset();
+    const int totV = vtx_off[B], totS = totV - B;
+    for (int p = 0; p < B; ++p)
+      if (vtx_off[p + 1] - vtx_off[p] < 2) return false;
+    std::vector<int> vfree((size_t)totV + B), np(B), hbw(B);
+    std::vector<long long> ws_off(B);
+    long long ws_tot = 0;
+    for (int p = 0; p < B; ++p) {
+      const int v0 = vtx_off[p], V = vtx_off[p + 1] - v0;
+      int* ff = vfree.data() + v0 + p;  // V + 1 entries
+      ff[0] = 0;
+      for (int v = 0; v < V; ++v) {
+        int cnt = 0;
+        for (int k = 0; k < H; ++k) cnt += ((vmask[v0 + v] >> k) & 1u) ? 0 : 1;
+        ff[v + 1] = ff[v] + cnt;
+      }
+      int hb = 0;  // a free slot of vertex v couples to the free slots of v-1 .. v+1 (oracle/linear.cpp LinearSolver::solve)
+      for (int v = 0; v < V; ++v)
+        if (ff[v + 1] > ff[v]) hb = std::max(hb, ff[std::min(v + 2, V)] - 1 - ff[v]);
+      np[p] = ff[V];
+      hbw[p] = hb;
+      ws_off[p] = ws_tot;
+      ws_tot += (long long)gen::ws_doubles<N>(V - 1, np[p], hb);
+    }
+    int* d_vtx_off = scratch_.template alloc<int>((size_t)B + 1);
+    uint8_t* d_vmask = scratch_.template alloc<uint8_t>(totV);
+    int* d_vfree = scratch_.template alloc<int>(vfree.size());
+    double* d_vval = scratch_.template alloc<double>((size_t)totV * H * TG_D);
+    int* d_np = scratch_.template alloc<int>(B);
+    int* d_hbw = scratch_.template alloc<int>(B);
+    double* d_times = scratch_.template alloc<double>(totS);
+    double* d_recs = scratch_.template alloc<double>((size_t)totS * gen::Rec<N>::kSize);
+    long long* d_ws_off = scratch_.template alloc<long long>(B);
+    double* d_ws = scratch_.template alloc<double>((size_t)std::max<long long>(ws_tot, 1));
+    double* d_coef = scratch_.template alloc<double>((size_t)totS * TG_D * N);
+    double* d_cost = scratch_.template alloc<double>(B);
+    be_.h2d(d_vtx_off, vtx_off, sizeof(int) * ((size_t)B + 1));
+    be_.h2d(d_vmask, vmask, totV);
+    be_.h2d(d_vfree, vfree.data(), sizeof(int) * vfree.size());
+    be_.h2d(d_vval, vval, sizeof(double) * (size_t)totV * H * TG_D);
+    be_.h2d(d_np, np.data(), sizeof(int) * B);
+    be_.h2d(d_hbw, hbw.data(), sizeof(int) * B);
+    be_.h2d(d_times, times, sizeof(double) * totS);
+    be_.h2d(d_ws_off, ws_off.data(), sizeof(long long) * B);
+    be_.for_each((size_t)totS, gen::RecordHeadFn<N>{r, d_times, d_recs});
+    be_.for_each((size_t)totS * N, gen::RecordHrowFn<N>{d_recs});
+    be_.for_each_warp((size_t)B, gen::SolveFn<N>{r, d_vtx_off, d_vmask, d_vfree, d_vval, d_np, d_hbw, d_recs, d_ws_off, d_ws, d_coef, d_cost});
+    launches(3);
+    counters.solves += B;
+    counters.segment_setups += totS;
+    if (coef) be_.d2h(coef, d_coef, sizeof(double) * (size_t)totS * TG_D * N);
+    if (cost) be_.d2h(cost, d_cost, sizeof(double) * B);
+    return true;
+  }
+  // Trajectory::evaluate at n times of one trajectory of N-coefficient segments
+  template <int N>
+  void evaluate_batch_n(int S, const double* coef, const double* times, int n, const double* t, int deriv, double* out, uint8_t* ok) {
+    scratch_.reset();
+    double* d_coef = scratch_.template alloc<double>((size_t)S * TG_D * N);
+    double* d_T = scratch_.template alloc<double>(S);
+    double* d_t = scratch_.template alloc<double>(std::max(n, 1));
+    double* d_out = scratch_.template alloc<double>((size_t)std::max(n, 1) * 4);
+    uint8_t* d_ok = scratch_.template alloc<uint8_t>(std::max(n, 1));
+    be_.h2d(d_coef, coef, sizeof(double) * (size_t)S * TG_D * N);
+    be_.h2d(d_T, times, sizeof(double) * S);
+    be_.h2d(d_t, t, sizeof(double) * n);
+    be_.for_each(n, gen::EvaluateFn<N>{S, deriv, d_coef, d_T, d_t, d_out, d_ok});
+    launches(1);
+    be_.d2h(out, d_out, sizeof(double) * 4 * (size_t)n);
+    if (ok) be_.d2h(ok, d_ok, n);
+  }
+  // sampleWholeTrajectory for B trajectories of N-coefficient segments (the dt walk does not depend on N)
+  template <int N>
+  void sample_batch_n(int B, const int* seg_off, const double* coef, const double* times, double dt, int* counts, double* samples, double* full) {
+    scratch_.reset();
+    const int totS = seg_off[B];
+    int* d_seg_off = scratch_.template alloc<int>((size_t)B + 1);
+    double* d_times = scratch_.template alloc<double>(std::max(totS, 1));
+    double* d_coef = scratch_.template alloc<double>((size_t)std::max(totS, 1) * TG_D * N);
+    be_.h2d(d_seg_off, seg_off, sizeof(int) * ((size_t)B + 1));
+    be_.h2d(d_times, times, sizeof(double) * totS);
+    be_.h2d(d_coef, coef, sizeof(double) * (size_t)totS * TG_D * N);
+    int* cap = scratch_.template alloc<int>((size_t)B + 1);
+    int* d_smp_off = scratch_.template alloc<int>((size_t)B + 1);
+    int* d_count = scratch_.template alloc<int>(B);
+    be_.for_each(B, GenSampleCapFn{d_seg_off, d_times, dt, cap});
+    be_.exclusive_scan(cap, d_smp_off, B);
+    std::vector<int> smp_off(B + 1);
+    be_.d2h(smp_off.data(), d_smp_off, sizeof(int) * (B + 1));
+    const size_t slots = (size_t)std::max(smp_off[B], 1);
+    int* seg_idx = scratch_.template alloc<int>(slots);
+    int* smp_prob = scratch_.template alloc<int>(slots);
+    double* t_in = scratch_.template alloc<double>(slots);
+    be_.for_each(B, GenSampleWalkFn{d_seg_off, d_times, dt, d_smp_off, seg_idx, t_in, d_count});
+    launches(3);
+    be_.d2h(counts, d_count, sizeof(int) * B);
+    std::vector<int> dst(B + 1, 0);
+    for (int p = 0; p < B; ++p) dst[p + 1] = dst[p] + counts[p];
+    counters.samples += dst[B];
+    if ((!samples && !full) || dst[B] == 0) return;
+    double* d_xyzh = samples ? scratch_.template alloc<double>(slots * 4) : nullptr;
+    double* d_full = full ? scratch_.template alloc<double>(slots * 19) : nullptr;
+    be_.for_each(B, SlotProblemFn{B, d_smp_off, smp_prob});
+    be_.for_each((size_t)smp_off[B], gen::SampleEvalFn<N>{d_seg_off, d_smp_off, smp_prob, d_count, seg_idx, t_in, d_coef, d_xyzh, d_full});
+    launches(2);
+    // a trajectory's samples are contiguous from its slot offset; the unused tail of each capacity range is skipped here
+    for (int p = 0; p < B; ++p) {
+      if (counts[p] == 0) continue;
+      if (samples) be_.d2h(samples + 4 * (size_t)dst[p], d_xyzh + 4 * (size_t)smp_off[p], sizeof(double) * 4 * (size_t)counts[p]);
+      if (full) be_.d2h(full + 19 * (size_t)dst[p], d_full + 19 * (size_t)smp_off[p], sizeof(double) * 19 * (size_t)counts[p]);
+    }
+  }
+
   size_t objective_chunk = (size_t)1 << 15;
   size_t sweep_chunk = (size_t)1 << 17;
 

@@ -48,7 +48,10 @@
 
 namespace orc {
 
-constexpr int kN = 10;        // coefficients per polynomial (node.cpp:1063)
+#ifndef ORC_N
+#define ORC_N 10  // the node's only instantiation (node.cpp:1063); liboracle_n{6,8,12}.so are built with -DORC_N for the general-N tests
+#endif
+constexpr int kN = ORC_N;     // coefficients per polynomial (lin.h:46-55: even, <= Polynomial::kMaxN = 12)
 constexpr int kHalf = kN / 2;  // derivative slots per vertex (lin_impl.h:206)
 constexpr int kD = 4;          // x, y, z, heading (node.cpp:902)
 

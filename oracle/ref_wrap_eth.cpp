@@ -16,7 +16,10 @@
 #include "oracle.h"
 
 namespace etg = eth_trajectory_generation;
-static const int kN = 10, kHalf = 5, kD = 4;
+#ifndef REF_N
+#define REF_N 10  // _ref/libref_eth_n{6,8,12}.so instantiate the reference templates for the other even N (lin.h:46-55)
+#endif
+static const int kN = REF_N, kHalf = REF_N / 2, kD = 4;
 
 namespace orc {
 // bridge used by ref_shim/nlopt.hpp: LD_LBFGS -> oracle/plis.cpp
@@ -73,9 +76,9 @@ static void store_segments(const etg::Segment::Vector& segs, double* coeffs, dou
 
 extern "C" {
 
-// PolynomialOptimization<10>::setupMappingMatrix / invertMappingMatrix / computeQuadraticCostJacobian (row-major 10x10 out)
+// PolynomialOptimization<REF_N>::setupMappingMatrix / invertMappingMatrix / computeQuadraticCostJacobian (row-major 10x10 out)
 void ref_segment_matrices(double T, int r, double* A, double* Ainv, double* Q) {
-  typedef etg::PolynomialOptimization<10> PO;
+  typedef etg::PolynomialOptimization<REF_N> PO;
   PO::SquareMatrix a, ai, q;
   a.setZero();
   ai.setZero();
@@ -92,7 +95,7 @@ void ref_segment_matrices(double T, int r, double* A, double* Ainv, double* Q) {
 
 // setupFromVertices + solveLinear + getSegments + computeCost + getFreeConstraints
 int ref_solve_linear(int V, const uint8_t* mask, const double* vals, const double* times, int r, double* coeffs, double* cost, double* dp, int* dims) {
-  etg::PolynomialOptimization<10> opt(kD);
+  etg::PolynomialOptimization<REF_N> opt(kD);
   const std::vector<double> t(times, times + (V - 1));
   if (!opt.setupFromVertices(make_vertices(V, mask, vals), t, r)) return 1;
   if (!opt.solveLinear()) return 2;
@@ -116,7 +119,7 @@ int ref_solve_linear(int V, const uint8_t* mask, const double* vals, const doubl
 
 // getR: (n_fixed + n_free)^2 row-major
 int ref_dense_R(int V, const uint8_t* mask, const double* vals, const double* times, int r, double* R) {
-  etg::PolynomialOptimization<10> opt(kD);
+  etg::PolynomialOptimization<REF_N> opt(kD);
   const std::vector<double> t(times, times + (V - 1));
   if (!opt.setupFromVertices(make_vertices(V, mask, vals), t, r)) return 1;
   Eigen::MatrixXd Rm;
@@ -129,7 +132,7 @@ int ref_dense_R(int V, const uint8_t* mask, const double* vals, const double* ti
 // computeMaximumOfMagnitude(derivative) after a linear solve at `times`
 int ref_solve_max_magnitude(int V, const uint8_t* mask, const double* vals, const double* times, int r, int derivative, double* time, double* value,
                             int* segment_idx) {
-  etg::PolynomialOptimization<10> opt(kD);
+  etg::PolynomialOptimization<REF_N> opt(kD);
   const std::vector<double> t(times, times + (V - 1));
   if (!opt.setupFromVertices(make_vertices(V, mask, vals), t, r)) return 1;
   opt.solveLinear();
@@ -230,7 +233,7 @@ int ref_trajectory_evaluate(int S, const double* coeffs, const double* times, do
   return (t > acc) ? 0 : 1;
 }
 
-// PolynomialOptimizationNonLinear<10>: setupFromVertices + 12 x addMaximumMagnitudeConstraint + optimize() + getSegments,
+// PolynomialOptimizationNonLinear<REF_N>: setupFromVertices + 12 x addMaximumMagnitudeConstraint + optimize() + getSegments,
 // with the node's parameter recipe (node.cpp:880-905, 1063-1083); limits9 = v_h v_v a_h a_v j_h j_v v_hdg a_hdg j_hdg
 int ref_time_alloc(int V, const uint8_t* mask, const double* vals, double* times, int r, int max_evals, double f_rel, double x_rel, const double* L,
                    double* coeffs, int* code, int* n_evals, double* final_cost) {
@@ -242,7 +245,7 @@ int ref_time_alloc(int V, const uint8_t* mask, const double* vals, double* times
   parameters.initial_stepsize_rel = 0.1;
   parameters.max_iterations = max_evals;
   parameters.max_time = 1e9;
-  etg::PolynomialOptimizationNonLinear<10> opt(kD, parameters);
+  etg::PolynomialOptimizationNonLinear<REF_N> opt(kD, parameters);
   const std::vector<double> t(times, times + (V - 1));
   opt.setupFromVertices(make_vertices(V, mask, vals), t, r);
   using namespace etg::derivative_order;
@@ -284,7 +287,7 @@ int ref_objective(int V, const uint8_t* mask, const double* vals, int r, int met
     parameters.use_soft_constraints = use_soft != 0;
     parameters.soft_constraint_weight = soft_weight;
     parameters.random_seed = 0;
-    etg::PolynomialOptimizationNonLinear<10> opt(kD, parameters);
+    etg::PolynomialOptimizationNonLinear<REF_N> opt(kD, parameters);
     const std::vector<double> t(xk, xk + S);
     opt.setupFromVertices(make_vertices(V, mask, vals), t, r);
     for (int c = 0; c < ncon; ++c) opt.addMaximumMagnitudeConstraint(0, con_deriv[c], con_value[c]);

@@ -62,6 +62,9 @@ struct EmuBackend {
   }
   template <class F>
   void for_each(size_t n, const F& f) { parallel(n, [&](size_t i) { f(i); }); }
+  // one "warp" per work item (CudaBackend::for_each_warp): TG_PHASE runs the 32 lanes of every phase one after the other
+  template <class F>
+  void for_each_warp(size_t n, const F& f) { parallel(n, [&](size_t i) { f(i, 0); }); }
   // work items with F::kScratch doubles of private scratch (shared memory on the device), stride 1 here
   template <class F>
   void for_each_scratch(size_t n, const F& f) {

@@ -361,3 +361,46 @@ def sweep_costs(mask, vals, r, cand_times, nthreads=0):
     costs = np.zeros(K)
     lib().orc_sweep_costs(mask.shape[0], _ptr(mask, u8p), _ptr(vals), int(r), K, _ptr(cand), _ptr(costs), int(nthreads))
     return costs
+
+
+class OracleN:
+    """The restatement compiled for another even coefficient count (oracle/Makefile: liboracle_n{6,8,12}.so = the same sources
+    with -DORC_N); n = 10 is liboracle.so itself.  Each library has its own math-mode switch."""
+
+    def __init__(self, n, mode=MATH_DET):
+        self.N, self.HALF = int(n), int(n) // 2
+        name = "liboracle.so" if self.N == 10 else f"liboracle_n{self.N}.so"
+        path = os.path.join(ORACLE_DIR, name)
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, name])
+        self.lib = C.CDLL(path)
+        self.lib.orc_set_math_mode(int(mode))
+
+    def solve_linear(self, mask, vals, times, r):
+        """vals [V][N/2][4] -> coef [S][4][N], cost"""
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        V = mask.shape[0]
+        coeffs = np.zeros((V - 1, D, self.N))
+        cost = C.c_double()
+        dims = (C.c_int * 2)()
+        dpv = np.zeros(D * self.HALF * V)
+        rc = self.lib.orc_solve_linear(V, _ptr(mask, u8p), _ptr(vals), _ptr(times), int(r), _ptr(coeffs), C.byref(cost), _ptr(dpv), dims)
+        assert rc == 0
+        return coeffs, cost.value
+
+    def trajectory_evaluate(self, coeffs, times, t, deriv):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        out = np.zeros(4)
+        ok = self.lib.orc_trajectory_evaluate(len(times), _ptr(coeffs), _ptr(times), C.c_double(float(t)), int(deriv), _ptr(out))
+        return out, bool(ok)
+
+    def sample(self, coeffs, times, dt, cap=100000):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        out = np.zeros((cap, 19))
+        n = self.lib.orc_sample(len(times), _ptr(coeffs), _ptr(times), C.c_double(float(dt)), cap, _ptr(out), None)
+        assert n >= 0
+        return out[:n].copy()
