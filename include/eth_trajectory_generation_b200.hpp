@@ -166,30 +166,42 @@ struct Extremum {  // eth/extremum.h:31-55: ordered by value
 class Segment {
  public:
   typedef std::vector<Segment> Vector;
-  Segment() : time_(0.0), coef_(b200::kD * b200::kN, 0.0) {}
-  int N() const { return b200::kN; }
-  int D() const { return b200::kD; }
+  Segment() : time_(0.0), N_(b200::kN), D_(b200::kD), coef_(b200::kD * b200::kN, 0.0) {}
+  Segment(int N, int D) : time_(0.0), N_(N), D_(D), coef_((size_t)N * D, 0.0) {}  // eth/segment.h:48
+  int N() const { return N_; }
+  int D() const { return D_; }
   double getTime() const { return time_; }
   void setTime(double t) { time_ = t; }
   // coefficients of dimension `dim`, increasing powers (eth/polynomial.h:35-37)
-  const double* coefficients(int dim) const { return coef_.data() + dim * b200::kN; }
-  double* coefficients(int dim) { return coef_.data() + dim * b200::kN; }
-  const double* data() const { return coef_.data(); }
+  const double* coefficients(int dim) const { return coef_.data() + dim * N_; }
+  double* coefficients(int dim) { return coef_.data() + dim * N_; }
+  const double* data() const { return coef_.data(); }  // [D][N]
 
  private:
   double time_;
+  int N_, D_;
   std::vector<double> coef_;
 };
 
 class Trajectory {
  public:
   Trajectory() {}
-  int D() const { return b200::kD; }
-  int N() const { return b200::kN; }
+  // shape of the segments (eth/trajectory.h:58-60; 10 coefficients x 4 dimensions while empty, the node's shape)
+  int D() const { return segments_.empty() ? b200::kD : segments_.front().D(); }
+  int N() const { return segments_.empty() ? b200::kN : segments_.front().N(); }
   int K() const { return (int)segments_.size(); }
   bool empty() const { return segments_.empty(); }
   void clear() { segments_.clear(); }
-  void setSegments(const Segment::Vector& segments) { segments_ = segments; }
+  void setSegments(const Segment::Vector& segments) {  // eth/trajectory.h:97-104: every segment must have the same shape
+    for (const Segment& sg : segments)
+      if (sg.N() != segments.front().N() || sg.D() != segments.front().D()) {
+        std::printf("[Trajectory]: segments of different shapes, not set\n");
+        return;
+      }
+    segments_ = segments;
+  }
+  // the tuned kernels take 10 coefficients x 4 dimensions; other shapes go through the general-shape entry points (tg_*_nd)
+  bool tunedShape() const { return N() == b200::kN && D() == b200::kD; }
   void getSegments(Segment::Vector* segments) const {
     if (segments) *segments = segments_;
   }
@@ -207,16 +219,17 @@ class Trajectory {
   }
   // Trajectory::evaluate(t, derivative) (eth/trajectory.cpp:55-87); past the end: prints, returns zeros.
   Vector evaluate(double t, int derivative = derivative_order::POSITION) const {
-    Vector out = b200::make_vector(b200::kD, 0.0);
+    Vector out = b200::make_vector((size_t)D(), 0.0);
     if (segments_.empty()) return out;
     std::vector<double> coef, times;
     pack(&coef, &times);
     uint8_t ok = 0;
     double v4[b200::kD] = {0, 0, 0, 0};
     b200::Context& c = b200::Context::instance();
-    c.check(tg_evaluate_batch(c.get(), K(), coef.data(), times.data(), 1, &t, derivative, v4, &ok), "tg_evaluate_batch");
+    if (tunedShape()) c.check(tg_evaluate_batch(c.get(), K(), coef.data(), times.data(), 1, &t, derivative, v4, &ok), "tg_evaluate_batch");
+    else c.check(tg_evaluate_batch_nd(c.get(), N(), D(), K(), coef.data(), times.data(), 1, &t, derivative, v4, &ok), "tg_evaluate_batch_nd");
     if (!ok) std::printf("[Trajectory]: time out of range, returning zeros\n");
-    for (int d = 0; d < b200::kD; ++d) out[d] = v4[d];
+    for (int d = 0; d < D(); ++d) out[d] = v4[d];
     return out;
   }
   // evaluateRange (eth/trajectory.cpp:93-151): the dt walk of the sampler, derivative `derivative` only
@@ -231,8 +244,9 @@ class Trajectory {
                                           double j_max_horizontal, double j_max_vertical, double v_max_heading, double a_max_heading,
                                           double j_max_heading) {
     if (segments_.empty()) return true;
+    if (!requireTenCoefficients("scaleSegmentTimesToMeetConstraints")) return false;
     std::vector<double> coef, times;
-    pack(&coef, &times);
+    pack4(&coef, &times);
     const double L[9] = {v_max_horizontal, v_max_vertical, a_max_horizontal, a_max_vertical, j_max_horizontal,
                          j_max_vertical,   v_max_heading,  a_max_heading,    j_max_heading};
     const int seg_off[2] = {0, K()};
@@ -240,24 +254,51 @@ class Trajectory {
     uint8_t within = 0;
     b200::Context& c = b200::Context::instance();
     c.check(tg_scale_times_batch(c.get(), 1, seg_off, coef.data(), times.data(), L, &passes, &within), "tg_scale_times_batch");
-    unpack(coef, times);
+    unpack4(coef, times);
     return within != 0;
   }
 
   // marshalling helpers (also used by the optimisers)
+  // coef: [K][D][N] in the trajectory's own shape
   void pack(std::vector<double>* coef, std::vector<double>* times) const {
-    coef->resize((size_t)K() * b200::kD * b200::kN);
+    const size_t dn = (size_t)D() * N();
+    coef->resize((size_t)K() * dn);
     times->resize(K());
     for (int i = 0; i < K(); ++i) {
       (*times)[i] = segments_[i].getTime();
-      for (int e = 0; e < b200::kD * b200::kN; ++e) (*coef)[(size_t)i * b200::kD * b200::kN + e] = segments_[i].data()[e];
+      for (size_t e = 0; e < dn; ++e) (*coef)[(size_t)i * dn + e] = segments_[i].data()[e];
     }
   }
-  void unpack(const std::vector<double>& coef, const std::vector<double>& times) {
-    segments_.assign(times.size(), Segment());
+  void unpack(const std::vector<double>& coef, const std::vector<double>& times, int n_coef = b200::kN, int dims = b200::kD) {
+    segments_.assign(times.size(), Segment(n_coef, dims));
     for (size_t i = 0; i < times.size(); ++i) {
       segments_[i].setTime(times[i]);
-      for (int d = 0; d < b200::kD; ++d)
+      for (int d = 0; d < dims; ++d)
+        for (int k = 0; k < n_coef; ++k) segments_[i].coefficients(d)[k] = coef[(i * dims + d) * n_coef + k];
+    }
+  }
+  // The maxima, time scaling and magnitude entry points exist for 10 coefficients only.  Fewer than 4 dimensions are carried as zero
+  // dimensions: a zero polynomial adds exact zeros to every sum of squares, so the other dimensions' results do not change.
+  bool requireTenCoefficients(const char* what) const {
+    if (N() == b200::kN) return true;
+    std::printf("[Trajectory]: %s is not available for N = %d on the B200 path (N = 10 only)\n", what, N());
+    return false;
+  }
+  void pack4(std::vector<double>* coef, std::vector<double>* times) const {  // [K][4][10], D() <= 4
+    coef->assign((size_t)K() * b200::kD * b200::kN, 0.0);
+    times->resize(K());
+    for (int i = 0; i < K(); ++i) {
+      (*times)[i] = segments_[i].getTime();
+      for (int d = 0; d < D(); ++d)
+        for (int k = 0; k < b200::kN; ++k) (*coef)[((size_t)i * b200::kD + d) * b200::kN + k] = segments_[i].coefficients(d)[k];
+    }
+  }
+  void unpack4(const std::vector<double>& coef, const std::vector<double>& times) {  // keeps the trajectory's D
+    const int dims = D();
+    segments_.assign(times.size(), Segment(b200::kN, dims));
+    for (size_t i = 0; i < times.size(); ++i) {
+      segments_[i].setTime(times[i]);
+      for (int d = 0; d < dims; ++d)
         for (int k = 0; k < b200::kN; ++k) segments_[i].coefficients(d)[k] = coef[(i * b200::kD + d) * b200::kN + k];
     }
   }
@@ -265,9 +306,9 @@ class Trajectory {
  private:
   void max_of_group(int group, double* v_max, double* a_max, double* j_max) const {
     double m[3] = {-1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
-    if (!segments_.empty()) {
+    if (!segments_.empty() && requireTenCoefficients("computeMaxDerivatives")) {
       std::vector<double> coef, times, maxima((size_t)K() * 9);
-      pack(&coef, &times);
+      pack4(&coef, &times);
       b200::Context& c = b200::Context::instance();
       c.check(tg_extrema_batch(c.get(), K(), coef.data(), times.data(), maxima.data()), "tg_extrema_batch");
       for (int i = 0; i < K(); ++i)
@@ -323,15 +364,25 @@ inline bool sampleWholeTrajectory(const Trajectory& trajectory, double sampling_
     std::printf("[sampleWholeTrajectory]: empty trajectory or non-positive sampling interval\n");
     return false;
   }
+  if (trajectory.D() < 3) {
+    std::printf("[sampleWholeTrajectory]: Dimension has to be at least 3, but is %d\n", trajectory.D());  // eth/trajectory_sampling.cpp:58-61
+    return false;
+  }
   std::vector<double> coef, times;
   trajectory.pack(&coef, &times);
   const int seg_off[2] = {0, trajectory.K()};
+  const int n_coef = trajectory.N(), dims = trajectory.D();
+  const bool tuned = trajectory.tunedShape();
   int count = 0;
   b200::Context& c = b200::Context::instance();
-  c.check(tg_sample_batch(c.get(), 1, seg_off, coef.data(), times.data(), sampling_interval, &count, nullptr, nullptr), "tg_sample_batch");
+  auto sample = [&](double* xyzh, double* full) {
+    if (tuned) c.check(tg_sample_batch(c.get(), 1, seg_off, coef.data(), times.data(), sampling_interval, &count, xyzh, full), "tg_sample_batch");
+    else c.check(tg_sample_batch_nd(c.get(), n_coef, dims, 1, seg_off, coef.data(), times.data(), sampling_interval, &count, xyzh, full), "tg_sample_batch_nd");
+  };
+  sample(nullptr, nullptr);
   if (count <= 0) return false;
   std::vector<double> xyzh((size_t)count * 4), full((size_t)count * 19);
-  c.check(tg_sample_batch(c.get(), 1, seg_off, coef.data(), times.data(), sampling_interval, &count, xyzh.data(), full.data()), "tg_sample_batch");
+  sample(xyzh.data(), full.data());
   states->resize(count);
   for (int i = 0; i < count; ++i) {
     auto& s = (*states)[i];
@@ -344,7 +395,7 @@ inline bool sampleWholeTrajectory(const Trajectory& trajectory, double sampling_
       s.jerk_W[k] = f[12 + k];
       s.snap_W[k] = f[15 + k];
     }
-    b200::fill_heading(s, f);
+    if (dims == 4) b200::fill_heading(s, f);  // eth/trajectory_sampling.cpp:99-103: only a 4-dimensional trajectory sets the yaw
   }
   return true;
 }
@@ -386,43 +437,50 @@ inline void Trajectory::evaluateRange(double t_start, double t_end, double dt, i
     acc += dt;
   }
   if (ts.empty()) return;
-  std::vector<double> out(ts.size() * b200::kD);
+  const int dims = D();
+  std::vector<double> out(ts.size() * (size_t)dims);
   std::vector<uint8_t> ok(ts.size());
   b200::Context& c = b200::Context::instance();
+  const bool tuned = tunedShape();
   // one device call per run of samples that fall into the same segment: that segment alone, evaluated at time_in_segment
   for (size_t k0 = 0; k0 < ts.size();) {
     size_t k1 = k0;
     while (k1 < ts.size() && seg_of[k1] == seg_of[k0]) ++k1;
     const Segment& sg = segments_[seg_of[k0]];
     const double T = sg.getTime();
-    c.check(tg_evaluate_batch(c.get(), 1, sg.data(), &T, (int)(k1 - k0), ts.data() + k0, derivative, out.data() + k0 * b200::kD, ok.data() + k0), "tg_evaluate_batch");
+    if (tuned)
+      c.check(tg_evaluate_batch(c.get(), 1, sg.data(), &T, (int)(k1 - k0), ts.data() + k0, derivative, out.data() + k0 * dims, ok.data() + k0), "tg_evaluate_batch");
+    else
+      c.check(tg_evaluate_batch_nd(c.get(), N(), dims, 1, sg.data(), &T, (int)(k1 - k0), ts.data() + k0, derivative, out.data() + k0 * dims, ok.data() + k0),
+              "tg_evaluate_batch_nd");
     k0 = k1;
   }
   for (size_t k = 0; k < ts.size(); ++k) {
-    Vector v = b200::make_vector(b200::kD, 0.0);
-    for (int d = 0; d < b200::kD; ++d) v[d] = out[k * b200::kD + d];
+    Vector v = b200::make_vector((size_t)dims, 0.0);
+    for (int d = 0; d < dims; ++d) v[d] = out[k * dims + d];
     result->push_back(v);
   }
 }
 
 // ---- vertex marshalling ------------------------------------------------------------------------------------------------
 namespace b200 {
-// masks / fixed values of a vertex list; constraints above derivative 4 are dropped with a warning (lin_impl.h:84-102)
-inline bool pack_vertices(const Vertex::Vector& vertices, std::vector<uint8_t>* mask, std::vector<double>* vals) {
+// masks / fixed values ([V][half][dims]) of a vertex list; constraints above derivative half-1 are dropped with a warning
+// (lin_impl.h:84-102)
+inline bool pack_vertices(const Vertex::Vector& vertices, std::vector<uint8_t>* mask, std::vector<double>* vals, int half = kHalf, int dims = kD) {
   mask->assign(vertices.size(), 0);
-  vals->assign(vertices.size() * kHalf * kD, 0.0);
+  vals->assign(vertices.size() * (size_t)half * dims, 0.0);
   for (size_t v = 0; v < vertices.size(); ++v) {
-    if (vertices[v].D() != (size_t)kD) {
-      std::printf("[PolynomialOptimization]: the B200 path is built for 4 dimensions (x, y, z, heading)\n");
+    if (vertices[v].D() != (size_t)dims) {
+      std::printf("[PolynomialOptimization]: vertex %zu has %zu dimensions, the optimisation %d\n", v, vertices[v].D(), dims);
       return false;
     }
     for (const auto& kv : vertices[v].constraints()) {
-      if (kv.first < 0 || kv.first >= kHalf) {
-        std::printf("[PolynomialOptimization]: constraint of derivative %d ignored (highest possible: %d)\n", kv.first, kHalf - 1);
+      if (kv.first < 0 || kv.first >= half) {
+        std::printf("[PolynomialOptimization]: constraint of derivative %d ignored (highest possible: %d)\n", kv.first, half - 1);
         continue;
       }
       (*mask)[v] |= (uint8_t)(1u << kv.first);
-      for (int d = 0; d < kD; ++d) (*vals)[(v * kHalf + kv.first) * kD + d] = kv.second[d];
+      for (int d = 0; d < dims; ++d) (*vals)[(v * half + kv.first) * dims + d] = kv.second[d];
     }
   }
   return true;
@@ -430,28 +488,26 @@ inline bool pack_vertices(const Vertex::Vector& vertices, std::vector<uint8_t>* 
 }  // namespace b200
 
 // ---- PolynomialOptimization<N> (lin.h:60-233) -----------------------------------------------------------------------------
+// N = 10 on 4 dimensions with derivative_to_optimize 2..4 (the node's shape, node.cpp:902, 907-921, 1063) runs on the tuned kernels;
+// every other shape the reference's template allows up to Polynomial::kMaxN = 12 -- N in {6, 8, 10, 12}, 1..4 dimensions,
+// derivative_to_optimize 0 .. N/2-1 -- on the general-shape kernels (tg_solve_linear_batch_nd), bit-identical where both apply.
 template <int _N = 10>
 class PolynomialOptimization {
-  static_assert(_N == 10, "the B200 kernels are built for N = 10 coefficients (the node's only instantiation, node.cpp:1063)");
+  static_assert(_N == 6 || _N == 8 || _N == 10 || _N == 12, "the B200 path is built for N = 6, 8, 10 or 12 coefficients (lin.h:46-55, kMaxN = 12)");
 
  public:
   enum { N = _N };
+  static constexpr int kHighestDerivativeToOptimize = N / 2 - 1;  // lin.h:55
   explicit PolynomialOptimization(size_t dimension) : dimension_(dimension), derivative_to_optimize_(derivative_order::INVALID), cost_(0.0), solved_(false) {}
 
   // lin_impl.h:61-106
   bool setupFromVertices(const Vertex::Vector& vertices, const std::vector<double>& segment_times, int derivative_to_optimize) {
-    if (!(derivative_to_optimize >= 0 && derivative_to_optimize <= b200::kHalf - 1)) {
-      std::printf("[PolynomialOptimization]: you tried to optimize a derivative that is not possible\n");
+    if (!(derivative_to_optimize >= 0 && derivative_to_optimize <= kHighestDerivativeToOptimize)) {
+      std::printf("[PolynomialOptimization]: you tried to optimize a derivative that is not possible\n");  // lin_impl.h:63-66
       return false;
     }
-    if (derivative_to_optimize < derivative_order::ACCELERATION) {
-      // the reference accepts 0 and 1 as well (lin_impl.h:61-70); the kernels integrate the squared 2nd, 3rd or 4th derivative
-      // (the node's three choices, node.cpp:907-921).  Refuse loudly instead of optimising something else.
-      std::printf("[PolynomialOptimization]: derivative_to_optimize = %d is not supported by the B200 path (2, 3 or 4)\n", derivative_to_optimize);
-      return false;
-    }
-    if (dimension_ != (size_t)b200::kD) {
-      std::printf("[PolynomialOptimization]: the B200 path is built for 4 dimensions (x, y, z, heading)\n");
+    if (dimension_ < 1 || dimension_ > (size_t)b200::kD) {
+      std::printf("[PolynomialOptimization]: the B200 path carries 1 to 4 dimensions\n");
       return false;
     }
     if (vertices.size() < 2 || segment_times.size() != vertices.size() - 1) {
@@ -462,7 +518,11 @@ class PolynomialOptimization {
     vertices_ = vertices;
     segment_times_ = segment_times;
     solved_ = false;
-    return b200::pack_vertices(vertices_, &mask_, &vals_);
+    return b200::pack_vertices(vertices_, &mask_, &vals_, N / 2, (int)dimension_);
+  }
+  // the node's shape: tuned kernels
+  bool tunedShape() const {
+    return N == b200::kN && dimension_ == (size_t)b200::kD && derivative_to_optimize_ >= derivative_order::ACCELERATION;
   }
   // lin_impl.h:288-304
   void updateSegmentTimes(const std::vector<double>& segment_times) {
@@ -478,10 +538,12 @@ class PolynomialOptimization {
     if (vertices_.empty()) return false;
     const int V = (int)vertices_.size();
     const int vtx_off[2] = {0, V};
-    coef_.resize((size_t)(V - 1) * b200::kD * b200::kN);
+    coef_.resize((size_t)(V - 1) * dimension_ * N);
     b200::Context& c = b200::Context::instance();
-    const int r = derivative_to_optimize_;  // 2, 3 or 4 (setupFromVertices refuses anything else)
-    const int rc = tg_solve_linear_batch(c.get(), 1, vtx_off, mask_.data(), vals_.data(), segment_times_.data(), r, coef_.data(), &cost_);
+    const int r = derivative_to_optimize_;
+    const int rc = tunedShape() ? tg_solve_linear_batch(c.get(), 1, vtx_off, mask_.data(), vals_.data(), segment_times_.data(), r, coef_.data(), &cost_)
+                                : tg_solve_linear_batch_nd(c.get(), N, (int)dimension_, 1, vtx_off, mask_.data(), vals_.data(), segment_times_.data(), r,
+                                                           coef_.data(), &cost_);
     if (rc != TG_OK) {
       std::printf("[PolynomialOptimization]: solveLinear failed: %s\n", tg_last_error(c.get()));
       return false;
@@ -504,17 +566,21 @@ class PolynomialOptimization {
   void getTrajectory(Trajectory* trajectory) const {  // lin.h:153-160
     if (!trajectory) return;
     trajectory->clear();
-    if (solved_) trajectory->unpack(coef_, segment_times_);
+    if (solved_) trajectory->unpack(coef_, segment_times_, N, (int)dimension_);
   }
   // lin_impl.h:477-508 (the reference's optional list of all candidates is not produced)
   Extremum computeMaximumOfMagnitude(int derivative, std::vector<Extremum>* candidates = nullptr) const {
     if (candidates) candidates->clear();
     Extremum e;
     if (!solved_ || segment_times_.empty()) return e;
+    Trajectory t;
+    getTrajectory(&t);
+    if (!t.requireTenCoefficients("computeMaximumOfMagnitude")) return e;
+    std::vector<double> c4, times;
+    t.pack4(&c4, &times);  // missing dimensions as zero polynomials: they add exact zeros to the squared magnitude
     b200::Context& c = b200::Context::instance();
     const int off[2] = {0, (int)segment_times_.size()};
-    c.check(tg_max_magnitude_batch(c.get(), 1, off, coef_.data(), segment_times_.data(), derivative, &e.value, &e.time, &e.segment_idx),
-            "tg_max_magnitude_batch");
+    c.check(tg_max_magnitude_batch(c.get(), 1, off, c4.data(), times.data(), derivative, &e.value, &e.time, &e.segment_idx), "tg_max_magnitude_batch");
     return e;
   }
   template <int Derivative>
@@ -580,6 +646,11 @@ class PolynomialOptimizationNonLinear {
   }
   // nl_impl.h:51-82
   bool setupFromVertices(const Vertex::Vector& vertices, const std::vector<double>& segment_times, int derivative_to_optimize) {
+    // the time allocation runs on the tuned kernels only: the node's shape (node.cpp:902, 907-921, 1063)
+    if (N != b200::kN || poly_opt_.getDimension() != (size_t)b200::kD || derivative_to_optimize < derivative_order::ACCELERATION) {
+      std::printf("[PolynomialOptimizationNonLinear]: the B200 time allocation is built for N = 10, 4 dimensions, derivative_to_optimize 2..4\n");
+      return false;
+    }
     return poly_opt_.setupFromVertices(vertices, segment_times, derivative_to_optimize);
   }
   // nl_impl.h:538-565; the (dimension, derivative) -> limit mapping of scaleSegmentTimesWithViolation (355-381):

@@ -31,8 +31,8 @@ class Vertex:
     """eth_trajectory_generation::Vertex (eth/vertex.h:42-116): derivative -> D-vector constraints."""
 
     def __init__(self, dimension=D):
-        if dimension != D:
-            raise ValueError("the B200 path is built for D = 4 (x, y, z, heading) like the node (node.cpp:902)")
+        if not 1 <= dimension <= D:
+            raise ValueError("the B200 path carries 1 to 4 dimensions (the node uses 4: x, y, z, heading, node.cpp:902)")
         self.D = dimension
         self.constraints = {}
 
@@ -56,23 +56,25 @@ class Vertex:
     def getConstraint(self, derivative):
         return self.constraints.get(int(derivative))
 
-    def mask_and_values(self):
-        """Constraints with derivative > 4 are dropped, as setupFromVertices does (lin_impl.h:84-102)."""
+    def mask_and_values(self, half=HALF):
+        """Constraints with derivative > N/2 - 1 are dropped, as setupFromVertices does (lin_impl.h:84-102).  Values [half][D]."""
         m = 0
-        vals = np.zeros((HALF, D))
+        vals = np.zeros((half, self.D))
         for k, v in self.constraints.items():
-            if 0 <= k < HALF:
+            if 0 <= k < half:
                 m |= 1 << k
                 vals[k] = v
         return m, vals
 
 
-def pack_vertices(vertex_lists):
+def pack_vertices(vertex_lists, half=HALF, dimension=D):
     vtx_off = [0]
     masks, vals = [], []
     for vl in vertex_lists:
         for v in vl:
-            m, x = v.mask_and_values()
+            if v.D != dimension:
+                raise ValueError("vertex dimension %d does not match the optimisation's %d" % (v.D, dimension))
+            m, x = v.mask_and_values(half)
             masks.append(m)
             vals.append(x)
         vtx_off.append(len(masks))
@@ -119,9 +121,20 @@ class Trajectory:
     def getSegmentTimes(self):
         return self.times.copy()
 
+    def shape(self):
+        """(D, N) of the segments (Trajectory::D(), N(), eth/trajectory.h:58-60)."""
+        return (D, N) if self.coef is None else tuple(self.coef.shape[1:])
+
+    def _tuned(self):
+        return self.shape() == (D, N)
+
     def evaluate(self, t, derivative=derivative_order.POSITION):
         """Trajectory::evaluate (eth/trajectory.cpp:55-87); t may be an array.  Past-the-end queries return zeros."""
-        out, ok = self._c().evaluate(self.coef, self.times, t, derivative)
+        if self._tuned():
+            out, ok = self._c().evaluate(self.coef, self.times, t, derivative)
+        else:
+            d, n = self.shape()
+            out, ok = self._c().evaluate_nd(n, d, self.coef, self.times, t, derivative)
         return out[0] if np.isscalar(t) else out
 
     def computeMaxDerivatives(self):
@@ -140,18 +153,28 @@ def sample_whole_trajectory(trajectory, dt, full=False, ctx=None):
     Returns samples [M, 4] (x, y, z, heading) or, with full=True, [M, 19] = p4 v4 a4 j3 s3 yaw."""
     c = ctx or trajectory._c()
     seg_off = np.array([0, trajectory.K()], dtype=np.int32)
-    counts, samples, fullv = c.sample_batch(seg_off, trajectory.coef, trajectory.times, dt, full=full)
+    if trajectory._tuned():
+        counts, samples, fullv = c.sample_batch(seg_off, trajectory.coef, trajectory.times, dt, full=full)
+    else:  # any N in {6, 8, 10, 12}; D >= 3 as the reference demands (eth/trajectory_sampling.cpp:58-61)
+        d, n = trajectory.shape()
+        counts, samples, fullv = c.sample_batch_nd(n, d, seg_off, trajectory.coef, trajectory.times, dt, full=full)
     return fullv if full else samples
 
 
 class PolynomialOptimization:
-    """eth_trajectory_generation::PolynomialOptimization<10> (lin.h:60-233) for one problem or a batch."""
+    """eth_trajectory_generation::PolynomialOptimization<N> (lin.h:60-233) for one problem or a batch.  N = 10 on 4 dimensions with
+    derivative_to_optimize 2..4 (the node's shape) runs on the tuned kernels; N in {6, 8, 10, 12}, 1..4 dimensions and
+    derivative_to_optimize 0 .. N/2-1 on the general-shape kernels (tg_solve_linear_batch_nd)."""
 
     N = N
 
-    def __init__(self, dimension=D, ctx=None):
-        if dimension != D:
-            raise ValueError("D = 4 only")
+    def __init__(self, dimension=D, ctx=None, n_coefficients=N):
+        if not 1 <= dimension <= D:
+            raise ValueError("1 to 4 dimensions")
+        if n_coefficients not in (6, 8, 10, 12):
+            raise ValueError("N = 6, 8, 10 or 12 coefficients (lin.h:46-55; Polynomial::kMaxN = 12)")
+        self.N = n_coefficients
+        self.dimension = dimension
         self._ctx = ctx
         self._lists = None
         self.derivative_to_optimize = derivative_order.INVALID
@@ -161,11 +184,7 @@ class PolynomialOptimization:
         return self._ctx or default_context()
 
     def setupFromVertices(self, vertices, times, derivative_to_optimize):  # lin_impl.h:61-106
-        if 0 <= derivative_to_optimize < 2:
-            # the reference accepts 0 and 1 as well (lin_impl.h:61-70); the kernels integrate the squared 2nd, 3rd or 4th derivative
-            print("[PolynomialOptimization]: derivative_to_optimize = %d is not supported by the B200 path (2, 3 or 4)" % derivative_to_optimize)
-            return False
-        if not (0 <= derivative_to_optimize <= 4):
+        if not (0 <= derivative_to_optimize <= self.N // 2 - 1):  # kHighestDerivativeToOptimize (lin.h:55, lin_impl.h:63-66)
             print("You tried to optimize a derivative that is not possible")  # CHECK prints and continues (eth/misc.h)
             return False
         single = len(vertices) > 0 and isinstance(vertices[0], Vertex)
@@ -183,10 +202,13 @@ class PolynomialOptimization:
         self._times = [np.asarray(times, dtype=np.float64)] if self._single else [np.asarray(t, dtype=np.float64) for t in times]
 
     def solveLinear(self):  # lin_impl.h:340-373
-        vtx_off, masks, vals = pack_vertices(self._lists)
+        vtx_off, masks, vals = pack_vertices(self._lists, self.N // 2, self.dimension)
         self._seg_off = vtx_off - np.arange(len(vtx_off), dtype=np.int32)
-        self.coef, self.cost = self._c().solve_linear_batch(vtx_off, masks, vals, np.concatenate(self._times),
-                                                            self.derivative_to_optimize)
+        if self.N == N and self.dimension == D and self.derivative_to_optimize >= 2:
+            self.coef, self.cost = self._c().solve_linear_batch(vtx_off, masks, vals, np.concatenate(self._times), self.derivative_to_optimize)
+        else:
+            self.coef, self.cost = self._c().solve_linear_batch_nd(self.N, self.dimension, vtx_off, masks, vals, np.concatenate(self._times),
+                                                                   self.derivative_to_optimize)
         return True
 
     def computeCost(self):  # lin_impl.h:127-141

@@ -159,10 +159,20 @@ int main(int argc, char** argv) {
     dump(f, "df4_times", t2.data(), t2.size());
     dump(f, "df4_coef", c2.data(), c2.size());
   }
-  // derivative_to_optimize below 2 is refused loudly
+  // derivative_to_optimize below 2: the linear optimisation takes it (general-shape kernels, lin_impl.h:61-70 accepts 0 .. N/2-1);
+  // the time allocation, built for the node's three choices, refuses it loudly
   {
     PolynomialOptimization<10> lin(dimension);
-    const double refused = lin.setupFromVertices(vertices, times, derivative_order::VELOCITY) ? 0.0 : 1.0;
+    if (!lin.setupFromVertices(vertices, times, derivative_order::VELOCITY) || !lin.solveLinear()) return 4;
+    Trajectory t1;
+    lin.getTrajectory(&t1);
+    std::vector<double> c1, tt1;
+    t1.pack(&c1, &tt1);
+    c1.push_back(lin.computeCost());
+    dump(f, "r1_coef_cost", c1.data(), c1.size());
+    NonlinearOptimizationParameters prm;
+    PolynomialOptimizationNonLinear<10> nl1(dimension, prm);
+    const double refused = nl1.setupFromVertices(vertices, times, derivative_order::VELOCITY) ? 0.0 : 1.0;
     dump(f, "r1_refused", &refused, 1);
   }
   // TrajectoryGeneratorBatch over two contexts (two host threads): same results as one context

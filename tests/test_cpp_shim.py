@@ -198,6 +198,89 @@ def _check_eigen(res, ctx):
         assert np.array_equal(res[key + "_times"][0], opt._dfo.times) and np.array_equal(res[key + "_coef"][0].reshape(-1, 4, 10), opt._dfo.coef)
         assert np.array_equal(m[2:5], opt._dfo.cost_parts)
     assert res["r1_refused"][0][0] == 1.0 and res["multi_ctx_same"][0][0] == 1.0
+    c1, cost1 = O.OracleN(10).solve_linear(mask, vals, times, 1)  # derivative_to_optimize = 1 through the general-shape kernels
+    assert np.array_equal(res["r1_coef_cost"][0][:-1].reshape(-1, 4, 10), c1) and res["r1_coef_cost"][0][-1] == cost1
+
+
+def _check_general(res):
+    """tests/cpp/test_shim_general.cpp: PolynomialOptimization<8>(3), <12>(4), <6>(1), <10>(3) against the oracle compiled for that N."""
+    def wp(i, dims):
+        return np.array([1.7 * i, 0.6 if i % 2 == 0 else -0.4, 3.0 + 0.25 * i, 0.15 * i])[:dims]
+
+    for key, n_coef, dims, r in (("n8d3", 8, 3, 3), ("n12d4", 12, 4, 4), ("n6d1", 6, 1, 2), ("n10d3", 10, 3, 2)):
+        H, V = n_coef // 2, 6
+        orc = O.OracleN(n_coef)
+        mask = np.ones(V, np.uint8)
+        mask[0] = mask[-1] = (1 << (r + 1)) - 1
+        mask[2] |= 2
+        vals = np.zeros((V, H, 4))
+        for i in range(V):
+            vals[i, 0, :dims] = wp(i, dims)
+        vals[2, 1, :dims] = 0.3
+        times = np.array([0.8 + 0.3 * (i % 3) for i in range(V - 1)])
+        coef, cost = orc.solve_linear(mask, vals, times, r)
+        assert np.array_equal(res[key + "_coef"][0].reshape(V - 1, dims, n_coef), coef[:, :dims]), key
+        assert res[key + "_cost"][0][0] == cost, key
+        tot = 0.0
+        for t in times:
+            tot += t
+        k = 0
+        for tq in (0.0, 1.3, tot * 0.8):
+            for deriv in (0, 1, 2):
+                assert np.array_equal(res[key + "_eval"][k], orc.trajectory_evaluate(coef, times, tq, deriv)[0][:dims]), (key, tq, deriv)
+                k += 1
+        # evaluateRange(0.4, max, 0.35, velocity): the reference's walk (eth/trajectory.cpp:93-151)
+        acc, i = 0.0, 0
+        for i in range(len(times)):
+            acc += times[i]
+            if acc > 0.4:
+                break
+        acc -= times[i]
+        tin, want = 0.4 - acc, []
+        while acc < tot:
+            if tin > times[i]:
+                tin = tin - times[i]
+                i += 1
+                if i >= len(times):
+                    break
+                continue
+            want.append(orc.trajectory_evaluate(coef[i:i + 1], times[i:i + 1], tin, 1)[0][:dims])
+            tin += 0.35
+            acc += 0.35
+        assert np.array_equal(res[key + "_range"][0].reshape(-1, dims), np.array(want)), key
+        if dims >= 3:
+            full = orc.sample(coef, times, 0.2)
+            got = res[key + "_samples"][0].reshape(-1, 3, 3)
+            assert got.shape[0] == full.shape[0]
+            assert np.array_equal(got[:, :, 0], full[:, 0:3]) and np.array_equal(got[:, :, 1], full[:, 4:7]) and np.array_equal(got[:, :, 2], full[:, 15:18])
+        else:
+            assert res[key + "_samples"][0].size == 0
+    # N = 10 on three dimensions: maxima / magnitude / time scaling equal the four-dimensional run with a zero heading
+    V = 5
+    mask = np.ones(V, np.uint8)
+    mask[0] = mask[-1] = 0b111
+    vals = np.zeros((V, 5, 4))
+    for i in range(V):
+        vals[i, 0, :3] = wp(i, 3)
+    times = np.full(V - 1, 0.7)
+    coef, _, _, _ = O.solve_linear(mask, vals, times, 2)
+    mx = O.segment_maxima(coef, times)
+    assert np.array_equal(res["n10d3_max"][0], np.concatenate([mx[:, 0:3].max(axis=0), mx[:, 3:6].max(axis=0)]))
+    t, v, i = O.max_magnitude(coef, times, 1)
+    assert np.array_equal(res["n10d3_maxmag"][0], [t, v, float(i)])
+    c2, t2, passes, within = O.scale_times(coef, times)
+    assert np.array_equal(res["n10d3_scaled_times"][0][:-1], t2) and res["n10d3_scaled_times"][0][-1] == float(within)
+    assert np.array_equal(res["n10d3_scaled_coef"][0].reshape(-1, 3, 10), c2[:, :3])
+    assert res["d5_refused"][0][0] == 1.0 and res["n8_scale_refused"][0][0] == 0.0
+
+
+def test_cpp_shim_general_shapes_on_host_emulation(oracle, emu_lib, tmp_path):
+    _check_general(_run_shim(os.path.join(ROOT, "tests", "host_emu"), "tg_emu", tmp_path, "test_shim_general.cpp"))
+
+
+@pytest.mark.gpu
+def test_cpp_shim_general_shapes_on_gpu(oracle, gpu_ctx, tmp_path):
+    _check_general(_run_shim(os.path.join(ROOT, "mrs_uav_trajectory_generation_b200"), "tg_b200", tmp_path, "test_shim_general.cpp"))
 
 
 def test_cpp_shim_eigen_types_on_host_emulation(oracle, emu_lib, emu_ctx, tmp_path):

@@ -129,6 +129,52 @@ def check_refusals(ctx):
             ctx.solve_linear_batch_nd(n_coef, dims, off, m, vv, t, r)
 
 
+def check_api(ctx):
+    """The reference-shaped host classes on another shape: Vertex(3), PolynomialOptimization<8>(3), Trajectory, sampleWholeTrajectory."""
+    import mrs_uav_trajectory_generation_b200.api as A
+
+    n_coef, dims, r = 8, 3, 3
+    pts = [np.array([1.3 * i, (-1.0) ** i * 0.7, 2.0 + 0.2 * i]) for i in range(6)]
+    verts = []
+    for i, p in enumerate(pts):
+        v = A.Vertex(dims)
+        if i in (0, len(pts) - 1):
+            v.makeStartOrEnd(p, r)
+        else:
+            v.addConstraint(A.derivative_order.POSITION, p)
+        verts.append(v)
+    times = np.array([0.9, 1.1, 0.7, 1.4, 1.0])
+    opt = A.PolynomialOptimization(dims, ctx=ctx, n_coefficients=n_coef)
+    assert opt.setupFromVertices(verts, times, r) and opt.solveLinear()
+    assert not A.PolynomialOptimization(dims, ctx=ctx, n_coefficients=n_coef).setupFromVertices(verts, times, 4)  # above N/2 - 1
+    traj = opt.getTrajectory()
+    assert traj.shape() == (dims, n_coef)
+    orc = O.OracleN(n_coef)
+    mask = np.ones(len(pts), np.uint8)
+    mask[0] = mask[-1] = (1 << (r + 1)) - 1
+    vals = np.zeros((len(pts), n_coef // 2, 4))
+    for i, p in enumerate(pts):
+        vals[i, 0, :dims] = p
+    c_o, cost_o = orc.solve_linear(mask, vals, times, r)
+    assert np.array_equal(traj.coef, c_o[:, :dims]) and opt.computeCost() == cost_o
+    assert np.array_equal(traj.evaluate(2.2, 1), orc.trajectory_evaluate(c_o, times, 2.2, 1)[0][:dims])
+    full = A.sample_whole_trajectory(traj, 0.25, full=True)
+    assert np.array_equal(full, orc.sample(c_o, times, 0.25))
+    opt4 = A.PolynomialOptimization(4, ctx=ctx, n_coefficients=8)
+    assert opt4.setupFromVertices(verts, times, 2)
+    with pytest.raises(ValueError):
+        opt4.solveLinear()  # three-dimensional vertices in a four-dimensional optimisation
+
+
+def test_api_general_shape_emulator(emu_ctx, oracle):
+    check_api(emu_ctx)
+
+
+@pytest.mark.gpu
+def test_api_general_shape_gpu(gpu_ctx, oracle):
+    check_api(gpu_ctx)
+
+
 @pytest.mark.parametrize("n_coef,dims", SHAPES)
 def test_linear_general_shape_emulator(emu_ctx, oracle, n_coef, dims):
     check_linear(emu_ctx, n_coef, dims)
