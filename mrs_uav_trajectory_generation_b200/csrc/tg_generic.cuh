@@ -13,7 +13,7 @@
 //                                                      (lin_impl.h:310-373, 263-282, 127-141) -- the phases of tg_solve.cuh
 //   poly_eval_n<N>, sample_eval_n<N>                   Trajectory::evaluate / sampleWholeTrajectory (eth/trajectory.cpp:55-151,
 //                                                      eth/trajectory_sampling.cpp:49-124)
-// Every sum is the DENSE sum over ascending index, exactly as oracle/linear.cpp writes it (the tuned path skips structural
+// Every sum is the DENSE sum over ascending index, exactly as the reference-order restatement writes it (the tuned path skips structural
 // zeros, which is the same IEEE result); for N = 10 this path and the tuned one are compared bit for bit in the tests.
 // D: the device works on 4 right-hand sides; tg_*_nd pad D < 4 with zero dimensions (a zero dimension adds exact zeros to the
 // cost and nothing to the other dimensions) and strip them from the outputs.

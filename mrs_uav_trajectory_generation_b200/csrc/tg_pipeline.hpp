@@ -1172,7 +1172,7 @@ class Pipeline {
         for (int k = 0; k < H; ++k) cnt += ((vmask[v0 + v] >> k) & 1u) ? 0 : 1;
         ff[v + 1] = ff[v] + cnt;
       }
-      int hb = 0;  // a free slot of vertex v couples to the free slots of v-1 .. v+1 (oracle/linear.cpp LinearSolver::solve)
+      int hb = 0;  // a free slot of vertex v couples to the free slots of v-1 .. v+1 (lin_impl.h:317-333)
       for (int v = 0; v < V; ++v)
         if (ff[v + 1] > ff[v]) hb = std::max(hb, ff[std::min(v + 2, V)] - 1 - ff[v]);
       np[p] = ff[V];
