@@ -38,6 +38,7 @@ extern "C" {
 #define TG_ERR_CUDA (-2)
 #define TG_ERR_INVALID (-3)
 #define TG_ERR_NO_RESULT (-4)
+#define TG_ERR_CAPACITY (-5)
 
 typedef struct tg_ctx tg_ctx;
 
@@ -108,6 +109,15 @@ double tg_last_device_ms(const tg_ctx* ctx);
  * results: [B] host.  totals[2]: total segments and total samples of the final trajectories (sizes for tg_fetch_outputs). */
 int tg_optimize_batch(tg_ctx* ctx, int B, const int* wp_off, const double* wp, const uint8_t* stop_at, const double* init14,
                       const tg_params* params, int inputs_on_device, tg_result* results, long long* totals);
+/* tg_optimize_batch with the samples of every path (what getTrajectoryReference hands to the tracker, node.cpp:1560-1606) copied to
+ *   host memory WHILE the later validation / subdivision rounds of optimize() (node.cpp:729-785) still run: a path's samples are final
+ *   as soon as its own validation passes, and most paths finish in the first rounds.  samples_out: samples_cap rows of 4 doubles
+ *   (x y z heading) in host memory -- page-locked memory for a real overlap --; paths are stored in COMPLETION order:
+ *   smp_begin[p] = first row of path p, results[p].n_samples rows.  TG_ERR_CAPACITY when samples_cap < totals[1] (the batch
+ *   result is complete and can be read with tg_fetch_outputs).  Everything else as tg_optimize_batch. */
+int tg_optimize_batch_streamed(tg_ctx* ctx, int B, const int* wp_off, const double* wp, const uint8_t* stop_at, const double* init14,
+                               const tg_params* params, int inputs_on_device, tg_result* results, long long* totals, double* samples_out,
+                               long long samples_cap, long long* smp_begin);
 /* Copies the outputs of the last tg_optimize_batch to host buffers (any pointer may be NULL):
  *   seg_off[B+1] (segment offsets; vertex offset of problem p = seg_off[p] + p), wp[(totS+B)*4] final waypoint lists,
  *   times[totS], coef[totS*40], smp_off[B+1], samples[totM*4].

@@ -111,6 +111,8 @@ class Library:
         L.tg_get_counters.argtypes = [C.c_void_p, _llp]
         L.tg_get_flop_counters.argtypes = [C.c_void_p, _dp]
         L.tg_optimize_batch.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _u8p, _dp, C.POINTER(Params), C.c_int, C.c_void_p, _llp]
+        L.tg_optimize_batch_streamed.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _u8p, _dp, C.POINTER(Params), C.c_int, C.c_void_p, _llp, _dp,
+                                                  C.c_longlong, _llp]
         L.tg_fetch_outputs.argtypes = [C.c_void_p, _ip, _dp, _dp, _dp, _ip, _dp]
         L.tg_solve_linear_batch.argtypes = [C.c_void_p, C.c_int, _ip, _u8p, _dp, _dp, C.c_int, _dp, _dp]
         L.tg_time_alloc_batch.argtypes = [C.c_void_p, C.c_int, _ip, _u8p, _dp, _dp, C.POINTER(Params), _dp, _ip, _ip, _ip, _dp]
@@ -257,6 +259,29 @@ class Context:
         self._B = B
         self._totals = (totals[0], totals[1])
         return res, self._totals
+
+    def optimize_batch_streamed(self, wp_off, wp, samples_out, stop_at=None, init14=None, params=None, inputs_on_device=False):
+        """tg_optimize_batch_streamed: optimize_batch with the samples copied into `samples_out` (float64 [cap, 4]; page-locked for a
+        real overlap) while later rounds still run.  Returns (results, totals, smp_begin): path p owns rows
+        smp_begin[p] : smp_begin[p] + results['n_samples'][p] (completion order, not path order)."""
+        wp_off = np.ascontiguousarray(wp_off, dtype=np.int32)
+        B = len(wp_off) - 1
+        if not inputs_on_device:
+            wp = np.ascontiguousarray(wp, dtype=np.float64)
+            stop_at = None if stop_at is None else np.ascontiguousarray(stop_at, dtype=np.uint8)
+            init14 = None if init14 is None else np.ascontiguousarray(init14, dtype=np.float64)
+        if samples_out.dtype != np.float64 or not samples_out.flags["C_CONTIGUOUS"] or samples_out.ndim != 2 or samples_out.shape[1] != 4:
+            raise ValueError("samples_out: C-contiguous float64 [cap, 4]")
+        params = params or self.L.default_params()
+        res = np.zeros(B, dtype=RESULT_DTYPE)
+        totals = (C.c_longlong * 2)()
+        begin = np.zeros(B, dtype=np.int64)
+        self._check(self.L.lib.tg_optimize_batch_streamed(self.h, B, _p(wp_off, _ip), _p(wp), _p(stop_at, _u8p), _p(init14), C.byref(params),
+                                                          1 if inputs_on_device else 0, res.ctypes.data_as(C.c_void_p), totals,
+                                                          _p(samples_out), int(samples_out.shape[0]), _p(begin, _llp)))
+        self._B = B
+        self._totals = (totals[0], totals[1])
+        return res, self._totals, begin
 
     def fetch_outputs(self, want=("seg_off", "wp", "times", "coef", "smp_off", "samples"), out=None):
         """Copies the last batch's outputs to host arrays (optionally into caller-provided pinned buffers `out`)."""

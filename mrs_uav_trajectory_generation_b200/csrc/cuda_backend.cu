@@ -311,6 +311,8 @@ struct CudaBackend {
   bool force_general_solve = false;
   int oct_reg_warps = 8;  // resident single-warp CTAs of k_solve_oct per SM as far as registers allow
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // d2h_overlapped
+  cudaEvent_t copy_ready = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   static constexpr int kSideStreams = 9;
   cudaStream_t side[kSideStreams] = {};
@@ -384,6 +386,8 @@ struct CudaBackend {
       if (ev_side[i]) cudaEventDestroy(ev_side[i]);
     }
     if (ev_fork) cudaEventDestroy(ev_fork);
+    if (copy_ready) cudaEventDestroy(copy_ready);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (stream) cudaStreamDestroy(stream);
   }
   CudaBackend(const CudaBackend&) = delete;
@@ -433,6 +437,22 @@ struct CudaBackend {
     if (n) TG_CUDA_CHECK(cudaMemsetAsync(d, v, n, stream));
   }
   void sync() { TG_CUDA_CHECK(cudaStreamSynchronize(stream)); }
+  // Device-to-host copy that does not hold up the compute stream: it waits for what has been enqueued so far, then runs on its own
+  // stream while later launches proceed (a real overlap needs a pinned destination; a pageable one still gives the right bytes).
+  // copy_join() waits for every such copy.
+  void d2h_overlapped(void* d, const void* s, size_t n) {
+    if (!n) return;
+    if (!copy_stream) {
+      TG_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+      TG_CUDA_CHECK(cudaEventCreateWithFlags(&copy_ready, cudaEventDisableTiming));
+    }
+    TG_CUDA_CHECK(cudaEventRecord(copy_ready, stream));
+    TG_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, copy_ready, 0));
+    TG_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, copy_stream));
+  }
+  void copy_join() {
+    if (copy_stream) TG_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+  }
   void timer_start() {
     bind();
     TG_CUDA_CHECK(cudaEventRecord(ev0, stream));

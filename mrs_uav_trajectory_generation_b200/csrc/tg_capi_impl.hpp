@@ -202,6 +202,29 @@ int tg_optimize_batch(tg_ctx* ctx, int B, const int* wp_off, const double* wp, c
   });
 }
 
+int tg_optimize_batch_streamed(tg_ctx* ctx, int B, const int* wp_off, const double* wp, const uint8_t* stop_at, const double* init14,
+                               const tg_params* params, int inputs_on_device, tg_result* results, long long* totals, double* samples_out,
+                               long long samples_cap, long long* smp_begin) {
+  if (!ctx) return TG_ERR_INVALID;
+  if (!samples_out || samples_cap < 0 || !smp_begin || B < 0) { ctx->err = "invalid argument"; return TG_ERR_INVALID; }
+  for (int p = 0; p < B; ++p) smp_begin[p] = 0;
+  tg::Pipeline<TG_BACKEND>::EarlySamples& e = ctx->pipe.early;
+  e.host = samples_out;
+  e.cap = samples_cap;
+  e.used = 0;
+  e.begin = smp_begin;
+  e.overflow = false;
+  const int lanes = ctx->lanes;
+  ctx->lanes = 1;  // one pipeline owns the stream of finished samples
+  const int rc = tg_optimize_batch(ctx, B, wp_off, wp, stop_at, init14, params, inputs_on_device, results, totals);
+  ctx->lanes = lanes;
+  const bool overflow = e.overflow;
+  e = tg::Pipeline<TG_BACKEND>::EarlySamples();
+  if (rc != TG_OK) return rc;
+  if (overflow) { ctx->err = "samples_out is too small (totals[1] rows are needed); the results can still be read with tg_fetch_outputs"; return TG_ERR_CAPACITY; }
+  return TG_OK;
+}
+
 int tg_fetch_outputs(tg_ctx* ctx, int* seg_off, double* wp, double* times, double* coef, int* smp_off, double* samples) {
   return tg_guard(ctx, [&]() -> int {
     if (ctx->last_B <= 0) { ctx->err = "no batch result to fetch"; return TG_ERR_NO_RESULT; }

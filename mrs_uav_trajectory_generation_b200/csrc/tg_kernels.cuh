@@ -1147,6 +1147,22 @@ struct GatherFn {
   }
 };
 
+// samples of the members whose result is final, compacted in member order: one warp per member (dst_row < 0: not final yet)
+struct GatherSamplesFn {
+  const int* smp_off;
+  const ProbState* ps;
+  const int* dst_row;
+  const double* xyzh;
+  double* out;
+  TG_HD void operator()(size_t item) const {
+    const int m = (int)(item >> 5), lane = (int)(item & 31);
+    const int d = dst_row[m];
+    if (d < 0) return;
+    const int n = ps[m].n_samples * 4;
+    for (int i = lane; i < n; i += 32) out[4 * (size_t)d + i] = xyzh[4 * (size_t)smp_off[m] + i];
+  }
+};
+
 // vertex -> problem map: one thread per problem
 struct VtxProblemFn {
   const int* seg_off;

@@ -273,6 +273,42 @@ class Pipeline {
   }
 
   // ---------------------------------------------------------------------------------------------------------------
+  // Samples streamed to the host while later rounds still run (tg_optimize_batch_streamed).  A path's samples are final as soon as
+  // its validation passes (or it fails); most paths finish in the first rounds, so their device-to-host copy -- 120 MB per 65 536
+  // paths, the largest cost outside the kernels -- overlaps the rounds that follow.  Paths land in COMPLETION order: begin[p] is
+  // the first row of path p.  Too small a buffer sets `overflow` and stops the copies (the results stay fetchable).
+  struct EarlySamples {
+    double* host = nullptr;
+    long long cap = 0, used = 0;
+    long long* begin = nullptr;  // [B]
+    bool overflow = false;
+  };
+  EarlySamples early;
+  void stream_finished_samples(Group& g, const std::vector<int>& finals) {
+    if (!early.host || early.overflow || finals.empty()) return;
+    std::vector<int> dst((size_t)g.B, -1);
+    long long rows = 0;
+    for (int m : finals) {
+      dst[m] = (int)rows;
+      early.begin[g.orig[m]] = early.used + rows;
+      rows += g.ps[m].n_samples;
+    }
+    if (rows == 0) return;
+    if (early.used + rows > early.cap) {
+      early.overflow = true;
+      return;
+    }
+    // the compact copy and the offsets live in the persistent arena: the copy engine reads them after scratch_ has been reset
+    int* d_dst = persist_.template alloc<int>((size_t)g.B);
+    double* d_rows = persist_.template alloc<double>((size_t)rows * 4);
+    be_.h2d(d_dst, dst.data(), sizeof(int) * (size_t)g.B);
+    be_.for_each((size_t)g.B * 32, GatherSamplesFn{g.d_smp_off, g.d_ps, d_dst, g.d_xyzh, d_rows});
+    launches(1);
+    be_.d2h_overlapped(early.host + 4 * early.used, d_rows, sizeof(double) * 4 * (size_t)rows);
+    early.used += rows;
+  }
+
+  // ---------------------------------------------------------------------------------------------------------------
   // optimize(): findTrajectory + validation + subdivision rounds for a whole host batch.
   // wp_off: [B+1] vertex offsets (host).  wp/stop/init14: host pointers, or device pointers when on_device_inputs.
   void optimize_batch(int B, const int* wp_off, const double* wp, const uint8_t* stop, const double* init14, const Params& P,
@@ -337,10 +373,12 @@ class Pipeline {
           be_.d2h(g->ps.data(), g->d_ps, sizeof(ProbState) * g->B);
         }
         const int gi = group_index(g);
+        std::vector<int> finals;  // members whose result is final after this round
         for (int m = 0; m < g->B; ++m) {
           const int p = g->orig[m];
           const ProbState& ps = g->ps[m];
           Result& R = results[p];
+          if (early.host && !(ps.status == kFindOk && !last_round && ps.next_V > 0)) finals.push_back(m);
           final_group_[p] = gi;
           final_index_[p] = m;
           const int S = g->seg_off[m + 1] - g->seg_off[m];
@@ -363,6 +401,7 @@ class Pipeline {
           if (ps.next_V > 0) pending.emplace_back(g, m);
           else R.safe = 1;
         }
+        stream_finished_samples(*g, finals);
       }
       if (pending.empty()) break;
       // members of a next-round group in order of their new segment count (the order inside a group is free: results
@@ -411,6 +450,7 @@ class Pipeline {
       }
       current.swap(next);
     }
+    if (early.host) be_.copy_join();
   }
 
   // sizes of the ragged outputs of the last optimize_batch: totals[0] = segments, totals[1] = samples

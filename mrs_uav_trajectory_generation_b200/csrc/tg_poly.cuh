@@ -71,9 +71,6 @@ struct WArr {
 #ifndef TG_JT_REP
 #define TG_JT_REP 1
 #endif
-#ifndef TG_JT_PIPE
-#define TG_JT_PIPE 1  // O(N) loops with the next shared-memory operand loaded ahead of the dependent arithmetic
-#endif
 #ifndef TG_JT_SCHED
 #define TG_JT_SCHED 1  // 0: majority state first, 1: oldest first
 #endif
@@ -120,21 +117,6 @@ struct JtMachine {
     double bb, aa;
     q[0] = bb = pp[0];
     q[1] = aa = -(bb * uu) + pp[1];
-#if TG_JT_PIPE
-    // Software pipelining: the work arrays live in shared memory and the compiler cannot prove that pp and q are different arrays, so
-    // it keeps every load of pp[i] behind the store of q[i-1] -- the ~25-cycle load then sits on the dependent chain of every
-    // iteration.  Loading the next coefficient before this iteration's arithmetic takes it off the chain; same operations, same order.
-    double nxt = pp[(nn > 2) ? 2 : 1];
-#pragma unroll 1
-    for (int i = 2; i < nn; i++) {
-      const double cur = nxt;
-      nxt = pp[(i + 1 < nn) ? i + 1 : i];
-      const double t = -(aa * uu + bb * vv_) + cur;
-      q[i] = t;
-      bb = aa;
-      aa = t;
-    }
-#else
 #pragma unroll 1
     for (int i = 2; i < nn; i++) {
       const double t = -(aa * uu + bb * vv_) + pp[i];
@@ -142,7 +124,6 @@ struct JtMachine {
       bb = aa;
       aa = t;
     }
-#endif
     *ra = aa;
     *rb = bb;
   }
@@ -182,21 +163,8 @@ struct JtMachine {
       a3 = TG_DIV(a3, a1);
       K[0] = qp[0];
       K[1] = -(a7 * qp[0]) + qp[1];
-#if TG_JT_PIPE
-      double q1 = qp[1], k0 = qk[0], q2 = qp[(N > 2) ? 2 : 1];
-#pragma unroll 1
-      for (int i = 2; i < N; i++) {
-        const double c1 = q1, ck = k0, c2 = q2;
-        const int in = (i + 1 < N) ? i + 1 : i;
-        q1 = c2;
-        k0 = qk[in - 2];
-        q2 = qp[in];
-        K[i] = -(a7 * c1) + a3 * ck + c2;
-      }
-#else
 #pragma unroll 1
       for (int i = 2; i < N; i++) K[i] = -(a7 * qp[i - 1]) + a3 * qk[i - 2] + qp[i];
-#endif
     } else {
       K[0] = 0.0;
       K[1] = -a7 * qp[0];
@@ -591,30 +559,13 @@ struct JtMachine {
       const int nm1 = N - 1;
       double pv;
       qp[0] = pv = p[0];
-      const double ms = dabs(rs);
-      double ee = 0.5 * dabs(pv);
-#if TG_JT_PIPE
-      {
-        // synthetic division and its error bound in one pass (the bound's chain reads qp[i] = pv as it is produced: same
-        // operations in the same order on both chains), next coefficient loaded ahead of the arithmetic
-        double nxt = p[1];
-#pragma unroll 1
-        for (int i = 1; i < NN; i++) {
-          const double cur = nxt;
-          nxt = p[(i + 1 < NN) ? i + 1 : i];
-          pv = pv * rs + cur;
-          qp[i] = pv;
-          ee = ee * ms + dabs(pv);
-        }
-      }
-      const double mp = dabs(pv);
-#else
 #pragma unroll 1
       for (int i = 1; i < NN; i++) qp[i] = pv = pv * rs + p[i];
       const double mp = dabs(pv);
+      const double ms = dabs(rs);
+      double ee = 0.5 * dabs(qp[0]);
 #pragma unroll 1
       for (int i = 1; i < NN; i++) ee = ee * ms + dabs(qp[i]);
-#endif
       if (mp <= 20.0 * TG_DBL_EPSILON * (2.0 * ee - mp)) {
         szr = rs;
         szi = 0.0;
@@ -630,45 +581,6 @@ struct JtMachine {
           romp = mp;
           double kv;
           qk[0] = kv = K[0];
-#if TG_JT_PIPE
-          {
-            double nxt = K[1];
-#pragma unroll 1
-            for (int i = 1; i < N; i++) {
-              const double cur = nxt;
-              nxt = K[(i + 1 < N) ? i + 1 : i];
-              qk[i] = kv = kv * rs + cur;
-            }
-          }
-          if (dabs(kv) > dabs(K[nm1]) * 10.0 * TG_DBL_EPSILON) {
-            // the new K and its value at rs in one pass: K[i] is evaluated as it is produced
-            rt = -TG_DIV(pv, kv);
-            kv = qp[0];
-            K[0] = kv;
-            double nk = qk[0], nq = qp[1];
-#pragma unroll 1
-            for (int i = 1; i < N; i++) {
-              const double ck = nk, cq = nq;
-              const int in = (i + 1 < N) ? i + 1 : i;
-              nk = qk[in - 1];
-              nq = qp[in];
-              const double kn = rt * ck + cq;
-              K[i] = kn;
-              kv = kv * rs + kn;
-            }
-          } else {
-            K[0] = 0.0;
-            kv = 0.0;
-            double nk = qk[0];
-#pragma unroll 1
-            for (int i = 1; i < N; i++) {
-              const double ck = nk;
-              nk = qk[(i + 1 < N) ? i : i - 1];
-              K[i] = ck;
-              kv = kv * rs + ck;
-            }
-          }
-#else
 #pragma unroll 1
           for (int i = 1; i < N; i++) qk[i] = kv = kv * rs + K[i];
           if (dabs(kv) > dabs(K[nm1]) * 10.0 * TG_DBL_EPSILON) {
@@ -684,7 +596,6 @@ struct JtMachine {
           kv = K[0];
 #pragma unroll 1
           for (int i = 1; i < N; i++) kv = kv * rs + K[i];
-#endif
           rt = ((dabs(kv) > (dabs(K[nm1]) * 10.0 * TG_DBL_EPSILON)) ? -TG_DIV(pv, kv) : 0.0);
           rs = rs + rt;
         }

@@ -34,6 +34,8 @@ struct EmuBackend {
   void d2d(void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
   void dev_memset(void* d, int v, size_t n) { std::memset(d, v, n); }
   void sync() {}
+  void d2h_overlapped(void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
+  void copy_join() {}
   void bind() {}
   void timer_start() {}
   double timer_stop() { return 0.0; }

@@ -374,7 +374,33 @@ def compare_optimize(ctx, wp_off, wp, stop_at=None, init=None, params_kw=None, c
                  and np.array_equal(out["samples"][m0:m1], rs) and np.array_equal(out["wp"][s0 + p:s1 + p + 1], rw)
                  and g["max_dev"] == r.max_dev and g["final_cost"] == r.final_cost and g["baca_total"] == r.baca_total)
     assert worst <= COEF_RTOL, worst
+    if B <= 2048:
+        check_streamed_equals_fetched(ctx, wp_off, wp, stop_at, init, params_kw, res, out)
     return res, out, exact, worst
+
+
+def check_streamed_equals_fetched(ctx, wp_off, wp, stop_at, init, params_kw, res, out):
+    """tg_optimize_batch_streamed (samples copied out while later rounds run, completion order) delivers the same results and, path by
+    path, the same sample rows as tg_optimize_batch + tg_fetch_outputs; a buffer that is too small is refused without losing the batch."""
+    tot = int(res["n_samples"].sum())
+    buf = np.full((tot + 7, 4), np.nan)
+    res2, totals2, begin = ctx.optimize_batch_streamed(wp_off, wp, buf, stop_at, init, ctx.L.default_params(**params_kw))
+    assert res2.tobytes() == res.tobytes() and totals2[1] == tot
+    used = np.zeros(tot + 7, bool)
+    for p in range(len(res)):
+        n, m0 = int(res["n_samples"][p]), int(out["smp_off"][p])
+        assert np.array_equal(buf[begin[p]:begin[p] + n], out["samples"][m0:m0 + n]), p
+        assert not used[begin[p]:begin[p] + n].any()
+        used[begin[p]:begin[p] + n] = True
+    assert used[:tot].all() and not used[tot:].any() and np.isnan(buf[tot:]).all()
+    if tot > 1:
+        try:
+            ctx.optimize_batch_streamed(wp_off, wp, np.empty((tot - 1, 4)), stop_at, init, ctx.L.default_params(**params_kw))
+            raise AssertionError("a buffer one row short was accepted")
+        except Exception as e:  # TgError: TG_ERR_CAPACITY
+            assert "too small" in str(e), e
+        again = ctx.fetch_outputs(want=("smp_off", "samples"))  # the batch result is complete all the same
+        assert np.array_equal(again["samples"], out["samples"])
 
 
 def check_random_flier(ctx, B, first_index=0, **params_kw):
