@@ -1147,6 +1147,23 @@ struct GatherFn {
   }
 };
 
+// any non-finite waypoint or initial-state entry among the uploaded inputs (checkNaN of the path callbacks, node.cpp:1896-1900): one
+// thread per path; the count only says whether the host has to find out which paths to leave out
+struct FiniteInputsFn {
+  const int* seg_off;
+  const double* wp;      // [totV][4]
+  const double* init14;  // [B][14] or null
+  int* bad;
+  TG_HD void operator()(size_t pi) const {
+    const int p = (int)pi, v0 = seg_off[p] + p, V = seg_off[p + 1] - seg_off[p] + 1;
+    bool finite = true;
+    for (int i = 0; i < V * 4; ++i) finite = finite && dfinite(wp[(size_t)v0 * 4 + i]);
+    if (init14 && init14[(size_t)p * 14] != 0.0)
+      for (int k = 1; k < 14; ++k) finite = finite && dfinite(init14[(size_t)p * 14 + k]);
+    if (!finite) TG_ATOMIC_ADD(bad, 1);
+  }
+};
+
 // samples of the members whose result is final, compacted in member order: one warp per member (dst_row < 0: not final yet)
 struct GatherSamplesFn {
   const int* smp_off;

@@ -128,7 +128,7 @@ class Pipeline {
 
   // ---------------------------------------------------------------------------------------------------------------
   // findTrajectory over one group.  Inputs (wp/stop/init14) already in device memory inside `g`.
-  void find_group(Group& g, const Params& P) {
+  void find_group(Group& g, const Params& P, bool validate) {
     const int B = g.B, totS = g.totS, totV = g.totV;
     BatchPtrs& b = g.bp;
     std::memset(&b, 0, sizeof(b));
@@ -193,6 +193,10 @@ class Pipeline {
     launches(4);
     if (P.override_heading_atan2) {  // validation reads positions only, so the override may happen here
       be_.for_each(B, HeadingAtan2Fn{g.d_smp_off, g.d_ps, g.d_xyzh});
+      launches(1);
+    }
+    if (validate) {  // validateTrajectorySpatial (node.cpp:1401-1455) before the one read-back of the per-problem state
+      be_.for_each(B, ValidateFn{g.bp, g.d_smp_off, g.d_xyzh, g.d_seg_ok, P.max_deviation, P.first_segment_checked, P.check_deviation});
       launches(1);
     }
     g.ps.resize(B);
@@ -313,19 +317,23 @@ class Pipeline {
   // wp_off: [B+1] vertex offsets (host).  wp/stop/init14: host pointers, or device pointers when on_device_inputs.
   void optimize_batch(int B, const int* wp_off, const double* wp, const uint8_t* stop, const double* init14, const Params& P,
                       bool on_device_inputs, Result* results) {
-    persist_.reset();
-    scratch_.reset();
-    groups_.clear();
-    final_group_.assign(B, -1);
-    final_index_.assign(B, -1);
-    B_ = B;
-    for (int p = 0; p < B; ++p) {
-      std::memset(&results[p], 0, sizeof(Result));
-      results[p].nlopt_code = -1;
-    }
-    // round 0: consecutive groups within the segment budget
+    // round 0: consecutive groups within the segment budget.  Non-finite host inputs are looked for on the device first (one small
+    // launch per group over data that is being uploaded anyway); only a batch that has one pays for the host scan, which is what
+    // tells the groups which paths to leave out (2.9 M isfinite tests per 65 536 paths: ~2 ms of every host-buffer call otherwise).
     std::vector<Group*> current;
-    {
+    for (int attempt = 0;; ++attempt) {
+      const bool host_scan = attempt > 0;
+      persist_.reset();
+      scratch_.reset();
+      groups_.clear();
+      current.clear();
+      final_group_.assign(B, -1);
+      final_index_.assign(B, -1);
+      B_ = B;
+      for (int p = 0; p < B; ++p) {
+        std::memset(&results[p], 0, sizeof(Result));
+        results[p].nlopt_code = -1;
+      }
       std::vector<int> members;
       size_t segs = 0;
       for (int p = 0; p < B; ++p) {
@@ -334,7 +342,7 @@ class Pipeline {
         // cannot drop its caller's message, so the path is excluded and flagged (host inputs only: device-resident inputs are the
         // caller's contract)
         bool finite = true;
-        if (!on_device_inputs && S >= 1) {
+        if (host_scan && S >= 1) {
           for (int v = wp_off[p]; v < wp_off[p + 1] && finite; ++v)
             for (int k = 0; k < 4; ++k) finite = finite && std::isfinite(wp[(size_t)v * 4 + k]);
           if (finite && init14 && init14[(size_t)p * 14] != 0.0)
@@ -359,19 +367,22 @@ class Pipeline {
         segs += S;
       }
       if (!members.empty()) current.push_back(make_group_from_host(members, wp_off, wp, stop, init14, on_device_inputs));
+      if (on_device_inputs || host_scan || current.empty()) break;  // device-resident inputs are the caller's contract
+      int* d_bad = scratch_.template alloc<int>(1);
+      be_.dev_memset(d_bad, 0, sizeof(int));
+      for (Group* g : current) be_.for_each(g->B, FiniteInputsFn{g->d_seg_off, g->d_wp, g->d_init14, d_bad});
+      launches((int)current.size());
+      int bad = 0;
+      be_.d2h(&bad, d_bad, sizeof(int));
+      if (bad == 0) break;
     }
     for (int round = 0;; ++round) {
       // run findTrajectory on every group of this round, then validate
       std::vector<std::pair<Group*, int>> pending;  // (group, member) that need another round
       for (Group* g : current) {
         scratch_.reset();
-        find_group(*g, P);
         const bool last_round = (round >= P.max_deviation_iters);
-        if (!last_round) {
-          be_.for_each(g->B, ValidateFn{g->bp, g->d_smp_off, g->d_xyzh, g->d_seg_ok, P.max_deviation, P.first_segment_checked, P.check_deviation});
-          launches(1);
-          be_.d2h(g->ps.data(), g->d_ps, sizeof(ProbState) * g->B);
-        }
+        find_group(*g, P, !last_round);
         const int gi = group_index(g);
         std::vector<int> finals;  // members whose result is final after this round
         for (int m = 0; m < g->B; ++m) {
@@ -411,9 +422,26 @@ class Pipeline {
         while (a < pending.size()) {
           size_t e = a;
           while (e < pending.size() && pending[e].first == pending[a].first) ++e;
-          std::stable_sort(pending.begin() + a, pending.begin() + e, [](const std::pair<Group*, int>& x, const std::pair<Group*, int>& y) {
-            return x.first->ps[x.second].next_V < y.first->ps[y.second].next_V;
-          });
+          // stable counting sort on the new vertex count (a few hundred distinct values at most): the device waits for this loop, and a
+          // comparison sort of ~40 000 entries cost it milliseconds per round
+          int kmin = pending[a].first->ps[pending[a].second].next_V, kmax = kmin;
+          for (size_t i = a; i < e; ++i) {
+            const int k = pending[i].first->ps[pending[i].second].next_V;
+            kmin = std::min(kmin, k);
+            kmax = std::max(kmax, k);
+          }
+          if ((size_t)(kmax - kmin) <= (e - a) + 1024) {
+            std::vector<size_t> start((size_t)(kmax - kmin) + 2, 0);
+            for (size_t i = a; i < e; ++i) ++start[(size_t)(pending[i].first->ps[pending[i].second].next_V - kmin) + 1];
+            for (size_t k = 1; k < start.size(); ++k) start[k] += start[k - 1];
+            std::vector<std::pair<Group*, int>> sorted(e - a);
+            for (size_t i = a; i < e; ++i) sorted[start[(size_t)(pending[i].first->ps[pending[i].second].next_V - kmin)]++] = pending[i];
+            std::copy(sorted.begin(), sorted.end(), pending.begin() + a);
+          } else {
+            std::stable_sort(pending.begin() + a, pending.begin() + e, [](const std::pair<Group*, int>& x, const std::pair<Group*, int>& y) {
+              return x.first->ps[x.second].next_V < y.first->ps[y.second].next_V;
+            });
+          }
           a = e;
         }
       }
