@@ -8,6 +8,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -415,7 +416,7 @@ struct CudaBackend {
   void d2h(void* d, const void* s, size_t n) {
     if (n && n <= kStageBytes && h_stage) {
       TG_CUDA_CHECK(cudaMemcpyAsync(h_stage, s, n, cudaMemcpyDeviceToHost, stream));
-      TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+      wait_stream();
       std::memcpy(d, h_stage, n);
       return;
     }
@@ -425,12 +426,12 @@ struct CudaBackend {
     if (n && n <= kBigStageBytes && use_big_stage) {
       if (!h_stage_big) TG_CUDA_CHECK(cudaHostAlloc(&h_stage_big, kBigStageBytes, cudaHostAllocDefault));
       TG_CUDA_CHECK(cudaMemcpyAsync(h_stage_big, s, n, cudaMemcpyDeviceToHost, stream));
-      TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+      wait_stream();
       std::memcpy(d, h_stage_big, n);
       return;
     }
     if (n) TG_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream));
-    TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    wait_stream();
   }
   // dynamic shared memory opt-in, once per kernel and size (not on every launch)
   // (the attribute belongs to the function on a device, not to a context: the record is shared by all contexts of the process and
@@ -450,7 +451,22 @@ struct CudaBackend {
   void dev_memset(void* d, int v, size_t n) {
     if (n) TG_CUDA_CHECK(cudaMemsetAsync(d, v, n, stream));
   }
-  void sync() { TG_CUDA_CHECK(cudaStreamSynchronize(stream)); }
+  void sync() { wait_stream(); }
+  // every host wait on the compute stream goes through here; TG_TRACE_HOST=1 accumulates the time spent waiting, so that
+  // (call time - wait time) = host work during which the device may sit idle (printed per batch call by tg_optimize_batch)
+  double wait_s = 0.0;
+  long long waits = 0;
+  const bool trace_host = std::getenv("TG_TRACE_HOST") != nullptr;
+  void wait_stream() {
+    if (!trace_host) {
+      TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+      return;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    TG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    ++waits;
+  }
   // Device-to-host copy that does not hold up the compute stream: it waits for what has been enqueued so far, then runs on its own
   // stream while later launches proceed (a real overlap needs a pinned destination; a pageable one still gives the right bytes).
   // copy_join() waits for every such copy.

@@ -5,6 +5,8 @@
 #define TG_CAPI_IMPL_HPP_
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <exception>
 #include <memory>
@@ -185,7 +187,19 @@ int tg_optimize_batch(tg_ctx* ctx, int B, const int* wp_off, const double* wp, c
       t.join();
       if (!err0.empty() || !err1.empty()) throw std::runtime_error(err0.empty() ? err1 : err0);
     } else if (B > 0) {
+#if defined(__CUDACC__)
+      const auto t0 = std::chrono::steady_clock::now();
+      const double w0 = ctx->be.wait_s;
+      const long long n0 = ctx->be.waits;
+#endif
       ctx->pipe.optimize_batch(B, wp_off, wp, stop_at, init14, P, inputs_on_device != 0, ctx->last.data());
+#if defined(__CUDACC__)
+      if (ctx->be.trace_host) {
+        const double tot = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::fprintf(stderr, "[tg] optimize_batch B=%d: %.2f ms, of which %.2f ms waiting for the device in %lld waits, %.2f ms host work\n", B,
+                     1e3 * tot, 1e3 * (ctx->be.wait_s - w0), ctx->be.waits - n0, 1e3 * (tot - (ctx->be.wait_s - w0)));
+      }
+#endif
     }
     ctx->last_ms = ctx->be.timer_stop();  // both lanes have drained (their last calls were synchronous read-backs)
     std::memcpy(results, ctx->last.data(), sizeof(tg_result) * (size_t)B);

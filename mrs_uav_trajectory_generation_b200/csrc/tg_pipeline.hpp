@@ -8,6 +8,7 @@
 #define TG_PIPELINE_HPP_
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -130,6 +131,7 @@ class Pipeline {
   // findTrajectory over one group.  Inputs (wp/stop/init14) already in device memory inside `g`.
   void find_group(Group& g, const Params& P, bool validate) {
     const int B = g.B, totS = g.totS, totV = g.totV;
+    HostTrace tf0 = trace_mark();
     BatchPtrs& b = g.bp;
     std::memset(&b, 0, sizeof(b));
     b.B = B; b.totS = totS; b.totV = totV; b.r = P.derivative_to_optimize;
@@ -164,8 +166,12 @@ class Pipeline {
     be_.d2h(h_np.data(), b.np, sizeof(int) * B);
     be_.d2h(h_hbw.data(), b.hbw, sizeof(int) * B);
     const std::vector<SolveBucket> buckets = make_buckets(B, g.seg_off.data(), h_np.data(), h_hbw.data(), ws, ows, stats[3]);
+    trace_report(" find: prepare + buckets", -1, tf0);
+    tf0 = trace_mark();
     if (P.run_time_alloc) {
       time_alloc_core(b, P, stats, &buckets);
+      trace_report(" find: time allocation", -1, tf0);
+      tf0 = trace_mark();
     } else {
       b.recs = scratch_.template alloc<double>((size_t)totS * TG_REC_SIZE);
     }
@@ -201,6 +207,8 @@ class Pipeline {
     }
     g.ps.resize(B);
     be_.d2h(g.ps.data(), g.d_ps, sizeof(ProbState) * B);
+    trace_report(" find: solve .. state read", -1, tf0);
+    tf0 = trace_mark();
     if (P.run_time_alloc) {
       int executed = 0;
       be_.d2h(&executed, b.stats + 5, sizeof(int));
@@ -230,6 +238,7 @@ class Pipeline {
       counters.root_finds += (long long)(P.run_time_alloc ? (g.ps[p].n_scale_passes + 1) * 9 * S : 0);
       counters.samples += g.ps[p].n_samples;
     }
+    trace_report(" find: counters", -1, tf0);
   }
 
   // ---------------------------------------------------------------------------------------------------------------
@@ -281,6 +290,17 @@ class Pipeline {
   // its validation passes (or it fails); most paths finish in the first rounds, so their device-to-host copy -- 120 MB per 65 536
   // paths, the largest cost outside the kernels -- overlaps the rounds that follow.  Paths land in COMPLETION order: begin[p] is
   // the first row of path p.  Too small a buffer sets `overflow` and stops the copies (the results stay fetchable).
+  // TG_TRACE_HOST: host time outside device waits, per phase of a round (the device may be idle during it)
+  struct HostTrace {
+    std::chrono::steady_clock::time_point t;
+    double w;
+  };
+  HostTrace trace_mark() const { return HostTrace{std::chrono::steady_clock::now(), be_.wait_s}; }
+  void trace_report(const char* what, int round, const HostTrace& m) const {
+    if (!be_.trace_host) return;
+    const double tot = std::chrono::duration<double>(std::chrono::steady_clock::now() - m.t).count();
+    std::fprintf(stderr, "[tg]   round %d %-28s %7.2f ms, host work %6.2f ms\n", round, what, 1e3 * tot, 1e3 * (tot - (be_.wait_s - m.w)));
+  }
   struct EarlySamples {
     double* host = nullptr;
     long long cap = 0, used = 0;
@@ -382,11 +402,17 @@ class Pipeline {
       for (Group* g : current) {
         scratch_.reset();
         const bool last_round = (round >= P.max_deviation_iters);
+        HostTrace tm = trace_mark();
         find_group(*g, P, !last_round);
+        trace_report("find_group", round, tm);
+        tm = trace_mark();
         const int gi = group_index(g);
         std::vector<int> finals;  // members whose result is final after this round
+        if (early.host) finals.reserve((size_t)g->B);
         for (int m = 0; m < g->B; ++m) {
           const int p = g->orig[m];
+          // from round 1 on the members are ordered by their new size, not by path: results[] is walked at random (the device waits)
+          if (m + 16 < g->B) __builtin_prefetch(&results[g->orig[m + 16]], 1);
           const ProbState& ps = g->ps[m];
           Result& R = results[p];
           if (early.host && !(ps.status == kFindOk && !last_round && ps.next_V > 0)) finals.push_back(m);
@@ -413,8 +439,10 @@ class Pipeline {
           else R.safe = 1;
         }
         stream_finished_samples(*g, finals);
+        trace_report("results + streamed samples", round, tm);
       }
       if (pending.empty()) break;
+      const HostTrace tn = trace_mark();
       // members of a next-round group in order of their new segment count (the order inside a group is free: results
       // go back through `orig`), so that problems of one workspace class are consecutive -> SolveBucket runs
       {
@@ -454,6 +482,9 @@ class Pipeline {
         Group& ng = *groups_.back();
         std::vector<int> srcm;
         size_t segs = 0;
+        srcm.reserve(pending.size() - i);
+        ng.orig.reserve(pending.size() - i);
+        ng.seg_off.reserve(pending.size() - i + 1);
         ng.seg_off.push_back(0);
         while (i < pending.size() && pending[i].first == src) {
           const int m = pending[i].second;
@@ -477,6 +508,7 @@ class Pipeline {
         next.push_back(&ng);
       }
       current.swap(next);
+      trace_report("sort + next groups", round, tn);
     }
     if (early.host) be_.copy_join();
   }

@@ -34,6 +34,8 @@ struct EmuBackend {
   void d2d(void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
   void dev_memset(void* d, int v, size_t n) { std::memset(d, v, n); }
   void sync() {}
+  double wait_s = 0.0;  // CudaBackend's host-wait trace (TG_TRACE_HOST) has nothing to measure here
+  const bool trace_host = false;
   void d2h_overlapped(void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
   void copy_join() {}
   void bind() {}

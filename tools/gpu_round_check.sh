@@ -11,6 +11,12 @@ for spec in "k_solve_thread:2:solve_thread" "SetupMellingerFn<.int.0>:2:SetupHea
   pat=${spec%%:*}; rest=${spec#*:}; skip=${rest%%:*}; name=${rest#*:}
   timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$pat" -s $skip -c 1 -o gpurun_out/${tag}_$name python tools/prof_driver.py 65536 1 > gpurun_out/${tag}_ncu_$name.log 2>&1
 done
+# general-shape path (tg_solve_linear_batch_nd): bench beside the oracle, ncu --set full of its three kernels at N = 12
+timeout 300 python tools/bench_general_shape.py > gpurun_out/${tag}_general_shape.json 2> gpurun_out/${tag}_general_shape.err
+for spec in "RecordHeadFn<.int.12>:GenRecordHead12" "RecordHrowFn<.int.12>:GenRecordHrow12" "SolveFn<.int.12>:GenSolve12"; do
+  pat=${spec%%:*}; name=${spec#*:}
+  TG_GS_B=16384 timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$pat" -s 2 -c 1 -o gpurun_out/${tag}_$name python tools/bench_general_shape.py > gpurun_out/${tag}_ncu_$name.log 2>&1
+done
 # gpurun brings back at most 64 MiB: keep the CSV pages of every report, drop the reports themselves
 for rep in gpurun_out/${tag}_*.ncu-rep; do
   ncu -i $rep --page raw --csv > ${rep%.ncu-rep}_raw.csv 2>/dev/null
