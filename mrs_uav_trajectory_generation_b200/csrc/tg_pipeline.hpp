@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -77,12 +78,24 @@ struct Result {
   long long total_solves, total_root_calls, total_evals;
 };
 
+// a typed view of host memory owned by the backend's page-locked arena
+template <class T>
+struct HostView {
+  T* p = nullptr;
+  size_t n = 0;
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+  T* data() { return p; }
+  size_t size() const { return n; }
+};
+
 // One processed group of problems whose outputs stay on the device until gathered.
 struct Group {
   int B = 0, totS = 0, totV = 0, totSlots = 0;
   std::vector<int> seg_off, smp_off;       // host copies
-  std::vector<ProbState> ps;               // host copy after find
+  HostView<ProbState> ps;                  // host copy after find (page-locked arena of the backend, valid until the next batch call)
   std::vector<int> orig;                   // original problem index of each member
+  std::vector<int> h_np, h_hbw;            // host copies of the unknown counts / half bandwidths (work accounting)
   // device (persistent arena)
   int* d_seg_off = nullptr;
   double* d_wp = nullptr;
@@ -162,7 +175,10 @@ class Pipeline {
     be_.d2h(stats, b.stats, sizeof(stats));
     const int ws = stats[0], ows = stats[2];
     alloc_solution_buffers(b, (size_t)(P.run_time_alloc ? totV : B), stats);
-    std::vector<int> h_np(B), h_hbw(B);
+    std::vector<int>& h_np = g.h_np;
+    std::vector<int>& h_hbw = g.h_hbw;
+    h_np.resize(B);
+    h_hbw.resize(B);
     be_.d2h(h_np.data(), b.np, sizeof(int) * B);
     be_.d2h(h_hbw.data(), b.hbw, sizeof(int) * B);
     const std::vector<SolveBucket> buckets = make_buckets(B, g.seg_off.data(), h_np.data(), h_hbw.data(), ws, ows, stats[3]);
@@ -205,15 +221,21 @@ class Pipeline {
       be_.for_each(B, ValidateFn{g.bp, g.d_smp_off, g.d_xyzh, g.d_seg_ok, P.max_deviation, P.first_segment_checked, P.check_deviation});
       launches(1);
     }
-    g.ps.resize(B);
-    be_.d2h(g.ps.data(), g.d_ps, sizeof(ProbState) * B);
+    g.ps = HostView<ProbState>{static_cast<ProbState*>(be_.pinned_alloc(sizeof(ProbState) * (size_t)B)), (size_t)B};
+    be_.d2h_pinned(g.ps.data(), g.d_ps, sizeof(ProbState) * B);
     trace_report(" find: solve .. state read", -1, tf0);
-    tf0 = trace_mark();
     if (P.run_time_alloc) {
       int executed = 0;
       be_.d2h(&executed, b.stats + 5, sizeof(int));
       counters.root_finds_executed += executed;
     }
+  }
+  // work accounting of one processed group (SURVEY.md 8(d) formulas x what was launched); pure host arithmetic over the per-problem
+  // state, deferred like fill_results
+  void account_group(const Group& g, const Params& P) {
+    const int B = g.B;
+    const std::vector<int>& h_np = g.h_np;
+    const std::vector<int>& h_hbw = g.h_hbw;
     for (int p = 0; p < B; ++p) {
       const int S = g.seg_off[p + 1] - g.seg_off[p];
       const int ev = g.ps[p].n_evals;
@@ -238,7 +260,6 @@ class Pipeline {
       counters.root_finds += (long long)(P.run_time_alloc ? (g.ps[p].n_scale_passes + 1) * 9 * S : 0);
       counters.samples += g.ps[p].n_samples;
     }
-    trace_report(" find: counters", -1, tf0);
   }
 
   // ---------------------------------------------------------------------------------------------------------------
@@ -308,6 +329,44 @@ class Pipeline {
     bool overflow = false;
   };
   EarlySamples early;
+  // host bookkeeping of a finished round that the device does not wait for (see optimize_batch)
+  std::function<void()> deferred_;
+  bool defer_bookkeeping = std::getenv("TG_DEFER") ? std::atoi(std::getenv("TG_DEFER")) != 0 : true;  // off only for A/B measurements
+  void run_deferred() {
+    if (!deferred_) return;
+    std::function<void()> f = std::move(deferred_);
+    deferred_ = nullptr;
+    f();
+  }
+  void fill_results(const Group& g, int gi, int round, bool last_round, const Params& P, Result* results) {
+    for (int m = 0; m < g.B; ++m) {
+      const int p = g.orig[m];
+      // from round 1 on the members are ordered by their new size, not by path: results[] is walked at random
+      if (m + 16 < g.B) __builtin_prefetch(&results[g.orig[m + 16]], 1);
+      const ProbState& ps = g.ps[m];
+      Result& R = results[p];
+      final_group_[p] = gi;
+      final_index_[p] = m;
+      const int S = g.seg_off[m + 1] - g.seg_off[m];
+      R.status = ps.status;
+      R.nlopt_code = ps.nlopt_code;
+      R.n_evals = ps.n_evals;
+      R.rounds = round;
+      R.n_waypoints = S + 1;
+      R.n_samples = ps.n_samples;
+      R.n_scale_passes = ps.n_scale_passes;
+      R.final_cost = P.run_time_alloc ? ps.final_cost : ps.cost;
+      R.baca_total = ps.baca_total;
+      R.total_evals += ps.n_evals;
+      R.total_solves += (long long)ps.n_evals * (S == 1 ? 1 : S + 2) + 1;  // reference count: S+2 solves per evaluation
+      R.total_root_calls += P.run_time_alloc ? (long long)ps.n_scale_passes * 18 * S : 0;
+      if (ps.status != kFindOk) { R.success = 0; continue; }
+      R.success = 1;
+      if (last_round) { R.safe = 0; continue; }  // returned without re-validation (node.cpp:729-785)
+      R.max_dev = ps.max_dev;
+      if (ps.next_V <= 0) R.safe = 1;
+    }
+  }
   void stream_finished_samples(Group& g, const std::vector<int>& finals) {
     if (!early.host || early.overflow || finals.empty()) return;
     std::vector<int> dst((size_t)g.B, -1);
@@ -341,11 +400,13 @@ class Pipeline {
     // launch per group over data that is being uploaded anyway); only a batch that has one pays for the host scan, which is what
     // tells the groups which paths to leave out (2.9 M isfinite tests per 65 536 paths: ~2 ms of every host-buffer call otherwise).
     std::vector<Group*> current;
+    deferred_ = nullptr;
     for (int attempt = 0;; ++attempt) {
       const bool host_scan = attempt > 0;
       persist_.reset();
       scratch_.reset();
       groups_.clear();
+      be_.pinned_reset();
       current.clear();
       final_group_.assign(B, -1);
       final_index_.assign(B, -1);
@@ -406,40 +467,27 @@ class Pipeline {
         find_group(*g, P, !last_round);
         trace_report("find_group", round, tm);
         tm = trace_mark();
-        const int gi = group_index(g);
+        // What the next round needs (which members go on) and which members are final: one light pass over the per-problem state.
+        // The result records and the work accounting -- ~1.5 ms of host stores per round that nothing on the device depends on -- are
+        // deferred: they run while the device works on the first evaluation of the next round (run_deferred in time_alloc_core).
         std::vector<int> finals;  // members whose result is final after this round
         if (early.host) finals.reserve((size_t)g->B);
         for (int m = 0; m < g->B; ++m) {
-          const int p = g->orig[m];
-          // from round 1 on the members are ordered by their new size, not by path: results[] is walked at random (the device waits)
-          if (m + 16 < g->B) __builtin_prefetch(&results[g->orig[m + 16]], 1);
           const ProbState& ps = g->ps[m];
-          Result& R = results[p];
-          if (early.host && !(ps.status == kFindOk && !last_round && ps.next_V > 0)) finals.push_back(m);
-          final_group_[p] = gi;
-          final_index_[p] = m;
-          const int S = g->seg_off[m + 1] - g->seg_off[m];
-          R.status = ps.status;
-          R.nlopt_code = ps.nlopt_code;
-          R.n_evals = ps.n_evals;
-          R.rounds = round;
-          R.n_waypoints = S + 1;
-          R.n_samples = ps.n_samples;
-          R.n_scale_passes = ps.n_scale_passes;
-          R.final_cost = P.run_time_alloc ? ps.final_cost : ps.cost;
-          R.baca_total = ps.baca_total;
-          R.total_evals += ps.n_evals;
-          R.total_solves += (long long)ps.n_evals * (S == 1 ? 1 : S + 2) + 1;  // reference count: S+2 solves per evaluation
-          R.total_root_calls += P.run_time_alloc ? (long long)ps.n_scale_passes * 18 * S : 0;
-          if (ps.status != kFindOk) { R.success = 0; continue; }
-          R.success = 1;
-          if (last_round) { R.safe = 0; continue; }  // returned without re-validation (node.cpp:729-785)
-          R.max_dev = ps.max_dev;
-          if (ps.next_V > 0) pending.emplace_back(g, m);
-          else R.safe = 1;
+          if (ps.status == kFindOk && !last_round && ps.next_V > 0) pending.emplace_back(g, m);
+          else if (early.host) finals.push_back(m);
         }
         stream_finished_samples(*g, finals);
-        trace_report("results + streamed samples", round, tm);
+        run_deferred();
+        {
+          const int gi = group_index(g);
+          deferred_ = [this, g, gi, round, last_round, results, &P]() {
+            fill_results(*g, gi, round, last_round, P, results);
+            account_group(*g, P);
+          };
+          if (!defer_bookkeeping) run_deferred();
+        }
+        trace_report("next-round scan + streamed samples", round, tm);
       }
       if (pending.empty()) break;
       const HostTrace tn = trace_mark();
@@ -510,6 +558,7 @@ class Pipeline {
       current.swap(next);
       trace_report("sort + next groups", round, tn);
     }
+    run_deferred();
     if (early.host) be_.copy_join();
   }
 
@@ -817,6 +866,7 @@ class Pipeline {
         launches(4);
       }
       counters.mellinger_launches += 1;
+      run_deferred();  // the previous round's result records: host stores while the device runs this evaluation
       int back[8];  // stats[7 .. 14]
       be_.d2h(back, b.stats + 7, sizeof(back));
       if (back[0] == 0) break;

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <thread>
 #include <limits>
@@ -37,6 +38,14 @@ struct EmuBackend {
   double wait_s = 0.0;  // CudaBackend's host-wait trace (TG_TRACE_HOST) has nothing to measure here
   const bool trace_host = false;
   void d2h_overlapped(void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
+  // CudaBackend's page-locked arena: plain heap blocks here, released at the next reset
+  std::vector<std::unique_ptr<char[]>> pinned_blocks;
+  void pinned_reset() { pinned_blocks.clear(); }
+  void* pinned_alloc(size_t bytes) {
+    pinned_blocks.emplace_back(new char[bytes ? bytes : 1]);
+    return pinned_blocks.back().get();
+  }
+  void d2h_pinned(void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
   void copy_join() {}
   void bind() {}
   void timer_start() {}
