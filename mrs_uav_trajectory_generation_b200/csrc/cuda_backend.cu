@@ -380,7 +380,10 @@ struct CudaBackend {
     if (scan_tmp) cudaFree(scan_tmp);
     if (h_stage) cudaFreeHost(h_stage);
     if (h_stage_big) cudaFreeHost(h_stage_big);
-    for (PinnedChunk& c : pinned_chunks) cudaFreeHost(c.p);
+    for (PinnedChunk& c : pinned_chunks) {
+      if (pinned_state) cudaFreeHost(c.p);
+      else delete[] c.p;
+    }
     if (solve_slab) cudaFree(solve_slab);
     if (thread_slab) cudaFree(thread_slab);
     if (gen_slab) cudaFree(gen_slab);
@@ -459,6 +462,7 @@ struct CudaBackend {
   struct PinnedChunk { char* p; size_t cap; };
   std::vector<PinnedChunk> pinned_chunks;
   size_t pinned_chunk = 0, pinned_used = 0;
+  const bool pinned_state = std::getenv("TG_PINNED_STATE") ? std::atoi(std::getenv("TG_PINNED_STATE")) != 0 : true;
   void pinned_reset() { pinned_chunk = 0; pinned_used = 0; }
   void* pinned_alloc(size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
@@ -476,11 +480,13 @@ struct CudaBackend {
       }
       PinnedChunk c;
       c.cap = std::max(bytes, (size_t)8 << 20);
-      TG_CUDA_CHECK(cudaHostAlloc((void**)&c.p, c.cap, cudaHostAllocDefault));
+      if (pinned_state) TG_CUDA_CHECK(cudaHostAlloc((void**)&c.p, c.cap, cudaHostAllocDefault));
+      else c.p = new char[c.cap];  // TG_PINNED_STATE=0 (A/B measurements): pageable memory, staged copies
       pinned_chunks.push_back(c);
     }
   }
   void d2h_pinned(void* d, const void* s, size_t n) {
+    if (!pinned_state) { d2h(d, s, n); return; }
     if (n) TG_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream));
     wait_stream();
   }
