@@ -112,7 +112,8 @@ inline std::string trajectoryToYaml(const Trajectory& trajectory) {
 }
 
 // segmentsFromYaml (io.cpp:72-112): false when a key is missing, a coefficient row is not a sequence, the number of rows is not
-// D or a row does not hold N numbers; N and D other than this build's (10, 4) are refused too (the classes are fixed-size here)
+// D or a row does not hold N numbers.  Segments of any N and D are read (what the device entry points then accept is their business:
+// N in {6, 8, 10, 12}, D in 1..4)
 inline bool segmentsFromYaml(const std::string& text, Segment::Vector* segments) {
   if (!segments) return false;
   segments->clear();
@@ -128,9 +129,9 @@ inline bool segmentsFromYaml(const std::string& text, Segment::Vector* segments)
   auto close = [&]() -> bool {
     if (!cur.open) return true;
     if (!(cur.n && cur.d && cur.t && cur.c)) return false;
-    if (cur.N != b200::kN || cur.D != b200::kD) return false;
+    if (cur.N < 1 || cur.D < 1) return false;
     if ((int)cur.rows.size() != cur.D) return false;
-    Segment s;
+    Segment s(cur.N, cur.D);  // any shape the document declares, as the reference reads it (Segment(N, D), io.cpp:85-88)
     for (int d = 0; d < cur.D; ++d) {
       if ((int)cur.rows[d].size() != cur.N) return false;
       for (int i = 0; i < cur.N; ++i) s.coefficients(d)[i] = cur.rows[d][i];

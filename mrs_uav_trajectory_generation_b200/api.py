@@ -114,8 +114,8 @@ class Trajectory:
         from . import segment_io
 
         r = segment_io.segments_from_yaml(text)
-        if r is None or r[0].shape[1:] != (D, N):
-            return None
+        if r is None or not (1 <= r[0].shape[1] <= D and r[0].shape[2] in (6, 8, 10, 12)):
+            return None  # shapes the device entry points take: N in {6, 8, 10, 12}, 1..4 dimensions
         return cls(r[0], r[1], ctx)
 
     def getSegmentTimes(self):

@@ -160,6 +160,10 @@ def check_api(ctx):
     assert np.array_equal(traj.evaluate(2.2, 1), orc.trajectory_evaluate(c_o, times, 2.2, 1)[0][:dims])
     full = A.sample_whole_trajectory(traj, 0.25, full=True)
     assert np.array_equal(full, orc.sample(c_o, times, 0.25))
+    # the segment YAML format carries the shape (eth/io.cpp:27-59): write, read back, same trajectory
+    back = A.Trajectory.fromYaml(traj.toYaml(), ctx=ctx)
+    assert back is not None and back.shape() == (dims, n_coef) and np.array_equal(back.coef, traj.coef)
+    assert np.array_equal(back.evaluate(1.1, 2), orc.trajectory_evaluate(c_o, np.floor(times * 1e9) * 1e-9, 1.1, 2)[0][:dims])
     opt4 = A.PolynomialOptimization(4, ctx=ctx, n_coefficients=8)
     assert opt4.setupFromVertices(verts, times, 2)
     with pytest.raises(ValueError):

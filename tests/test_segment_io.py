@@ -54,3 +54,4 @@ def test_cpp_header_reads_and_writes_the_same_documents(emu_lib, tmp_path):
     for t in t1:
         acc += t
     assert float(out[7]) == acc
+    assert out[9] == "1"  # an N = 6, D = 3 document: read, written back, evaluated through the general-shape entry point
