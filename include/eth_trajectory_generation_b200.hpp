@@ -647,8 +647,15 @@ class PolynomialOptimizationNonLinear {
   // nl_impl.h:51-82
   bool setupFromVertices(const Vertex::Vector& vertices, const std::vector<double>& segment_times, int derivative_to_optimize) {
     // the time allocation runs on the tuned kernels only: the node's shape (node.cpp:902, 907-921, 1063)
-    if (N != b200::kN || poly_opt_.getDimension() != (size_t)b200::kD || derivative_to_optimize < derivative_order::ACCELERATION) {
-      std::printf("[PolynomialOptimizationNonLinear]: the B200 time allocation is built for N = 10, 4 dimensions, derivative_to_optimize 2..4\n");
+    // the time allocation runs on the tuned kernels only: N = 10, derivative_to_optimize 2..4 (node.cpp:907-921, 1063).  Fewer than four
+    // dimensions are carried as zero dimensions by the Mellinger method (a zero polynomial adds exact zeros to the cost, to its
+    // gradient and to every squared magnitude); the derivative-free methods optimise D x n_free variables and need all four.
+    const size_t dims = poly_opt_.getDimension();
+    const bool mellinger = optimization_parameters_.time_alloc_method == NonlinearOptimizationParameters::kMellingerOuterLoop;
+    if (N != b200::kN || derivative_to_optimize < derivative_order::ACCELERATION || dims < 1 || dims > (size_t)b200::kD ||
+        (dims != (size_t)b200::kD && !mellinger)) {
+      std::printf("[PolynomialOptimizationNonLinear]: the B200 time allocation is built for N = 10, derivative_to_optimize 2..4, 4 dimensions "
+                  "(1..4 with kMellingerOuterLoop)\n");
       return false;
     }
     return poly_opt_.setupFromVertices(vertices, segment_times, derivative_to_optimize);
@@ -723,11 +730,27 @@ class PolynomialOptimizationNonLinear {
     int code = -1, evals = 0, passes = 0;
     double cost = 0.0;
     b200::Context& c = b200::Context::instance();
-    const int rc = tg_time_alloc_batch(c.get(), 1, vtx_off, poly_opt_.vertexMasks().data(), poly_opt_.vertexValues().data(), times.data(), &P,
-                                       coef.data(), &code, &evals, &passes, &cost);
+    const int dims = (int)poly_opt_.getDimension();
+    std::vector<double> vals4;  // [V][5][4]: the vertex values with the missing dimensions zero
+    const double* vals = poly_opt_.vertexValues().data();
+    if (dims != b200::kD) {
+      vals4.assign((size_t)V * b200::kHalf * b200::kD, 0.0);
+      for (size_t i = 0; i < (size_t)V * b200::kHalf; ++i)
+        for (int d = 0; d < dims; ++d) vals4[i * b200::kD + d] = vals[i * dims + d];
+      vals = vals4.data();
+    }
+    const int rc = tg_time_alloc_batch(c.get(), 1, vtx_off, poly_opt_.vertexMasks().data(), vals, times.data(), &P, coef.data(), &code, &evals,
+                                       &passes, &cost);
     if (rc != TG_OK) {
       std::printf("[PolynomialOptimizationNonLinear]: optimize failed: %s\n", tg_last_error(c.get()));
       return -1;  // nlopt::FAILURE
+    }
+    if (dims != b200::kD) {  // [S][4][10] -> [S][dims][10]
+      std::vector<double> cd((size_t)S * dims * b200::kN);
+      for (int i = 0; i < S; ++i)
+        for (int d = 0; d < dims; ++d)
+          for (int k = 0; k < b200::kN; ++k) cd[((size_t)i * dims + d) * b200::kN + k] = coef[((size_t)i * b200::kD + d) * b200::kN + k];
+      coef.swap(cd);
     }
     poly_opt_.adopt(times, coef, cost);
     optimization_info_.n_iterations = evals;

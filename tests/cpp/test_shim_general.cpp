@@ -111,6 +111,30 @@ int main(int argc, char** argv) {
     tt.push_back(within ? 1.0 : 0.0);
     dump(f, "n10d3_scaled_times", tt.data(), tt.size());
     dump(f, "n10d3_scaled_coef", coef.data(), coef.size());
+    // PolynomialOptimizationNonLinear<10> on three dimensions (Mellinger): optimize() + getTrajectory; a derivative-free method is refused
+    {
+      NonlinearOptimizationParameters prm;
+      prm.time_alloc_method = NonlinearOptimizationParameters::kMellingerOuterLoop;
+      PolynomialOptimizationNonLinear<10> nl(3, prm);
+      if (!nl.setupFromVertices(vertices, std::vector<double>(4, 0.7), derivative_order::ACCELERATION)) return 53;
+      nl.addMaximumMagnitudeConstraint(0, derivative_order::VELOCITY, 4.0);
+      nl.addMaximumMagnitudeConstraint(2, derivative_order::VELOCITY, 2.0);
+      nl.addMaximumMagnitudeConstraint(0, derivative_order::ACCELERATION, 2.0);
+      nl.addMaximumMagnitudeConstraint(2, derivative_order::ACCELERATION, 1.0);
+      const int code = nl.optimize();
+      Trajectory tn;
+      nl.getTrajectory(&tn);
+      if (tn.D() != 3 || tn.N() != 10) return 54;
+      std::vector<double> cn, ttn;
+      tn.pack(&cn, &ttn);
+      ttn.push_back((double)code);
+      dump(f, "nl3_times_code", ttn.data(), ttn.size());
+      dump(f, "nl3_coef", cn.data(), cn.size());
+      prm.time_alloc_method = NonlinearOptimizationParameters::kSquaredTime;
+      PolynomialOptimizationNonLinear<10> nl0(3, prm);
+      const double refused0 = nl0.setupFromVertices(vertices, std::vector<double>(4, 0.7), derivative_order::ACCELERATION) ? 0.0 : 1.0;
+      dump(f, "nl3_dfo_refused", &refused0, 1);
+    }
     // a shape outside the template's range of the B200 path is refused
     PolynomialOptimization<8> o8(5);
     const double refused = o8.setupFromVertices(vertices, std::vector<double>(4, 0.7), 2) ? 0.0 : 1.0;

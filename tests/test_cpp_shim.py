@@ -272,6 +272,13 @@ def _check_general(res):
     assert np.array_equal(res["n10d3_scaled_times"][0][:-1], t2) and res["n10d3_scaled_times"][0][-1] == float(within)
     assert np.array_equal(res["n10d3_scaled_coef"][0].reshape(-1, 3, 10), c2[:, :3])
     assert res["d5_refused"][0][0] == 1.0 and res["n8_scale_refused"][0][0] == 0.0
+    # PolynomialOptimizationNonLinear<10>(3), Mellinger: the four-dimensional run with a zero heading, limits as set in the C++ test
+    big = 3.40282346638528859812e+38
+    P = O.default_params(limits=(4.0, 2.0, 2.0, 1.0, big, big, big, big, big))
+    ref = O.time_alloc(mask, vals, times, 2, P)
+    assert np.array_equal(res["nl3_times_code"][0][:-1], ref["times"]) and int(res["nl3_times_code"][0][-1]) == ref["nlopt_code"]
+    assert np.array_equal(res["nl3_coef"][0].reshape(-1, 3, 10), ref["coef"][:, :3]) and np.all(ref["coef"][:, 3] == 0.0)
+    assert res["nl3_dfo_refused"][0][0] == 1.0
 
 
 def test_cpp_shim_general_shapes_on_host_emulation(oracle, emu_lib, tmp_path):
